@@ -1,0 +1,642 @@
+// HBM-bound kernels of the dual-encoder path: casts, patch im2col, token assembly, (residual-add +) LayerNorm
+// forward/backward, embedding gather/scatter, L2 normalise, column sums, fused AdamW.
+// All are coalesced 128-bit accesses, one warp per row for the row-wise ops, grids sized in multiples of the SM count
+// for the grid-stride ones.
+#include "common.cuh"
+#include "mmb200_internal.h"
+
+namespace mmb {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+static inline int grid_for(long long n_items, int per_block) {
+  long long b = (n_items + per_block - 1) / per_block;
+  long long cap = (long long)num_sms() * 16;
+  return (int)(b < cap ? (b < 1 ? 1 : b) : cap);
+}
+
+// ---------------------------------------------------------------------------------------------
+// fp32 -> bf16 cast (weights, once per optimizer step)
+// ---------------------------------------------------------------------------------------------
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n) {
+  const long long n4 = n >> 2;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(src) + i);
+    uint2 o;
+    o.x = pack_bf16x2(v.x, v.y);
+    o.y = pack_bf16x2(v.z, v.w);
+    reinterpret_cast<uint2*>(dst)[i] = o;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) dst[(n4 << 2) + threadIdx.x] = __float2bfloat16(src[(n4 << 2) + threadIdx.x]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Patch im2col + cast: image [B,3,H,W] fp32 -> patches [B*P, 3*ps*ps] bf16, K order (c, kh, kw) == the flattening
+// of conv.weight [width,3,ps,ps] (models/clip/image_encoder.py:50-56,91).  Patch index row-major (py, px)
+// == flatten(2) of the conv output (:94).  ps must be a multiple of 2.
+// ---------------------------------------------------------------------------------------------
+__global__ void im2col_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, int B, int H, int W,
+                              int ps) {
+  const int gp = W / ps, P = (H / ps) * gp, K = 3 * ps * ps;
+  const long long total2 = (long long)B * P * K / 2;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total2;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long e = i * 2;
+    const int k = (int)(e % K);
+    const long long row = e / K;
+    const int p = (int)(row % P);
+    const int b = (int)(row / P);
+    const int c = k / (ps * ps), r = k % (ps * ps), kh = r / ps, kw = r % ps;
+    const int py = p / gp, px = p % gp;
+    const float2 v = __ldg(reinterpret_cast<const float2*>(
+        img + (((long long)b * 3 + c) * H + (py * ps + kh)) * W + px * ps + kw));
+    reinterpret_cast<uint32_t*>(out)[i] = pack_bf16x2(v.x, v.y);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Row-wise LayerNorm machinery: one warp per row, row held in registers as float4 x NV (d = 128*NV, NV <= 8).
+// ---------------------------------------------------------------------------------------------
+constexpr int LN_MAX_NV = 8;
+
+struct LnRow {
+  float4 v[LN_MAX_NV];
+};
+
+__device__ __forceinline__ void ln_stats(const LnRow& r, int nv, int d, float eps, float& mean, float& rstd) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAX_NV; ++i)
+    if (i < nv) s += r.v[i].x + r.v[i].y + r.v[i].z + r.v[i].w;
+  mean = warp_sum(s) / d;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAX_NV; ++i)
+    if (i < nv) {
+      const float a = r.v[i].x - mean, b = r.v[i].y - mean, c = r.v[i].z - mean, e = r.v[i].w - mean;
+      q += a * a + b * b + c * c + e * e;
+    }
+  rstd = rsqrtf(warp_sum(q) / d + eps);
+}
+
+// x_out = x_in (+ y);  ln_out = LN(x_out) * gamma + beta   (fp32 statistics, eps inside the sqrt)
+//   x_in : fp32 [M,d] or nullptr;  y : bf16 [M,d] or nullptr;  x_out : fp32 [M,d] or nullptr (may alias x_in)
+//   ln_bf16 : bf16 [M,d] or nullptr; ln_f32 : fp32 [M,d] or nullptr; mean/rstd : fp32 [M] or nullptr
+//   row_idx : optional gather: logical row m reads physical row (m*rows_per_group + row_idx[m]) (row_idx null -> +0)
+// Replaces F.layer_norm + residual add (torch/nn/modules/transformer.py:946-951) and Fp32LayerNorm
+// (torchmultimodal/modules/layers/normalizations.py:17-25).
+__global__ void add_ln_fwd_kernel(const float* __restrict__ x_in, const __nv_bfloat16* __restrict__ y,
+                                  float* __restrict__ x_out, __nv_bfloat16* __restrict__ ln_bf16,
+                                  float* __restrict__ ln_f32, const float* __restrict__ gamma,
+                                  const float* __restrict__ beta, float* __restrict__ mean_out,
+                                  float* __restrict__ rstd_out, const int* __restrict__ row_idx, int rows_per_group,
+                                  int M, int d, float eps) {
+  const int nv = d >> 7;
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (int m = blockIdx.x * wpb + (threadIdx.x >> 5); m < M; m += gridDim.x * wpb) {
+    long long src = m;
+    if (rows_per_group > 0) src = (long long)m * rows_per_group + (row_idx ? row_idx[m] : 0);
+    LnRow r;
+#pragma unroll
+    for (int i = 0; i < LN_MAX_NV; ++i)
+      if (i < nv) {
+        const int c = (i * 32 + lane) * 4;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (x_in) a = *reinterpret_cast<const float4*>(x_in + src * d + c);
+        if (y) {
+          const uint2 u = *reinterpret_cast<const uint2*>(y + src * d + c);
+          a.x += bf16_lo(u.x); a.y += bf16_hi(u.x); a.z += bf16_lo(u.y); a.w += bf16_hi(u.y);
+        }
+        r.v[i] = a;
+        if (x_out) *reinterpret_cast<float4*>(x_out + src * d + c) = a;
+      }
+    float mean, rstd;
+    ln_stats(r, nv, d, eps, mean, rstd);
+    if (lane == 0) {
+      if (mean_out) mean_out[m] = mean;
+      if (rstd_out) rstd_out[m] = rstd;
+    }
+#pragma unroll
+    for (int i = 0; i < LN_MAX_NV; ++i)
+      if (i < nv) {
+        const int c = (i * 32 + lane) * 4;
+        const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(beta + c));
+        float4 o;
+        o.x = (r.v[i].x - mean) * rstd * g.x + b.x;
+        o.y = (r.v[i].y - mean) * rstd * g.y + b.y;
+        o.z = (r.v[i].z - mean) * rstd * g.z + b.z;
+        o.w = (r.v[i].w - mean) * rstd * g.w + b.w;
+        if (ln_bf16) {
+          uint2 u;
+          u.x = pack_bf16x2(o.x, o.y);
+          u.y = pack_bf16x2(o.z, o.w);
+          *reinterpret_cast<uint2*>(ln_bf16 + (long long)m * d + c) = u;
+        }
+        if (ln_f32) *reinterpret_cast<float4*>(ln_f32 + (long long)m * d + c) = o;
+      }
+  }
+}
+
+// CLIP ViT token assembly + ln_pre (models/clip/image_encoder.py:94-106):
+//   t[b,0,:] = cls + pos[0];  t[b,1+p,:] = patch_out[b*P+p,:] + pos[1+p];  x0 = Fp32LayerNorm(t)
+// patch_out is the bf16 output of the patch-embedding GEMM.  Saves mean/rstd of t for the backward.
+__global__ void vit_embed_ln_fwd_kernel(const __nv_bfloat16* __restrict__ patch_out, const float* __restrict__ cls,
+                                        const float* __restrict__ pos, const float* __restrict__ gamma,
+                                        const float* __restrict__ beta, float* __restrict__ x0,
+                                        float* __restrict__ mean_out, float* __restrict__ rstd_out, int B, int S,
+                                        int d, float eps) {
+  const int nv = d >> 7;
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const int M = B * S;
+  for (int m = blockIdx.x * wpb + (threadIdx.x >> 5); m < M; m += gridDim.x * wpb) {
+    const int b = m / S, s = m - b * S;
+    LnRow r;
+#pragma unroll
+    for (int i = 0; i < LN_MAX_NV; ++i)
+      if (i < nv) {
+        const int c = (i * 32 + lane) * 4;
+        float4 a = __ldg(reinterpret_cast<const float4*>(pos + (long long)s * d + c));
+        if (s == 0) {
+          const float4 t = __ldg(reinterpret_cast<const float4*>(cls + c));
+          a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
+        } else {
+          const uint2 u = *reinterpret_cast<const uint2*>(patch_out + ((long long)b * (S - 1) + (s - 1)) * d + c);
+          a.x += bf16_lo(u.x); a.y += bf16_hi(u.x); a.z += bf16_lo(u.y); a.w += bf16_hi(u.y);
+        }
+        r.v[i] = a;
+      }
+    float mean, rstd;
+    ln_stats(r, nv, d, eps, mean, rstd);
+    if (lane == 0) { mean_out[m] = mean; rstd_out[m] = rstd; }
+#pragma unroll
+    for (int i = 0; i < LN_MAX_NV; ++i)
+      if (i < nv) {
+        const int c = (i * 32 + lane) * 4;
+        const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
+        const float4 bb = __ldg(reinterpret_cast<const float4*>(beta + c));
+        float4 o;
+        o.x = (r.v[i].x - mean) * rstd * g.x + bb.x;
+        o.y = (r.v[i].y - mean) * rstd * g.y + bb.y;
+        o.z = (r.v[i].z - mean) * rstd * g.z + bb.z;
+        o.w = (r.v[i].w - mean) * rstd * g.w + bb.w;
+        *reinterpret_cast<float4*>(x0 + (long long)m * d + c) = o;
+      }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// LayerNorm backward (+ residual-gradient add).  For each row:
+//   xhat = (x - mean) * rstd;  dyg = dy * gamma
+//   dx   = rstd * (dyg - mean_d(dyg) - xhat * mean_d(dyg * xhat))
+//   g_out = (g_in ? g_in : 0) + dx         (fp32 [M,d], may alias g_in)     and/or  g_bf16 = bf16(g_out)
+//   dgamma += sum_rows dy * xhat ; dbeta += sum_rows dy      (fp32 atomics, one per column per block)
+// Input modes for x:  MODE_X      : x fp32 [M,d]
+//                     MODE_VIT    : x is re-assembled from patch_out/cls/pos (token assembly, see above)
+// dy is bf16 [M,d] (dy_bf16) or fp32 [M,d] (dy_f32).  Row scatter: with row_idx/rows_per_group the logical row m
+// reads x and writes g at physical row m*rows_per_group + row_idx[m].
+// ---------------------------------------------------------------------------------------------
+struct LnBwdArgs {
+  const float* x; const __nv_bfloat16* patch_out; const float* cls; const float* pos; int S;  // x sources
+  const __nv_bfloat16* dy_bf16; const float* dy_f32;
+  const float* mean; const float* rstd; const float* gamma;
+  const float* g_in; float* g_out; __nv_bfloat16* g_bf16;
+  float* dgamma; float* dbeta;
+  const int* row_idx; int rows_per_group;
+  int M, d;
+};
+
+template <bool VIT>
+__global__ void ln_bwd_kernel(const LnBwdArgs a) {
+  extern __shared__ float sred[];  // [2][d]
+  const int d = a.d, nv = d >> 7;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int wpb = blockDim.x >> 5;
+  for (int i = threadIdx.x; i < 2 * d; i += blockDim.x) sred[i] = 0.f;
+  __syncthreads();
+  float4 accg[LN_MAX_NV], accb[LN_MAX_NV];
+#pragma unroll
+  for (int i = 0; i < LN_MAX_NV; ++i) { accg[i] = make_float4(0.f, 0.f, 0.f, 0.f); accb[i] = accg[i]; }
+
+  for (int m = blockIdx.x * wpb + wib; m < a.M; m += gridDim.x * wpb) {
+    long long phys = m;
+    if (a.rows_per_group > 0) phys = (long long)m * a.rows_per_group + (a.row_idx ? a.row_idx[m] : 0);
+    const float mean = a.mean[m], rstd = a.rstd[m];
+    float4 xh[LN_MAX_NV], dy[LN_MAX_NV];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAX_NV; ++i)
+      if (i < nv) {
+        const int c = (i * 32 + lane) * 4;
+        float4 x;
+        if (VIT) {
+          const int b = m / a.S, s = m - b * a.S;
+          x = __ldg(reinterpret_cast<const float4*>(a.pos + (long long)s * d + c));
+          if (s == 0) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(a.cls + c));
+            x.x += t.x; x.y += t.y; x.z += t.z; x.w += t.w;
+          } else {
+            const uint2 u = *reinterpret_cast<const uint2*>(a.patch_out + ((long long)b * (a.S - 1) + (s - 1)) * d + c);
+            x.x += bf16_lo(u.x); x.y += bf16_hi(u.x); x.z += bf16_lo(u.y); x.w += bf16_hi(u.y);
+          }
+        } else {
+          x = *reinterpret_cast<const float4*>(a.x + phys * d + c);
+        }
+        float4 g4;
+        if (a.dy_bf16) {
+          const uint2 u = *reinterpret_cast<const uint2*>(a.dy_bf16 + (long long)m * d + c);
+          g4 = make_float4(bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y));
+        } else {
+          g4 = *reinterpret_cast<const float4*>(a.dy_f32 + (long long)m * d + c);
+        }
+        const float4 gm = __ldg(reinterpret_cast<const float4*>(a.gamma + c));
+        float4 h;
+        h.x = (x.x - mean) * rstd; h.y = (x.y - mean) * rstd; h.z = (x.z - mean) * rstd; h.w = (x.w - mean) * rstd;
+        accg[i].x += g4.x * h.x; accg[i].y += g4.y * h.y; accg[i].z += g4.z * h.z; accg[i].w += g4.w * h.w;
+        accb[i].x += g4.x; accb[i].y += g4.y; accb[i].z += g4.z; accb[i].w += g4.w;
+        g4.x *= gm.x; g4.y *= gm.y; g4.z *= gm.z; g4.w *= gm.w;  // dy * gamma
+        s1 += g4.x + g4.y + g4.z + g4.w;
+        s2 += g4.x * h.x + g4.y * h.y + g4.z * h.z + g4.w * h.w;
+        xh[i] = h; dy[i] = g4;
+      }
+    s1 = warp_sum(s1) / d;
+    s2 = warp_sum(s2) / d;
+#pragma unroll
+    for (int i = 0; i < LN_MAX_NV; ++i)
+      if (i < nv) {
+        const int c = (i * 32 + lane) * 4;
+        float4 o;
+        o.x = rstd * (dy[i].x - s1 - xh[i].x * s2);
+        o.y = rstd * (dy[i].y - s1 - xh[i].y * s2);
+        o.z = rstd * (dy[i].z - s1 - xh[i].z * s2);
+        o.w = rstd * (dy[i].w - s1 - xh[i].w * s2);
+        if (a.g_in) {
+          const float4 gi = *reinterpret_cast<const float4*>(a.g_in + phys * d + c);
+          o.x += gi.x; o.y += gi.y; o.z += gi.z; o.w += gi.w;
+        }
+        if (a.g_out) *reinterpret_cast<float4*>(a.g_out + phys * d + c) = o;
+        if (a.g_bf16) {
+          uint2 u;
+          u.x = pack_bf16x2(o.x, o.y);
+          u.y = pack_bf16x2(o.z, o.w);
+          *reinterpret_cast<uint2*>(a.g_bf16 + phys * d + c) = u;
+        }
+      }
+  }
+  // block reduction of dgamma / dbeta partials, then one atomic per column per block
+#pragma unroll
+  for (int i = 0; i < LN_MAX_NV; ++i)
+    if (i < nv) {
+      const int c = (i * 32 + lane) * 4;
+      atomicAdd(&sred[c + 0], accg[i].x); atomicAdd(&sred[c + 1], accg[i].y);
+      atomicAdd(&sred[c + 2], accg[i].z); atomicAdd(&sred[c + 3], accg[i].w);
+      atomicAdd(&sred[d + c + 0], accb[i].x); atomicAdd(&sred[d + c + 1], accb[i].y);
+      atomicAdd(&sred[d + c + 2], accb[i].z); atomicAdd(&sred[d + c + 3], accb[i].w);
+    }
+  __syncthreads();
+  for (int i = threadIdx.x; i < d; i += blockDim.x) {
+    if (a.dgamma) atomicAdd(a.dgamma + i, sred[i]);
+    if (a.dbeta) atomicAdd(a.dbeta + i, sred[d + i]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// out[j] += sum_b in[b, j]   (positional-embedding / cls-token gradients: sum over the batch)
+//   in fp32 [Bn, n] with row stride ld; columns [0,n) ; optional row subset via (row0, row_step)
+// ---------------------------------------------------------------------------------------------
+__global__ void batch_sum_kernel(const float* __restrict__ in, float* __restrict__ out, int Bn, long long ld, int n,
+                                 int b_chunk) {
+  const int j = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (j >= n) return;
+  const int b0 = blockIdx.y * b_chunk, b1 = min(b0 + b_chunk, Bn);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int b = b0; b < b1; ++b) {
+    const float4 v = *reinterpret_cast<const float4*>(in + (long long)b * ld + j);
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  atomicAdd(out + j, acc.x); atomicAdd(out + j + 1, acc.y); atomicAdd(out + j + 2, acc.z); atomicAdd(out + j + 3, acc.w);
+}
+
+// ---------------------------------------------------------------------------------------------
+// out[n] += sum_m x[m, n]   (bias gradients), x bf16 [M, N] row-major with leading dim ld
+// ---------------------------------------------------------------------------------------------
+__global__ void colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, int M, int N,
+                                   long long ld, int rows_per_block) {
+  // block = 256 threads: 32 column-octets (256 columns) x 8 row lanes
+  const int co = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int n = (blockIdx.x * 32 + co) * 8;
+  const int m0 = blockIdx.y * rows_per_block, m1 = min(m0 + rows_per_block, M);
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (n < N) {
+    for (int m = m0 + rl; m < m1; m += 8) {
+      const uint4 u = *reinterpret_cast<const uint4*>(x + (long long)m * ld + n);
+      acc[0] += bf16_lo(u.x); acc[1] += bf16_hi(u.x); acc[2] += bf16_lo(u.y); acc[3] += bf16_hi(u.y);
+      acc[4] += bf16_lo(u.z); acc[5] += bf16_hi(u.z); acc[6] += bf16_lo(u.w); acc[7] += bf16_hi(u.w);
+    }
+  }
+  __shared__ float s[8][32][9];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) s[rl][co][e] = acc[e];
+  __syncthreads();
+  if (rl == 0 && n < N) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float t = 0.f;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) t += s[r][co][e];
+      atomicAdd(out + n + e, t);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Text embedding: x[b,s,:] = emb[token[b,s],:] + pos[s,:]   (models/clip/text_encoder.py:118-119)
+// Token ids are int64 (bit-exact gather); ids outside [0,V) trap (torch raises an index error).
+// ---------------------------------------------------------------------------------------------
+__global__ void text_embed_fwd_kernel(const long long* __restrict__ tokens, const float* __restrict__ emb,
+                                      const float* __restrict__ pos, float* __restrict__ x, int B, int S, int d,
+                                      int V) {
+  const int d4 = d >> 2;
+  const long long total = (long long)B * S * d4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % d4);
+    const long long row = i / d4;
+    const int s = (int)(row % S);
+    const long long tok = tokens[row];
+    if (tok < 0 || tok >= V) __trap();
+    const float4 e = __ldg(reinterpret_cast<const float4*>(emb + tok * d) + c);
+    const float4 p = __ldg(reinterpret_cast<const float4*>(pos + (long long)s * d) + c);
+    reinterpret_cast<float4*>(x)[i] = make_float4(e.x + p.x, e.y + p.y, e.z + p.z, e.w + p.w);
+  }
+}
+// demb[token[b,s],:] += g[b,s,:]  (fp32 atomics; dpos is produced by batch_sum)
+__global__ void text_embed_bwd_kernel(const long long* __restrict__ tokens, const float* __restrict__ g,
+                                      float* __restrict__ demb, int B, int S, int d) {
+  const int d4 = d >> 2;
+  const long long total = (long long)B * S * d4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % d4);
+    const long long row = i / d4;
+    const long long tok = tokens[row];
+    const float4 v = reinterpret_cast<const float4*>(g)[i];
+    float* dst = demb + tok * d + c * 4;
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+  }
+}
+// idx[b] = argmax_s tokens[b,s] (first maximum, like torch.argmax)  (models/clip/text_encoder.py:130-132)
+__global__ void argmax_tokens_kernel(const long long* __restrict__ tokens, int* __restrict__ idx, int B, int S) {
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (b >= B) return;
+  long long best = LLONG_MIN;
+  int bi = 0x7fffffff;
+  for (int s = lane; s < S; s += 32) {
+    const long long t = tokens[(long long)b * S + s];
+    if (t > best) { best = t; bi = s; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const long long ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+  }
+  if (lane == 0) idx[b] = bi;
+}
+
+// ---------------------------------------------------------------------------------------------
+// L2 normalise rows (F.normalize, models/clip/model.py:72-73): y = x / max(||x||, eps)
+// ---------------------------------------------------------------------------------------------
+__global__ void l2norm_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, __nv_bfloat16* __restrict__ y_bf16,
+                                  float* __restrict__ inv_norm, int B, int E, float eps) {
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (b >= B) return;
+  float s = 0.f;
+  for (int c = lane * 4; c < E; c += 128) {
+    const float4 v = *reinterpret_cast<const float4*>(x + (long long)b * E + c);
+    s += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  s = warp_sum(s);
+  const float inv = 1.f / fmaxf(sqrtf(s), eps);
+  if (lane == 0 && inv_norm) inv_norm[b] = inv;
+  for (int c = lane * 4; c < E; c += 128) {
+    const float4 v = *reinterpret_cast<const float4*>(x + (long long)b * E + c);
+    const float4 o = make_float4(v.x * inv, v.y * inv, v.z * inv, v.w * inv);
+    if (y) *reinterpret_cast<float4*>(y + (long long)b * E + c) = o;
+    if (y_bf16) {
+      uint2 u;
+      u.x = pack_bf16x2(o.x, o.y);
+      u.y = pack_bf16x2(o.z, o.w);
+      *reinterpret_cast<uint2*>(y_bf16 + (long long)b * E + c) = u;
+    }
+  }
+}
+// dx = (dy - y * <y, dy>) * inv_norm     (valid when ||x|| > eps, which holds for any non-degenerate embedding)
+__global__ void l2norm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y,
+                                  const float* __restrict__ inv_norm, float* __restrict__ dx,
+                                  __nv_bfloat16* __restrict__ dx_bf16, int B, int E) {
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (b >= B) return;
+  float s = 0.f;
+  for (int c = lane * 4; c < E; c += 128) {
+    const float4 a = *reinterpret_cast<const float4*>(dy + (long long)b * E + c);
+    const float4 v = *reinterpret_cast<const float4*>(y + (long long)b * E + c);
+    s += a.x * v.x + a.y * v.y + a.z * v.z + a.w * v.w;
+  }
+  s = warp_sum(s);
+  const float inv = inv_norm[b];
+  for (int c = lane * 4; c < E; c += 128) {
+    const float4 a = *reinterpret_cast<const float4*>(dy + (long long)b * E + c);
+    const float4 v = *reinterpret_cast<const float4*>(y + (long long)b * E + c);
+    const float4 o = make_float4((a.x - v.x * s) * inv, (a.y - v.y * s) * inv, (a.z - v.z * s) * inv, (a.w - v.w * s) * inv);
+    if (dx) *reinterpret_cast<float4*>(dx + (long long)b * E + c) = o;
+    if (dx_bf16) {
+      uint2 u;
+      u.x = pack_bf16x2(o.x, o.y);
+      u.y = pack_bf16x2(o.z, o.w);
+      *reinterpret_cast<uint2*>(dx_bf16 + (long long)b * E + c) = u;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused AdamW over a flat parameter buffer (torch.optim.AdamW semantics, decoupled weight decay); also emits the
+// bf16 copy of the updated weights that the next step's GEMMs read, and zeroes the gradient.
+// ---------------------------------------------------------------------------------------------
+__global__ void adamw_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                             __nv_bfloat16* __restrict__ p_bf16, long long n, float lr, float beta1, float beta2,
+                             float eps, float wd, float bc1, float bc2, float grad_scale, int zero_grad) {
+  const long long n4 = n >> 2;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 P = reinterpret_cast<float4*>(p)[i];
+    float4 G = reinterpret_cast<float4*>(g)[i];
+    float4 Mv = reinterpret_cast<float4*>(m)[i];
+    float4 V = reinterpret_cast<float4*>(v)[i];
+    float* pp = &P.x; float* gg = &G.x; float* mm = &Mv.x; float* vv = &V.x;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float gr = gg[e] * grad_scale;
+      pp[e] *= (1.f - lr * wd);
+      mm[e] = beta1 * mm[e] + (1.f - beta1) * gr;
+      vv[e] = beta2 * vv[e] + (1.f - beta2) * gr * gr;
+      const float denom = sqrtf(vv[e]) / sqrtf(bc2) + eps;
+      pp[e] -= (lr / bc1) * (mm[e] / denom);
+    }
+    reinterpret_cast<float4*>(p)[i] = P;
+    reinterpret_cast<float4*>(m)[i] = Mv;
+    reinterpret_cast<float4*>(v)[i] = V;
+    if (zero_grad) reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p_bf16) {
+      uint2 u;
+      u.x = pack_bf16x2(P.x, P.y);
+      u.y = pack_bf16x2(P.z, P.w);
+      reinterpret_cast<uint2*>(p_bf16)[i] = u;
+    }
+  }
+}
+
+}  // namespace mmb
+
+using namespace mmb;
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+#define LAUNCH_RC() ((int)cudaGetLastError())
+
+extern "C" int mmb_cast_f32_to_bf16(const float* src, void* dst, long long n, void* stream) {
+  if (n <= 0) return MMB_OK;
+  if ((reinterpret_cast<uintptr_t>(src) & 15) || (reinterpret_cast<uintptr_t>(dst) & 7)) return MMB_ERR_ARG;
+  cast_f32_bf16_kernel<<<grid_for(n / 4 + 1, 256), 256, 0, ST(stream)>>>(src, (__nv_bfloat16*)dst, n);
+  return LAUNCH_RC();
+}
+
+extern "C" int mmb_im2col_patches(const float* img, void* out, int B, int H, int W, int ps, void* stream) {
+  if (B <= 0 || ps <= 0 || (ps & 1) || H % ps || W % ps) return MMB_ERR_ARG;
+  const long long total2 = (long long)B * (H / ps) * (W / ps) * 3 * ps * ps / 2;
+  im2col_kernel<<<grid_for(total2, 256), 256, 0, ST(stream)>>>(img, (__nv_bfloat16*)out, B, H, W, ps);
+  return LAUNCH_RC();
+}
+
+static inline bool ln_dim_ok(int d) { return d > 0 && (d & 127) == 0 && (d >> 7) <= LN_MAX_NV; }
+
+extern "C" int mmb_add_layernorm_fwd(const float* x_in, const void* y_bf16, float* x_out, void* ln_bf16, float* ln_f32,
+                                     const float* gamma, const float* beta, float* mean, float* rstd,
+                                     const int* row_idx, int rows_per_group, int M, int d, float eps, void* stream) {
+  if (!ln_dim_ok(d)) return MMB_ERR_UNSUPPORTED;
+  if (M <= 0) return MMB_OK;
+  add_ln_fwd_kernel<<<grid_for(M, 8), 256, 0, ST(stream)>>>(x_in, (const __nv_bfloat16*)y_bf16, x_out,
+                                                             (__nv_bfloat16*)ln_bf16, ln_f32, gamma, beta, mean, rstd,
+                                                             row_idx, rows_per_group, M, d, eps);
+  return LAUNCH_RC();
+}
+
+extern "C" int mmb_vit_embed_ln_fwd(const void* patch_out, const float* cls, const float* pos, const float* gamma,
+                                    const float* beta, float* x0, float* mean, float* rstd, int B, int S, int d,
+                                    float eps, void* stream) {
+  if (!ln_dim_ok(d)) return MMB_ERR_UNSUPPORTED;
+  vit_embed_ln_fwd_kernel<<<grid_for((long long)B * S, 8), 256, 0, ST(stream)>>>(
+      (const __nv_bfloat16*)patch_out, cls, pos, gamma, beta, x0, mean, rstd, B, S, d, eps);
+  return LAUNCH_RC();
+}
+
+extern "C" int mmb_layernorm_bwd(const float* x, const void* dy_bf16, const float* dy_f32, const float* mean,
+                                 const float* rstd, const float* gamma, const float* g_in, float* g_out, void* g_bf16,
+                                 float* dgamma, float* dbeta, const int* row_idx, int rows_per_group, int M, int d,
+                                 void* stream) {
+  if (!ln_dim_ok(d)) return MMB_ERR_UNSUPPORTED;
+  if (M <= 0) return MMB_OK;
+  LnBwdArgs a{};
+  a.x = x; a.dy_bf16 = (const __nv_bfloat16*)dy_bf16; a.dy_f32 = dy_f32; a.mean = mean; a.rstd = rstd; a.gamma = gamma;
+  a.g_in = g_in; a.g_out = g_out; a.g_bf16 = (__nv_bfloat16*)g_bf16; a.dgamma = dgamma; a.dbeta = dbeta;
+  a.row_idx = row_idx; a.rows_per_group = rows_per_group; a.M = M; a.d = d;
+  int grid = num_sms() * 4;
+  if (grid > (M + 7) / 8) grid = (M + 7) / 8;
+  ln_bwd_kernel<false><<<grid, 256, 2 * d * sizeof(float), ST(stream)>>>(a);
+  return LAUNCH_RC();
+}
+
+extern "C" int mmb_vit_embed_ln_bwd(const void* patch_out, const float* cls, const float* pos, const float* dy_f32,
+                                    const float* mean, const float* rstd, const float* gamma, float* dt_f32,
+                                    float* dgamma, float* dbeta, int B, int S, int d, void* stream) {
+  if (!ln_dim_ok(d)) return MMB_ERR_UNSUPPORTED;
+  LnBwdArgs a{};
+  a.patch_out = (const __nv_bfloat16*)patch_out; a.cls = cls; a.pos = pos; a.S = S;
+  a.dy_f32 = dy_f32; a.mean = mean; a.rstd = rstd; a.gamma = gamma; a.g_out = dt_f32;
+  a.dgamma = dgamma; a.dbeta = dbeta; a.M = B * S; a.d = d;
+  int grid = num_sms() * 4;
+  if (grid > (a.M + 7) / 8) grid = (a.M + 7) / 8;
+  ln_bwd_kernel<true><<<grid, 256, 2 * d * sizeof(float), ST(stream)>>>(a);
+  return LAUNCH_RC();
+}
+
+extern "C" int mmb_batch_sum(const float* in, float* out, int Bn, long long ld, int n, void* stream) {
+  if (n & 3) return MMB_ERR_ARG;
+  const int bx = (n / 4 + 127) / 128;
+  int chunks = (num_sms() * 4 + bx - 1) / bx;
+  if (chunks > Bn) chunks = Bn;
+  if (chunks < 1) chunks = 1;
+  const int b_chunk = (Bn + chunks - 1) / chunks;
+  dim3 grid(bx, (Bn + b_chunk - 1) / b_chunk);
+  batch_sum_kernel<<<grid, 128, 0, ST(stream)>>>(in, out, Bn, ld, n, b_chunk);
+  return LAUNCH_RC();
+}
+
+extern "C" int mmb_colsum_bf16(const void* x, float* out, int M, int N, long long ld, void* stream) {
+  if ((N & 7) || (ld & 7)) return MMB_ERR_ARG;
+  const int bx = (N + 255) / 256;
+  int chunks = (num_sms() * 8 + bx - 1) / bx;
+  int rows_per_block = (M + chunks - 1) / chunks;
+  rows_per_block = ((rows_per_block + 7) / 8) * 8;
+  dim3 grid(bx, (M + rows_per_block - 1) / rows_per_block);
+  colsum_bf16_kernel<<<grid, 256, 0, ST(stream)>>>((const __nv_bfloat16*)x, out, M, N, ld, rows_per_block);
+  return LAUNCH_RC();
+}
+
+extern "C" int mmb_text_embed_fwd(const long long* tokens, const float* emb, const float* pos, float* x, int B, int S,
+                                  int d, int V, void* stream) {
+  if (d & 3) return MMB_ERR_ARG;
+  text_embed_fwd_kernel<<<grid_for((long long)B * S * d / 4, 256), 256, 0, ST(stream)>>>(tokens, emb, pos, x, B, S, d, V);
+  return LAUNCH_RC();
+}
+extern "C" int mmb_text_embed_bwd(const long long* tokens, const float* g, float* demb, int B, int S, int d,
+                                  void* stream) {
+  if (d & 3) return MMB_ERR_ARG;
+  text_embed_bwd_kernel<<<grid_for((long long)B * S * d / 4, 256), 256, 0, ST(stream)>>>(tokens, g, demb, B, S, d);
+  return LAUNCH_RC();
+}
+extern "C" int mmb_argmax_tokens(const long long* tokens, int* idx, int B, int S, void* stream) {
+  argmax_tokens_kernel<<<(B + 7) / 8, 256, 0, ST(stream)>>>(tokens, idx, B, S);
+  return LAUNCH_RC();
+}
+extern "C" int mmb_l2norm_fwd(const float* x, float* y, void* y_bf16, float* inv_norm, int B, int E, float eps,
+                              void* stream) {
+  if (E & 3) return MMB_ERR_ARG;
+  l2norm_fwd_kernel<<<(B + 7) / 8, 256, 0, ST(stream)>>>(x, y, (__nv_bfloat16*)y_bf16, inv_norm, B, E, eps);
+  return LAUNCH_RC();
+}
+extern "C" int mmb_l2norm_bwd(const float* dy, const float* y, const float* inv_norm, float* dx, void* dx_bf16, int B,
+                              int E, void* stream) {
+  if (E & 3) return MMB_ERR_ARG;
+  l2norm_bwd_kernel<<<(B + 7) / 8, 256, 0, ST(stream)>>>(dy, y, inv_norm, dx, (__nv_bfloat16*)dx_bf16, B, E);
+  return LAUNCH_RC();
+}
+extern "C" int mmb_adamw_step(float* p, float* g, float* m, float* v, void* p_bf16, long long n, float lr, float beta1,
+                              float beta2, float eps, float weight_decay, int step, float grad_scale, int zero_grad,
+                              void* stream) {
+  if (n & 3) return MMB_ERR_ARG;
+  const float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
+  adamw_kernel<<<grid_for(n / 4, 256), 256, 0, ST(stream)>>>(p, g, m, v, (__nv_bfloat16*)p_bf16, n, lr, beta1, beta2,
+                                                              eps, weight_decay, bc1, bc2, grad_scale, zero_grad);
+  return LAUNCH_RC();
+}
+extern "C" int mmb_memset_async(void* p, int value, long long bytes, void* stream) {
+  return (int)cudaMemsetAsync(p, value, (size_t)bytes, ST(stream));
+}

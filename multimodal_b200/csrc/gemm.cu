@@ -1,0 +1,461 @@
+// Persistent warp-specialised bf16 GEMM for sm_100a: TMA -> smem ring -> tcgen05.mma (TMEM accumulators)
+// -> epilogue warps (tcgen05.ld -> registers -> swizzled smem slab -> TMA store / TMA reduce-add).
+//
+// One kernel covers every dense contraction on the dual-encoder path:
+//   forward linears   y = x W^T      A K-major [M,K],  B K-major [N,K]      (torch/nn/functional.py:6478,6690;
+//                                                                            torch/nn/modules/transformer.py:980-982)
+//   dgrad             dx = dy W      A K-major [M,N'], B MN-major [N',K']
+//   wgrad             dW = dy^T x    A MN-major [tokens,N'], B MN-major [tokens,K']   (split-K, fp32 reduce-add)
+//   logits            a b^T * T      (modules/losses/contrastive_loss_with_temperature.py:90-95)
+//
+// Tile: BLOCK_M=128 x BLOCK_N=256 x BLOCK_K=64, 4-stage smem ring (48 KB/stage), 2 TMEM accumulator stages
+// (2 x 256 fp32 columns = all 512 TMEM columns) so the epilogue of tile i overlaps the MMAs of tile i+1.
+// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2..5 = epilogue.
+#include "common.cuh"
+#include "mmb200_internal.h"
+
+namespace mmb {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_N = 256;
+constexpr int BLOCK_K = 64;
+constexpr int UMMA_K = 16;
+constexpr int STAGES = 4;
+constexpr int ACC_STAGES = 2;
+constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
+constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;  // 32 KB
+constexpr int SLAB_BYTES = 128 * 128;           // 128 rows x 128 B
+constexpr int NUM_SLABS = 2;
+constexpr int GEMM_THREADS = 192;
+constexpr int EPI_THREADS = 128;
+constexpr int GEMM_SMEM_BYTES = 1024 /*align slack*/ + STAGES * (A_BYTES + B_BYTES) + NUM_SLABS * SLAB_BYTES + 256;
+
+struct GemmArgs {
+  int M, N, K;
+  int m_tiles, n_tiles, splits, kb_total, kb_per_split;
+  float alpha;
+  const float* bias;          // [N] fp32 or nullptr
+  const __nv_bfloat16* aux;   // EPI_DACT: pre-activation [M, ld_aux]
+  long long ld_aux;
+  void* d0; void* d1;         // bf16 epilogues write with plain coalesced stores
+  long long ldd0, ldd1;
+  int reduce_add;             // fp32 epilogue: TMA reduce-add instead of store
+};
+
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+template <bool A_MN, bool B_MN, int EPI, int ACT>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+            const __grid_constant__ CUtensorMap tmD0, const __grid_constant__ CUtensorMap tmD1, const GemmArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * A_BYTES;
+  uint8_t* sSlab = smem + STAGES * (A_BYTES + B_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sSlab + NUM_SLABS * SLAB_BYTES);
+  uint64_t* full_bar = bars;                   // [STAGES]
+  uint64_t* empty_bar = bars + STAGES;         // [STAGES]
+  uint64_t* tfull_bar = bars + 2 * STAGES;     // [ACC_STAGES]
+  uint64_t* tempty_bar = bars + 2 * STAGES + ACC_STAGES;  // [ACC_STAGES]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2 * ACC_STAGES);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    if (EPI == EPI_F32) tma_prefetch_desc(&tmD0);
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < ACC_STAGES; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 4);  // one arrive per epilogue warp
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, ACC_STAGES * BLOCK_N);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tiles_mn = p.m_tiles * p.n_tiles;
+  const int total_tiles = tiles_mn * p.splits;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int split = t / tiles_mn;
+        const int rem = t - split * tiles_mn;
+        const int m_blk = rem / p.n_tiles, n_blk = rem - m_blk * p.n_tiles;
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[stage], A_BYTES + B_BYTES);
+          uint8_t* a_dst = sA + stage * A_BYTES;
+          uint8_t* b_dst = sB + stage * B_BYTES;
+          if (!A_MN) {
+            tma_load_2d(&tmA, &full_bar[stage], a_dst, kb * BLOCK_K, m_blk * BLOCK_M);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BLOCK_M / 64; ++j)
+              tma_load_2d(&tmA, &full_bar[stage], a_dst + j * (64 * BLOCK_K * 2), m_blk * BLOCK_M + j * 64,
+                          kb * BLOCK_K);
+          }
+          if (!B_MN) {
+            tma_load_2d(&tmB, &full_bar[stage], b_dst, kb * BLOCK_K, n_blk * BLOCK_N);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BLOCK_N / 64; ++j)
+              tma_load_2d(&tmB, &full_bar[stage], b_dst + j * (64 * BLOCK_K * 2), n_blk * BLOCK_N + j * 64,
+                          kb * BLOCK_K);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N, A_MN, B_MN);
+      // K-major SW128: 8-row groups 1024 B apart (SBO); LBO unused. MN-major SW128: 64-element MN blocks
+      // (one TMA box, BLOCK_K rows x 128 B) 8192 B apart (LBO); 8-row k groups 1024 B apart (SBO).
+      constexpr uint32_t A_LBO = A_MN ? 64 * BLOCK_K * 2 : 16, B_LBO = B_MN ? 64 * BLOCK_K * 2 : 16;
+      constexpr uint32_t A_KSTEP = A_MN ? (UMMA_K / 8) * 1024 : UMMA_K * 2;  // bytes per UMMA_K step
+      constexpr uint32_t B_KSTEP = B_MN ? (UMMA_K / 8) * 1024 : UMMA_K * 2;
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int split = t / tiles_mn;
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t adesc = make_smem_desc_sw128(smem_u32(sA + stage * A_BYTES), A_LBO, 1024);
+          const uint64_t bdesc = make_smem_desc_sw128(smem_u32(sB + stage * B_BYTES), B_LBO, 1024);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            umma_bf16(d_tmem, adesc + (uint64_t)((k * A_KSTEP) >> 4), bdesc + (uint64_t)((k * B_KSTEP) >> 4), idesc,
+                      (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees this smem stage once the MMAs above have read it
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+        if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== Epilogue (warps 2..5) =====================
+    const int q = warp & 3;              // TMEM lane quadrant this warp may access
+    const int row = q * 32 + lane;       // row of the tile owned by this thread
+    const int epi_tid = threadIdx.x - 64;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    int slab = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int split = t / tiles_mn;
+      const int rem = t - split * tiles_mn;
+      const int m_blk = rem / p.n_tiles, n_blk = rem - m_blk * p.n_tiles;
+      const int m0 = m_blk * BLOCK_M, n0 = n_blk * BLOCK_N;
+      const bool add_bias = (p.bias != nullptr) && (split == 0);
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N;
+
+      if (EPI == EPI_F32) {
+        // fp32 output: one 32-column chunk == one 128 B x 128 row slab.
+        for (int c = 0; c < BLOCK_N / 32; ++c) {
+          if (n0 + c * 32 >= p.N) break;
+          uint32_t v[32];
+          tmem_ld32(t_addr + c * 32, v);
+          if (epi_tid == 0) tma_store_wait_read<NUM_SLABS - 1>();
+          tmem_ld_wait();
+          epi_bar_sync();
+          uint8_t* dst = sSlab + slab * SLAB_BYTES + row * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 o;
+            const int n = n0 + c * 32 + j * 4;
+            float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (add_bias && n < p.N) b = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+            o.x = __uint_as_float(v[j * 4 + 0]) * p.alpha + b.x;
+            o.y = __uint_as_float(v[j * 4 + 1]) * p.alpha + b.y;
+            o.z = __uint_as_float(v[j * 4 + 2]) * p.alpha + b.z;
+            o.w = __uint_as_float(v[j * 4 + 3]) * p.alpha + b.w;
+            *reinterpret_cast<float4*>(dst + ((j ^ (row & 7)) << 4)) = o;
+          }
+          fence_proxy_async_smem();
+          epi_bar_sync();
+          if (epi_tid == 0) {
+            if (p.reduce_add)
+              tma_reduce_add_2d(&tmD0, sSlab + slab * SLAB_BYTES, n0 + c * 32, m0);
+            else
+              tma_store_2d(&tmD0, sSlab + slab * SLAB_BYTES, n0 + c * 32, m0);
+            tma_store_commit();
+          }
+          slab ^= 1;
+        }
+      } else {
+        // bf16 outputs.  Per 64-column group: TMEM -> registers -> (bias / activation / act') -> bf16 -> swizzled
+        // smem slab (thread == row) -> one named barrier -> row-contiguous coalesced 16 B st.global (4 rows of
+        // 128 B per warp instruction).  Two slab sets alternate, so one barrier per group is sufficient.
+        // EPI_BF16_ACT writes two tensors (D0 = pre-activation, D1 = act(D0)) and therefore uses both slabs per
+        // group (two barriers per group).
+        constexpr bool DUAL = (EPI == EPI_BF16_ACT);
+        __nv_bfloat16* D0p = reinterpret_cast<__nv_bfloat16*>(p.d0);
+        __nv_bfloat16* D1p = reinterpret_cast<__nv_bfloat16*>(p.d1);
+        for (int g = 0; g < BLOCK_N / 64; ++g) {
+          if (n0 + g * 64 >= p.N) break;
+          if (DUAL) epi_bar_sync();  // both slabs are rewritten every group
+          uint8_t* dst0 = sSlab + (DUAL ? 0 : slab * SLAB_BYTES) + row * 128;
+          uint8_t* dst1 = sSlab + SLAB_BYTES + row * 128;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            uint32_t v[32];
+            tmem_ld32(t_addr + g * 64 + h * 32, v);
+            const int nb = n0 + g * 64 + h * 32;
+            uint4 auxv[4];
+            if (EPI == EPI_BF16_DACT) {
+              const bool ok = (m0 + row) < p.M;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                auxv[j] = make_uint4(0, 0, 0, 0);
+                if (ok && nb + j * 8 < p.N)
+                  auxv[j] = __ldg(reinterpret_cast<const uint4*>(p.aux + (long long)(m0 + row) * p.ld_aux + nb + j * 8));
+              }
+            }
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {  // 8 columns -> one 16 B chunk
+              float f[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[j * 8 + e]) * p.alpha;
+              const int n = nb + j * 8;
+              if (add_bias && n < p.N) {
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+                const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4));
+                f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+                f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+              }
+              if (EPI == EPI_BF16_DACT) {
+                const uint32_t a[4] = {auxv[j].x, auxv[j].y, auxv[j].z, auxv[j].w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  f[2 * e] *= act_grad<ACT>(bf16_lo(a[e]));
+                  f[2 * e + 1] *= act_grad<ACT>(bf16_hi(a[e]));
+                }
+              }
+              uint4 o;
+              o.x = pack_bf16x2(f[0], f[1]);
+              o.y = pack_bf16x2(f[2], f[3]);
+              o.z = pack_bf16x2(f[4], f[5]);
+              o.w = pack_bf16x2(f[6], f[7]);
+              const int off = ((h * 4 + j) ^ (row & 7)) << 4;
+              *reinterpret_cast<uint4*>(dst0 + off) = o;
+              if (DUAL) {
+                // The activation is applied to the bf16-ROUNDED pre-activation: exactly what the backward (which
+                // only sees the stored bf16 pre-activation) differentiates.
+                const uint32_t pr[4] = {o.x, o.y, o.z, o.w};
+                float a[8];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  a[2 * e] = act_fn<ACT>(bf16_lo(pr[e]));
+                  a[2 * e + 1] = act_fn<ACT>(bf16_hi(pr[e]));
+                }
+                uint4 oa;
+                oa.x = pack_bf16x2(a[0], a[1]);
+                oa.y = pack_bf16x2(a[2], a[3]);
+                oa.z = pack_bf16x2(a[4], a[5]);
+                oa.w = pack_bf16x2(a[6], a[7]);
+                *reinterpret_cast<uint4*>(dst1 + off) = oa;
+              }
+            }
+          }
+          epi_bar_sync();
+          // coalesced copy-out: 128 rows x 8 chunks of 16 B; thread -> (row = it*16 + tid/8, chunk = tid%8)
+          {
+            const int ch = epi_tid & 7;
+            const int ncol = n0 + g * 64 + ch * 8;
+            const uint8_t* s0 = sSlab + (DUAL ? 0 : slab * SLAB_BYTES);
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int r = it * 16 + (epi_tid >> 3);
+              if (m0 + r < p.M && ncol < p.N) {
+                const int off = r * 128 + ((ch ^ (r & 7)) << 4);
+                const uint4 val = *reinterpret_cast<const uint4*>(s0 + off);
+                *reinterpret_cast<uint4*>(D0p + (long long)(m0 + r) * p.ldd0 + ncol) = val;
+                if (DUAL) {
+                  const uint4 val1 = *reinterpret_cast<const uint4*>(s0 + SLAB_BYTES + off);
+                  *reinterpret_cast<uint4*>(D1p + (long long)(m0 + r) * p.ldd1 + ncol) = val1;
+                }
+              }
+            }
+          }
+          slab ^= 1;
+        }
+      }
+      // All TMEM reads of this accumulator stage are complete (tmem_ld_wait above) -> hand it back to the MMA warp.
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+    }
+    if (epi_tid == 0) tma_store_wait_all<0>();
+  }
+
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, ACC_STAGES * BLOCK_N);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// Host side
+// ----------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess || !p)
+      return nullptr;
+    fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+// 2-D row-major tensor [outer, inner] with row pitch `pitch_bytes`; box = [box_outer, box_inner]; 128B swizzle.
+int make_tmap_2d(CUtensorMap* out, const void* ptr, int elem_bytes, bool is_f32, uint64_t inner, uint64_t outer,
+                 uint64_t pitch_bytes, uint32_t box_inner, uint32_t box_outer) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) return MMB_ERR_DRIVER;
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (pitch_bytes & 15) || box_inner * elem_bytes != 128) return MMB_ERR_ARG;
+  cuuint64_t gdim[2] = {inner, outer};
+  cuuint64_t gstr[1] = {pitch_bytes};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, is_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                   const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? MMB_OK : MMB_ERR_DRIVER;
+}
+
+static int g_num_sms = 0;
+int num_sms() {
+  if (!g_num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return g_num_sms;
+}
+
+template <bool A_MN, bool B_MN, int EPI, int ACT>
+static int launch(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tD0, const CUtensorMap& tD1,
+                  const GemmArgs& args, cudaStream_t stream) {
+  auto kfn = gemm_kernel<A_MN, B_MN, EPI, ACT>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  const int total = args.m_tiles * args.n_tiles * args.splits;
+  const int grid = total < num_sms() ? total : num_sms();
+  kfn<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(tA, tB, tD0, tD1, args);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace mmb
+
+using namespace mmb;
+
+extern "C" int mmb_gemm_bf16(const void* A, long long lda, int a_mn_major, const void* B, long long ldb,
+                             int b_mn_major, void* D0, long long ldd0, void* D1, long long ldd1, int M, int N, int K,
+                             int epilogue, int act, float alpha, const float* bias, const void* aux,
+                             long long ld_aux, int splits, int accumulate, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (M <= 0 || N <= 0 || K <= 0) return MMB_ERR_ARG;
+  if ((N & 7) || (lda & 7) || (ldb & 7)) return MMB_ERR_ARG;
+  GemmArgs g;
+  g.M = M; g.N = N; g.K = K;
+  g.m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
+  g.n_tiles = (N + BLOCK_N - 1) / BLOCK_N;
+  g.kb_total = (K + BLOCK_K - 1) / BLOCK_K;
+  if (splits < 1) splits = 1;
+  if (splits > g.kb_total) splits = g.kb_total;
+  if (epilogue != EPI_F32) splits = 1;
+  g.kb_per_split = (g.kb_total + splits - 1) / splits;
+  g.splits = (g.kb_total + g.kb_per_split - 1) / g.kb_per_split;
+  g.alpha = alpha;
+  g.bias = bias;
+  g.aux = reinterpret_cast<const __nv_bfloat16*>(aux);
+  g.ld_aux = ld_aux;
+  g.d0 = D0; g.d1 = D1; g.ldd0 = ldd0; g.ldd1 = ldd1;
+  g.reduce_add = (accumulate || g.splits > 1) ? 1 : 0;
+
+  CUtensorMap tA, tB, tD0, tD1;
+  int rc;
+  // A: K-major -> global [M rows][K inner]; MN-major -> global [K rows][M inner]
+  if (!a_mn_major) rc = make_tmap_2d(&tA, A, 2, false, K, M, lda * 2, 64, BLOCK_M);
+  else             rc = make_tmap_2d(&tA, A, 2, false, M, K, lda * 2, 64, BLOCK_K);
+  if (rc) return rc;
+  if (!b_mn_major) rc = make_tmap_2d(&tB, B, 2, false, K, N, ldb * 2, 64, BLOCK_N);
+  else             rc = make_tmap_2d(&tB, B, 2, false, N, K, ldb * 2, 64, BLOCK_K);
+  if (rc) return rc;
+  if (epilogue == EPI_F32) {
+    if (ldd0 & 3) return MMB_ERR_ARG;
+    rc = make_tmap_2d(&tD0, D0, 4, true, N, M, ldd0 * 4, 32, 128);
+    if (rc) return rc;
+    tD1 = tD0;
+    if (g.splits > 1 && !accumulate) {
+      cudaError_t e = cudaMemset2DAsync(D0, ldd0 * 4, 0, (size_t)N * 4, M, stream);
+      if (e != cudaSuccess) return (int)e;
+    }
+  } else {
+    if ((ldd0 & 7) || (reinterpret_cast<uintptr_t>(D0) & 15)) return MMB_ERR_ARG;
+    if (epilogue == EPI_BF16_ACT && (!D1 || (ldd1 & 7) || (reinterpret_cast<uintptr_t>(D1) & 15))) return MMB_ERR_ARG;
+    if (epilogue == EPI_BF16_DACT && (!aux || (ld_aux & 7) || (reinterpret_cast<uintptr_t>(aux) & 15))) return MMB_ERR_ARG;
+    tD0 = tA;  // unused by the bf16 epilogues
+    tD1 = tA;
+  }
+
+  const int am = a_mn_major ? 1 : 0, bm = b_mn_major ? 1 : 0;
+#define MMB_CASE(AM, BM, E, AC) \
+  if (am == AM && bm == BM && epilogue == E && (AC < 0 || act == AC))    \
+    return launch<(AM != 0), (BM != 0), E, (AC < 0 ? 0 : AC)>(tA, tB, tD0, tD1, g, stream);
+  MMB_CASE(0, 0, EPI_BF16, -1)
+  MMB_CASE(0, 0, EPI_BF16_ACT, ACT_QUICK_GELU)
+  MMB_CASE(0, 0, EPI_BF16_ACT, ACT_GELU_ERF)
+  MMB_CASE(0, 0, EPI_F32, -1)
+  MMB_CASE(0, 1, EPI_BF16, -1)
+  MMB_CASE(0, 1, EPI_BF16_DACT, ACT_QUICK_GELU)
+  MMB_CASE(0, 1, EPI_BF16_DACT, ACT_GELU_ERF)
+  MMB_CASE(0, 1, EPI_F32, -1)
+  MMB_CASE(1, 1, EPI_F32, -1)
+  MMB_CASE(1, 0, EPI_F32, -1)
+#undef MMB_CASE
+  return MMB_ERR_UNSUPPORTED;
+}
