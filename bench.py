@@ -1,0 +1,290 @@
+#!/usr/bin/env python
+"""Headline benchmark: image-text pairs/sec of one CLIP ViT-B/16 contrastive pre-training step (forward + loss +
+backward + gradient all-reduce + AdamW), bs=1024 per GPU, bf16 tensor-core math, synthetic 224x224x3 / 77-token data.
+
+    python bench.py --gpus 1 --steps 5 --warmup 3                  # ours, one GPU
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W                     # ours, N GPUs (weak scaling)
+    python bench.py --impl reference --steps 3 --warmup 1          # reference arm: CPU fp32 port of the reference path
+
+Prints ONE JSON line (rank 0).  See DESIGN.md §Measurement for every field.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# Algorithmic FLOPs per pair, CLIP ViT-B/16 (SURVEY.md §8d / BASELINE.md §5): forward 41.01 GF, step = 3x forward.
+F_FWD_B16 = 35.127e9 + 5.887e9
+F_STEP_B16 = 3.0 * F_FWD_B16
+METRIC = "image-text pairs/sec (CLIP ViT-B/16 contrastive pretrain step, bs=1024/GPU)"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=1024, help="per-GPU batch (default = the BASELINE.json config)")
+    ap.add_argument("--cpu-batch", type=int, default=8, help="sample size of the CPU reference/port legs")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return float(d["bf16_tflops_sustained"]), float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json, sustained cuBLAS bf16)"
+    return 1400.0, 6650.0, "fallback (B200_PROFILING.md: 1.4 PFLOP/s sustained)"
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# CPU reference arm / cpu_baseline: the oracle port (fp32, all host threads) of the reference's own path
+# ----------------------------------------------------------------------------------------------------------------
+def cpu_port_run(steps, warmup, batch):
+    import torch
+    from oracle import clip_oracle as O  # test-infrastructure port; allowed here (cpu_baseline / --impl reference)
+    from multimodal_b200.models.clip.model import clip_vit_b16
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    sd = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in clip_vit_b16().state_dict().items()}
+    scale = torch.tensor(math.log(1 / 0.07), requires_grad=True)
+    img, txt = O.synthetic_batch(batch)
+    params = [v for v in sd.values() if v.requires_grad] + [scale]
+
+    def step():
+        a, b = O.clip_forward(img, txt, sd, 12, 8)
+        loss = O.contrastive_loss(a, b, O.clamp_logit_scale(scale))[0]
+        loss.backward()
+        with torch.no_grad():  # plain SGD update: the cheapest possible optimizer (favours the CPU arm)
+            for p in params:
+                p -= 1e-4 * p.grad
+                p.grad = None
+        return float(loss)
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    return batch / dt, dt, cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    val, dt, cores = cpu_port_run(args.steps, args.warmup, args.cpu_batch)
+    sample = f"{args.cpu_batch} pairs/step x {args.steps} steps (fwd+loss+bwd+SGD), fp32 eager, {cores} threads"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "CLIP ViT-B/16 contrastive pretrain step (fwd+loss+bwd+update), CPU port of the reference path",
+                   "per_gpu_batch": args.cpu_batch, "image": "224x224x3", "text_len": 77},
+        "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# clocks sampling during the timed region
+# ----------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.path = tempfile.mktemp(suffix=".csv")
+        self.proc = None
+        self.idx = gpu_index
+
+    def start(self):
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                         stderr=subprocess.DEVNULL)
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.proc.wait()
+        self.f.close()
+        sm, mx, reasons = [], [], set()
+        for line in open(self.path):
+            p = [x.strip() for x in line.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1])); mx.append(float(p[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.path)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N > 1")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from multimodal_b200 import _lib, ops
+    from multimodal_b200.models.clip.model import clip_vit_b16
+    from multimodal_b200.modules.losses.contrastive_loss_with_temperature import ContrastiveLossWithTemperature
+    from multimodal_b200.train import ContrastiveTrainer
+    from oracle import clip_oracle as O  # only for the synthetic-input generator + the bounded cpu_baseline leg
+
+    _lib.lib()  # fail loudly right away if the CUDA library is missing
+    B = args.batch
+    torch.manual_seed(0)
+    model = clip_vit_b16().to(dev)
+    loss_mod = ContrastiveLossWithTemperature().to(dev)
+    trainer = ContrastiveTrainer(model, loss_mod)
+
+    img_h, txt_h = O.synthetic_batch(B, rank=rank)
+    img_h, txt_h = img_h.pin_memory(), txt_h.pin_memory()
+    img_d, txt_d = img_h.to(dev, non_blocking=True), txt_h.to(dev, non_blocking=True)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- warm-up (allocations, first-touch, clocks) ----
+    for _ in range(max(args.warmup, 3)):
+        loss = trainer.step(img_d, txt_d)
+    barrier()
+
+    # ---- timed: device-resident inputs ----
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ops.GEMM_TIMING = []
+    launches0 = _lib.LAUNCHES
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        loss = trainer.step(img_d, txt_d)
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_dev = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+    launches = (_lib.LAUNCHES - launches0) // args.steps
+    gemm_log, ops.GEMM_TIMING = ops.GEMM_TIMING, None
+    final_loss = float(loss.item())
+
+    # live roofline of the dominant kernel (mmb::gemm_kernel): algorithmic FLOPs / CUDA-event duration per launch
+    tot_f, tot_ms, by_kind = 0.0, 0.0, {}
+    for flops, kind, (a, b) in gemm_log:
+        ms = a.elapsed_time(b)
+        tot_f += flops; tot_ms += ms
+        k = by_kind.setdefault(str(kind), [0.0, 0.0, 0]); k[0] += flops; k[1] += ms; k[2] += 1
+    peak_tf, _, peak_src = measured_peaks()
+    achieved = tot_f / (tot_ms * 1e-3) / 1e12 if tot_ms > 0 else 0.0
+    n_gemm = max(len(gemm_log), 1)
+
+    # ---- timed: end to end through the public step() with host inputs (H2D of inputs + D2H of the loss every step) ----
+    barrier()
+    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(args.steps):
+        xi = img_h.to(dev, non_blocking=True)
+        xt = txt_h.to(dev, non_blocking=True)
+        l_host = float(trainer.step(xi, xt).item())
+    t1.record()
+    barrier()
+    ms_e2e = max_over_ranks(t0.elapsed_time(t1) / args.steps)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    value = B * world / (ms_dev * 1e-3)
+    e2e_val = B * world / (ms_e2e * 1e-3)
+    step_tf = value * F_STEP_B16 / 1e12 / world
+    out = {
+        "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic",
+        "config": {"workload": "CLIP ViT-B/16 contrastive pretrain step (fwd+loss+bwd+grad-allreduce+AdamW)",
+                   "per_gpu_batch": B, "global_batch": B * world, "image": "224x224x3 fp32", "text_len": 77,
+                   "parallelism": f"dp{world}", "l2": "activations (~84 GB/step) and inputs (616 MB) exceed the 126 MB L2; no flush needed",
+                   "final_loss": final_loss},
+        "e2e": {"value": e2e_val, "unit": "pairs/s", "h2d_bytes_per_step": img_h.numel() * 4 + txt_h.numel() * 8,
+                "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
+                     "frac": achieved / peak_tf if peak_tf else None, "traffic": None,
+                     "kernel": "mmb::gemm_kernel (tcgen05, all instantiations; per-launch average over the timed region)",
+                     "launches_per_step": n_gemm // args.steps, "flops_per_launch_avg": tot_f / n_gemm,
+                     "ms_per_launch_avg": tot_ms / n_gemm, "gemm_share_of_step": (tot_ms / args.steps) / ms_dev,
+                     "peak_source": peak_src,
+                     "step_level": {"achieved": step_tf, "frac": step_tf / peak_tf,
+                                    "note": "whole step: pairs/s/GPU x 123.04 GF / peak"},
+                     "by_kind": {k: {"tflops": v[0] / (v[1] * 1e-3) / 1e12, "ms_per_step": v[1] / args.steps, "n": v[2] // args.steps}
+                                 for k, v in by_kind.items()}},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        val, dt, cores = cpu_port_run(2, 1, args.cpu_batch)
+        out["cpu_baseline"] = {"value": val, "unit": "pairs/s", "cores": cores, "kind": "port",
+                               "sample": f"{args.cpu_batch} pairs/step x 2 steps (fwd+loss+bwd+SGD), fp32 eager oracle port"}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

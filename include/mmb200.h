@@ -42,6 +42,87 @@ int mmb_gemm_bf16(const void* A, long long lda, int a_mn_major, const void* B, l
                   float alpha, const float* bias, const void* aux, long long ld_aux, int splits, int accumulate,
                   void* stream);
 
+
+/* ---- HBM-bound kernels ------------------------------------------------------------------------------------ */
+
+/* dst[i] = bf16(src[i]) — parameter shadow for the tensor-core operands (what torch.autocast does per call). */
+int mmb_cast_f32_to_bf16(const float* src, void* dst_bf16, long long n, void* stream);
+
+/* Patch im2col + cast: img fp32 [B,3,H,W] -> bf16 [B*(H/ps)*(W/ps), 3*ps*ps], K order (c,kh,kw), patches row-major.
+ * Replaces the data movement half of nn.Conv2d(3,width,ps,ps,bias=False), models/clip/image_encoder.py:50-56,91-97. */
+int mmb_im2col_patches(const float* img, void* out_bf16, int B, int H, int W, int ps, void* stream);
+
+/* x_out = x_in (+ y_bf16); ln = LayerNorm(x_out)*gamma+beta, fp32 statistics.  Any of x_in/y/x_out/ln_bf16/ln_f32/
+ * mean/rstd may be NULL.  rows_per_group > 0 selects the gather mode: logical row m reads physical row
+ * m*rows_per_group + (row_idx ? row_idx[m] : 0) and every output is written compactly at row m.
+ * Replaces: residual add + norm1/norm2 (torch/nn/modules/transformer.py:946-951), Fp32LayerNorm ln_post / ln_final
+ * (torchmultimodal/modules/layers/normalizations.py:17-25; models/clip/image_encoder.py:111, text_encoder.py:125). */
+int mmb_add_layernorm_fwd(const float* x_in, const void* y_bf16, float* x_out, void* ln_bf16, float* ln_f32,
+                          const float* gamma, const float* beta, float* mean, float* rstd, const int* row_idx,
+                          int rows_per_group, int M, int d, float eps, void* stream);
+
+/* CLIP ViT token assembly + ln_pre: x0 = LN(cat(cls, patch_out) + pos) (models/clip/image_encoder.py:94-106). */
+int mmb_vit_embed_ln_fwd(const void* patch_out_bf16, const float* cls, const float* pos, const float* gamma,
+                         const float* beta, float* x0, float* mean, float* rstd, int B, int S, int d, float eps,
+                         void* stream);
+
+/* LayerNorm backward (+ residual-gradient add): g_out = (g_in?) + dLN/dx; dgamma/dbeta accumulated with atomics.
+ * dy is bf16 or fp32 (exactly one non-NULL).  Gather mode as in the forward: x/dy/mean/rstd are compact [M,d],
+ * g_out/g_bf16 are scattered to the physical rows of a zero-initialised [*,d] buffer. */
+int mmb_layernorm_bwd(const float* x, const void* dy_bf16, const float* dy_f32, const float* mean, const float* rstd,
+                      const float* gamma, const float* g_in, float* g_out, void* g_bf16, float* dgamma, float* dbeta,
+                      const int* row_idx, int rows_per_group, int M, int d, void* stream);
+
+/* Backward of mmb_vit_embed_ln_fwd: dt = d/d(cat+pos) fp32 [B,S,d]; dpatch = bf16 copy of rows s>=1, compact. */
+int mmb_vit_embed_ln_bwd(const void* patch_out_bf16, const float* cls, const float* pos, const float* dy_f32,
+                         const float* mean, const float* rstd, const float* gamma, float* dt_f32, void* dpatch_bf16,
+                         float* dgamma, float* dbeta, int B, int S, int d, void* stream);
+
+/* out[j] += sum_b in[b*ld + j], j < n   (positional-embedding / cls gradients) */
+int mmb_batch_sum(const float* in, float* out, int Bn, long long ld, int n, void* stream);
+/* out[n] += sum_m x[m*ld + n]           (bias gradients), x bf16 */
+int mmb_colsum_bf16(const void* x_bf16, float* out, int M, int N, long long ld, void* stream);
+
+/* x[b,s,:] = emb[tokens[b,s],:] + pos[s,:]; tokens int64, bit-exact gather (models/clip/text_encoder.py:118-119). */
+int mmb_text_embed_fwd(const long long* tokens, const float* emb, const float* pos, float* x, int B, int S, int d,
+                       int V, void* stream);
+int mmb_text_embed_bwd(const long long* tokens, const float* g, float* demb, int B, int S, int d, void* stream);
+/* idx[b] = argmax_s tokens[b,s], first maximum (EOT position; models/clip/text_encoder.py:130-132). Bit-exact. */
+int mmb_argmax_tokens(const long long* tokens, int* idx, int B, int S, void* stream);
+
+/* F.normalize(x, dim=1, eps) (models/clip/model.py:72-73) and its backward. */
+int mmb_l2norm_fwd(const float* x, float* y, void* y_bf16, float* inv_norm, int B, int E, float eps, void* stream);
+int mmb_l2norm_bwd(const float* dy, const float* y, const float* inv_norm, float* dx, void* dx_bf16, int B, int E,
+                   void* stream);
+
+/* Fused AdamW over a flat buffer (torch.optim.AdamW update rule); writes the bf16 shadow and optionally zeroes g. */
+int mmb_adamw_step(float* p, float* g, float* m, float* v, void* p_bf16, long long n, float lr, float beta1,
+                   float beta2, float eps, float weight_decay, int step, float grad_scale, int zero_grad,
+                   void* stream);
+int mmb_memset_async(void* p, int value, long long bytes, void* stream);
+
+/* ---- attention --------------------------------------------------------------------------------------------- */
+/* O = softmax(Q K^T * scale [+ causal mask]) V per (batch, head); qkv bf16 [B*S, 3*H*64] packed [q|k|v], out bf16
+ * [B*S, H*64], lse fp32 [B,H,S].  Replaces F.scaled_dot_product_attention (torch/nn/functional.py:6682). */
+int mmb_attention_fwd(const void* qkv, void* out, float* lse, int B, int S, int H, int head_dim, int causal,
+                      float scale, void* stream);
+int mmb_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, int B, int S,
+                      int H, int head_dim, int causal, float scale, void* stream);
+
+/* ---- contrastive loss -------------------------------------------------------------------------------------- */
+/* One direction of contrastive_loss_with_temperature (modules/losses/contrastive_loss_with_temperature.py:81-107):
+ * logits = exp(*logit_scale) * sims; row_loss[i] = CE(logits[i], label_offset + i) with label smoothing;
+ * dsims (bf16 and/or fp32, same leading dim) = d(loss_weight * mean_i row_loss)/d sims; *dscale_accum += same w.r.t. logit_scale. */
+int mmb_contrastive_ce(const float* sims, long long ld, const float* logit_scale, int rows, int N, int label_offset,
+                       float label_smoothing, float loss_weight, float* row_loss, void* dsims_bf16, float* dsims_f32,
+                       long long ld_d, float* dscale_accum, float* logits_out, long long ld_l, void* stream);
+/* fp32 SIMT matmul for tiny / unaligned shapes the tensor-core path rejects: C (+)= alpha*op(A)op(B);
+ * ta: A stored [K,M]; tb: B stored [N,K]. */
+int mmb_matmul_f32(const float* A, long long lda, int ta, const float* B, long long ldb, int tb, float* C,
+                   long long ldc, int M, int N, int K, float alpha, int accumulate, void* stream);
+/* out[0] (+)= scale * sum(in[0..n)) — deterministic */
+int mmb_sum_scale(const float* in, int n, float scale, float* out, int accumulate, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

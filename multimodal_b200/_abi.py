@@ -8,6 +8,26 @@ vp, ll, i32, f32 = C.c_void_p, C.c_longlong, C.c_int, C.c_float
 PROTOTYPES = {
     "mmb_version": (i32, []),
     "mmb_gemm_bf16": (i32, [vp, ll, i32, vp, ll, i32, vp, ll, vp, ll, i32, i32, i32, i32, i32, f32, vp, vp, ll, i32, i32, vp]),
+    "mmb_cast_f32_to_bf16": (i32, [vp, vp, ll, vp]),
+    "mmb_im2col_patches": (i32, [vp, vp, i32, i32, i32, i32, vp]),
+    "mmb_add_layernorm_fwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, f32, vp]),
+    "mmb_vit_embed_ln_fwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, f32, vp]),
+    "mmb_layernorm_bwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]),
+    "mmb_vit_embed_ln_bwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]),
+    "mmb_batch_sum": (i32, [vp, vp, i32, ll, i32, vp]),
+    "mmb_colsum_bf16": (i32, [vp, vp, i32, i32, ll, vp]),
+    "mmb_text_embed_fwd": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, vp]),
+    "mmb_text_embed_bwd": (i32, [vp, vp, vp, i32, i32, i32, vp]),
+    "mmb_argmax_tokens": (i32, [vp, vp, i32, i32, vp]),
+    "mmb_l2norm_fwd": (i32, [vp, vp, vp, vp, i32, i32, f32, vp]),
+    "mmb_l2norm_bwd": (i32, [vp, vp, vp, vp, vp, i32, i32, vp]),
+    "mmb_adamw_step": (i32, [vp, vp, vp, vp, vp, ll, f32, f32, f32, f32, f32, i32, f32, i32, vp]),
+    "mmb_memset_async": (i32, [vp, i32, ll, vp]),
+    "mmb_attention_fwd": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, f32, vp]),
+    "mmb_attention_bwd": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, vp]),
+    "mmb_contrastive_ce": (i32, [vp, ll, vp, i32, i32, i32, f32, f32, vp, vp, vp, ll, vp, vp, ll, vp]),
+    "mmb_matmul_f32": (i32, [vp, ll, i32, vp, ll, i32, vp, ll, i32, i32, i32, f32, i32, vp]),
+    "mmb_sum_scale": (i32, [vp, i32, f32, vp, i32, vp]),
 }
 
 

@@ -88,6 +88,12 @@ def lib() -> ctypes.CDLL:
     return _lib
 
 
+LAUNCHES = 0  # kernels launched through the C ABI (bench.py reports the count inside its timed region)
+
+
 def check(rc: int, what: str) -> None:
+    global LAUNCHES
     if rc != 0:
         raise MMBError(f"{what} failed with status {rc}")
+    if what != "mmb_memset_async":
+        LAUNCHES += 1

@@ -232,8 +232,19 @@ __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v 
 
 // QuickGELU (reference: torchmultimodal/modules/layers/activation.py:24-25): x * sigmoid(1.702 x).
 // sigmoid via ex2.approx + rcp.approx (2 MUFU ops): relative error ~1e-6, far below the bf16 output rounding.
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// branch-free (no IEEE slow paths): the epilogue must keep 8+ independent elements in flight to hide MUFU latency
 __device__ __forceinline__ float fast_sigmoid(float z) {
-  return __frcp_rn(1.f + exp2f(-1.4426950408889634f * z));
+  return rcp_approx(1.f + ex2_approx(-1.4426950408889634f * z));
 }
 __device__ __forceinline__ float quick_gelu(float x) { return x * fast_sigmoid(1.702f * x); }
 __device__ __forceinline__ float quick_gelu_grad(float x) {
@@ -243,7 +254,7 @@ __device__ __forceinline__ float quick_gelu_grad(float x) {
 // Exact (erf) GELU, as nn.GELU() in the FLAVA / CoCa MLPs (torchmultimodal/modules/layers/mlp.py:35)
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
 __device__ __forceinline__ float gelu_erf_grad(float x) {
-  return 0.5f * (1.f + erff(x * 0.70710678118654752f)) + x * 0.3989422804014327f * __expf(-0.5f * x * x);
+  return 0.5f * (1.f + erff(x * 0.70710678118654752f)) + x * 0.3989422804014327f * ex2_approx(-0.7213475204444817f * x * x);
 }
 template <int ACT>
 __device__ __forceinline__ float act_fn(float x) { return ACT == 0 ? quick_gelu(x) : gelu_erf(x); }

@@ -113,7 +113,7 @@ __global__ void add_ln_fwd_kernel(const float* __restrict__ x_in, const __nv_bfl
           a.x += bf16_lo(u.x); a.y += bf16_hi(u.x); a.z += bf16_lo(u.y); a.w += bf16_hi(u.y);
         }
         r.v[i] = a;
-        if (x_out) *reinterpret_cast<float4*>(x_out + src * d + c) = a;
+        if (x_out) *reinterpret_cast<float4*>(x_out + (long long)m * d + c) = a;  // compact in gather mode
       }
     float mean, rstd;
     ln_stats(r, nv, d, eps, mean, rstd);
@@ -246,7 +246,7 @@ __global__ void ln_bwd_kernel(const LnBwdArgs a) {
             x.x += bf16_lo(u.x); x.y += bf16_hi(u.x); x.z += bf16_lo(u.y); x.w += bf16_hi(u.y);
           }
         } else {
-          x = *reinterpret_cast<const float4*>(a.x + phys * d + c);
+          x = *reinterpret_cast<const float4*>(a.x + (long long)m * d + c);  // compact in gather mode
         }
         float4 g4;
         if (a.dy_bf16) {
@@ -285,7 +285,12 @@ __global__ void ln_bwd_kernel(const LnBwdArgs a) {
           uint2 u;
           u.x = pack_bf16x2(o.x, o.y);
           u.y = pack_bf16x2(o.z, o.w);
-          *reinterpret_cast<uint2*>(a.g_bf16 + phys * d + c) = u;
+          if (VIT) {  // bf16 gradient of the patch-embedding GEMM output: compact [B*(S-1), d], CLS row dropped
+            const int b = m / a.S, sidx = m - b * a.S;
+            if (sidx > 0) *reinterpret_cast<uint2*>(a.g_bf16 + ((long long)b * (a.S - 1) + (sidx - 1)) * d + c) = u;
+          } else {
+            *reinterpret_cast<uint2*>(a.g_bf16 + phys * d + c) = u;
+          }
         }
       }
   }
@@ -421,23 +426,17 @@ __global__ void l2norm_fwd_kernel(const float* __restrict__ x, float* __restrict
   const int lane = threadIdx.x & 31;
   if (b >= B) return;
   float s = 0.f;
-  for (int c = lane * 4; c < E; c += 128) {
-    const float4 v = *reinterpret_cast<const float4*>(x + (long long)b * E + c);
-    s += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  for (int c = lane; c < E; c += 32) {
+    const float v = x[(long long)b * E + c];
+    s += v * v;
   }
   s = warp_sum(s);
   const float inv = 1.f / fmaxf(sqrtf(s), eps);
   if (lane == 0 && inv_norm) inv_norm[b] = inv;
-  for (int c = lane * 4; c < E; c += 128) {
-    const float4 v = *reinterpret_cast<const float4*>(x + (long long)b * E + c);
-    const float4 o = make_float4(v.x * inv, v.y * inv, v.z * inv, v.w * inv);
-    if (y) *reinterpret_cast<float4*>(y + (long long)b * E + c) = o;
-    if (y_bf16) {
-      uint2 u;
-      u.x = pack_bf16x2(o.x, o.y);
-      u.y = pack_bf16x2(o.z, o.w);
-      *reinterpret_cast<uint2*>(y_bf16 + (long long)b * E + c) = u;
-    }
+  for (int c = lane; c < E; c += 32) {
+    const float o = x[(long long)b * E + c] * inv;
+    if (y) y[(long long)b * E + c] = o;
+    if (y_bf16) y_bf16[(long long)b * E + c] = __float2bfloat16(o);
   }
 }
 // dx = (dy - y * <y, dy>) * inv_norm     (valid when ||x|| > eps, which holds for any non-degenerate embedding)
@@ -448,24 +447,13 @@ __global__ void l2norm_bwd_kernel(const float* __restrict__ dy, const float* __r
   const int lane = threadIdx.x & 31;
   if (b >= B) return;
   float s = 0.f;
-  for (int c = lane * 4; c < E; c += 128) {
-    const float4 a = *reinterpret_cast<const float4*>(dy + (long long)b * E + c);
-    const float4 v = *reinterpret_cast<const float4*>(y + (long long)b * E + c);
-    s += a.x * v.x + a.y * v.y + a.z * v.z + a.w * v.w;
-  }
+  for (int c = lane; c < E; c += 32) s += dy[(long long)b * E + c] * y[(long long)b * E + c];
   s = warp_sum(s);
   const float inv = inv_norm[b];
-  for (int c = lane * 4; c < E; c += 128) {
-    const float4 a = *reinterpret_cast<const float4*>(dy + (long long)b * E + c);
-    const float4 v = *reinterpret_cast<const float4*>(y + (long long)b * E + c);
-    const float4 o = make_float4((a.x - v.x * s) * inv, (a.y - v.y * s) * inv, (a.z - v.z * s) * inv, (a.w - v.w * s) * inv);
-    if (dx) *reinterpret_cast<float4*>(dx + (long long)b * E + c) = o;
-    if (dx_bf16) {
-      uint2 u;
-      u.x = pack_bf16x2(o.x, o.y);
-      u.y = pack_bf16x2(o.z, o.w);
-      *reinterpret_cast<uint2*>(dx_bf16 + (long long)b * E + c) = u;
-    }
+  for (int c = lane; c < E; c += 32) {
+    const float o = (dy[(long long)b * E + c] - y[(long long)b * E + c] * s) * inv;
+    if (dx) dx[(long long)b * E + c] = o;
+    if (dx_bf16) dx_bf16[(long long)b * E + c] = __float2bfloat16(o);
   }
 }
 
@@ -565,11 +553,13 @@ extern "C" int mmb_layernorm_bwd(const float* x, const void* dy_bf16, const floa
 
 extern "C" int mmb_vit_embed_ln_bwd(const void* patch_out, const float* cls, const float* pos, const float* dy_f32,
                                     const float* mean, const float* rstd, const float* gamma, float* dt_f32,
-                                    float* dgamma, float* dbeta, int B, int S, int d, void* stream) {
+                                    void* dpatch_bf16, float* dgamma, float* dbeta, int B, int S, int d,
+                                    void* stream) {
   if (!ln_dim_ok(d)) return MMB_ERR_UNSUPPORTED;
   LnBwdArgs a{};
   a.patch_out = (const __nv_bfloat16*)patch_out; a.cls = cls; a.pos = pos; a.S = S;
   a.dy_f32 = dy_f32; a.mean = mean; a.rstd = rstd; a.gamma = gamma; a.g_out = dt_f32;
+  a.g_bf16 = (__nv_bfloat16*)dpatch_bf16;
   a.dgamma = dgamma; a.dbeta = dbeta; a.M = B * S; a.d = d;
   int grid = num_sms() * 4;
   if (grid > (a.M + 7) / 8) grid = (a.M + 7) / 8;
@@ -618,13 +608,11 @@ extern "C" int mmb_argmax_tokens(const long long* tokens, int* idx, int B, int S
 }
 extern "C" int mmb_l2norm_fwd(const float* x, float* y, void* y_bf16, float* inv_norm, int B, int E, float eps,
                               void* stream) {
-  if (E & 3) return MMB_ERR_ARG;
   l2norm_fwd_kernel<<<(B + 7) / 8, 256, 0, ST(stream)>>>(x, y, (__nv_bfloat16*)y_bf16, inv_norm, B, E, eps);
   return LAUNCH_RC();
 }
 extern "C" int mmb_l2norm_bwd(const float* dy, const float* y, const float* inv_norm, float* dx, void* dx_bf16, int B,
                               int E, void* stream) {
-  if (E & 3) return MMB_ERR_ARG;
   l2norm_bwd_kernel<<<(B + 7) / 8, 256, 0, ST(stream)>>>(dy, y, inv_norm, dx, (__nv_bfloat16*)dx_bf16, B, E);
   return LAUNCH_RC();
 }

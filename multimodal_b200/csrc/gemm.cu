@@ -398,7 +398,8 @@ extern "C" int mmb_gemm_bf16(const void* A, long long lda, int a_mn_major, const
                              long long ld_aux, int splits, int accumulate, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (M <= 0 || N <= 0 || K <= 0) return MMB_ERR_ARG;
-  if ((N & 7) || (lda & 7) || (ldb & 7)) return MMB_ERR_ARG;
+  if ((lda & 7) || (ldb & 7)) return MMB_ERR_ARG;
+  if (epilogue == EPI_F32 ? (N & 3) : (N & 7)) return MMB_ERR_ARG;
   GemmArgs g;
   g.M = M; g.N = N; g.K = K;
   g.m_tiles = (M + BLOCK_M - 1) / BLOCK_M;

@@ -1,0 +1,147 @@
+// Temperature-scaled softmax cross-entropy over similarity rows, forward + gradient in one pass.
+// Restates modules/losses/contrastive_loss_with_temperature.py:81-107 for one direction (a->b or b->a):
+//   logits = exp(logit_scale) * sims ; loss_i = CE(logits_i, label_i = label_offset + i) (+ label smoothing)
+// and emits d(mean loss * loss_weight)/d sims in bf16 (operand of the embedding-gradient GEMMs) plus the
+// contribution to d/d logit_scale (= sum dlogits * logits, because d logits / d logit_scale = logits).
+#include "common.cuh"
+#include "mmb200_internal.h"
+
+namespace mmb {
+
+__device__ __forceinline__ float block_reduce_max(float v, float* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = red[0];
+  for (int i = 1; i < (int)(blockDim.x >> 5); ++i) r = fmaxf(r, red[i]);
+  return r;
+}
+__device__ __forceinline__ float block_reduce_sum(float v, float* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = 0.f;
+  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) r += red[i];
+  return r;
+}
+
+__global__ void contrastive_ce_kernel(const float* __restrict__ sims, long long ld, const float* __restrict__ logit_scale,
+                                      int rows, int N, int label_offset, float smoothing, float loss_weight,
+                                      float* __restrict__ row_loss, __nv_bfloat16* __restrict__ dsims,
+                                      float* __restrict__ dsims_f32, long long ld_d, float* __restrict__ dscale_accum, float* __restrict__ logits_out,
+                                      long long ld_l) {
+  __shared__ float red[32];
+  const int i = blockIdx.x;
+  if (i >= rows) return;
+  const float T = __expf(*logit_scale);
+  const float* srow = sims + (long long)i * ld;
+  const int label = label_offset + i;
+  float mx = -INFINITY, sm = 0.f;
+  for (int j = threadIdx.x; j < N; j += blockDim.x) {
+    const float l = T * srow[j];
+    mx = fmaxf(mx, l);
+    sm += l;
+    if (logits_out) logits_out[(long long)i * ld_l + j] = l;
+  }
+  mx = block_reduce_max(mx, red);
+  const float mean_logit = block_reduce_sum(sm, red) / N;
+  float se = 0.f;
+  for (int j = threadIdx.x; j < N; j += blockDim.x) se += __expf(T * srow[j] - mx);
+  se = block_reduce_sum(se, red);
+  const float lse = mx + logf(se);
+  const float l_label = T * srow[label];
+  const float loss = (1.f - smoothing) * (lse - l_label) + smoothing * (lse - mean_logit);
+  if (threadIdx.x == 0 && row_loss) row_loss[i] = loss;
+  if (dsims || dsims_f32) {
+    const float gs = loss_weight / rows;
+    float ds_acc = 0.f;
+    for (int j = threadIdx.x; j < N; j += blockDim.x) {
+      const float l = T * srow[j];
+      const float p = __expf(l - lse);
+      float gl = p - smoothing / N;
+      if (j == label) gl -= (1.f - smoothing);
+      gl *= gs;                                   // d loss / d logit_ij
+      ds_acc += gl * l;                           // -> d / d logit_scale
+      if (dsims) dsims[(long long)i * ld_d + j] = __float2bfloat16(gl * T);  // d loss / d sim_ij
+      if (dsims_f32) dsims_f32[(long long)i * ld_d + j] = gl * T;
+    }
+    ds_acc = block_reduce_sum(ds_acc, red);
+    if (threadIdx.x == 0 && dscale_accum) atomicAdd(dscale_accum, ds_acc);
+  }
+}
+
+// out[0] = scale * sum(in[0..n))  (deterministic single-block tree; n is a batch size)
+__global__ void sum_scale_kernel(const float* __restrict__ in, int n, float scale, float* __restrict__ out, int accumulate) {
+  __shared__ float red[32];
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += in[i];
+  s = block_reduce_sum(s, red);
+  if (threadIdx.x == 0) out[0] = (accumulate ? out[0] : 0.f) + s * scale;
+}
+
+
+// Plain fp32 SIMT matmul for the tiny / unaligned shapes the tensor-core path rejects (e.g. the reference's own
+// 3x5 known-answer tests).  C[M,N] (+)= alpha * op(A) op(B);  ta: A stored [K,M];  tb: B stored [N,K].
+__global__ void matmul_f32_kernel(const float* __restrict__ A, long long lda, int ta, const float* __restrict__ B,
+                                  long long ldb, int tb, float* __restrict__ C, long long ldc, int M, int N, int K,
+                                  float alpha, int accumulate) {
+  __shared__ float sa[32][33], sb[32][33];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int row = blockIdx.y * 32 + ty, col = blockIdx.x * 32 + tx;
+  float acc = 0.f;
+  for (int k0 = 0; k0 < K; k0 += 32) {
+    {  // sa[m][k]
+      const int m = blockIdx.y * 32 + ty, k = k0 + tx;
+      float v = 0.f;
+      if (m < M && k < K) v = ta ? A[(long long)k * lda + m] : A[(long long)m * lda + k];
+      sa[ty][tx] = v;
+    }
+    {  // sb[k][n]
+      const int k = k0 + ty, n = blockIdx.x * 32 + tx;
+      float v = 0.f;
+      if (k < K && n < N) v = tb ? B[(long long)n * ldb + k] : B[(long long)k * ldb + n];
+      sb[ty][tx] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 32; ++k) acc += sa[ty][k] * sb[k][tx];
+    __syncthreads();
+  }
+  if (row < M && col < N) {
+    float* c = C + (long long)row * ldc + col;
+    *c = (accumulate ? *c : 0.f) + alpha * acc;
+  }
+}
+
+}  // namespace mmb
+
+using namespace mmb;
+
+extern "C" int mmb_contrastive_ce(const float* sims, long long ld, const float* logit_scale, int rows, int N,
+                                  int label_offset, float label_smoothing, float loss_weight, float* row_loss,
+                                  void* dsims_bf16, float* dsims_f32, long long ld_d, float* dscale_accum,
+                                  float* logits_out, long long ld_l, void* stream) {
+  if (rows <= 0 || N <= 0 || label_offset < 0 || label_offset + rows > N) return MMB_ERR_ARG;
+  contrastive_ce_kernel<<<rows, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      sims, ld, logit_scale, rows, N, label_offset, label_smoothing, loss_weight, row_loss,
+      (__nv_bfloat16*)dsims_bf16, dsims_f32, ld_d, dscale_accum, logits_out, ld_l);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int mmb_sum_scale(const float* in, int n, float scale, float* out, int accumulate, void* stream) {
+  sum_scale_kernel<<<1, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(in, n, scale, out, accumulate);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int mmb_matmul_f32(const float* A, long long lda, int ta, const float* B, long long ldb, int tb, float* C,
+                              long long ldc, int M, int N, int K, float alpha, int accumulate, void* stream) {
+  if (M <= 0 || N <= 0 || K <= 0) return MMB_ERR_ARG;
+  dim3 grid((N + 31) / 32, (M + 31) / 32), block(32, 32);
+  matmul_f32_kernel<<<grid, block, 0, reinterpret_cast<cudaStream_t>(stream)>>>(A, lda, ta, B, ldb, tb, C, ldc, M, N, K,
+                                                                               alpha, accumulate);
+  return (int)cudaGetLastError();
+}

@@ -1,0 +1,224 @@
+"""Typed Python wrappers over the C ABI (include/mmb200.h).
+
+PyTorch is used here for device memory and streams only: every function takes CUDA tensors, checks dtype /
+contiguity / device, and launches hand-written sm_100a kernels on ``torch.cuda.current_stream()``.  A CPU
+tensor, a missing library or a non-zero status raises — there is no eager / CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import MMBError
+
+EPI_BF16, EPI_BF16_ACT, EPI_BF16_DACT, EPI_F32 = 0, 1, 2, 3
+ACT_QUICK_GELU, ACT_GELU_ERF = 0, 1
+
+_NULL = ctypes.c_void_p(0)
+
+# When set to a list, every GEMM launch is bracketed by CUDA events on the launching stream and appended as
+# (algorithmic_flops, (a_mn, b_mn, epilogue), (start_event, end_event)) — used by bench.py for the live roofline.
+GEMM_TIMING = None
+
+
+def _p(t: Optional[torch.Tensor]):
+    return _NULL if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _chk(t: torch.Tensor, dtype, name: str):
+    if not t.is_cuda:
+        raise MMBError(f"{name}: expected a CUDA tensor (multimodal_b200 has no CPU path), got device {t.device}")
+    if t.dtype != dtype:
+        raise MMBError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+
+
+def _rowmajor(t: torch.Tensor, name: str):
+    if t.dim() != 2 or t.stride(1) != 1:
+        raise MMBError(f"{name}: expected a row-major 2-D tensor, got shape {tuple(t.shape)} stride {t.stride()}")
+
+
+def gemm(A, B, *, a_mn=False, b_mn=False, epilogue=EPI_BF16, out=None, out2=None, bias=None, aux=None, alpha=1.0,
+         act=ACT_QUICK_GELU, splits=1, accumulate=False):
+    """D = alpha * op(A) @ op(B)^T (+bias).  A: [M,K] (a_mn: stored [K,M]); B: [N,K] (b_mn: stored [K,N])."""
+    _chk(A, torch.bfloat16, "A"); _chk(B, torch.bfloat16, "B"); _rowmajor(A, "A"); _rowmajor(B, "B")
+    M, K = (A.shape[1], A.shape[0]) if a_mn else (A.shape[0], A.shape[1])
+    N, Kb = (B.shape[1], B.shape[0]) if b_mn else (B.shape[0], B.shape[1])
+    if K != Kb:
+        raise MMBError(f"gemm: contraction mismatch {K} vs {Kb}")
+    odt = torch.float32 if epilogue == EPI_F32 else torch.bfloat16
+    if out is None:
+        out = torch.empty((M, N), device=A.device, dtype=odt)
+    _chk(out, odt, "out"); _rowmajor(out, "out")
+    if tuple(out.shape) != (M, N):
+        raise MMBError(f"gemm: out shape {tuple(out.shape)} != {(M, N)}")
+    if epilogue == EPI_BF16_ACT:
+        if out2 is None:
+            out2 = torch.empty((M, N), device=A.device, dtype=torch.bfloat16)
+        _chk(out2, torch.bfloat16, "out2"); _rowmajor(out2, "out2")
+    if bias is not None:
+        _chk(bias, torch.float32, "bias")
+    if aux is not None:
+        _chk(aux, torch.bfloat16, "aux"); _rowmajor(aux, "aux")
+    ev = None
+    if GEMM_TIMING is not None:
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev[0].record()
+    rc = _lib.lib().mmb_gemm_bf16(_p(A), A.stride(0), int(a_mn), _p(B), B.stride(0), int(b_mn), _p(out), out.stride(0),
+                                  _p(out2), out2.stride(0) if out2 is not None else 0, M, N, K, epilogue, act,
+                                  float(alpha), _p(bias), _p(aux), aux.stride(0) if aux is not None else 0,
+                                  int(splits), int(accumulate), _stream())
+    _lib.check(rc, "mmb_gemm_bf16")
+    if ev is not None:
+        ev[1].record()
+        GEMM_TIMING.append((2.0 * M * N * K, (int(a_mn), int(b_mn), epilogue), ev))
+    return (out, out2) if epilogue == EPI_BF16_ACT else out
+
+
+def wgrad_splits(out_rows: int, out_cols: int, k: int, n_sms: int = 148) -> int:
+    """Split-K factor for a weight-gradient GEMM so that the tile count fills the machine."""
+    tiles = ((out_rows + 127) // 128) * ((out_cols + 255) // 256)
+    kb = (k + 63) // 64
+    if tiles >= n_sms:
+        return 1
+    best, best_eff = 1, 0.0
+    for s in range(1, min(kb, 64) + 1):
+        waves = -(-tiles * s // n_sms)
+        eff = tiles * s / (waves * n_sms)
+        if eff > best_eff + 1e-9 or (abs(eff - best_eff) < 1e-9 and s < best):
+            if kb // s >= 8:  # keep each split's main loop long enough to amortise the prologue
+                best, best_eff = s, eff
+    return best
+
+
+def cast_bf16(src: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _chk(src, torch.float32, "src")
+    if not src.is_contiguous():
+        raise MMBError("cast_bf16: src must be contiguous")
+    if out is None:
+        out = torch.empty(src.shape, device=src.device, dtype=torch.bfloat16)
+    _chk(out, torch.bfloat16, "out")
+    _lib.check(_lib.lib().mmb_cast_f32_to_bf16(_p(src), _p(out), src.numel(), _stream()), "mmb_cast_f32_to_bf16")
+    return out
+
+
+def im2col(img: torch.Tensor, ps: int, out: torch.Tensor) -> torch.Tensor:
+    _chk(img, torch.float32, "img"); _chk(out, torch.bfloat16, "out")
+    B, C, H, W = img.shape
+    _lib.check(_lib.lib().mmb_im2col_patches(_p(img), _p(out), B, H, W, ps, _stream()), "mmb_im2col_patches")
+    return out
+
+
+def add_layernorm_fwd(x_in, y, x_out, ln_bf16, ln_f32, gamma, beta, mean, rstd, M, d, eps, row_idx=None,
+                      rows_per_group=0):
+    _lib.check(_lib.lib().mmb_add_layernorm_fwd(_p(x_in), _p(y), _p(x_out), _p(ln_bf16), _p(ln_f32), _p(gamma), _p(beta),
+                                                _p(mean), _p(rstd), _p(row_idx), rows_per_group, M, d, float(eps),
+                                                _stream()), "mmb_add_layernorm_fwd")
+
+
+def vit_embed_ln_fwd(patch_out, cls, pos, gamma, beta, x0, mean, rstd, B, S, d, eps):
+    _lib.check(_lib.lib().mmb_vit_embed_ln_fwd(_p(patch_out), _p(cls), _p(pos), _p(gamma), _p(beta), _p(x0), _p(mean),
+                                               _p(rstd), B, S, d, float(eps), _stream()), "mmb_vit_embed_ln_fwd")
+
+
+def layernorm_bwd(x, dy_bf16, dy_f32, mean, rstd, gamma, g_in, g_out, g_bf16, dgamma, dbeta, M, d, row_idx=None,
+                  rows_per_group=0):
+    _lib.check(_lib.lib().mmb_layernorm_bwd(_p(x), _p(dy_bf16), _p(dy_f32), _p(mean), _p(rstd), _p(gamma), _p(g_in),
+                                            _p(g_out), _p(g_bf16), _p(dgamma), _p(dbeta), _p(row_idx), rows_per_group,
+                                            M, d, _stream()), "mmb_layernorm_bwd")
+
+
+def vit_embed_ln_bwd(patch_out, cls, pos, dy_f32, mean, rstd, gamma, dt_f32, dpatch_bf16, dgamma, dbeta, B, S, d):
+    _lib.check(_lib.lib().mmb_vit_embed_ln_bwd(_p(patch_out), _p(cls), _p(pos), _p(dy_f32), _p(mean), _p(rstd), _p(gamma),
+                                               _p(dt_f32), _p(dpatch_bf16), _p(dgamma), _p(dbeta), B, S, d, _stream()),
+               "mmb_vit_embed_ln_bwd")
+
+
+def batch_sum(inp, out, Bn, ld, n):
+    _lib.check(_lib.lib().mmb_batch_sum(_p(inp), _p(out), Bn, ld, n, _stream()), "mmb_batch_sum")
+
+
+def colsum_bf16(x, out, M, N, ld):
+    _lib.check(_lib.lib().mmb_colsum_bf16(_p(x), _p(out), M, N, ld, _stream()), "mmb_colsum_bf16")
+
+
+def text_embed_fwd(tokens, emb, pos, x, B, S, d, V):
+    _chk(tokens, torch.int64, "tokens")
+    _lib.check(_lib.lib().mmb_text_embed_fwd(_p(tokens), _p(emb), _p(pos), _p(x), B, S, d, V, _stream()), "mmb_text_embed_fwd")
+
+
+def text_embed_bwd(tokens, g, demb, B, S, d):
+    _lib.check(_lib.lib().mmb_text_embed_bwd(_p(tokens), _p(g), _p(demb), B, S, d, _stream()), "mmb_text_embed_bwd")
+
+
+def argmax_tokens(tokens, idx, B, S):
+    _chk(tokens, torch.int64, "tokens"); _chk(idx, torch.int32, "idx")
+    _lib.check(_lib.lib().mmb_argmax_tokens(_p(tokens), _p(idx), B, S, _stream()), "mmb_argmax_tokens")
+
+
+def l2norm_fwd(x, y, y_bf16, inv_norm, B, E, eps=1e-12):
+    _lib.check(_lib.lib().mmb_l2norm_fwd(_p(x), _p(y), _p(y_bf16), _p(inv_norm), B, E, float(eps), _stream()), "mmb_l2norm_fwd")
+
+
+def l2norm_bwd(dy, y, inv_norm, dx, dx_bf16, B, E):
+    _lib.check(_lib.lib().mmb_l2norm_bwd(_p(dy), _p(y), _p(inv_norm), _p(dx), _p(dx_bf16), B, E, _stream()), "mmb_l2norm_bwd")
+
+
+def adamw_step(p, g, m, v, p_bf16, n, lr, beta1, beta2, eps, wd, step, grad_scale=1.0, zero_grad=True):
+    _lib.check(_lib.lib().mmb_adamw_step(_p(p), _p(g), _p(m), _p(v), _p(p_bf16), n, lr, beta1, beta2, eps, wd, step,
+                                         grad_scale, int(zero_grad), _stream()), "mmb_adamw_step")
+
+
+def zero_(t: torch.Tensor):
+    if not t.is_cuda or not t.is_contiguous():
+        raise MMBError("zero_: expected a contiguous CUDA tensor")
+    _lib.check(_lib.lib().mmb_memset_async(_p(t), 0, t.numel() * t.element_size(), _stream()), "mmb_memset_async")
+    return t
+
+
+def attention_fwd(qkv, out, lse, B, S, H, causal, scale):
+    _chk(qkv, torch.bfloat16, "qkv"); _chk(out, torch.bfloat16, "out")
+    _lib.check(_lib.lib().mmb_attention_fwd(_p(qkv), _p(out), _p(lse), B, S, H, 64, int(causal), float(scale), _stream()),
+               "mmb_attention_fwd")
+
+
+def attention_bwd(qkv, out, dout, lse, dqkv, B, S, H, causal, scale):
+    _lib.check(_lib.lib().mmb_attention_bwd(_p(qkv), _p(out), _p(dout), _p(lse), _p(dqkv), B, S, H, 64, int(causal),
+                                            float(scale), _stream()), "mmb_attention_bwd")
+
+
+def contrastive_ce(sims, logit_scale, rows, N, label_offset, smoothing, loss_weight, row_loss, dsims_bf16, dsims_f32,
+                   dscale_accum, logits_out=None):
+    _chk(sims, torch.float32, "sims")
+    d = dsims_bf16 if dsims_bf16 is not None else dsims_f32
+    if dsims_bf16 is not None and dsims_f32 is not None and dsims_bf16.stride(0) != dsims_f32.stride(0):
+        raise MMBError("contrastive_ce: dsims_bf16 and dsims_f32 must share the leading dimension")
+    _lib.check(_lib.lib().mmb_contrastive_ce(_p(sims), sims.stride(0), _p(logit_scale), rows, N, label_offset,
+                                             float(smoothing), float(loss_weight), _p(row_loss), _p(dsims_bf16),
+                                             _p(dsims_f32), d.stride(0) if d is not None else 0, _p(dscale_accum),
+                                             _p(logits_out), logits_out.stride(0) if logits_out is not None else 0,
+                                             _stream()), "mmb_contrastive_ce")
+
+
+def sum_scale(inp, n, scale, out, accumulate=False):
+    _lib.check(_lib.lib().mmb_sum_scale(_p(inp), n, float(scale), _p(out), int(accumulate), _stream()), "mmb_sum_scale")
+
+
+def matmul_f32(A, B, *, ta=False, tb=False, out=None, alpha=1.0, accumulate=False):
+    """fp32 SIMT matmul (tiny / unaligned shapes).  C = alpha * op(A) @ op(B); ta: A stored [K,M]; tb: B stored [N,K]."""
+    _chk(A, torch.float32, "A"); _chk(B, torch.float32, "B"); _rowmajor(A, "A"); _rowmajor(B, "B")
+    M, K = (A.shape[1], A.shape[0]) if ta else (A.shape[0], A.shape[1])
+    N, Kb = (B.shape[0], B.shape[1]) if tb else (B.shape[1], B.shape[0])
+    if K != Kb:
+        raise MMBError(f"matmul_f32: contraction mismatch {K} vs {Kb}")
+    if out is None:
+        out = torch.empty((M, N), device=A.device, dtype=torch.float32)
+    _lib.check(_lib.lib().mmb_matmul_f32(_p(A), A.stride(0), int(ta), _p(B), B.stride(0), int(tb), _p(out), out.stride(0),
+                                         M, N, K, float(alpha), int(accumulate), _stream()), "mmb_matmul_f32")
+    return out

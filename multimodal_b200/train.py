@@ -1,0 +1,143 @@
+"""Data-parallel contrastive pre-training step: CLIP forward -> fused loss -> backward -> gradient all-reduce (NCCL,
+overlapped with the backward) -> fused AdamW, driven without autograd (the explicit schedules in engine.py).
+
+Mirrors the caller pattern of the reference's only plain-PyTorch loop, examples/flava/native/train.py:263-357
+(zero_grad -> autocast forward -> loss -> backward [DDP all-reduce overlaps] -> optimizer.step), with
+torch.optim.AdamW's update rule.  One process per GPU; NCCL is used for the gradient all-reduce only.
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+import torch.distributed as dist
+
+from . import ops
+from ._lib import MMBError
+from .engine import ParamStore
+from .engine_loss import _dist_state, _single_process
+from .utils.distributed import BackpropType
+
+
+class _FlatAdamW:
+    def __init__(self, store: ParamStore, lr, betas, eps, weight_decay):
+        store.flatten_()
+        self.store = store
+        self.m = torch.zeros_like(store.master)
+        self.v = torch.zeros_like(store.master)
+        self.lr, self.betas, self.eps, self.wd = lr, betas, eps, weight_decay
+        self.t = 0
+
+    def step(self, grad_scale: float):
+        st = self.store
+        self.t += 1
+        ops.adamw_step(st.master, st.g, self.m, self.v, st.wb, st.total, self.lr, self.betas[0], self.betas[1], self.eps,
+                       self.wd, self.t, grad_scale, True)
+        st._shadow_fresh = True  # the kernel wrote the bf16 shadow of the updated weights
+
+
+class ContrastiveTrainer:
+    """model: multimodal_b200 CLIP (ViT image tower + text tower); loss_module: ContrastiveLossWithTemperature."""
+
+    def __init__(self, model, loss_module, lr: float = 5e-4, betas=(0.9, 0.98), eps: float = 1e-6,
+                 weight_decay: float = 0.2, label_smoothing: float = 0.0,
+                 backprop_type: BackpropType = BackpropType.GLOBAL, grad_chunks: int = 3):
+        self.model, self.loss_module = model, loss_module
+        self.img = model.encoder_a._runtime()
+        self.txt = model.encoder_b._runtime()
+        self.world, self.rank = _dist_state()
+        self.opt_img = _FlatAdamW(self.img.store, lr, betas, eps, weight_decay)
+        self.opt_txt = _FlatAdamW(self.txt.store, lr, betas, eps, weight_decay)
+        dev = self.img.store.device
+        # logit_scale: a single fp32 scalar with its own (tiny) flat store; no weight decay (CLIP convention)
+        self.ls = loss_module.logit_scale
+        self.ls_buf = torch.zeros(4, device=dev, dtype=torch.float32)   # [value, pad...] 16 B aligned for the kernels
+        self.ls_g = torch.zeros(4, device=dev, dtype=torch.float32)
+        self.ls_m = torch.zeros(4, device=dev, dtype=torch.float32)
+        self.ls_v = torch.zeros(4, device=dev, dtype=torch.float32)
+        self.ls_t = 0
+        self.lr, self.betas, self.eps = lr, betas, eps
+        self.smoothing = label_smoothing
+        self.backprop_type = backprop_type
+        self.grad_chunks = max(1, grad_chunks)
+        self._works: List = []
+        self.kernel_launches = 0
+
+    # -- gradient all-reduce (NCCL) ------------------------------------------------------------------------
+    def _allreduce(self, t: torch.Tensor):
+        if self.world > 1:
+            self._works.append(dist.all_reduce(t, op=dist.ReduceOp.SUM, async_op=True))
+
+    def _layer_boundaries(self, tower) -> List[int]:
+        """Flat-buffer offsets at which the layer groups used for chunked all-reduce start."""
+        st, layers = tower.store, tower.stack.layers
+        L = len(layers)
+        idx = sorted({(L * i) // self.grad_chunks for i in range(1, self.grad_chunks)})
+        return [st.off[id(next(layers[i].parameters()))] for i in idx if 0 < i < L]
+
+    def step(self, image: torch.Tensor, text: torch.Tensor) -> torch.Tensor:
+        """One optimisation step on this rank's micro-batch; returns the (device) loss of this rank."""
+        img, txt = self.img, self.txt
+        dev = image.device
+        f32 = torch.float32
+        B = image.shape[0]
+        # reference: logit_scale.data.clamp_ every forward (contrastive_loss_with_temperature.py:193)
+        self.ls.data.clamp_(self.loss_module.logit_scale_min, self.loss_module.logit_scale_max)
+        self.ls_buf[0:1].copy_(self.ls.data.reshape(1))
+        # ---------------- forward ----------------
+        ea = img.forward(image, True)
+        eb = txt.forward(text, True)
+        E = ea.shape[1]
+        na, nb = torch.empty_like(ea), torch.empty_like(eb)
+        ia, ib = torch.empty(B, device=dev, dtype=f32), torch.empty(B, device=dev, dtype=f32)
+        ops.l2norm_fwd(ea, na, None, ia, B, E)
+        ops.l2norm_fwd(eb, nb, None, ib, B, E)
+        if self.world > 1:
+            from .symm import distributed_contrastive
+            res = distributed_contrastive(na, nb, self.ls_buf[0:1], self.smoothing, self.backprop_type, False, self.world,
+                                          self.rank)
+        else:
+            res = _single_process(na, nb, self.ls_buf[0:1], self.smoothing, False)
+        loss, _, _, _, _, dA, dB, dS = res
+        # ---------------- backward ----------------
+        dea, deb = torch.empty_like(ea), torch.empty_like(eb)
+        ops.l2norm_bwd(dA, na, ia, dea, None, B, E)
+        ops.l2norm_bwd(dB, nb, ib, deb, None, B, E)
+        self._works = []
+        txt.backward(deb)
+        self._allreduce(txt.store.g)                      # overlaps with the image tower's backward
+        bounds = self._layer_boundaries(img) if self.world > 1 else []
+        if bounds:
+            st = img.store
+            cuts = bounds + [st.total]
+            state = {"hi": len(cuts) - 1}
+
+            def on_layer_done(l, _st=st, _cuts=cuts, _state=state, _layers=img.stack.layers):
+                # layer l finished: every parameter at or after layer l's first offset that belongs to finished
+                # layers is final; flush the highest unfinished chunk when we cross its lower boundary.
+                off = _st.off[id(next(_layers[l].parameters()))]
+                while _state["hi"] >= 1 and off <= _cuts[_state["hi"] - 1]:
+                    lo, hi = _cuts[_state["hi"] - 1], _cuts[_state["hi"]]
+                    self._allreduce(_st.g[lo:hi])
+                    _state["hi"] -= 1
+
+            img.layer_done_cb = on_layer_done
+            img.backward(dea)
+            img.layer_done_cb = None
+            self._allreduce(st.g[0:cuts[0]])
+        else:
+            img.backward(dea)
+            self._allreduce(img.store.g)
+        self.ls_g[0:1].copy_(dS.reshape(1))
+        self._allreduce(self.ls_g)
+        for w in self._works:
+            w.wait()
+        # ---------------- optimizer ----------------
+        gs = 1.0 / self.world
+        self.opt_img.step(gs)
+        self.opt_txt.step(gs)
+        self.ls_t += 1
+        ops.adamw_step(self.ls_buf, self.ls_g, self.ls_m, self.ls_v, None, 4, self.lr, self.betas[0], self.betas[1],
+                       self.eps, 0.0, self.ls_t, gs, True)
+        self.ls.data.copy_(self.ls_buf[0])
+        return loss

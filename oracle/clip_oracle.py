@@ -1,0 +1,164 @@
+"""ORACLE (test infrastructure — never imported by the product path).
+
+A plain fp32 PyTorch restatement, op by op, of the reference's dual-encoder forward + contrastive loss.  It takes a
+reference-format ``state_dict`` (same key names / shapes as ``torchmultimodal.models.clip.model.CLIP``) and raw
+inputs, and uses only elementary tensor ops (matmul, softmax, mean/var, gather) so that every step can be read
+against the reference line it restates.  Gradients come from autograd over these elementary ops.
+
+Pinned (tests/test_oracle_cpu.py) against:
+  * golden vectors produced by importing the UNMODIFIED reference from /root/reference in the build container
+    (tests/golden/make_golden.py -> tests/golden/*.pt), and
+  * the reference's own known-answer tests (values quoted in the test file with their file:line).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this module.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional, Tuple
+
+import torch
+
+Tensor = torch.Tensor
+
+
+def layer_norm(x: Tensor, w: Tensor, b: Tensor, eps: float = 1e-5) -> Tensor:
+    """F.layer_norm over the last dim (biased variance, eps inside sqrt).
+    Restates: torch/nn/functional.py layer_norm as called by torch/nn/modules/transformer.py:946,951 (norm1/norm2)
+    and torchmultimodal/modules/layers/normalizations.py:17-25 (Fp32LayerNorm: same math in fp32)."""
+    mu = x.mean(dim=-1, keepdim=True)
+    var = ((x - mu) ** 2).mean(dim=-1, keepdim=True)
+    return (x - mu) / torch.sqrt(var + eps) * w + b
+
+
+def quick_gelu(x: Tensor) -> Tensor:
+    """torchmultimodal/modules/layers/activation.py:24-25 ('SiLU' == QuickGELU): sigmoid(1.702 x) * x."""
+    return torch.sigmoid(1.702 * x) * x
+
+
+def mha(x: Tensor, sd: Dict[str, Tensor], pfx: str, heads: int, causal: bool) -> Tensor:
+    """Self-attention block. x: [B,S,d].
+    Restates torch/nn/functional.py:6244 multi_head_attention_forward: packed in-projection (:6478), per-head
+    softmax(q k^T / sqrt(dh)) v (:6682, causal mask when is_causal), out-projection (:6690)."""
+    B, S, d = x.shape
+    dh = d // heads
+    qkv = x @ sd[pfx + "self_attn.in_proj_weight"].t() + sd[pfx + "self_attn.in_proj_bias"]
+    q, k, v = qkv.split(d, dim=-1)
+    q = q.view(B, S, heads, dh).transpose(1, 2)
+    k = k.view(B, S, heads, dh).transpose(1, 2)
+    v = v.view(B, S, heads, dh).transpose(1, 2)
+    att = (q @ k.transpose(-1, -2)) / math.sqrt(dh)
+    if causal:
+        mask = torch.full((S, S), float("-inf"), device=x.device, dtype=x.dtype).triu(1)  # text_encoder.py:74-77
+        att = att + mask
+    att = torch.softmax(att, dim=-1)
+    o = (att @ v).transpose(1, 2).reshape(B, S, d)
+    return o @ sd[pfx + "self_attn.out_proj.weight"].t() + sd[pfx + "self_attn.out_proj.bias"]
+
+
+def encoder_layer(x: Tensor, sd: Dict[str, Tensor], pfx: str, heads: int, causal: bool) -> Tensor:
+    """Pre-norm layer: torch/nn/modules/transformer.py:946-951 (_sa_block :961-978, _ff_block :980-982)."""
+    h = layer_norm(x, sd[pfx + "norm1.weight"], sd[pfx + "norm1.bias"])
+    x = x + mha(h, sd, pfx, heads, causal)
+    h = layer_norm(x, sd[pfx + "norm2.weight"], sd[pfx + "norm2.bias"])
+    h = quick_gelu(h @ sd[pfx + "linear1.weight"].t() + sd[pfx + "linear1.bias"])
+    return x + (h @ sd[pfx + "linear2.weight"].t() + sd[pfx + "linear2.bias"])
+
+
+def _num_layers(sd: Dict[str, Tensor], pfx: str) -> int:
+    n = 0
+    while f"{pfx}encoder.layers.{n}.norm1.weight" in sd:
+        n += 1
+    return n
+
+
+def vit_encoder(image: Tensor, sd: Dict[str, Tensor], pfx: str, heads: int) -> Tensor:
+    """models/clip/image_encoder.py:82-113."""
+    w = sd[pfx + "conv.weight"]  # [width, 3, ps, ps]
+    width, _, ps, _ = w.shape
+    B, C, H, W = image.shape
+    if C != 3:
+        raise ValueError(f"Expected 3 channels found {C}")
+    gh, gw = H // ps, W // ps
+    # conv with stride == kernel == ps and no bias (:50-56,:91) == per-patch dot product, K order (c, kh, kw)
+    patches = image.view(B, C, gh, ps, gw, ps).permute(0, 2, 4, 1, 3, 5).reshape(B, gh * gw, C * ps * ps)
+    x = patches @ w.reshape(width, -1).t()                                    # flatten(2).permute(0,2,1) :94-97
+    cls = sd[pfx + "cls_token_embedding"].expand(B, 1, width)
+    x = torch.cat([cls, x], dim=1) + sd[pfx + "positional_embedding"]         # :98-105
+    x = layer_norm(x, sd[pfx + "ln_pre.weight"], sd[pfx + "ln_pre.bias"])    # :106
+    for l in range(_num_layers(sd, pfx)):                                     # :108
+        x = encoder_layer(x, sd, f"{pfx}encoder.layers.{l}.", heads, causal=False)
+    x = layer_norm(x[:, 0, :], sd[pfx + "ln_post.weight"], sd[pfx + "ln_post.bias"])  # :111
+    return x @ sd[pfx + "projection"]                                         # :112
+
+
+def text_encoder(text: Tensor, sd: Dict[str, Tensor], pfx: str, heads: int, return_hidden_state: bool = False) -> Tensor:
+    """models/clip/text_encoder.py:113-134."""
+    pos = sd[pfx + "positional_embedding"]
+    if text.shape[1] != pos.shape[0]:
+        raise ValueError(f"length of input should be {pos.shape[0]} but found {text.shape[1]}")
+    x = sd[pfx + "token_embedding.weight"][text] + pos                        # :118-119
+    for l in range(_num_layers(sd, pfx)):                                     # :121 (causal)
+        x = encoder_layer(x, sd, f"{pfx}encoder.layers.{l}.", heads, causal=True)
+    hs = layer_norm(x, sd[pfx + "ln_final.weight"], sd[pfx + "ln_final.bias"])  # :125
+    if return_hidden_state:
+        return hs
+    eot = text.argmax(dim=-1)                                                 # :130-132 (first maximum)
+    return hs[torch.arange(hs.shape[0], device=hs.device), eot] @ sd[pfx + "projection.weight"].t()
+
+
+def normalize(x: Tensor, eps: float = 1e-12) -> Tensor:
+    """F.normalize(x) as used at models/clip/model.py:72-73: x / max(||x||_2, eps) along dim=1."""
+    return x / x.norm(dim=1, keepdim=True).clamp_min(eps)
+
+
+def clip_forward(image: Tensor, text: Tensor, sd: Dict[str, Tensor], img_heads: int, txt_heads: int) -> Tuple[Tensor, Tensor]:
+    """models/clip/model.py:65-74."""
+    a = vit_encoder(image, sd, "encoder_a.", img_heads)
+    b = text_encoder(text, sd, "encoder_b.", txt_heads)
+    return normalize(a), normalize(b)
+
+
+def cross_entropy(logits: Tensor, labels: Tensor, label_smoothing: float = 0.0) -> Tensor:
+    """F.cross_entropy(reduction='mean') incl. label smoothing, from log-softmax."""
+    lsm = logits - torch.logsumexp(logits, dim=-1, keepdim=True)
+    nll = -lsm.gather(1, labels.view(-1, 1)).squeeze(1)
+    smooth = -lsm.mean(dim=-1)
+    return ((1.0 - label_smoothing) * nll + label_smoothing * smooth).mean()
+
+
+def contrastive_loss(a: Tensor, b: Tensor, logit_scale: Tensor, a_all: Optional[Tensor] = None,
+                     b_all: Optional[Tensor] = None, rank: int = 0, label_smoothing: float = 0.0):
+    """modules/losses/contrastive_loss_with_temperature.py:50-115.  a_all / b_all are the (already gathered,
+    concatenated in rank order) global embeddings; None means single process (:31-33)."""
+    T = torch.exp(logit_scale)                                                # :81
+    a_all = a if a_all is None else a_all
+    b_all = b if b_all is None else b_all
+    labels = a.shape[0] * rank + torch.arange(a.shape[0], device=a.device)    # :39-41
+    logits_a = a @ b_all.t() * T                                              # :90-92
+    logits_b = b @ a_all.t() * T                                              # :93-95
+    loss_a = cross_entropy(logits_a, labels, label_smoothing)                 # :105
+    loss_b = cross_entropy(logits_b, labels, label_smoothing)                 # :106
+    return (loss_a + loss_b) / 2, logits_a, logits_b, loss_a, loss_b          # :107-115
+
+
+def clamp_logit_scale(logit_scale: Tensor, lo: Optional[float] = math.log(1), hi: Optional[float] = math.log(100)) -> Tensor:
+    """ContrastiveLossWithTemperature.forward clamps .data in place each call (:193)."""
+    return logit_scale.clamp(lo, hi)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Synthetic inputs of SURVEY.md §8(d)
+# ----------------------------------------------------------------------------------------------------------------
+def synthetic_batch(B: int, rank: int = 0, image_size: int = 224, ctx: int = 77, vocab: int = 49408,
+                    device: str = "cpu") -> Tuple[Tensor, Tensor]:
+    g = torch.Generator(device="cpu").manual_seed(1234 + rank)
+    img = torch.randn(B, 3, image_size, image_size, generator=g)
+    txt = torch.randint(1, vocab - 2, (B, ctx), generator=g)
+    txt[:, -1] = vocab - 1  # EOT is the unique maximum
+    return img.to(device), txt.to(device)
+
+
+def bf16_round_(sd: Dict[str, Tensor]) -> Dict[str, Tensor]:
+    """Round float tensors to bf16-representable fp32 (parity runs: removes operand-rounding as an error source)."""
+    return {k: (v.bfloat16().float() if v.is_floating_point() else v) for k, v in sd.items()}
