@@ -110,18 +110,42 @@ int mmb_attention_bwd(const void* qkv, const void* out, const void* dout, const 
                       int H, int head_dim, int causal, float scale, void* stream);
 
 /* ---- contrastive loss -------------------------------------------------------------------------------------- */
-/* One direction of contrastive_loss_with_temperature (modules/losses/contrastive_loss_with_temperature.py:81-107):
- * logits = exp(*logit_scale) * sims; row_loss[i] = CE(logits[i], label_offset + i) with label smoothing;
- * dsims (bf16 and/or fp32, same leading dim) = d(loss_weight * mean_i row_loss)/d sims; *dscale_accum += same w.r.t. logit_scale. */
-int mmb_contrastive_ce(const float* sims, long long ld, const float* logit_scale, int rows, int N, int label_offset,
-                       float label_smoothing, float loss_weight, float* row_loss, void* dsims_bf16, float* dsims_f32,
-                       long long ld_d, float* dscale_accum, float* logits_out, long long ld_l, void* stream);
+/* One direction of contrastive_loss_with_temperature (modules/losses/contrastive_loss_with_temperature.py:81-107),
+ * rows = this rank's batch, N = global batch, label(i) = label_offset + i (:39-41).
+ * stats: logits = exp(*logit_scale) * sims; row_loss[i] = CE(logits[i], label) with label smoothing; lse_out[i];
+ *        *dscale_accum += d(loss_weight * mean_i row_loss)/d logit_scale; optional logits output.
+ * grad : dsims (bf16 and/or fp32, leading dim ld_d) = d(loss_weight * sum over ALL ranks of mean row_loss)/d sims of
+ *        this rank's row block: the own-direction softmax term plus, for columns [col_lo, col_hi), the transposed
+ *        other-direction term rebuilt from the peers' row-LSE vector lse_col[N] — this replaces the reduce-scatter
+ *        of torch.distributed.nn.functional.all_gather's backward (utils/distributed.py:47-48).
+ *        GLOBAL backprop: [0,N); LOCAL: own block; NONE: lse_col = NULL. */
+int mmb_contrastive_ce_stats(const float* sims, long long ld, const float* logit_scale, int rows, int N,
+                             int label_offset, float label_smoothing, float loss_weight, float* row_loss,
+                             float* lse_out, float* dscale_accum, float* logits_out, long long ld_l, void* stream);
+int mmb_contrastive_ce_grad(const float* sims, long long ld, const float* logit_scale, int rows, int N,
+                            int label_offset, float label_smoothing, float loss_weight, const float* lse_row,
+                            const float* lse_col, int col_lo, int col_hi, void* dsims_bf16, float* dsims_f32,
+                            long long ld_d, void* stream);
 /* fp32 SIMT matmul for tiny / unaligned shapes the tensor-core path rejects: C (+)= alpha*op(A)op(B);
  * ta: A stored [K,M]; tb: B stored [N,K]. */
 int mmb_matmul_f32(const float* A, long long lda, int ta, const float* B, long long ldb, int tb, float* C,
                    long long ldc, int M, int N, int K, float alpha, int accumulate, void* stream);
 /* out[0] (+)= scale * sum(in[0..n)) — deterministic */
 int mmb_sum_scale(const float* in, int n, float scale, float* out, int accumulate, void* stream);
+
+
+/* ---- symmetric (CUDA-IPC peer-mapped) memory: the loss path's replacement for NCCL all_gather ----------------- */
+/* Replaces torch.distributed(.nn.functional).all_gather at utils/distributed.py:47-52: every rank allocates one
+ * buffer, exchanges the 64-byte IPC handles once (host side, any transport), maps the peers' buffers, and the
+ * kernels read peer memory directly over NVLink.  handle64 / ptr / peer_ptr are HOST pointers to host variables. */
+int mmb_symm_alloc(long long bytes, void** ptr);
+int mmb_symm_free(void* ptr);
+int mmb_symm_get_handle(void* ptr, void* handle64);
+int mmb_symm_open_handle(const void* handle64, void** peer_ptr);
+int mmb_symm_close_handle(void* peer_ptr);
+/* Cross-GPU barrier on `stream`: release-store `value` into slot [rank] of every peer's flag array, then wait until
+ * all `world` slots of my_flags are >= value.  peer_flags is a DEVICE array of `world` device pointers. */
+int mmb_symm_signal_wait(void* const* peer_flags, void* my_flags, int rank, int world, int value, void* stream);
 
 #ifdef __cplusplus
 }

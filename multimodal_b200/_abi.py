@@ -25,8 +25,15 @@ PROTOTYPES = {
     "mmb_memset_async": (i32, [vp, i32, ll, vp]),
     "mmb_attention_fwd": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, f32, vp]),
     "mmb_attention_bwd": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, vp]),
-    "mmb_contrastive_ce": (i32, [vp, ll, vp, i32, i32, i32, f32, f32, vp, vp, vp, ll, vp, vp, ll, vp]),
+    "mmb_contrastive_ce_stats": (i32, [vp, ll, vp, i32, i32, i32, f32, f32, vp, vp, vp, vp, ll, vp]),
+    "mmb_contrastive_ce_grad": (i32, [vp, ll, vp, i32, i32, i32, f32, f32, vp, vp, i32, i32, vp, vp, ll, vp]),
     "mmb_matmul_f32": (i32, [vp, ll, i32, vp, ll, i32, vp, ll, i32, i32, i32, f32, i32, vp]),
+    "mmb_symm_alloc": (i32, [ll, vp]),
+    "mmb_symm_free": (i32, [vp]),
+    "mmb_symm_get_handle": (i32, [vp, vp]),
+    "mmb_symm_open_handle": (i32, [vp, vp]),
+    "mmb_symm_close_handle": (i32, [vp]),
+    "mmb_symm_signal_wait": (i32, [vp, vp, i32, i32, i32, vp]),
     "mmb_sum_scale": (i32, [vp, i32, f32, vp, i32, vp]),
 }
 

@@ -212,103 +212,120 @@ struct LnBwdArgs {
   int M, d;
 };
 
-template <bool VIT>
-__global__ void ln_bwd_kernel(const LnBwdArgs a) {
+template <bool VIT, int NV>
+__global__ void __launch_bounds__(NV <= 4 ? 256 : 384, NV <= 4 ? 2 : 1) ln_bwd_kernel(const LnBwdArgs a) {
   extern __shared__ float sred[];  // [2][d]
-  const int d = a.d, nv = d >> 7;
+  constexpr int d = NV * 128;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int wpb = blockDim.x >> 5;
   for (int i = threadIdx.x; i < 2 * d; i += blockDim.x) sred[i] = 0.f;
   __syncthreads();
-  float4 accg[LN_MAX_NV], accb[LN_MAX_NV];
+  float4 accg[NV], accb[NV];
 #pragma unroll
-  for (int i = 0; i < LN_MAX_NV; ++i) { accg[i] = make_float4(0.f, 0.f, 0.f, 0.f); accb[i] = accg[i]; }
+  for (int i = 0; i < NV; ++i) { accg[i] = make_float4(0.f, 0.f, 0.f, 0.f); accb[i] = accg[i]; }
 
   for (int m = blockIdx.x * wpb + wib; m < a.M; m += gridDim.x * wpb) {
     long long phys = m;
     if (a.rows_per_group > 0) phys = (long long)m * a.rows_per_group + (a.row_idx ? a.row_idx[m] : 0);
     const float mean = a.mean[m], rstd = a.rstd[m];
-    float4 xh[LN_MAX_NV], dy[LN_MAX_NV];
+    float4 xh[NV], dy[NV];
+    // issue the x / dy loads of the whole row up front (2*NV independent 16 B loads per lane in flight)
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      if (VIT) {
+        const int b = m / a.S, s = m - b * a.S;
+        float4 x = __ldg(reinterpret_cast<const float4*>(a.pos + (long long)s * d + c));
+        if (s == 0) {
+          const float4 t = __ldg(reinterpret_cast<const float4*>(a.cls + c));
+          x.x += t.x; x.y += t.y; x.z += t.z; x.w += t.w;
+        } else {
+          const uint2 u = *reinterpret_cast<const uint2*>(a.patch_out + ((long long)b * (a.S - 1) + (s - 1)) * d + c);
+          x.x += bf16_lo(u.x); x.y += bf16_hi(u.x); x.z += bf16_lo(u.y); x.w += bf16_hi(u.y);
+        }
+        xh[i] = x;
+      } else {
+        xh[i] = *reinterpret_cast<const float4*>(a.x + (long long)m * d + c);  // compact in gather mode
+      }
+      if (a.dy_bf16) {
+        const uint2 u = *reinterpret_cast<const uint2*>(a.dy_bf16 + (long long)m * d + c);
+        dy[i] = make_float4(bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y));
+      } else {
+        dy[i] = *reinterpret_cast<const float4*>(a.dy_f32 + (long long)m * d + c);
+      }
+    }
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int i = 0; i < LN_MAX_NV; ++i)
-      if (i < nv) {
-        const int c = (i * 32 + lane) * 4;
-        float4 x;
-        if (VIT) {
-          const int b = m / a.S, s = m - b * a.S;
-          x = __ldg(reinterpret_cast<const float4*>(a.pos + (long long)s * d + c));
-          if (s == 0) {
-            const float4 t = __ldg(reinterpret_cast<const float4*>(a.cls + c));
-            x.x += t.x; x.y += t.y; x.z += t.z; x.w += t.w;
-          } else {
-            const uint2 u = *reinterpret_cast<const uint2*>(a.patch_out + ((long long)b * (a.S - 1) + (s - 1)) * d + c);
-            x.x += bf16_lo(u.x); x.y += bf16_hi(u.x); x.z += bf16_lo(u.y); x.w += bf16_hi(u.y);
-          }
-        } else {
-          x = *reinterpret_cast<const float4*>(a.x + (long long)m * d + c);  // compact in gather mode
-        }
-        float4 g4;
-        if (a.dy_bf16) {
-          const uint2 u = *reinterpret_cast<const uint2*>(a.dy_bf16 + (long long)m * d + c);
-          g4 = make_float4(bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y));
-        } else {
-          g4 = *reinterpret_cast<const float4*>(a.dy_f32 + (long long)m * d + c);
-        }
-        const float4 gm = __ldg(reinterpret_cast<const float4*>(a.gamma + c));
-        float4 h;
-        h.x = (x.x - mean) * rstd; h.y = (x.y - mean) * rstd; h.z = (x.z - mean) * rstd; h.w = (x.w - mean) * rstd;
-        accg[i].x += g4.x * h.x; accg[i].y += g4.y * h.y; accg[i].z += g4.z * h.z; accg[i].w += g4.w * h.w;
-        accb[i].x += g4.x; accb[i].y += g4.y; accb[i].z += g4.z; accb[i].w += g4.w;
-        g4.x *= gm.x; g4.y *= gm.y; g4.z *= gm.z; g4.w *= gm.w;  // dy * gamma
-        s1 += g4.x + g4.y + g4.z + g4.w;
-        s2 += g4.x * h.x + g4.y * h.y + g4.z * h.z + g4.w * h.w;
-        xh[i] = h; dy[i] = g4;
-      }
-    s1 = warp_sum(s1) / d;
-    s2 = warp_sum(s2) / d;
-#pragma unroll
-    for (int i = 0; i < LN_MAX_NV; ++i)
-      if (i < nv) {
-        const int c = (i * 32 + lane) * 4;
-        float4 o;
-        o.x = rstd * (dy[i].x - s1 - xh[i].x * s2);
-        o.y = rstd * (dy[i].y - s1 - xh[i].y * s2);
-        o.z = rstd * (dy[i].z - s1 - xh[i].z * s2);
-        o.w = rstd * (dy[i].w - s1 - xh[i].w * s2);
-        if (a.g_in) {
-          const float4 gi = *reinterpret_cast<const float4*>(a.g_in + phys * d + c);
-          o.x += gi.x; o.y += gi.y; o.z += gi.z; o.w += gi.w;
-        }
-        if (a.g_out) *reinterpret_cast<float4*>(a.g_out + phys * d + c) = o;
-        if (a.g_bf16) {
-          uint2 u;
-          u.x = pack_bf16x2(o.x, o.y);
-          u.y = pack_bf16x2(o.z, o.w);
-          if (VIT) {  // bf16 gradient of the patch-embedding GEMM output: compact [B*(S-1), d], CLS row dropped
-            const int b = m / a.S, sidx = m - b * a.S;
-            if (sidx > 0) *reinterpret_cast<uint2*>(a.g_bf16 + ((long long)b * (a.S - 1) + (sidx - 1)) * d + c) = u;
-          } else {
-            *reinterpret_cast<uint2*>(a.g_bf16 + phys * d + c) = u;
-          }
-        }
-      }
-  }
-  // block reduction of dgamma / dbeta partials, then one atomic per column per block
-#pragma unroll
-  for (int i = 0; i < LN_MAX_NV; ++i)
-    if (i < nv) {
+    for (int i = 0; i < NV; ++i) {
       const int c = (i * 32 + lane) * 4;
-      atomicAdd(&sred[c + 0], accg[i].x); atomicAdd(&sred[c + 1], accg[i].y);
-      atomicAdd(&sred[c + 2], accg[i].z); atomicAdd(&sred[c + 3], accg[i].w);
-      atomicAdd(&sred[d + c + 0], accb[i].x); atomicAdd(&sred[d + c + 1], accb[i].y);
-      atomicAdd(&sred[d + c + 2], accb[i].z); atomicAdd(&sred[d + c + 3], accb[i].w);
+      const float4 gm = __ldg(reinterpret_cast<const float4*>(a.gamma + c));
+      float4 h, g4 = dy[i];
+      h.x = (xh[i].x - mean) * rstd; h.y = (xh[i].y - mean) * rstd;
+      h.z = (xh[i].z - mean) * rstd; h.w = (xh[i].w - mean) * rstd;
+      accg[i].x += g4.x * h.x; accg[i].y += g4.y * h.y; accg[i].z += g4.z * h.z; accg[i].w += g4.w * h.w;
+      accb[i].x += g4.x; accb[i].y += g4.y; accb[i].z += g4.z; accb[i].w += g4.w;
+      g4.x *= gm.x; g4.y *= gm.y; g4.z *= gm.z; g4.w *= gm.w;  // dy * gamma
+      s1 += g4.x + g4.y + g4.z + g4.w;
+      s2 += g4.x * h.x + g4.y * h.y + g4.z * h.z + g4.w * h.w;
+      xh[i] = h; dy[i] = g4;
     }
+    s1 = warp_sum(s1) * (1.f / d);
+    s2 = warp_sum(s2) * (1.f / d);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      const float4 gi = a.g_in ? *reinterpret_cast<const float4*>(a.g_in + phys * d + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 o;
+      o.x = rstd * (dy[i].x - s1 - xh[i].x * s2) + gi.x;
+      o.y = rstd * (dy[i].y - s1 - xh[i].y * s2) + gi.y;
+      o.z = rstd * (dy[i].z - s1 - xh[i].z * s2) + gi.z;
+      o.w = rstd * (dy[i].w - s1 - xh[i].w * s2) + gi.w;
+      if (a.g_out) *reinterpret_cast<float4*>(a.g_out + phys * d + c) = o;
+      if (a.g_bf16) {
+        uint2 u;
+        u.x = pack_bf16x2(o.x, o.y);
+        u.y = pack_bf16x2(o.z, o.w);
+        if (VIT) {  // bf16 gradient of the patch-embedding GEMM output: compact [B*(S-1), d], CLS row dropped
+          const int b = m / a.S, sidx = m - b * a.S;
+          if (sidx > 0) *reinterpret_cast<uint2*>(a.g_bf16 + ((long long)b * (a.S - 1) + (sidx - 1)) * d + c) = u;
+        } else {
+          *reinterpret_cast<uint2*>(a.g_bf16 + phys * d + c) = u;
+        }
+      }
+    }
+  }
+  // block reduction of dgamma / dbeta partials, then one global
+  // atomic per column per block
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    atomicAdd(&sred[c + 0], accg[i].x); atomicAdd(&sred[c + 1], accg[i].y);
+    atomicAdd(&sred[c + 2], accg[i].z); atomicAdd(&sred[c + 3], accg[i].w);
+    atomicAdd(&sred[d + c + 0], accb[i].x); atomicAdd(&sred[d + c + 1], accb[i].y);
+    atomicAdd(&sred[d + c + 2], accb[i].z); atomicAdd(&sred[d + c + 3], accb[i].w);
+  }
   __syncthreads();
   for (int i = threadIdx.x; i < d; i += blockDim.x) {
     if (a.dgamma) atomicAdd(a.dgamma + i, sred[i]);
     if (a.dbeta) atomicAdd(a.dbeta + i, sred[d + i]);
   }
+}
+
+template <bool VIT>
+static int launch_ln_bwd(const LnBwdArgs& a, cudaStream_t st) {
+  const int nv = a.d >> 7;
+  const int threads = nv <= 4 ? 256 : 384;
+  int grid = num_sms() * (nv <= 4 ? 2 : 1);
+  const int wpb = threads / 32;
+  if (grid > (a.M + wpb - 1) / wpb) grid = (a.M + wpb - 1) / wpb;
+  const size_t sm = 2 * a.d * sizeof(float);
+  switch (nv) {
+#define LNB(NVV) case NVV: ln_bwd_kernel<VIT, NVV><<<grid, threads, sm, st>>>(a); break;
+    LNB(1) LNB(2) LNB(3) LNB(4) LNB(5) LNB(6) LNB(7) LNB(8)
+#undef LNB
+    default: return MMB_ERR_UNSUPPORTED;
+  }
+  return (int)cudaGetLastError();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -545,10 +562,7 @@ extern "C" int mmb_layernorm_bwd(const float* x, const void* dy_bf16, const floa
   a.x = x; a.dy_bf16 = (const __nv_bfloat16*)dy_bf16; a.dy_f32 = dy_f32; a.mean = mean; a.rstd = rstd; a.gamma = gamma;
   a.g_in = g_in; a.g_out = g_out; a.g_bf16 = (__nv_bfloat16*)g_bf16; a.dgamma = dgamma; a.dbeta = dbeta;
   a.row_idx = row_idx; a.rows_per_group = rows_per_group; a.M = M; a.d = d;
-  int grid = num_sms() * 4;
-  if (grid > (M + 7) / 8) grid = (M + 7) / 8;
-  ln_bwd_kernel<false><<<grid, 256, 2 * d * sizeof(float), ST(stream)>>>(a);
-  return LAUNCH_RC();
+  return launch_ln_bwd<false>(a, ST(stream));
 }
 
 extern "C" int mmb_vit_embed_ln_bwd(const void* patch_out, const float* cls, const float* pos, const float* dy_f32,
@@ -561,10 +575,7 @@ extern "C" int mmb_vit_embed_ln_bwd(const void* patch_out, const float* cls, con
   a.dy_f32 = dy_f32; a.mean = mean; a.rstd = rstd; a.gamma = gamma; a.g_out = dt_f32;
   a.g_bf16 = (__nv_bfloat16*)dpatch_bf16;
   a.dgamma = dgamma; a.dbeta = dbeta; a.M = B * S; a.d = d;
-  int grid = num_sms() * 4;
-  if (grid > (a.M + 7) / 8) grid = (a.M + 7) / 8;
-  ln_bwd_kernel<true><<<grid, 256, 2 * d * sizeof(float), ST(stream)>>>(a);
-  return LAUNCH_RC();
+  return launch_ln_bwd<true>(a, ST(stream));
 }
 
 extern "C" int mmb_batch_sum(const float* in, float* out, int Bn, long long ld, int n, void* stream) {

@@ -1,4 +1,4 @@
-// Temperature-scaled softmax cross-entropy over similarity rows, forward + gradient in one pass.
+// Temperature-scaled softmax cross-entropy over similarity rows: statistics pass + gradient pass.
 // Restates modules/losses/contrastive_loss_with_temperature.py:81-107 for one direction (a->b or b->a):
 //   logits = exp(logit_scale) * sims ; loss_i = CE(logits_i, label_i = label_offset + i) (+ label smoothing)
 // and emits d(mean loss * loss_weight)/d sims in bf16 (operand of the embedding-gradient GEMMs) plus the
@@ -29,11 +29,13 @@ __device__ __forceinline__ float block_reduce_sum(float v, float* red) {
   return r;
 }
 
-__global__ void contrastive_ce_kernel(const float* __restrict__ sims, long long ld, const float* __restrict__ logit_scale,
-                                      int rows, int N, int label_offset, float smoothing, float loss_weight,
-                                      float* __restrict__ row_loss, __nv_bfloat16* __restrict__ dsims,
-                                      float* __restrict__ dsims_f32, long long ld_d, float* __restrict__ dscale_accum, float* __restrict__ logits_out,
-                                      long long ld_l) {
+// Pass 1 (per local row i): logits = T * sims; row LSE; loss_i (with label smoothing); optional logits output;
+// d loss / d logit_scale accumulated (atomic).  label(i) = label_offset + i.
+__global__ void contrastive_ce_stats_kernel(const float* __restrict__ sims, long long ld,
+                                            const float* __restrict__ logit_scale, int rows, int N, int label_offset,
+                                            float smoothing, float loss_weight, float* __restrict__ row_loss,
+                                            float* __restrict__ lse_out, float* __restrict__ dscale_accum,
+                                            float* __restrict__ logits_out, long long ld_l) {
   __shared__ float red[32];
   const int i = blockIdx.x;
   if (i >= rows) return;
@@ -55,22 +57,50 @@ __global__ void contrastive_ce_kernel(const float* __restrict__ sims, long long 
   const float lse = mx + logf(se);
   const float l_label = T * srow[label];
   const float loss = (1.f - smoothing) * (lse - l_label) + smoothing * (lse - mean_logit);
-  if (threadIdx.x == 0 && row_loss) row_loss[i] = loss;
-  if (dsims || dsims_f32) {
-    const float gs = loss_weight / rows;
-    float ds_acc = 0.f;
+  if (threadIdx.x == 0) {
+    if (row_loss) row_loss[i] = loss;
+    if (lse_out) lse_out[i] = lse;
+  }
+  if (dscale_accum) {
+    // d loss_i / d logit_scale = sum_j (p_ij - (1-eps) y_ij - eps/N) * logit_ij   (d logit / d logit_scale = logit)
+    float acc = 0.f;
     for (int j = threadIdx.x; j < N; j += blockDim.x) {
       const float l = T * srow[j];
-      const float p = __expf(l - lse);
-      float gl = p - smoothing / N;
+      float gl = __expf(l - lse) - smoothing / N;
       if (j == label) gl -= (1.f - smoothing);
-      gl *= gs;                                   // d loss / d logit_ij
-      ds_acc += gl * l;                           // -> d / d logit_scale
-      if (dsims) dsims[(long long)i * ld_d + j] = __float2bfloat16(gl * T);  // d loss / d sim_ij
-      if (dsims_f32) dsims_f32[(long long)i * ld_d + j] = gl * T;
+      acc += gl * l;
     }
-    ds_acc = block_reduce_sum(ds_acc, red);
-    if (threadIdx.x == 0 && dscale_accum) atomicAdd(dscale_accum, ds_acc);
+    acc = block_reduce_sum(acc, red);
+    if (threadIdx.x == 0) atomicAdd(dscale_accum, acc * loss_weight / rows);
+  }
+}
+
+// Pass 2: gradient w.r.t. the similarity row-block of THIS rank, including (columns [col_lo, col_hi)) the part that
+// the reference obtains by reduce-scattering the gradient of the all-gathered embeddings:
+//   dsims[i,j] = gs*T*[ softmax_row(L)[i,j] - t_ij ]  +  1[col_lo<=j<col_hi] * gs*T*[ exp(L[i,j] - lse_col[j]) - t_ij ]
+// with t_ij = (1-eps)*1[j==label(i)] + eps/N and lse_col[j] the row-LSE of the OTHER direction's global row j
+// (L_other[j, i] == L[i, j]).  GLOBAL backprop: whole range; LOCAL: own block; NONE: empty range.
+__global__ void contrastive_ce_grad_kernel(const float* __restrict__ sims, long long ld,
+                                           const float* __restrict__ logit_scale, int rows, int N, int label_offset,
+                                           float smoothing, float loss_weight, const float* __restrict__ lse_row,
+                                           const float* __restrict__ lse_col, int col_lo, int col_hi,
+                                           __nv_bfloat16* __restrict__ dsims, float* __restrict__ dsims_f32,
+                                           long long ld_d) {
+  const int i = blockIdx.x;
+  if (i >= rows) return;
+  const float T = __expf(*logit_scale);
+  const float* srow = sims + (long long)i * ld;
+  const int label = label_offset + i;
+  const float lse = lse_row[i];
+  const float gsT = loss_weight / rows * T;
+  for (int j = threadIdx.x; j < N; j += blockDim.x) {
+    const float l = T * srow[j];
+    const float t = ((j == label) ? (1.f - smoothing) : 0.f) + smoothing / N;
+    float g = __expf(l - lse) - t;
+    if (lse_col && j >= col_lo && j < col_hi) g += __expf(l - lse_col[j]) - t;
+    g *= gsT;
+    if (dsims) dsims[(long long)i * ld_d + j] = __float2bfloat16(g);
+    if (dsims_f32) dsims_f32[(long long)i * ld_d + j] = g;
   }
 }
 
@@ -121,14 +151,25 @@ __global__ void matmul_f32_kernel(const float* __restrict__ A, long long lda, in
 
 using namespace mmb;
 
-extern "C" int mmb_contrastive_ce(const float* sims, long long ld, const float* logit_scale, int rows, int N,
-                                  int label_offset, float label_smoothing, float loss_weight, float* row_loss,
-                                  void* dsims_bf16, float* dsims_f32, long long ld_d, float* dscale_accum,
-                                  float* logits_out, long long ld_l, void* stream) {
+extern "C" int mmb_contrastive_ce_stats(const float* sims, long long ld, const float* logit_scale, int rows, int N,
+                                        int label_offset, float label_smoothing, float loss_weight, float* row_loss,
+                                        float* lse_out, float* dscale_accum, float* logits_out, long long ld_l,
+                                        void* stream) {
   if (rows <= 0 || N <= 0 || label_offset < 0 || label_offset + rows > N) return MMB_ERR_ARG;
-  contrastive_ce_kernel<<<rows, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      sims, ld, logit_scale, rows, N, label_offset, label_smoothing, loss_weight, row_loss,
-      (__nv_bfloat16*)dsims_bf16, dsims_f32, ld_d, dscale_accum, logits_out, ld_l);
+  contrastive_ce_stats_kernel<<<rows, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      sims, ld, logit_scale, rows, N, label_offset, label_smoothing, loss_weight, row_loss, lse_out, dscale_accum,
+      logits_out, ld_l);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int mmb_contrastive_ce_grad(const float* sims, long long ld, const float* logit_scale, int rows, int N,
+                                       int label_offset, float label_smoothing, float loss_weight,
+                                       const float* lse_row, const float* lse_col, int col_lo, int col_hi,
+                                       void* dsims_bf16, float* dsims_f32, long long ld_d, void* stream) {
+  if (rows <= 0 || N <= 0 || label_offset < 0 || label_offset + rows > N || !lse_row) return MMB_ERR_ARG;
+  contrastive_ce_grad_kernel<<<rows, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      sims, ld, logit_scale, rows, N, label_offset, label_smoothing, loss_weight, lse_row, lse_col, col_lo, col_hi,
+      (__nv_bfloat16*)dsims_bf16, dsims_f32, ld_d);
   return (int)cudaGetLastError();
 }
 

@@ -42,11 +42,7 @@ class ContrastiveFunction(torch.autograd.Function):
         a32 = a.detach().contiguous().float()
         b32 = b.detach().contiguous().float()
         s32 = logit_scale.detach().reshape(1).float().contiguous()
-        if world > 1:
-            from .symm import distributed_contrastive
-            res = distributed_contrastive(a32, b32, s32, smoothing, backprop_type, want_logits, world, rank)
-        else:
-            res = _single_process(a32, b32, s32, smoothing, want_logits)
+        res = contrastive_schedule(a32, b32, s32, smoothing, backprop_type, want_logits, world, rank)
         loss, logits_a, logits_b, loss_a, loss_b, dA, dB, dS = res
         ctx.save_for_backward(dA, dB, dS)
         ctx.in_dtypes = (a.dtype, b.dtype, logit_scale.dtype, logit_scale.shape)
@@ -71,42 +67,82 @@ def _tensor_path_ok(B: int, N: int, E: int) -> bool:
     return E % 8 == 0 and B % 8 == 0 and N % 8 == 0 and B >= 64 and E >= 64
 
 
-def _single_process(a, b, s, smoothing, want_logits):
-    """World size 1 (modules/losses/contrastive_loss_with_temperature.py:31-33: labels = arange(B), no comm)."""
+def contrastive_schedule(a, b, s, smoothing, backprop_type, want_logits, world, rank):
+    """Forward + all gradients of the contrastive loss for this rank's [B, E] embeddings (fp32, CUDA).
+
+    world == 1 follows contrastive_loss_with_temperature.py:31-33 (labels = arange(B), no communication).
+    world  > 1: every rank publishes bf16 embeddings + row-LSE vectors in its symmetric buffer (symm.py); peers read
+    them in place — the similarity / gradient GEMMs take the peer tensors as their TMA operands.
+    Returns (loss, logits_a, logits_b, loss_a, loss_b, dA, dB, dlogit_scale)."""
+    from .symm import get_comm
+
     dev = a.device
     B, E = a.shape
-    N = B
-    f32 = torch.float32
-    RLA = torch.empty(B, device=dev, dtype=f32)
-    RLB = torch.empty(B, device=dev, dtype=f32)
-    dS = torch.zeros(1, device=dev, dtype=f32)
-    ops.zero_(dS)
+    N = B * world
+    f32, bf = torch.float32, torch.bfloat16
+    tensor_path = _tensor_path_ok(B, N, E)
+    if world > 1 and not tensor_path:
+        raise MMBError(f"distributed contrastive loss needs B % 8 == 0, E % 8 == 0, B >= 64 (got B={B}, E={E})")
+    RLA, RLB = torch.empty(B, device=dev, dtype=f32), torch.empty(B, device=dev, dtype=f32)
+    dS = ops.zero_(torch.empty(1, device=dev, dtype=f32))
     logits_a = torch.empty((B, N), device=dev, dtype=f32) if want_logits else None
     logits_b = torch.empty((B, N), device=dev, dtype=f32) if want_logits else None
     out = torch.empty(3, device=dev, dtype=f32)
-    if _tensor_path_ok(B, N, E):
-        ab, bb = ops.cast_bf16(a), ops.cast_bf16(b)
-        SA = ops.gemm(ab, bb, epilogue=ops.EPI_F32)
-        SB = ops.gemm(bb, ab, epilogue=ops.EPI_F32)
-        DSA = torch.empty((B, N), device=dev, dtype=torch.bfloat16)
-        DSB = torch.empty((B, N), device=dev, dtype=torch.bfloat16)
-        ops.contrastive_ce(SA, s, B, N, 0, smoothing, 0.5, RLA, DSA, None, dS, logits_a)
-        ops.contrastive_ce(SB, s, B, N, 0, smoothing, 0.5, RLB, DSB, None, dS, logits_b)
-        dA = ops.gemm(DSA, bb, b_mn=True, epilogue=ops.EPI_F32)                      # dsims_a @ B_all
-        ops.gemm(DSB, bb, a_mn=True, b_mn=True, epilogue=ops.EPI_F32, out=dA, accumulate=True)  # dsims_b^T @ B_loc
-        dB = ops.gemm(DSB, ab, b_mn=True, epilogue=ops.EPI_F32)
-        ops.gemm(DSA, ab, a_mn=True, b_mn=True, epilogue=ops.EPI_F32, out=dB, accumulate=True)
+    lab = rank * B
+    if backprop_type == BackpropType.GLOBAL:
+        lo, hi = 0, N
+    elif backprop_type == BackpropType.LOCAL:
+        lo, hi = lab, lab + B
     else:
-        SA = ops.matmul_f32(a, b, tb=True)
-        SB = ops.matmul_f32(b, a, tb=True)
+        lo, hi = 0, 0
+    SA = torch.empty((B, N), device=dev, dtype=f32)
+    SB = torch.empty((B, N), device=dev, dtype=f32)
+    if tensor_path:
+        comm = get_comm(B, E, dev, world)
+        p = comm.step % 2
+        comm.step += 1
+        my = comm.my
+        ops.cast_bf16(a, my.a[p])
+        ops.cast_bf16(b, my.b[p])
+        comm.barrier()                                    # peers' embeddings are readable
+        for r in range(world):                            # TMA loads of the B operand read peer r's buffer in place
+            ops.gemm(my.a[p], comm.slots[r].b[p], epilogue=ops.EPI_F32, out=SA[:, r * B:(r + 1) * B])
+            ops.gemm(my.b[p], comm.slots[r].a[p], epilogue=ops.EPI_F32, out=SB[:, r * B:(r + 1) * B])
+        ops.contrastive_ce_stats(SA, s, B, N, lab, smoothing, 0.5, RLA, my.lse_a[p], dS, logits_a)
+        ops.contrastive_ce_stats(SB, s, B, N, lab, smoothing, 0.5, RLB, my.lse_b[p], dS, logits_b)
+        LA = LB = None
+        if hi > lo:
+            if world > 1:
+                comm.barrier()                            # peers' row-LSE vectors are readable
+                LA, LB = torch.empty(N, device=dev, dtype=f32), torch.empty(N, device=dev, dtype=f32)
+                for r in range(world):                    # 2*world copies of B floats (peer reads)
+                    LA[r * B:(r + 1) * B].copy_(comm.slots[r].lse_a[p])
+                    LB[r * B:(r + 1) * B].copy_(comm.slots[r].lse_b[p])
+            else:
+                LA, LB = my.lse_a[p], my.lse_b[p]
+        DSA = torch.empty((B, N), device=dev, dtype=bf)
+        DSB = torch.empty((B, N), device=dev, dtype=bf)
+        ops.contrastive_ce_grad(SA, s, B, N, lab, smoothing, 0.5, my.lse_a[p], LB, lo, hi, DSA, None)
+        ops.contrastive_ce_grad(SB, s, B, N, lab, smoothing, 0.5, my.lse_b[p], LA, lo, hi, DSB, None)
+        dA = torch.empty((B, E), device=dev, dtype=f32)
+        dB = torch.empty((B, E), device=dev, dtype=f32)
+        for r in range(world):
+            ops.gemm(DSA[:, r * B:(r + 1) * B], comm.slots[r].b[p], b_mn=True, epilogue=ops.EPI_F32, out=dA,
+                     accumulate=r > 0)
+            ops.gemm(DSB[:, r * B:(r + 1) * B], comm.slots[r].a[p], b_mn=True, epilogue=ops.EPI_F32, out=dB,
+                     accumulate=r > 0)
+    else:  # exact-fp32 SIMT path (single process, tiny / unaligned shapes)
+        ops.matmul_f32(a, b, tb=True, out=SA)
+        ops.matmul_f32(b, a, tb=True, out=SB)
+        La, Lb = torch.empty(B, device=dev, dtype=f32), torch.empty(B, device=dev, dtype=f32)
+        ops.contrastive_ce_stats(SA, s, B, N, 0, smoothing, 0.5, RLA, La, dS, logits_a)
+        ops.contrastive_ce_stats(SB, s, B, N, 0, smoothing, 0.5, RLB, Lb, dS, logits_b)
         DSA = torch.empty((B, N), device=dev, dtype=f32)
         DSB = torch.empty((B, N), device=dev, dtype=f32)
-        ops.contrastive_ce(SA, s, B, N, 0, smoothing, 0.5, RLA, None, DSA, dS, logits_a)
-        ops.contrastive_ce(SB, s, B, N, 0, smoothing, 0.5, RLB, None, DSB, dS, logits_b)
+        ops.contrastive_ce_grad(SA, s, B, N, 0, smoothing, 0.5, La, Lb if hi > lo else None, lo, hi, None, DSA)
+        ops.contrastive_ce_grad(SB, s, B, N, 0, smoothing, 0.5, Lb, La if hi > lo else None, lo, hi, None, DSB)
         dA = ops.matmul_f32(DSA, b)
-        ops.matmul_f32(DSB, b, ta=True, out=dA, accumulate=True)
         dB = ops.matmul_f32(DSB, a)
-        ops.matmul_f32(DSA, a, ta=True, out=dB, accumulate=True)
     ops.sum_scale(RLA, B, 1.0 / B, out[1:2])
     ops.sum_scale(RLB, B, 1.0 / B, out[2:3])
     ops.sum_scale(RLA, B, 0.5 / B, out[0:1])
@@ -114,6 +150,10 @@ def _single_process(a, b, s, smoothing, want_logits):
     empty = torch.empty(0, device=dev, dtype=f32)
     return (out[0], logits_a if want_logits else empty, logits_b if want_logits else empty, out[1], out[2], dA, dB,
             dS.reshape(()))
+
+
+def _single_process(a, b, s, smoothing, want_logits):
+    return contrastive_schedule(a, b, s, smoothing, BackpropType.GLOBAL, want_logits, 1, 0)
 
 
 def contrastive_loss_apply(embeddings_a, embeddings_b, logit_scale, smoothing: float,

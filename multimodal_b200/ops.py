@@ -193,17 +193,26 @@ def attention_bwd(qkv, out, dout, lse, dqkv, B, S, H, causal, scale):
                                             float(scale), _stream()), "mmb_attention_bwd")
 
 
-def contrastive_ce(sims, logit_scale, rows, N, label_offset, smoothing, loss_weight, row_loss, dsims_bf16, dsims_f32,
-                   dscale_accum, logits_out=None):
+def contrastive_ce_stats(sims, logit_scale, rows, N, label_offset, smoothing, loss_weight, row_loss, lse_out,
+                         dscale_accum, logits_out=None):
+    _chk(sims, torch.float32, "sims")
+    _lib.check(_lib.lib().mmb_contrastive_ce_stats(_p(sims), sims.stride(0), _p(logit_scale), rows, N, label_offset,
+                                                   float(smoothing), float(loss_weight), _p(row_loss), _p(lse_out),
+                                                   _p(dscale_accum), _p(logits_out),
+                                                   logits_out.stride(0) if logits_out is not None else 0, _stream()),
+               "mmb_contrastive_ce_stats")
+
+
+def contrastive_ce_grad(sims, logit_scale, rows, N, label_offset, smoothing, loss_weight, lse_row, lse_col, col_lo,
+                        col_hi, dsims_bf16, dsims_f32):
     _chk(sims, torch.float32, "sims")
     d = dsims_bf16 if dsims_bf16 is not None else dsims_f32
     if dsims_bf16 is not None and dsims_f32 is not None and dsims_bf16.stride(0) != dsims_f32.stride(0):
-        raise MMBError("contrastive_ce: dsims_bf16 and dsims_f32 must share the leading dimension")
-    _lib.check(_lib.lib().mmb_contrastive_ce(_p(sims), sims.stride(0), _p(logit_scale), rows, N, label_offset,
-                                             float(smoothing), float(loss_weight), _p(row_loss), _p(dsims_bf16),
-                                             _p(dsims_f32), d.stride(0) if d is not None else 0, _p(dscale_accum),
-                                             _p(logits_out), logits_out.stride(0) if logits_out is not None else 0,
-                                             _stream()), "mmb_contrastive_ce")
+        raise MMBError("contrastive_ce_grad: dsims_bf16 and dsims_f32 must share the leading dimension")
+    _lib.check(_lib.lib().mmb_contrastive_ce_grad(_p(sims), sims.stride(0), _p(logit_scale), rows, N, label_offset,
+                                                  float(smoothing), float(loss_weight), _p(lse_row), _p(lse_col),
+                                                  int(col_lo), int(col_hi), _p(dsims_bf16), _p(dsims_f32), d.stride(0),
+                                                  _stream()), "mmb_contrastive_ce_grad")
 
 
 def sum_scale(inp, n, scale, out, accumulate=False):

@@ -15,7 +15,7 @@ import torch.distributed as dist
 from . import ops
 from ._lib import MMBError
 from .engine import ParamStore
-from .engine_loss import _dist_state, _single_process
+from .engine_loss import _dist_state, contrastive_schedule
 from .utils.distributed import BackpropType
 
 
@@ -92,12 +92,8 @@ class ContrastiveTrainer:
         ia, ib = torch.empty(B, device=dev, dtype=f32), torch.empty(B, device=dev, dtype=f32)
         ops.l2norm_fwd(ea, na, None, ia, B, E)
         ops.l2norm_fwd(eb, nb, None, ib, B, E)
-        if self.world > 1:
-            from .symm import distributed_contrastive
-            res = distributed_contrastive(na, nb, self.ls_buf[0:1], self.smoothing, self.backprop_type, False, self.world,
-                                          self.rank)
-        else:
-            res = _single_process(na, nb, self.ls_buf[0:1], self.smoothing, False)
+        res = contrastive_schedule(na, nb, self.ls_buf[0:1], self.smoothing, self.backprop_type, False, self.world,
+                                   self.rank)
         loss, _, _, _, _, dA, dB, dS = res
         # ---------------- backward ----------------
         dea, deb = torch.empty_like(ea), torch.empty_like(eb)

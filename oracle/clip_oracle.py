@@ -162,3 +162,76 @@ def synthetic_batch(B: int, rank: int = 0, image_size: int = 224, ctx: int = 77,
 def bf16_round_(sd: Dict[str, Tensor]) -> Dict[str, Tensor]:
     """Round float tensors to bf16-representable fp32 (parity runs: removes operand-rounding as an error source)."""
     return {k: (v.bfloat16().float() if v.is_floating_point() else v) for k, v in sd.items()}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Distributed restatement (needs an initialised torch.distributed group; gloo on CPU or nccl on GPU)
+# ----------------------------------------------------------------------------------------------------------------
+def gather_tensor(t: Tensor, mode: str):
+    """utils/distributed.py:28-58.  mode: 'GLOBAL' (autograd all_gather: backward = reduce_scatter),
+    'LOCAL' (no-grad gather, own slot replaced by the live tensor), 'NONE' (no-grad gather)."""
+    import torch.distributed as dist
+    from torch.distributed.nn.functional import all_gather as all_gather_with_backprop
+
+    if mode == "GLOBAL":
+        return list(all_gather_with_backprop(t))
+    out = [torch.zeros_like(t) for _ in range(dist.get_world_size())]
+    dist.all_gather(out, t.detach())
+    if mode == "LOCAL":
+        out[dist.get_rank()] = t
+    return out
+
+
+def contrastive_loss_distributed(a: Tensor, b: Tensor, logit_scale: Tensor, mode: str = "GLOBAL",
+                                 label_smoothing: float = 0.0):
+    """contrastive_loss_with_temperature.py:26-115 with torch.distributed initialised (:35-45)."""
+    import torch.distributed as dist
+
+    a_all = torch.cat(gather_tensor(a, mode))
+    b_all = torch.cat(gather_tensor(b, mode))
+    return contrastive_loss(a, b, logit_scale, a_all, b_all, dist.get_rank(), label_smoothing)
+
+
+def contrastive_grads_lse_exchange(a: Tensor, b: Tensor, logit_scale: Tensor, mode: str = "GLOBAL",
+                                   label_smoothing: float = 0.0):
+    """Restatement of the CUDA schedule (multimodal_b200/engine_loss.py): no gradient traffic — each rank rebuilds
+    d(sum over ranks of loss)/d(its embeddings) from its own logits row block and the peers' row-LSE vectors.
+    Returns (loss, dA, dB, dlogit_scale) for THIS rank; must equal autograd over contrastive_loss_distributed."""
+    import torch.distributed as dist
+
+    W, r = dist.get_world_size(), dist.get_rank()
+    B = a.shape[0]
+    N = W * B
+    eps = label_smoothing
+
+    def gather(t):
+        out = [torch.zeros_like(t) for _ in range(W)]
+        dist.all_gather(out, t.contiguous())
+        return torch.cat(out)
+
+    with torch.no_grad():
+        T = torch.exp(logit_scale)
+        a_all, b_all = gather(a), gather(b)
+        La, Lb = a @ b_all.t() * T, b @ a_all.t() * T
+        lse_a, lse_b = torch.logsumexp(La, 1), torch.logsumexp(Lb, 1)
+        lse_a_all, lse_b_all = gather(lse_a), gather(lse_b)
+        y = torch.zeros(B, N, dtype=a.dtype, device=a.device)
+        y[torch.arange(B), r * B + torch.arange(B)] = 1.0
+        t = (1 - eps) * y + eps / N
+        gs = 0.5 / B
+        own_a, own_b = torch.exp(La - lse_a[:, None]) - t, torch.exp(Lb - lse_b[:, None]) - t
+        col = torch.zeros(N, dtype=torch.bool, device=a.device)
+        if mode == "GLOBAL":
+            col[:] = True
+        elif mode == "LOCAL":
+            col[r * B:(r + 1) * B] = True
+        tr_a = (torch.exp(La - lse_b_all[None, :]) - t) * col
+        tr_b = (torch.exp(Lb - lse_a_all[None, :]) - t) * col
+        dA = gs * T * (own_a + tr_a) @ b_all
+        dB = gs * T * (own_b + tr_b) @ a_all
+        dS = gs * ((own_a * La).sum() + (own_b * Lb).sum())
+        nll_a = lse_a - La[torch.arange(B), r * B + torch.arange(B)]
+        nll_b = lse_b - Lb[torch.arange(B), r * B + torch.arange(B)]
+        loss = 0.5 * (((1 - eps) * nll_a + eps * (lse_a - La.mean(1))).mean()
+                      + ((1 - eps) * nll_b + eps * (lse_b - Lb.mean(1))).mean())
+    return loss, dA, dB, dS
