@@ -12,6 +12,7 @@
 // TODO(round 2): tcgen05 version with S in TMEM.
 #include "common.cuh"
 #include "mmb200_internal.h"
+#include <stdlib.h>
 
 namespace mmb {
 
@@ -393,9 +394,24 @@ static int pick_warps(int S) {
 
 using namespace mmb;
 
+extern "C" int mmb_attention_fwd_tc(const void* qkv, void* out, float* lse, int B, int S, int H, int causal, float scale,
+                                    void* stream);
+extern "C" int mmb_attention_bwd_tc(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
+                                    int B, int S, int H, int causal, float scale, void* stream);
+static bool use_legacy_attention() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MMB_ATTN_LEGACY");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
 extern "C" int mmb_attention_fwd(const void* qkv, void* out, float* lse, int B, int S, int H, int head_dim, int causal,
                                  float scale, void* stream) {
   if (head_dim != HD) return MMB_ERR_UNSUPPORTED;
+  if (S <= 256 && !use_legacy_attention())  // tcgen05 path (attention_tc.cu); the HMMA kernels below serve 256 < S <= 320
+    return mmb_attention_fwd_tc(qkv, out, lse, B, S, H, causal, scale, stream);
   if (B <= 0 || S <= 0 || S > 320) return MMB_ERR_UNSUPPORTED;
   const int S_pad = (S + 15) & ~15;
   const int smem = 3 * S_pad * 128;
@@ -415,6 +431,8 @@ extern "C" int mmb_attention_fwd(const void* qkv, void* out, float* lse, int B, 
 extern "C" int mmb_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
                                  int B, int S, int H, int head_dim, int causal, float scale, void* stream) {
   if (head_dim != HD) return MMB_ERR_UNSUPPORTED;
+  if (S <= 256 && !use_legacy_attention())
+    return mmb_attention_bwd_tc(qkv, out, dout, lse, dqkv, B, S, H, causal, scale, stream);
   if (B <= 0 || S <= 0 || S > 320) return MMB_ERR_UNSUPPORTED;
   const int S_pad = (S + 15) & ~15;
   const int smem = 4 * S_pad * 128 + 2 * S_pad * 4;

@@ -1,0 +1,480 @@
+// tcgen05 attention for S <= 256, head_dim 64 (CLIP ViT-B/16 image S=197, text S=77): scores and gradients are
+// computed by 5th-gen tensor cores with TMEM accumulators; operands are staged by TMA straight out of the packed
+// in-projection output [B*S, 3d] (no head split/merge copies).  One thread per tile row does the softmax math on
+// TMEM rows (tcgen05.ld 32x32b), two warpgroups split the columns.
+//
+//   fwd   (b,h,q-tile):  S = Q K^T (TMEM, <=256 cols) -> softmax -> P (bf16, smem, K-major) -> O = P V (TMEM)
+//   dq    (b,h,q-tile):  per 64-wide kv chunk c: S_c = Q K_c^T, dP_c = dO V_c^T -> dS_c -> dQ += dS_c K_c
+//   dkdv  (b,h,kv-tile): per 64-wide q chunk c: S^T_c = K Q_c^T, dP^T_c = V dO_c^T -> P^T_c, dS^T_c ->
+//                        dV += P^T_c dO_c ; dK += dS^T_c Q_c
+// The chunked backward kernels double-buffer the S/dP accumulators in TMEM so the MMAs of chunk c+1 run under the
+// elementwise work of chunk c.  Replaces F.scaled_dot_product_attention + autograd (torch/nn/functional.py:6682).
+#include "common.cuh"
+#include "mmb200_internal.h"
+
+namespace mmb {
+
+constexpr int ATT_THREADS = 256;
+constexpr int ATOM = 16384;  // 128 rows x 128 B
+
+struct AttnTcArgs {
+  int S, H, S_pad;
+  float scale, scale_log2;
+  float* lse;                   // [B,H,S] natural log
+  __nv_bfloat16* out;           // fwd: O [B*S, d]
+  const __nv_bfloat16* o_in;    // bwd: O
+  const __nv_bfloat16* dout;    // bwd: dO [B*S, d]
+  __nv_bfloat16* dqkv;          // bwd: [B*S, 3d]
+};
+
+__device__ __forceinline__ uint64_t desc_k(uint32_t saddr) { return make_smem_desc_sw128(saddr, 16, 1024); }
+__device__ __forceinline__ uint64_t desc_mn(uint32_t saddr) { return make_smem_desc_sw128(saddr, 8192, 1024); }
+__device__ __forceinline__ uint32_t idesc_rt(int N, bool a_mn, bool b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+// store 16 consecutive bf16 (two 16 B pieces) of row r at column j0 (multiple of 16) of a K-major SW128 atom series
+__device__ __forceinline__ void store_p16(uint8_t* base, int r, int j0, const float (&p)[16]) {
+  uint8_t* a = base + (j0 >> 6) * ATOM + r * 128;
+  const int c8 = (j0 & 63) >> 3;
+  uint4 u0, u1;
+  u0.x = pack_bf16x2(p[0], p[1]); u0.y = pack_bf16x2(p[2], p[3]); u0.z = pack_bf16x2(p[4], p[5]); u0.w = pack_bf16x2(p[6], p[7]);
+  u1.x = pack_bf16x2(p[8], p[9]); u1.y = pack_bf16x2(p[10], p[11]); u1.z = pack_bf16x2(p[12], p[13]); u1.w = pack_bf16x2(p[14], p[15]);
+  *reinterpret_cast<uint4*>(a + ((c8 ^ (r & 7)) << 4)) = u0;
+  *reinterpret_cast<uint4*>(a + (((c8 + 1) ^ (r & 7)) << 4)) = u1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Forward
+// ------------------------------------------------------------------------------------------------
+template <bool CAUSAL>
+__global__ void __launch_bounds__(ATT_THREADS, 2)
+attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant__ CUtensorMap tmPad,
+                   const AttnTcArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;               // 16 KB   } aliased by sP (4 atoms) once S = Q K^T has completed
+  uint8_t* sK = smem + ATOM;        // <=32 KB }
+  uint8_t* sP = smem;
+  uint8_t* sV = smem + 4 * ATOM;    // <=32 KB
+  float* sRed = reinterpret_cast<float*>(smem + 6 * ATOM);  // [2][128] max, [2][128] sum
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sRed + 512);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int S = p.S, S_pad = p.S_pad, d = p.H * 64;
+  const uint32_t ncols = S_pad <= 128 ? 128u : 256u;
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tm128);
+    tma_prefetch_desc(&tmPad);
+    mbar_init(&bars[0], 1);  // Q,K landed
+    mbar_init(&bars[1], 1);  // V landed
+    mbar_init(&bars[2], 1);  // MMA done (phase 0: S, phase 1: O)
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, ncols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int row0 = b * S;
+
+  if (threadIdx.x == 0) {
+    mbar_arrive_expect_tx(&bars[0], ATOM + S_pad * 128);
+    tma_load_2d(&tm128, &bars[0], sQ, h * 64, row0 + qt * 128);
+    tma_load_2d(&tmPad, &bars[0], sK, d + h * 64, row0);
+    mbar_arrive_expect_tx(&bars[1], S_pad * 128);
+    tma_load_2d(&tmPad, &bars[1], sV, 2 * d + h * 64, row0);
+    mbar_wait(&bars[0], 0);
+    tc_fence_after();
+    const uint32_t id = idesc_rt(S_pad, false, false);
+    const uint64_t da = desc_k(smem_u32(sQ)), db = desc_k(smem_u32(sK));
+#pragma unroll
+    for (int k = 0; k < 4; ++k) umma_bf16(tmem, da + 2 * k, db + 2 * k, id, k > 0);
+    umma_commit(&bars[2]);
+  }
+  mbar_wait(&bars[2], 0);
+  tc_fence_after();
+
+  const int q4 = warp & 3, grp = warp >> 2;
+  const int r = q4 * 32 + lane;
+  const int qi = qt * 128 + r;
+  const uint32_t trow = tmem + ((uint32_t)(q4 * 32) << 16);
+  const int nchunk = S_pad >> 4;
+  const int c_lo = grp == 0 ? 0 : (nchunk + 1) / 2, c_hi = grp == 0 ? (nchunk + 1) / 2 : nchunk;
+  const int kv_lim = CAUSAL ? min(S, qi + 1) : S;  // columns >= kv_lim are masked
+
+  float mx = -INFINITY;
+  for (int c = c_lo; c < c_hi; ++c) {
+    uint32_t v[16];
+    tmem_ld16(trow + c * 16, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int e = 0; e < 16; ++e)
+      if (c * 16 + e < kv_lim) mx = fmaxf(mx, __uint_as_float(v[e]));
+  }
+  sRed[grp * 128 + r] = mx;
+  __syncthreads();  // also orders: every thread has finished reading Q/K smem?  (MMA done) -> sP may be written
+  mx = fmaxf(sRed[r], sRed[128 + r]) * p.scale_log2;
+  float sum = 0.f;
+  for (int c = c_lo; c < c_hi; ++c) {
+    uint32_t v[16];
+    tmem_ld16(trow + c * 16, v);
+    tmem_ld_wait();
+    float pr[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) {
+      const float x = (c * 16 + e < kv_lim) ? ex2_approx(__uint_as_float(v[e]) * p.scale_log2 - mx) : 0.f;
+      pr[e] = x;
+      sum += x;
+    }
+    store_p16(sP, r, c * 16, pr);
+  }
+  sRed[256 + grp * 128 + r] = sum;
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  const float l = sRed[256 + r] + sRed[384 + r];
+
+  if (threadIdx.x == 0) {
+    tc_fence_after();
+    mbar_wait(&bars[1], 0);
+    const uint32_t id = idesc_rt(64, false, true);
+    const uint32_t uP = smem_u32(sP), uV = smem_u32(sV);
+    for (int j = 0; j < nchunk; ++j) {
+      const uint64_t da = desc_k(uP + (j >> 2) * ATOM + (j & 3) * 32);
+      const uint64_t db = desc_mn(uV + j * 2048);
+      umma_bf16(tmem, da, db, id, j > 0);
+    }
+    umma_commit(&bars[2]);
+  }
+  mbar_wait(&bars[2], 1);
+  tc_fence_after();
+  {
+    uint32_t v[32];
+    tmem_ld32(trow + grp * 32, v);
+    tmem_ld_wait();
+    if (qi < S) {
+      const float inv = 1.f / l;
+      __nv_bfloat16* dst = p.out + ((long long)(row0 + qi)) * d + h * 64 + grp * 32;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint4 o;
+        o.x = pack_bf16x2(__uint_as_float(v[j * 8 + 0]) * inv, __uint_as_float(v[j * 8 + 1]) * inv);
+        o.y = pack_bf16x2(__uint_as_float(v[j * 8 + 2]) * inv, __uint_as_float(v[j * 8 + 3]) * inv);
+        o.z = pack_bf16x2(__uint_as_float(v[j * 8 + 4]) * inv, __uint_as_float(v[j * 8 + 5]) * inv);
+        o.w = pack_bf16x2(__uint_as_float(v[j * 8 + 6]) * inv, __uint_as_float(v[j * 8 + 7]) * inv);
+        reinterpret_cast<uint4*>(dst)[j] = o;
+      }
+      if (grp == 0 && p.lse) p.lse[((long long)b * p.H + h) * S + qi] = (mx + log2f(l)) * 0.6931471805599453f;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, ncols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Backward, shared chunk machinery.
+//   MODE_DQ  : tile rows = queries  (A0 = Q tile, A1 = dO tile; B chunks from K / V; accumulate dQ with B2 = K)
+//   MODE_DKDV: tile rows = keys     (A0 = K tile, A1 = V tile;  B chunks from Q / dO; accumulate dV (B2 = dO), dK (B2 = Q))
+// TMEM columns: S[2] @0,64 ; dP[2] @128,192 ; acc0 @256 ; acc1 @320.
+// ------------------------------------------------------------------------------------------------
+template <bool CAUSAL, bool DKDV>
+__global__ void __launch_bounds__(ATT_THREADS, 1)
+attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_constant__ CUtensorMap tmQKVPad,
+                   const __grid_constant__ CUtensorMap tmDO128, const __grid_constant__ CUtensorMap tmDOPad,
+                   const AttnTcArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA0 = smem;                 // 16 KB  tile operand 0 (Q | K_j)
+  uint8_t* sA1 = smem + ATOM;          // 16 KB  tile operand 1 (dO | V_j)
+  uint8_t* sB0 = smem + 2 * ATOM;      // 32 KB  full-length operand 0 (K | Q)
+  uint8_t* sB1 = smem + 4 * ATOM;      // 32 KB  full-length operand 1 (V | dO)
+  uint8_t* sDS = smem + 6 * ATOM;      // 2 x 16 KB  dS chunk (double buffered)
+  uint8_t* sPT = smem + 8 * ATOM;      // 2 x 16 KB  P^T chunk (DKDV only)
+  float* sL = reinterpret_cast<float*>(smem + (DKDV ? 10 : 8) * ATOM);  // [256] lse (log2 units) per q (DKDV only)
+  float* sD = sL + 256;                                                  // [256] rowsum(dO*O) per q (DKDV only)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sD + 256);
+  uint64_t* bar_load = bars;        // [1]
+  uint64_t* bar_s = bars + 1;       // [2] S/dP chunk ready
+  uint64_t* bar_acc = bars + 3;     // [2] accumulate-MMAs of a chunk done (dS / P^T buffers reusable)
+  uint64_t* bar_done = bars + 5;    // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int S = p.S, S_pad = p.S_pad, d = p.H * 64;
+  const int row0 = b * S;
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmQKV128); tma_prefetch_desc(&tmQKVPad);
+    tma_prefetch_desc(&tmDO128); tma_prefetch_desc(&tmDOPad);
+    mbar_init(bar_load, 1);
+    mbar_init(&bar_s[0], 1); mbar_init(&bar_s[1], 1);
+    mbar_init(&bar_acc[0], 1); mbar_init(&bar_acc[1], 1);
+    mbar_init(bar_done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (threadIdx.x == 0) {
+    mbar_arrive_expect_tx(bar_load, 2 * ATOM + 2 * S_pad * 128);
+    if (!DKDV) {
+      tma_load_2d(&tmQKV128, bar_load, sA0, h * 64, row0 + tile * 128);            // Q tile
+      tma_load_2d(&tmDO128, bar_load, sA1, h * 64, row0 + tile * 128);             // dO tile
+      tma_load_2d(&tmQKVPad, bar_load, sB0, d + h * 64, row0);                     // K
+      tma_load_2d(&tmQKVPad, bar_load, sB1, 2 * d + h * 64, row0);                 // V
+    } else {
+      tma_load_2d(&tmQKV128, bar_load, sA0, d + h * 64, row0 + tile * 128);        // K tile
+      tma_load_2d(&tmQKV128, bar_load, sA1, 2 * d + h * 64, row0 + tile * 128);    // V tile
+      tma_load_2d(&tmQKVPad, bar_load, sB0, h * 64, row0);                         // Q
+      tma_load_2d(&tmDOPad, bar_load, sB1, h * 64, row0);                          // dO
+    }
+  }
+
+  const int q4 = warp & 3, grp = warp >> 2;
+  const int r = q4 * 32 + lane;
+  const int ri = tile * 128 + r;  // global index of this thread's row (query for DQ, key for DKDV)
+  const uint32_t trow = tmem + ((uint32_t)(q4 * 32) << 16);
+
+  // per-row / per-column softmax statistics
+  float Lrow = 0.f, Drow = 0.f;
+  if (!DKDV) {
+    if (ri < S) {
+      const uint4* po = reinterpret_cast<const uint4*>(p.o_in + (long long)(row0 + ri) * d + h * 64);
+      const uint4* pd = reinterpret_cast<const uint4*>(p.dout + (long long)(row0 + ri) * d + h * 64);
+      float acc = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint4 a = __ldg(po + j), c = __ldg(pd + j);
+        acc += bf16_lo(a.x) * bf16_lo(c.x) + bf16_hi(a.x) * bf16_hi(c.x) + bf16_lo(a.y) * bf16_lo(c.y) +
+               bf16_hi(a.y) * bf16_hi(c.y) + bf16_lo(a.z) * bf16_lo(c.z) + bf16_hi(a.z) * bf16_hi(c.z) +
+               bf16_lo(a.w) * bf16_lo(c.w) + bf16_hi(a.w) * bf16_hi(c.w);
+      }
+      Drow = acc;
+      Lrow = p.lse[((long long)b * p.H + h) * S + ri] * 1.4426950408889634f;
+    }
+  } else {
+    const int qi = threadIdx.x;  // 256 threads cover S_pad <= 256 query columns
+    float acc = 0.f, L = 0.f;
+    if (qi < S) {
+      const uint4* po = reinterpret_cast<const uint4*>(p.o_in + (long long)(row0 + qi) * d + h * 64);
+      const uint4* pd = reinterpret_cast<const uint4*>(p.dout + (long long)(row0 + qi) * d + h * 64);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint4 a = __ldg(po + j), c = __ldg(pd + j);
+        acc += bf16_lo(a.x) * bf16_lo(c.x) + bf16_hi(a.x) * bf16_hi(c.x) + bf16_lo(a.y) * bf16_lo(c.y) +
+               bf16_hi(a.y) * bf16_hi(c.y) + bf16_lo(a.z) * bf16_lo(c.z) + bf16_hi(a.z) * bf16_hi(c.z) +
+               bf16_lo(a.w) * bf16_lo(c.w) + bf16_hi(a.w) * bf16_hi(c.w);
+      }
+      L = p.lse[((long long)b * p.H + h) * S + qi] * 1.4426950408889634f;
+    }
+    sL[qi] = L;
+    sD[qi] = acc;
+    __syncthreads();
+  }
+
+  const int nc = (S_pad + 63) >> 6;
+  const uint32_t uA0 = smem_u32(sA0), uA1 = smem_u32(sA1), uB0 = smem_u32(sB0), uB1 = smem_u32(sB1);
+  const uint32_t uDS = smem_u32(sDS), uPT = smem_u32(sPT);
+
+  auto issue_scores = [&](int c) {  // S_c / dP_c (or their transposes) into TMEM buffer c & 1
+    const int wc = min(64, S_pad - c * 64);
+    const uint32_t id = idesc_rt(wc, false, false);
+    const uint64_t a0 = desc_k(uA0), a1 = desc_k(uA1);
+    const uint64_t b0 = desc_k(uB0 + c * 8192), b1 = desc_k(uB1 + c * 8192);
+    const uint32_t ts = tmem + (c & 1) * 64, tp = tmem + 128 + (c & 1) * 64;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) umma_bf16(ts, a0 + 2 * k, b0 + 2 * k, id, k > 0);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) umma_bf16(tp, a1 + 2 * k, b1 + 2 * k, id, k > 0);
+    umma_commit(&bar_s[c & 1]);
+  };
+
+  if (threadIdx.x == 0) {
+    mbar_wait(bar_load, 0);
+    tc_fence_after();
+    issue_scores(0);
+  }
+
+  for (int c = 0; c < nc; ++c) {
+    const int wc = min(64, S_pad - c * 64);
+    if (threadIdx.x == 0 && c + 1 < nc) issue_scores(c + 1);  // runs under this chunk's elementwise work
+    if (c >= 2) mbar_wait(&bar_acc[c & 1], ((c >> 1) - 1) & 1);  // dS / P^T buffer (c & 1) free again
+    mbar_wait(&bar_s[c & 1], (c >> 1) & 1);
+    tc_fence_after();
+    // this thread: row r, columns [grp*32, grp*32+32) of the chunk
+    if (grp * 32 < wc) {
+      uint32_t sv[32], dv[32];
+      tmem_ld32(trow + (c & 1) * 64 + grp * 32, sv);
+      tmem_ld32(trow + 128 + (c & 1) * 64 + grp * 32, dv);
+      tmem_ld_wait();
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        float ds[16], pt[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          const int cj = c * 64 + grp * 32 + half * 16 + e;  // global column index (key for DQ, query for DKDV)
+          bool valid;
+          float L, Dv;
+          if (!DKDV) {
+            valid = (ri < S) && (cj < S) && (!CAUSAL || cj <= ri);
+            L = Lrow; Dv = Drow;
+          } else {
+            valid = (ri < S) && (cj < S) && (!CAUSAL || ri <= cj);
+            L = sL[cj & 255]; Dv = sD[cj & 255];
+          }
+          const float pv = valid ? ex2_approx(__uint_as_float(sv[half * 16 + e]) * p.scale_log2 - L) : 0.f;
+          pt[e] = pv;
+          ds[e] = pv * (__uint_as_float(dv[half * 16 + e]) - Dv) * p.scale;
+        }
+        if (grp * 32 + half * 16 < wc) {
+          store_p16(sDS + (c & 1) * ATOM, r, grp * 32 + half * 16, ds);
+          if (DKDV) store_p16(sPT + (c & 1) * ATOM, r, grp * 32 + half * 16, pt);
+        }
+      }
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      tc_fence_after();
+      const uint32_t id = idesc_rt(64, false, true);
+      const int ks = wc >> 4;
+      if (!DKDV) {   // dQ += dS_c K_c
+        for (int k = 0; k < ks; ++k)
+          umma_bf16(tmem + 256, desc_k(uDS + (c & 1) * ATOM + k * 32), desc_mn(uB0 + c * 8192 + k * 2048), id,
+                    (c > 0 || k > 0));
+      } else {       // dV += P^T_c dO_c ; dK += dS^T_c Q_c
+        for (int k = 0; k < ks; ++k)
+          umma_bf16(tmem + 256, desc_k(uPT + (c & 1) * ATOM + k * 32), desc_mn(uB1 + c * 8192 + k * 2048), id,
+                    (c > 0 || k > 0));
+        for (int k = 0; k < ks; ++k)
+          umma_bf16(tmem + 320, desc_k(uDS + (c & 1) * ATOM + k * 32), desc_mn(uB0 + c * 8192 + k * 2048), id,
+                    (c > 0 || k > 0));
+      }
+      umma_commit(&bar_acc[c & 1]);
+      if (c == nc - 1) umma_commit(bar_done);
+    }
+  }
+  mbar_wait(bar_done, 0);
+  tc_fence_after();
+  {
+    const long long ld = 3LL * d;
+    if (!DKDV) {
+      uint32_t v[32];
+      tmem_ld32(trow + 256 + grp * 32, v);
+      tmem_ld_wait();
+      if (ri < S) {
+        __nv_bfloat16* dst = p.dqkv + (long long)(row0 + ri) * ld + h * 64 + grp * 32;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint4 o;
+          o.x = pack_bf16x2(__uint_as_float(v[j * 8 + 0]), __uint_as_float(v[j * 8 + 1]));
+          o.y = pack_bf16x2(__uint_as_float(v[j * 8 + 2]), __uint_as_float(v[j * 8 + 3]));
+          o.z = pack_bf16x2(__uint_as_float(v[j * 8 + 4]), __uint_as_float(v[j * 8 + 5]));
+          o.w = pack_bf16x2(__uint_as_float(v[j * 8 + 6]), __uint_as_float(v[j * 8 + 7]));
+          reinterpret_cast<uint4*>(dst)[j] = o;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int which = 0; which < 2; ++which) {  // 0: dV (cols 256..319) -> V block; 1: dK (320..383) -> K block
+        uint32_t v[32];
+        tmem_ld32(trow + 256 + which * 64 + grp * 32, v);
+        tmem_ld_wait();
+        if (ri < S) {
+          __nv_bfloat16* dst = p.dqkv + (long long)(row0 + ri) * ld + (which == 0 ? 2 * d : d) + h * 64 + grp * 32;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 o;
+            o.x = pack_bf16x2(__uint_as_float(v[j * 8 + 0]), __uint_as_float(v[j * 8 + 1]));
+            o.y = pack_bf16x2(__uint_as_float(v[j * 8 + 2]), __uint_as_float(v[j * 8 + 3]));
+            o.z = pack_bf16x2(__uint_as_float(v[j * 8 + 4]), __uint_as_float(v[j * 8 + 5]));
+            o.w = pack_bf16x2(__uint_as_float(v[j * 8 + 6]), __uint_as_float(v[j * 8 + 7]));
+            reinterpret_cast<uint4*>(dst)[j] = o;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+constexpr int FWD_SMEM = 1024 + 6 * ATOM + 2048 + 64;
+constexpr int BWD_DQ_SMEM = 1024 + 8 * ATOM + 2048 + 128;
+constexpr int BWD_DKDV_SMEM = 1024 + 10 * ATOM + 2048 + 128;
+
+}  // namespace mmb
+
+using namespace mmb;
+
+extern "C" int mmb_attention_fwd_tc(const void* qkv, void* out, float* lse, int B, int S, int H, int causal, float scale,
+                                    void* stream) {
+  if (B <= 0 || S <= 0 || S > 256) return MMB_ERR_UNSUPPORTED;
+  const int d = H * 64, S_pad = (S + 15) & ~15;
+  CUtensorMap tm128, tmPad;
+  int rc = make_tmap_2d(&tm128, qkv, 2, false, 3ull * d, (uint64_t)B * S, 3ull * d * 2, 64, 128);
+  if (rc) return rc;
+  rc = make_tmap_2d(&tmPad, qkv, 2, false, 3ull * d, (uint64_t)B * S, 3ull * d * 2, 64, S_pad);
+  if (rc) return rc;
+  AttnTcArgs a{};
+  a.S = S; a.H = H; a.S_pad = S_pad; a.scale = scale; a.scale_log2 = scale * 1.4426950408889634f;
+  a.lse = lse; a.out = (__nv_bfloat16*)out;
+  dim3 grid((S + 127) / 128, H, B);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (causal) {
+    cudaFuncSetAttribute(attn_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM);
+    attn_fwd_tc_kernel<true><<<grid, ATT_THREADS, FWD_SMEM, st>>>(tm128, tmPad, a);
+  } else {
+    cudaFuncSetAttribute(attn_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM);
+    attn_fwd_tc_kernel<false><<<grid, ATT_THREADS, FWD_SMEM, st>>>(tm128, tmPad, a);
+  }
+  return (int)cudaGetLastError();
+}
+
+extern "C" int mmb_attention_bwd_tc(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
+                                    int B, int S, int H, int causal, float scale, void* stream) {
+  if (B <= 0 || S <= 0 || S > 256) return MMB_ERR_UNSUPPORTED;
+  const int d = H * 64, S_pad = (S + 15) & ~15;
+  CUtensorMap q128, qPad, o128, oPad;
+  int rc = make_tmap_2d(&q128, qkv, 2, false, 3ull * d, (uint64_t)B * S, 3ull * d * 2, 64, 128);
+  if (rc) return rc;
+  rc = make_tmap_2d(&qPad, qkv, 2, false, 3ull * d, (uint64_t)B * S, 3ull * d * 2, 64, S_pad);
+  if (rc) return rc;
+  rc = make_tmap_2d(&o128, dout, 2, false, (uint64_t)d, (uint64_t)B * S, (uint64_t)d * 2, 64, 128);
+  if (rc) return rc;
+  rc = make_tmap_2d(&oPad, dout, 2, false, (uint64_t)d, (uint64_t)B * S, (uint64_t)d * 2, 64, S_pad);
+  if (rc) return rc;
+  AttnTcArgs a{};
+  a.S = S; a.H = H; a.S_pad = S_pad; a.scale = scale; a.scale_log2 = scale * 1.4426950408889634f;
+  a.lse = const_cast<float*>(lse); a.o_in = (const __nv_bfloat16*)out; a.dout = (const __nv_bfloat16*)dout;
+  a.dqkv = (__nv_bfloat16*)dqkv;
+  dim3 grid((S + 127) / 128, H, B);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+#define LAUNCH_BWD(C, K, SM)                                                                         \
+  cudaFuncSetAttribute(attn_bwd_tc_kernel<C, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM);  \
+  attn_bwd_tc_kernel<C, K><<<grid, ATT_THREADS, SM, st>>>(q128, qPad, o128, oPad, a);
+  if (causal) {
+    LAUNCH_BWD(true, true, BWD_DKDV_SMEM)
+    LAUNCH_BWD(true, false, BWD_DQ_SMEM)
+  } else {
+    LAUNCH_BWD(false, true, BWD_DKDV_SMEM)
+    LAUNCH_BWD(false, false, BWD_DQ_SMEM)
+  }
+#undef LAUNCH_BWD
+  return (int)cudaGetLastError();
+}

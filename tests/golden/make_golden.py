@@ -60,10 +60,11 @@ def main():
         "emb_a": o.embeddings_a.detach().clone(), "emb_b": o.embeddings_b.detach().clone(),
         "loss": res.loss.detach().clone(), "logits_a": res.logits_a.detach().clone(),
         "logits_b": res.logits_b.detach().clone(),
-        # full gradients for small tensors; (sum, abs-sum, first 256 values) for the large ones
+        # full gradients for small tensors; (abs-sum, abs-max, 4096 evenly strided samples) for the large ones
         "grads": {k: (p.grad.detach().clone() if p.numel() <= 20000 else
-                      {"sum": p.grad.double().sum(), "abssum": p.grad.double().abs().sum(),
-                       "head": p.grad.reshape(-1)[:256].clone(), "shape": tuple(p.shape)})
+                      {"abssum": p.grad.double().abs().sum(), "absmax": p.grad.abs().max(),
+                       "stride": max(1, p.numel() // 4096),
+                       "sample": p.grad.reshape(-1)[::max(1, p.numel() // 4096)].clone(), "shape": tuple(p.shape)})
                   for k, p in m.named_parameters()},
         "logit_scale_grad": loss_mod.logit_scale.grad.detach().clone(),
     }

@@ -238,7 +238,8 @@ def test_clip_small_against_reference_golden(dev, golden):
         ref = g["grads"][k]
         assert p.grad is not None, k
         if isinstance(ref, dict):
-            errs.append(_rel(p.grad.reshape(-1)[:256].cpu(), ref["head"]))
+            samp = p.grad.reshape(-1)[::ref["stride"]].cpu()
+            errs.append(((samp - ref["sample"]).abs().max() / ref["absmax"]).item())
             assert abs(p.grad.double().abs().sum().item() - ref["abssum"].item()) < 2e-2 * ref["abssum"].item(), k
         else:
             errs.append(_rel(p.grad.cpu(), ref))
