@@ -13,6 +13,7 @@
 // Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2..5 = epilogue.
 #include "common.cuh"
 #include "mmb200_internal.h"
+#include <stdlib.h>
 
 namespace mmb {
 
@@ -20,15 +21,22 @@ constexpr int BLOCK_M = 128;
 constexpr int BLOCK_N = 256;
 constexpr int BLOCK_K = 64;
 constexpr int UMMA_K = 16;
-constexpr int STAGES = 4;
 constexpr int ACC_STAGES = 2;
-constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
-constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;  // 32 KB
+constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB per CTA
+// 1-CTA mode: each CTA loads the whole 256-row B tile (32 KB), 4 stages.  CTA-pair mode (cta_group::2, 256x256 tile
+// per pair): each CTA loads its 128 rows of A and HALF of B (16 KB), 6 stages; the pair's MMA reads B from both CTAs'
+// shared memory, which halves the per-SM shared-memory and L2->SM traffic per flop.
+template <bool CTA2> struct Cfg {
+  static constexpr int LOAD_N = CTA2 ? 128 : 256;
+  static constexpr int B_BYTES = LOAD_N * BLOCK_K * 2;
+  static constexpr int STAGES = CTA2 ? 6 : 4;
+  static constexpr int TILE_M = CTA2 ? 256 : 128;
+};
 constexpr int SLAB_BYTES = 128 * 128;           // 128 rows x 128 B
 constexpr int NUM_SLABS = 2;
 constexpr int GEMM_THREADS = 192;
 constexpr int EPI_THREADS = 128;
-constexpr int GEMM_SMEM_BYTES = 1024 /*align slack*/ + STAGES * (A_BYTES + B_BYTES) + NUM_SLABS * SLAB_BYTES + 256;
+constexpr int GEMM_SMEM_BYTES = 1024 /*align slack*/ + 4 * (A_BYTES + 32768) + NUM_SLABS * SLAB_BYTES + 256;  // == 6 * (16K + 16K) + ...
 
 struct GemmArgs {
   int M, N, K;
@@ -43,13 +51,24 @@ struct GemmArgs {
 };
 
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 
-template <bool A_MN, bool B_MN, int EPI, int ACT>
+template <bool A_MN, bool B_MN, int EPI, int ACT, bool CTA2>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmD0, const __grid_constant__ CUtensorMap tmD1, const GemmArgs p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int STAGES = Cfg<CTA2>::STAGES, B_BYTES = Cfg<CTA2>::B_BYTES, LOAD_N = Cfg<CTA2>::LOAD_N;
+  constexpr int TILE_M = Cfg<CTA2>::TILE_M;
+  const uint32_t rank = CTA2 ? cluster_ctarank() : 0u;   // 0 = leader of the CTA pair (issues the MMAs)
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * A_BYTES;
   uint8_t* sSlab = smem + STAGES * (A_BYTES + B_BYTES);
@@ -73,25 +92,30 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     for (int i = 0; i < ACC_STAGES; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 4);  // one arrive per epilogue warp
+      mbar_init(&tempty_bar[i], CTA2 ? 8 : 4);  // one arrive per epilogue warp (of both CTAs of a pair)
     }
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, ACC_STAGES * BLOCK_N);
+  if (warp == 1) {
+    if (CTA2) tmem_alloc_2sm(tmem_slot, ACC_STAGES * BLOCK_N);
+    else      tmem_alloc(tmem_slot, ACC_STAGES * BLOCK_N);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (CTA2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   const int tiles_mn = p.m_tiles * p.n_tiles;
   const int total_tiles = tiles_mn * p.splits;
+  const int tile_first = CTA2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int tile_step = CTA2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      for (int t = tile_first; t < total_tiles; t += tile_step) {
         const int split = t / tiles_mn;
         const int rem = t - split * tiles_mn;
         const int m_blk = rem / p.n_tiles, n_blk = rem - m_blk * p.n_tiles;
@@ -99,24 +123,29 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full_bar[stage], A_BYTES + B_BYTES);
+          // CTA pair: only the leader arms its full barrier, with the bytes of BOTH CTAs; the peer's TMA loads
+          // complete_tx on the leader's barrier (cta_group::2 form).
+          if (!CTA2) mbar_arrive_expect_tx(&full_bar[stage], A_BYTES + B_BYTES);
+          else if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * (A_BYTES + B_BYTES));
           uint8_t* a_dst = sA + stage * A_BYTES;
           uint8_t* b_dst = sB + stage * B_BYTES;
+          const int m_row = m_blk * TILE_M + (int)rank * BLOCK_M;
+          const int n_row = n_blk * BLOCK_N + (int)rank * LOAD_N;
+          auto ld = [&](const CUtensorMap* m, void* dst, int c0, int c1) {
+            if (CTA2) tma_load_2d_2sm(m, &full_bar[stage], dst, c0, c1);
+            else      tma_load_2d(m, &full_bar[stage], dst, c0, c1);
+          };
           if (!A_MN) {
-            tma_load_2d(&tmA, &full_bar[stage], a_dst, kb * BLOCK_K, m_blk * BLOCK_M);
+            ld(&tmA, a_dst, kb * BLOCK_K, m_row);
           } else {
 #pragma unroll
-            for (int j = 0; j < BLOCK_M / 64; ++j)
-              tma_load_2d(&tmA, &full_bar[stage], a_dst + j * (64 * BLOCK_K * 2), m_blk * BLOCK_M + j * 64,
-                          kb * BLOCK_K);
+            for (int j = 0; j < BLOCK_M / 64; ++j) ld(&tmA, a_dst + j * (64 * BLOCK_K * 2), m_row + j * 64, kb * BLOCK_K);
           }
           if (!B_MN) {
-            tma_load_2d(&tmB, &full_bar[stage], b_dst, kb * BLOCK_K, n_blk * BLOCK_N);
+            ld(&tmB, b_dst, kb * BLOCK_K, n_row);
           } else {
 #pragma unroll
-            for (int j = 0; j < BLOCK_N / 64; ++j)
-              tma_load_2d(&tmB, &full_bar[stage], b_dst + j * (64 * BLOCK_K * 2), n_blk * BLOCK_N + j * 64,
-                          kb * BLOCK_K);
+            for (int j = 0; j < LOAD_N / 64; ++j) ld(&tmB, b_dst + j * (64 * BLOCK_K * 2), n_row + j * 64, kb * BLOCK_K);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -124,8 +153,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N, A_MN, B_MN);
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(TILE_M, BLOCK_N, A_MN, B_MN);
       // K-major SW128: 8-row groups 1024 B apart (SBO); LBO unused. MN-major SW128: 64-element MN blocks
       // (one TMA box, BLOCK_K rows x 128 B) 8192 B apart (LBO); 8-row k groups 1024 B apart (SBO).
       constexpr uint32_t A_LBO = A_MN ? 64 * BLOCK_K * 2 : 16, B_LBO = B_MN ? 64 * BLOCK_K * 2 : 16;
@@ -135,7 +164,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      for (int t = tile_first; t < total_tiles; t += tile_step) {
         const int split = t / tiles_mn;
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
@@ -149,13 +178,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           const uint64_t bdesc = make_smem_desc_sw128(smem_u32(sB + stage * B_BYTES), B_LBO, 1024);
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            umma_bf16(d_tmem, adesc + (uint64_t)((k * A_KSTEP) >> 4), bdesc + (uint64_t)((k * B_KSTEP) >> 4), idesc,
-                      (kb > kb0 || k > 0) ? 1u : 0u);
+            if (CTA2)
+              umma_bf16_2sm(d_tmem, adesc + (uint64_t)((k * A_KSTEP) >> 4), bdesc + (uint64_t)((k * B_KSTEP) >> 4),
+                            idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            else
+              umma_bf16(d_tmem, adesc + (uint64_t)((k * A_KSTEP) >> 4), bdesc + (uint64_t)((k * B_KSTEP) >> 4), idesc,
+                        (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);  // frees this smem stage once the MMAs above have read it
+          // frees this smem stage (in both CTAs of a pair) once the MMAs above have read it
+          if (CTA2) umma_commit_2sm(&empty_bar[stage], 3); else umma_commit(&empty_bar[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+        // accumulator complete -> epilogue (of both CTAs of a pair)
+        if (CTA2) umma_commit_2sm(&tfull_bar[acc], 3); else umma_commit(&tfull_bar[acc]);
         if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -167,11 +202,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     int acc = 0;
     uint32_t acc_phase = 0;
     int slab = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    for (int t = tile_first; t < total_tiles; t += tile_step) {
       const int split = t / tiles_mn;
       const int rem = t - split * tiles_mn;
       const int m_blk = rem / p.n_tiles, n_blk = rem - m_blk * p.n_tiles;
-      const int m0 = m_blk * BLOCK_M, n0 = n_blk * BLOCK_N;
+      const int m0 = m_blk * TILE_M + (int)rank * BLOCK_M, n0 = n_blk * BLOCK_N;
       const bool add_bias = (p.bias != nullptr) && (split == 0);
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
@@ -312,7 +347,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       // All TMEM reads of this accumulator stage are complete (tmem_ld_wait above) -> hand it back to the MMA warp.
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (lane == 0) {
+        if (CTA2 && rank != 0) mbar_arrive_cluster(&tempty_bar[acc], 0);  // the leader's MMA warp owns the wait
+        else mbar_arrive(&tempty_bar[acc]);
+      }
       if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
     }
     if (epi_tid == 0) tma_store_wait_all<0>();
@@ -320,10 +358,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
   __syncwarp();
   tc_fence_before();
-  __syncthreads();
+  if (CTA2) cluster_sync_all(); else __syncthreads();  // pair: nobody exits / frees while the peer still signals it
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, ACC_STAGES * BLOCK_N);
+    if (CTA2) tmem_dealloc_2sm(tmem_base, ACC_STAGES * BLOCK_N);
+    else      tmem_dealloc(tmem_base, ACC_STAGES * BLOCK_N);
   }
 }
 
@@ -372,10 +411,10 @@ int num_sms() {
   return g_num_sms;
 }
 
-template <bool A_MN, bool B_MN, int EPI, int ACT>
-static int launch(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tD0, const CUtensorMap& tD1,
-                  const GemmArgs& args, cudaStream_t stream) {
-  auto kfn = gemm_kernel<A_MN, B_MN, EPI, ACT>;
+template <bool A_MN, bool B_MN, int EPI, int ACT, bool CTA2>
+static int launch_impl(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tD0, const CUtensorMap& tD1,
+                       const GemmArgs& args, cudaStream_t stream) {
+  auto kfn = gemm_kernel<A_MN, B_MN, EPI, ACT, CTA2>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
@@ -383,9 +422,21 @@ static int launch(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMa
     attr_set = true;
   }
   const int total = args.m_tiles * args.n_tiles * args.splits;
-  const int grid = total < num_sms() ? total : num_sms();
-  kfn<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(tA, tB, tD0, tD1, args);
-  return (int)cudaGetLastError();
+  cudaLaunchConfig_t cfg{};
+  cudaLaunchAttribute attr[1];
+  if (CTA2) {
+    const int clusters = total < num_sms() / 2 ? total : num_sms() / 2;
+    cfg.gridDim = dim3(2 * clusters);
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+  } else {
+    cfg.gridDim = dim3(total < num_sms() ? total : num_sms());
+  }
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = GEMM_SMEM_BYTES;
+  cfg.stream = stream;
+  return (int)cudaLaunchKernelEx(&cfg, kfn, tA, tB, tD0, tD1, args);
 }
 
 }  // namespace mmb
@@ -400,9 +451,18 @@ extern "C" int mmb_gemm_bf16(const void* A, long long lda, int a_mn_major, const
   if (M <= 0 || N <= 0 || K <= 0) return MMB_ERR_ARG;
   if ((lda & 7) || (ldb & 7)) return MMB_ERR_ARG;
   if (epilogue == EPI_F32 ? (N & 3) : (N & 7)) return MMB_ERR_ARG;
+  // CTA-pair mode (cta_group::2, 256x256 tiles) for everything large enough to fill the 74 SM pairs at least once;
+  // MMB_GEMM_CTA2=0 forces the 1-CTA kernel (A/B testing), =1 forces pairs.
+  static int cta2_env = -2;
+  if (cta2_env == -2) {
+    const char* e = getenv("MMB_GEMM_CTA2");
+    cta2_env = e ? atoi(e) : -1;
+  }
+  const long long big_tiles = (long long)((M + 255) / 256) * ((N + BLOCK_N - 1) / BLOCK_N);
+  const bool cta2 = cta2_env == 1 || (cta2_env == -1 && M >= 512 && big_tiles * (splits < 1 ? 1 : splits) >= 37);
   GemmArgs g;
   g.M = M; g.N = N; g.K = K;
-  g.m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
+  g.m_tiles = cta2 ? (M + 255) / 256 : (M + BLOCK_M - 1) / BLOCK_M;
   g.n_tiles = (N + BLOCK_N - 1) / BLOCK_N;
   g.kb_total = (K + BLOCK_K - 1) / BLOCK_K;
   if (splits < 1) splits = 1;
@@ -423,7 +483,7 @@ extern "C" int mmb_gemm_bf16(const void* A, long long lda, int a_mn_major, const
   if (!a_mn_major) rc = make_tmap_2d(&tA, A, 2, false, K, M, lda * 2, 64, BLOCK_M);
   else             rc = make_tmap_2d(&tA, A, 2, false, M, K, lda * 2, 64, BLOCK_K);
   if (rc) return rc;
-  if (!b_mn_major) rc = make_tmap_2d(&tB, B, 2, false, K, N, ldb * 2, 64, BLOCK_N);
+  if (!b_mn_major) rc = make_tmap_2d(&tB, B, 2, false, K, N, ldb * 2, 64, cta2 ? 128 : BLOCK_N);
   else             rc = make_tmap_2d(&tB, B, 2, false, N, K, ldb * 2, 64, BLOCK_K);
   if (rc) return rc;
   if (epilogue == EPI_F32) {
@@ -444,9 +504,10 @@ extern "C" int mmb_gemm_bf16(const void* A, long long lda, int a_mn_major, const
   }
 
   const int am = a_mn_major ? 1 : 0, bm = b_mn_major ? 1 : 0;
-#define MMB_CASE(AM, BM, E, AC) \
-  if (am == AM && bm == BM && epilogue == E && (AC < 0 || act == AC))    \
-    return launch<(AM != 0), (BM != 0), E, (AC < 0 ? 0 : AC)>(tA, tB, tD0, tD1, g, stream);
+#define MMB_CASE(AM, BM, E, AC)                                                                             \
+  if (am == AM && bm == BM && epilogue == E && (AC < 0 || act == AC))                                       \
+    return cta2 ? launch_impl<(AM != 0), (BM != 0), E, (AC < 0 ? 0 : AC), true>(tA, tB, tD0, tD1, g, stream) \
+                : launch_impl<(AM != 0), (BM != 0), E, (AC < 0 ? 0 : AC), false>(tA, tB, tD0, tD1, g, stream);
   MMB_CASE(0, 0, EPI_BF16, -1)
   MMB_CASE(0, 0, EPI_BF16_ACT, ACT_QUICK_GELU)
   MMB_CASE(0, 0, EPI_BF16_ACT, ACT_GELU_ERF)

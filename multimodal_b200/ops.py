@@ -81,19 +81,22 @@ def gemm(A, B, *, a_mn=False, b_mn=False, epilogue=EPI_BF16, out=None, out2=None
     return (out, out2) if epilogue == EPI_BF16_ACT else out
 
 
-def wgrad_splits(out_rows: int, out_cols: int, k: int, n_sms: int = 148) -> int:
-    """Split-K factor for a weight-gradient GEMM so that the tile count fills the machine."""
-    tiles = ((out_rows + 127) // 128) * ((out_cols + 255) // 256)
+def wgrad_splits(out_rows: int, out_cols: int, k: int, n_units: int = 74) -> int:
+    """Split-K factor for a weight-gradient GEMM so that the (256 x 256, one per SM pair) tile count fills the machine."""
+    tiles = ((out_rows + 255) // 256) * ((out_cols + 255) // 256)
     kb = (k + 63) // 64
-    if tiles >= n_sms:
+    if tiles >= 2 * n_units:
         return 1
     best, best_eff = 1, 0.0
     for s in range(1, min(kb, 64) + 1):
-        waves = -(-tiles * s // n_sms)
-        eff = tiles * s / (waves * n_sms)
-        if eff > best_eff + 1e-9 or (abs(eff - best_eff) < 1e-9 and s < best):
-            if kb // s >= 8:  # keep each split's main loop long enough to amortise the prologue
-                best, best_eff = s, eff
+        if kb // s < 8:  # keep each split's main loop long enough to amortise the prologue
+            break
+        waves = -(-tiles * s // n_units)
+        eff = tiles * s / (waves * n_units)
+        if eff >= 0.9:  # smallest split that fills >= 90% of the last wave: every extra split adds reduce-add traffic
+            return s
+        if eff > best_eff + 1e-9:
+            best, best_eff = s, eff
     return best
 
 

@@ -27,13 +27,14 @@ def ptr(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
 
 
-def gemm(A, a_mn, B, b_mn, M, N, K, epi, act=0, alpha=1.0, bias=None, aux=None, splits=1, accumulate=0, D0=None):
+def gemm(A, a_mn, B, b_mn, M, N, K, epi, act=0, alpha=1.0, bias=None, aux=None, splits=1, accumulate=0, D0=None, D1=None):
     if epi == 3:
         D0 = torch.full((M, N), float("nan"), device=dev, dtype=torch.float32) if D0 is None else D0
         D1 = None
     else:
-        D0 = torch.full((M, N), float("nan"), device=dev, dtype=torch.bfloat16)
-        D1 = torch.full((M, N), float("nan"), device=dev, dtype=torch.bfloat16) if epi == 1 else None
+        D0 = torch.full((M, N), float("nan"), device=dev, dtype=torch.bfloat16) if D0 is None else D0
+        if epi == 1 and D1 is None:
+            D1 = torch.full((M, N), float("nan"), device=dev, dtype=torch.bfloat16)
     st = torch.cuda.current_stream().cuda_stream
     rc = L.mmb_gemm_bf16(ptr(A), A.stride(0), a_mn, ptr(B), B.stride(0), b_mn, ptr(D0), D0.stride(0), ptr(D1),
                          D1.stride(0) if D1 is not None else 0, M, N, K, epi, act, alpha, ptr(bias), ptr(aux),
@@ -98,13 +99,15 @@ def bench(M, N, K, a_mn, b_mn, epi, splits=1, iters=10, name=""):
     B = torch.randn((K, N) if b_mn else (N, K), device=dev).bfloat16()
     aux = torch.randn(M, N, device=dev).bfloat16() if epi == 2 else None
     bias = torch.randn(N, device=dev)
+    D0 = torch.empty((M, N), device=dev, dtype=torch.float32 if epi == 3 else torch.bfloat16)
+    D1 = torch.empty((M, N), device=dev, dtype=torch.bfloat16) if epi == 1 else None
     for _ in range(3):
-        gemm(A, a_mn, B, b_mn, M, N, K, epi, bias=bias, aux=aux, splits=splits)
+        gemm(A, a_mn, B, b_mn, M, N, K, epi, bias=bias, aux=aux, splits=splits, D0=D0, D1=D1, accumulate=int(epi == 3))
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(iters):
-        gemm(A, a_mn, B, b_mn, M, N, K, epi, bias=bias, aux=aux, splits=splits)
+        gemm(A, a_mn, B, b_mn, M, N, K, epi, bias=bias, aux=aux, splits=splits, D0=D0, D1=D1, accumulate=int(epi == 3))
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
@@ -112,11 +115,12 @@ def bench(M, N, K, a_mn, b_mn, epi, splits=1, iters=10, name=""):
     # cuBLAS reference point (library baseline, not the product)
     A2 = A.t() if a_mn else A
     B2 = B.t() if b_mn else B
+    Dc = torch.empty((M, N), device=dev, dtype=torch.bfloat16)
     for _ in range(3):
-        torch.matmul(A2, B2.t())
+        torch.matmul(A2, B2.t(), out=Dc)
     e0.record()
     for _ in range(iters):
-        torch.matmul(A2, B2.t())
+        torch.matmul(A2, B2.t(), out=Dc)
     e1.record()
     torch.cuda.synchronize()
     ms2 = e0.elapsed_time(e1) / iters
