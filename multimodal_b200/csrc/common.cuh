@@ -255,10 +255,20 @@ __device__ __forceinline__ float rcp_approx(float x) {
 __device__ __forceinline__ float fast_sigmoid(float z) {
   return rcp_approx(1.f + ex2_approx(-1.4426950408889634f * z));
 }
-__device__ __forceinline__ float quick_gelu(float x) { return x * fast_sigmoid(1.702f * x); }
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// sigmoid(1.702 x) = 0.5 + 0.5 tanh(0.851 x): ONE MUFU op (tanh.approx, rel. error 2^-11 < bf16 output rounding).
+__device__ __forceinline__ float quick_gelu(float x) {
+  const float t = tanh_approx(0.851f * x), h = 0.5f * x;
+  return fmaf(h, t, h);
+}
 __device__ __forceinline__ float quick_gelu_grad(float x) {
-  const float s = fast_sigmoid(1.702f * x);
-  return s * (1.f + 1.702f * x * (1.f - s));
+  const float s = fmaf(0.5f, tanh_approx(0.851f * x), 0.5f);
+  const float a = 1.702f * x;
+  return fmaf(s, fmaf(-a, s, a), s);  // s * (1 + a * (1 - s))
 }
 // Exact (erf) GELU, as nn.GELU() in the FLAVA / CoCa MLPs (torchmultimodal/modules/layers/mlp.py:35)
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }

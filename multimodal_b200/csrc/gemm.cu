@@ -10,7 +10,7 @@
 //
 // Tile: BLOCK_M=128 x BLOCK_N=256 x BLOCK_K=64, 4-stage smem ring (48 KB/stage), 2 TMEM accumulator stages
 // (2 x 256 fp32 columns = all 512 TMEM columns) so the epilogue of tile i overlaps the MMAs of tile i+1.
-// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2..5 = epilogue.
+// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2..9 = epilogue (two column halves).
 #include "common.cuh"
 #include "mmb200_internal.h"
 #include <stdlib.h>
@@ -34,8 +34,8 @@ template <bool CTA2> struct Cfg {
 };
 constexpr int SLAB_BYTES = 128 * 128;           // 128 rows x 128 B
 constexpr int NUM_SLABS = 2;
-constexpr int GEMM_THREADS = 192;
-constexpr int EPI_THREADS = 128;
+constexpr int GEMM_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int EPI_THREADS = 256;
 constexpr int GEMM_SMEM_BYTES = 1024 /*align slack*/ + 4 * (A_BYTES + 32768) + NUM_SLABS * SLAB_BYTES + 256;  // == 6 * (16K + 16K) + ...
 
 struct GemmArgs {
@@ -50,7 +50,8 @@ struct GemmArgs {
   int reduce_add;             // fp32 epilogue: TMA reduce-add instead of store
 };
 
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void half_bar_sync(int h) { asm volatile("bar.sync %0, 128;" ::"r"(2 + h) : "memory"); }
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -92,7 +93,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     for (int i = 0; i < ACC_STAGES; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], CTA2 ? 8 : 4);  // one arrive per epilogue warp (of both CTAs of a pair)
+      mbar_init(&tempty_bar[i], CTA2 ? 16 : 8);  // one arrive per epilogue warp (of both CTAs of a pair)
     }
     fence_mbar_init();
   }
@@ -195,10 +196,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
     }
   } else {
-    // ===================== Epilogue (warps 2..5) =====================
-    const int q = warp & 3;              // TMEM lane quadrant this warp may access
-    const int row = q * 32 + lane;       // row of the tile owned by this thread
-    const int epi_tid = threadIdx.x - 64;
+    // ===================== Epilogue (warps 2..9) =====================
+    // Thread == tile row (TMEM lane); the two warpgroups ("halves") split the columns so that every SM sub-partition
+    // has two epilogue warps to interleave (MUFU / tcgen05.ld latency hiding).
+    const int q = warp & 3;                   // TMEM lane quadrant this warp may access
+    const int half = (warp - 2) >> 2;         // 0: warps 2..5, 1: warps 6..9
+    const int row = q * 32 + lane;            // row of the tile owned by this thread
+    const int epi_tid = threadIdx.x - 64;     // 0..255
     int acc = 0;
     uint32_t acc_phase = 0;
     int slab = 0;
@@ -213,44 +217,43 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N;
 
       if (EPI == EPI_F32) {
-        // fp32 output: one 32-column chunk == one 128 B x 128 row slab.
-        for (int c = 0; c < BLOCK_N / 32; ++c) {
+        // fp32 output: a 32-column chunk is one 128 B x 128 row slab.  Half h owns chunks c == h (mod 2), slab h, named
+        // barrier 1+h and its own TMA bulk-group accounting (issued by its first thread).
+        const int htid = epi_tid & 127;
+        uint8_t* myslab = sSlab + half * SLAB_BYTES;
+        for (int c = half; c < BLOCK_N / 32; c += 2) {
           if (n0 + c * 32 >= p.N) break;
           uint32_t v[32];
           tmem_ld32(t_addr + c * 32, v);
-          if (epi_tid == 0) tma_store_wait_read<NUM_SLABS - 1>();
+          if (htid == 0) tma_store_wait_read<0>();
           tmem_ld_wait();
-          epi_bar_sync();
-          uint8_t* dst = sSlab + slab * SLAB_BYTES + row * 128;
+          half_bar_sync(half);
+          uint8_t* dst = myslab + row * 128;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             float4 o;
             const int n = n0 + c * 32 + j * 4;
-            float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (add_bias && n < p.N) b = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-            o.x = __uint_as_float(v[j * 4 + 0]) * p.alpha + b.x;
-            o.y = __uint_as_float(v[j * 4 + 1]) * p.alpha + b.y;
-            o.z = __uint_as_float(v[j * 4 + 2]) * p.alpha + b.z;
-            o.w = __uint_as_float(v[j * 4 + 3]) * p.alpha + b.w;
+            float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (add_bias && n < p.N) bb = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+            o.x = __uint_as_float(v[j * 4 + 0]) * p.alpha + bb.x;
+            o.y = __uint_as_float(v[j * 4 + 1]) * p.alpha + bb.y;
+            o.z = __uint_as_float(v[j * 4 + 2]) * p.alpha + bb.z;
+            o.w = __uint_as_float(v[j * 4 + 3]) * p.alpha + bb.w;
             *reinterpret_cast<float4*>(dst + ((j ^ (row & 7)) << 4)) = o;
           }
           fence_proxy_async_smem();
-          epi_bar_sync();
-          if (epi_tid == 0) {
-            if (p.reduce_add)
-              tma_reduce_add_2d(&tmD0, sSlab + slab * SLAB_BYTES, n0 + c * 32, m0);
-            else
-              tma_store_2d(&tmD0, sSlab + slab * SLAB_BYTES, n0 + c * 32, m0);
+          half_bar_sync(half);
+          if (htid == 0) {
+            if (p.reduce_add) tma_reduce_add_2d(&tmD0, myslab, n0 + c * 32, m0);
+            else              tma_store_2d(&tmD0, myslab, n0 + c * 32, m0);
             tma_store_commit();
           }
-          slab ^= 1;
         }
       } else {
-        // bf16 outputs.  Per 64-column group: TMEM -> registers -> (bias / activation / act') -> bf16 -> swizzled
-        // smem slab (thread == row) -> one named barrier -> row-contiguous coalesced 16 B st.global (4 rows of
-        // 128 B per warp instruction).  Two slab sets alternate, so one barrier per group is sufficient.
-        // EPI_BF16_ACT writes two tensors (D0 = pre-activation, D1 = act(D0)) and therefore uses both slabs per
-        // group (two barriers per group).
+        // bf16 outputs.  Per 64-column group: each half converts its 32 columns (TMEM -> registers -> bias /
+        // activation / act' -> bf16) into the swizzled smem slab (thread == row), one 256-thread named barrier, then a
+        // row-contiguous coalesced 16 B copy-out (8 rows of 128 B per warp instruction).  Slabs alternate, so one
+        // barrier per group suffices; EPI_BF16_ACT writes two tensors and uses both slabs per group (two barriers).
         constexpr bool DUAL = (EPI == EPI_BF16_ACT);
         __nv_bfloat16* D0p = reinterpret_cast<__nv_bfloat16*>(p.d0);
         __nv_bfloat16* D1p = reinterpret_cast<__nv_bfloat16*>(p.d1);
@@ -259,8 +262,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           if (DUAL) epi_bar_sync();  // both slabs are rewritten every group
           uint8_t* dst0 = sSlab + (DUAL ? 0 : slab * SLAB_BYTES) + row * 128;
           uint8_t* dst1 = sSlab + SLAB_BYTES + row * 128;
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
+          {
+            const int h = half;
             uint32_t v[32];
             tmem_ld32(t_addr + g * 64 + h * 32, v);
             const int nb = n0 + g * 64 + h * 32;
@@ -322,14 +325,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
           }
           epi_bar_sync();
-          // coalesced copy-out: 128 rows x 8 chunks of 16 B; thread -> (row = it*16 + tid/8, chunk = tid%8)
+          // coalesced copy-out: 128 rows x 8 chunks of 16 B; thread -> (row = it*32 + tid/8, chunk = tid%8)
           {
             const int ch = epi_tid & 7;
             const int ncol = n0 + g * 64 + ch * 8;
             const uint8_t* s0 = sSlab + (DUAL ? 0 : slab * SLAB_BYTES);
 #pragma unroll
-            for (int it = 0; it < 8; ++it) {
-              const int r = it * 16 + (epi_tid >> 3);
+            for (int it = 0; it < 4; ++it) {
+              const int r = it * 32 + (epi_tid >> 3);
               if (m0 + r < p.M && ncol < p.N) {
                 const int off = r * 128 + ((ch ^ (r & 7)) << 4);
                 const uint4 val = *reinterpret_cast<const uint4*>(s0 + off);
@@ -353,7 +356,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
       if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
     }
-    if (epi_tid == 0) tma_store_wait_all<0>();
+    if ((epi_tid & 127) == 0) tma_store_wait_all<0>();
   }
 
   __syncwarp();
