@@ -26,10 +26,12 @@ constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB per CTA
 // 1-CTA mode: each CTA loads the whole 256-row B tile (32 KB), 4 stages.  CTA-pair mode (cta_group::2, 256x256 tile
 // per pair): each CTA loads its 128 rows of A and HALF of B (16 KB), 6 stages; the pair's MMA reads B from both CTAs'
 // shared memory, which halves the per-SM shared-memory and L2->SM traffic per flop.
-template <bool CTA2> struct Cfg {
+template <bool CTA2, int EPI> struct Cfg {
   static constexpr int LOAD_N = CTA2 ? 128 : 256;
   static constexpr int B_BYTES = LOAD_N * BLOCK_K * 2;
-  static constexpr int STAGES = CTA2 ? 6 : 4;
+  // EPI_BF16_DACT gives one ring stage (32 / 48 KB) to two 16 KB slabs into which the act'(aux) operand is
+  // TMA-prefetched while the tile's MMAs are still running.
+  static constexpr int STAGES = (CTA2 ? 6 : 4) - (EPI == EPI_BF16_DACT ? 1 : 0);
   static constexpr int TILE_M = CTA2 ? 256 : 128;
 };
 constexpr int SLAB_BYTES = 128 * 128;           // 128 rows x 128 B
@@ -67,18 +69,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const __grid_constant__ CUtensorMap tmD0, const __grid_constant__ CUtensorMap tmD1, const GemmArgs p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  constexpr int STAGES = Cfg<CTA2>::STAGES, B_BYTES = Cfg<CTA2>::B_BYTES, LOAD_N = Cfg<CTA2>::LOAD_N;
-  constexpr int TILE_M = Cfg<CTA2>::TILE_M;
+  constexpr int STAGES = Cfg<CTA2, EPI>::STAGES, B_BYTES = Cfg<CTA2, EPI>::B_BYTES, LOAD_N = Cfg<CTA2, EPI>::LOAD_N;
+  constexpr int TILE_M = Cfg<CTA2, EPI>::TILE_M;
   const uint32_t rank = CTA2 ? cluster_ctarank() : 0u;   // 0 = leader of the CTA pair (issues the MMAs)
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * A_BYTES;
   uint8_t* sSlab = smem + STAGES * (A_BYTES + B_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sSlab + NUM_SLABS * SLAB_BYTES);
+  uint8_t* sAux = sSlab + NUM_SLABS * SLAB_BYTES;   // 2 slabs, EPI_BF16_DACT only
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sSlab + (EPI == EPI_BF16_DACT ? 2 : 1) * NUM_SLABS * SLAB_BYTES);
   uint64_t* full_bar = bars;                   // [STAGES]
   uint64_t* empty_bar = bars + STAGES;         // [STAGES]
   uint64_t* tfull_bar = bars + 2 * STAGES;     // [ACC_STAGES]
   uint64_t* tempty_bar = bars + 2 * STAGES + ACC_STAGES;  // [ACC_STAGES]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2 * ACC_STAGES);
+  uint64_t* aux_bar = bars + 2 * STAGES + 2 * ACC_STAGES;  // [2] aux slab landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2 * ACC_STAGES + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -87,6 +91,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     if (EPI == EPI_F32) tma_prefetch_desc(&tmD0);
+    if (EPI == EPI_BF16_DACT) { tma_prefetch_desc(&tmD1); mbar_init(&aux_bar[0], 1); mbar_init(&aux_bar[1], 1); }
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
@@ -206,12 +211,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     int acc = 0;
     uint32_t acc_phase = 0;
     int slab = 0;
+    uint32_t aux_phase = 0;  // bit b = parity of aux slab b
     for (int t = tile_first; t < total_tiles; t += tile_step) {
       const int split = t / tiles_mn;
       const int rem = t - split * tiles_mn;
       const int m_blk = rem / p.n_tiles, n_blk = rem - m_blk * p.n_tiles;
       const int m0 = m_blk * TILE_M + (int)rank * BLOCK_M, n0 = n_blk * BLOCK_N;
       const bool add_bias = (p.bias != nullptr) && (split == 0);
+      if (EPI == EPI_BF16_DACT && epi_tid == 0) {
+        // prefetch the act' operand of the first two 64-column groups while this tile's MMAs are still in flight
+#pragma unroll
+        for (int g = 0; g < 2; ++g)
+          if (n0 + g * 64 < p.N) {
+            mbar_arrive_expect_tx(&aux_bar[g], SLAB_BYTES);
+            tma_load_2d(&tmD1, &aux_bar[g], sAux + g * SLAB_BYTES, n0 + g * 64, m0);
+          }
+      }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N;
@@ -269,13 +284,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const int nb = n0 + g * 64 + h * 32;
             uint4 auxv[4];
             if (EPI == EPI_BF16_DACT) {
-              const bool ok = (m0 + row) < p.M;
+              mbar_wait(&aux_bar[g & 1], (aux_phase >> (g & 1)) & 1);
+              const uint8_t* arow = sAux + (g & 1) * SLAB_BYTES + row * 128;
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                auxv[j] = make_uint4(0, 0, 0, 0);
-                if (ok && nb + j * 8 < p.N)
-                  auxv[j] = __ldg(reinterpret_cast<const uint4*>(p.aux + (long long)(m0 + row) * p.ld_aux + nb + j * 8));
-              }
+              for (int j = 0; j < 4; ++j)
+                auxv[j] = *reinterpret_cast<const uint4*>(arow + (((h * 4 + j) ^ (row & 7)) << 4));
             }
             tmem_ld_wait();
 #pragma unroll
@@ -325,6 +338,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
           }
           epi_bar_sync();
+          if (EPI == EPI_BF16_DACT) {
+            aux_phase ^= 1u << (g & 1);
+            if (epi_tid == 0 && g + 2 < BLOCK_N / 64 && n0 + (g + 2) * 64 < p.N) {  // slab (g & 1) is free again
+              mbar_arrive_expect_tx(&aux_bar[g & 1], SLAB_BYTES);
+              tma_load_2d(&tmD1, &aux_bar[g & 1], sAux + (g & 1) * SLAB_BYTES, n0 + (g + 2) * 64, m0);
+            }
+          }
           // coalesced copy-out: 128 rows x 8 chunks of 16 B; thread -> (row = it*32 + tid/8, chunk = tid%8)
           {
             const int ch = epi_tid & 7;
@@ -504,6 +524,10 @@ extern "C" int mmb_gemm_bf16(const void* A, long long lda, int a_mn_major, const
     if (epilogue == EPI_BF16_DACT && (!aux || (ld_aux & 7) || (reinterpret_cast<uintptr_t>(aux) & 15))) return MMB_ERR_ARG;
     tD0 = tA;  // unused by the bf16 epilogues
     tD1 = tA;
+    if (epilogue == EPI_BF16_DACT) {  // act' operand, TMA-prefetched in 128-row x 64-column slabs
+      rc = make_tmap_2d(&tD1, aux, 2, false, N, M, ld_aux * 2, 64, 128);
+      if (rc) return rc;
+    }
   }
 
   const int am = a_mn_major ? 1 : 0, bm = b_mn_major ? 1 : 0;

@@ -136,7 +136,7 @@ def main():
         (256, 256, 128, 0, 1, 3, 1), (1000, 768, 264, 0, 1, 0, 1), (640, 512, 512, 0, 1, 2, 1),
         (256, 256, 128, 1, 1, 3, 1), (768, 768, 4096, 1, 1, 3, 4), (1000, 520, 1000, 1, 1, 3, 3),
         (256, 256, 128, 1, 0, 3, 1),
-        (4096, 2304, 768, 0, 0, 0, 1),
+        (4096, 2304, 768, 0, 0, 0, 1), (5000, 3072, 768, 0, 1, 2, 1), (5000, 3072, 768, 0, 0, 1, 1),
     ]
     for c in cases:
         try:
