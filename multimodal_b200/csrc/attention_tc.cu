@@ -25,6 +25,7 @@ struct AttnTcArgs {
   const __nv_bfloat16* o_in;    // bwd: O
   const __nv_bfloat16* dout;    // bwd: dO [B*S, d]
   __nv_bfloat16* dqkv;          // bwd: [B*S, 3d]
+  float* dsum;                  // bwd: rowsum(dO * O) [B,H,S], written by the dQ kernel, read by the dK/dV kernel
 };
 
 __device__ __forceinline__ uint64_t desc_k(uint32_t saddr) { return make_smem_desc_sw128(saddr, 16, 1024); }
@@ -179,65 +180,81 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
 }
 
 // ------------------------------------------------------------------------------------------------
-// Backward, shared chunk machinery.
-//   MODE_DQ  : tile rows = queries  (A0 = Q tile, A1 = dO tile; B chunks from K / V; accumulate dQ with B2 = K)
-//   MODE_DKDV: tile rows = keys     (A0 = K tile, A1 = V tile;  B chunks from Q / dO; accumulate dV (B2 = dO), dK (B2 = Q))
-// TMEM columns: S[2] @0,64 ; dP[2] @128,192 ; acc0 @256 ; acc1 @320.
+// Backward.  One skeleton, two roles:
+//   DQ   : tile rows = queries  (resident A0 = Q tile, A1 = dO tile; chunk ring streams K_c / V_c;
+//          acc0 = dQ += dS_c K_c)                                           -> also stores D = rowsum(dO * O)
+//   DKDV : tile rows = keys     (resident A0 = K tile, A1 = V tile;  chunk ring streams Q_c / dO_c;
+//          acc0 = dV += P^T_c dO_c, acc1 = dK += dS^T_c Q_c)
+// 64-wide chunks of the other sequence dimension are TMA-streamed through a small ring; TMEM holds S_c, dP_c and
+// the accumulators (256 columns) and shared memory stays under 100 KB, so TWO CTAs are resident per SM and one
+// CTA's softmax arithmetic overlaps the other's MMAs / loads.
+// TMEM columns: S @0 ; dP @64 ; acc0 @128 ; acc1 @192.
 // ------------------------------------------------------------------------------------------------
 template <bool CAUSAL, bool DKDV>
-__global__ void __launch_bounds__(ATT_THREADS, 1)
-attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_constant__ CUtensorMap tmQKVPad,
-                   const __grid_constant__ CUtensorMap tmDO128, const __grid_constant__ CUtensorMap tmDOPad,
+__global__ void __launch_bounds__(ATT_THREADS, 2)
+attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_constant__ CUtensorMap tmQKV64,
+                   const __grid_constant__ CUtensorMap tmDO128, const __grid_constant__ CUtensorMap tmDO64,
                    const AttnTcArgs p) {
+  constexpr int RING = DKDV ? 2 : 3;
+  constexpr int CH = 8192;  // one 64-row x 128 B chunk operand
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sA0 = smem;                 // 16 KB  tile operand 0 (Q | K_j)
-  uint8_t* sA1 = smem + ATOM;          // 16 KB  tile operand 1 (dO | V_j)
-  uint8_t* sB0 = smem + 2 * ATOM;      // 32 KB  full-length operand 0 (K | Q)
-  uint8_t* sB1 = smem + 4 * ATOM;      // 32 KB  full-length operand 1 (V | dO)
-  uint8_t* sDS = smem + 6 * ATOM;      // 2 x 16 KB  dS chunk (double buffered)
-  uint8_t* sPT = smem + 8 * ATOM;      // 2 x 16 KB  P^T chunk (DKDV only)
-  float* sL = reinterpret_cast<float*>(smem + (DKDV ? 10 : 8) * ATOM);  // [256] lse (log2 units) per q (DKDV only)
-  float* sD = sL + 256;                                                  // [256] rowsum(dO*O) per q (DKDV only)
+  uint8_t* sA0 = smem;                        // 16 KB  tile operand 0 (Q | K_j)
+  uint8_t* sA1 = smem + ATOM;                 // 16 KB  tile operand 1 (dO | V_j)
+  uint8_t* sRing = smem + 2 * ATOM;           // RING x (B0_c 8 KB | B1_c 8 KB)
+  uint8_t* sDS = sRing + RING * 2 * CH;       // 16 KB  dS chunk (K-major A operand)
+  uint8_t* sPT = sDS + ATOM;                  // 16 KB  P^T chunk (DKDV only)
+  float* sL = reinterpret_cast<float*>(sDS + (DKDV ? 2 : 1) * ATOM);  // [256] lse (log2 units) per q (DKDV only)
+  float* sD = sL + 256;                                                // [256] rowsum(dO*O) per q (DKDV only)
   uint64_t* bars = reinterpret_cast<uint64_t*>(sD + 256);
-  uint64_t* bar_load = bars;        // [1]
-  uint64_t* bar_s = bars + 1;       // [2] S/dP chunk ready
-  uint64_t* bar_acc = bars + 3;     // [2] accumulate-MMAs of a chunk done (dS / P^T buffers reusable)
-  uint64_t* bar_done = bars + 5;    // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+  uint64_t* bar_tile = bars;        // [1] A0/A1 landed
+  uint64_t* bar_ld = bars + 1;      // [RING] chunk operands landed
+  uint64_t* bar_s = bars + 4;       // [1] S_c/dP_c ready (parity c & 1)
+  uint64_t* bar_acc = bars + 5;     // [1] accumulate-MMAs of chunk c done (parity c & 1)
+  uint64_t* bar_done = bars + 6;    // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tile = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int S = p.S, S_pad = p.S_pad, d = p.H * 64;
   const int row0 = b * S;
+  const int nc = (S_pad + 63) >> 6;
   if (threadIdx.x == 0) {
-    tma_prefetch_desc(&tmQKV128); tma_prefetch_desc(&tmQKVPad);
-    tma_prefetch_desc(&tmDO128); tma_prefetch_desc(&tmDOPad);
-    mbar_init(bar_load, 1);
-    mbar_init(&bar_s[0], 1); mbar_init(&bar_s[1], 1);
-    mbar_init(&bar_acc[0], 1); mbar_init(&bar_acc[1], 1);
-    mbar_init(bar_done, 1);
+    tma_prefetch_desc(&tmQKV128); tma_prefetch_desc(&tmQKV64);
+    tma_prefetch_desc(&tmDO128); tma_prefetch_desc(&tmDO64);
+    mbar_init(bar_tile, 1);
+    for (int i = 0; i < RING; ++i) mbar_init(&bar_ld[i], 1);
+    mbar_init(bar_s, 1); mbar_init(bar_acc, 1); mbar_init(bar_done, 1);
     fence_mbar_init();
   }
-  if (warp == 0) tmem_alloc(tmem_slot, 512);
+  if (warp == 0) tmem_alloc(tmem_slot, 256);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (threadIdx.x == 0) {
-    mbar_arrive_expect_tx(bar_load, 2 * ATOM + 2 * S_pad * 128);
+  auto load_chunk = [&](int c) {  // thread 0 only
+    const int st = c % RING;
+    uint8_t* dst = sRing + st * 2 * CH;
+    mbar_arrive_expect_tx(&bar_ld[st], 2 * CH);
     if (!DKDV) {
-      tma_load_2d(&tmQKV128, bar_load, sA0, h * 64, row0 + tile * 128);            // Q tile
-      tma_load_2d(&tmDO128, bar_load, sA1, h * 64, row0 + tile * 128);             // dO tile
-      tma_load_2d(&tmQKVPad, bar_load, sB0, d + h * 64, row0);                     // K
-      tma_load_2d(&tmQKVPad, bar_load, sB1, 2 * d + h * 64, row0);                 // V
+      tma_load_2d(&tmQKV64, &bar_ld[st], dst, d + h * 64, row0 + c * 64);          // K_c
+      tma_load_2d(&tmQKV64, &bar_ld[st], dst + CH, 2 * d + h * 64, row0 + c * 64);  // V_c
     } else {
-      tma_load_2d(&tmQKV128, bar_load, sA0, d + h * 64, row0 + tile * 128);        // K tile
-      tma_load_2d(&tmQKV128, bar_load, sA1, 2 * d + h * 64, row0 + tile * 128);    // V tile
-      tma_load_2d(&tmQKVPad, bar_load, sB0, h * 64, row0);                         // Q
-      tma_load_2d(&tmDOPad, bar_load, sB1, h * 64, row0);                          // dO
+      tma_load_2d(&tmQKV64, &bar_ld[st], dst, h * 64, row0 + c * 64);               // Q_c
+      tma_load_2d(&tmDO64, &bar_ld[st], dst + CH, h * 64, row0 + c * 64);            // dO_c
     }
+  };
+  if (threadIdx.x == 0) {
+    mbar_arrive_expect_tx(bar_tile, 2 * ATOM);
+    if (!DKDV) {
+      tma_load_2d(&tmQKV128, bar_tile, sA0, h * 64, row0 + tile * 128);           // Q tile
+      tma_load_2d(&tmDO128, bar_tile, sA1, h * 64, row0 + tile * 128);            // dO tile
+    } else {
+      tma_load_2d(&tmQKV128, bar_tile, sA0, d + h * 64, row0 + tile * 128);       // K tile
+      tma_load_2d(&tmQKV128, bar_tile, sA1, 2 * d + h * 64, row0 + tile * 128);   // V tile
+    }
+    for (int c = 0; c < RING && c < nc; ++c) load_chunk(c);
   }
 
   const int q4 = warp & 3, grp = warp >> 2;
@@ -245,7 +262,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_co
   const int ri = tile * 128 + r;  // global index of this thread's row (query for DQ, key for DKDV)
   const uint32_t trow = tmem + ((uint32_t)(q4 * 32) << 16);
 
-  // per-row / per-column softmax statistics
+  // softmax statistics: per row (DQ; also published for the DKDV kernel) or per column via smem (DKDV)
   float Lrow = 0.f, Drow = 0.f;
   if (!DKDV) {
     if (ri < S) {
@@ -261,107 +278,99 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_co
       }
       Drow = acc;
       Lrow = p.lse[((long long)b * p.H + h) * S + ri] * 1.4426950408889634f;
+      if (grp == 0) p.dsum[((long long)b * p.H + h) * S + ri] = acc;
     }
   } else {
     const int qi = threadIdx.x;  // 256 threads cover S_pad <= 256 query columns
-    float acc = 0.f, L = 0.f;
-    if (qi < S) {
-      const uint4* po = reinterpret_cast<const uint4*>(p.o_in + (long long)(row0 + qi) * d + h * 64);
-      const uint4* pd = reinterpret_cast<const uint4*>(p.dout + (long long)(row0 + qi) * d + h * 64);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const uint4 a = __ldg(po + j), c = __ldg(pd + j);
-        acc += bf16_lo(a.x) * bf16_lo(c.x) + bf16_hi(a.x) * bf16_hi(c.x) + bf16_lo(a.y) * bf16_lo(c.y) +
-               bf16_hi(a.y) * bf16_hi(c.y) + bf16_lo(a.z) * bf16_lo(c.z) + bf16_hi(a.z) * bf16_hi(c.z) +
-               bf16_lo(a.w) * bf16_lo(c.w) + bf16_hi(a.w) * bf16_hi(c.w);
-      }
-      L = p.lse[((long long)b * p.H + h) * S + qi] * 1.4426950408889634f;
-    }
-    sL[qi] = L;
-    sD[qi] = acc;
+    const bool ok = qi < S;
+    sL[qi] = ok ? p.lse[((long long)b * p.H + h) * S + qi] * 1.4426950408889634f : 0.f;
+    sD[qi] = ok ? p.dsum[((long long)b * p.H + h) * S + qi] : 0.f;
     __syncthreads();
   }
 
-  const int nc = (S_pad + 63) >> 6;
-  const uint32_t uA0 = smem_u32(sA0), uA1 = smem_u32(sA1), uB0 = smem_u32(sB0), uB1 = smem_u32(sB1);
+  const uint32_t uA0 = smem_u32(sA0), uA1 = smem_u32(sA1), uRing = smem_u32(sRing);
   const uint32_t uDS = smem_u32(sDS), uPT = smem_u32(sPT);
 
-  auto issue_scores = [&](int c) {  // S_c / dP_c (or their transposes) into TMEM buffer c & 1
+  auto issue_scores = [&](int c) {  // S_c / dP_c (or their transposes); thread 0 only, chunk c's operands have landed
     const int wc = min(64, S_pad - c * 64);
     const uint32_t id = idesc_rt(wc, false, false);
-    const uint64_t a0 = desc_k(uA0), a1 = desc_k(uA1);
-    const uint64_t b0 = desc_k(uB0 + c * 8192), b1 = desc_k(uB1 + c * 8192);
-    const uint32_t ts = tmem + (c & 1) * 64, tp = tmem + 128 + (c & 1) * 64;
+    const uint32_t ub = uRing + (c % RING) * 2 * CH;
+    const uint64_t a0 = desc_k(uA0), a1 = desc_k(uA1), b0 = desc_k(ub), b1 = desc_k(ub + CH);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) umma_bf16(ts, a0 + 2 * k, b0 + 2 * k, id, k > 0);
+    for (int k = 0; k < 4; ++k) umma_bf16(tmem, a0 + 2 * k, b0 + 2 * k, id, k > 0);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) umma_bf16(tp, a1 + 2 * k, b1 + 2 * k, id, k > 0);
-    umma_commit(&bar_s[c & 1]);
+    for (int k = 0; k < 4; ++k) umma_bf16(tmem + 64, a1 + 2 * k, b1 + 2 * k, id, k > 0);
+    umma_commit(bar_s);
   };
 
   if (threadIdx.x == 0) {
-    mbar_wait(bar_load, 0);
+    mbar_wait(bar_tile, 0);
+    mbar_wait(&bar_ld[0], 0);
     tc_fence_after();
     issue_scores(0);
   }
 
   for (int c = 0; c < nc; ++c) {
     const int wc = min(64, S_pad - c * 64);
-    if (threadIdx.x == 0 && c + 1 < nc) issue_scores(c + 1);  // runs under this chunk's elementwise work
-    if (c >= 2) mbar_wait(&bar_acc[c & 1], ((c >> 1) - 1) & 1);  // dS / P^T buffer (c & 1) free again
-    mbar_wait(&bar_s[c & 1], (c >> 1) & 1);
+    mbar_wait(bar_s, c & 1);
     tc_fence_after();
-    // this thread: row r, columns [grp*32, grp*32+32) of the chunk
-    if (grp * 32 < wc) {
-      uint32_t sv[32], dv[32];
-      tmem_ld32(trow + (c & 1) * 64 + grp * 32, sv);
-      tmem_ld32(trow + 128 + (c & 1) * 64 + grp * 32, dv);
+    // this thread: row r, columns [grp*32, grp*32+32) of the chunk, processed as two 16-column halves
+    float ds[2][16], pt[2][16];
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      uint32_t sv[16], dv[16];
+      tmem_ld16(trow + grp * 32 + half * 16, sv);
+      tmem_ld16(trow + 64 + grp * 32 + half * 16, dv);
       tmem_ld_wait();
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        float ds[16], pt[16];
-#pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          const int cj = c * 64 + grp * 32 + half * 16 + e;  // global column index (key for DQ, query for DKDV)
-          bool valid;
-          float L, Dv;
-          if (!DKDV) {
-            valid = (ri < S) && (cj < S) && (!CAUSAL || cj <= ri);
-            L = Lrow; Dv = Drow;
-          } else {
-            valid = (ri < S) && (cj < S) && (!CAUSAL || ri <= cj);
-            L = sL[cj & 255]; Dv = sD[cj & 255];
-          }
-          const float pv = valid ? ex2_approx(__uint_as_float(sv[half * 16 + e]) * p.scale_log2 - L) : 0.f;
-          pt[e] = pv;
-          ds[e] = pv * (__uint_as_float(dv[half * 16 + e]) - Dv) * p.scale;
+      for (int e = 0; e < 16; ++e) {
+        const int cj = c * 64 + grp * 32 + half * 16 + e;  // global column index (key for DQ, query for DKDV)
+        bool valid;
+        float L, Dv;
+        if (!DKDV) {
+          valid = (ri < S) && (cj < S) && (!CAUSAL || cj <= ri);
+          L = Lrow; Dv = Drow;
+        } else {
+          valid = (ri < S) && (cj < S) && (!CAUSAL || ri <= cj);
+          L = sL[cj & 255]; Dv = sD[cj & 255];
         }
-        if (grp * 32 + half * 16 < wc) {
-          store_p16(sDS + (c & 1) * ATOM, r, grp * 32 + half * 16, ds);
-          if (DKDV) store_p16(sPT + (c & 1) * ATOM, r, grp * 32 + half * 16, pt);
-        }
+        const float pv = valid ? ex2_approx(__uint_as_float(sv[e]) * p.scale_log2 - L) : 0.f;
+        pt[half][e] = pv;
+        ds[half][e] = pv * (__uint_as_float(dv[e]) - Dv) * p.scale;
       }
     }
+    if (c >= 1) {
+      mbar_wait(bar_acc, (c - 1) & 1);  // accumulate-MMAs of chunk c-1 done: dS / P^T buffers and ring stage (c-1)%RING free
+      if (threadIdx.x == 0 && c + RING - 1 < nc) load_chunk(c + RING - 1);
+    }
+#pragma unroll
+    for (int half = 0; half < 2; ++half)
+      if (grp * 32 + half * 16 < wc) {
+        store_p16(sDS, r, grp * 32 + half * 16, ds[half]);
+        if (DKDV) store_p16(sPT, r, grp * 32 + half * 16, pt[half]);
+      }
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
     if (threadIdx.x == 0) {
       tc_fence_after();
+      if (c + 1 < nc) {  // next chunk's scores first: they are what the other threads wait for
+        mbar_wait(&bar_ld[(c + 1) % RING], ((c + 1) / RING) & 1);
+        issue_scores(c + 1);
+      }
       const uint32_t id = idesc_rt(64, false, true);
+      const uint32_t ub = uRing + (c % RING) * 2 * CH;
       const int ks = wc >> 4;
       if (!DKDV) {   // dQ += dS_c K_c
         for (int k = 0; k < ks; ++k)
-          umma_bf16(tmem + 256, desc_k(uDS + (c & 1) * ATOM + k * 32), desc_mn(uB0 + c * 8192 + k * 2048), id,
-                    (c > 0 || k > 0));
+          umma_bf16(tmem + 128, desc_k(uDS + k * 32), desc_mn(ub + k * 2048), id, (c > 0 || k > 0));
       } else {       // dV += P^T_c dO_c ; dK += dS^T_c Q_c
         for (int k = 0; k < ks; ++k)
-          umma_bf16(tmem + 256, desc_k(uPT + (c & 1) * ATOM + k * 32), desc_mn(uB1 + c * 8192 + k * 2048), id,
-                    (c > 0 || k > 0));
+          umma_bf16(tmem + 128, desc_k(uPT + k * 32), desc_mn(ub + CH + k * 2048), id, (c > 0 || k > 0));
         for (int k = 0; k < ks; ++k)
-          umma_bf16(tmem + 320, desc_k(uDS + (c & 1) * ATOM + k * 32), desc_mn(uB0 + c * 8192 + k * 2048), id,
-                    (c > 0 || k > 0));
+          umma_bf16(tmem + 192, desc_k(uDS + k * 32), desc_mn(ub + k * 2048), id, (c > 0 || k > 0));
       }
-      umma_commit(&bar_acc[c & 1]);
+      umma_commit(bar_acc);
       if (c == nc - 1) umma_commit(bar_done);
     }
   }
@@ -369,12 +378,15 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_co
   tc_fence_after();
   {
     const long long ld = 3LL * d;
-    if (!DKDV) {
+#pragma unroll
+    for (int which = 0; which < (DKDV ? 2 : 1); ++which) {
+      // DQ: acc0 -> Q block.  DKDV: acc0 = dV -> V block (2d), acc1 = dK -> K block (d)
       uint32_t v[32];
-      tmem_ld32(trow + 256 + grp * 32, v);
+      tmem_ld32(trow + 128 + which * 64 + grp * 32, v);
       tmem_ld_wait();
       if (ri < S) {
-        __nv_bfloat16* dst = p.dqkv + (long long)(row0 + ri) * ld + h * 64 + grp * 32;
+        const int coff = !DKDV ? 0 : (which == 0 ? 2 * d : d);
+        __nv_bfloat16* dst = p.dqkv + (long long)(row0 + ri) * ld + coff + h * 64 + grp * 32;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           uint4 o;
@@ -385,38 +397,19 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_co
           reinterpret_cast<uint4*>(dst)[j] = o;
         }
       }
-    } else {
-#pragma unroll
-      for (int which = 0; which < 2; ++which) {  // 0: dV (cols 256..319) -> V block; 1: dK (320..383) -> K block
-        uint32_t v[32];
-        tmem_ld32(trow + 256 + which * 64 + grp * 32, v);
-        tmem_ld_wait();
-        if (ri < S) {
-          __nv_bfloat16* dst = p.dqkv + (long long)(row0 + ri) * ld + (which == 0 ? 2 * d : d) + h * 64 + grp * 32;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint4 o;
-            o.x = pack_bf16x2(__uint_as_float(v[j * 8 + 0]), __uint_as_float(v[j * 8 + 1]));
-            o.y = pack_bf16x2(__uint_as_float(v[j * 8 + 2]), __uint_as_float(v[j * 8 + 3]));
-            o.z = pack_bf16x2(__uint_as_float(v[j * 8 + 4]), __uint_as_float(v[j * 8 + 5]));
-            o.w = pack_bf16x2(__uint_as_float(v[j * 8 + 6]), __uint_as_float(v[j * 8 + 7]));
-            reinterpret_cast<uint4*>(dst)[j] = o;
-          }
-        }
-      }
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 0) {
     tc_fence_after();
-    tmem_dealloc(tmem, 512);
+    tmem_dealloc(tmem, 256);
   }
 }
 
 constexpr int FWD_SMEM = 1024 + 6 * ATOM + 2048 + 64;
-constexpr int BWD_DQ_SMEM = 1024 + 8 * ATOM + 2048 + 128;
-constexpr int BWD_DKDV_SMEM = 1024 + 10 * ATOM + 2048 + 128;
+constexpr int BWD_DQ_SMEM = 1024 + 2 * ATOM + 3 * 16384 + ATOM + 2048 + 128;        //  99.3 KB -> 2 CTAs / SM
+constexpr int BWD_DKDV_SMEM = 1024 + 2 * ATOM + 2 * 16384 + 2 * ATOM + 2048 + 128;  //  99.3 KB -> 2 CTAs / SM
 
 }  // namespace mmb
 
@@ -450,30 +443,40 @@ extern "C" int mmb_attention_bwd_tc(const void* qkv, const void* out, const void
                                     int B, int S, int H, int causal, float scale, void* stream) {
   if (B <= 0 || S <= 0 || S > 256) return MMB_ERR_UNSUPPORTED;
   const int d = H * 64, S_pad = (S + 15) & ~15;
-  CUtensorMap q128, qPad, o128, oPad;
+  CUtensorMap q128, q64, o128, o64;
   int rc = make_tmap_2d(&q128, qkv, 2, false, 3ull * d, (uint64_t)B * S, 3ull * d * 2, 64, 128);
   if (rc) return rc;
-  rc = make_tmap_2d(&qPad, qkv, 2, false, 3ull * d, (uint64_t)B * S, 3ull * d * 2, 64, S_pad);
+  rc = make_tmap_2d(&q64, qkv, 2, false, 3ull * d, (uint64_t)B * S, 3ull * d * 2, 64, 64);
   if (rc) return rc;
   rc = make_tmap_2d(&o128, dout, 2, false, (uint64_t)d, (uint64_t)B * S, (uint64_t)d * 2, 64, 128);
   if (rc) return rc;
-  rc = make_tmap_2d(&oPad, dout, 2, false, (uint64_t)d, (uint64_t)B * S, (uint64_t)d * 2, 64, S_pad);
+  rc = make_tmap_2d(&o64, dout, 2, false, (uint64_t)d, (uint64_t)B * S, (uint64_t)d * 2, 64, 64);
   if (rc) return rc;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  // scratch for D = rowsum(dO * O): grows on demand, stream-ordered (one scratch per process / device)
+  static float* dsum = nullptr;
+  static size_t dsum_cap = 0;
+  const size_t need = (size_t)B * H * S * sizeof(float);
+  if (need > dsum_cap) {
+    if (dsum) cudaFree(dsum);
+    cudaError_t e = cudaMalloc(&dsum, need);
+    if (e != cudaSuccess) { dsum = nullptr; dsum_cap = 0; return (int)e; }
+    dsum_cap = need;
+  }
   AttnTcArgs a{};
   a.S = S; a.H = H; a.S_pad = S_pad; a.scale = scale; a.scale_log2 = scale * 1.4426950408889634f;
   a.lse = const_cast<float*>(lse); a.o_in = (const __nv_bfloat16*)out; a.dout = (const __nv_bfloat16*)dout;
-  a.dqkv = (__nv_bfloat16*)dqkv;
+  a.dqkv = (__nv_bfloat16*)dqkv; a.dsum = dsum;
   dim3 grid((S + 127) / 128, H, B);
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
 #define LAUNCH_BWD(C, K, SM)                                                                         \
   cudaFuncSetAttribute(attn_bwd_tc_kernel<C, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM);  \
-  attn_bwd_tc_kernel<C, K><<<grid, ATT_THREADS, SM, st>>>(q128, qPad, o128, oPad, a);
+  attn_bwd_tc_kernel<C, K><<<grid, ATT_THREADS, SM, st>>>(q128, q64, o128, o64, a);
   if (causal) {
+    LAUNCH_BWD(true, false, BWD_DQ_SMEM)     // dQ first: it also publishes D for the dK/dV kernel
     LAUNCH_BWD(true, true, BWD_DKDV_SMEM)
-    LAUNCH_BWD(true, false, BWD_DQ_SMEM)
   } else {
-    LAUNCH_BWD(false, true, BWD_DKDV_SMEM)
     LAUNCH_BWD(false, false, BWD_DQ_SMEM)
+    LAUNCH_BWD(false, true, BWD_DKDV_SMEM)
   }
 #undef LAUNCH_BWD
   return (int)cudaGetLastError();
