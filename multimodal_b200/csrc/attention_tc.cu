@@ -53,7 +53,9 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant__ CUtensorMap tmPad,
                    const AttnTcArgs p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024 B alignment for the 128B-swizzle atoms; pointer arithmetic on the __shared__ array keeps the address
+  // space known to the compiler (LDS/STS instead of generic LD/ST).
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sQ = smem;               // 16 KB   } aliased by sP (4 atoms) once S = Q K^T has completed
   uint8_t* sK = smem + ATOM;        // <=32 KB }
   uint8_t* sP = smem;
@@ -111,9 +113,14 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
     uint32_t v[16];
     tmem_ld16(trow + c * 16, v);
     tmem_ld_wait();
+    if (c * 16 + 16 <= kv_lim) {
 #pragma unroll
-    for (int e = 0; e < 16; ++e)
-      if (c * 16 + e < kv_lim) mx = fmaxf(mx, __uint_as_float(v[e]));
+      for (int e = 0; e < 16; ++e) mx = fmaxf(mx, __uint_as_float(v[e]));
+    } else {
+#pragma unroll
+      for (int e = 0; e < 16; ++e)
+        if (c * 16 + e < kv_lim) mx = fmaxf(mx, __uint_as_float(v[e]));
+    }
   }
   sRed[grp * 128 + r] = mx;
   __syncthreads();  // also orders: every thread has finished reading Q/K smem?  (MMA done) -> sP may be written
@@ -124,11 +131,19 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
     tmem_ld16(trow + c * 16, v);
     tmem_ld_wait();
     float pr[16];
+    if (c * 16 + 16 <= kv_lim) {
 #pragma unroll
-    for (int e = 0; e < 16; ++e) {
-      const float x = (c * 16 + e < kv_lim) ? ex2_approx(__uint_as_float(v[e]) * p.scale_log2 - mx) : 0.f;
-      pr[e] = x;
-      sum += x;
+      for (int e = 0; e < 16; ++e) {
+        pr[e] = ex2_approx(fmaf(__uint_as_float(v[e]), p.scale_log2, -mx));
+        sum += pr[e];
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        const float x = (c * 16 + e < kv_lim) ? ex2_approx(__uint_as_float(v[e]) * p.scale_log2 - mx) : 0.f;
+        pr[e] = x;
+        sum += x;
+      }
     }
     store_p16(sP, r, c * 16, pr);
   }
@@ -190,15 +205,19 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
 // CTA's softmax arithmetic overlaps the other's MMAs / loads.
 // TMEM columns: S @0 ; dP @64 ; acc0 @128 ; acc1 @192.
 // ------------------------------------------------------------------------------------------------
+constexpr int BWD_THREADS = ATT_THREADS + 32;  // 8 worker warps (thread == tile row x column half) + 1 issuer warp
+
 template <bool CAUSAL, bool DKDV>
-__global__ void __launch_bounds__(ATT_THREADS, 2)
+__global__ void __launch_bounds__(BWD_THREADS, 2)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_constant__ CUtensorMap tmQKV64,
                    const __grid_constant__ CUtensorMap tmDO128, const __grid_constant__ CUtensorMap tmDO64,
                    const AttnTcArgs p) {
   constexpr int RING = DKDV ? 2 : 3;
   constexpr int CH = 8192;  // one 64-row x 128 B chunk operand
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024 B alignment for the 128B-swizzle atoms; pointer arithmetic on the __shared__ array keeps the address
+  // space known to the compiler (LDS/STS instead of generic LD/ST).
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sA0 = smem;                        // 16 KB  tile operand 0 (Q | K_j)
   uint8_t* sA1 = smem + ATOM;                 // 16 KB  tile operand 1 (dO | V_j)
   uint8_t* sRing = smem + 2 * ATOM;           // RING x (B0_c 8 KB | B1_c 8 KB)
@@ -209,10 +228,12 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_co
   uint64_t* bars = reinterpret_cast<uint64_t*>(sD + 256);
   uint64_t* bar_tile = bars;        // [1] A0/A1 landed
   uint64_t* bar_ld = bars + 1;      // [RING] chunk operands landed
-  uint64_t* bar_s = bars + 4;       // [1] S_c/dP_c ready (parity c & 1)
-  uint64_t* bar_acc = bars + 5;     // [1] accumulate-MMAs of chunk c done (parity c & 1)
-  uint64_t* bar_done = bars + 6;    // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
+  uint64_t* bar_s = bars + 4;       // S_c/dP_c ready                       issuer -> workers (parity c & 1)
+  uint64_t* bar_acc = bars + 5;     // accumulate-MMAs of chunk c complete   issuer -> workers + issuer
+  uint64_t* bar_done = bars + 6;    // all MMAs complete
+  uint64_t* bar_rd = bars + 7;      // workers finished READING S_c/dP_c from TMEM (8 warp arrivals) -> issuer
+  uint64_t* bar_st = bars + 8;      // workers finished WRITING dS_c / P^T_c to smem (8 warp arrivals) -> issuer
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tile = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -225,158 +246,194 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_co
     mbar_init(bar_tile, 1);
     for (int i = 0; i < RING; ++i) mbar_init(&bar_ld[i], 1);
     mbar_init(bar_s, 1); mbar_init(bar_acc, 1); mbar_init(bar_done, 1);
+    mbar_init(bar_rd, 8); mbar_init(bar_st, 8);
     fence_mbar_init();
   }
-  if (warp == 0) tmem_alloc(tmem_slot, 256);
+  if (warp == 8) tmem_alloc(tmem_slot, 256);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  auto load_chunk = [&](int c) {  // thread 0 only
-    const int st = c % RING;
-    uint8_t* dst = sRing + st * 2 * CH;
-    mbar_arrive_expect_tx(&bar_ld[st], 2 * CH);
-    if (!DKDV) {
-      tma_load_2d(&tmQKV64, &bar_ld[st], dst, d + h * 64, row0 + c * 64);          // K_c
-      tma_load_2d(&tmQKV64, &bar_ld[st], dst + CH, 2 * d + h * 64, row0 + c * 64);  // V_c
-    } else {
-      tma_load_2d(&tmQKV64, &bar_ld[st], dst, h * 64, row0 + c * 64);               // Q_c
-      tma_load_2d(&tmDO64, &bar_ld[st], dst + CH, h * 64, row0 + c * 64);            // dO_c
-    }
-  };
-  if (threadIdx.x == 0) {
-    mbar_arrive_expect_tx(bar_tile, 2 * ATOM);
-    if (!DKDV) {
-      tma_load_2d(&tmQKV128, bar_tile, sA0, h * 64, row0 + tile * 128);           // Q tile
-      tma_load_2d(&tmDO128, bar_tile, sA1, h * 64, row0 + tile * 128);            // dO tile
-    } else {
-      tma_load_2d(&tmQKV128, bar_tile, sA0, d + h * 64, row0 + tile * 128);       // K tile
-      tma_load_2d(&tmQKV128, bar_tile, sA1, 2 * d + h * 64, row0 + tile * 128);   // V tile
-    }
-    for (int c = 0; c < RING && c < nc; ++c) load_chunk(c);
-  }
-
-  const int q4 = warp & 3, grp = warp >> 2;
-  const int r = q4 * 32 + lane;
-  const int ri = tile * 128 + r;  // global index of this thread's row (query for DQ, key for DKDV)
-  const uint32_t trow = tmem + ((uint32_t)(q4 * 32) << 16);
-
-  // softmax statistics: per row (DQ; also published for the DKDV kernel) or per column via smem (DKDV)
-  float Lrow = 0.f, Drow = 0.f;
-  if (!DKDV) {
-    if (ri < S) {
-      const uint4* po = reinterpret_cast<const uint4*>(p.o_in + (long long)(row0 + ri) * d + h * 64);
-      const uint4* pd = reinterpret_cast<const uint4*>(p.dout + (long long)(row0 + ri) * d + h * 64);
-      float acc = 0.f;
+  if (warp == 8) {
+    // ======================= issuer warp: TMA loads + every tcgen05.mma =======================
+    if (lane == 0) {
+      const uint32_t uA0 = smem_u32(sA0), uA1 = smem_u32(sA1), uRing = smem_u32(sRing);
+      const uint32_t uDS = smem_u32(sDS), uPT = smem_u32(sPT);
+      auto load_chunk = [&](int c) {
+        const int st = c % RING;
+        uint8_t* dst = sRing + st * 2 * CH;
+        mbar_arrive_expect_tx(&bar_ld[st], 2 * CH);
+        if (!DKDV) {
+          tma_load_2d(&tmQKV64, &bar_ld[st], dst, d + h * 64, row0 + c * 64);          // K_c
+          tma_load_2d(&tmQKV64, &bar_ld[st], dst + CH, 2 * d + h * 64, row0 + c * 64);  // V_c
+        } else {
+          tma_load_2d(&tmQKV64, &bar_ld[st], dst, h * 64, row0 + c * 64);               // Q_c
+          tma_load_2d(&tmDO64, &bar_ld[st], dst + CH, h * 64, row0 + c * 64);            // dO_c
+        }
+      };
+      auto issue_scores = [&](int c) {  // S_c / dP_c (or their transposes)
+        const int wc = min(64, S_pad - c * 64);
+        const uint32_t id = idesc_rt(wc, false, false);
+        const uint32_t ub = uRing + (c % RING) * 2 * CH;
+        const uint64_t a0 = desc_k(uA0), a1 = desc_k(uA1), b0 = desc_k(ub), b1 = desc_k(ub + CH);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const uint4 a = __ldg(po + j), c = __ldg(pd + j);
-        acc += bf16_lo(a.x) * bf16_lo(c.x) + bf16_hi(a.x) * bf16_hi(c.x) + bf16_lo(a.y) * bf16_lo(c.y) +
-               bf16_hi(a.y) * bf16_hi(c.y) + bf16_lo(a.z) * bf16_lo(c.z) + bf16_hi(a.z) * bf16_hi(c.z) +
-               bf16_lo(a.w) * bf16_lo(c.w) + bf16_hi(a.w) * bf16_hi(c.w);
+        for (int k = 0; k < 4; ++k) umma_bf16(tmem, a0 + 2 * k, b0 + 2 * k, id, k > 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(tmem + 64, a1 + 2 * k, b1 + 2 * k, id, k > 0);
+        umma_commit(bar_s);
+      };
+      mbar_arrive_expect_tx(bar_tile, 2 * ATOM);
+      if (!DKDV) {
+        tma_load_2d(&tmQKV128, bar_tile, sA0, h * 64, row0 + tile * 128);           // Q tile
+        tma_load_2d(&tmDO128, bar_tile, sA1, h * 64, row0 + tile * 128);            // dO tile
+      } else {
+        tma_load_2d(&tmQKV128, bar_tile, sA0, d + h * 64, row0 + tile * 128);       // K tile
+        tma_load_2d(&tmQKV128, bar_tile, sA1, 2 * d + h * 64, row0 + tile * 128);   // V tile
       }
-      Drow = acc;
-      Lrow = p.lse[((long long)b * p.H + h) * S + ri] * 1.4426950408889634f;
-      if (grp == 0) p.dsum[((long long)b * p.H + h) * S + ri] = acc;
+      for (int c = 0; c < RING && c < nc; ++c) load_chunk(c);
+      mbar_wait(bar_tile, 0);
+      mbar_wait(&bar_ld[0], 0);
+      tc_fence_after();
+      issue_scores(0);
+      for (int c = 0; c < nc; ++c) {
+        const int wc = min(64, S_pad - c * 64);
+        if (c >= 1) {  // ring stage (c-1) % RING was last read by the accumulate-MMAs of chunk c-1
+          mbar_wait(bar_acc, (c - 1) & 1);
+          if (c + RING - 1 < nc) load_chunk(c + RING - 1);
+        }
+        if (c + 1 < nc) {  // S/dP TMEM columns are free as soon as every worker has read chunk c
+          mbar_wait(bar_rd, c & 1);
+          mbar_wait(&bar_ld[(c + 1) % RING], ((c + 1) / RING) & 1);
+          tc_fence_after();
+          issue_scores(c + 1);  // runs under the workers' exp / FMA work on chunk c
+        }
+        mbar_wait(bar_st, c & 1);  // dS_c (and P^T_c) are in shared memory
+        tc_fence_after();
+        const uint32_t id = idesc_rt(64, false, true);
+        const uint32_t ub = uRing + (c % RING) * 2 * CH;
+        const int ks = wc >> 4;
+        if (!DKDV) {   // dQ += dS_c K_c
+          for (int k = 0; k < ks; ++k)
+            umma_bf16(tmem + 128, desc_k(uDS + k * 32), desc_mn(ub + k * 2048), id, (c > 0 || k > 0));
+        } else {       // dV += P^T_c dO_c ; dK += dS^T_c Q_c
+          for (int k = 0; k < ks; ++k)
+            umma_bf16(tmem + 128, desc_k(uPT + k * 32), desc_mn(ub + CH + k * 2048), id, (c > 0 || k > 0));
+          for (int k = 0; k < ks; ++k)
+            umma_bf16(tmem + 192, desc_k(uDS + k * 32), desc_mn(ub + k * 2048), id, (c > 0 || k > 0));
+        }
+        umma_commit(bar_acc);
+        if (c == nc - 1) umma_commit(bar_done);
+      }
     }
   } else {
-    const int qi = threadIdx.x;  // 256 threads cover S_pad <= 256 query columns
-    const bool ok = qi < S;
-    sL[qi] = ok ? p.lse[((long long)b * p.H + h) * S + qi] * 1.4426950408889634f : 0.f;
-    sD[qi] = ok ? p.dsum[((long long)b * p.H + h) * S + qi] : 0.f;
-    __syncthreads();
-  }
+    // ======================= 8 worker warps =======================
+    const int q4 = warp & 3, grp = warp >> 2;
+    const int r = q4 * 32 + lane;
+    const int ri = tile * 128 + r;  // global index of this thread's row (query for DQ, key for DKDV)
+    const uint32_t trow = tmem + ((uint32_t)(q4 * 32) << 16);
 
-  const uint32_t uA0 = smem_u32(sA0), uA1 = smem_u32(sA1), uRing = smem_u32(sRing);
-  const uint32_t uDS = smem_u32(sDS), uPT = smem_u32(sPT);
-
-  auto issue_scores = [&](int c) {  // S_c / dP_c (or their transposes); thread 0 only, chunk c's operands have landed
-    const int wc = min(64, S_pad - c * 64);
-    const uint32_t id = idesc_rt(wc, false, false);
-    const uint32_t ub = uRing + (c % RING) * 2 * CH;
-    const uint64_t a0 = desc_k(uA0), a1 = desc_k(uA1), b0 = desc_k(ub), b1 = desc_k(ub + CH);
+    // softmax statistics: per row (DQ; also published for the DKDV kernel) or per column via smem (DKDV)
+    float Lrow = 0.f, Drow = 0.f;
+    if (!DKDV) {
+      if (ri < S) {
+        const uint4* po = reinterpret_cast<const uint4*>(p.o_in + (long long)(row0 + ri) * d + h * 64);
+        const uint4* pd = reinterpret_cast<const uint4*>(p.dout + (long long)(row0 + ri) * d + h * 64);
+        float acc = 0.f;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) umma_bf16(tmem, a0 + 2 * k, b0 + 2 * k, id, k > 0);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) umma_bf16(tmem + 64, a1 + 2 * k, b1 + 2 * k, id, k > 0);
-    umma_commit(bar_s);
-  };
-
-  if (threadIdx.x == 0) {
-    mbar_wait(bar_tile, 0);
-    mbar_wait(&bar_ld[0], 0);
-    tc_fence_after();
-    issue_scores(0);
-  }
-
-  for (int c = 0; c < nc; ++c) {
-    const int wc = min(64, S_pad - c * 64);
-    mbar_wait(bar_s, c & 1);
-    tc_fence_after();
-    // this thread: row r, columns [grp*32, grp*32+32) of the chunk, processed as two 16-column halves
-    float ds[2][16], pt[2][16];
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      uint32_t sv[16], dv[16];
-      tmem_ld16(trow + grp * 32 + half * 16, sv);
-      tmem_ld16(trow + 64 + grp * 32 + half * 16, dv);
-      tmem_ld_wait();
-#pragma unroll
-      for (int e = 0; e < 16; ++e) {
-        const int cj = c * 64 + grp * 32 + half * 16 + e;  // global column index (key for DQ, query for DKDV)
-        bool valid;
-        float L, Dv;
-        if (!DKDV) {
-          valid = (ri < S) && (cj < S) && (!CAUSAL || cj <= ri);
-          L = Lrow; Dv = Drow;
-        } else {
-          valid = (ri < S) && (cj < S) && (!CAUSAL || ri <= cj);
-          L = sL[cj & 255]; Dv = sD[cj & 255];
+        for (int j = 0; j < 8; ++j) {
+          const uint4 a = __ldg(po + j), c = __ldg(pd + j);
+          acc += bf16_lo(a.x) * bf16_lo(c.x) + bf16_hi(a.x) * bf16_hi(c.x) + bf16_lo(a.y) * bf16_lo(c.y) +
+                 bf16_hi(a.y) * bf16_hi(c.y) + bf16_lo(a.z) * bf16_lo(c.z) + bf16_hi(a.z) * bf16_hi(c.z) +
+                 bf16_lo(a.w) * bf16_lo(c.w) + bf16_hi(a.w) * bf16_hi(c.w);
         }
-        const float pv = valid ? ex2_approx(__uint_as_float(sv[e]) * p.scale_log2 - L) : 0.f;
-        pt[half][e] = pv;
-        ds[half][e] = pv * (__uint_as_float(dv[e]) - Dv) * p.scale;
+        Drow = acc;
+        Lrow = p.lse[((long long)b * p.H + h) * S + ri] * 1.4426950408889634f;
+        if (grp == 0) p.dsum[((long long)b * p.H + h) * S + ri] = acc;
       }
+    } else {
+      const int qi = threadIdx.x;  // 256 worker threads cover S_pad <= 256 query columns
+      const bool ok = qi < S;
+      sL[qi] = ok ? p.lse[((long long)b * p.H + h) * S + qi] * 1.4426950408889634f : 0.f;
+      sD[qi] = ok ? p.dsum[((long long)b * p.H + h) * S + qi] : 0.f;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
     }
-    if (c >= 1) {
-      mbar_wait(bar_acc, (c - 1) & 1);  // accumulate-MMAs of chunk c-1 done: dS / P^T buffers and ring stage (c-1)%RING free
-      if (threadIdx.x == 0 && c + RING - 1 < nc) load_chunk(c + RING - 1);
-    }
-#pragma unroll
-    for (int half = 0; half < 2; ++half)
-      if (grp * 32 + half * 16 < wc) {
-        store_p16(sDS, r, grp * 32 + half * 16, ds[half]);
-        if (DKDV) store_p16(sPT, r, grp * 32 + half * 16, pt[half]);
-      }
-    fence_proxy_async_smem();
-    tc_fence_before();
-    __syncthreads();
-    if (threadIdx.x == 0) {
+
+    for (int c = 0; c < nc; ++c) {
+      const int wc = min(64, S_pad - c * 64);
+      mbar_wait(bar_s, c & 1);
       tc_fence_after();
-      if (c + 1 < nc) {  // next chunk's scores first: they are what the other threads wait for
-        mbar_wait(&bar_ld[(c + 1) % RING], ((c + 1) / RING) & 1);
-        issue_scores(c + 1);
+      // this thread: row r, columns [grp*32, grp*32+32) of the chunk
+      uint32_t sv[32], dv[32];
+      tmem_ld32(trow + grp * 32, sv);
+      tmem_ld32(trow + 64 + grp * 32, dv);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_rd);       // TMEM S/dP of this chunk consumed -> next chunk's MMAs may overwrite
+      if (c >= 1) mbar_wait(bar_acc, (c - 1) & 1);  // dS / P^T buffers free (normally long since complete)
+      {
+        const int cbase = c * 64 + grp * 32;  // first global column (key for DQ, query for DKDV) of this thread's 32
+        // interior fast path: the whole 32-column strip is unmasked for this row (all but the last chunk / the causal
+        // diagonal / padding rows) -> no per-element predicates or index arithmetic
+        const bool full = (ri < S) && (cbase + 32 <= S) && (!CAUSAL || (DKDV ? (ri <= cbase) : (cbase + 31 <= ri)));
+        const float nD = -Drow * p.scale;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          float ds[16], pt[16];
+          if (full) {
+            if (!DKDV) {
+#pragma unroll
+              for (int e = 0; e < 16; ++e) {
+                const float pv = ex2_approx(fmaf(__uint_as_float(sv[half * 16 + e]), p.scale_log2, -Lrow));
+                ds[e] = pv * fmaf(__uint_as_float(dv[half * 16 + e]), p.scale, nD);
+              }
+            } else {
+              const float4* pl = reinterpret_cast<const float4*>(sL + cbase + half * 16);
+              const float4* pd = reinterpret_cast<const float4*>(sD + cbase + half * 16);
+#pragma unroll
+              for (int e4 = 0; e4 < 4; ++e4) {
+                const float4 l4 = pl[e4], d4 = pd[e4];
+                const float ls[4] = {l4.x, l4.y, l4.z, l4.w}, dd[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const int e = e4 * 4 + k;
+                  const float pv = ex2_approx(fmaf(__uint_as_float(sv[half * 16 + e]), p.scale_log2, -ls[k]));
+                  pt[e] = pv;
+                  ds[e] = pv * (__uint_as_float(dv[half * 16 + e]) - dd[k]) * p.scale;
+                }
+              }
+            }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              const int cj = cbase + half * 16 + e;
+              bool valid;
+              float L, Dv;
+              if (!DKDV) {
+                valid = (ri < S) && (cj < S) && (!CAUSAL || cj <= ri);
+                L = Lrow; Dv = Drow;
+              } else {
+                valid = (ri < S) && (cj < S) && (!CAUSAL || ri <= cj);
+                L = sL[cj & 255]; Dv = sD[cj & 255];
+              }
+              const float pv = valid ? ex2_approx(__uint_as_float(sv[half * 16 + e]) * p.scale_log2 - L) : 0.f;
+              pt[e] = pv;
+              ds[e] = pv * (__uint_as_float(dv[half * 16 + e]) - Dv) * p.scale;
+            }
+          }
+          if (grp * 32 + half * 16 < wc) {
+            store_p16(sDS, r, grp * 32 + half * 16, ds);
+            if (DKDV) store_p16(sPT, r, grp * 32 + half * 16, pt);
+          }
+        }
       }
-      const uint32_t id = idesc_rt(64, false, true);
-      const uint32_t ub = uRing + (c % RING) * 2 * CH;
-      const int ks = wc >> 4;
-      if (!DKDV) {   // dQ += dS_c K_c
-        for (int k = 0; k < ks; ++k)
-          umma_bf16(tmem + 128, desc_k(uDS + k * 32), desc_mn(ub + k * 2048), id, (c > 0 || k > 0));
-      } else {       // dV += P^T_c dO_c ; dK += dS^T_c Q_c
-        for (int k = 0; k < ks; ++k)
-          umma_bf16(tmem + 128, desc_k(uPT + k * 32), desc_mn(ub + CH + k * 2048), id, (c > 0 || k > 0));
-        for (int k = 0; k < ks; ++k)
-          umma_bf16(tmem + 192, desc_k(uDS + k * 32), desc_mn(ub + k * 2048), id, (c > 0 || k > 0));
-      }
-      umma_commit(bar_acc);
-      if (c == nc - 1) umma_commit(bar_done);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_st);
     }
-  }
-  mbar_wait(bar_done, 0);
-  tc_fence_after();
-  {
+    mbar_wait(bar_done, 0);
+    tc_fence_after();
     const long long ld = 3LL * d;
 #pragma unroll
     for (int which = 0; which < (DKDV ? 2 : 1); ++which) {
@@ -401,7 +458,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_co
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) {
+  if (warp == 8) {
     tc_fence_after();
     tmem_dealloc(tmem, 256);
   }
@@ -470,7 +527,7 @@ extern "C" int mmb_attention_bwd_tc(const void* qkv, const void* out, const void
   dim3 grid((S + 127) / 128, H, B);
 #define LAUNCH_BWD(C, K, SM)                                                                         \
   cudaFuncSetAttribute(attn_bwd_tc_kernel<C, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM);  \
-  attn_bwd_tc_kernel<C, K><<<grid, ATT_THREADS, SM, st>>>(q128, q64, o128, o64, a);
+  attn_bwd_tc_kernel<C, K><<<grid, BWD_THREADS, SM, st>>>(q128, q64, o128, o64, a);
   if (causal) {
     LAUNCH_BWD(true, false, BWD_DQ_SMEM)     // dQ first: it also publishes D for the dK/dV kernel
     LAUNCH_BWD(true, true, BWD_DKDV_SMEM)

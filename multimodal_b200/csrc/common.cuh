@@ -65,12 +65,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  const uint64_t t0 = global_timer_ns();
+  // slow path: try_wait already suspends the thread for a hardware-defined interval; the wall-clock watchdog is
+  // consulted only every 2048 polls so that the spin loop stays 3 instructions long.
+  uint32_t polls = 0;
+  uint64_t t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (global_timer_ns() - t0 > MMB_WATCHDOG_NS) {
-      printf("mmb watchdog: mbarrier wait timed out (block %d thread %d parity %u)\n", (int)blockIdx.x,
-             (int)threadIdx.x, parity);
-      __trap();
+    if ((++polls & 2047u) == 0) {
+      const uint64_t now = global_timer_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > MMB_WATCHDOG_NS) {
+        printf("mmb watchdog: mbarrier wait timed out (block %d thread %d parity %u)\n", (int)blockIdx.x,
+               (int)threadIdx.x, parity);
+        __trap();
+      }
     }
   }
 }

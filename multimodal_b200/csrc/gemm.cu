@@ -68,7 +68,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmD0, const __grid_constant__ CUtensorMap tmD1, const GemmArgs p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024 B alignment for the 128B-swizzle atoms; pointer arithmetic on the __shared__ array keeps the address
+  // space known to the compiler (LDS/STS instead of generic LD/ST).
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   constexpr int STAGES = Cfg<CTA2, EPI>::STAGES, B_BYTES = Cfg<CTA2, EPI>::B_BYTES, LOAD_N = Cfg<CTA2, EPI>::LOAD_N;
   constexpr int TILE_M = Cfg<CTA2, EPI>::TILE_M;
   const uint32_t rank = CTA2 ? cluster_ctarank() : 0u;   // 0 = leader of the CTA pair (issues the MMAs)

@@ -137,3 +137,41 @@ class ContrastiveTrainer:
                        self.eps, 0.0, self.ls_t, gs, True)
         self.ls.data.copy_(self.ls_buf[0])
         return loss
+
+
+class HostPrefetcher:
+    """Double-buffered host->device staging of (image, text) batches on a side stream, so the H2D copy of step i+1
+    overlaps the compute of step i.  `batches` is an iterable of pinned host tensor pairs."""
+
+    def __init__(self, batches, device):
+        self.it = iter(batches)
+        self.device = device
+        self.stream = torch.cuda.Stream(device=device)
+        self._next = self._stage()
+
+    def _stage(self):
+        try:
+            img_h, txt_h = next(self.it)
+        except StopIteration:
+            return None
+        with torch.cuda.stream(self.stream):
+            img = img_h.to(self.device, non_blocking=True)
+            txt = txt_h.to(self.device, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        return img, txt, ev
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        cur = self._next
+        if cur is None:
+            raise StopIteration
+        img, txt, ev = cur
+        main = torch.cuda.current_stream(self.device)
+        main.wait_event(ev)
+        img.record_stream(main)
+        txt.record_stream(main)
+        self._next = self._stage()   # H2D of the following batch overlaps this step's kernels
+        return img, txt

@@ -235,3 +235,43 @@ def contrastive_grads_lse_exchange(a: Tensor, b: Tensor, logit_scale: Tensor, mo
         loss = 0.5 * (((1 - eps) * nll_a + eps * (lse_a - La.mean(1))).mean()
                       + ((1 - eps) * nll_b + eps * (lse_b - Lb.mean(1))).mean())
     return loss, dA, dB, dS
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Timing variant (bench.py cpu_baseline / --impl reference): the same restatement expressed with the fused library
+# calls the reference itself dispatches to on CPU (F.linear / F.layer_norm / F.scaled_dot_product_attention), so the
+# CPU arm is not handicapped by the op-by-op form above.  Checked against clip_forward in tests/test_oracle_cpu.py.
+# ----------------------------------------------------------------------------------------------------------------
+def _encoder_layer_fused(x: Tensor, sd: Dict[str, Tensor], pfx: str, heads: int, causal: bool) -> Tensor:
+    import torch.nn.functional as F
+
+    B, S, d = x.shape
+    h = F.layer_norm(x, (d,), sd[pfx + "norm1.weight"], sd[pfx + "norm1.bias"], 1e-5)
+    qkv = F.linear(h, sd[pfx + "self_attn.in_proj_weight"], sd[pfx + "self_attn.in_proj_bias"])
+    q, k, v = (t.view(B, S, heads, d // heads).transpose(1, 2) for t in qkv.split(d, dim=-1))
+    o = F.scaled_dot_product_attention(q, k, v, is_causal=causal).transpose(1, 2).reshape(B, S, d)
+    x = x + F.linear(o, sd[pfx + "self_attn.out_proj.weight"], sd[pfx + "self_attn.out_proj.bias"])
+    h = F.layer_norm(x, (d,), sd[pfx + "norm2.weight"], sd[pfx + "norm2.bias"], 1e-5)
+    h = F.linear(h, sd[pfx + "linear1.weight"], sd[pfx + "linear1.bias"])
+    h = torch.sigmoid(1.702 * h) * h
+    return x + F.linear(h, sd[pfx + "linear2.weight"], sd[pfx + "linear2.bias"])
+
+
+def clip_forward_fused(image: Tensor, text: Tensor, sd: Dict[str, Tensor], img_heads: int, txt_heads: int):
+    import torch.nn.functional as F
+
+    pfx = "encoder_a."
+    w = sd[pfx + "conv.weight"]
+    x = F.conv2d(image, w, stride=w.shape[-1]).flatten(2).permute(0, 2, 1)
+    x = torch.cat([sd[pfx + "cls_token_embedding"].expand(x.shape[0], 1, -1), x], dim=1) + sd[pfx + "positional_embedding"]
+    x = F.layer_norm(x, x.shape[-1:], sd[pfx + "ln_pre.weight"], sd[pfx + "ln_pre.bias"], 1e-5)
+    for l in range(_num_layers(sd, pfx)):
+        x = _encoder_layer_fused(x, sd, f"{pfx}encoder.layers.{l}.", img_heads, False)
+    a = F.layer_norm(x[:, 0, :], x.shape[-1:], sd[pfx + "ln_post.weight"], sd[pfx + "ln_post.bias"], 1e-5) @ sd[pfx + "projection"]
+    pfx = "encoder_b."
+    y = F.embedding(text, sd[pfx + "token_embedding.weight"]) + sd[pfx + "positional_embedding"]
+    for l in range(_num_layers(sd, pfx)):
+        y = _encoder_layer_fused(y, sd, f"{pfx}encoder.layers.{l}.", txt_heads, True)
+    y = F.layer_norm(y, y.shape[-1:], sd[pfx + "ln_final.weight"], sd[pfx + "ln_final.bias"], 1e-5)
+    b = F.linear(y[torch.arange(y.shape[0]), text.argmax(dim=-1)], sd[pfx + "projection.weight"])
+    return F.normalize(a), F.normalize(b)

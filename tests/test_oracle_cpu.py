@@ -52,6 +52,16 @@ def test_oracle_b16_forward_matches_reference_golden_and_init_mirror(golden):
     torch.testing.assert_close(loss, g["loss"], rtol=0, atol=1e-5)
 
 
+def test_fused_timing_variant_matches_oracle(golden):
+    """bench.py's CPU arm uses oracle.clip_forward_fused (library-fused ops); it must be the same function."""
+    g = golden["clip_small"]
+    with torch.no_grad():
+        a, b = O.clip_forward(g["image"], g["text"], g["state_dict"], 2, 2)
+        af, bf = O.clip_forward_fused(g["image"], g["text"], g["state_dict"], 2, 2)
+    torch.testing.assert_close(af, a, rtol=0, atol=2e-6)
+    torch.testing.assert_close(bf, b, rtol=0, atol=2e-6)
+
+
 def test_reference_kat_contrastive_loss():
     """tests/modules/losses/test_contrastive_loss_with_temperature.py:75-82 (9.8753) and :112-123 (10.2524)."""
     torch.manual_seed(1234)
