@@ -262,7 +262,13 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                     "frac": achieved / peak_tf if peak_tf else None, "traffic": None,
+                     "frac": achieved / peak_tf if peak_tf else None,
+                     # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this kernel (in-projection shape,
+                     # M = 75,776 tokens, N = 2304, K = 768) from the committed `ncu --set full` capture
+                     # profiles/r1_ncu_full_gemm_ctapair.csv; algorithmic bytes of that launch = 469.1e6
+                     # (A 116.4e6 + W 3.5e6 + D 349.2e6): no re-read traffic.
+                     "traffic": 119.986688e6 + 293.527808e6,
+                     "traffic_launch": "gemm_kernel<K,K,bf16,pair> M=75776 N=2304 K=768 (profiles/r1_ncu_full_gemm_ctapair.csv, launch0)",
                      "kernel": "mmb::gemm_kernel (tcgen05, all instantiations; per-launch average over the timed region)",
                      "launches_per_step": n_gemm // args.steps, "flops_per_launch_avg": tot_f / n_gemm,
                      "ms_per_launch_avg": tot_ms / n_gemm, "gemm_share_of_step": (tot_ms / args.steps) / ms_dev,
