@@ -48,9 +48,10 @@ int mmb_gemm_bf16(const void* A, long long lda, int a_mn_major, const void* B, l
 /* dst[i] = bf16(src[i]) — parameter shadow for the tensor-core operands (what torch.autocast does per call). */
 int mmb_cast_f32_to_bf16(const float* src, void* dst_bf16, long long n, void* stream);
 
-/* Patch im2col + cast: img fp32 [B,3,H,W] -> bf16 [B*(H/ps)*(W/ps), 3*ps*ps], K order (c,kh,kw), patches row-major.
+/* Patch im2col + cast: img fp32 [B,3,H,W] -> bf16 [B*(H/ps)*(W/ps), 3*ps*ps] with row pitch ld_out elements (>= 3*ps*ps;
+ * a multiple of 8 keeps the rows TMA-addressable, e.g. 592 for 14x14 patches), K order (c,kh,kw), patches row-major.
  * Replaces the data movement half of nn.Conv2d(3,width,ps,ps,bias=False), models/clip/image_encoder.py:50-56,91-97. */
-int mmb_im2col_patches(const float* img, void* out_bf16, int B, int H, int W, int ps, void* stream);
+int mmb_im2col_patches(const float* img, void* out_bf16, long long ld_out, int B, int H, int W, int ps, void* stream);
 
 /* x_out = x_in (+ y_bf16); ln = LayerNorm(x_out)*gamma+beta, fp32 statistics.  Any of x_in/y/x_out/ln_bf16/ln_f32/
  * mean/rstd may be NULL.  rows_per_group > 0 selects the gather mode: logical row m reads physical row

@@ -381,7 +381,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_co
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           float ds[16], pt[16];
-          if (full) {
+          if (ri >= S) {  // padding row of the last tile: contributes nothing
+#pragma unroll
+            for (int e = 0; e < 16; ++e) { ds[e] = 0.f; pt[e] = 0.f; }
+          } else if (full) {
             if (!DKDV) {
 #pragma unroll
               for (int e = 0; e < 16; ++e) {

@@ -66,11 +66,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   // slow path: try_wait already suspends the thread for a hardware-defined interval; the wall-clock watchdog is
-  // consulted only every 2048 polls so that the spin loop stays 3 instructions long.
+  // consulted only every 1024 polls.
   uint32_t polls = 0;
   uint64_t t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if ((++polls & 2047u) == 0) {
+    if ((++polls & 1023u) == 0) {
       const uint64_t now = global_timer_ns();
       if (t0 == 0) t0 = now;
       else if (now - t0 > MMB_WATCHDOG_NS) {

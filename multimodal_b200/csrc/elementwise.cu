@@ -40,7 +40,7 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat1
 // == flatten(2) of the conv output (:94).  ps must be a multiple of 2.
 // ---------------------------------------------------------------------------------------------
 __global__ void im2col_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, int B, int H, int W,
-                              int ps) {
+                              int ps, long long ld_out) {
   const int gp = W / ps, P = (H / ps) * gp, K = 3 * ps * ps;
   const long long total2 = (long long)B * P * K / 2;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total2;
@@ -54,7 +54,7 @@ __global__ void im2col_kernel(const float* __restrict__ img, __nv_bfloat16* __re
     const int py = p / gp, px = p % gp;
     const float2 v = __ldg(reinterpret_cast<const float2*>(
         img + (((long long)b * 3 + c) * H + (py * ps + kh)) * W + px * ps + kw));
-    reinterpret_cast<uint32_t*>(out)[i] = pack_bf16x2(v.x, v.y);
+    *reinterpret_cast<uint32_t*>(out + row * ld_out + k) = pack_bf16x2(v.x, v.y);
   }
 }
 
@@ -534,10 +534,11 @@ extern "C" int mmb_cast_f32_to_bf16(const float* src, void* dst, long long n, vo
   return LAUNCH_RC();
 }
 
-extern "C" int mmb_im2col_patches(const float* img, void* out, int B, int H, int W, int ps, void* stream) {
-  if (B <= 0 || ps <= 0 || (ps & 1) || H % ps || W % ps) return MMB_ERR_ARG;
+extern "C" int mmb_im2col_patches(const float* img, void* out, long long ld_out, int B, int H, int W, int ps,
+                                  void* stream) {
+  if (B <= 0 || ps <= 0 || (ps & 1) || H % ps || W % ps || (ld_out & 1) || ld_out < 3LL * ps * ps) return MMB_ERR_ARG;
   const long long total2 = (long long)B * (H / ps) * (W / ps) * 3 * ps * ps / 2;
-  im2col_kernel<<<grid_for(total2, 256), 256, 0, ST(stream)>>>(img, (__nv_bfloat16*)out, B, H, W, ps);
+  im2col_kernel<<<grid_for(total2, 256), 256, 0, ST(stream)>>>(img, (__nv_bfloat16*)out, B, H, W, ps, ld_out);
   return LAUNCH_RC();
 }
 

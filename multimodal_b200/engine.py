@@ -264,12 +264,18 @@ class ViTTower:
         K = 3 * ps * ps
         bf, f32 = torch.bfloat16, torch.float32
         st.refresh()
-        PATCH = ws.get("img.PATCH", (B * P, K), bf)
+        Kp = -(-K // 8) * 8   # row pitch: bf16 rows must be 16 B multiples for TMA (K = 588 -> 592 for 14x14 patches)
+        PATCH = ws.get("img.PATCH", (B * P, Kp), bf)[:, :K]
         PO = ws.get("img.PO", (B * P, d), bf)
         X0 = ws.get("img.X0", (B * S, d), f32)
         m0 = ws.get("img.m0", (B * S,), f32); r0 = ws.get("img.r0", (B * S,), f32)
         ops.im2col(image, ps, PATCH)
-        ops.gemm(PATCH, st.shadow2d(mod.conv.weight), out=PO)
+        wconv = st.shadow2d(mod.conv.weight)
+        if Kp != K:  # re-pitch the (tiny) conv weight shadow the same way
+            wpad = ws.get("img.WCONV", (d, Kp), bf)[:, :K]
+            wpad.copy_(wconv)
+            wconv = wpad
+        ops.gemm(PATCH, wconv, out=PO)
         ops.vit_embed_ln_fwd(PO, mod.cls_token_embedding, mod.positional_embedding, mod.ln_pre.weight, mod.ln_pre.bias,
                              X0, m0, r0, B, S, d, mod.ln_pre.eps)
         XM, Y = self.stack.forward(X0, B, S, training)
@@ -306,7 +312,8 @@ class ViTTower:
                              mod.ln_pre.weight, G, DP, st.grad(mod.ln_pre.weight), st.grad(mod.ln_pre.bias), B, S, d)
         ops.batch_sum(G, st.grad(mod.positional_embedding), B, S * d, S * d)
         ops.batch_sum(G, st.grad(mod.cls_token_embedding), B, S * d, d)
-        PATCH = ws.get("img.PATCH", (B * P, 3 * self.ps * self.ps), bf)
+        K = 3 * self.ps * self.ps
+        PATCH = ws.get("img.PATCH", (B * P, -(-K // 8) * 8), bf)[:, :K]
         ops.gemm(DP, PATCH, a_mn=True, b_mn=True, epilogue=ops.EPI_F32, out=st.grad2d(mod.conv.weight),
                  splits=ops.wgrad_splits(d, PATCH.shape[1], B * P), accumulate=True)
 

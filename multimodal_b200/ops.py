@@ -114,7 +114,8 @@ def cast_bf16(src: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Te
 def im2col(img: torch.Tensor, ps: int, out: torch.Tensor) -> torch.Tensor:
     _chk(img, torch.float32, "img"); _chk(out, torch.bfloat16, "out")
     B, C, H, W = img.shape
-    _lib.check(_lib.lib().mmb_im2col_patches(_p(img), _p(out), B, H, W, ps, _stream()), "mmb_im2col_patches")
+    _rowmajor(out, "out")
+    _lib.check(_lib.lib().mmb_im2col_patches(_p(img), _p(out), out.stride(0), B, H, W, ps, _stream()), "mmb_im2col_patches")
     return out
 
 

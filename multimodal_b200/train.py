@@ -141,12 +141,16 @@ class ContrastiveTrainer:
 
 class HostPrefetcher:
     """Double-buffered host->device staging of (image, text) batches on a side stream, so the H2D copy of step i+1
-    overlaps the compute of step i.  `batches` is an iterable of pinned host tensor pairs."""
+    overlaps the compute of step i.  `batches` is an iterable of pinned host tensor pairs (all of one shape); two
+    persistent device buffer pairs are reused, guarded by events (no allocator traffic in the loop)."""
 
     def __init__(self, batches, device):
         self.it = iter(batches)
         self.device = device
         self.stream = torch.cuda.Stream(device=device)
+        self.bufs = [None, None]          # (img, txt) device buffers
+        self.free_ev = [None, None]       # recorded on the compute stream when the buffer's consumer was enqueued
+        self.k = 0
         self._next = self._stage()
 
     def _stage(self):
@@ -154,12 +158,20 @@ class HostPrefetcher:
             img_h, txt_h = next(self.it)
         except StopIteration:
             return None
+        i = self.k & 1
+        self.k += 1
+        if self.bufs[i] is None:
+            self.bufs[i] = (torch.empty(img_h.shape, dtype=img_h.dtype, device=self.device),
+                            torch.empty(txt_h.shape, dtype=txt_h.dtype, device=self.device))
+        img, txt = self.bufs[i]
         with torch.cuda.stream(self.stream):
-            img = img_h.to(self.device, non_blocking=True)
-            txt = txt_h.to(self.device, non_blocking=True)
+            if self.free_ev[i] is not None:
+                self.stream.wait_event(self.free_ev[i])   # the step that read this buffer has been fully enqueued+run
+            img.copy_(img_h, non_blocking=True)
+            txt.copy_(txt_h, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(self.stream)
-        return img, txt, ev
+        return img, txt, ev, i
 
     def __iter__(self):
         return self
@@ -168,10 +180,15 @@ class HostPrefetcher:
         cur = self._next
         if cur is None:
             raise StopIteration
-        img, txt, ev = cur
+        img, txt, ev, i = cur
         main = torch.cuda.current_stream(self.device)
         main.wait_event(ev)
-        img.record_stream(main)
-        txt.record_stream(main)
-        self._next = self._stage()   # H2D of the following batch overlaps this step's kernels
+        if self._prev is not None:                      # the previous batch's step is enqueued on `main` by now
+            e = torch.cuda.Event()
+            e.record(main)
+            self.free_ev[self._prev] = e
+        self._prev = i
+        self._next = self._stage()                      # H2D of the following batch overlaps this step's kernels
         return img, txt
+
+    _prev = None

@@ -270,6 +270,27 @@ def test_clip_b16_forward_against_oracle(dev):
     assert torch.equal(out_t.embeddings_a, out.embeddings_a) and torch.equal(out_t.embeddings_b, out.embeddings_b)
 
 
+def test_clip_l14_forward_backward_runs_and_matches_oracle(dev):
+    """ViT-L/14 (BASELINE.json config 4 architecture; S = 257 > 256 uses the mma.sync attention kernels)."""
+    from multimodal_b200.models.clip.model import clip_vit_l14
+    from multimodal_b200.modules.losses.contrastive_loss_with_temperature import ContrastiveLossWithTemperature
+
+    torch.manual_seed(0)
+    m = clip_vit_l14()
+    sd = {k: v.to(dev) for k, v in m.state_dict().items()}
+    assert sd["encoder_a.conv.weight"].shape == (1024, 3, 14, 14) and sd["encoder_b.projection.weight"].shape == (768, 768)
+    m = m.to(dev).train()
+    img, txt = O.synthetic_batch(4, device=dev)
+    with torch.no_grad():
+        ra, rb = O.clip_forward(img, txt, sd, 16, 12)
+    out = m(img, txt)
+    assert (out.embeddings_a - ra).abs().max().item() < 4e-3
+    assert (out.embeddings_b - rb).abs().max().item() < 4e-3
+    ContrastiveLossWithTemperature().to(dev)(out.embeddings_a, out.embeddings_b).backward()
+    g = m.encoder_a.encoder.layers[0].linear1.weight.grad
+    assert g is not None and torch.isfinite(g).all() and g.abs().sum() > 0
+
+
 def test_trainer_step_matches_autograd_path_and_learns(dev):
     """The autograd-free ContrastiveTrainer and the nn.Module/autograd path produce the same gradients; a few
     AdamW steps on a fixed batch reduce the loss (size-independent property)."""
