@@ -110,6 +110,28 @@ int mmb_attention_fwd(const void* qkv, void* out, float* lse, int B, int S, int 
 int mmb_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, int B, int S,
                       int H, int head_dim, int causal, float scale, void* stream);
 
+/* Same with a key-padding mask [B,S] (1 = attend, 0 = masked_fill(-inf)): the BERT-style attention of the FLAVA text
+ * tower (modules/encoders/bert_text_encoder.py:87-93 -> modules/layers/attention.py:228-229).  S <= 256. */
+int mmb_attention_fwd_kmask(const void* qkv, void* out, float* lse, const unsigned char* kmask, int B, int S, int H,
+                            int head_dim, int causal, float scale, void* stream);
+
+/* ---- FLAVA encoder front/back ends (config 3, forward) -------------------------------------------------------- */
+/* x = LayerNorm(word[ids] + pos[arange(S)] + type[type_ids or 0]) — BERTTextEmbeddings.forward,
+ * modules/layers/text_embedding.py:70-104.  ids/type_ids int64 (bit-exact gathers).  kmask_out (optional) receives
+ * ids != pad_id, the default padding mask of BERTTextEncoder.forward (bert_text_encoder.py:87-90). */
+int mmb_bert_embed_ln_fwd(const long long* ids, const long long* type_ids, const float* word, const float* pos,
+                          const float* type, const float* gamma, const float* beta, float* x, unsigned char* kmask_out,
+                          long long pad_id, int B, int S, int d, int V, float eps, void* stream);
+/* x = cat(cls, mask ? mask_token : patch_out) + pos — ImageEmbeddings.forward, models/flava/image_encoder.py:139-175. */
+int mmb_vit_assemble_fwd(const void* patch_out_bf16, const float* cls, const float* pos, const float* mask_token,
+                         const unsigned char* patch_mask, float* x, int B, int S, int d, void* stream);
+/* out[b,:] = bf16(x[b*rows_per_group + row, :]) — `hidden[:, 0]` selects (Pooler, projections; losses/flava.py:92-96). */
+int mmb_gather_rows_cast(const float* x, void* out_bf16, int B, int rows_per_group, int row, int d, void* stream);
+int mmb_tanh_inplace(float* x, long long n, void* stream);
+/* out[b] = cat([cls], a[b], b[b]) along tokens — models/flava/transformer.py:55-58 + model.py:294-297. */
+int mmb_concat_tokens(const float* cls, const float* a, const float* b, float* out, int B, int Sa, int Sb, int d,
+                      void* stream);
+
 /* ---- contrastive loss -------------------------------------------------------------------------------------- */
 /* One direction of contrastive_loss_with_temperature (modules/losses/contrastive_loss_with_temperature.py:81-107),
  * rows = this rank's batch, N = global batch, label(i) = label_offset + i (:39-41).

@@ -25,6 +25,12 @@ PROTOTYPES = {
     "mmb_memset_async": (i32, [vp, i32, ll, vp]),
     "mmb_attention_fwd": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, f32, vp]),
     "mmb_attention_bwd": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, vp]),
+    "mmb_attention_fwd_kmask": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, vp]),
+    "mmb_bert_embed_ln_fwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, ll, i32, i32, i32, i32, f32, vp]),
+    "mmb_vit_assemble_fwd": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]),
+    "mmb_gather_rows_cast": (i32, [vp, vp, i32, i32, i32, i32, vp]),
+    "mmb_tanh_inplace": (i32, [vp, ll, vp]),
+    "mmb_concat_tokens": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, vp]),
     "mmb_contrastive_ce_stats": (i32, [vp, ll, vp, i32, i32, i32, f32, f32, vp, vp, vp, vp, ll, vp]),
     "mmb_contrastive_ce_grad": (i32, [vp, ll, vp, i32, i32, i32, f32, f32, vp, vp, i32, i32, vp, vp, ll, vp]),
     "mmb_matmul_f32": (i32, [vp, ll, i32, vp, ll, i32, vp, ll, i32, i32, i32, f32, i32, vp]),

@@ -26,6 +26,7 @@ struct AttnTcArgs {
   const __nv_bfloat16* dout;    // bwd: dO [B*S, d]
   __nv_bfloat16* dqkv;          // bwd: [B*S, 3d]
   float* dsum;                  // bwd: rowsum(dO * O) [B,H,S], written by the dQ kernel, read by the dK/dV kernel
+  const uint8_t* kmask;         // fwd: optional key-padding mask [B,S], 1 = attend (utils/attention.py:13-53)
 };
 
 __device__ __forceinline__ uint64_t desc_k(uint32_t saddr) { return make_smem_desc_sw128(saddr, 16, 1024); }
@@ -61,13 +62,16 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
   uint8_t* sP = smem;
   uint8_t* sV = smem + 4 * ATOM;    // <=32 KB
   float* sRed = reinterpret_cast<float*>(smem + 6 * ATOM);  // [2][128] max, [2][128] sum
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sRed + 512);
+  uint8_t* sMask = reinterpret_cast<uint8_t*>(sRed + 512);   // [256] key mask of this batch row (1 = attend)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sMask + 256);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int S = p.S, S_pad = p.S_pad, d = p.H * 64;
   const uint32_t ncols = S_pad <= 128 ? 128u : 256u;
+  const bool has_mask = p.kmask != nullptr;
+  sMask[threadIdx.x] = (threadIdx.x < S && (!has_mask || p.kmask[(long long)blockIdx.z * S + threadIdx.x])) ? 1 : 0;
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tm128);
     tma_prefetch_desc(&tmPad);
@@ -113,13 +117,13 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
     uint32_t v[16];
     tmem_ld16(trow + c * 16, v);
     tmem_ld_wait();
-    if (c * 16 + 16 <= kv_lim) {
+    if (c * 16 + 16 <= kv_lim && !has_mask) {
 #pragma unroll
       for (int e = 0; e < 16; ++e) mx = fmaxf(mx, __uint_as_float(v[e]));
     } else {
 #pragma unroll
       for (int e = 0; e < 16; ++e)
-        if (c * 16 + e < kv_lim) mx = fmaxf(mx, __uint_as_float(v[e]));
+        if (c * 16 + e < kv_lim && sMask[c * 16 + e]) mx = fmaxf(mx, __uint_as_float(v[e]));
     }
   }
   sRed[grp * 128 + r] = mx;
@@ -131,7 +135,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
     tmem_ld16(trow + c * 16, v);
     tmem_ld_wait();
     float pr[16];
-    if (c * 16 + 16 <= kv_lim) {
+    if (c * 16 + 16 <= kv_lim && !has_mask) {
 #pragma unroll
       for (int e = 0; e < 16; ++e) {
         pr[e] = ex2_approx(fmaf(__uint_as_float(v[e]), p.scale_log2, -mx));
@@ -140,7 +144,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
     } else {
 #pragma unroll
       for (int e = 0; e < 16; ++e) {
-        const float x = (c * 16 + e < kv_lim) ? ex2_approx(__uint_as_float(v[e]) * p.scale_log2 - mx) : 0.f;
+        const float x = (c * 16 + e < kv_lim && sMask[c * 16 + e]) ? ex2_approx(__uint_as_float(v[e]) * p.scale_log2 - mx) : 0.f;
         pr[e] = x;
         sum += x;
       }
@@ -467,7 +471,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_co
   }
 }
 
-constexpr int FWD_SMEM = 1024 + 6 * ATOM + 2048 + 64;
+constexpr int FWD_SMEM = 1024 + 6 * ATOM + 2048 + 256 + 64;
 constexpr int BWD_DQ_SMEM = 1024 + 2 * ATOM + 3 * 16384 + ATOM + 2048 + 128;        //  99.3 KB -> 2 CTAs / SM
 constexpr int BWD_DKDV_SMEM = 1024 + 2 * ATOM + 2 * 16384 + 2 * ATOM + 2048 + 128;  //  99.3 KB -> 2 CTAs / SM
 
@@ -476,7 +480,11 @@ constexpr int BWD_DKDV_SMEM = 1024 + 2 * ATOM + 2 * 16384 + 2 * ATOM + 2048 + 12
 using namespace mmb;
 
 extern "C" int mmb_attention_fwd_tc(const void* qkv, void* out, float* lse, int B, int S, int H, int causal, float scale,
-                                    void* stream) {
+                                    void* stream);
+extern "C" int mmb_attention_fwd_kmask(const void* qkv, void* out, float* lse, const unsigned char* kmask, int B, int S,
+                                       int H, int head_dim, int causal, float scale, void* stream);
+static int attention_fwd_tc_impl(const void* qkv, void* out, float* lse, const uint8_t* kmask, int B, int S, int H,
+                                 int causal, float scale, void* stream) {
   if (B <= 0 || S <= 0 || S > 256) return MMB_ERR_UNSUPPORTED;
   const int d = H * 64, S_pad = (S + 15) & ~15;
   CUtensorMap tm128, tmPad;
@@ -486,7 +494,7 @@ extern "C" int mmb_attention_fwd_tc(const void* qkv, void* out, float* lse, int 
   if (rc) return rc;
   AttnTcArgs a{};
   a.S = S; a.H = H; a.S_pad = S_pad; a.scale = scale; a.scale_log2 = scale * 1.4426950408889634f;
-  a.lse = lse; a.out = (__nv_bfloat16*)out;
+  a.lse = lse; a.out = (__nv_bfloat16*)out; a.kmask = kmask;
   dim3 grid((S + 127) / 128, H, B);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (causal) {
@@ -497,6 +505,18 @@ extern "C" int mmb_attention_fwd_tc(const void* qkv, void* out, float* lse, int 
     attn_fwd_tc_kernel<false><<<grid, ATT_THREADS, FWD_SMEM, st>>>(tm128, tmPad, a);
   }
   return (int)cudaGetLastError();
+}
+
+extern "C" int mmb_attention_fwd_tc(const void* qkv, void* out, float* lse, int B, int S, int H, int causal, float scale,
+                                    void* stream) {
+  return attention_fwd_tc_impl(qkv, out, lse, nullptr, B, S, H, causal, scale, stream);
+}
+// Same with a key-padding mask [B,S] (1 = attend): BERT-style attention of the FLAVA text tower
+// (modules/encoders/bert_text_encoder.py:87-93 -> modules/layers/attention.py:228-229 masked_fill(-inf)).
+extern "C" int mmb_attention_fwd_kmask(const void* qkv, void* out, float* lse, const unsigned char* kmask, int B, int S,
+                                       int H, int head_dim, int causal, float scale, void* stream) {
+  if (head_dim != 64 || S > 256) return MMB_ERR_UNSUPPORTED;
+  return attention_fwd_tc_impl(qkv, out, lse, kmask, B, S, H, causal, scale, stream);
 }
 
 extern "C" int mmb_attention_bwd_tc(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,

@@ -70,6 +70,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t polls = 0;
   uint64_t t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
+#ifdef MMB_WAIT_NANOSLEEP
+    __nanosleep(MMB_WAIT_NANOSLEEP);  // back off: a spinning warp otherwise steals issue slots from working warps
+#endif
     if ((++polls & 1023u) == 0) {
       const uint64_t now = global_timer_ns();
       if (t0 == 0) t0 = now;

@@ -191,6 +191,127 @@ __global__ void vit_embed_ln_fwd_kernel(const __nv_bfloat16* __restrict__ patch_
   }
 }
 
+// BERT embeddings (modules/layers/text_embedding.py:70-104): x = LayerNorm(word[ids] + pos[s] + type[type_ids]),
+// position ids = arange(S), token types default to 0.  One warp per token, fp32 statistics.
+__global__ void bert_embed_ln_fwd_kernel(const long long* __restrict__ ids, const long long* __restrict__ type_ids,
+                                         const float* __restrict__ word, const float* __restrict__ pos,
+                                         const float* __restrict__ type, const float* __restrict__ gamma,
+                                         const float* __restrict__ beta, float* __restrict__ x,
+                                         unsigned char* __restrict__ kmask_out, long long pad_id, int B, int S, int d,
+                                         int V, float eps) {
+  const int nv = d >> 7;
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const int M = B * S;
+  for (int m = blockIdx.x * wpb + (threadIdx.x >> 5); m < M; m += gridDim.x * wpb) {
+    const int s = m % S;
+    const long long tok = ids[m];
+    if (tok < 0 || tok >= V) __trap();
+    const long long ty = type_ids ? type_ids[m] : 0;
+    if (kmask_out && lane == 0) kmask_out[m] = (tok != pad_id) ? 1 : 0;  // bert_text_encoder.py:87-90 (bit-exact)
+    LnRow r;
+#pragma unroll
+    for (int i = 0; i < LN_MAX_NV; ++i)
+      if (i < nv) {
+        const int c = (i * 32 + lane) * 4;
+        const float4 a = __ldg(reinterpret_cast<const float4*>(word + tok * d + c));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(pos + (long long)s * d + c));
+        const float4 t = __ldg(reinterpret_cast<const float4*>(type + ty * d + c));
+        r.v[i] = make_float4(a.x + b.x + t.x, a.y + b.y + t.y, a.z + b.z + t.z, a.w + b.w + t.w);
+      }
+    float mean, rstd;
+    ln_stats(r, nv, d, eps, mean, rstd);
+#pragma unroll
+    for (int i = 0; i < LN_MAX_NV; ++i)
+      if (i < nv) {
+        const int c = (i * 32 + lane) * 4;
+        const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
+        const float4 bb = __ldg(reinterpret_cast<const float4*>(beta + c));
+        float4 o;
+        o.x = (r.v[i].x - mean) * rstd * g.x + bb.x;
+        o.y = (r.v[i].y - mean) * rstd * g.y + bb.y;
+        o.z = (r.v[i].z - mean) * rstd * g.z + bb.z;
+        o.w = (r.v[i].w - mean) * rstd * g.w + bb.w;
+        *reinterpret_cast<float4*>(x + (long long)m * d + c) = o;
+      }
+  }
+}
+
+// FLAVA image embeddings (models/flava/image_encoder.py:139-175): x[b,0] = cls + pos[0];
+// x[b,1+p] = (mask[b,p] ? mask_token : patch_out[b*P+p]) + pos[1+p].   No LayerNorm here.
+__global__ void vit_assemble_fwd_kernel(const __nv_bfloat16* __restrict__ patch_out, const float* __restrict__ cls,
+                                        const float* __restrict__ pos, const float* __restrict__ mask_token,
+                                        const unsigned char* __restrict__ patch_mask, float* __restrict__ x, int B, int S,
+                                        int d) {
+  const int d4 = d >> 2;
+  const long long total = (long long)B * S * d4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % d4) * 4;
+    const long long row = i / d4;
+    const int s = (int)(row % S);
+    const int b = (int)(row / S);
+    float4 a = __ldg(reinterpret_cast<const float4*>(pos + (long long)s * d + c));
+    float4 t;
+    if (s == 0) {
+      t = __ldg(reinterpret_cast<const float4*>(cls + c));
+    } else if (patch_mask && mask_token && patch_mask[(long long)b * (S - 1) + (s - 1)]) {
+      t = __ldg(reinterpret_cast<const float4*>(mask_token + c));
+    } else {
+      const uint2 u = *reinterpret_cast<const uint2*>(patch_out + ((long long)b * (S - 1) + (s - 1)) * d + c);
+      t = make_float4(bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y));
+    }
+    reinterpret_cast<float4*>(x)[i] = make_float4(a.x + t.x, a.y + t.y, a.z + t.z, a.w + t.w);
+  }
+}
+
+// out[b,:] = bf16(x[(b*rows_per_group + row)*d : +d])   (select one token per sequence, e.g. CLS, as a GEMM operand)
+__global__ void gather_rows_cast_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int B,
+                                        int rows_per_group, int row, int d) {
+  const int d4 = d >> 2;
+  const long long total = (long long)B * d4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % d4) * 4;
+    const long long b = i / d4;
+    const float4 v = *reinterpret_cast<const float4*>(x + (b * rows_per_group + row) * d + c);
+    uint2 u;
+    u.x = pack_bf16x2(v.x, v.y);
+    u.y = pack_bf16x2(v.z, v.w);
+    *reinterpret_cast<uint2*>(out + b * d + c) = u;
+  }
+}
+
+__global__ void tanh_inplace_kernel(float* __restrict__ x, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    x[i] = tanhf(x[i]);
+}
+
+// out[b] = cat(cls (optional), a[b], b[b]) along the sequence dim; all fp32 [.., d]
+// (FLAVATransformerWithoutEmbeddings.forward + FLAVAModel.encode_mm: models/flava/transformer.py:55-58, model.py:294-297)
+__global__ void concat_tokens_kernel(const float* __restrict__ cls, const float* __restrict__ a,
+                                     const float* __restrict__ bsrc, float* __restrict__ out, int B, int Sa, int Sb,
+                                     int d) {
+  const int d4 = d >> 2;
+  const int So = (cls ? 1 : 0) + Sa + Sb;
+  const long long total = (long long)B * So * d4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % d4) * 4;
+    const long long row = i / d4;
+    int s = (int)(row % So);
+    const long long b = row / So;
+    float4 v;
+    if (cls) {
+      if (s == 0) { reinterpret_cast<float4*>(out)[i] = __ldg(reinterpret_cast<const float4*>(cls + c)); continue; }
+      s -= 1;
+    }
+    if (s < Sa) v = *reinterpret_cast<const float4*>(a + (b * Sa + s) * d + c);
+    else        v = *reinterpret_cast<const float4*>(bsrc + (b * Sb + (s - Sa)) * d + c);
+    reinterpret_cast<float4*>(out)[i] = v;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // LayerNorm backward (+ residual-gradient add).  For each row:
 //   xhat = (x - mean) * rstd;  dyg = dy * gamma
@@ -650,4 +771,40 @@ extern "C" int mmb_adamw_step(float* p, float* g, float* m, float* v, void* p_bf
 }
 extern "C" int mmb_memset_async(void* p, int value, long long bytes, void* stream) {
   return (int)cudaMemsetAsync(p, value, (size_t)bytes, ST(stream));
+}
+
+extern "C" int mmb_bert_embed_ln_fwd(const long long* ids, const long long* type_ids, const float* word, const float* pos,
+                                     const float* type, const float* gamma, const float* beta, float* x,
+                                     unsigned char* kmask_out, long long pad_id, int B, int S, int d, int V, float eps,
+                                     void* stream) {
+  if (!ln_dim_ok(d)) return MMB_ERR_UNSUPPORTED;
+  bert_embed_ln_fwd_kernel<<<grid_for((long long)B * S, 8), 256, 0, ST(stream)>>>(ids, type_ids, word, pos, type, gamma,
+                                                                                 beta, x, kmask_out, pad_id, B, S, d, V,
+                                                                                 eps);
+  return LAUNCH_RC();
+}
+extern "C" int mmb_vit_assemble_fwd(const void* patch_out, const float* cls, const float* pos, const float* mask_token,
+                                    const unsigned char* patch_mask, float* x, int B, int S, int d, void* stream) {
+  if (d & 3) return MMB_ERR_ARG;
+  vit_assemble_fwd_kernel<<<grid_for((long long)B * S * d / 4, 256), 256, 0, ST(stream)>>>(
+      (const __nv_bfloat16*)patch_out, cls, pos, mask_token, patch_mask, x, B, S, d);
+  return LAUNCH_RC();
+}
+extern "C" int mmb_gather_rows_cast(const float* x, void* out_bf16, int B, int rows_per_group, int row, int d,
+                                    void* stream) {
+  if (d & 3) return MMB_ERR_ARG;
+  gather_rows_cast_kernel<<<grid_for((long long)B * d / 4, 256), 256, 0, ST(stream)>>>(x, (__nv_bfloat16*)out_bf16, B,
+                                                                                     rows_per_group, row, d);
+  return LAUNCH_RC();
+}
+extern "C" int mmb_tanh_inplace(float* x, long long n, void* stream) {
+  tanh_inplace_kernel<<<grid_for(n, 256), 256, 0, ST(stream)>>>(x, n);
+  return LAUNCH_RC();
+}
+extern "C" int mmb_concat_tokens(const float* cls, const float* a, const float* b, float* out, int B, int Sa, int Sb,
+                                 int d, void* stream) {
+  if (d & 3) return MMB_ERR_ARG;
+  const long long total = (long long)B * ((cls ? 1 : 0) + Sa + Sb) * d / 4;
+  concat_tokens_kernel<<<grid_for(total, 256), 256, 0, ST(stream)>>>(cls, a, b, out, B, Sa, Sb, d);
+  return LAUNCH_RC();
 }

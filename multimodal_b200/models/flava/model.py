@@ -1,0 +1,210 @@
+"""FLAVA model — drop-in for the encoder path of torchmultimodal/models/flava/model.py:36-298, 428-520
+(`FLAVAOutput`, `flava_multimodal_encoder`, `FLAVAModel`, `flava_model`).  BASELINE.json config 3 ("FLAVA encoders
+forward") is `FLAVAModel.forward`.  Pre-training / classification heads, losses and the DALL-E codebook
+(model.py:301-420, 524-744) are outside SURVEY.md §8 and not provided.
+"""
+from collections import namedtuple
+from functools import partial
+from typing import Any, Callable, List, Optional, Tuple, Union
+
+import torch
+from torch import nn, Tensor
+
+from ...modules.layers.normalizations import Fp32LayerNorm
+from ...modules.layers.transformer import TransformerOutput
+from ...modules.losses.flava import Pooler
+from .image_encoder import flava_image_encoder
+from .text_encoder import flava_text_encoder
+from .transformer import FLAVATransformerWithoutEmbeddings, TransformerEncoder
+
+FLAVAOutput = namedtuple(
+    "FLAVAOutput",
+    ["image", "image_masked", "text", "text_masked", "multimodal", "multimodal_masked", "projected_image_embeddings",
+     "projected_text_embeddings"],
+    defaults=(None, None, None, None, None, None, None, None),
+)
+FLAVAOutput.__annotations__ = {
+    "image": TransformerOutput, "image_masked": TransformerOutput, "text": TransformerOutput,
+    "text_masked": TransformerOutput, "multimodal": TransformerOutput, "multimodal_masked": TransformerOutput,
+}
+
+
+def flava_multimodal_encoder(hidden_size: int = 768, num_attention_heads: int = 12, num_hidden_layers: int = 12,
+                             dropout: float = 0.0, intermediate_size: int = 3072,
+                             intermediate_activation: Callable[..., nn.Module] = nn.GELU,
+                             layer_norm_eps: float = 1e-12) -> FLAVATransformerWithoutEmbeddings:
+    encoder = TransformerEncoder(n_layer=num_hidden_layers, d_model=hidden_size, n_head=num_attention_heads,
+                                 dim_feedforward=intermediate_size, activation=intermediate_activation,
+                                 layer_norm_eps=layer_norm_eps, dropout=dropout, norm_first=True)
+    layernorm = Fp32LayerNorm(hidden_size, eps=layer_norm_eps)
+    pooler = Pooler(hidden_size=hidden_size)
+    return FLAVATransformerWithoutEmbeddings(encoder=encoder, layernorm=layernorm, pooler=pooler, hidden_size=hidden_size)
+
+
+def _snapshot(out: TransformerOutput) -> TransformerOutput:
+    """Detach an encoder's output from its workspace (the same encoder runs again for the masked pass)."""
+    if out.last_hidden_state is None:
+        return out
+    return out._replace(last_hidden_state=out.last_hidden_state.clone(),
+                        hidden_states=[h.clone() for h in out.hidden_states] if out.hidden_states else out.hidden_states)
+
+
+class FLAVAModel(nn.Module):
+    def __init__(self, image_encoder: nn.Module, text_encoder: nn.Module, mm_encoder: nn.Module,
+                 image_to_mm_projection: nn.Module, text_to_mm_projection: nn.Module, text_projection: nn.Module,
+                 image_projection: nn.Module, **kwargs: Any) -> None:
+        super().__init__()
+        self.image_encoder = image_encoder
+        self.text_encoder = text_encoder
+        self.mm_encoder = mm_encoder
+        self.image_to_mm_projection = image_to_mm_projection
+        self.text_to_mm_projection = text_to_mm_projection
+        self.text_projection = text_projection
+        self.image_projection = image_projection
+
+    @torch.no_grad()
+    def forward(self, image: Optional[Tensor] = None, text: Optional[Tensor] = None,
+                image_patches_mask: Optional[Tensor] = None, text_masked: Optional[Tensor] = None,
+                required_embedding: Optional[str] = None, skip_unmasked_mm_encoder: bool = True) -> FLAVAOutput:
+        if required_embedding is None:
+            if image is not None and text is not None:
+                required_embedding = "mm"
+            elif image is not None:
+                required_embedding = "image"
+            else:
+                required_embedding = "text"
+
+        # The encoders' outputs alias per-encoder workspaces; the unmasked results must survive the masked pass of
+        # the same encoder, so they are snapshotted (one D2D copy of the hidden states) when a second pass follows.
+        two_image_passes = image is not None and required_embedding in ("image", "mm")
+        two_text_passes = text is not None and text_masked is not None and required_embedding in ("text", "mm")
+
+        image_encoding_out = self._encode_data_to_embeddings(
+            image, required_embedding, ["image", "mm"], partial(self.encode_image, projection=True))
+        if len(image_encoding_out) == 2:
+            image_outputs, projected_image_embeddings = image_encoding_out[0], image_encoding_out[1]
+            if two_image_passes:
+                image_outputs = _snapshot(image_outputs)
+        else:
+            image_outputs, projected_image_embeddings = image_encoding_out, None
+
+        text_encoding_out = self._encode_data_to_embeddings(
+            text, required_embedding, ["text", "mm"], partial(self.encode_text, projection=True))
+        if len(text_encoding_out) == 2:
+            text_outputs, projected_text_embeddings = text_encoding_out[0], text_encoding_out[1]
+            if two_text_passes:
+                text_outputs = _snapshot(text_outputs)
+        else:
+            text_outputs, projected_text_embeddings = text_encoding_out, None
+
+        multimodal_outputs = TransformerOutput()
+        multimodal_masked_outputs = TransformerOutput()
+        if required_embedding == "mm" and not skip_unmasked_mm_encoder:
+            # unmasked multimodal pass first: the masked one below then owns the mm workspace
+            multimodal_outputs = _snapshot(self.encode_mm(
+                image_outputs.hidden_states[-1] if image_outputs.hidden_states else None,
+                text_outputs.hidden_states[-1] if text_outputs.hidden_states else None))
+
+        image_masked_outputs = self._encode_data_to_embeddings(
+            image, required_embedding, ["image", "mm"],
+            partial(self.encode_image, image_patches_mask=image_patches_mask))
+        assert type(image_masked_outputs) == TransformerOutput
+        text_masked_outputs = self._encode_data_to_embeddings(
+            text_masked, required_embedding, ["text", "mm"], self.encode_text)
+        assert type(text_masked_outputs) == TransformerOutput
+
+        if required_embedding == "mm":
+            multimodal_masked_outputs = self.encode_mm(
+                image_masked_outputs.hidden_states[-1] if image_masked_outputs.hidden_states else None,
+                text_masked_outputs.hidden_states[-1] if text_masked_outputs.hidden_states else None)
+
+        return FLAVAOutput(image=image_outputs, image_masked=image_masked_outputs, text=text_outputs,
+                           text_masked=text_masked_outputs, multimodal=multimodal_outputs,
+                           multimodal_masked=multimodal_masked_outputs,
+                           projected_image_embeddings=projected_image_embeddings,
+                           projected_text_embeddings=projected_text_embeddings)
+
+    @torch.no_grad()
+    def encode_image(self, image: Tensor, image_patches_mask: Optional[Tensor] = None, projection: bool = False
+                     ) -> Union[Tuple[TransformerOutput, Tensor], Optional[TransformerOutput]]:
+        if image_patches_mask is not None:
+            encoded_image = self.image_encoder(image, image_patches_mask)
+        else:
+            encoded_image = self.image_encoder(image)
+        if projection:
+            projected_embeddings = self._project_cls(self.image_encoder, encoded_image, self.image_projection, "iproj")
+            return encoded_image, projected_embeddings
+        return encoded_image
+
+    @torch.no_grad()
+    def encode_text(self, text: Tensor, text_mask: Optional[Tensor] = None, projection: bool = False
+                    ) -> Union[Tuple[TransformerOutput, Tensor], Optional[TransformerOutput]]:
+        encoded_text = self.text_encoder(input_ids=text, attention_mask=text_mask, return_attn_weights=True,
+                                         return_hidden_states=True)
+        if projection:
+            projected_embeddings = self._project_cls(self.text_encoder, encoded_text, self.text_projection, "tproj")
+            return encoded_text, projected_embeddings
+        return encoded_text
+
+    @staticmethod
+    def _project_cls(encoder: nn.Module, out: TransformerOutput, linear: nn.Module, key: str) -> Tensor:
+        return encoder._runtime().stack.project_first_token(out.last_hidden_state, linear, key)
+
+    def _encode_data_to_embeddings(self, data: Optional[Tensor], selected_head_encoder: str, encoder_options: List[str],
+                                   encode_callable: Callable[..., Any]) -> Any:
+        output: Any = TransformerOutput()
+        if data is not None and selected_head_encoder in encoder_options:
+            output = encode_callable(data)
+        return output
+
+    @torch.no_grad()
+    def encode_mm(self, image_embedding: Tensor, text_embedding: Tensor) -> TransformerOutput:
+        if image_embedding is None or text_embedding is None:
+            return TransformerOutput()
+        return self.mm_encoder._runtime().forward_projected(image_embedding, text_embedding,
+                                                            self.image_to_mm_projection, self.text_to_mm_projection)
+
+
+def flava_model(
+    # Image encoder specific parameters
+    image_hidden_size: int = 768, image_num_attention_heads: int = 12, image_num_hidden_layers: int = 12,
+    image_dropout: float = 0.0, image_intermediate_size: int = 3072,
+    image_intermediate_activation: Callable[..., nn.Module] = nn.GELU, image_layer_norm_eps: float = 1e-12,
+    use_image_masking: bool = True, image_size: int = 224, patch_size: int = 16, num_channels: int = 3,
+    # Text encoder specific parameters
+    text_hidden_size: int = 768, text_num_attention_heads: int = 12, text_num_hidden_layers: int = 12,
+    text_dropout: float = 0.0, text_intermediate_size: int = 3072,
+    text_intermediate_activation: Callable[..., nn.Module] = nn.GELU, text_layer_norm_eps: float = 1e-12,
+    vocab_size: int = 30522, pad_token_id: int = 0, type_vocab_size: int = 2, max_position_embeddings: int = 512,
+    # Multimodal encoder specific parameters
+    multimodal_hidden_size: int = 768, multimodal_num_attention_heads: int = 12, multimodal_num_hidden_layers: int = 6,
+    multimodal_dropout: float = 0.0, multimodal_intermediate_size: int = 3072,
+    multimodal_intermediate_activation: Callable[..., nn.Module] = nn.GELU, multimodal_layer_norm_eps: float = 1e-12,
+    # projection
+    text_and_image_proj_size: int = 768, pretrained: bool = False, **kwargs: Any,
+) -> FLAVAModel:
+    if pretrained:
+        raise NotImplementedError("pretrained checkpoints need network access; load a state_dict explicitly "
+                                  "(keys are identical to the reference's)")
+    image_encoder = flava_image_encoder(
+        hidden_size=image_hidden_size, num_attention_heads=image_num_attention_heads,
+        num_hidden_layers=image_num_hidden_layers, use_image_masking=use_image_masking, dropout=image_dropout,
+        intermediate_size=image_intermediate_size, intermediate_activation=image_intermediate_activation,
+        layer_norm_eps=image_layer_norm_eps, image_size=image_size, patch_size=patch_size, num_channels=num_channels)
+    text_encoder = flava_text_encoder(
+        hidden_size=text_hidden_size, num_attention_heads=text_num_attention_heads,
+        num_hidden_layers=text_num_hidden_layers, dropout=text_dropout, intermediate_size=text_intermediate_size,
+        intermediate_activation=text_intermediate_activation, layer_norm_eps=text_layer_norm_eps, vocab_size=vocab_size,
+        pad_token_id=pad_token_id, type_vocab_size=type_vocab_size, max_position_embeddings=max_position_embeddings)
+    mm_encoder = flava_multimodal_encoder(
+        hidden_size=multimodal_hidden_size, num_attention_heads=multimodal_num_attention_heads,
+        num_hidden_layers=multimodal_num_hidden_layers, dropout=multimodal_dropout,
+        intermediate_size=multimodal_intermediate_size, intermediate_activation=multimodal_intermediate_activation,
+        layer_norm_eps=multimodal_layer_norm_eps)
+    image_to_mm_projection = nn.Linear(image_hidden_size, multimodal_hidden_size)
+    text_to_mm_projection = nn.Linear(text_hidden_size, multimodal_hidden_size)
+    image_projection = nn.Linear(image_hidden_size, text_and_image_proj_size)
+    text_projection = nn.Linear(text_hidden_size, text_and_image_proj_size)
+    return FLAVAModel(image_encoder=image_encoder, text_encoder=text_encoder, mm_encoder=mm_encoder,
+                      image_to_mm_projection=image_to_mm_projection, text_to_mm_projection=text_to_mm_projection,
+                      text_projection=text_projection, image_projection=image_projection)

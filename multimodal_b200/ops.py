@@ -235,3 +235,36 @@ def matmul_f32(A, B, *, ta=False, tb=False, out=None, alpha=1.0, accumulate=Fals
     _lib.check(_lib.lib().mmb_matmul_f32(_p(A), A.stride(0), int(ta), _p(B), B.stride(0), int(tb), _p(out), out.stride(0),
                                          M, N, K, float(alpha), int(accumulate), _stream()), "mmb_matmul_f32")
     return out
+
+
+# ---- FLAVA forward helpers -----------------------------------------------------------------------------------------
+def attention_fwd_kmask(qkv, out, lse, kmask, B, S, H, causal, scale):
+    _chk(qkv, torch.bfloat16, "qkv"); _chk(kmask, torch.uint8, "kmask")
+    _lib.check(_lib.lib().mmb_attention_fwd_kmask(_p(qkv), _p(out), _p(lse), _p(kmask), B, S, H, 64, int(causal),
+                                                  float(scale), _stream()), "mmb_attention_fwd_kmask")
+
+
+def bert_embed_ln_fwd(ids, type_ids, word, pos, type_emb, gamma, beta, x, kmask_out, pad_id, B, S, d, V, eps):
+    _chk(ids, torch.int64, "ids")
+    _lib.check(_lib.lib().mmb_bert_embed_ln_fwd(_p(ids), _p(type_ids), _p(word), _p(pos), _p(type_emb), _p(gamma), _p(beta),
+                                                _p(x), _p(kmask_out), int(pad_id), B, S, d, V, float(eps), _stream()),
+               "mmb_bert_embed_ln_fwd")
+
+
+def vit_assemble_fwd(patch_out, cls, pos, mask_token, patch_mask, x, B, S, d):
+    _lib.check(_lib.lib().mmb_vit_assemble_fwd(_p(patch_out), _p(cls), _p(pos), _p(mask_token), _p(patch_mask), _p(x), B, S,
+                                               d, _stream()), "mmb_vit_assemble_fwd")
+
+
+def gather_rows_cast(x, out, B, rows_per_group, row, d):
+    _lib.check(_lib.lib().mmb_gather_rows_cast(_p(x), _p(out), B, rows_per_group, row, d, _stream()), "mmb_gather_rows_cast")
+
+
+def tanh_(x):
+    _chk(x, torch.float32, "x")
+    _lib.check(_lib.lib().mmb_tanh_inplace(_p(x), x.numel(), _stream()), "mmb_tanh_inplace")
+    return x
+
+
+def concat_tokens(cls, a, b, out, B, Sa, Sb, d):
+    _lib.check(_lib.lib().mmb_concat_tokens(_p(cls), _p(a), _p(b), _p(out), B, Sa, Sb, d, _stream()), "mmb_concat_tokens")
