@@ -141,14 +141,18 @@ int mmb_concat_tokens(const float* cls, const float* a, const float* b, float* o
  *        this rank's row block: the own-direction softmax term plus, for columns [col_lo, col_hi), the transposed
  *        other-direction term rebuilt from the peers' row-LSE vector lse_col[N] — this replaces the reduce-scatter
  *        of torch.distributed.nn.functional.all_gather's backward (utils/distributed.py:47-48).
- *        GLOBAL backprop: [0,N); LOCAL: own block; NONE: lse_col = NULL. */
+ *        GLOBAL backprop: [0,N); LOCAL: own block; NONE: lse_col = NULL.
+ *  row_w / col_w (optional, NULL = uniform 1/rows): the boolean row `mask` of the reference
+ *        (contrastive_loss_with_temperature.py:97-100) as masked-mean weights mask_i / count(mask): row_w[rows] for this
+ *        rank's rows, col_w[N] for the global rows (each in its own rank's mean) entering the other-direction term. */
 int mmb_contrastive_ce_stats(const float* sims, long long ld, const float* logit_scale, int rows, int N,
                              int label_offset, float label_smoothing, float loss_weight, float* row_loss,
-                             float* lse_out, float* dscale_accum, float* logits_out, long long ld_l, void* stream);
+                             float* lse_out, float* dscale_accum, float* logits_out, long long ld_l,
+                             const float* row_w, void* stream);
 int mmb_contrastive_ce_grad(const float* sims, long long ld, const float* logit_scale, int rows, int N,
                             int label_offset, float label_smoothing, float loss_weight, const float* lse_row,
                             const float* lse_col, int col_lo, int col_hi, void* dsims_bf16, float* dsims_f32,
-                            long long ld_d, void* stream);
+                            long long ld_d, const float* row_w, const float* col_w, void* stream);
 /* fp32 SIMT matmul for tiny / unaligned shapes the tensor-core path rejects: C (+)= alpha*op(A)op(B);
  * ta: A stored [K,M]; tb: B stored [N,K]. */
 int mmb_matmul_f32(const float* A, long long lda, int ta, const float* B, long long ldb, int tb, float* C,

@@ -31,8 +31,8 @@ PROTOTYPES = {
     "mmb_gather_rows_cast": (i32, [vp, vp, i32, i32, i32, i32, vp]),
     "mmb_tanh_inplace": (i32, [vp, ll, vp]),
     "mmb_concat_tokens": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, vp]),
-    "mmb_contrastive_ce_stats": (i32, [vp, ll, vp, i32, i32, i32, f32, f32, vp, vp, vp, vp, ll, vp]),
-    "mmb_contrastive_ce_grad": (i32, [vp, ll, vp, i32, i32, i32, f32, f32, vp, vp, i32, i32, vp, vp, ll, vp]),
+    "mmb_contrastive_ce_stats": (i32, [vp, ll, vp, i32, i32, i32, f32, f32, vp, vp, vp, vp, ll, vp, vp]),
+    "mmb_contrastive_ce_grad": (i32, [vp, ll, vp, i32, i32, i32, f32, f32, vp, vp, i32, i32, vp, vp, ll, vp, vp, vp]),
     "mmb_matmul_f32": (i32, [vp, ll, i32, vp, ll, i32, vp, ll, i32, i32, i32, f32, i32, vp]),
     "mmb_symm_alloc": (i32, [ll, vp]),
     "mmb_symm_free": (i32, [vp]),

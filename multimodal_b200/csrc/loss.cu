@@ -35,7 +35,8 @@ __global__ void contrastive_ce_stats_kernel(const float* __restrict__ sims, long
                                             const float* __restrict__ logit_scale, int rows, int N, int label_offset,
                                             float smoothing, float loss_weight, float* __restrict__ row_loss,
                                             float* __restrict__ lse_out, float* __restrict__ dscale_accum,
-                                            float* __restrict__ logits_out, long long ld_l) {
+                                            float* __restrict__ logits_out, long long ld_l,
+                                            const float* __restrict__ row_w) {
   __shared__ float red[32];
   const int i = blockIdx.x;
   if (i >= rows) return;
@@ -57,8 +58,11 @@ __global__ void contrastive_ce_stats_kernel(const float* __restrict__ sims, long
   const float lse = mx + logf(se);
   const float l_label = T * srow[label];
   const float loss = (1.f - smoothing) * (lse - l_label) + smoothing * (lse - mean_logit);
+  // row_w (optional): per-row weight of the mean, mask_i / count(mask) (contrastive_loss_with_temperature.py:97-100
+  // selects rows before F.cross_entropy(reduction="mean")); without it every row weighs 1 / rows.
+  const float wrow = row_w ? row_w[i] : 1.f / rows;
   if (threadIdx.x == 0) {
-    if (row_loss) row_loss[i] = loss;
+    if (row_loss) row_loss[i] = row_w ? loss * wrow * rows : loss;  // so that sum(row_loss) / rows is the masked mean
     if (lse_out) lse_out[i] = lse;
   }
   if (dscale_accum) {
@@ -71,7 +75,7 @@ __global__ void contrastive_ce_stats_kernel(const float* __restrict__ sims, long
       acc += gl * l;
     }
     acc = block_reduce_sum(acc, red);
-    if (threadIdx.x == 0) atomicAdd(dscale_accum, acc * loss_weight / rows);
+    if (threadIdx.x == 0) atomicAdd(dscale_accum, acc * loss_weight * wrow);
   }
 }
 
@@ -85,20 +89,25 @@ __global__ void contrastive_ce_grad_kernel(const float* __restrict__ sims, long 
                                            float smoothing, float loss_weight, const float* __restrict__ lse_row,
                                            const float* __restrict__ lse_col, int col_lo, int col_hi,
                                            __nv_bfloat16* __restrict__ dsims, float* __restrict__ dsims_f32,
-                                           long long ld_d) {
+                                           long long ld_d, const float* __restrict__ row_w,
+                                           const float* __restrict__ col_w) {
   const int i = blockIdx.x;
   if (i >= rows) return;
   const float T = __expf(*logit_scale);
   const float* srow = sims + (long long)i * ld;
   const int label = label_offset + i;
   const float lse = lse_row[i];
-  const float gsT = loss_weight / rows * T;
+  // row weights: this rank's masked-mean weights; col_w[j]: the weight global row j carries in ITS rank's mean
+  const float gsT = loss_weight * T * (row_w ? row_w[i] : 1.f / rows);
+  const float gcT = loss_weight * T / rows;
   for (int j = threadIdx.x; j < N; j += blockDim.x) {
     const float l = T * srow[j];
     const float t = ((j == label) ? (1.f - smoothing) : 0.f) + smoothing / N;
-    float g = __expf(l - lse) - t;
-    if (lse_col && j >= col_lo && j < col_hi) g += __expf(l - lse_col[j]) - t;
-    g *= gsT;
+    float g = gsT * (__expf(l - lse) - t);
+    if (lse_col && j >= col_lo && j < col_hi) {
+      const float wc = col_w ? loss_weight * T * col_w[j] : gcT;
+      if (wc != 0.f) g += wc * (__expf(l - lse_col[j]) - t);  // masked-out peer rows may carry a non-finite LSE
+    }
     if (dsims) dsims[(long long)i * ld_d + j] = __float2bfloat16(g);
     if (dsims_f32) dsims_f32[(long long)i * ld_d + j] = g;
   }
@@ -154,22 +163,23 @@ using namespace mmb;
 extern "C" int mmb_contrastive_ce_stats(const float* sims, long long ld, const float* logit_scale, int rows, int N,
                                         int label_offset, float label_smoothing, float loss_weight, float* row_loss,
                                         float* lse_out, float* dscale_accum, float* logits_out, long long ld_l,
-                                        void* stream) {
+                                        const float* row_w, void* stream) {
   if (rows <= 0 || N <= 0 || label_offset < 0 || label_offset + rows > N) return MMB_ERR_ARG;
   contrastive_ce_stats_kernel<<<rows, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       sims, ld, logit_scale, rows, N, label_offset, label_smoothing, loss_weight, row_loss, lse_out, dscale_accum,
-      logits_out, ld_l);
+      logits_out, ld_l, row_w);
   return (int)cudaGetLastError();
 }
 
 extern "C" int mmb_contrastive_ce_grad(const float* sims, long long ld, const float* logit_scale, int rows, int N,
                                        int label_offset, float label_smoothing, float loss_weight,
                                        const float* lse_row, const float* lse_col, int col_lo, int col_hi,
-                                       void* dsims_bf16, float* dsims_f32, long long ld_d, void* stream) {
+                                       void* dsims_bf16, float* dsims_f32, long long ld_d, const float* row_w,
+                                       const float* col_w, void* stream) {
   if (rows <= 0 || N <= 0 || label_offset < 0 || label_offset + rows > N || !lse_row) return MMB_ERR_ARG;
   contrastive_ce_grad_kernel<<<rows, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       sims, ld, logit_scale, rows, N, label_offset, label_smoothing, loss_weight, lse_row, lse_col, col_lo, col_hi,
-      (__nv_bfloat16*)dsims_bf16, dsims_f32, ld_d);
+      (__nv_bfloat16*)dsims_bf16, dsims_f32, ld_d, row_w, col_w);
   return (int)cudaGetLastError();
 }
 

@@ -33,7 +33,7 @@ def _dist_state():
 
 class ContrastiveFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, a, b, logit_scale, smoothing, backprop_type, want_logits):
+    def forward(ctx, a, b, logit_scale, smoothing, backprop_type, want_logits, mask=None):
         if a.shape != b.shape or a.dim() != 2:
             raise MMBError(f"contrastive loss expects two [B, E] tensors, got {tuple(a.shape)} and {tuple(b.shape)}")
         if not (a.is_cuda and b.is_cuda and logit_scale.is_cuda):
@@ -42,7 +42,7 @@ class ContrastiveFunction(torch.autograd.Function):
         a32 = a.detach().contiguous().float()
         b32 = b.detach().contiguous().float()
         s32 = logit_scale.detach().reshape(1).float().contiguous()
-        res = contrastive_schedule(a32, b32, s32, smoothing, backprop_type, want_logits, world, rank)
+        res = contrastive_schedule(a32, b32, s32, smoothing, backprop_type, want_logits, world, rank, mask)
         loss, logits_a, logits_b, loss_a, loss_b, dA, dB, dS = res
         ctx.save_for_backward(dA, dB, dS)
         ctx.in_dtypes = (a.dtype, b.dtype, logit_scale.dtype, logit_scale.shape)
@@ -58,21 +58,24 @@ class ContrastiveFunction(torch.autograd.Function):
         dA, dB, dS = ctx.saved_tensors
         da_t, db_t, ds_t, s_shape = ctx.in_dtypes
         if g_loss is None:
-            return None, None, None, None, None, None
+            return None, None, None, None, None, None, None
         g = g_loss.float()
-        return (dA * g).to(da_t), (dB * g).to(db_t), (dS * g).reshape(s_shape).to(ds_t), None, None, None
+        return (dA * g).to(da_t), (dB * g).to(db_t), (dS * g).reshape(s_shape).to(ds_t), None, None, None, None
 
 
 def _tensor_path_ok(B: int, N: int, E: int) -> bool:
     return E % 8 == 0 and B % 8 == 0 and N % 8 == 0 and B >= 64 and E >= 64
 
 
-def contrastive_schedule(a, b, s, smoothing, backprop_type, want_logits, world, rank):
+def contrastive_schedule(a, b, s, smoothing, backprop_type, want_logits, world, rank, mask=None):
     """Forward + all gradients of the contrastive loss for this rank's [B, E] embeddings (fp32, CUDA).
 
     world == 1 follows contrastive_loss_with_temperature.py:31-33 (labels = arange(B), no communication).
     world  > 1: every rank publishes bf16 embeddings + row-LSE vectors in its symmetric buffer (symm.py); peers read
     them in place — the similarity / gradient GEMMs take the peer tensors as their TMA operands.
+    mask (optional bool [B]): the reference keeps only the masked rows of both logit matrices and of the labels before
+    the mean cross-entropy (contrastive_loss_with_temperature.py:97-100).  Here it becomes per-row weights
+    mask_i / count(mask) of the mean; in GLOBAL mode the peers' weights travel with their row-LSE vectors.
     Returns (loss, logits_a, logits_b, loss_a, loss_b, dA, dB, dlogit_scale)."""
     from .symm import get_comm
 
@@ -97,6 +100,12 @@ def contrastive_schedule(a, b, s, smoothing, backprop_type, want_logits, world, 
         lo, hi = 0, 0
     SA = torch.empty((B, N), device=dev, dtype=f32)
     SB = torch.empty((B, N), device=dev, dtype=f32)
+    RW = CW = None
+    if mask is not None:
+        if mask.shape != (B,):
+            raise ValueError(f"mask must have shape [{B}], got {tuple(mask.shape)}")
+        mb = mask.to(device=dev).bool()
+        RW = mb.to(f32) / mb.sum().to(f32)   # [B] scalars: plumbing (0/0 -> nan, as the reference's empty mean)
     if tensor_path:
         comm = get_comm(B, E, dev, world)
         p = comm.step % 2
@@ -104,12 +113,14 @@ def contrastive_schedule(a, b, s, smoothing, backprop_type, want_logits, world, 
         my = comm.my
         ops.cast_bf16(a, my.a[p])
         ops.cast_bf16(b, my.b[p])
+        if RW is not None:
+            my.w[p].copy_(RW)
         comm.barrier()                                    # peers' embeddings are readable
         for r in range(world):                            # TMA loads of the B operand read peer r's buffer in place
             ops.gemm(my.a[p], comm.slots[r].b[p], epilogue=ops.EPI_F32, out=SA[:, r * B:(r + 1) * B])
             ops.gemm(my.b[p], comm.slots[r].a[p], epilogue=ops.EPI_F32, out=SB[:, r * B:(r + 1) * B])
-        ops.contrastive_ce_stats(SA, s, B, N, lab, smoothing, 0.5, RLA, my.lse_a[p], dS, logits_a)
-        ops.contrastive_ce_stats(SB, s, B, N, lab, smoothing, 0.5, RLB, my.lse_b[p], dS, logits_b)
+        ops.contrastive_ce_stats(SA, s, B, N, lab, smoothing, 0.5, RLA, my.lse_a[p], dS, logits_a, RW)
+        ops.contrastive_ce_stats(SB, s, B, N, lab, smoothing, 0.5, RLB, my.lse_b[p], dS, logits_b, RW)
         LA = LB = None
         if hi > lo:
             if world > 1:
@@ -118,12 +129,16 @@ def contrastive_schedule(a, b, s, smoothing, backprop_type, want_logits, world, 
                 for r in range(world):                    # 2*world copies of B floats (peer reads)
                     LA[r * B:(r + 1) * B].copy_(comm.slots[r].lse_a[p])
                     LB[r * B:(r + 1) * B].copy_(comm.slots[r].lse_b[p])
+                if RW is not None:                        # every rank passes a mask or none does (same call site)
+                    CW = torch.empty(N, device=dev, dtype=f32)
+                    for r in range(world):
+                        CW[r * B:(r + 1) * B].copy_(comm.slots[r].w[p])
             else:
-                LA, LB = my.lse_a[p], my.lse_b[p]
+                LA, LB, CW = my.lse_a[p], my.lse_b[p], RW
         DSA = torch.empty((B, N), device=dev, dtype=bf)
         DSB = torch.empty((B, N), device=dev, dtype=bf)
-        ops.contrastive_ce_grad(SA, s, B, N, lab, smoothing, 0.5, my.lse_a[p], LB, lo, hi, DSA, None)
-        ops.contrastive_ce_grad(SB, s, B, N, lab, smoothing, 0.5, my.lse_b[p], LA, lo, hi, DSB, None)
+        ops.contrastive_ce_grad(SA, s, B, N, lab, smoothing, 0.5, my.lse_a[p], LB, lo, hi, DSA, None, RW, CW)
+        ops.contrastive_ce_grad(SB, s, B, N, lab, smoothing, 0.5, my.lse_b[p], LA, lo, hi, DSB, None, RW, CW)
         dA = torch.empty((B, E), device=dev, dtype=f32)
         dB = torch.empty((B, E), device=dev, dtype=f32)
         for r in range(world):
@@ -135,12 +150,12 @@ def contrastive_schedule(a, b, s, smoothing, backprop_type, want_logits, world, 
         ops.matmul_f32(a, b, tb=True, out=SA)
         ops.matmul_f32(b, a, tb=True, out=SB)
         La, Lb = torch.empty(B, device=dev, dtype=f32), torch.empty(B, device=dev, dtype=f32)
-        ops.contrastive_ce_stats(SA, s, B, N, 0, smoothing, 0.5, RLA, La, dS, logits_a)
-        ops.contrastive_ce_stats(SB, s, B, N, 0, smoothing, 0.5, RLB, Lb, dS, logits_b)
+        ops.contrastive_ce_stats(SA, s, B, N, 0, smoothing, 0.5, RLA, La, dS, logits_a, RW)
+        ops.contrastive_ce_stats(SB, s, B, N, 0, smoothing, 0.5, RLB, Lb, dS, logits_b, RW)
         DSA = torch.empty((B, N), device=dev, dtype=f32)
         DSB = torch.empty((B, N), device=dev, dtype=f32)
-        ops.contrastive_ce_grad(SA, s, B, N, 0, smoothing, 0.5, La, Lb if hi > lo else None, lo, hi, None, DSA)
-        ops.contrastive_ce_grad(SB, s, B, N, 0, smoothing, 0.5, Lb, La if hi > lo else None, lo, hi, None, DSB)
+        ops.contrastive_ce_grad(SA, s, B, N, 0, smoothing, 0.5, La, Lb if hi > lo else None, lo, hi, None, DSA, RW, RW)
+        ops.contrastive_ce_grad(SB, s, B, N, 0, smoothing, 0.5, Lb, La if hi > lo else None, lo, hi, None, DSB, RW, RW)
         dA = ops.matmul_f32(DSA, b)
         dB = ops.matmul_f32(DSB, a)
     ops.sum_scale(RLA, B, 1.0 / B, out[1:2])
@@ -148,6 +163,8 @@ def contrastive_schedule(a, b, s, smoothing, backprop_type, want_logits, world, 
     ops.sum_scale(RLA, B, 0.5 / B, out[0:1])
     ops.sum_scale(RLB, B, 0.5 / B, out[0:1], accumulate=True)
     empty = torch.empty(0, device=dev, dtype=f32)
+    if mask is not None and want_logits:   # the reference returns the row-selected logits (:98-99)
+        logits_a, logits_b = logits_a[mb], logits_b[mb]
     return (out[0], logits_a if want_logits else empty, logits_b if want_logits else empty, out[1], out[2], dA, dB,
             dS.reshape(()))
 
@@ -159,8 +176,5 @@ def _single_process(a, b, s, smoothing, want_logits):
 def contrastive_loss_apply(embeddings_a, embeddings_b, logit_scale, smoothing: float,
                            backprop_type: BackpropType = BackpropType.GLOBAL, mask: Optional[torch.Tensor] = None,
                            want_logits: bool = False) -> Tuple[torch.Tensor, ...]:
-    if mask is not None:
-        # TODO(FLAVA, config 3): boolean row mask (modules/losses/contrastive_loss_with_temperature.py:97-100)
-        raise NotImplementedError("row `mask` is not supported by the fused contrastive loss yet")
     return ContrastiveFunction.apply(embeddings_a, embeddings_b, logit_scale, float(smoothing), backprop_type,
-                                     bool(want_logits))
+                                     bool(want_logits), mask)

@@ -198,17 +198,17 @@ def attention_bwd(qkv, out, dout, lse, dqkv, B, S, H, causal, scale):
 
 
 def contrastive_ce_stats(sims, logit_scale, rows, N, label_offset, smoothing, loss_weight, row_loss, lse_out,
-                         dscale_accum, logits_out=None):
+                         dscale_accum, logits_out=None, row_w=None):
     _chk(sims, torch.float32, "sims")
     _lib.check(_lib.lib().mmb_contrastive_ce_stats(_p(sims), sims.stride(0), _p(logit_scale), rows, N, label_offset,
                                                    float(smoothing), float(loss_weight), _p(row_loss), _p(lse_out),
                                                    _p(dscale_accum), _p(logits_out),
-                                                   logits_out.stride(0) if logits_out is not None else 0, _stream()),
-               "mmb_contrastive_ce_stats")
+                                                   logits_out.stride(0) if logits_out is not None else 0, _p(row_w),
+                                                   _stream()), "mmb_contrastive_ce_stats")
 
 
 def contrastive_ce_grad(sims, logit_scale, rows, N, label_offset, smoothing, loss_weight, lse_row, lse_col, col_lo,
-                        col_hi, dsims_bf16, dsims_f32):
+                        col_hi, dsims_bf16, dsims_f32, row_w=None, col_w=None):
     _chk(sims, torch.float32, "sims")
     d = dsims_bf16 if dsims_bf16 is not None else dsims_f32
     if dsims_bf16 is not None and dsims_f32 is not None and dsims_bf16.stride(0) != dsims_f32.stride(0):
@@ -216,7 +216,7 @@ def contrastive_ce_grad(sims, logit_scale, rows, N, label_offset, smoothing, los
     _lib.check(_lib.lib().mmb_contrastive_ce_grad(_p(sims), sims.stride(0), _p(logit_scale), rows, N, label_offset,
                                                   float(smoothing), float(loss_weight), _p(lse_row), _p(lse_col),
                                                   int(col_lo), int(col_hi), _p(dsims_bf16), _p(dsims_f32), d.stride(0),
-                                                  _stream()), "mmb_contrastive_ce_grad")
+                                                  _p(row_w), _p(col_w), _stream()), "mmb_contrastive_ce_grad")
 
 
 def sum_scale(inp, n, scale, out, accumulate=False):

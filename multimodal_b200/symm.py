@@ -39,10 +39,11 @@ class _Slots:
 
     def __init__(self, raw: torch.Tensor, B: int, E: int):
         off = 0
-        self.a, self.b, self.lse_a, self.lse_b = [], [], [], []
+        self.a, self.b, self.lse_a, self.lse_b, self.w = [], [], [], [], []
         for _ in range(2):
             for lst, nbytes, dt, shape in ((self.a, B * E * 2, torch.bfloat16, (B, E)), (self.b, B * E * 2, torch.bfloat16, (B, E)),
-                                           (self.lse_a, B * 4, torch.float32, (B,)), (self.lse_b, B * 4, torch.float32, (B,))):
+                                           (self.lse_a, B * 4, torch.float32, (B,)), (self.lse_b, B * 4, torch.float32, (B,)),
+                                           (self.w, B * 4, torch.float32, (B,))):
                 lst.append(raw[off:off + nbytes].view(dt).view(shape))
                 off += _align(nbytes)
         self.flags = raw[off:off + 128].view(torch.int32)
@@ -51,7 +52,7 @@ class _Slots:
 
     @staticmethod
     def size(B: int, E: int) -> int:
-        return 2 * (2 * _align(B * E * 2) + 2 * _align(B * 4)) + 128
+        return 2 * (2 * _align(B * E * 2) + 3 * _align(B * 4)) + 128
 
 
 class SymmComm:

@@ -128,7 +128,8 @@ def cross_entropy(logits: Tensor, labels: Tensor, label_smoothing: float = 0.0) 
 
 
 def contrastive_loss(a: Tensor, b: Tensor, logit_scale: Tensor, a_all: Optional[Tensor] = None,
-                     b_all: Optional[Tensor] = None, rank: int = 0, label_smoothing: float = 0.0):
+                     b_all: Optional[Tensor] = None, rank: int = 0, label_smoothing: float = 0.0,
+                     mask: Optional[Tensor] = None):
     """modules/losses/contrastive_loss_with_temperature.py:50-115.  a_all / b_all are the (already gathered,
     concatenated in rank order) global embeddings; None means single process (:31-33)."""
     T = torch.exp(logit_scale)                                                # :81
@@ -137,6 +138,8 @@ def contrastive_loss(a: Tensor, b: Tensor, logit_scale: Tensor, a_all: Optional[
     labels = a.shape[0] * rank + torch.arange(a.shape[0], device=a.device)    # :39-41
     logits_a = a @ b_all.t() * T                                              # :90-92
     logits_b = b @ a_all.t() * T                                              # :93-95
+    if mask is not None:                                                      # :97-100
+        logits_a, logits_b, labels = logits_a[mask], logits_b[mask], labels[mask]
     loss_a = cross_entropy(logits_a, labels, label_smoothing)                 # :105
     loss_b = cross_entropy(logits_b, labels, label_smoothing)                 # :106
     return (loss_a + loss_b) / 2, logits_a, logits_b, loss_a, loss_b          # :107-115
@@ -183,17 +186,17 @@ def gather_tensor(t: Tensor, mode: str):
 
 
 def contrastive_loss_distributed(a: Tensor, b: Tensor, logit_scale: Tensor, mode: str = "GLOBAL",
-                                 label_smoothing: float = 0.0):
+                                 label_smoothing: float = 0.0, mask: Optional[Tensor] = None):
     """contrastive_loss_with_temperature.py:26-115 with torch.distributed initialised (:35-45)."""
     import torch.distributed as dist
 
     a_all = torch.cat(gather_tensor(a, mode))
     b_all = torch.cat(gather_tensor(b, mode))
-    return contrastive_loss(a, b, logit_scale, a_all, b_all, dist.get_rank(), label_smoothing)
+    return contrastive_loss(a, b, logit_scale, a_all, b_all, dist.get_rank(), label_smoothing, mask)
 
 
 def contrastive_grads_lse_exchange(a: Tensor, b: Tensor, logit_scale: Tensor, mode: str = "GLOBAL",
-                                   label_smoothing: float = 0.0):
+                                   label_smoothing: float = 0.0, mask: Optional[Tensor] = None):
     """Restatement of the CUDA schedule (multimodal_b200/engine_loss.py): no gradient traffic — each rank rebuilds
     d(sum over ranks of loss)/d(its embeddings) from its own logits row block and the peers' row-LSE vectors.
     Returns (loss, dA, dB, dlogit_scale) for THIS rank; must equal autograd over contrastive_loss_distributed."""
@@ -218,22 +221,24 @@ def contrastive_grads_lse_exchange(a: Tensor, b: Tensor, logit_scale: Tensor, mo
         y = torch.zeros(B, N, dtype=a.dtype, device=a.device)
         y[torch.arange(B), r * B + torch.arange(B)] = 1.0
         t = (1 - eps) * y + eps / N
-        gs = 0.5 / B
+        # per-row weights of this rank's mean (mask_i / count) and, gathered, of every global row in ITS rank's mean
+        w = torch.full((B,), 1.0 / B, dtype=a.dtype) if mask is None else mask.to(a.dtype) / mask.sum().to(a.dtype)
+        w_all = gather(w)
         own_a, own_b = torch.exp(La - lse_a[:, None]) - t, torch.exp(Lb - lse_b[:, None]) - t
         col = torch.zeros(N, dtype=torch.bool, device=a.device)
         if mode == "GLOBAL":
             col[:] = True
         elif mode == "LOCAL":
             col[r * B:(r + 1) * B] = True
-        tr_a = (torch.exp(La - lse_b_all[None, :]) - t) * col
-        tr_b = (torch.exp(Lb - lse_a_all[None, :]) - t) * col
-        dA = gs * T * (own_a + tr_a) @ b_all
-        dB = gs * T * (own_b + tr_b) @ a_all
-        dS = gs * ((own_a * La).sum() + (own_b * Lb).sum())
+        tr_a = (torch.exp(La - lse_b_all[None, :]) - t) * (col * w_all)[None, :]
+        tr_b = (torch.exp(Lb - lse_a_all[None, :]) - t) * (col * w_all)[None, :]
+        dA = 0.5 * T * (own_a * w[:, None] + tr_a) @ b_all
+        dB = 0.5 * T * (own_b * w[:, None] + tr_b) @ a_all
+        dS = 0.5 * ((own_a * La * w[:, None]).sum() + (own_b * Lb * w[:, None]).sum())
         nll_a = lse_a - La[torch.arange(B), r * B + torch.arange(B)]
         nll_b = lse_b - Lb[torch.arange(B), r * B + torch.arange(B)]
-        loss = 0.5 * (((1 - eps) * nll_a + eps * (lse_a - La.mean(1))).mean()
-                      + ((1 - eps) * nll_b + eps * (lse_b - Lb.mean(1))).mean())
+        loss = 0.5 * ((((1 - eps) * nll_a + eps * (lse_a - La.mean(1))) * w).sum()
+                      + (((1 - eps) * nll_b + eps * (lse_b - Lb.mean(1))) * w).sum())
     return loss, dA, dB, dS
 
 

@@ -47,14 +47,16 @@ def _worker_lse(rank, world, port, q):
         B, E = 6, 16
         a0 = O.normalize(torch.randn(B, E, dtype=torch.float64))
         b0 = O.normalize(torch.randn(B, E, dtype=torch.float64))
+        masks = (None, torch.tensor([1, 0, 1, 1, 0, 1], dtype=torch.bool) if rank == 0
+                 else torch.tensor([0, 1, 1, 0, 0, 0], dtype=torch.bool))   # different row counts per rank
         for mode in ("GLOBAL", "LOCAL", "NONE"):
-            for eps in (0.0, 0.1):
+            for eps, mask in ((0.0, None), (0.1, None), (0.0, masks[1]), (0.1, masks[1])):
                 a = a0.clone().requires_grad_(True)
                 b = b0.clone().requires_grad_(True)
                 s = torch.tensor(math.log(1 / 0.07), dtype=torch.float64, requires_grad=True)
-                loss = O.contrastive_loss_distributed(a, b, s, mode, eps)[0]
+                loss = O.contrastive_loss_distributed(a, b, s, mode, eps, mask)[0]
                 loss.backward()
-                l2, dA, dB, dS = O.contrastive_grads_lse_exchange(a0, b0, s.detach(), mode, eps)
+                l2, dA, dB, dS = O.contrastive_grads_lse_exchange(a0, b0, s.detach(), mode, eps, mask)
                 torch.testing.assert_close(l2, loss.detach(), rtol=1e-12, atol=1e-12)
                 torch.testing.assert_close(dA, a.grad, rtol=1e-10, atol=1e-12)
                 torch.testing.assert_close(dB, b.grad, rtol=1e-10, atol=1e-12)

@@ -35,16 +35,18 @@ def _worker_loss(rank, world, port, q):
         B, E = 128, 256
         a0 = O.normalize(torch.randn(B, E, device=dev))
         b0 = O.normalize(torch.randn(B, E, device=dev))
+        row_mask = torch.rand(B, device=dev) < (0.8 if rank == 0 else 0.4)   # different kept-row counts per rank
+        row_mask[0] = True
         for mode in (BackpropType.GLOBAL, BackpropType.LOCAL, BackpropType.NONE):
-            for eps in (0.0, 0.1):
+            for eps, mask in ((0.0, None), (0.1, None), (0.1, row_mask)):
                 a, b = a0.clone().requires_grad_(True), b0.clone().requires_grad_(True)
                 s = torch.tensor(math.log(1 / 0.07), device=dev, requires_grad=True)
-                res = contrastive_loss_with_temperature(a, b, s, backprop_type=mode,
+                res = contrastive_loss_with_temperature(a, b, s, backprop_type=mode, mask=mask,
                                                         cross_entropy_kwargs={"label_smoothing": eps})
                 res.loss.backward()
                 ar, br = a0.clone().requires_grad_(True), b0.clone().requires_grad_(True)
                 sr = torch.tensor(math.log(1 / 0.07), device=dev, requires_grad=True)
-                ref = O.contrastive_loss_distributed(ar, br, sr, mode.name, eps)
+                ref = O.contrastive_loss_distributed(ar, br, sr, mode.name, eps, mask)
                 ref[0].backward()
                 assert abs(res.loss.item() - ref[0].item()) < 3e-3, (mode, eps, res.loss.item(), ref[0].item())
                 assert (res.logits_a - ref[1]).abs().max().item() < 3e-2     # bf16 embeddings x T=14.3

@@ -202,6 +202,36 @@ def test_contrastive_loss_tensor_core_path(dev):
     assert abs(s.grad.item() - s_r.grad.item()) < 2e-3 * max(1.0, abs(s_r.grad.item()))
 
 
+def test_contrastive_loss_row_mask_against_reference_golden(dev):
+    """`mask` argument (contrastive_loss_with_temperature.py:97-100) on the exact-fp32 path (3x5 KAT) and on the
+    tensor-core path (B=128, E=64), against outputs + autograd gradients of the unmodified reference."""
+    import os
+
+    from multimodal_b200.modules.losses.contrastive_loss_with_temperature import contrastive_loss_with_temperature
+
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "loss_mask_golden.pt"))
+    for name, c in g.items():
+        exact = name == "kat_3x5"
+        a, b = c["a"].to(dev).requires_grad_(True), c["b"].to(dev).requires_grad_(True)
+        s = torch.tensor(math.log(1 / 0.07), device=dev, requires_grad=True)
+        kw = {"label_smoothing": c["smoothing"]} if c["smoothing"] else None
+        res = contrastive_loss_with_temperature(a, b, s, mask=c["mask"].to(dev), cross_entropy_kwargs=kw)
+        res.loss.backward()
+        assert res.logits_a.shape == c["logits_a"].shape
+        assert abs(res.loss.item() - c["loss"].item()) < (1e-4 if exact else 3e-3), (name, res.loss.item())
+        assert abs(res.loss_a.item() - c["loss_a"].item()) < (1e-4 if exact else 3e-3)
+        assert (res.logits_a.cpu() - c["logits_a"]).abs().max().item() < (1e-4 if exact else 3e-2)
+        assert (res.logits_b.cpu() - c["logits_b"]).abs().max().item() < (1e-4 if exact else 3e-2)
+        tol = 1e-4 if exact else 2e-2
+        assert _rel(a.grad.cpu(), c["dA"]) < tol and _rel(b.grad.cpu(), c["dB"]) < tol, name
+        assert abs(s.grad.item() - c["dS"].item()) < (1e-3 if exact else 5e-3) * max(1.0, abs(c["dS"].item()))
+        # masked-out rows receive gradient only through the other direction's columns; all-True mask == no mask
+        full = contrastive_loss_with_temperature(a.detach(), b.detach(), s.detach(), mask=torch.ones_like(c["mask"]).to(dev),
+                                                 cross_entropy_kwargs=kw).loss
+        none = contrastive_loss_with_temperature(a.detach(), b.detach(), s.detach(), cross_entropy_kwargs=kw).loss
+        assert abs(full.item() - none.item()) < 1e-6
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # end to end
 # ---------------------------------------------------------------------------------------------------------------

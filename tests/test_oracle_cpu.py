@@ -130,3 +130,20 @@ def test_no_cpu_fallback():
     enc = CLIPViTEncoder(embedding_dim=64, patch_size=16, image_size=64, width=128, heads=2, layers=1)
     with pytest.raises(MMBError):
         enc(torch.ones(2, 3, 64, 64))
+
+
+def test_oracle_masked_loss_matches_reference_golden():
+    """Row `mask` (contrastive_loss_with_temperature.py:97-100): oracle forward + autograd vs the reference's."""
+    import os
+
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "loss_mask_golden.pt"))
+    for name, c in g.items():
+        a, b = c["a"].clone().requires_grad_(True), c["b"].clone().requires_grad_(True)
+        s = torch.tensor(math.log(1 / 0.07), requires_grad=True)
+        loss, la, lb, loss_a, loss_b = O.contrastive_loss(a, b, s, label_smoothing=c["smoothing"], mask=c["mask"])
+        loss.backward()
+        assert torch.allclose(loss, c["loss"], atol=1e-5), name
+        assert torch.allclose(la, c["logits_a"], atol=1e-5) and torch.allclose(lb, c["logits_b"], atol=1e-5)
+        assert torch.allclose(loss_a, c["loss_a"], atol=1e-5) and torch.allclose(loss_b, c["loss_b"], atol=1e-5)
+        assert torch.allclose(a.grad, c["dA"], atol=1e-6) and torch.allclose(b.grad, c["dB"], atol=1e-6)
+        assert torch.allclose(s.grad, c["dS"], atol=1e-4)
