@@ -122,7 +122,8 @@ int mmb_attention_fwd_kmask(const void* qkv, void* out, float* lse, const unsign
 int mmb_bert_embed_ln_fwd(const long long* ids, const long long* type_ids, const float* word, const float* pos,
                           const float* type, const float* gamma, const float* beta, float* x, unsigned char* kmask_out,
                           long long pad_id, int B, int S, int d, int V, float eps, void* stream);
-/* x = cat(cls, mask ? mask_token : patch_out) + pos — ImageEmbeddings.forward, models/flava/image_encoder.py:139-175. */
+/* x = cat(cls, mask ? mask_token : patch_out) + pos — ImageEmbeddings.forward, models/flava/image_encoder.py:139-175,
+ * and PatchEmbeddings.forward, modules/layers/patch_embedding.py:104-154 (cls = NULL: include_cls_embed=False, S = P). */
 int mmb_vit_assemble_fwd(const void* patch_out_bf16, const float* cls, const float* pos, const float* mask_token,
                          const unsigned char* patch_mask, float* x, int B, int S, int d, void* stream);
 /* out[b,:] = bf16(x[b*rows_per_group + row, :]) — `hidden[:, 0]` selects (Pooler, projections; losses/flava.py:92-96). */
@@ -131,6 +132,26 @@ int mmb_tanh_inplace(float* x, long long n, void* stream);
 /* out[b] = cat([cls], a[b], b[b]) along tokens — models/flava/transformer.py:55-58 + model.py:294-297. */
 int mmb_concat_tokens(const float* cls, const float* a, const float* b, float* out, int B, int Sa, int Sb, int d,
                       void* stream);
+
+
+/* ---- CoCa forward helpers ------------------------------------------------------------------ */
+/* x[b,s] = emb[ids[b,s]] + pos[s] (s < S-1), x[b,S-1] = cls + pos[S-1]; ids is [B, S-1] when cls != NULL, else [B, S]
+ * — CoCaTextEmbeddings.forward, models/coca/text_decoder.py:48-60. */
+int mmb_coca_text_embed_fwd(const long long* ids, const float* emb, const float* cls, const float* pos, float* x, int B,
+                            int S, int d, int V, void* stream);
+/* softmax(Q K^T * scale + mask) V for cross-attention / head_dim 64, 96, 128 / batch-shared queries / boolean masks:
+ * F.scaled_dot_product_attention at modules/layers/multi_head_attention.py:74-76,171-173.  q,k,v,out are bf16 with row
+ * strides ld* and batch strides bs* (elements, multiples of 8; bsq = 0 shares the queries across the batch); head h
+ * occupies columns [h*head_dim, (h+1)*head_dim).  mask (optional, uint8, 1 = attend) is addressed
+ * mask[b*mask_bs + i*mask_qs + j] (mask_qs = 0: key-padding mask).  causal follows SDPA's is_causal (j <= i). */
+int mmb_attention_fwd_generic(const void* q, long long ldq, long long bsq, const void* k, long long ldk, long long bsk,
+                              const void* v, long long ldv, long long bsv, void* out, long long ldo, long long bso,
+                              const void* mask, long long mask_bs, long long mask_qs, int B, int Sq, int Skv, int H,
+                              int head_dim, int causal, float scale, void* stream);
+/* accum[0] += sum_i CE(logits[i,:], labels[i*label_stride]) over rows with label != ignore_index; accum[1] += #rows
+ * — nn.CrossEntropyLoss(ignore_index=pad_idx), models/coca/coca_model.py:425,447-450 (forward). */
+int mmb_ce_labels(const float* logits, long long ld, const long long* labels, long long label_stride,
+                  long long ignore_index, int M, int V, float* row_loss, float* accum, void* stream);
 
 /* ---- contrastive loss -------------------------------------------------------------------------------------- */
 /* One direction of contrastive_loss_with_temperature (modules/losses/contrastive_loss_with_temperature.py:81-107),

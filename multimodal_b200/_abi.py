@@ -31,6 +31,10 @@ PROTOTYPES = {
     "mmb_gather_rows_cast": (i32, [vp, vp, i32, i32, i32, i32, vp]),
     "mmb_tanh_inplace": (i32, [vp, ll, vp]),
     "mmb_concat_tokens": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, vp]),
+    "mmb_coca_text_embed_fwd": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]),
+    "mmb_attention_fwd_generic": (i32, [vp, ll, ll, vp, ll, ll, vp, ll, ll, vp, ll, ll, vp, ll, ll, i32, i32, i32, i32, i32,
+                                        i32, f32, vp]),
+    "mmb_ce_labels": (i32, [vp, ll, vp, ll, ll, i32, i32, vp, vp, vp]),
     "mmb_contrastive_ce_stats": (i32, [vp, ll, vp, i32, i32, i32, f32, f32, vp, vp, vp, vp, ll, vp, vp]),
     "mmb_contrastive_ce_grad": (i32, [vp, ll, vp, i32, i32, i32, f32, f32, vp, vp, i32, i32, vp, vp, ll, vp, vp, vp]),
     "mmb_matmul_f32": (i32, [vp, ll, i32, vp, ll, i32, vp, ll, i32, i32, i32, f32, i32, vp]),

@@ -237,13 +237,16 @@ __global__ void bert_embed_ln_fwd_kernel(const long long* __restrict__ ids, cons
   }
 }
 
-// FLAVA image embeddings (models/flava/image_encoder.py:139-175): x[b,0] = cls + pos[0];
-// x[b,1+p] = (mask[b,p] ? mask_token : patch_out[b*P+p]) + pos[1+p].   No LayerNorm here.
+// ViT token assembly without LayerNorm (FLAVA: models/flava/image_encoder.py:139-175; TorchMultimodal PatchEmbeddings:
+// modules/layers/patch_embedding.py:104-154):  with cls:  x[b,0] = cls + pos[0]; x[b,1+p] = e[b,p] + pos[1+p]
+//                                             cls == NULL (CoCa, include_cls_embed=False): x[b,p] = e[b,p] + pos[p]
+// where e[b,p] = mask[b,p] ? mask_token : patch_out[b*P+p].
 __global__ void vit_assemble_fwd_kernel(const __nv_bfloat16* __restrict__ patch_out, const float* __restrict__ cls,
                                         const float* __restrict__ pos, const float* __restrict__ mask_token,
                                         const unsigned char* __restrict__ patch_mask, float* __restrict__ x, int B, int S,
                                         int d) {
   const int d4 = d >> 2;
+  const int off = cls ? 1 : 0, P = S - off;
   const long long total = (long long)B * S * d4;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -253,15 +256,83 @@ __global__ void vit_assemble_fwd_kernel(const __nv_bfloat16* __restrict__ patch_
     const int b = (int)(row / S);
     float4 a = __ldg(reinterpret_cast<const float4*>(pos + (long long)s * d + c));
     float4 t;
-    if (s == 0) {
+    if (s < off) {
       t = __ldg(reinterpret_cast<const float4*>(cls + c));
-    } else if (patch_mask && mask_token && patch_mask[(long long)b * (S - 1) + (s - 1)]) {
+    } else if (patch_mask && mask_token && patch_mask[(long long)b * P + (s - off)]) {
       t = __ldg(reinterpret_cast<const float4*>(mask_token + c));
     } else {
-      const uint2 u = *reinterpret_cast<const uint2*>(patch_out + ((long long)b * (S - 1) + (s - 1)) * d + c);
+      const uint2 u = *reinterpret_cast<const uint2*>(patch_out + ((long long)b * P + (s - off)) * d + c);
       t = make_float4(bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y));
     }
     reinterpret_cast<float4*>(x)[i] = make_float4(a.x + t.x, a.y + t.y, a.z + t.z, a.w + t.w);
+  }
+}
+
+// CoCa text embeddings (models/coca/text_decoder.py:48-60): x[b,s] = emb[ids[b,s]] + pos[s] for s < S-1 and
+// x[b,S-1] = cls + pos[S-1] (the CLS embedding is appended, not prepended).  cls == NULL: plain S-token embedding.
+__global__ void coca_text_embed_fwd_kernel(const long long* __restrict__ ids, const float* __restrict__ emb,
+                                           const float* __restrict__ cls, const float* __restrict__ pos,
+                                           float* __restrict__ x, int B, int S, int d, int V) {
+  const int d4 = d >> 2;
+  const int T = cls ? S - 1 : S;  // tokens per sequence in ids
+  const long long total = (long long)B * S * d4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % d4);
+    const long long row = i / d4;
+    const int s = (int)(row % S);
+    const long long b = row / S;
+    float4 e;
+    if (s < T) {
+      const long long tok = ids[b * T + s];
+      if (tok < 0 || tok >= V) __trap();
+      e = __ldg(reinterpret_cast<const float4*>(emb + tok * d) + c);
+    } else {
+      e = __ldg(reinterpret_cast<const float4*>(cls) + c);
+    }
+    const float4 p = __ldg(reinterpret_cast<const float4*>(pos + (long long)s * d) + c);
+    reinterpret_cast<float4*>(x)[i] = make_float4(e.x + p.x, e.y + p.y, e.z + p.z, e.w + p.w);
+  }
+}
+
+// Cross-entropy over rows of fp32 logits [M, V] against int64 labels with ignore_index (nn.CrossEntropyLoss(
+// ignore_index=pad) of models/coca/coca_model.py:425,447-450): accum[0] += sum of row losses, accum[1] += #valid rows.
+__global__ void __launch_bounds__(256) ce_labels_kernel(const float* __restrict__ logits, long long ld,
+                                                        const long long* __restrict__ labels, long long label_stride,
+                                                        long long ignore_index, int M, int V,
+                                                        float* __restrict__ row_loss, float* __restrict__ accum) {
+  __shared__ float red[8];
+  const int i = blockIdx.x;
+  if (i >= M) return;
+  const long long lab = labels[(long long)i * label_stride];
+  if (lab == ignore_index) {
+    if (threadIdx.x == 0 && row_loss) row_loss[i] = 0.f;
+    return;
+  }
+  if (lab < 0 || lab >= V) __trap();
+  const float* row = logits + (long long)i * ld;
+  float mx = -INFINITY;
+  for (int j = threadIdx.x; j < V; j += blockDim.x) mx = fmaxf(mx, row[j]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  mx = red[0];
+  for (int w = 1; w < 8; ++w) mx = fmaxf(mx, red[w]);
+  __syncthreads();
+  float se = 0.f;
+  for (int j = threadIdx.x; j < V; j += blockDim.x) se += __expf(row[j] - mx);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) se += __shfl_xor_sync(0xffffffffu, se, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = se;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    const float loss = mx + logf(t) - row[lab];
+    if (row_loss) row_loss[i] = loss;
+    atomicAdd(accum, loss);
+    atomicAdd(accum + 1, 1.f);
   }
 }
 
@@ -788,6 +859,19 @@ extern "C" int mmb_vit_assemble_fwd(const void* patch_out, const float* cls, con
   if (d & 3) return MMB_ERR_ARG;
   vit_assemble_fwd_kernel<<<grid_for((long long)B * S * d / 4, 256), 256, 0, ST(stream)>>>(
       (const __nv_bfloat16*)patch_out, cls, pos, mask_token, patch_mask, x, B, S, d);
+  return LAUNCH_RC();
+}
+extern "C" int mmb_coca_text_embed_fwd(const long long* ids, const float* emb, const float* cls, const float* pos,
+                                       float* x, int B, int S, int d, int V, void* stream) {
+  if (d & 3) return MMB_ERR_ARG;
+  coca_text_embed_fwd_kernel<<<grid_for((long long)B * S * d / 4, 256), 256, 0, ST(stream)>>>(ids, emb, cls, pos, x, B, S,
+                                                                                              d, V);
+  return LAUNCH_RC();
+}
+extern "C" int mmb_ce_labels(const float* logits, long long ld, const long long* labels, long long label_stride,
+                             long long ignore_index, int M, int V, float* row_loss, float* accum, void* stream) {
+  if (M <= 0 || V <= 0 || !accum) return MMB_ERR_ARG;
+  ce_labels_kernel<<<M, 256, 0, ST(stream)>>>(logits, ld, labels, label_stride, ignore_index, M, V, row_loss, accum);
   return LAUNCH_RC();
 }
 extern "C" int mmb_gather_rows_cast(const float* x, void* out_bf16, int B, int rows_per_group, int row, int d,

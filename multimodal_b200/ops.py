@@ -268,3 +268,29 @@ def tanh_(x):
 
 def concat_tokens(cls, a, b, out, B, Sa, Sb, d):
     _lib.check(_lib.lib().mmb_concat_tokens(_p(cls), _p(a), _p(b), _p(out), B, Sa, Sb, d, _stream()), "mmb_concat_tokens")
+
+
+# ---- CoCa forward helpers ---------------------------------------------------------------------------------------
+def coca_text_embed_fwd(ids, emb, cls, pos, x, B, S, d, V):
+    _chk(ids, torch.int64, "ids")
+    _lib.check(_lib.lib().mmb_coca_text_embed_fwd(_p(ids), _p(emb), _p(cls), _p(pos), _p(x), B, S, d, V, _stream()),
+               "mmb_coca_text_embed_fwd")
+
+
+def attention_fwd_generic(q, k, v, out, *, B, Sq, Skv, H, head_dim, bsq, bsk, bsv, bso, scale, mask=None, mask_bs=0,
+                          mask_qs=0, causal=False):
+    """q/k/v/out: 2-D bf16 views [rows, >= H*head_dim] (row-major, possibly column slices of a wider matrix)."""
+    for t, n in ((q, "q"), (k, "k"), (v, "v"), (out, "out")):
+        _chk(t, torch.bfloat16, n); _rowmajor(t, n)
+    if mask is not None:
+        _chk(mask, torch.uint8, "mask")
+    _lib.check(_lib.lib().mmb_attention_fwd_generic(_p(q), q.stride(0), int(bsq), _p(k), k.stride(0), int(bsk), _p(v),
+                                                    v.stride(0), int(bsv), _p(out), out.stride(0), int(bso), _p(mask),
+                                                    int(mask_bs), int(mask_qs), B, Sq, Skv, H, head_dim, int(causal),
+                                                    float(scale), _stream()), "mmb_attention_fwd_generic")
+
+
+def ce_labels(logits, labels, label_stride, ignore_index, M, V, row_loss, accum):
+    _chk(logits, torch.float32, "logits"); _chk(labels, torch.int64, "labels"); _rowmajor(logits, "logits")
+    _lib.check(_lib.lib().mmb_ce_labels(_p(logits), logits.stride(0), _p(labels), int(label_stride), int(ignore_index), M,
+                                        V, _p(row_loss), _p(accum), _stream()), "mmb_ce_labels")
