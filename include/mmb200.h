@@ -36,11 +36,14 @@ int mmb_version(void);
  * Replaces: F.linear in torch/nn/functional.py:6478 (in-proj), :6690 (out-proj),
  *           torch/nn/modules/transformer.py:980-982 (linear1/linear2), their autograd dgrad/wgrad,
  *           torch.matmul in modules/losses/contrastive_loss_with_temperature.py:90-95,
- *           `x @ self.projection` in models/clip/image_encoder.py:112, Linear in text_encoder.py:130. */
+ *           `x @ self.projection` in models/clip/image_encoder.py:112, Linear in text_encoder.py:130.
+ * colsum (optional, EPI_BF16 / EPI_BF16_DACT): colsum[n] += sum_m of the bf16-rounded D0[m,n] — the bias gradient of
+ *           the Linear whose input-gradient this GEMM produces (linear1.bias from the FC2 dgrad), fused into the
+ *           epilogue's copy-out so the tensor is not re-read by a column-sum pass. */
 int mmb_gemm_bf16(const void* A, long long lda, int a_mn_major, const void* B, long long ldb, int b_mn_major,
                   void* D0, long long ldd0, void* D1, long long ldd1, int M, int N, int K, int epilogue, int act,
                   float alpha, const float* bias, const void* aux, long long ld_aux, int splits, int accumulate,
-                  void* stream);
+                  float* colsum, void* stream);
 
 
 /* ---- HBM-bound kernels ------------------------------------------------------------------------------------ */
@@ -69,10 +72,13 @@ int mmb_vit_embed_ln_fwd(const void* patch_out_bf16, const float* cls, const flo
 
 /* LayerNorm backward (+ residual-gradient add): g_out = (g_in?) + dLN/dx; dgamma/dbeta accumulated with atomics.
  * dy is bf16 or fp32 (exactly one non-NULL).  Gather mode as in the forward: x/dy/mean/rstd are compact [M,d],
- * g_out/g_bf16 are scattered to the physical rows of a zero-initialised [*,d] buffer. */
+ * g_out/g_bf16 are scattered to the physical rows of a zero-initialised [*,d] buffer.
+ * gsum (optional, needs g_bf16): gsum[c] += sum over rows of the bf16-rounded g — the bias gradient of the Linear layer
+ * whose backward consumes g_bf16 next (out_proj / linear2 in torch/nn/modules/transformer.py:961-982), fused here so
+ * that tensor is not re-read by a column-sum kernel. */
 int mmb_layernorm_bwd(const float* x, const void* dy_bf16, const float* dy_f32, const float* mean, const float* rstd,
                       const float* gamma, const float* g_in, float* g_out, void* g_bf16, float* dgamma, float* dbeta,
-                      const int* row_idx, int rows_per_group, int M, int d, void* stream);
+                      const int* row_idx, int rows_per_group, int M, int d, float* gsum, void* stream);
 
 /* Backward of mmb_vit_embed_ln_fwd: dt = d/d(cat+pos) fp32 [B,S,d]; dpatch = bf16 copy of rows s>=1, compact. */
 int mmb_vit_embed_ln_bwd(const void* patch_out_bf16, const float* cls, const float* pos, const float* dy_f32,

@@ -7,12 +7,12 @@ vp, ll, i32, f32 = C.c_void_p, C.c_longlong, C.c_int, C.c_float
 
 PROTOTYPES = {
     "mmb_version": (i32, []),
-    "mmb_gemm_bf16": (i32, [vp, ll, i32, vp, ll, i32, vp, ll, vp, ll, i32, i32, i32, i32, i32, f32, vp, vp, ll, i32, i32, vp]),
+    "mmb_gemm_bf16": (i32, [vp, ll, i32, vp, ll, i32, vp, ll, vp, ll, i32, i32, i32, i32, i32, f32, vp, vp, ll, i32, i32, vp, vp]),
     "mmb_cast_f32_to_bf16": (i32, [vp, vp, ll, vp]),
     "mmb_im2col_patches": (i32, [vp, vp, ll, i32, i32, i32, i32, vp]),
     "mmb_add_layernorm_fwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, f32, vp]),
     "mmb_vit_embed_ln_fwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, f32, vp]),
-    "mmb_layernorm_bwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]),
+    "mmb_layernorm_bwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp, vp]),
     "mmb_vit_embed_ln_bwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]),
     "mmb_batch_sum": (i32, [vp, vp, i32, ll, i32, vp]),
     "mmb_colsum_bf16": (i32, [vp, vp, i32, i32, ll, vp]),

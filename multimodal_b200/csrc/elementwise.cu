@@ -7,6 +7,10 @@
 
 namespace mmb {
 
+__device__ __forceinline__ void red_add_v4(float* dst, const float4& v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -400,119 +404,107 @@ struct LnBwdArgs {
   const float* mean; const float* rstd; const float* gamma;
   const float* g_in; float* g_out; __nv_bfloat16* g_bf16;
   float* dgamma; float* dbeta;
+  float* gsum;  // optional: gsum[c] += sum_rows bf16(g_out[row, c]) — the bias gradient of the Linear that consumes g_bf16
   const int* row_idx; int rows_per_group;
   int M, d;
 };
 
+// One CTA of NV warps per row (one float4 of the row per thread): ~20 live registers per thread, so 10-16 CTAs are
+// resident per SM and 60+ warps hide the HBM latency (the earlier warp-per-row version kept the whole row plus three
+// per-lane column accumulators in ~170 registers and ran at 12 warps per SM, latency-bound at ~65 % of HBM peak).
+// The two row reductions cross the NV warps through a double-buffered smem slot: one __syncthreads per row.
 template <bool VIT, int NV>
-__global__ void __launch_bounds__(NV <= 4 ? 256 : 384, NV <= 4 ? 2 : 1) ln_bwd_kernel(const LnBwdArgs a) {
-  extern __shared__ float sred[];  // [2][d]
+__global__ void __launch_bounds__(NV * 32, 1536 / (NV * 32)) ln_bwd_kernel(const LnBwdArgs a) {
   constexpr int d = NV * 128;
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int wpb = blockDim.x >> 5;
-  for (int i = threadIdx.x; i < 2 * d; i += blockDim.x) sred[i] = 0.f;
-  __syncthreads();
-  float4 accg[NV], accb[NV];
-#pragma unroll
-  for (int i = 0; i < NV; ++i) { accg[i] = make_float4(0.f, 0.f, 0.f, 0.f); accb[i] = accg[i]; }
-
-  for (int m = blockIdx.x * wpb + wib; m < a.M; m += gridDim.x * wpb) {
+  __shared__ float part[2][NV][2];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int c = threadIdx.x * 4;
+  const float4 gm = __ldg(reinterpret_cast<const float4*>(a.gamma + c));
+  float4 accg = make_float4(0.f, 0.f, 0.f, 0.f), accb = accg, accs = accg;
+  const bool want_gsum = a.gsum != nullptr;
+  int buf = 0;
+  for (int m = blockIdx.x; m < a.M; m += gridDim.x) {
     long long phys = m;
     if (a.rows_per_group > 0) phys = (long long)m * a.rows_per_group + (a.row_idx ? a.row_idx[m] : 0);
+    // issue every global load of the row before the first use
+    float4 x, dy, gi = make_float4(0.f, 0.f, 0.f, 0.f);
+    uint2 pu = make_uint2(0u, 0u), du = pu;
+    float4 cl = make_float4(0.f, 0.f, 0.f, 0.f);
+    int s = 0;
+    if (VIT) {
+      const int b = m / a.S;
+      s = m - b * a.S;
+      x = __ldg(reinterpret_cast<const float4*>(a.pos + (long long)s * d + c));
+      if (s == 0) cl = __ldg(reinterpret_cast<const float4*>(a.cls + c));
+      else pu = *reinterpret_cast<const uint2*>(a.patch_out + ((long long)b * (a.S - 1) + (s - 1)) * d + c);
+    } else {
+      x = *reinterpret_cast<const float4*>(a.x + (long long)m * d + c);  // compact in gather mode
+    }
+    if (a.dy_bf16) du = *reinterpret_cast<const uint2*>(a.dy_bf16 + (long long)m * d + c);
+    else           dy = *reinterpret_cast<const float4*>(a.dy_f32 + (long long)m * d + c);
+    if (a.g_in) gi = *reinterpret_cast<const float4*>(a.g_in + phys * d + c);
     const float mean = a.mean[m], rstd = a.rstd[m];
-    float4 xh[NV], dy[NV];
-    // issue the x / dy loads of the whole row up front (2*NV independent 16 B loads per lane in flight)
+    if (VIT) {
+      if (s == 0) { x.x += cl.x; x.y += cl.y; x.z += cl.z; x.w += cl.w; }
+      else { x.x += bf16_lo(pu.x); x.y += bf16_hi(pu.x); x.z += bf16_lo(pu.y); x.w += bf16_hi(pu.y); }
+    }
+    if (a.dy_bf16) dy = make_float4(bf16_lo(du.x), bf16_hi(du.x), bf16_lo(du.y), bf16_hi(du.y));
+    float4 h;
+    h.x = (x.x - mean) * rstd; h.y = (x.y - mean) * rstd; h.z = (x.z - mean) * rstd; h.w = (x.w - mean) * rstd;
+    accg.x += dy.x * h.x; accg.y += dy.y * h.y; accg.z += dy.z * h.z; accg.w += dy.w * h.w;
+    accb.x += dy.x; accb.y += dy.y; accb.z += dy.z; accb.w += dy.w;
+    dy.x *= gm.x; dy.y *= gm.y; dy.z *= gm.z; dy.w *= gm.w;  // dy * gamma
+    float s1 = warp_sum(dy.x + dy.y + dy.z + dy.w);
+    float s2 = warp_sum(dy.x * h.x + dy.y * h.y + dy.z * h.z + dy.w * h.w);
+    if (NV > 1) {
+      if (lane == 0) { part[buf][w][0] = s1; part[buf][w][1] = s2; }
+      __syncthreads();
+      s1 = 0.f; s2 = 0.f;
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int c = (i * 32 + lane) * 4;
-      if (VIT) {
-        const int b = m / a.S, s = m - b * a.S;
-        float4 x = __ldg(reinterpret_cast<const float4*>(a.pos + (long long)s * d + c));
-        if (s == 0) {
-          const float4 t = __ldg(reinterpret_cast<const float4*>(a.cls + c));
-          x.x += t.x; x.y += t.y; x.z += t.z; x.w += t.w;
-        } else {
-          const uint2 u = *reinterpret_cast<const uint2*>(a.patch_out + ((long long)b * (a.S - 1) + (s - 1)) * d + c);
-          x.x += bf16_lo(u.x); x.y += bf16_hi(u.x); x.z += bf16_lo(u.y); x.w += bf16_hi(u.y);
-        }
-        xh[i] = x;
+      for (int i = 0; i < NV; ++i) { s1 += part[buf][i][0]; s2 += part[buf][i][1]; }
+      buf ^= 1;
+    }
+    s1 *= (1.f / d);
+    s2 *= (1.f / d);
+    float4 o;
+    o.x = rstd * (dy.x - s1 - h.x * s2) + gi.x;
+    o.y = rstd * (dy.y - s1 - h.y * s2) + gi.y;
+    o.z = rstd * (dy.z - s1 - h.z * s2) + gi.z;
+    o.w = rstd * (dy.w - s1 - h.w * s2) + gi.w;
+    if (a.g_out) *reinterpret_cast<float4*>(a.g_out + phys * d + c) = o;
+    if (a.g_bf16) {
+      uint2 u;
+      u.x = pack_bf16x2(o.x, o.y);
+      u.y = pack_bf16x2(o.z, o.w);
+      if (want_gsum) {  // sums the ROUNDED values: identical to a column sum over the stored bf16 tensor
+        accs.x += bf16_lo(u.x); accs.y += bf16_hi(u.x); accs.z += bf16_lo(u.y); accs.w += bf16_hi(u.y);
+      }
+      if (VIT) {  // bf16 gradient of the patch-embedding GEMM output: compact [B*(S-1), d], CLS row dropped
+        const int b = m / a.S;
+        if (s > 0) *reinterpret_cast<uint2*>(a.g_bf16 + ((long long)b * (a.S - 1) + (s - 1)) * d + c) = u;
       } else {
-        xh[i] = *reinterpret_cast<const float4*>(a.x + (long long)m * d + c);  // compact in gather mode
-      }
-      if (a.dy_bf16) {
-        const uint2 u = *reinterpret_cast<const uint2*>(a.dy_bf16 + (long long)m * d + c);
-        dy[i] = make_float4(bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y));
-      } else {
-        dy[i] = *reinterpret_cast<const float4*>(a.dy_f32 + (long long)m * d + c);
-      }
-    }
-    float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int c = (i * 32 + lane) * 4;
-      const float4 gm = __ldg(reinterpret_cast<const float4*>(a.gamma + c));
-      float4 h, g4 = dy[i];
-      h.x = (xh[i].x - mean) * rstd; h.y = (xh[i].y - mean) * rstd;
-      h.z = (xh[i].z - mean) * rstd; h.w = (xh[i].w - mean) * rstd;
-      accg[i].x += g4.x * h.x; accg[i].y += g4.y * h.y; accg[i].z += g4.z * h.z; accg[i].w += g4.w * h.w;
-      accb[i].x += g4.x; accb[i].y += g4.y; accb[i].z += g4.z; accb[i].w += g4.w;
-      g4.x *= gm.x; g4.y *= gm.y; g4.z *= gm.z; g4.w *= gm.w;  // dy * gamma
-      s1 += g4.x + g4.y + g4.z + g4.w;
-      s2 += g4.x * h.x + g4.y * h.y + g4.z * h.z + g4.w * h.w;
-      xh[i] = h; dy[i] = g4;
-    }
-    s1 = warp_sum(s1) * (1.f / d);
-    s2 = warp_sum(s2) * (1.f / d);
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int c = (i * 32 + lane) * 4;
-      const float4 gi = a.g_in ? *reinterpret_cast<const float4*>(a.g_in + phys * d + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-      float4 o;
-      o.x = rstd * (dy[i].x - s1 - xh[i].x * s2) + gi.x;
-      o.y = rstd * (dy[i].y - s1 - xh[i].y * s2) + gi.y;
-      o.z = rstd * (dy[i].z - s1 - xh[i].z * s2) + gi.z;
-      o.w = rstd * (dy[i].w - s1 - xh[i].w * s2) + gi.w;
-      if (a.g_out) *reinterpret_cast<float4*>(a.g_out + phys * d + c) = o;
-      if (a.g_bf16) {
-        uint2 u;
-        u.x = pack_bf16x2(o.x, o.y);
-        u.y = pack_bf16x2(o.z, o.w);
-        if (VIT) {  // bf16 gradient of the patch-embedding GEMM output: compact [B*(S-1), d], CLS row dropped
-          const int b = m / a.S, sidx = m - b * a.S;
-          if (sidx > 0) *reinterpret_cast<uint2*>(a.g_bf16 + ((long long)b * (a.S - 1) + (sidx - 1)) * d + c) = u;
-        } else {
-          *reinterpret_cast<uint2*>(a.g_bf16 + phys * d + c) = u;
-        }
+        *reinterpret_cast<uint2*>(a.g_bf16 + phys * d + c) = u;
       }
     }
   }
-  // block reduction of dgamma / dbeta partials, then one global
-  // atomic per column per block
-#pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const int c = (i * 32 + lane) * 4;
-    atomicAdd(&sred[c + 0], accg[i].x); atomicAdd(&sred[c + 1], accg[i].y);
-    atomicAdd(&sred[c + 2], accg[i].z); atomicAdd(&sred[c + 3], accg[i].w);
-    atomicAdd(&sred[d + c + 0], accb[i].x); atomicAdd(&sred[d + c + 1], accb[i].y);
-    atomicAdd(&sred[d + c + 2], accb[i].z); atomicAdd(&sred[d + c + 3], accb[i].w);
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < d; i += blockDim.x) {
-    if (a.dgamma) atomicAdd(a.dgamma + i, sred[i]);
-    if (a.dbeta) atomicAdd(a.dbeta + i, sred[d + i]);
-  }
+  // every thread owns 4 distinct columns: one vector reduction per output per CTA
+  if (a.dgamma) red_add_v4(a.dgamma + c, accg);
+  if (a.dbeta) red_add_v4(a.dbeta + c, accb);
+  if (want_gsum) red_add_v4(a.gsum + c, accs);
 }
 
 template <bool VIT>
 static int launch_ln_bwd(const LnBwdArgs& a, cudaStream_t st) {
   const int nv = a.d >> 7;
-  const int threads = nv <= 4 ? 256 : 384;
-  int grid = num_sms() * (nv <= 4 ? 2 : 1);
-  const int wpb = threads / 32;
-  if (grid > (a.M + wpb - 1) / wpb) grid = (a.M + wpb - 1) / wpb;
-  const size_t sm = 2 * a.d * sizeof(float);
+  const int threads = nv * 32;
+  int per_sm = 1536 / threads;   // matches the kernel's __launch_bounds__ (<= 42 registers per thread)
+  if (per_sm > 24) per_sm = 24;
+  int grid = num_sms() * per_sm;
+  if (grid > a.M) grid = a.M;
+  if ((reinterpret_cast<uintptr_t>(a.dgamma) | reinterpret_cast<uintptr_t>(a.dbeta) | reinterpret_cast<uintptr_t>(a.gsum)) & 15)
+    return MMB_ERR_ARG;  // vector reductions
   switch (nv) {
-#define LNB(NVV) case NVV: ln_bwd_kernel<VIT, NVV><<<grid, threads, sm, st>>>(a); break;
+#define LNB(NVV) case NVV: ln_bwd_kernel<VIT, NVV><<<grid, threads, 0, st>>>(a); break;
     LNB(1) LNB(2) LNB(3) LNB(4) LNB(5) LNB(6) LNB(7) LNB(8)
 #undef LNB
     default: return MMB_ERR_UNSUPPORTED;
@@ -759,10 +751,12 @@ extern "C" int mmb_vit_embed_ln_fwd(const void* patch_out, const float* cls, con
 extern "C" int mmb_layernorm_bwd(const float* x, const void* dy_bf16, const float* dy_f32, const float* mean,
                                  const float* rstd, const float* gamma, const float* g_in, float* g_out, void* g_bf16,
                                  float* dgamma, float* dbeta, const int* row_idx, int rows_per_group, int M, int d,
-                                 void* stream) {
+                                 float* gsum, void* stream) {
   if (!ln_dim_ok(d)) return MMB_ERR_UNSUPPORTED;
   if (M <= 0) return MMB_OK;
+  if (gsum && !g_bf16) return MMB_ERR_ARG;
   LnBwdArgs a{};
+  a.gsum = gsum;
   a.x = x; a.dy_bf16 = (const __nv_bfloat16*)dy_bf16; a.dy_f32 = dy_f32; a.mean = mean; a.rstd = rstd; a.gamma = gamma;
   a.g_in = g_in; a.g_out = g_out; a.g_bf16 = (__nv_bfloat16*)g_bf16; a.dgamma = dgamma; a.dbeta = dbeta;
   a.row_idx = row_idx; a.rows_per_group = rows_per_group; a.M = M; a.d = d;

@@ -49,6 +49,7 @@ struct GemmArgs {
   long long ld_aux;
   void* d0; void* d1;         // bf16 epilogues write with plain coalesced stores
   long long ldd0, ldd1;
+  float* colsum;              // bf16 epilogues (not ACT): colsum[n] += sum_m bf16(D0[m,n]) (bias gradient), or nullptr
   int reduce_add;             // fp32 epilogue: TMA reduce-add instead of store
 };
 
@@ -352,6 +353,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const int ch = epi_tid & 7;
             const int ncol = n0 + g * 64 + ch * 8;
             const uint8_t* s0 = sSlab + (DUAL ? 0 : slab * SLAB_BYTES);
+            const bool want_cs = !DUAL && p.colsum != nullptr;   // uniform
+            float cs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int it = 0; it < 4; ++it) {
               const int r = it * 32 + (epi_tid >> 3);
@@ -359,10 +362,30 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 const int off = r * 128 + ((ch ^ (r & 7)) << 4);
                 const uint4 val = *reinterpret_cast<const uint4*>(s0 + off);
                 *reinterpret_cast<uint4*>(D0p + (long long)(m0 + r) * p.ldd0 + ncol) = val;
+                if (want_cs) {
+                  cs[0] += bf16_lo(val.x); cs[1] += bf16_hi(val.x); cs[2] += bf16_lo(val.y); cs[3] += bf16_hi(val.y);
+                  cs[4] += bf16_lo(val.z); cs[5] += bf16_hi(val.z); cs[6] += bf16_lo(val.w); cs[7] += bf16_hi(val.w);
+                }
                 if (DUAL) {
                   const uint4 val1 = *reinterpret_cast<const uint4*>(s0 + SLAB_BYTES + off);
                   *reinterpret_cast<uint4*>(D1p + (long long)(m0 + r) * p.ldd1 + ncol) = val1;
                 }
+              }
+            }
+            if (want_cs) {
+              // Column sums of the tile's rounded output (the bias gradient of the layer whose dgrad this is): the 4
+              // lanes of a warp that share a 16 B chunk fold with two shuffles, then lanes 0..7 fire 2 vector reds each.
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                cs[e] += __shfl_xor_sync(0xffffffffu, cs[e], 8);
+                cs[e] += __shfl_xor_sync(0xffffffffu, cs[e], 16);
+              }
+              if (lane < 8 && ncol < p.N) {
+                float* dst = p.colsum + ncol;
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(cs[0]), "f"(cs[1]), "f"(cs[2]),
+                             "f"(cs[3]) : "memory");
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4), "f"(cs[4]), "f"(cs[5]),
+                             "f"(cs[6]), "f"(cs[7]) : "memory");
               }
             }
           }
@@ -471,7 +494,7 @@ using namespace mmb;
 extern "C" int mmb_gemm_bf16(const void* A, long long lda, int a_mn_major, const void* B, long long ldb,
                              int b_mn_major, void* D0, long long ldd0, void* D1, long long ldd1, int M, int N, int K,
                              int epilogue, int act, float alpha, const float* bias, const void* aux,
-                             long long ld_aux, int splits, int accumulate, void* stream_) {
+                             long long ld_aux, int splits, int accumulate, float* colsum, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (M <= 0 || N <= 0 || K <= 0) return MMB_ERR_ARG;
   if ((lda & 7) || (ldb & 7)) return MMB_ERR_ARG;
@@ -501,6 +524,9 @@ extern "C" int mmb_gemm_bf16(const void* A, long long lda, int a_mn_major, const
   g.ld_aux = ld_aux;
   g.d0 = D0; g.d1 = D1; g.ldd0 = ldd0; g.ldd1 = ldd1;
   g.reduce_add = (accumulate || g.splits > 1) ? 1 : 0;
+  if (colsum && (epilogue == EPI_F32 || epilogue == EPI_BF16_ACT || (reinterpret_cast<uintptr_t>(colsum) & 15)))
+    return MMB_ERR_ARG;
+  g.colsum = colsum;
 
   CUtensorMap tA, tB, tD0, tD1;
   int rc;

@@ -8,6 +8,8 @@ the reference call stack:
 """
 from __future__ import annotations
 
+import os
+
 from typing import Dict, List, Optional, Sequence
 
 import torch
@@ -184,9 +186,16 @@ class TransformerStack:
         self._X0 = X0 if training else None
         return XM_prev, Y
 
-    def backward(self, G: torch.Tensor, Gb: torch.Tensor, B: int, S: int, on_layer_done=None) -> torch.Tensor:
+    def top_bias_grad(self) -> torch.Tensor:
+        """Gradient slot of the last layer's linear2.bias: the producer of the incoming Gb sums its columns into it."""
+        return self.store.grad(self.layers[-1].linear2.bias)
+
+    def backward(self, G: torch.Tensor, Gb: torch.Tensor, B: int, S: int, on_layer_done=None,
+                 top_bias_done: bool = False) -> torch.Tensor:
         """G (fp32) / Gb (bf16 copy): gradient w.r.t. the final residual stream [B*S, d].  Returns G w.r.t. X0
-        (in place).  Parameter gradients are ACCUMULATED into the ParamStore's flat fp32 buffer."""
+        (in place).  Parameter gradients are ACCUMULATED into the ParamStore's flat fp32 buffer.
+        The bias gradients of linear2 / out_proj are column sums of Gb; they are produced by the LayerNorm-backward
+        kernel that writes Gb (`gsum`), not by a separate pass (top_bias_done: the caller's kernel did the top one)."""
         if not self.saved:
             raise MMBError("backward called without a saved training forward")
         st, d, ff, H = self.store, self.d, self.ff, self.H
@@ -209,20 +218,22 @@ class TransformerStack:
             # ---- MLP branch:  y = W2 act(W1 LN2(x) + b1) + b2 ----
             ops.gemm(Gb, HACT, a_mn=True, b_mn=True, epilogue=ops.EPI_F32, out=st.grad(layer.linear2.weight),
                      splits=sp(d, ff, M), accumulate=True)
-            ops.colsum_bf16(Gb, st.grad(layer.linear2.bias), M, d, d)
+            if l == self.L - 1 and not top_bias_done:
+                ops.colsum_bf16(Gb, st.grad(layer.linear2.bias), M, d, d)
             dPRE = HACT  # overwrite: act output is dead once its wgrad has been issued (same stream)
+            fuse = os.environ.get("MMB_FUSE_COLSUM_GEMM", "1") == "1"
             ops.gemm(Gb, st.shadow(layer.linear2.weight), b_mn=True, epilogue=ops.EPI_BF16_DACT, aux=PRE, out=dPRE,
-                     act=self.act)
+                     act=self.act, colsum=st.grad(layer.linear1.bias) if fuse else None)   # db1 = colsum(dPRE), fused into the epilogue
             ops.gemm(dPRE, LN2, a_mn=True, b_mn=True, epilogue=ops.EPI_F32, out=st.grad(layer.linear1.weight),
                      splits=sp(ff, d, M), accumulate=True)
-            ops.colsum_bf16(dPRE, st.grad(layer.linear1.bias), M, ff, ff)
+            if not fuse:
+                ops.colsum_bf16(dPRE, st.grad(layer.linear1.bias), M, ff, ff)
             ops.gemm(dPRE, st.shadow(layer.linear1.weight), b_mn=True, out=T1)
             ops.layernorm_bwd(XM, T1, None, m2, r2, layer.norm2.weight, G, G, Gb, st.grad(layer.norm2.weight),
-                              st.grad(layer.norm2.bias), M, d)
+                              st.grad(layer.norm2.bias), M, d, gsum=st.grad(at.out_proj.bias))
             # ---- attention branch ----
             ops.gemm(Gb, O, a_mn=True, b_mn=True, epilogue=ops.EPI_F32, out=st.grad(at.out_proj.weight),
                      splits=sp(d, d, M), accumulate=True)
-            ops.colsum_bf16(Gb, st.grad(at.out_proj.bias), M, d, d)
             ops.gemm(Gb, st.shadow(at.out_proj.weight), b_mn=True, out=T1)  # dO
             ops.attention_bwd(QKV, O, T1, LSE, T3, B, S, H, self.causal, self.scale)
             ops.gemm(T3, LN1, a_mn=True, b_mn=True, epilogue=ops.EPI_F32, out=st.grad(at.in_proj_weight),
@@ -230,7 +241,8 @@ class TransformerStack:
             ops.colsum_bf16(T3, st.grad(at.in_proj_bias), M, 3 * d, 3 * d)
             ops.gemm(T3, st.shadow(at.in_proj_weight), b_mn=True, out=T1)
             ops.layernorm_bwd(XA, T1, None, m1, r1, layer.norm1.weight, G, G, Gb, st.grad(layer.norm1.weight),
-                              st.grad(layer.norm1.bias), M, d)
+                              st.grad(layer.norm1.bias), M, d,
+                              gsum=st.grad(self.layers[l - 1].linear2.bias) if l > 0 else None)
             if on_layer_done is not None:
                 on_layer_done(l)  # all parameter gradients of layer l are final (data-parallel all-reduce hook)
         return G
@@ -304,8 +316,9 @@ class ViTTower:
         Gb = ws.get("img.Gb", (M, d), bf)
         ops.zero_(G); ops.zero_(Gb)
         ops.layernorm_bwd(XSEL, None, dLNP, ws.get("img.mP", (B,), f32), ws.get("img.rP", (B,), f32), mod.ln_post.weight, None, G, Gb,
-                          st.grad(mod.ln_post.weight), st.grad(mod.ln_post.bias), B, d, row_idx=None, rows_per_group=S)
-        self.stack.backward(G, Gb, B, S, on_layer_done=getattr(self, "layer_done_cb", None))
+                          st.grad(mod.ln_post.weight), st.grad(mod.ln_post.bias), B, d, row_idx=None, rows_per_group=S,
+                          gsum=self.stack.top_bias_grad())
+        self.stack.backward(G, Gb, B, S, on_layer_done=getattr(self, "layer_done_cb", None), top_bias_done=True)
         PO = ws.get("img.PO", (B * P, d), bf)
         DP = ws.get("img.DP", (B * P, d), bf)
         ops.vit_embed_ln_bwd(PO, mod.cls_token_embedding, mod.positional_embedding, G, ws.get("img.m0", (M,), f32), ws.get("img.r0", (M,), f32),
@@ -379,7 +392,8 @@ class TextTower:
         ops.zero_(G); ops.zero_(Gb)
         IDX = ws.get("txt.IDX", (B,), torch.int32)
         ops.layernorm_bwd(XSEL, None, dLNF, ws.get("txt.mF", (B,), f32), ws.get("txt.rF", (B,), f32), mod.ln_final.weight, None, G, Gb,
-                          st.grad(mod.ln_final.weight), st.grad(mod.ln_final.bias), B, d, row_idx=IDX, rows_per_group=S)
-        self.stack.backward(G, Gb, B, S)
+                          st.grad(mod.ln_final.weight), st.grad(mod.ln_final.bias), B, d, row_idx=IDX, rows_per_group=S,
+                          gsum=self.stack.top_bias_grad())
+        self.stack.backward(G, Gb, B, S, top_bias_done=True)
         ops.batch_sum(G, st.grad(mod.positional_embedding), B, S * d, S * d)
         ops.text_embed_bwd(self.tokens, G, st.grad(mod.token_embedding.weight), B, S, d)

@@ -45,7 +45,7 @@ def _rowmajor(t: torch.Tensor, name: str):
 
 
 def gemm(A, B, *, a_mn=False, b_mn=False, epilogue=EPI_BF16, out=None, out2=None, bias=None, aux=None, alpha=1.0,
-         act=ACT_QUICK_GELU, splits=1, accumulate=False):
+         act=ACT_QUICK_GELU, splits=1, accumulate=False, colsum=None):
     """D = alpha * op(A) @ op(B)^T (+bias).  A: [M,K] (a_mn: stored [K,M]); B: [N,K] (b_mn: stored [K,N])."""
     _chk(A, torch.bfloat16, "A"); _chk(B, torch.bfloat16, "B"); _rowmajor(A, "A"); _rowmajor(B, "B")
     M, K = (A.shape[1], A.shape[0]) if a_mn else (A.shape[0], A.shape[1])
@@ -73,7 +73,7 @@ def gemm(A, B, *, a_mn=False, b_mn=False, epilogue=EPI_BF16, out=None, out2=None
     rc = _lib.lib().mmb_gemm_bf16(_p(A), A.stride(0), int(a_mn), _p(B), B.stride(0), int(b_mn), _p(out), out.stride(0),
                                   _p(out2), out2.stride(0) if out2 is not None else 0, M, N, K, epilogue, act,
                                   float(alpha), _p(bias), _p(aux), aux.stride(0) if aux is not None else 0,
-                                  int(splits), int(accumulate), _stream())
+                                  int(splits), int(accumulate), _p(colsum), _stream())
     _lib.check(rc, "mmb_gemm_bf16")
     if ev is not None:
         ev[1].record()
@@ -132,10 +132,10 @@ def vit_embed_ln_fwd(patch_out, cls, pos, gamma, beta, x0, mean, rstd, B, S, d, 
 
 
 def layernorm_bwd(x, dy_bf16, dy_f32, mean, rstd, gamma, g_in, g_out, g_bf16, dgamma, dbeta, M, d, row_idx=None,
-                  rows_per_group=0):
+                  rows_per_group=0, gsum=None):
     _lib.check(_lib.lib().mmb_layernorm_bwd(_p(x), _p(dy_bf16), _p(dy_f32), _p(mean), _p(rstd), _p(gamma), _p(g_in),
                                             _p(g_out), _p(g_bf16), _p(dgamma), _p(dbeta), _p(row_idx), rows_per_group,
-                                            M, d, _stream()), "mmb_layernorm_bwd")
+                                            M, d, _p(gsum), _stream()), "mmb_layernorm_bwd")
 
 
 def vit_embed_ln_bwd(patch_out, cls, pos, dy_f32, mean, rstd, gamma, dt_f32, dpatch_bf16, dgamma, dbeta, B, S, d):

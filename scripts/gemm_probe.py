@@ -38,7 +38,7 @@ def gemm(A, a_mn, B, b_mn, M, N, K, epi, act=0, alpha=1.0, bias=None, aux=None, 
     st = torch.cuda.current_stream().cuda_stream
     rc = L.mmb_gemm_bf16(ptr(A), A.stride(0), a_mn, ptr(B), B.stride(0), b_mn, ptr(D0), D0.stride(0), ptr(D1),
                          D1.stride(0) if D1 is not None else 0, M, N, K, epi, act, alpha, ptr(bias), ptr(aux),
-                         aux.stride(0) if aux is not None else 0, splits, accumulate, ctypes.c_void_p(st))
+                         aux.stride(0) if aux is not None else 0, splits, accumulate, ctypes.c_void_p(0), ctypes.c_void_p(st))
     if rc != 0:
         raise RuntimeError(f"mmb_gemm_bf16 rc={rc}")
     return D0, D1

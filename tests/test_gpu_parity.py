@@ -46,15 +46,20 @@ def test_gemm_tcgen05(dev, M, N, K, a_mn, b_mn, epi, splits):
     bias = torch.randn(N, device=dev)
     ref = A2.float() @ B2.float().t()
     if epi == 0:
-        out = ops.gemm(A, B, a_mn=a_mn, b_mn=b_mn, epilogue=0, bias=bias, alpha=0.5)
+        cs = torch.ones(N, device=dev)
+        out = ops.gemm(A, B, a_mn=a_mn, b_mn=b_mn, epilogue=0, bias=bias, alpha=0.5, colsum=cs)
         assert _rel(out, 0.5 * ref + bias) < 6e-3  # bf16 output rounding
+        # fused bias-gradient column sums: accumulated (+=) over the ROUNDED output, fp32
+        torch.testing.assert_close(cs, 1.0 + out.float().sum(0), rtol=1e-4, atol=1e-3 * out.float().abs().sum(0).max().item())
     elif epi == 1:
         pre, act = ops.gemm(A, B, a_mn=a_mn, b_mn=b_mn, epilogue=1, bias=bias, alpha=0.125)
         assert _rel(pre, 0.125 * ref + bias) < 6e-3
         assert _rel(act, O.quick_gelu(pre.float())) < 6e-3
     elif epi == 2:
         aux = torch.randn(M, N, device=dev).bfloat16()
-        out = ops.gemm(A, B, a_mn=a_mn, b_mn=b_mn, epilogue=2, aux=aux, alpha=0.125)
+        cs = torch.zeros(N, device=dev)
+        out = ops.gemm(A, B, a_mn=a_mn, b_mn=b_mn, epilogue=2, aux=aux, alpha=0.125, colsum=cs)
+        torch.testing.assert_close(cs, out.float().sum(0), rtol=1e-4, atol=1e-3 * out.float().abs().sum(0).max().item())
         x = aux.float()
         s = torch.sigmoid(1.702 * x)
         assert _rel(out, 0.125 * ref * (s * (1 + 1.702 * x * (1 - s)))) < 6e-3
@@ -120,6 +125,13 @@ def test_add_layernorm_fwd_bwd(dev, M, d):
     torch.testing.assert_close(gout - gin, xs.grad, rtol=1e-4, atol=1e-5)
     torch.testing.assert_close(dg, gp.grad, rtol=1e-4, atol=1e-4)
     torch.testing.assert_close(db, bp.grad, rtol=1e-4, atol=1e-4)
+    # fused column sums of the bf16 gradient copy (bias gradient of the Linear that consumes it)
+    gb = torch.empty(M, d, device=dev, dtype=torch.bfloat16)
+    gs = torch.full((d,), 2.0, device=dev)
+    dg.zero_(); db.zero_()
+    ops.layernorm_bwd(xo, None, dy, mean, rstd, g, gin, gout, gb, dg, db, M, d, gsum=gs)
+    torch.testing.assert_close(gb.float(), gout, rtol=1e-2, atol=1e-2)
+    torch.testing.assert_close(gs, 2.0 + gb.float().sum(0), rtol=1e-4, atol=1e-3 * gb.float().abs().sum(0).max().item())
 
 
 def test_integer_paths_bit_exact(dev):
