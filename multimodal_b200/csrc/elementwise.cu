@@ -414,7 +414,7 @@ struct LnBwdArgs {
 // per-lane column accumulators in ~170 registers and ran at 12 warps per SM, latency-bound at ~65 % of HBM peak).
 // The two row reductions cross the NV warps through a double-buffered smem slot: one __syncthreads per row.
 template <bool VIT, int NV>
-__global__ void __launch_bounds__(NV * 32, 1536 / (NV * 32)) ln_bwd_kernel(const LnBwdArgs a) {
+__global__ void __launch_bounds__(NV * 32, (1536 / (NV * 32) > 32 ? 32 : 1536 / (NV * 32))) ln_bwd_kernel(const LnBwdArgs a) {
   constexpr int d = NV * 128;
   __shared__ float part[2][NV][2];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
