@@ -23,8 +23,13 @@ __device__ unsigned long long* g_attn_trace = nullptr;
     if (g_attn_trace && blockIdx.z == gridDim.z / 2 && blockIdx.y == 3)                                          \
       g_attn_trace[(((kind) * 2 + (tile)) * 2 + (role)) * 64 + (slot)] = clock64();                             \
   } while (0)
+#define PTRACE(kind, role, slot)                                                                                 \
+  do {                                                                                                           \
+    if (g_attn_trace && blockIdx.x == 1 && n == 6) g_attn_trace[((kind) * 4 + (role)) * 64 + (slot)] = clock64(); \
+  } while (0)
 #else
 #define ATRACE(kind, tile, role, slot) do {} while (0)
+#define PTRACE(kind, role, slot) do {} while (0)
 #endif
 
 constexpr int ATT_THREADS = 256;
@@ -533,17 +538,18 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_co
 // TMEM (512 columns): [S|dP] buffer i at i*128 (S +0, dP +64); accumulators of tile parity j at 256 + j*128 (+0, +64).
 // Barrier phases are derived from running counters (tile sequence n, global chunk sequence g).
 // ------------------------------------------------------------------------------------------------
-constexpr int P_WORKERS = 8;                       // worker warps 0..7 (TMEM lane quadrant = warp & 3)
-constexpr int P_STATS = 2;                         // statistics warps 11..12: softmax LSE and D = rowsum(dO*O), one tile ahead
-constexpr int P_THREADS = (P_WORKERS + 3 + P_STATS) * 32;  // + producer warp 8, score issuer 9, accumulate issuer 10
-
-template <bool CAUSAL, bool DKDV>
-__global__ void __launch_bounds__(P_THREADS, 1)
+constexpr int P_STATS = 2;   // statistics warps: softmax LSE and D = rowsum(dO*O), one tile ahead
+// NG column groups per row: 4*NG worker warps (TMEM lane quadrant = warp & 3, column group = warp >> 2), then the
+// producer warp, the score issuer, the accumulate issuer and the statistics warps.
+template <bool CAUSAL, bool DKDV, int NG>
+__global__ void __launch_bounds__((4 * NG + 3 + P_STATS) * 32, 1)
 attn_bwd_persist_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_constant__ CUtensorMap tmQKV64,
                         const __grid_constant__ CUtensorMap tmDO128, const __grid_constant__ CUtensorMap tmDO64,
                         const AttnTcArgs p, const int n_work) {
   constexpr int RING = DKDV ? 3 : 4;
   constexpr int CH = 8192;  // one 64-row x 128 B chunk operand
+  constexpr int P_WORKERS = 4 * NG;
+  constexpr int CW = 64 / NG;   // columns of a chunk per worker thread
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sA = smem;                                   // [2 tile buffers][A0 16 KB | A1 16 KB]
@@ -637,9 +643,12 @@ attn_bwd_persist_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gr
         for (int c = 0; c < nc; ++c, ++g) {
           const int st = (int)(g % RING), sb = (int)(g & 1);
           const int wc = min(64, S_pad - c * 64);
+          PTRACE(DKDV, 1, c * 4 + 0);
           mbar_wait(&ring_full[st], (uint32_t)((g / RING) & 1));
+          PTRACE(DKDV, 1, c * 4 + 1);
           mbar_wait(&sdp_empty[sb], (uint32_t)(((g >> 1) & 1) ^ 1));
           tc_fence_after();
+          PTRACE(DKDV, 1, c * 4 + 2);
           const uint32_t id = idesc_rt(wc, false, false);
           const uint32_t ub = uRing + st * 2 * CH;
           const uint64_t b0 = desc_k(ub), b1 = desc_k(ub + CH);
@@ -649,6 +658,7 @@ attn_bwd_persist_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gr
 #pragma unroll
           for (int k = 0; k < 4; ++k) umma_bf16(tS + 64, a1 + 2 * k, b1 + 2 * k, id, k > 0);
           umma_commit(&sdp_full[sb]);
+          PTRACE(DKDV, 1, c * 4 + 3);
         }
         umma_commit(&tile_empty[tb]);   // every MMA that reads this tile buffer has been issued before this commit
       }
@@ -667,7 +677,9 @@ attn_bwd_persist_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gr
         for (int c = 0; c < nc; ++c, ++g) {
           const int st = (int)(g % RING), sb = (int)(g & 1);
           const int wc = min(64, S_pad - c * 64);
+          PTRACE(DKDV, 2, c * 4 + 0);
           mbar_wait(&ds_full[sb], (uint32_t)((g >> 1) & 1));
+          PTRACE(DKDV, 2, c * 4 + 1);
           mbar_wait(&ring_full[st], (uint32_t)((g / RING) & 1));  // long complete; acquires the TMA writes for this thread
           tc_fence_after();
           const uint32_t ub = uRing + st * 2 * CH;
@@ -684,6 +696,7 @@ attn_bwd_persist_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gr
           umma_commit(&ds_empty[sb]);
           umma_commit(&ring_empty[st]);
           if (c == nc - 1) umma_commit(&acc_full[ab]);
+          PTRACE(DKDV, 2, c * 4 + 2);
         }
       }
     }
@@ -735,7 +748,7 @@ attn_bwd_persist_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gr
       if (lane == 0) mbar_arrive(&stat_full[n & 1]);   // release: the smem writes above are visible to the waiters
     }
   } else {
-    // ======================= 8 worker warps: thread == tile row x column half =======================
+    // ======================= 4*NG worker warps: thread == tile row x column group =======================
     const int q4 = warp & 3, grp = warp >> 2;
     const int r = q4 * 32 + lane;
     const uint32_t trow = tmem + ((uint32_t)(q4 * 32) << 16);
@@ -749,33 +762,44 @@ attn_bwd_persist_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gr
       float Lrow = 0.f, Drow = 0.f;
       const float* sL = sLD + (n & 1) * 512;
       const float* sD = sL + 256;
+      if (threadIdx.x == 0) PTRACE(DKDV, 0, 40);
       mbar_wait(&stat_full[n & 1], (n >> 1) & 1);
       if (!DKDV) {
         Lrow = sL[r];
         Drow = sD[r];
       }
+      if (threadIdx.x == 0) PTRACE(DKDV, 0, 41);
 
       for (int c = 0; c < nc; ++c, ++g) {
         const int sb = (int)(g & 1);
         const int wc = min(64, S_pad - c * 64);
+        if (threadIdx.x == 0) PTRACE(DKDV, 0, c * 5 + 0);
         mbar_wait(&sdp_full[sb], (uint32_t)((g >> 1) & 1));
         tc_fence_after();
-        uint32_t sv[32], dv[32];
-        tmem_ld32(trow + sb * 128 + grp * 32, sv);
-        tmem_ld32(trow + sb * 128 + 64 + grp * 32, dv);
+        if (threadIdx.x == 0) PTRACE(DKDV, 0, c * 5 + 1);
+        uint32_t sv[CW], dv[CW];
+        if (CW == 32) {
+          tmem_ld32(trow + sb * 128 + grp * 32, reinterpret_cast<uint32_t(&)[32]>(sv));
+          tmem_ld32(trow + sb * 128 + 64 + grp * 32, reinterpret_cast<uint32_t(&)[32]>(dv));
+        } else {
+          tmem_ld16(trow + sb * 128 + grp * 16, reinterpret_cast<uint32_t(&)[16]>(sv));
+          tmem_ld16(trow + sb * 128 + 64 + grp * 16, reinterpret_cast<uint32_t(&)[16]>(dv));
+        }
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&sdp_empty[sb]);
+        if (threadIdx.x == 0) PTRACE(DKDV, 0, c * 5 + 2);
         mbar_wait(&ds_empty[sb], (uint32_t)(((g >> 1) & 1) ^ 1));  // accumulate MMAs of chunk g-2 have left the buffer
+        if (threadIdx.x == 0) PTRACE(DKDV, 0, c * 5 + 3);
         uint8_t* myDS = sDS + sb * ATOM;
         uint8_t* myPT = sPT + sb * ATOM;
         {
-          const int cbase = c * 64 + grp * 32;
-          const bool full = (ri < S) && (cbase + 32 <= S) && (!CAUSAL || (DKDV ? (ri <= cbase) : (cbase + 31 <= ri)));
+          const int cbase = c * 64 + grp * CW;
+          const bool full = (ri < S) && (cbase + CW <= S) && (!CAUSAL || (DKDV ? (ri <= cbase) : (cbase + CW - 1 <= ri)));
           const float nD = -Drow * p.scale;
 #pragma unroll
-          for (int half = 0; half < 2; ++half) {
+          for (int half = 0; half < CW / 16; ++half) {
             float ds[16], pt[16];
             if (ri >= S) {
 #pragma unroll
@@ -821,26 +845,34 @@ attn_bwd_persist_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gr
                 ds[e] = pv * (__uint_as_float(dv[half * 16 + e]) - Dv) * p.scale;
               }
             }
-            if (grp * 32 + half * 16 < wc) {
-              store_p16(myDS, r, grp * 32 + half * 16, ds);
-              if (DKDV) store_p16(myPT, r, grp * 32 + half * 16, pt);
+            if (grp * CW + half * 16 < wc) {
+              store_p16(myDS, r, grp * CW + half * 16, ds);
+              if (DKDV) store_p16(myPT, r, grp * CW + half * 16, pt);
             }
           }
         }
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&ds_full[sb]);
+        if (threadIdx.x == 0) PTRACE(DKDV, 0, c * 5 + 4);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&stat_empty[n & 1]);   // this warp no longer reads sLD[n & 1]
       // ---- tile epilogue: accumulators (TMEM buffer n & 1) -> bf16 -> dqkv ----
       const int ab = n & 1;
+      if (threadIdx.x == 0) PTRACE(DKDV, 0, 42);
       mbar_wait(&acc_full[ab], (n >> 1) & 1);
       tc_fence_after();
+      if (threadIdx.x == 0) PTRACE(DKDV, 0, 43);
       const long long ld = 3LL * d;
-      uint32_t v0[32], v1[32];
-      tmem_ld32(trow + 256 + ab * 128 + grp * 32, v0);
-      if (DKDV) tmem_ld32(trow + 256 + ab * 128 + 64 + grp * 32, v1);
+      uint32_t v0[CW], v1[CW];
+      if (CW == 32) {
+        tmem_ld32(trow + 256 + ab * 128 + grp * 32, reinterpret_cast<uint32_t(&)[32]>(v0));
+        if (DKDV) tmem_ld32(trow + 256 + ab * 128 + 64 + grp * 32, reinterpret_cast<uint32_t(&)[32]>(v1));
+      } else {
+        tmem_ld16(trow + 256 + ab * 128 + grp * 16, reinterpret_cast<uint32_t(&)[16]>(v0));
+        if (DKDV) tmem_ld16(trow + 256 + ab * 128 + 64 + grp * 16, reinterpret_cast<uint32_t(&)[16]>(v1));
+      }
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
@@ -851,9 +883,9 @@ attn_bwd_persist_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gr
           // DQ: acc0 -> Q block.  DKDV: acc0 = dV -> V block (2d), acc1 = dK -> K block (d)
           const uint32_t* v = which == 0 ? v0 : v1;
           const int coff = !DKDV ? 0 : (which == 0 ? 2 * d : d);
-          __nv_bfloat16* dst = p.dqkv + (long long)(row0 + ri) * ld + coff + h * 64 + grp * 32;
+          __nv_bfloat16* dst = p.dqkv + (long long)(row0 + ri) * ld + coff + h * 64 + grp * CW;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
+          for (int j = 0; j < CW / 8; ++j) {
             uint4 o;
             o.x = pack_bf16x2(__uint_as_float(v[j * 8 + 0]), __uint_as_float(v[j * 8 + 1]));
             o.y = pack_bf16x2(__uint_as_float(v[j * 8 + 2]), __uint_as_float(v[j * 8 + 3]));
@@ -863,6 +895,7 @@ attn_bwd_persist_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gr
           }
         }
       }
+      if (threadIdx.x == 0) PTRACE(DKDV, 0, 44);
     }
   }
   tc_fence_before();
@@ -968,9 +1001,19 @@ extern "C" int mmb_attention_bwd_tc(const void* qkv, const void* out, const void
     cudaGetDevice(&dev_id);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev_id);
     const int grid_p = n_work < sms ? n_work : sms;
-#define LAUNCH_BWDP(C, K, SM)                                                                                  \
-  cudaFuncSetAttribute(attn_bwd_persist_kernel<C, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM);       \
-  attn_bwd_persist_kernel<C, K><<<grid_p, P_THREADS, SM, st>>>(q128, q64, o128, o64, a, n_work);
+    static int png_env = -1;  // MMB_ATTN_PNG=2|4: worker column groups of the persistent kernel (default 2)
+    if (png_env < 0) {
+      const char* e = getenv("MMB_ATTN_PNG");
+      png_env = (e && e[0] == '4') ? 4 : 2;   // 16 worker warps measured 3 % slower than 8 (TMEM-read bound)
+    }
+#define LAUNCH_BWDP(C, K, SM)                                                                                     \
+  if (png_env == 2) {                                                                                             \
+    cudaFuncSetAttribute(attn_bwd_persist_kernel<C, K, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM);     \
+    attn_bwd_persist_kernel<C, K, 2><<<grid_p, (8 + 3 + P_STATS) * 32, SM, st>>>(q128, q64, o128, o64, a, n_work); \
+  } else {                                                                                                        \
+    cudaFuncSetAttribute(attn_bwd_persist_kernel<C, K, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM);     \
+    attn_bwd_persist_kernel<C, K, 4><<<grid_p, (16 + 3 + P_STATS) * 32, SM, st>>>(q128, q64, o128, o64, a, n_work); \
+  }
     if (causal) {
       LAUNCH_BWDP(true, false, BWDP_DQ_SMEM)
       LAUNCH_BWDP(true, true, BWDP_DKDV_SMEM)
