@@ -36,8 +36,6 @@ template <bool CTA2, int EPI> struct Cfg {
 };
 constexpr int SLAB_BYTES = 128 * 128;           // 128 rows x 128 B
 constexpr int NUM_SLABS = 2;
-constexpr int GEMM_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
-constexpr int EPI_THREADS = 256;
 constexpr int GEMM_SMEM_BYTES = 1024 /*align slack*/ + 4 * (A_BYTES + 32768) + NUM_SLABS * SLAB_BYTES + 256;  // == 6 * (16K + 16K) + ...
 
 struct GemmArgs {
@@ -53,7 +51,7 @@ struct GemmArgs {
   int reduce_add;             // fp32 epilogue: TMA reduce-add instead of store
 };
 
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+template <int NT> __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory"); }
 __device__ __forceinline__ void half_bar_sync(int h) { asm volatile("bar.sync %0, 128;" ::"r"(2 + h) : "memory"); }
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -64,8 +62,10 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
-template <bool A_MN, bool B_MN, int EPI, int ACT, bool CTA2>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+// EW = epilogue warps: 8 (thread == row x column half) or, for the activation epilogues whose per-element math
+// (MUFU + ~8 FP32 ops) two warps per scheduler cannot hide, 16 (thread == row x column quarter).
+template <bool A_MN, bool B_MN, int EPI, int ACT, bool CTA2, int EW>
+__global__ void __launch_bounds__(64 + EW * 32, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmD0, const __grid_constant__ CUtensorMap tmD1, const GemmArgs p) {
   extern __shared__ uint8_t smem_raw[];
@@ -101,7 +101,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     for (int i = 0; i < ACC_STAGES; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], CTA2 ? 16 : 8);  // one arrive per epilogue warp (of both CTAs of a pair)
+      mbar_init(&tempty_bar[i], CTA2 ? 2 * EW : EW);  // one arrive per epilogue warp (of both CTAs of a pair)
     }
     fence_mbar_init();
   }
@@ -207,10 +207,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     // ===================== Epilogue (warps 2..9) =====================
     // Thread == tile row (TMEM lane); the two warpgroups ("halves") split the columns so that every SM sub-partition
     // has two epilogue warps to interleave (MUFU / tcgen05.ld latency hiding).
+    static_assert(EW == 8 || (EW == 16 && EPI != EPI_F32), "the fp32 epilogue is written for two column halves");
+    constexpr int NP = EW / 4;                // column parts per 64-column group
+    constexpr int CWE = 64 / NP;              // columns per thread per group (32 | 16)
+    constexpr int ENT = EW * 32;              // epilogue threads
     const int q = warp & 3;                   // TMEM lane quadrant this warp may access
-    const int half = (warp - 2) >> 2;         // 0: warps 2..5, 1: warps 6..9
+    const int half = (warp - 2) >> 2;         // column part: 0: warps 2..5, 1: warps 6..9, (2, 3: warps 10..17)
     const int row = q * 32 + lane;            // row of the tile owned by this thread
-    const int epi_tid = threadIdx.x - 64;     // 0..255
+    const int epi_tid = threadIdx.x - 64;     // 0..ENT-1
     int acc = 0;
     uint32_t acc_phase = 0;
     int slab = 0;
@@ -277,25 +281,26 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         __nv_bfloat16* D1p = reinterpret_cast<__nv_bfloat16*>(p.d1);
         for (int g = 0; g < BLOCK_N / 64; ++g) {
           if (n0 + g * 64 >= p.N) break;
-          if (DUAL) epi_bar_sync();  // both slabs are rewritten every group
+          if (DUAL) epi_bar_sync<ENT>();  // both slabs are rewritten every group
           uint8_t* dst0 = sSlab + (DUAL ? 0 : slab * SLAB_BYTES) + row * 128;
           uint8_t* dst1 = sSlab + SLAB_BYTES + row * 128;
           {
             const int h = half;
-            uint32_t v[32];
-            tmem_ld32(t_addr + g * 64 + h * 32, v);
-            const int nb = n0 + g * 64 + h * 32;
-            uint4 auxv[4];
+            uint32_t v[CWE];
+            if (CWE == 32) tmem_ld32(t_addr + g * 64 + h * 32, reinterpret_cast<uint32_t(&)[32]>(v));
+            else           tmem_ld16(t_addr + g * 64 + h * 16, reinterpret_cast<uint32_t(&)[16]>(v));
+            const int nb = n0 + g * 64 + h * CWE;
+            uint4 auxv[CWE / 8];
             if (EPI == EPI_BF16_DACT) {
               mbar_wait(&aux_bar[g & 1], (aux_phase >> (g & 1)) & 1);
               const uint8_t* arow = sAux + (g & 1) * SLAB_BYTES + row * 128;
 #pragma unroll
-              for (int j = 0; j < 4; ++j)
-                auxv[j] = *reinterpret_cast<const uint4*>(arow + (((h * 4 + j) ^ (row & 7)) << 4));
+              for (int j = 0; j < CWE / 8; ++j)
+                auxv[j] = *reinterpret_cast<const uint4*>(arow + (((h * (CWE / 8) + j) ^ (row & 7)) << 4));
             }
             tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {  // 8 columns -> one 16 B chunk
+            for (int j = 0; j < CWE / 8; ++j) {  // 8 columns -> one 16 B chunk
               float f[8];
 #pragma unroll
               for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[j * 8 + e]) * p.alpha;
@@ -319,7 +324,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               o.y = pack_bf16x2(f[2], f[3]);
               o.z = pack_bf16x2(f[4], f[5]);
               o.w = pack_bf16x2(f[6], f[7]);
-              const int off = ((h * 4 + j) ^ (row & 7)) << 4;
+              const int off = ((h * (CWE / 8) + j) ^ (row & 7)) << 4;
               *reinterpret_cast<uint4*>(dst0 + off) = o;
               if (DUAL) {
                 // The activation is applied to the bf16-ROUNDED pre-activation: exactly what the backward (which
@@ -340,7 +345,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               }
             }
           }
-          epi_bar_sync();
+          epi_bar_sync<ENT>();
           if (EPI == EPI_BF16_DACT) {
             aux_phase ^= 1u << (g & 1);
             if (epi_tid == 0 && g + 2 < BLOCK_N / 64 && n0 + (g + 2) * 64 < p.N) {  // slab (g & 1) is free again
@@ -348,7 +353,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               tma_load_2d(&tmD1, &aux_bar[g & 1], sAux + (g & 1) * SLAB_BYTES, n0 + (g + 2) * 64, m0);
             }
           }
-          // coalesced copy-out: 128 rows x 8 chunks of 16 B; thread -> (row = it*32 + tid/8, chunk = tid%8)
+          // coalesced copy-out: 128 rows x 8 chunks of 16 B; thread -> (row = it*(ENT/8) + tid/8, chunk = tid%8)
           {
             const int ch = epi_tid & 7;
             const int ncol = n0 + g * 64 + ch * 8;
@@ -356,8 +361,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const bool want_cs = !DUAL && p.colsum != nullptr;   // uniform
             float cs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-            for (int it = 0; it < 4; ++it) {
-              const int r = it * 32 + (epi_tid >> 3);
+            for (int it = 0; it < 1024 / ENT; ++it) {
+              const int r = it * (ENT / 8) + (epi_tid >> 3);
               if (m0 + r < p.M && ncol < p.N) {
                 const int off = r * 128 + ((ch ^ (r & 7)) << 4);
                 const uint4 val = *reinterpret_cast<const uint4*>(s0 + off);
@@ -459,10 +464,10 @@ int num_sms() {
   return g_num_sms;
 }
 
-template <bool A_MN, bool B_MN, int EPI, int ACT, bool CTA2>
+template <bool A_MN, bool B_MN, int EPI, int ACT, bool CTA2, int EW>
 static int launch_impl(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tD0, const CUtensorMap& tD1,
                        const GemmArgs& args, cudaStream_t stream) {
-  auto kfn = gemm_kernel<A_MN, B_MN, EPI, ACT, CTA2>;
+  auto kfn = gemm_kernel<A_MN, B_MN, EPI, ACT, CTA2, EW>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
@@ -481,7 +486,7 @@ static int launch_impl(const CUtensorMap& tA, const CUtensorMap& tB, const CUten
   } else {
     cfg.gridDim = dim3(total < num_sms() ? total : num_sms());
   }
-  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.blockDim = dim3(64 + EW * 32);
   cfg.dynamicSmemBytes = GEMM_SMEM_BYTES;
   cfg.stream = stream;
   return (int)cudaLaunchKernelEx(&cfg, kfn, tA, tB, tD0, tD1, args);
@@ -559,10 +564,23 @@ extern "C" int mmb_gemm_bf16(const void* A, long long lda, int a_mn_major, const
   }
 
   const int am = a_mn_major ? 1 : 0, bm = b_mn_major ? 1 : 0;
-#define MMB_CASE(AM, BM, E, AC)                                                                             \
-  if (am == AM && bm == BM && epilogue == E && (AC < 0 || act == AC))                                       \
-    return cta2 ? launch_impl<(AM != 0), (BM != 0), E, (AC < 0 ? 0 : AC), true>(tA, tB, tD0, tD1, g, stream) \
-                : launch_impl<(AM != 0), (BM != 0), E, (AC < 0 ? 0 : AC), false>(tA, tB, tD0, tD1, g, stream);
+  // activation epilogues: 8 epilogue warps; MMB_GEMM_EW=16 selects the experimental 16-warp variant (FC2-dgrad x act'
+  // 871 -> 996 TFLOP/s in isolation, FC1+act unchanged; not yet validated inside the full training step)
+  static int ew_env = -1;
+  if (ew_env < 0) {
+    const char* e = getenv("MMB_GEMM_EW");
+    ew_env = (e && e[0] == '1' && e[1] == '6') ? 16 : 8;
+  }
+  const bool act_epi = epilogue == EPI_BF16_ACT || epilogue == EPI_BF16_DACT;
+#define MMB_CASE(AM, BM, E, AC)                                                                                     \
+  if (am == AM && bm == BM && epilogue == E && (AC < 0 || act == AC)) {                                             \
+    constexpr int EWX = (E == EPI_BF16_ACT || E == EPI_BF16_DACT) ? 16 : 8;                                         \
+    if (act_epi && ew_env == 16)                                                                                    \
+      return cta2 ? launch_impl<(AM != 0), (BM != 0), E, (AC < 0 ? 0 : AC), true, EWX>(tA, tB, tD0, tD1, g, stream)  \
+                  : launch_impl<(AM != 0), (BM != 0), E, (AC < 0 ? 0 : AC), false, EWX>(tA, tB, tD0, tD1, g, stream); \
+    return cta2 ? launch_impl<(AM != 0), (BM != 0), E, (AC < 0 ? 0 : AC), true, 8>(tA, tB, tD0, tD1, g, stream)      \
+                : launch_impl<(AM != 0), (BM != 0), E, (AC < 0 ? 0 : AC), false, 8>(tA, tB, tD0, tD1, g, stream);     \
+  }
   MMB_CASE(0, 0, EPI_BF16, -1)
   MMB_CASE(0, 0, EPI_BF16_ACT, ACT_QUICK_GELU)
   MMB_CASE(0, 0, EPI_BF16_ACT, ACT_GELU_ERF)
