@@ -975,16 +975,22 @@ extern "C" int mmb_attention_bwd_tc(const void* qkv, const void* out, const void
   rc = make_tmap_2d(&o64, dout, 2, false, (uint64_t)d, (uint64_t)B * S, (uint64_t)d * 2, 64, 64);
   if (rc) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  // scratch for D = rowsum(dO * O): grows on demand, stream-ordered (one scratch per process / device)
-  static float* dsum = nullptr;
-  static size_t dsum_cap = 0;
+  // scratch for D = rowsum(dO * O): one buffer per device, grows on demand (cudaFree synchronises, so a buffer still
+  // in use by an earlier launch is never freed under it)
+  constexpr int MAX_DEV = 64;
+  static float* dsum_dev[MAX_DEV] = {};
+  static size_t dsum_cap[MAX_DEV] = {};
+  int cur_dev = 0;
+  cudaGetDevice(&cur_dev);
+  if (cur_dev < 0 || cur_dev >= MAX_DEV) return MMB_ERR_UNSUPPORTED;
   const size_t need = (size_t)B * H * S * sizeof(float);
-  if (need > dsum_cap) {
-    if (dsum) cudaFree(dsum);
-    cudaError_t e = cudaMalloc(&dsum, need);
-    if (e != cudaSuccess) { dsum = nullptr; dsum_cap = 0; return (int)e; }
-    dsum_cap = need;
+  if (need > dsum_cap[cur_dev]) {
+    if (dsum_dev[cur_dev]) cudaFree(dsum_dev[cur_dev]);
+    cudaError_t e = cudaMalloc(&dsum_dev[cur_dev], need);
+    if (e != cudaSuccess) { dsum_dev[cur_dev] = nullptr; dsum_cap[cur_dev] = 0; return (int)e; }
+    dsum_cap[cur_dev] = need;
   }
+  float* dsum = dsum_dev[cur_dev];
   AttnTcArgs a{};
   a.S = S; a.H = H; a.S_pad = S_pad; a.scale = scale; a.scale_log2 = scale * 1.4426950408889634f;
   a.lse = const_cast<float*>(lse); a.o_in = (const __nv_bfloat16*)out; a.dout = (const __nv_bfloat16*)dout;
