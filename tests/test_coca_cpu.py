@@ -54,3 +54,29 @@ def test_coca_modules_refuse_cpu_execution():
     inp = CC.inputs("coca_parallel")
     with pytest.raises(MMBError):
         m(inp["images"], inp["texts"])
+
+
+def test_coca_oracle_reproduces_reference_known_answers():
+    """The reference's own constant-init known-answer test (tests/models/coca/test_coca_model.py:45-165): pooled
+    embeddings 0.3536, logits 8.0, losses contrastive 0.6931 / captioning 3.9120 (parallel pooler), run through OUR
+    drop-in builder's state dict (same keys) and the oracle."""
+    from multimodal_b200.models.coca import coca_for_pretraining
+
+    kw = dict(vision_patch_size=4, vision_dim_feedforward=24, vision_n_layer=2, vision_n_head=2, vocab_size=50,
+              num_text_positions=11, text_hidden_dim=8, text_n_layer=2, text_n_head=2, text_dim_feedforward=32,
+              text_output_dim=8, fusion_n_layer=2, fusion_n_head=2, fusion_dim_feedforward=32,
+              multimodal_output_projection_dim=50, pooler_input_embed_dim=6, pooler_output_embed_dim=8, image_size=12,
+              pooler_n_head=2, cascaded_pooler=False)
+    m = coca_for_pretraining(**kw).eval()
+    with torch.no_grad():   # tests/test_utils.py:193-205 init_weights_with_constant
+        for n, p in m.named_parameters():
+            p.fill_(0.0 if n.endswith(("text_projection.bias", "output_projection.bias", "vision_proj.bias")) else 1.0)
+    torch.manual_seed(0)
+    images = torch.randn(2, 3, 12, 12)
+    texts = torch.tensor([[1, 3, 4, 5, 6, 7, 8, 2, 0, 0, 0], [1, 25, 28, 34, 39, 45, 40, 5, 12, 6, 2]])
+    out = CO.coca_forward(m.state_dict(), kw, images, texts)
+    assert torch.allclose(out["image_pooled_output"], 0.3536 * torch.ones(2, 8), atol=1e-4)
+    assert torch.allclose(out["text_pooled_output"], 0.3536 * torch.ones(2, 8), atol=1e-4)
+    assert torch.allclose(out["multimodal_embeddings"], 8.0 * torch.ones(2, 10, 50), atol=1e-4)
+    assert abs(out["contrastive"].item() - 0.6931) < 1e-4
+    assert abs(out["captioning"].item() - 3.9120) < 1e-4

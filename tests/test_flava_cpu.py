@@ -66,3 +66,36 @@ def test_flava_modules_refuse_cpu_execution():
         m.image_encoder(None)
     with pytest.raises(ValueError):
         m.text_encoder()
+
+
+def test_flava_text_oracle_reproduces_reference_known_answers():
+    """tests/models/flava/test_text_encoder.py:26-125 of the reference: 2-d BERT encoder built under seed 0 from the
+    drop-in containers (same RNG consumption as the reference's) + fixed embedding tables; hidden states with and without
+    an explicit attention mask."""
+    from functools import partial
+
+    from torch import nn
+
+    from multimodal_b200.models.flava.transformer import init_transformer_weights, TransformerEncoder
+    from multimodal_b200.modules.encoders.bert_text_encoder import BERTTextEncoder
+    from multimodal_b200.modules.layers.text_embedding import BERTTextEmbeddings
+
+    torch.manual_seed(0)
+    emb_w = torch.Tensor([[0, 1], [1, 0], [1, 1]])
+    emb = BERTTextEmbeddings(hidden_size=2, vocab_size=3, max_position_embeddings=2, dropout=0)
+    emb.word_embeddings = nn.Embedding.from_pretrained(emb_w)
+    emb.position_embeddings = nn.Embedding.from_pretrained(emb_w)
+    emb.token_type_embeddings = nn.Embedding.from_pretrained(emb_w)
+    enc = TransformerEncoder(n_layer=1, d_model=2, n_head=1, dim_feedforward=1, activation=nn.GELU, norm_first=True)
+    m = BERTTextEncoder(embeddings=emb, encoder=enc, layernorm=nn.LayerNorm(2), pooler=nn.Identity(),
+                        weight_init_fn=partial(init_transformer_weights, initializer_range=0.02))
+    sd = {"text_encoder." + k: v for k, v in m.state_dict().items()}
+    cfg = dict(text_num_hidden_layers=1, text_num_attention_heads=1, pad_token_id=0, text_layer_norm_eps=1e-12)
+    # the test's final LayerNorm is nn.LayerNorm(2) (eps 1e-5); the oracle applies one eps to all: irrelevant at 1e-4
+    ids = torch.tensor([[0, 1]])
+    out = FO.text_encoder(ids, sd, cfg)      # test_text_transformer: default mask = ids != pad (token 0 is the pad id)
+    assert torch.allclose(out["hidden_states"][0], torch.Tensor([[[1.0, -1.0], [-1.0, 1.0]]]), atol=1e-4)
+    assert torch.allclose(out["hidden_states"][1], torch.Tensor([[[1.0008, -0.9994], [-0.9997, 1.0012]]]), atol=1e-4)
+    assert torch.allclose(out["last_hidden_state"], torch.Tensor([[[1.0, -1.0], [-1.0, 1.0]]]), atol=1e-3)
+    out = FO.text_encoder(ids, sd, cfg, attention_mask=torch.tensor([[1, 0]]))   # test_text_transformer_attn_mask
+    assert torch.allclose(out["hidden_states"][1], torch.Tensor([[[0.9997, -1.0012], [-1.0008, 0.9994]]]), atol=1e-4)
