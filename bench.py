@@ -184,6 +184,14 @@ def run_ours(args):
     from multimodal_b200.train import ContrastiveTrainer
     from oracle import clip_oracle as O  # only for the synthetic-input generator + the bounded cpu_baseline leg
 
+    if not _lib.LIB_PATH.exists():  # harness convenience on a fresh checkout: local rank 0 builds, the others wait
+        if int(os.environ.get("LOCAL_RANK", "0")) == 0:
+            _lib.build()
+        else:
+            t_wait = time.time()
+            while not _lib.LIB_PATH.exists() and time.time() - t_wait < 900:
+                time.sleep(2)
+            time.sleep(2)
     _lib.lib()  # fail loudly right away if the CUDA library is missing
     B = args.batch
     torch.manual_seed(0)
