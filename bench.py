@@ -80,7 +80,7 @@ def cpu_port_run(steps, warmup, batch, budget_s=None):
             for p in params:
                 p -= 1e-4 * p.grad
                 p.grad = None
-        return float(loss)
+        return float(loss.detach())
 
     for _ in range(warmup):
         step()
