@@ -99,3 +99,25 @@ def test_flava_text_oracle_reproduces_reference_known_answers():
     assert torch.allclose(out["last_hidden_state"], torch.Tensor([[[1.0, -1.0], [-1.0, 1.0]]]), atol=1e-3)
     out = FO.text_encoder(ids, sd, cfg, attention_mask=torch.tensor([[1, 0]]))   # test_text_transformer_attn_mask
     assert torch.allclose(out["hidden_states"][1], torch.Tensor([[[0.9997, -1.0012], [-1.0008, 0.9994]]]), atol=1e-4)
+
+
+def test_flava_image_oracle_reproduces_reference_known_answers():
+    """tests/models/flava/test_image_encoder.py:20-130 of the reference: 1x1-patch, 2-d image transformer built under
+    seed 0 from the drop-in containers; embeddings and final hidden state for an all-ones image."""
+    from torch import nn
+
+    from multimodal_b200.models.flava.image_encoder import ImageEmbeddings, ImageTransformer
+    from multimodal_b200.models.flava.transformer import TransformerEncoder
+
+    torch.manual_seed(0)
+    emb = ImageEmbeddings(image_size=2, patch_size=1, hidden_size=2)
+    enc = TransformerEncoder(n_layer=1, d_model=2, n_head=1, dim_feedforward=1, activation=nn.GELU, norm_first=True)
+    m = ImageTransformer(embeddings=emb, encoder=enc, layernorm=nn.LayerNorm(2), pooler=nn.Identity())
+    sd = {"image_encoder." + k: v for k, v in m.state_dict().items()}
+    cfg = dict(patch_size=1, image_num_hidden_layers=1, image_num_attention_heads=1, image_layer_norm_eps=1e-12,
+               image_final_layer_norm_eps=1e-5)   # the test passes a plain nn.LayerNorm(2) as the final layernorm
+    out = FO.image_encoder(torch.ones(2, 3, 2, 2), sd, cfg)
+    e = torch.Tensor([[0.0, 0.0]] + [[0.0224, 0.0573]] * 4)
+    assert torch.allclose(out["hidden_states"][0], e.expand(2, 5, 2), atol=1e-4)
+    last = torch.Tensor([[-0.0040, 0.0040]] + [[-0.9840, 0.9840]] * 4)
+    assert torch.allclose(out["last_hidden_state"], last.expand(2, 5, 2), atol=1e-4)
