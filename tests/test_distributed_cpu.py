@@ -100,3 +100,48 @@ def test_symmetric_slot_layout():
     assert all(x % 256 == 0 for x in ptrs) and ptrs == sorted(ptrs) and len(set(ptrs)) == 8
     assert s.a[1].shape == (B, E) and s.a[1].dtype == torch.bfloat16 and s.lse_b[0].dtype == torch.float32
     assert s.flags.numel() == 32 and s.flags.dtype == torch.int32
+
+
+def _worker_reference_kat(rank, world, port, q):
+    """The reference's own multi-GPU known-answer test (tests/modules/losses/test_contrastive_loss_with_temperature.py
+    :129-239: global batch 4 split over the ranks, Linear(8,3) / Linear(5,3) encoders under seed 0, GLOBAL backprop):
+    mean loss 3.8848, mean image-weight grad 0.0979, mean text-bias grad -1.8151, logit_scale grad 3.6792 — here through
+    the oracle's all-gather formulation AND through the LSE-exchange schedule the CUDA path implements."""
+    from oracle import clip_oracle as O
+
+    _init(rank, world, port)
+    try:
+        torch.manual_seed(0)
+        image_tensor, text_tensor = torch.randn(4, 8), torch.randn(4, 5)          # fixture order of the reference test
+        image_encoder, text_encoder = torch.nn.Linear(8, 3), torch.nn.Linear(5, 3)
+        lb = 4 // world
+        li, lt = torch.split(image_tensor, lb)[rank], torch.split(text_tensor, lb)[rank]
+        scale = torch.tensor(math.log(1 / 0.07), requires_grad=True)
+        a, b = image_encoder(li), text_encoder(lt)
+        loss = O.contrastive_loss_distributed(a, b, O.clamp_logit_scale(scale), "GLOBAL")[0]
+        loss.backward()
+
+        def gathered_mean(x):
+            xs = [torch.zeros_like(x) for _ in range(world)]
+            dist.all_gather(xs, x.contiguous())
+            return torch.stack(xs).mean().item()
+
+        assert abs(gathered_mean(loss.detach().reshape(1)) - 3.8848) < 1e-3
+        assert abs(gathered_mean(image_encoder.weight.grad) - 0.0979) < 1e-3
+        assert abs(gathered_mean(text_encoder.bias.grad) - (-1.8151)) < 1e-3
+        assert abs(gathered_mean(scale.grad.reshape(1)) - 3.6792) < 1e-3
+        # the same numbers from the no-gradient-traffic schedule (what engine_loss.contrastive_schedule runs)
+        l2, dA, dB, dS = O.contrastive_grads_lse_exchange(a.detach(), b.detach(), scale.detach().clamp(0, math.log(100)), "GLOBAL")
+        w_grad = dA.t() @ li              # d loss / d W_image = dA^T x  (Linear backward), per rank
+        assert abs(gathered_mean(l2.reshape(1)) - 3.8848) < 1e-3
+        assert abs(gathered_mean(w_grad) - 0.0979) < 1e-3
+        assert abs(gathered_mean(dB.sum(0)) - (-1.8151)) < 1e-3
+        assert abs(gathered_mean(dS.reshape(1)) - 3.6792) < 1e-3
+        q.put((rank, "ok"))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_reference_multi_gpu_loss_known_answers_gloo():
+    _run(_worker_reference_kat, world=2)
+    _run(_worker_reference_kat, world=1)
