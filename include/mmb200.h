@@ -45,6 +45,12 @@ int mmb_gemm_bf16(const void* A, long long lda, int a_mn_major, const void* B, l
                   float alpha, const float* bias, const void* aux, long long ld_aux, int splits, int accumulate,
                   float* colsum, void* stream);
 
+/* Test / A-B hook (process-wide): force the kernel variant mmb_gemm_bf16 dispatches to.
+ *   cta2: -1 = automatic (size heuristic), 0 = 1-CTA 128x256 tiles, 1 = CTA pairs (cta_group::2, 256x256 tiles);
+ *   epilogue_warps: 0 = default, 8 or 16 = warps of the activation epilogues.  Returns MMB_ERR_ARG on other values.
+ * No reference counterpart: it exists so the parity tests can drive both kernels over every operand / epilogue case. */
+int mmb_gemm_set_mode(int cta2, int epilogue_warps);
+
 
 /* ---- HBM-bound kernels ------------------------------------------------------------------------------------ */
 
@@ -109,15 +115,15 @@ int mmb_adamw_step(float* p, float* g, float* m, float* v, void* p_bf16, long lo
 int mmb_memset_async(void* p, int value, long long bytes, void* stream);
 
 /* ---- attention --------------------------------------------------------------------------------------------- */
-/* O = softmax(Q K^T * scale [+ causal mask]) V per (batch, head); qkv bf16 [B*S, 3*H*64] packed [q|k|v], out bf16
- * [B*S, H*64], lse fp32 [B,H,S].  Replaces F.scaled_dot_product_attention (torch/nn/functional.py:6682). */
+/* O = softmax(Q K^T * scale [+ causal mask]) V per (batch, head), head_dim 64, S <= 384 (tcgen05 kernels; larger S
+ * returns MMB_ERR_UNSUPPORTED); qkv bf16 [B*S, 3*H*64] packed [q|k|v], out bf16 [B*S, H*64], lse fp32 [B,H,S].  Replaces F.scaled_dot_product_attention (torch/nn/functional.py:6682). */
 int mmb_attention_fwd(const void* qkv, void* out, float* lse, int B, int S, int H, int head_dim, int causal,
                       float scale, void* stream);
 int mmb_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, int B, int S,
                       int H, int head_dim, int causal, float scale, void* stream);
 
 /* Same with a key-padding mask [B,S] (1 = attend, 0 = masked_fill(-inf)): the BERT-style attention of the FLAVA text
- * tower (modules/encoders/bert_text_encoder.py:87-93 -> modules/layers/attention.py:228-229).  S <= 256. */
+ * tower (modules/encoders/bert_text_encoder.py:87-93 -> modules/layers/attention.py:228-229).  S <= 384. */
 int mmb_attention_fwd_kmask(const void* qkv, void* out, float* lse, const unsigned char* kmask, int B, int S, int H,
                             int head_dim, int causal, float scale, void* stream);
 

@@ -8,6 +8,7 @@ vp, ll, i32, f32 = C.c_void_p, C.c_longlong, C.c_int, C.c_float
 PROTOTYPES = {
     "mmb_version": (i32, []),
     "mmb_gemm_bf16": (i32, [vp, ll, i32, vp, ll, i32, vp, ll, vp, ll, i32, i32, i32, i32, i32, f32, vp, vp, ll, i32, i32, vp, vp]),
+    "mmb_gemm_set_mode": (i32, [i32, i32]),
     "mmb_cast_f32_to_bf16": (i32, [vp, vp, ll, vp]),
     "mmb_im2col_patches": (i32, [vp, vp, ll, i32, i32, i32, i32, vp]),
     "mmb_add_layernorm_fwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, f32, vp]),

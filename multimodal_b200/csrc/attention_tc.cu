@@ -70,29 +70,34 @@ __device__ __forceinline__ void store_p16(uint8_t* base, int r, int j0, const fl
 template <bool CAUSAL>
 __global__ void __launch_bounds__(ATT_THREADS, 2)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant__ CUtensorMap tmPad,
-                   const AttnTcArgs p) {
+                   const __grid_constant__ CUtensorMap tmRem, const AttnTcArgs p) {
   extern __shared__ uint8_t smem_raw[];
   // 1024 B alignment for the 128B-swizzle atoms; pointer arithmetic on the __shared__ array keeps the address
   // space known to the compiler (LDS/STS instead of generic LD/ST).
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* sQ = smem;               // 16 KB   } aliased by sP (4 atoms) once S = Q K^T has completed
-  uint8_t* sK = smem + ATOM;        // <=32 KB }
+  // S_pad <= 256: Q 16 KB | K <= 32 KB (aliased by P, 4 atoms, once S = Q K^T has completed) | V <= 32 KB: two CTAs
+  // per SM.  256 < S_pad <= 384 (ViT-L/14 with CLS, FLAVA multimodal): K and V take 3 atoms each, P 6 (one CTA / SM).
+  const int S = p.S, S_pad = p.S_pad, d = p.H * 64;
+  const bool big = S_pad > 256;
+  uint8_t* sQ = smem;
+  uint8_t* sK = smem + ATOM;
   uint8_t* sP = smem;
-  uint8_t* sV = smem + 4 * ATOM;    // <=32 KB
-  float* sRed = reinterpret_cast<float*>(smem + 6 * ATOM);  // [2][128] max, [2][128] sum
-  uint8_t* sMask = reinterpret_cast<uint8_t*>(sRed + 512);   // [256] key mask of this batch row (1 = attend)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sMask + 256);
+  uint8_t* sV = smem + (big ? 6 : 4) * ATOM;
+  float* sRed = reinterpret_cast<float*>(smem + (big ? 9 : 6) * ATOM);  // [2][128] max, [2][128] sum
+  uint8_t* sMask = reinterpret_cast<uint8_t*>(sRed + 512);   // [SMAX_FWD] key mask of this batch row (1 = attend)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sMask + 384);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-  const int S = p.S, S_pad = p.S_pad, d = p.H * 64;
-  const uint32_t ncols = S_pad <= 128 ? 128u : 256u;
+  const uint32_t ncols = S_pad <= 128 ? 128u : (S_pad <= 256 ? 256u : 512u);
   const bool has_mask = p.kmask != nullptr;
-  sMask[threadIdx.x] = (threadIdx.x < S && (!has_mask || p.kmask[(long long)blockIdx.z * S + threadIdx.x])) ? 1 : 0;
+  for (int i = threadIdx.x; i < 384; i += ATT_THREADS)
+    sMask[i] = (i < S && (!has_mask || p.kmask[(long long)blockIdx.z * S + i])) ? 1 : 0;
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tm128);
     tma_prefetch_desc(&tmPad);
+    if (big) tma_prefetch_desc(&tmRem);
     mbar_init(&bars[0], 1);  // Q,K landed
     mbar_init(&bars[1], 1);  // V landed
     mbar_init(&bars[2], 1);  // MMA done (phase 0: S, phase 1: O)
@@ -106,17 +111,29 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
   const int row0 = b * S;
 
   if (threadIdx.x == 0) {
+    // K / V rows [0, min(S_pad,256)) come in one box (tmPad), the remainder (S_pad > 256) in a second one (tmRem)
+    const int n1 = big ? 256 : S_pad, n2 = S_pad - n1;
     mbar_arrive_expect_tx(&bars[0], ATOM + S_pad * 128);
     tma_load_2d(&tm128, &bars[0], sQ, h * 64, row0 + qt * 128);
     tma_load_2d(&tmPad, &bars[0], sK, d + h * 64, row0);
+    if (big) tma_load_2d(&tmRem, &bars[0], sK + 256 * 128, d + h * 64, row0 + 256);
     mbar_arrive_expect_tx(&bars[1], S_pad * 128);
     tma_load_2d(&tmPad, &bars[1], sV, 2 * d + h * 64, row0);
+    if (big) tma_load_2d(&tmRem, &bars[1], sV + 256 * 128, 2 * d + h * 64, row0 + 256);
     mbar_wait(&bars[0], 0);
     tc_fence_after();
-    const uint32_t id = idesc_rt(S_pad, false, false);
     const uint64_t da = desc_k(smem_u32(sQ)), db = desc_k(smem_u32(sK));
+    {
+      const uint32_t id = idesc_rt(n1, false, false);   // UMMA N <= 256: the scores are issued in two column blocks
 #pragma unroll
-    for (int k = 0; k < 4; ++k) umma_bf16(tmem, da + 2 * k, db + 2 * k, id, k > 0);
+      for (int k = 0; k < 4; ++k) umma_bf16(tmem, da + 2 * k, db + 2 * k, id, k > 0);
+    }
+    if (big) {
+      const uint32_t id = idesc_rt(n2, false, false);
+      const uint64_t db2 = desc_k(smem_u32(sK) + 256 * 128);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) umma_bf16(tmem + 256, da + 2 * k, db2 + 2 * k, id, k > 0);
+    }
     umma_commit(&bars[2]);
   }
   mbar_wait(&bars[2], 0);
@@ -215,311 +232,6 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
     tmem_dealloc(tmem, ncols);
   }
 }
-
-// ------------------------------------------------------------------------------------------------
-// Backward.  One skeleton, two roles:
-//   DQ   : tile rows = queries  (resident A0 = Q tile, A1 = dO tile; chunk ring streams K_c / V_c;
-//          acc0 = dQ += dS_c K_c)                                           -> also stores D = rowsum(dO * O)
-//   DKDV : tile rows = keys     (resident A0 = K tile, A1 = V tile;  chunk ring streams Q_c / dO_c;
-//          acc0 = dV += P^T_c dO_c, acc1 = dK += dS^T_c Q_c)
-// 64-wide chunks of the other sequence dimension are TMA-streamed through a small ring; TMEM holds S_c, dP_c and
-// the accumulators (256 columns) and shared memory stays under 100 KB, so TWO CTAs are resident per SM and one
-// CTA's softmax arithmetic overlaps the other's MMAs / loads.
-// TMEM columns: S @0 ; dP @64 ; acc0 @128 ; acc1 @192.
-// ------------------------------------------------------------------------------------------------
-// NG column groups: thread == (tile row) x (column group); 4*NG worker warps + 1 issuer warp.  NG = 4 (16 worker
-// warps, 16 columns per thread per chunk) doubles the resident warps per SM but measured 4 % SLOWER than NG = 2: the
-// per-CTA critical path is the single-thread MMA issue + the TMA prologue (scripts/attn_trace.py), not warp count.
-template <bool CAUSAL, bool DKDV, int NG>
-__global__ void __launch_bounds__(NG * 128 + 32, 2)
-attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_constant__ CUtensorMap tmQKV64,
-                   const __grid_constant__ CUtensorMap tmDO128, const __grid_constant__ CUtensorMap tmDO64,
-                   const AttnTcArgs p) {
-  constexpr int RING = DKDV ? 2 : 3;
-  constexpr int CH = 8192;  // one 64-row x 128 B chunk operand
-  constexpr int NW = 4 * NG;      // worker warps; the issuer is warp NW
-  constexpr int CW = 64 / NG;     // columns of a chunk per worker thread
-  extern __shared__ uint8_t smem_raw[];
-  // 1024 B alignment for the 128B-swizzle atoms; pointer arithmetic on the __shared__ array keeps the address
-  // space known to the compiler (LDS/STS instead of generic LD/ST).
-  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* sA0 = smem;                        // 16 KB  tile operand 0 (Q | K_j)
-  uint8_t* sA1 = smem + ATOM;                 // 16 KB  tile operand 1 (dO | V_j)
-  uint8_t* sRing = smem + 2 * ATOM;           // RING x (B0_c 8 KB | B1_c 8 KB)
-  uint8_t* sDS = sRing + RING * 2 * CH;       // 16 KB  dS chunk (K-major A operand)
-  uint8_t* sPT = sDS + ATOM;                  // 16 KB  P^T chunk (DKDV only)
-  float* sL = reinterpret_cast<float*>(sDS + (DKDV ? 2 : 1) * ATOM);  // [256] lse (log2 units) per q (DKDV only)
-  float* sD = sL + 256;                                                // [256] rowsum(dO*O) per q (DKDV only)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sD + 256);
-  uint64_t* bar_tile = bars;        // [1] A0/A1 landed
-  uint64_t* bar_ld = bars + 1;      // [RING] chunk operands landed
-  uint64_t* bar_s = bars + 4;       // S_c/dP_c ready                       issuer -> workers (parity c & 1)
-  uint64_t* bar_acc = bars + 5;     // accumulate-MMAs of chunk c complete   issuer -> workers + issuer
-  uint64_t* bar_done = bars + 6;    // all MMAs complete
-  uint64_t* bar_rd = bars + 7;      // workers finished READING S_c/dP_c from TMEM (8 warp arrivals) -> issuer
-  uint64_t* bar_st = bars + 8;      // workers finished WRITING dS_c / P^T_c to smem (8 warp arrivals) -> issuer
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tile = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-  const int S = p.S, S_pad = p.S_pad, d = p.H * 64;
-  const int row0 = b * S;
-  const int nc = (S_pad + 63) >> 6;
-  if (threadIdx.x == 0) ATRACE(DKDV, tile, 0, 0);
-  if (threadIdx.x == 0) {
-    tma_prefetch_desc(&tmQKV128); tma_prefetch_desc(&tmQKV64);
-    tma_prefetch_desc(&tmDO128); tma_prefetch_desc(&tmDO64);
-    mbar_init(bar_tile, 1);
-    for (int i = 0; i < RING; ++i) mbar_init(&bar_ld[i], 1);
-    mbar_init(bar_s, 1); mbar_init(bar_acc, 1); mbar_init(bar_done, 1);
-    mbar_init(bar_rd, NW); mbar_init(bar_st, NW);
-    fence_mbar_init();
-  }
-  if (warp == NW) tmem_alloc(tmem_slot, 256);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
-  if (threadIdx.x == 0) ATRACE(DKDV, tile, 0, 1);
-
-  if (warp == NW) {
-    // ======================= issuer warp: TMA loads + every tcgen05.mma =======================
-    if (lane == 0) {
-      const uint32_t uA0 = smem_u32(sA0), uA1 = smem_u32(sA1), uRing = smem_u32(sRing);
-      const uint32_t uDS = smem_u32(sDS), uPT = smem_u32(sPT);
-      auto load_chunk = [&](int c) {
-        const int st = c % RING;
-        uint8_t* dst = sRing + st * 2 * CH;
-        mbar_arrive_expect_tx(&bar_ld[st], 2 * CH);
-        if (!DKDV) {
-          tma_load_2d(&tmQKV64, &bar_ld[st], dst, d + h * 64, row0 + c * 64);          // K_c
-          tma_load_2d(&tmQKV64, &bar_ld[st], dst + CH, 2 * d + h * 64, row0 + c * 64);  // V_c
-        } else {
-          tma_load_2d(&tmQKV64, &bar_ld[st], dst, h * 64, row0 + c * 64);               // Q_c
-          tma_load_2d(&tmDO64, &bar_ld[st], dst + CH, h * 64, row0 + c * 64);            // dO_c
-        }
-      };
-      auto issue_scores = [&](int c) {  // S_c / dP_c (or their transposes)
-        const int wc = min(64, S_pad - c * 64);
-        const uint32_t id = idesc_rt(wc, false, false);
-        const uint32_t ub = uRing + (c % RING) * 2 * CH;
-        const uint64_t a0 = desc_k(uA0), a1 = desc_k(uA1), b0 = desc_k(ub), b1 = desc_k(ub + CH);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16(tmem, a0 + 2 * k, b0 + 2 * k, id, k > 0);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16(tmem + 64, a1 + 2 * k, b1 + 2 * k, id, k > 0);
-        umma_commit(bar_s);
-      };
-      mbar_arrive_expect_tx(bar_tile, 2 * ATOM);
-      if (!DKDV) {
-        tma_load_2d(&tmQKV128, bar_tile, sA0, h * 64, row0 + tile * 128);           // Q tile
-        tma_load_2d(&tmDO128, bar_tile, sA1, h * 64, row0 + tile * 128);            // dO tile
-      } else {
-        tma_load_2d(&tmQKV128, bar_tile, sA0, d + h * 64, row0 + tile * 128);       // K tile
-        tma_load_2d(&tmQKV128, bar_tile, sA1, 2 * d + h * 64, row0 + tile * 128);   // V tile
-      }
-      for (int c = 0; c < RING && c < nc; ++c) load_chunk(c);
-      mbar_wait(bar_tile, 0);
-      mbar_wait(&bar_ld[0], 0);
-      tc_fence_after();
-      ATRACE(DKDV, tile, 1, 0);
-      issue_scores(0);
-      ATRACE(DKDV, tile, 1, 1);
-      for (int c = 0; c < nc; ++c) {
-        const int wc = min(64, S_pad - c * 64);
-        if (c >= 1) {  // ring stage (c-1) % RING was last read by the accumulate-MMAs of chunk c-1
-          mbar_wait(bar_acc, (c - 1) & 1);
-          if (c + RING - 1 < nc) load_chunk(c + RING - 1);
-        }
-        if (c + 1 < nc) {  // S/dP TMEM columns are free as soon as every worker has read chunk c
-          mbar_wait(bar_rd, c & 1);
-          mbar_wait(&bar_ld[(c + 1) % RING], ((c + 1) / RING) & 1);
-          tc_fence_after();
-          ATRACE(DKDV, tile, 1, 8 + c * 4 + 0);
-          issue_scores(c + 1);  // runs under the workers' exp / FMA work on chunk c
-          ATRACE(DKDV, tile, 1, 8 + c * 4 + 1);
-        }
-        mbar_wait(bar_st, c & 1);  // dS_c (and P^T_c) are in shared memory
-        tc_fence_after();
-        ATRACE(DKDV, tile, 1, 8 + c * 4 + 2);
-        const uint32_t id = idesc_rt(64, false, true);
-        const uint32_t ub = uRing + (c % RING) * 2 * CH;
-        const int ks = wc >> 4;
-        if (!DKDV) {   // dQ += dS_c K_c
-          for (int k = 0; k < ks; ++k)
-            umma_bf16(tmem + 128, desc_k(uDS + k * 32), desc_mn(ub + k * 2048), id, (c > 0 || k > 0));
-        } else {       // dV += P^T_c dO_c ; dK += dS^T_c Q_c
-          for (int k = 0; k < ks; ++k)
-            umma_bf16(tmem + 128, desc_k(uPT + k * 32), desc_mn(ub + CH + k * 2048), id, (c > 0 || k > 0));
-          for (int k = 0; k < ks; ++k)
-            umma_bf16(tmem + 192, desc_k(uDS + k * 32), desc_mn(ub + k * 2048), id, (c > 0 || k > 0));
-        }
-        umma_commit(bar_acc);
-        ATRACE(DKDV, tile, 1, 8 + c * 4 + 3);
-        if (c == nc - 1) umma_commit(bar_done);
-      }
-    }
-  } else {
-    // ======================= 4*NG worker warps =======================
-    const int q4 = warp & 3, grp = warp >> 2;
-    const int r = q4 * 32 + lane;
-    const int ri = tile * 128 + r;  // global index of this thread's row (query for DQ, key for DKDV)
-    const uint32_t trow = tmem + ((uint32_t)(q4 * 32) << 16);
-
-    // softmax statistics: per row (DQ; also published for the DKDV kernel) or per column via smem (DKDV)
-    float Lrow = 0.f, Drow = 0.f;
-    if (!DKDV) {
-      // each column group sums its 64/NG head dims of dO * O; the partials meet in shared memory
-      float acc = 0.f;
-      if (ri < S) {
-        const uint4* po = reinterpret_cast<const uint4*>(p.o_in + (long long)(row0 + ri) * d + h * 64) + grp * (8 / NG);
-        const uint4* pd = reinterpret_cast<const uint4*>(p.dout + (long long)(row0 + ri) * d + h * 64) + grp * (8 / NG);
-#pragma unroll
-        for (int j = 0; j < 8 / NG; ++j) {
-          const uint4 a = __ldg(po + j), c = __ldg(pd + j);
-          acc += bf16_lo(a.x) * bf16_lo(c.x) + bf16_hi(a.x) * bf16_hi(c.x) + bf16_lo(a.y) * bf16_lo(c.y) +
-                 bf16_hi(a.y) * bf16_hi(c.y) + bf16_lo(a.z) * bf16_lo(c.z) + bf16_hi(a.z) * bf16_hi(c.z) +
-                 bf16_lo(a.w) * bf16_lo(c.w) + bf16_hi(a.w) * bf16_hi(c.w);
-        }
-        Lrow = p.lse[((long long)b * p.H + h) * S + ri] * 1.4426950408889634f;
-      }
-      sL[grp * 128 + r] = acc;   // sL/sD: 512 floats
-      asm volatile("bar.sync 1, %0;" ::"n"(NG * 128) : "memory");
-#pragma unroll
-      for (int gI = 0; gI < NG; ++gI) Drow += sL[gI * 128 + r];
-      if (grp == 0 && ri < S) p.dsum[((long long)b * p.H + h) * S + ri] = Drow;
-    } else {
-      const int qi = threadIdx.x;  // the first 256 worker threads cover S_pad <= 256 query columns
-      if (qi < 256) {
-        const bool ok = qi < S;
-        sL[qi] = ok ? p.lse[((long long)b * p.H + h) * S + qi] * 1.4426950408889634f : 0.f;
-        sD[qi] = ok ? p.dsum[((long long)b * p.H + h) * S + qi] : 0.f;
-      }
-      asm volatile("bar.sync 1, %0;" ::"n"(NG * 128) : "memory");
-    }
-
-    if (threadIdx.x == 0) ATRACE(DKDV, tile, 0, 2);
-    for (int c = 0; c < nc; ++c) {
-      const int wc = min(64, S_pad - c * 64);
-      mbar_wait(bar_s, c & 1);
-      tc_fence_after();
-      if (threadIdx.x == 0) ATRACE(DKDV, tile, 0, 8 + c * 4 + 0);
-      // this thread: row r, columns [grp*CW, grp*CW+CW) of the chunk
-      uint32_t sv[CW], dv[CW];
-      if (CW == 32) {
-        tmem_ld32(trow + grp * 32, reinterpret_cast<uint32_t(&)[32]>(sv));
-        tmem_ld32(trow + 64 + grp * 32, reinterpret_cast<uint32_t(&)[32]>(dv));
-      } else {
-        tmem_ld16(trow + grp * 16, reinterpret_cast<uint32_t(&)[16]>(sv));
-        tmem_ld16(trow + 64 + grp * 16, reinterpret_cast<uint32_t(&)[16]>(dv));
-      }
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_rd);       // TMEM S/dP of this chunk consumed -> next chunk's MMAs may overwrite
-      if (threadIdx.x == 0) ATRACE(DKDV, tile, 0, 8 + c * 4 + 1);
-      if (c >= 1) mbar_wait(bar_acc, (c - 1) & 1);  // dS / P^T buffers free (normally long since complete)
-      if (threadIdx.x == 0) ATRACE(DKDV, tile, 0, 8 + c * 4 + 2);
-      {
-        const int cbase = c * 64 + grp * CW;  // first global column (key for DQ, query for DKDV) of this thread's CW
-        // interior fast path: the whole CW-column strip is unmasked for this row (all but the last chunk / the causal
-        // diagonal / padding rows) -> no per-element predicates or index arithmetic
-        const bool full = (ri < S) && (cbase + CW <= S) && (!CAUSAL || (DKDV ? (ri <= cbase) : (cbase + CW - 1 <= ri)));
-        const float nD = -Drow * p.scale;
-#pragma unroll
-        for (int half = 0; half < CW / 16; ++half) {
-          float ds[16], pt[16];
-          if (ri >= S) {  // padding row of the last tile: contributes nothing
-#pragma unroll
-            for (int e = 0; e < 16; ++e) { ds[e] = 0.f; pt[e] = 0.f; }
-          } else if (full) {
-            if (!DKDV) {
-#pragma unroll
-              for (int e = 0; e < 16; ++e) {
-                const float pv = ex2_approx(fmaf(__uint_as_float(sv[half * 16 + e]), p.scale_log2, -Lrow));
-                ds[e] = pv * fmaf(__uint_as_float(dv[half * 16 + e]), p.scale, nD);
-              }
-            } else {
-              const float4* pl = reinterpret_cast<const float4*>(sL + cbase + half * 16);
-              const float4* pd = reinterpret_cast<const float4*>(sD + cbase + half * 16);
-#pragma unroll
-              for (int e4 = 0; e4 < 4; ++e4) {
-                const float4 l4 = pl[e4], d4 = pd[e4];
-                const float ls[4] = {l4.x, l4.y, l4.z, l4.w}, dd[4] = {d4.x, d4.y, d4.z, d4.w};
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                  const int e = e4 * 4 + k;
-                  const float pv = ex2_approx(fmaf(__uint_as_float(sv[half * 16 + e]), p.scale_log2, -ls[k]));
-                  pt[e] = pv;
-                  ds[e] = pv * (__uint_as_float(dv[half * 16 + e]) - dd[k]) * p.scale;
-                }
-              }
-            }
-          } else {
-#pragma unroll
-            for (int e = 0; e < 16; ++e) {
-              const int cj = cbase + half * 16 + e;
-              bool valid;
-              float L, Dv;
-              if (!DKDV) {
-                valid = (ri < S) && (cj < S) && (!CAUSAL || cj <= ri);
-                L = Lrow; Dv = Drow;
-              } else {
-                valid = (ri < S) && (cj < S) && (!CAUSAL || ri <= cj);
-                L = sL[cj & 255]; Dv = sD[cj & 255];
-              }
-              const float pv = valid ? ex2_approx(__uint_as_float(sv[half * 16 + e]) * p.scale_log2 - L) : 0.f;
-              pt[e] = pv;
-              ds[e] = pv * (__uint_as_float(dv[half * 16 + e]) - Dv) * p.scale;
-            }
-          }
-          if (grp * CW + half * 16 < wc) {
-            store_p16(sDS, r, grp * CW + half * 16, ds);
-            if (DKDV) store_p16(sPT, r, grp * CW + half * 16, pt);
-          }
-        }
-      }
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_st);
-      if (threadIdx.x == 0) ATRACE(DKDV, tile, 0, 8 + c * 4 + 3);
-    }
-    mbar_wait(bar_done, 0);
-    tc_fence_after();
-    if (threadIdx.x == 0) ATRACE(DKDV, tile, 0, 3);
-    const long long ld = 3LL * d;
-#pragma unroll
-    for (int which = 0; which < (DKDV ? 2 : 1); ++which) {
-      // DQ: acc0 -> Q block.  DKDV: acc0 = dV -> V block (2d), acc1 = dK -> K block (d)
-      uint32_t v[CW];
-      if (CW == 32) tmem_ld32(trow + 128 + which * 64 + grp * 32, reinterpret_cast<uint32_t(&)[32]>(v));
-      else          tmem_ld16(trow + 128 + which * 64 + grp * 16, reinterpret_cast<uint32_t(&)[16]>(v));
-      tmem_ld_wait();
-      if (ri < S) {
-        const int coff = !DKDV ? 0 : (which == 0 ? 2 * d : d);
-        __nv_bfloat16* dst = p.dqkv + (long long)(row0 + ri) * ld + coff + h * 64 + grp * CW;
-#pragma unroll
-        for (int j = 0; j < CW / 8; ++j) {
-          uint4 o;
-          o.x = pack_bf16x2(__uint_as_float(v[j * 8 + 0]), __uint_as_float(v[j * 8 + 1]));
-          o.y = pack_bf16x2(__uint_as_float(v[j * 8 + 2]), __uint_as_float(v[j * 8 + 3]));
-          o.z = pack_bf16x2(__uint_as_float(v[j * 8 + 4]), __uint_as_float(v[j * 8 + 5]));
-          o.w = pack_bf16x2(__uint_as_float(v[j * 8 + 6]), __uint_as_float(v[j * 8 + 7]));
-          reinterpret_cast<uint4*>(dst)[j] = o;
-        }
-      }
-    }
-  }
-  if (threadIdx.x == 0) ATRACE(DKDV, tile, 0, 4);
-  tc_fence_before();
-  __syncthreads();
-  if (warp == NW) {
-    tc_fence_after();
-    tmem_dealloc(tmem, 256);
-  }
-  if (threadIdx.x == 0) ATRACE(DKDV, tile, 0, 5);
-}
-
 
 // ------------------------------------------------------------------------------------------------
 // Backward, persistent version (round-1 final): ONE CTA per SM loops over (batch, head, 128-row tile) work items with
@@ -906,12 +618,382 @@ attn_bwd_persist_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gr
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Backward, persistent PING-PONG version (round 2; default).  Same producer / two issuers / statistics warps as
+// attn_bwd_persist_kernel, but the eight worker warps form TWO GROUPS that serve ALTERNATE chunks (group = parity of
+// the running chunk counter) instead of splitting every chunk's columns.  In the column-split kernel all workers hit
+// the same fixed latencies at the same time (mbarrier check ~90-250 clk, tcgen05.ld ~250, buffer check ~220,
+// fence.proxy.async + arrive ~240: ~960 of the ~1900 clocks of a chunk, profiles/r1_attn_bwd_phase_trace.txt) and the
+// SM idles; here each sub-partition holds one warp of each group, so one group's waits run under the other's
+// exp / FMA / pack work.  A thread owns one tile row and all 64 columns of its chunk (two 32-column halves).
+// The epilogue of tile n (TMEM accumulators -> bf16 -> dqkv) is deferred until after the group's first chunk of tile
+// n+1, so a group never waits for the other group's last chunk.  Sequence lengths up to SMAX = 384 (3 row tiles, 6
+// chunks): CLIP ViT-L/14 with CLS (257) and the FLAVA multimodal encoder (275) run here too.
+// ------------------------------------------------------------------------------------------------
+constexpr int SMAX = 384;
+constexpr int PP_STATS = 1;   // one statistics warp (12 warps per CTA: register allocation is per 4 warps)
+template <bool CAUSAL, bool DKDV>
+__global__ void __launch_bounds__((8 + 3 + PP_STATS) * 32, 1)   // 12 warps -> 168 registers per thread available
+attn_bwd_pp_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_constant__ CUtensorMap tmQKV64,
+                   const __grid_constant__ CUtensorMap tmDO128, const __grid_constant__ CUtensorMap tmDO64,
+                   const AttnTcArgs p, const int n_work) {
+  constexpr int RING = DKDV ? 3 : 4;
+  constexpr int CH = 8192;  // one 64-row x 128 B chunk operand
+  constexpr int P_WORKERS = 8;
+  constexpr int SLD = 2 * SMAX;  // floats per statistics buffer: lse(log2) [SMAX] | rowsum(dO*O) [SMAX]
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sA = smem;                                   // [2 tile buffers][A0 16 KB | A1 16 KB]
+  uint8_t* sRing = sA + 4 * ATOM;                       // RING x (B0_c 8 KB | B1_c 8 KB)
+  uint8_t* sDS = sRing + RING * 2 * CH;                 // [2] dS chunk (16 KB each)
+  uint8_t* sPT = sDS + 2 * ATOM;                        // [2] P^T chunk (DKDV only)
+  float* sLD = reinterpret_cast<float*>(sPT + (DKDV ? 2 : 0) * ATOM);  // [2][SLD]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sLD + 2 * SLD);
+  uint64_t* tile_full = bars;            // [2]  tile operands landed                 producer(TMA) -> score issuer
+  uint64_t* tile_empty = bars + 2;       // [2]  last score MMA of the tile complete  score issuer  -> producer
+  uint64_t* ring_full = bars + 4;        // [RING]
+  uint64_t* ring_empty = bars + 8;       // [RING] accumulate MMAs of the chunk complete            -> producer
+  uint64_t* sdp_full = bars + 12;        // [2]  S_c/dP_c in TMEM                     score issuer  -> worker group
+  uint64_t* sdp_empty = bars + 14;       // [2]  the group has read them (4 warps)                  -> score issuer
+  uint64_t* ds_full = bars + 16;         // [2]  dS_c (P^T_c) in smem (4 warps)       worker group  -> acc issuer
+  uint64_t* ds_empty = bars + 18;        // [2]  accumulate MMAs done with them       acc issuer    -> worker group
+  uint64_t* acc_full = bars + 20;        // [2]  accumulators of the tile final       acc issuer    -> workers
+  uint64_t* acc_empty = bars + 22;       // [2]  workers have read them (8 warps)                   -> acc issuer
+  uint64_t* stat_full = bars + 24;       // [2]  LSE / D of the tile in sLD (2 warps) stats warps   -> workers
+  uint64_t* stat_empty = bars + 26;      // [2]  workers are done with them (8 warps)               -> stats warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 28);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int S = p.S, S_pad = p.S_pad, d = p.H * 64;
+  const int nc = (S_pad + 63) >> 6;
+  const int ntile = (S + 127) >> 7;
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmQKV128); tma_prefetch_desc(&tmQKV64);
+    tma_prefetch_desc(&tmDO128); tma_prefetch_desc(&tmDO64);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tile_full[i], 1); mbar_init(&tile_empty[i], 1);
+      mbar_init(&sdp_full[i], 1); mbar_init(&sdp_empty[i], P_WORKERS / 2);
+      mbar_init(&ds_full[i], P_WORKERS / 2); mbar_init(&ds_empty[i], 1);
+      mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], P_WORKERS);
+      mbar_init(&stat_full[i], PP_STATS); mbar_init(&stat_empty[i], P_WORKERS);
+    }
+    for (int i = 0; i < RING; ++i) { mbar_init(&ring_full[i], 1); mbar_init(&ring_empty[i], 1); }
+    fence_mbar_init();
+  }
+  if (warp == P_WORKERS) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == P_WORKERS) {
+    // ======================= TMA producer =======================
+    if (lane == 0) {
+      int n = 0;
+      long long g = 0;
+      for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++n) {
+        const int tile = w % ntile, bh = w / ntile;
+        const int h = bh % p.H, b = bh / p.H;
+        const int row0 = b * S;
+        const int tb = n & 1;
+        mbar_wait(&tile_empty[tb], ((n >> 1) & 1) ^ 1);
+        uint8_t* a0 = sA + tb * 2 * ATOM;
+        mbar_arrive_expect_tx(&tile_full[tb], 2 * ATOM);
+        if (!DKDV) {
+          tma_load_2d(&tmQKV128, &tile_full[tb], a0, h * 64, row0 + tile * 128);               // Q tile
+          tma_load_2d(&tmDO128, &tile_full[tb], a0 + ATOM, h * 64, row0 + tile * 128);          // dO tile
+        } else {
+          tma_load_2d(&tmQKV128, &tile_full[tb], a0, d + h * 64, row0 + tile * 128);           // K tile
+          tma_load_2d(&tmQKV128, &tile_full[tb], a0 + ATOM, 2 * d + h * 64, row0 + tile * 128); // V tile
+        }
+        for (int c = 0; c < nc; ++c, ++g) {
+          const int st = (int)(g % RING);
+          mbar_wait(&ring_empty[st], (uint32_t)(((g / RING) & 1) ^ 1));
+          uint8_t* dst = sRing + st * 2 * CH;
+          mbar_arrive_expect_tx(&ring_full[st], 2 * CH);
+          if (!DKDV) {
+            tma_load_2d(&tmQKV64, &ring_full[st], dst, d + h * 64, row0 + c * 64);           // K_c
+            tma_load_2d(&tmQKV64, &ring_full[st], dst + CH, 2 * d + h * 64, row0 + c * 64);   // V_c
+          } else {
+            tma_load_2d(&tmQKV64, &ring_full[st], dst, h * 64, row0 + c * 64);                // Q_c
+            tma_load_2d(&tmDO64, &ring_full[st], dst + CH, h * 64, row0 + c * 64);             // dO_c
+          }
+        }
+      }
+    }
+  } else if (warp == P_WORKERS + 1) {
+    // ======================= score issuer: S_c = A0 B0_c^T, dP_c = A1 B1_c^T =======================
+    if (lane == 0) {
+      const uint32_t uA = smem_u32(sA), uRing = smem_u32(sRing);
+      int n = 0;
+      long long g = 0;
+      for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++n) {
+        const int tb = n & 1;
+        mbar_wait(&tile_full[tb], (n >> 1) & 1);
+        const uint64_t a0 = desc_k(uA + tb * 2 * ATOM), a1 = desc_k(uA + tb * 2 * ATOM + ATOM);
+        for (int c = 0; c < nc; ++c, ++g) {
+          const int st = (int)(g % RING), sb = (int)(g & 1);
+          const int wc = min(64, S_pad - c * 64);
+          mbar_wait(&ring_full[st], (uint32_t)((g / RING) & 1));
+          mbar_wait(&sdp_empty[sb], (uint32_t)(((g >> 1) & 1) ^ 1));
+          tc_fence_after();
+          const uint32_t id = idesc_rt(wc, false, false);
+          const uint32_t ub = uRing + st * 2 * CH;
+          const uint64_t b0 = desc_k(ub), b1 = desc_k(ub + CH);
+          const uint32_t tS = tmem + sb * 128;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16(tS, a0 + 2 * k, b0 + 2 * k, id, k > 0);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16(tS + 64, a1 + 2 * k, b1 + 2 * k, id, k > 0);
+          umma_commit(&sdp_full[sb]);
+        }
+        umma_commit(&tile_empty[tb]);   // every MMA that reads this tile buffer has been issued before this commit
+      }
+    }
+  } else if (warp == P_WORKERS + 2) {
+    // ======================= accumulate issuer: dQ += dS_c K_c  |  dV += P^T_c dO_c ; dK += dS^T_c Q_c ==============
+    if (lane == 0) {
+      const uint32_t uRing = smem_u32(sRing), uDS = smem_u32(sDS), uPT = smem_u32(sPT);
+      const uint32_t id = idesc_rt(64, false, true);
+      int n = 0;
+      long long g = 0;
+      for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++n) {
+        const int ab = n & 1;
+        mbar_wait(&acc_empty[ab], ((n >> 1) & 1) ^ 1);
+        const uint32_t tA = tmem + 256 + ab * 128;
+        for (int c = 0; c < nc; ++c, ++g) {
+          const int st = (int)(g % RING), sb = (int)(g & 1);
+          const int wc = min(64, S_pad - c * 64);
+          mbar_wait(&ds_full[sb], (uint32_t)((g >> 1) & 1));
+          mbar_wait(&ring_full[st], (uint32_t)((g / RING) & 1));  // long complete; acquires the TMA writes for this thread
+          tc_fence_after();
+          const uint32_t ub = uRing + st * 2 * CH;
+          const int ks = wc >> 4;
+          if (!DKDV) {
+            for (int k = 0; k < ks; ++k)
+              umma_bf16(tA, desc_k(uDS + sb * ATOM + k * 32), desc_mn(ub + k * 2048), id, (c > 0 || k > 0));
+          } else {
+            for (int k = 0; k < ks; ++k)
+              umma_bf16(tA, desc_k(uPT + sb * ATOM + k * 32), desc_mn(ub + CH + k * 2048), id, (c > 0 || k > 0));
+            for (int k = 0; k < ks; ++k)
+              umma_bf16(tA + 64, desc_k(uDS + sb * ATOM + k * 32), desc_mn(ub + k * 2048), id, (c > 0 || k > 0));
+          }
+          umma_commit(&ds_empty[sb]);
+          umma_commit(&ring_empty[st]);
+          if (c == nc - 1) umma_commit(&acc_full[ab]);
+        }
+      }
+    }
+  } else if (warp >= P_WORKERS + 3) {
+    // ======================= statistics warps: sLD[n & 1] = {LSE (log2 units) [SMAX], D [SMAX]} of tile n ==========
+    const int t = (warp - (P_WORKERS + 3)) * 32 + lane;   // 0 .. 32*PP_STATS-1
+    int n = 0;
+    for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++n) {
+      const int tile = w % ntile, bh = w / ntile;
+      const int h = bh % p.H, b = bh / p.H;
+      const int row0 = b * S;
+      float* wL = sLD + (n & 1) * SLD;
+      const long long sbase = ((long long)b * p.H + h) * S;
+      mbar_wait(&stat_empty[n & 1], ((n >> 1) & 1) ^ 1);
+      if (!DKDV) {
+#pragma unroll
+        for (int k = 0; k < 128 / (PP_STATS * 32); ++k) {
+          const int rr = t + k * (PP_STATS * 32);
+          const int ri = tile * 128 + rr;
+          float acc = 0.f, L = 0.f;
+          if (ri < S) {
+            const uint4* po = reinterpret_cast<const uint4*>(p.o_in + (long long)(row0 + ri) * d + h * 64);
+            const uint4* pd = reinterpret_cast<const uint4*>(p.dout + (long long)(row0 + ri) * d + h * 64);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const uint4 a = __ldg(po + j), c = __ldg(pd + j);
+              acc += bf16_lo(a.x) * bf16_lo(c.x) + bf16_hi(a.x) * bf16_hi(c.x) + bf16_lo(a.y) * bf16_lo(c.y) +
+                     bf16_hi(a.y) * bf16_hi(c.y) + bf16_lo(a.z) * bf16_lo(c.z) + bf16_hi(a.z) * bf16_hi(c.z) +
+                     bf16_lo(a.w) * bf16_lo(c.w) + bf16_hi(a.w) * bf16_hi(c.w);
+            }
+            L = p.lse[sbase + ri] * 1.4426950408889634f;
+            p.dsum[sbase + ri] = acc;
+          }
+          wL[rr] = L;
+          wL[SMAX + rr] = acc;
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < SMAX / (PP_STATS * 32); ++k) {
+          const int qi = t + k * (PP_STATS * 32);
+          const bool ok = qi < S;
+          wL[qi] = ok ? p.lse[sbase + qi] * 1.4426950408889634f : 0.f;
+          wL[SMAX + qi] = ok ? p.dsum[sbase + qi] : 0.f;
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&stat_full[n & 1]);   // release: the smem writes above are visible to the waiters
+    }
+  } else {
+    // ======================= 8 worker warps: group = chunk parity, thread == tile row =======================
+    const int q4 = warp & 3, grp = warp >> 2;
+    const int r = q4 * 32 + lane;
+    const uint32_t trow = tmem + ((uint32_t)(q4 * 32) << 16);
+    const long long ld = 3LL * d;
+    // deferred tile epilogue: accumulators (TMEM buffer pn & 1) -> bf16 -> dqkv; this group converts columns
+    // [grp*32, grp*32+32) of every accumulator
+    int pn = -1, p_row0 = 0, p_ri = 0, p_h = 0;
+    auto tile_epilogue = [&]() {
+      const int ab = pn & 1;
+      mbar_wait(&acc_full[ab], (pn >> 1) & 1);
+      tc_fence_after();
+      uint32_t v0[32], v1[32];
+      tmem_ld32(trow + 256 + ab * 128 + grp * 32, v0);
+      if (DKDV) tmem_ld32(trow + 256 + ab * 128 + 64 + grp * 32, v1);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[ab]);
+      if (p_ri < S) {
+#pragma unroll
+        for (int which = 0; which < (DKDV ? 2 : 1); ++which) {
+          // DQ: acc0 -> Q block.  DKDV: acc0 = dV -> V block (2d), acc1 = dK -> K block (d)
+          const uint32_t* v = which == 0 ? v0 : v1;
+          const int coff = !DKDV ? 0 : (which == 0 ? 2 * d : d);
+          __nv_bfloat16* dst = p.dqkv + (long long)(p_row0 + p_ri) * ld + coff + p_h * 64 + grp * 32;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 o;
+            o.x = pack_bf16x2(__uint_as_float(v[j * 8 + 0]), __uint_as_float(v[j * 8 + 1]));
+            o.y = pack_bf16x2(__uint_as_float(v[j * 8 + 2]), __uint_as_float(v[j * 8 + 3]));
+            o.z = pack_bf16x2(__uint_as_float(v[j * 8 + 4]), __uint_as_float(v[j * 8 + 5]));
+            o.w = pack_bf16x2(__uint_as_float(v[j * 8 + 6]), __uint_as_float(v[j * 8 + 7]));
+            reinterpret_cast<uint4*>(dst)[j] = o;
+          }
+        }
+      }
+      pn = -1;
+    };
+    int n = 0;
+    long long g = 0;
+    for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++n) {
+      const int tile = w % ntile, bh = w / ntile;
+      const int h = bh % p.H, b = bh / p.H;
+      const int row0 = b * S;
+      const int ri = tile * 128 + r;  // global index of this thread's row (query for DQ, key for DKDV)
+      float Lrow = 0.f, Drow = 0.f;
+      const float* sL = sLD + (n & 1) * SLD;
+      const float* sD = sL + SMAX;
+      mbar_wait(&stat_full[n & 1], (n >> 1) & 1);
+      if (!DKDV) {
+        Lrow = sL[r];
+        Drow = sD[r];
+      }
+      const float nD = -Drow * p.scale;
+      for (int c = 0; c < nc; ++c) {
+        const long long gc = g + c;
+        if ((int)(gc & 1) != grp) continue;
+        const int sb = grp;
+        const uint32_t par = (uint32_t)((gc >> 1) & 1);
+        const int wc = min(64, S_pad - c * 64);
+        mbar_wait(&sdp_full[sb], par);
+        tc_fence_after();
+        uint8_t* myDS = sDS + sb * ATOM;
+        uint8_t* myPT = sPT + sb * ATOM;
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          uint32_t sv[32], dv[32];
+          tmem_ld32(trow + sb * 128 + hf * 32, sv);
+          tmem_ld32(trow + sb * 128 + 64 + hf * 32, dv);
+          tmem_ld_wait();
+          if (hf == 1) {   // S_c / dP_c of this chunk are in registers -> the score issuer may overwrite the buffer
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sdp_empty[sb]);
+          } else {
+            mbar_wait(&ds_empty[sb], par ^ 1);   // accumulate MMAs of chunk gc-2 have left the dS / P^T buffers
+          }
+          const int cbase = c * 64 + hf * 32;   // first global column (key for DQ, query for DKDV) of this half
+          // interior fast path: the whole 32-column strip is unmasked for this row
+          const bool full = (ri < S) && (cbase + 32 <= S) && (!CAUSAL || (DKDV ? (ri <= cbase) : (cbase + 31 <= ri)));
+#pragma unroll
+          for (int qt = 0; qt < 2; ++qt) {
+            float ds[16], pt[16];
+            if (ri >= S) {
+#pragma unroll
+              for (int e = 0; e < 16; ++e) { ds[e] = 0.f; pt[e] = 0.f; }
+            } else if (full) {
+              if (!DKDV) {
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                  const float pv = ex2_approx(fmaf(__uint_as_float(sv[qt * 16 + e]), p.scale_log2, -Lrow));
+                  ds[e] = pv * fmaf(__uint_as_float(dv[qt * 16 + e]), p.scale, nD);
+                }
+              } else {
+                const float4* pl = reinterpret_cast<const float4*>(sL + cbase + qt * 16);
+                const float4* pd = reinterpret_cast<const float4*>(sD + cbase + qt * 16);
+#pragma unroll
+                for (int e4 = 0; e4 < 4; ++e4) {
+                  const float4 l4 = pl[e4], d4 = pd[e4];
+                  const float ls[4] = {l4.x, l4.y, l4.z, l4.w}, dd[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) {
+                    const int e = e4 * 4 + k;
+                    const float pv = ex2_approx(fmaf(__uint_as_float(sv[qt * 16 + e]), p.scale_log2, -ls[k]));
+                    pt[e] = pv;
+                    ds[e] = pv * (__uint_as_float(dv[qt * 16 + e]) - dd[k]) * p.scale;
+                  }
+                }
+              }
+            } else {
+#pragma unroll
+              for (int e = 0; e < 16; ++e) {
+                const int cj = cbase + qt * 16 + e;
+                bool valid;
+                float L, Dv;
+                if (!DKDV) {
+                  valid = (cj < S) && (!CAUSAL || cj <= ri);
+                  L = Lrow; Dv = Drow;
+                } else {
+                  valid = (cj < S) && (!CAUSAL || ri <= cj);
+                  const int cq = min(cj, SMAX - 1);
+                  L = sL[cq]; Dv = sD[cq];
+                }
+                const float pv = valid ? ex2_approx(__uint_as_float(sv[qt * 16 + e]) * p.scale_log2 - L) : 0.f;
+                pt[e] = pv;
+                ds[e] = pv * (__uint_as_float(dv[qt * 16 + e]) - Dv) * p.scale;
+              }
+            }
+            if (hf * 32 + qt * 16 < wc) {
+              store_p16(myDS, r, hf * 32 + qt * 16, ds);
+              if (DKDV) store_p16(myPT, r, hf * 32 + qt * 16, pt);
+            }
+          }
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ds_full[sb]);
+        if (pn >= 0) tile_epilogue();   // previous tile's accumulators: long final by now
+      }
+      g += nc;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&stat_empty[n & 1]);   // this warp no longer reads sLD[n & 1]
+      if (pn >= 0) tile_epilogue();                      // (this group served no chunk of tile n)
+      pn = n; p_row0 = row0; p_ri = ri; p_h = h;
+    }
+    if (pn >= 0) tile_epilogue();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == P_WORKERS) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+constexpr int BWDPP_DQ_SMEM = 1024 + 4 * ATOM + 4 * 16384 + 2 * ATOM + 2 * 2 * SMAX * 4 + 512;     // 171.5 KB
+constexpr int BWDPP_DKDV_SMEM = 1024 + 4 * ATOM + 3 * 16384 + 4 * ATOM + 2 * 2 * SMAX * 4 + 512;   // 187.5 KB
+
 constexpr int BWDP_DQ_SMEM = 1024 + 4 * ATOM + 4 * 16384 + 2 * ATOM + 4096 + 512;              // 169.5 KB
 constexpr int BWDP_DKDV_SMEM = 1024 + 4 * ATOM + 3 * 16384 + 4 * ATOM + 4096 + 512;            // 185.5 KB
 
-constexpr int FWD_SMEM = 1024 + 6 * ATOM + 2048 + 256 + 64;
-constexpr int BWD_DQ_SMEM = 1024 + 2 * ATOM + 3 * 16384 + ATOM + 2048 + 128;        //  99.3 KB -> 2 CTAs / SM
-constexpr int BWD_DKDV_SMEM = 1024 + 2 * ATOM + 2 * 16384 + 2 * ATOM + 2048 + 128;  //  99.3 KB -> 2 CTAs / SM
+constexpr int FWD_SMEM = 1024 + 6 * ATOM + 2048 + 384 + 64;
+constexpr int FWD_SMEM_BIG = 1024 + 9 * ATOM + 2048 + 384 + 64;
 
 }  // namespace mmb
 
@@ -927,24 +1009,31 @@ extern "C" int mmb_attention_fwd_kmask(const void* qkv, void* out, float* lse, c
                                        int H, int head_dim, int causal, float scale, void* stream);
 static int attention_fwd_tc_impl(const void* qkv, void* out, float* lse, const uint8_t* kmask, int B, int S, int H,
                                  int causal, float scale, void* stream) {
-  if (B <= 0 || S <= 0 || S > 256) return MMB_ERR_UNSUPPORTED;
+  if (B <= 0 || S <= 0 || S > SMAX) return MMB_ERR_UNSUPPORTED;
   const int d = H * 64, S_pad = (S + 15) & ~15;
-  CUtensorMap tm128, tmPad;
+  const bool big = S_pad > 256;
+  CUtensorMap tm128, tmPad, tmRem;
   int rc = make_tmap_2d(&tm128, qkv, 2, false, 3ull * d, (uint64_t)B * S, 3ull * d * 2, 64, 128);
   if (rc) return rc;
-  rc = make_tmap_2d(&tmPad, qkv, 2, false, 3ull * d, (uint64_t)B * S, 3ull * d * 2, 64, S_pad);
+  rc = make_tmap_2d(&tmPad, qkv, 2, false, 3ull * d, (uint64_t)B * S, 3ull * d * 2, 64, big ? 256 : S_pad);
   if (rc) return rc;
+  tmRem = tmPad;
+  if (big) {
+    rc = make_tmap_2d(&tmRem, qkv, 2, false, 3ull * d, (uint64_t)B * S, 3ull * d * 2, 64, S_pad - 256);
+    if (rc) return rc;
+  }
+  const int smem_bytes = big ? FWD_SMEM_BIG : FWD_SMEM;
   AttnTcArgs a{};
   a.S = S; a.H = H; a.S_pad = S_pad; a.scale = scale; a.scale_log2 = scale * 1.4426950408889634f;
   a.lse = lse; a.out = (__nv_bfloat16*)out; a.kmask = kmask;
   dim3 grid((S + 127) / 128, H, B);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (causal) {
-    cudaFuncSetAttribute(attn_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM);
-    attn_fwd_tc_kernel<true><<<grid, ATT_THREADS, FWD_SMEM, st>>>(tm128, tmPad, a);
+    cudaFuncSetAttribute(attn_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM_BIG);
+    attn_fwd_tc_kernel<true><<<grid, ATT_THREADS, smem_bytes, st>>>(tm128, tmPad, tmRem, a);
   } else {
-    cudaFuncSetAttribute(attn_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM);
-    attn_fwd_tc_kernel<false><<<grid, ATT_THREADS, FWD_SMEM, st>>>(tm128, tmPad, a);
+    cudaFuncSetAttribute(attn_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM_BIG);
+    attn_fwd_tc_kernel<false><<<grid, ATT_THREADS, smem_bytes, st>>>(tm128, tmPad, tmRem, a);
   }
   return (int)cudaGetLastError();
 }
@@ -957,13 +1046,13 @@ extern "C" int mmb_attention_fwd_tc(const void* qkv, void* out, float* lse, int 
 // (modules/encoders/bert_text_encoder.py:87-93 -> modules/layers/attention.py:228-229 masked_fill(-inf)).
 extern "C" int mmb_attention_fwd_kmask(const void* qkv, void* out, float* lse, const unsigned char* kmask, int B, int S,
                                        int H, int head_dim, int causal, float scale, void* stream) {
-  if (head_dim != 64 || S > 256) return MMB_ERR_UNSUPPORTED;
+  if (head_dim != 64) return MMB_ERR_UNSUPPORTED;
   return attention_fwd_tc_impl(qkv, out, lse, kmask, B, S, H, causal, scale, stream);
 }
 
 extern "C" int mmb_attention_bwd_tc(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
                                     int B, int S, int H, int causal, float scale, void* stream) {
-  if (B <= 0 || S <= 0 || S > 256) return MMB_ERR_UNSUPPORTED;
+  if (B <= 0 || S <= 0 || S > SMAX) return MMB_ERR_UNSUPPORTED;
   const int d = H * 64, S_pad = (S + 15) & ~15;
   CUtensorMap q128, q64, o128, o64;
   int rc = make_tmap_2d(&q128, qkv, 2, false, 3ull * d, (uint64_t)B * S, 3ull * d * 2, 64, 128);
@@ -995,33 +1084,20 @@ extern "C" int mmb_attention_bwd_tc(const void* qkv, const void* out, const void
   a.S = S; a.H = H; a.S_pad = S_pad; a.scale = scale; a.scale_log2 = scale * 1.4426950408889634f;
   a.lse = const_cast<float*>(lse); a.o_in = (const __nv_bfloat16*)out; a.dout = (const __nv_bfloat16*)dout;
   a.dqkv = (__nv_bfloat16*)dqkv; a.dsum = dsum;
-  dim3 grid((S + 127) / 128, H, B);
-  static int persist_env = -1;  // MMB_ATTN_BWD_PERSIST=0 selects the two-CTA-per-SM kernels (A/B testing)
-  if (persist_env < 0) {
-    const char* e = getenv("MMB_ATTN_BWD_PERSIST");
-    persist_env = (e && e[0] == '0') ? 0 : 1;
+  const int n_work = ((S + 127) / 128) * H * B;
+  const int grid_p = n_work < num_sms() ? n_work : num_sms();
+  // MMB_ATTN_BWD=colsplit selects the round-1 column-split persistent kernel (A/B testing; S <= 256 only)
+  static int variant = -1;
+  if (variant < 0) {
+    const char* e = getenv("MMB_ATTN_BWD");
+    variant = (e && e[0] == 'c') ? 1 : 0;
   }
-  if (persist_env) {
-    const int n_work = ((S + 127) / 128) * H * B;
-    int dev_id = 0, sms = 148;
-    cudaGetDevice(&dev_id);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev_id);
-    const int grid_p = n_work < sms ? n_work : sms;
-    static int png_env = -1;  // MMB_ATTN_PNG=2|4: worker column groups of the persistent kernel (default 2)
-    if (png_env < 0) {
-      const char* e = getenv("MMB_ATTN_PNG");
-      png_env = (e && e[0] == '4') ? 4 : 2;   // 16 worker warps measured 3 % slower than 8 (TMEM-read bound)
-    }
+  if (variant == 1 && S <= 256) {
 #define LAUNCH_BWDP(C, K, SM)                                                                                     \
-  if (png_env == 2) {                                                                                             \
     cudaFuncSetAttribute(attn_bwd_persist_kernel<C, K, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM);     \
-    attn_bwd_persist_kernel<C, K, 2><<<grid_p, (8 + 3 + P_STATS) * 32, SM, st>>>(q128, q64, o128, o64, a, n_work); \
-  } else {                                                                                                        \
-    cudaFuncSetAttribute(attn_bwd_persist_kernel<C, K, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM);     \
-    attn_bwd_persist_kernel<C, K, 4><<<grid_p, (16 + 3 + P_STATS) * 32, SM, st>>>(q128, q64, o128, o64, a, n_work); \
-  }
+    attn_bwd_persist_kernel<C, K, 2><<<grid_p, (8 + 3 + P_STATS) * 32, SM, st>>>(q128, q64, o128, o64, a, n_work);
     if (causal) {
-      LAUNCH_BWDP(true, false, BWDP_DQ_SMEM)
+      LAUNCH_BWDP(true, false, BWDP_DQ_SMEM)     // dQ first: it also publishes D for the dK/dV kernel
       LAUNCH_BWDP(true, true, BWDP_DKDV_SMEM)
     } else {
       LAUNCH_BWDP(false, false, BWDP_DQ_SMEM)
@@ -1030,26 +1106,29 @@ extern "C" int mmb_attention_bwd_tc(const void* qkv, const void* out, const void
 #undef LAUNCH_BWDP
     return (int)cudaGetLastError();
   }
-  static int ng_env = -1;  // MMB_ATTN_NG=2|4: worker column groups (A/B testing; 4 measured slower); default 2
-  if (ng_env < 0) {
-    const char* e = getenv("MMB_ATTN_NG");
-    ng_env = (e && e[0] == '4') ? 4 : 2;
-  }
-#define LAUNCH_BWD(C, K, SM)                                                                                  \
-  if (ng_env == 2) {                                                                                          \
-    cudaFuncSetAttribute(attn_bwd_tc_kernel<C, K, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM);      \
-    attn_bwd_tc_kernel<C, K, 2><<<grid, 2 * 128 + 32, SM, st>>>(q128, q64, o128, o64, a);                    \
-  } else {                                                                                                    \
-    cudaFuncSetAttribute(attn_bwd_tc_kernel<C, K, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM);      \
-    attn_bwd_tc_kernel<C, K, 4><<<grid, 4 * 128 + 32, SM, st>>>(q128, q64, o128, o64, a);                    \
-  }
+#define LAUNCH_BWDPP(C, K, SM)                                                                                    \
+  cudaFuncSetAttribute(attn_bwd_pp_kernel<C, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM);               \
+  attn_bwd_pp_kernel<C, K><<<grid_p, (8 + 3 + PP_STATS) * 32, SM, st>>>(q128, q64, o128, o64, a, n_work);
   if (causal) {
-    LAUNCH_BWD(true, false, BWD_DQ_SMEM)     // dQ first: it also publishes D for the dK/dV kernel
-    LAUNCH_BWD(true, true, BWD_DKDV_SMEM)
+    LAUNCH_BWDPP(true, false, BWDPP_DQ_SMEM)     // dQ first: it also publishes D for the dK/dV kernel
+    LAUNCH_BWDPP(true, true, BWDPP_DKDV_SMEM)
   } else {
-    LAUNCH_BWD(false, false, BWD_DQ_SMEM)
-    LAUNCH_BWD(false, true, BWD_DKDV_SMEM)
+    LAUNCH_BWDPP(false, false, BWDPP_DQ_SMEM)
+    LAUNCH_BWDPP(false, true, BWDPP_DKDV_SMEM)
   }
-#undef LAUNCH_BWD
+#undef LAUNCH_BWDPP
   return (int)cudaGetLastError();
+}
+
+// Public entry points (include/mmb200.h).  Every sequence length up to SMAX = 384 runs on the tcgen05 kernels above;
+// there is no other attention path for head_dim 64 (the round-1 mma.sync kernels for 256 < S <= 320 are gone).
+extern "C" int mmb_attention_fwd(const void* qkv, void* out, float* lse, int B, int S, int H, int head_dim, int causal,
+                                 float scale, void* stream) {
+  if (head_dim != 64) return MMB_ERR_UNSUPPORTED;
+  return mmb_attention_fwd_tc(qkv, out, lse, B, S, H, causal, scale, stream);
+}
+extern "C" int mmb_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
+                                 int B, int S, int H, int head_dim, int causal, float scale, void* stream) {
+  if (head_dim != 64) return MMB_ERR_UNSUPPORTED;
+  return mmb_attention_bwd_tc(qkv, out, dout, lse, dqkv, B, S, H, causal, scale, stream);
 }

@@ -14,6 +14,7 @@
 #include "common.cuh"
 #include "mmb200_internal.h"
 #include <stdlib.h>
+#include <mutex>
 
 namespace mmb {
 
@@ -29,14 +30,16 @@ constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB per CTA
 template <bool CTA2, int EPI> struct Cfg {
   static constexpr int LOAD_N = CTA2 ? 128 : 256;
   static constexpr int B_BYTES = LOAD_N * BLOCK_K * 2;
-  // EPI_BF16_DACT gives one ring stage (32 / 48 KB) to two 16 KB slabs into which the act'(aux) operand is
-  // TMA-prefetched while the tile's MMAs are still running.
-  static constexpr int STAGES = (CTA2 ? 6 : 4) - (EPI == EPI_BF16_DACT ? 1 : 0);
+  // The activation epilogues give one ring stage (32 / 48 KB) to two more 16 KB slabs: EPI_BF16_DACT TMA-prefetches
+  // the act'(aux) operand into them while the tile's MMAs are still running; EPI_BF16_ACT alternates two
+  // (pre-activation, activation) slab pairs so that one named barrier per 64-column group suffices.
+  static constexpr int STAGES = (CTA2 ? 6 : 4) - ((EPI == EPI_BF16_DACT || EPI == EPI_BF16_ACT) ? 1 : 0);
   static constexpr int TILE_M = CTA2 ? 256 : 128;
 };
 constexpr int SLAB_BYTES = 128 * 128;           // 128 rows x 128 B
 constexpr int NUM_SLABS = 2;
-constexpr int GEMM_SMEM_BYTES = 1024 /*align slack*/ + 4 * (A_BYTES + 32768) + NUM_SLABS * SLAB_BYTES + 256;  // == 6 * (16K + 16K) + ...
+constexpr int BIAS_BYTES = BLOCK_N * 4;          // the tile's bias slice, staged once per tile (bf16 epilogues)
+constexpr int GEMM_SMEM_BYTES = 1024 /*align slack*/ + 4 * (A_BYTES + 32768) + NUM_SLABS * SLAB_BYTES + BIAS_BYTES + 256;  // == 6 * (16K + 16K) + ...
 
 struct GemmArgs {
   int M, N, K;
@@ -78,8 +81,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * A_BYTES;
   uint8_t* sSlab = smem + STAGES * (A_BYTES + B_BYTES);
-  uint8_t* sAux = sSlab + NUM_SLABS * SLAB_BYTES;   // 2 slabs, EPI_BF16_DACT only
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sSlab + (EPI == EPI_BF16_DACT ? 2 : 1) * NUM_SLABS * SLAB_BYTES);
+  uint8_t* sAux = sSlab + NUM_SLABS * SLAB_BYTES;   // 2 more slabs: EPI_BF16_DACT (aux prefetch) / EPI_BF16_ACT (2nd pair)
+  constexpr bool FOUR_SLABS = (EPI == EPI_BF16_DACT || EPI == EPI_BF16_ACT);
+  float* sBias = reinterpret_cast<float*>(sSlab + (FOUR_SLABS ? 2 : 1) * NUM_SLABS * SLAB_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sBias) + BIAS_BYTES);
   uint64_t* full_bar = bars;                   // [STAGES]
   uint64_t* empty_bar = bars + STAGES;         // [STAGES]
   uint64_t* tfull_bar = bars + 2 * STAGES;     // [ACC_STAGES]
@@ -93,7 +98,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    if (EPI == EPI_F32) tma_prefetch_desc(&tmD0);
+    tma_prefetch_desc(&tmD0);
+    if (EPI == EPI_BF16_ACT) tma_prefetch_desc(&tmD1);
     if (EPI == EPI_BF16_DACT) { tma_prefetch_desc(&tmD1); mbar_init(&aux_bar[0], 1); mbar_init(&aux_bar[1], 1); }
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
@@ -234,9 +240,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             tma_load_2d(&tmD1, &aux_bar[g], sAux + g * SLAB_BYTES, n0 + g * 64, m0);
           }
       }
+      if (EPI != EPI_F32 && p.bias != nullptr) {
+        // stage the tile's bias slice in shared memory (every reader of the previous tile's slice has passed that
+        // tile's last group barrier); global-load latency is taken here, under the MMAs, instead of in every group
+        if (epi_tid < BLOCK_N) sBias[epi_tid] = (add_bias && n0 + epi_tid < p.N) ? __ldg(p.bias + n0 + epi_tid) : 0.f;
+      }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
+      if (EPI != EPI_F32 && p.bias != nullptr) epi_bar_sync<ENT>();
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N;
+      // All TMEM reads of this accumulator stage are complete (tcgen05.wait::ld) -> hand it back to the MMA warp.
+      auto release_acc = [&]() {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (CTA2 && rank != 0) mbar_arrive_cluster(&tempty_bar[acc], 0);  // the leader's MMA warp owns the wait
+          else mbar_arrive(&tempty_bar[acc]);
+        }
+      };
 
       if (EPI == EPI_F32) {
         // fp32 output: a 32-column chunk is one 128 B x 128 row slab.  Half h owns chunks c == h (mod 2), slab h, named
@@ -272,138 +293,137 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
         }
       } else {
-        // bf16 outputs.  Per 64-column group: each half converts its 32 columns (TMEM -> registers -> bias /
-        // activation / act' -> bf16) into the swizzled smem slab (thread == row), one 256-thread named barrier, then a
-        // row-contiguous coalesced 16 B copy-out (8 rows of 128 B per warp instruction).  Slabs alternate, so one
-        // barrier per group suffices; EPI_BF16_ACT writes two tensors and uses both slabs per group (two barriers).
+        // bf16 outputs.  Per 64-column group: each column part converts its columns (TMEM -> registers -> bias /
+        // activation / act' -> bf16) into a 128B-swizzled smem slab (thread == row); one named barrier; then ONE thread
+        // hands the slab to the TMA store engine (cp.async.bulk.tensor clips the M / N edges).  No LDS/STG copy-out: the
+        // epilogue warps only convert.  Slabs alternate (EPI_BF16_ACT: two (pre-activation, activation) pairs), the
+        // issuing thread drains its bulk-group reads before each barrier, so a slab is free again two groups later.
+        // The tcgen05.ld of group g+1 is issued before the math of group g, and the accumulator stage is handed back
+        // to the MMA warp as soon as the last load has landed in registers.
         constexpr bool DUAL = (EPI == EPI_BF16_ACT);
-        __nv_bfloat16* D0p = reinterpret_cast<__nv_bfloat16*>(p.d0);
-        __nv_bfloat16* D1p = reinterpret_cast<__nv_bfloat16*>(p.d1);
-        for (int g = 0; g < BLOCK_N / 64; ++g) {
+        constexpr int NG4 = BLOCK_N / 64;
+        uint32_t vbuf[2][CWE];
+        auto ld_group = [&](int g, uint32_t (&v)[CWE]) {
+          if (CWE == 32) tmem_ld32(t_addr + g * 64 + half * 32, reinterpret_cast<uint32_t(&)[32]>(v));
+          else           tmem_ld16(t_addr + g * 64 + half * 16, reinterpret_cast<uint32_t(&)[16]>(v));
+        };
+        ld_group(0, vbuf[0]);
+#pragma unroll
+        for (int g = 0; g < NG4; ++g) {
           if (n0 + g * 64 >= p.N) break;
-          if (DUAL) epi_bar_sync<ENT>();  // both slabs are rewritten every group
-          uint8_t* dst0 = sSlab + (DUAL ? 0 : slab * SLAB_BYTES) + row * 128;
-          uint8_t* dst1 = sSlab + SLAB_BYTES + row * 128;
-          {
-            const int h = half;
-            uint32_t v[CWE];
-            if (CWE == 32) tmem_ld32(t_addr + g * 64 + h * 32, reinterpret_cast<uint32_t(&)[32]>(v));
-            else           tmem_ld16(t_addr + g * 64 + h * 16, reinterpret_cast<uint32_t(&)[16]>(v));
-            const int nb = n0 + g * 64 + h * CWE;
-            uint4 auxv[CWE / 8];
-            if (EPI == EPI_BF16_DACT) {
-              mbar_wait(&aux_bar[g & 1], (aux_phase >> (g & 1)) & 1);
-              const uint8_t* arow = sAux + (g & 1) * SLAB_BYTES + row * 128;
+          uint32_t (&v)[CWE] = vbuf[g & 1];
+          const int sl = DUAL ? 2 * slab : slab;              // slab (pair) of this group
+          uint8_t* slab0 = sSlab + sl * SLAB_BYTES;
+          uint8_t* dst0 = slab0 + row * 128;
+          uint8_t* dst1 = dst0 + SLAB_BYTES;
+          const int h = half;
+          const int nb = n0 + g * 64 + h * CWE;
+          uint4 auxv[CWE / 8];
+          if (EPI == EPI_BF16_DACT) {
+            mbar_wait(&aux_bar[g & 1], (aux_phase >> (g & 1)) & 1);
+            const uint8_t* arow = sAux + (g & 1) * SLAB_BYTES + row * 128;
 #pragma unroll
-              for (int j = 0; j < CWE / 8; ++j)
-                auxv[j] = *reinterpret_cast<const uint4*>(arow + (((h * (CWE / 8) + j) ^ (row & 7)) << 4));
-            }
-            tmem_ld_wait();
+            for (int j = 0; j < CWE / 8; ++j)
+              auxv[j] = *reinterpret_cast<const uint4*>(arow + (((h * (CWE / 8) + j) ^ (row & 7)) << 4));
+          }
+          tmem_ld_wait();
+          if (g + 1 < NG4 && n0 + (g + 1) * 64 < p.N) ld_group(g + 1, vbuf[(g + 1) & 1]);
+          else release_acc();                                 // every TMEM read of this stage is in registers
 #pragma unroll
-            for (int j = 0; j < CWE / 8; ++j) {  // 8 columns -> one 16 B chunk
-              float f[8];
+          for (int j = 0; j < CWE / 8; ++j) {  // 8 columns -> one 16 B chunk
+            float f[8];
+            if (add_bias) {
+              const float4 b0 = *reinterpret_cast<const float4*>(sBias + g * 64 + h * CWE + j * 8);
+              const float4 b1 = *reinterpret_cast<const float4*>(sBias + g * 64 + h * CWE + j * 8 + 4);
+              const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] = fmaf(__uint_as_float(v[j * 8 + e]), p.alpha, bb[e]);
+            } else {
 #pragma unroll
               for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[j * 8 + e]) * p.alpha;
-              const int n = nb + j * 8;
-              if (add_bias && n < p.N) {
-                const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-                const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4));
-                f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
-                f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
-              }
-              if (EPI == EPI_BF16_DACT) {
-                const uint32_t a[4] = {auxv[j].x, auxv[j].y, auxv[j].z, auxv[j].w};
+            }
+            if (EPI == EPI_BF16_DACT) {
+              const uint32_t a[4] = {auxv[j].x, auxv[j].y, auxv[j].z, auxv[j].w};
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  f[2 * e] *= act_grad<ACT>(bf16_lo(a[e]));
-                  f[2 * e + 1] *= act_grad<ACT>(bf16_hi(a[e]));
-                }
-              }
-              uint4 o;
-              o.x = pack_bf16x2(f[0], f[1]);
-              o.y = pack_bf16x2(f[2], f[3]);
-              o.z = pack_bf16x2(f[4], f[5]);
-              o.w = pack_bf16x2(f[6], f[7]);
-              const int off = ((h * (CWE / 8) + j) ^ (row & 7)) << 4;
-              *reinterpret_cast<uint4*>(dst0 + off) = o;
-              if (DUAL) {
-                // The activation is applied to the bf16-ROUNDED pre-activation: exactly what the backward (which
-                // only sees the stored bf16 pre-activation) differentiates.
-                const uint32_t pr[4] = {o.x, o.y, o.z, o.w};
-                float a[8];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  a[2 * e] = act_fn<ACT>(bf16_lo(pr[e]));
-                  a[2 * e + 1] = act_fn<ACT>(bf16_hi(pr[e]));
-                }
-                uint4 oa;
-                oa.x = pack_bf16x2(a[0], a[1]);
-                oa.y = pack_bf16x2(a[2], a[3]);
-                oa.z = pack_bf16x2(a[4], a[5]);
-                oa.w = pack_bf16x2(a[6], a[7]);
-                *reinterpret_cast<uint4*>(dst1 + off) = oa;
+              for (int e = 0; e < 4; ++e) {
+                f[2 * e] *= act_grad<ACT>(bf16_lo(a[e]));
+                f[2 * e + 1] *= act_grad<ACT>(bf16_hi(a[e]));
               }
             }
+            uint4 o;
+            o.x = pack_bf16x2(f[0], f[1]);
+            o.y = pack_bf16x2(f[2], f[3]);
+            o.z = pack_bf16x2(f[4], f[5]);
+            o.w = pack_bf16x2(f[6], f[7]);
+            const int off = ((h * (CWE / 8) + j) ^ (row & 7)) << 4;
+            *reinterpret_cast<uint4*>(dst0 + off) = o;
+            if (DUAL) {
+              // The activation is applied to the bf16-ROUNDED pre-activation: exactly what the backward (which
+              // only sees the stored bf16 pre-activation) differentiates.
+              const uint32_t pr[4] = {o.x, o.y, o.z, o.w};
+              float a[8];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                a[2 * e] = act_fn<ACT>(bf16_lo(pr[e]));
+                a[2 * e + 1] = act_fn<ACT>(bf16_hi(pr[e]));
+              }
+              uint4 oa;
+              oa.x = pack_bf16x2(a[0], a[1]);
+              oa.y = pack_bf16x2(a[2], a[3]);
+              oa.z = pack_bf16x2(a[4], a[5]);
+              oa.w = pack_bf16x2(a[6], a[7]);
+              *reinterpret_cast<uint4*>(dst1 + off) = oa;
+            }
           }
+          (void)nb;
+          fence_proxy_async_smem();                       // generic-proxy slab writes -> visible to the TMA engine
+          if (epi_tid == 0) tma_store_wait_read<0>();     // stores of the previous group have left their slab
           epi_bar_sync<ENT>();
+          if (epi_tid == 0) {
+            tma_store_2d(&tmD0, slab0, n0 + g * 64, m0);
+            if (DUAL) tma_store_2d(&tmD1, slab0 + SLAB_BYTES, n0 + g * 64, m0);
+            tma_store_commit();
+          }
           if (EPI == EPI_BF16_DACT) {
             aux_phase ^= 1u << (g & 1);
-            if (epi_tid == 0 && g + 2 < BLOCK_N / 64 && n0 + (g + 2) * 64 < p.N) {  // slab (g & 1) is free again
+            if (epi_tid == 0 && g + 2 < NG4 && n0 + (g + 2) * 64 < p.N) {  // aux slab (g & 1) is free again
               mbar_arrive_expect_tx(&aux_bar[g & 1], SLAB_BYTES);
               tma_load_2d(&tmD1, &aux_bar[g & 1], sAux + (g & 1) * SLAB_BYTES, n0 + (g + 2) * 64, m0);
             }
           }
-          // coalesced copy-out: 128 rows x 8 chunks of 16 B; thread -> (row = it*(ENT/8) + tid/8, chunk = tid%8)
-          {
+          if (!DUAL && p.colsum != nullptr) {   // uniform
+            // Column sums of the tile's rounded output (the bias gradient of the layer whose dgrad this is), read back
+            // from the slab: thread -> (16 B chunk ch, rows r = it*(ENT/8) + tid/8); the 4 lanes of a warp that share
+            // a chunk fold with two shuffles, then lanes 0..7 fire two vector reds each.
             const int ch = epi_tid & 7;
             const int ncol = n0 + g * 64 + ch * 8;
-            const uint8_t* s0 = sSlab + (DUAL ? 0 : slab * SLAB_BYTES);
-            const bool want_cs = !DUAL && p.colsum != nullptr;   // uniform
             float cs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int it = 0; it < 1024 / ENT; ++it) {
               const int r = it * (ENT / 8) + (epi_tid >> 3);
-              if (m0 + r < p.M && ncol < p.N) {
-                const int off = r * 128 + ((ch ^ (r & 7)) << 4);
-                const uint4 val = *reinterpret_cast<const uint4*>(s0 + off);
-                *reinterpret_cast<uint4*>(D0p + (long long)(m0 + r) * p.ldd0 + ncol) = val;
-                if (want_cs) {
-                  cs[0] += bf16_lo(val.x); cs[1] += bf16_hi(val.x); cs[2] += bf16_lo(val.y); cs[3] += bf16_hi(val.y);
-                  cs[4] += bf16_lo(val.z); cs[5] += bf16_hi(val.z); cs[6] += bf16_lo(val.w); cs[7] += bf16_hi(val.w);
-                }
-                if (DUAL) {
-                  const uint4 val1 = *reinterpret_cast<const uint4*>(s0 + SLAB_BYTES + off);
-                  *reinterpret_cast<uint4*>(D1p + (long long)(m0 + r) * p.ldd1 + ncol) = val1;
-                }
+              const uint4 val = *reinterpret_cast<const uint4*>(slab0 + r * 128 + ((ch ^ (r & 7)) << 4));
+              if (m0 + r < p.M) {
+                cs[0] += bf16_lo(val.x); cs[1] += bf16_hi(val.x); cs[2] += bf16_lo(val.y); cs[3] += bf16_hi(val.y);
+                cs[4] += bf16_lo(val.z); cs[5] += bf16_hi(val.z); cs[6] += bf16_lo(val.w); cs[7] += bf16_hi(val.w);
               }
             }
-            if (want_cs) {
-              // Column sums of the tile's rounded output (the bias gradient of the layer whose dgrad this is): the 4
-              // lanes of a warp that share a 16 B chunk fold with two shuffles, then lanes 0..7 fire 2 vector reds each.
 #pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                cs[e] += __shfl_xor_sync(0xffffffffu, cs[e], 8);
-                cs[e] += __shfl_xor_sync(0xffffffffu, cs[e], 16);
-              }
-              if (lane < 8 && ncol < p.N) {
-                float* dst = p.colsum + ncol;
-                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(cs[0]), "f"(cs[1]), "f"(cs[2]),
-                             "f"(cs[3]) : "memory");
-                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4), "f"(cs[4]), "f"(cs[5]),
-                             "f"(cs[6]), "f"(cs[7]) : "memory");
-              }
+            for (int e = 0; e < 8; ++e) {
+              cs[e] += __shfl_xor_sync(0xffffffffu, cs[e], 8);
+              cs[e] += __shfl_xor_sync(0xffffffffu, cs[e], 16);
+            }
+            if (lane < 8 && ncol < p.N) {
+              float* dst = p.colsum + ncol;
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(cs[0]), "f"(cs[1]), "f"(cs[2]),
+                           "f"(cs[3]) : "memory");
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4), "f"(cs[4]), "f"(cs[5]),
+                           "f"(cs[6]), "f"(cs[7]) : "memory");
             }
           }
           slab ^= 1;
         }
       }
-      // All TMEM reads of this accumulator stage are complete (tmem_ld_wait above) -> hand it back to the MMA warp.
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if (CTA2 && rank != 0) mbar_arrive_cluster(&tempty_bar[acc], 0);  // the leader's MMA warp owns the wait
-        else mbar_arrive(&tempty_bar[acc]);
-      }
+      if (EPI == EPI_F32) release_acc();   // fp32 path: after its last tcgen05.wait::ld
       if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
     }
     if ((epi_tid & 127) == 0) tma_store_wait_all<0>();
@@ -438,12 +458,40 @@ static PFN_encodeTiled get_encode_fn() {
   return fn;
 }
 
+// A tensor map is a pure function of (pointer, dims, pitch, box, dtype): the training step re-issues the same ~300
+// GEMMs / attention launches on persistent workspaces every step, so the encoded descriptors are memoised (the
+// driver call costs ~1-2 us each, 3-4 per launch).  Small direct-mapped cache; a miss simply re-encodes.
+struct TmapKey {
+  const void* ptr; uint64_t inner, outer, pitch; uint32_t box_inner, box_outer, kind;
+  bool operator==(const TmapKey& o) const {
+    return ptr == o.ptr && inner == o.inner && outer == o.outer && pitch == o.pitch && box_inner == o.box_inner &&
+           box_outer == o.box_outer && kind == o.kind;
+  }
+};
+struct TmapSlot { TmapKey key; CUtensorMap map; bool valid; };
+constexpr int TMAP_CACHE_SLOTS = 4096;
+static TmapSlot* g_tmap_cache = nullptr;
+static std::mutex g_tmap_mu;
+
 // 2-D row-major tensor [outer, inner] with row pitch `pitch_bytes`; box = [box_outer, box_inner]; 128B swizzle.
 int make_tmap_2d(CUtensorMap* out, const void* ptr, int elem_bytes, bool is_f32, uint64_t inner, uint64_t outer,
                  uint64_t pitch_bytes, uint32_t box_inner, uint32_t box_outer) {
   PFN_encodeTiled enc = get_encode_fn();
   if (!enc) return MMB_ERR_DRIVER;
   if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (pitch_bytes & 15) || box_inner * elem_bytes != 128) return MMB_ERR_ARG;
+  const TmapKey key{ptr, inner, outer, pitch_bytes, box_inner, box_outer, (uint32_t)(is_f32 ? 1 : 0)};
+  uint64_t hsh = reinterpret_cast<uintptr_t>(ptr) * 0x9E3779B97F4A7C15ull;
+  hsh ^= (inner * 0xC2B2AE3D27D4EB4Full) ^ (outer * 0x165667B19E3779F9ull) ^ (pitch_bytes << 17) ^
+         ((uint64_t)box_outer << 40) ^ ((uint64_t)box_inner << 52) ^ key.kind;
+  const int slot = (int)((hsh >> 20) % TMAP_CACHE_SLOTS);
+  {
+    std::lock_guard<std::mutex> lk(g_tmap_mu);
+    if (!g_tmap_cache) g_tmap_cache = new TmapSlot[TMAP_CACHE_SLOTS]();
+    if (g_tmap_cache[slot].valid && g_tmap_cache[slot].key == key) {
+      *out = g_tmap_cache[slot].map;
+      return MMB_OK;
+    }
+  }
   cuuint64_t gdim[2] = {inner, outer};
   cuuint64_t gstr[1] = {pitch_bytes};
   cuuint32_t box[2] = {box_inner, box_outer};
@@ -451,7 +499,14 @@ int make_tmap_2d(CUtensorMap* out, const void* ptr, int elem_bytes, bool is_f32,
   CUresult r = enc(out, is_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
                    const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS ? MMB_OK : MMB_ERR_DRIVER;
+  if (r != CUDA_SUCCESS) return MMB_ERR_DRIVER;
+  {
+    std::lock_guard<std::mutex> lk(g_tmap_mu);
+    g_tmap_cache[slot].key = key;
+    g_tmap_cache[slot].map = *out;
+    g_tmap_cache[slot].valid = true;
+  }
+  return MMB_OK;
 }
 
 static int g_num_sms = 0;
@@ -496,6 +551,17 @@ static int launch_impl(const CUtensorMap& tA, const CUtensorMap& tB, const CUten
 
 using namespace mmb;
 
+// Test / A-B hook: force the kernel variant mmb_gemm_bf16 dispatches to (process-wide).
+//   cta2: -1 = automatic (size heuristic / MMB_GEMM_CTA2), 0 = 1-CTA 128x256 tiles, 1 = CTA pairs (256x256 tiles)
+//   epilogue_warps: 0 = default (8 / MMB_GEMM_EW), 8 or 16 = activation-epilogue warps
+static int g_force_cta2 = -1, g_force_ew = 0;
+extern "C" int mmb_gemm_set_mode(int cta2, int epilogue_warps) {
+  if (cta2 < -1 || cta2 > 1 || (epilogue_warps != 0 && epilogue_warps != 8 && epilogue_warps != 16)) return MMB_ERR_ARG;
+  g_force_cta2 = cta2;
+  g_force_ew = epilogue_warps;
+  return MMB_OK;
+}
+
 extern "C" int mmb_gemm_bf16(const void* A, long long lda, int a_mn_major, const void* B, long long ldb,
                              int b_mn_major, void* D0, long long ldd0, void* D1, long long ldd1, int M, int N, int K,
                              int epilogue, int act, float alpha, const float* bias, const void* aux,
@@ -506,11 +572,12 @@ extern "C" int mmb_gemm_bf16(const void* A, long long lda, int a_mn_major, const
   if (epilogue == EPI_F32 ? (N & 3) : (N & 7)) return MMB_ERR_ARG;
   // CTA-pair mode (cta_group::2, 256x256 tiles) for everything large enough to fill the 74 SM pairs at least once;
   // MMB_GEMM_CTA2=0 forces the 1-CTA kernel (A/B testing), =1 forces pairs.
-  static int cta2_env = -2;
-  if (cta2_env == -2) {
+  static int cta2_env0 = -2;
+  if (cta2_env0 == -2) {
     const char* e = getenv("MMB_GEMM_CTA2");
-    cta2_env = e ? atoi(e) : -1;
+    cta2_env0 = e ? atoi(e) : -1;
   }
+  const int cta2_env = g_force_cta2 >= 0 ? g_force_cta2 : cta2_env0;   // mmb_gemm_set_mode() wins over the env var
   const long long big_tiles = (long long)((M + 255) / 256) * ((N + BLOCK_N - 1) / BLOCK_N);
   const bool cta2 = cta2_env == 1 || (cta2_env == -1 && M >= 512 && big_tiles * (splits < 1 ? 1 : splits) >= 37);
   GemmArgs g;
@@ -555,8 +622,14 @@ extern "C" int mmb_gemm_bf16(const void* A, long long lda, int a_mn_major, const
     if ((ldd0 & 7) || (reinterpret_cast<uintptr_t>(D0) & 15)) return MMB_ERR_ARG;
     if (epilogue == EPI_BF16_ACT && (!D1 || (ldd1 & 7) || (reinterpret_cast<uintptr_t>(D1) & 15))) return MMB_ERR_ARG;
     if (epilogue == EPI_BF16_DACT && (!aux || (ld_aux & 7) || (reinterpret_cast<uintptr_t>(aux) & 15))) return MMB_ERR_ARG;
-    tD0 = tA;  // unused by the bf16 epilogues
-    tD1 = tA;
+    // bf16 outputs leave through TMA stores of 128-row x 64-column (128 B) swizzled slabs; the tensor map clips M / N
+    rc = make_tmap_2d(&tD0, D0, 2, false, N, M, ldd0 * 2, 64, 128);
+    if (rc) return rc;
+    tD1 = tD0;
+    if (epilogue == EPI_BF16_ACT) {
+      rc = make_tmap_2d(&tD1, D1, 2, false, N, M, ldd1 * 2, 64, 128);
+      if (rc) return rc;
+    }
     if (epilogue == EPI_BF16_DACT) {  // act' operand, TMA-prefetched in 128-row x 64-column slabs
       rc = make_tmap_2d(&tD1, aux, 2, false, N, M, ld_aux * 2, 64, 128);
       if (rc) return rc;
@@ -566,11 +639,12 @@ extern "C" int mmb_gemm_bf16(const void* A, long long lda, int a_mn_major, const
   const int am = a_mn_major ? 1 : 0, bm = b_mn_major ? 1 : 0;
   // activation epilogues: 8 epilogue warps; MMB_GEMM_EW=16 selects the experimental 16-warp variant (FC2-dgrad x act'
   // 871 -> 996 TFLOP/s in isolation, FC1+act unchanged; not yet validated inside the full training step)
-  static int ew_env = -1;
-  if (ew_env < 0) {
+  static int ew_env0 = -1;
+  if (ew_env0 < 0) {
     const char* e = getenv("MMB_GEMM_EW");
-    ew_env = (e && e[0] == '1' && e[1] == '6') ? 16 : 8;
+    ew_env0 = (e && e[0] == '1' && e[1] == '6') ? 16 : 8;
   }
+  const int ew_env = g_force_ew > 0 ? g_force_ew : ew_env0;
   const bool act_epi = epilogue == EPI_BF16_ACT || epilogue == EPI_BF16_DACT;
 #define MMB_CASE(AM, BM, E, AC)                                                                                     \
   if (am == AM && bm == BM && epilogue == E && (AC < 0 || act == AC)) {                                             \
