@@ -112,6 +112,17 @@ int mmb_l2norm_bwd(const float* dy, const float* y, const float* inv_norm, float
 int mmb_adamw_step(float* p, float* g, float* m, float* v, void* p_bf16, long long n, float lr, float beta1,
                    float beta2, float eps, float weight_decay, int step, float grad_scale, int zero_grad,
                    void* stream);
+
+/* AnyPrecisionAdamW.step for ONE fp32 parameter tensor (modules/optimizers/anyprecision.py:99-199): momentum /
+ * variance / Kahan-compensation buffers in caller-chosen dtypes (*_dtype: 0 = fp32, 1 = bf16; reference defaults: fp32
+ * momentum, bf16 variance, bf16 compensation).  comp == NULL selects the plain update (use_kahan_summation=False).
+ * Every in-place rounding of the reference is reproduced; one fused pass replaces its ~12 elementwise kernels.
+ * p_bf16 (optional): bf16 copy of the updated weights (the GEMM operand shadow); zero_grad clears g in the same pass;
+ * grad_scale multiplies g first (1/world after a summed all-reduce; the reference has no such factor: pass 1). */
+int mmb_anyprecision_adamw_step(float* p, float* g, void* m, int m_dtype, void* v, int v_dtype, void* comp,
+                                int comp_dtype, void* p_bf16, long long n, double lr, double beta1, double beta2,
+                                double eps, double weight_decay, int step, float grad_scale, int zero_grad,
+                                void* stream);
 int mmb_memset_async(void* p, int value, long long bytes, void* stream);
 
 /* ---- attention --------------------------------------------------------------------------------------------- */

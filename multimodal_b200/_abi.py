@@ -3,7 +3,7 @@ from __future__ import annotations
 
 import ctypes as C
 
-vp, ll, i32, f32 = C.c_void_p, C.c_longlong, C.c_int, C.c_float
+vp, ll, i32, f32, f64 = C.c_void_p, C.c_longlong, C.c_int, C.c_float, C.c_double
 
 PROTOTYPES = {
     "mmb_version": (i32, []),
@@ -23,6 +23,7 @@ PROTOTYPES = {
     "mmb_l2norm_fwd": (i32, [vp, vp, vp, vp, i32, i32, f32, vp]),
     "mmb_l2norm_bwd": (i32, [vp, vp, vp, vp, vp, i32, i32, vp]),
     "mmb_adamw_step": (i32, [vp, vp, vp, vp, vp, ll, f32, f32, f32, f32, f32, i32, f32, i32, vp]),
+    "mmb_anyprecision_adamw_step": (i32, [vp, vp, vp, i32, vp, i32, vp, i32, vp, ll, f64, f64, f64, f64, f64, i32, f32, i32, vp]),
     "mmb_memset_async": (i32, [vp, i32, ll, vp]),
     "mmb_attention_fwd": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, f32, vp]),
     "mmb_attention_bwd": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, vp]),

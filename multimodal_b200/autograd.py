@@ -33,6 +33,12 @@ class TowerFunction(torch.autograd.Function):
             st.zero_grads()
         rt.backward(demb.contiguous().float())
         if flat:  # p.grad are views of the flat buffer: gradients were accumulated in place
+            # `optimizer.zero_grad(set_to_none=True)` (torch's default) or `p.grad = None` severs those views; re-attach
+            # them, otherwise gradients would pile up invisibly in the flat buffer while the optimizer skips the parameter
+            for p in st.params:
+                want = st.grad(p)
+                if p.grad is None or p.grad.data_ptr() != want.data_ptr():
+                    p.grad = want
             return (None, None) + (None,) * ctx.n
         g = st.g.clone()
         grads = []

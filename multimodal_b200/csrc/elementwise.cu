@@ -705,6 +705,60 @@ __global__ void adamw_kernel(float* __restrict__ p, float* __restrict__ g, float
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// AnyPrecisionAdamW (torchmultimodal/modules/optimizers/anyprecision.py:99-199): AdamW whose momentum, variance and
+// Kahan-compensation buffers live in caller-chosen dtypes (fp32 or bf16; reference defaults: fp32 momentum, bf16
+// variance, bf16 compensation).  Every in-place op of the reference rounds to the STATE's dtype; the kernel reproduces
+// those roundings one for one (rn<T>) with fp32 op-math in between, as TensorIterator does for mixed-dtype operands:
+//   m  = rn_M(rn_M(m * b1) + (1 - b1) * g)                      (:161  mul_ ; add_(alpha))
+//   v  = rn_V(fma((1 - b2) * g, g, rn_V(v * b2)))               (:164  mul_ ; addcmul_)
+//   cv = rn_V(rn_V(rn_V(sqrt(v)) / sqrt(1 - b2^t)) + eps)       (:174  sqrt ; / ; add_)
+//   plain: p += -step_size * (m / cv)                           (:190  addcdiv_)
+//   Kahan: c = rn_C(c - step_size * (m / cv)); t = p; p += c; c = rn_C(c + (t - p))      (:177-186)
+// Parameters and gradients are fp32 (this runtime keeps fp32 masters); the bf16 GEMM shadow is refreshed in the same
+// pass.  One fused pass instead of the reference's ~12 elementwise kernels per parameter tensor.
+// ---------------------------------------------------------------------------------------------
+template <typename T> __device__ __forceinline__ float st_load(const T* p, long long i);
+template <> __device__ __forceinline__ float st_load<float>(const float* p, long long i) { return p[i]; }
+template <> __device__ __forceinline__ float st_load<__nv_bfloat16>(const __nv_bfloat16* p, long long i) { return __bfloat162float(p[i]); }
+template <typename T> __device__ __forceinline__ float rn(float x);
+template <> __device__ __forceinline__ float rn<float>(float x) { return x; }
+template <> __device__ __forceinline__ float rn<__nv_bfloat16>(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+template <typename T> __device__ __forceinline__ void st_store(T* p, long long i, float x);
+template <> __device__ __forceinline__ void st_store<float>(float* p, long long i, float x) { p[i] = x; }
+template <> __device__ __forceinline__ void st_store<__nv_bfloat16>(__nv_bfloat16* p, long long i, float x) { p[i] = __float2bfloat16_rn(x); }
+
+template <typename TM, typename TV, typename TC, bool KAHAN>
+__global__ void anyprecision_adamw_kernel(float* __restrict__ p, float* __restrict__ g, TM* __restrict__ m,
+                                          TV* __restrict__ v, TC* __restrict__ comp, __nv_bfloat16* __restrict__ p_bf16,
+                                          long long n, float decay, float beta1, float beta2, float alpha1, float alpha2,
+                                          float eps, float neg_step_size, float denom_corr, float grad_scale,
+                                          int zero_grad) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float gr = g[i] * grad_scale;
+    float P = p[i] * decay;                                                     // decay == 1 when weight_decay == 0
+    const float M = rn<TM>(fmaf(alpha1, gr, rn<TM>(st_load<TM>(m, i) * beta1)));  // add_(alpha) is a fused multiply-add
+    const float V = rn<TV>(fmaf(__fmul_rn(alpha2, gr), gr, rn<TV>(st_load<TV>(v, i) * beta2)));   // addcmul contracts to an FMA
+    const float cv = rn<TV>(rn<TV>(rn<TV>(sqrtf(V)) / denom_corr) + eps);
+    const float upd = __fdiv_rn(__fmul_rn(neg_step_size, M), cv);               // addcdiv: (value * t1) / t2
+    if (KAHAN) {
+      float C = rn<TC>(__fadd_rn(st_load<TC>(comp, i), upd));
+      const float T = P;
+      P = __fadd_rn(P, C);
+      C = rn<TC>(__fadd_rn(C, __fsub_rn(T, P)));
+      st_store<TC>(comp, i, C);
+    } else {
+      P = __fadd_rn(P, upd);
+    }
+    p[i] = P;
+    st_store<TM>(m, i, M);
+    st_store<TV>(v, i, V);
+    if (zero_grad) g[i] = 0.f;
+    if (p_bf16) p_bf16[i] = __float2bfloat16_rn(P);
+  }
+}
+
 }  // namespace mmb
 
 using namespace mmb;
@@ -884,5 +938,42 @@ extern "C" int mmb_concat_tokens(const float* cls, const float* a, const float* 
   if (d & 3) return MMB_ERR_ARG;
   const long long total = (long long)B * ((cls ? 1 : 0) + Sa + Sb) * d / 4;
   concat_tokens_kernel<<<grid_for(total, 256), 256, 0, ST(stream)>>>(cls, a, b, out, B, Sa, Sb, d);
+  return LAUNCH_RC();
+}
+
+// dtype codes: 0 = fp32, 1 = bf16.  Hyper-parameters arrive as doubles (Python floats) and are folded / rounded to
+// fp32 exactly where the reference does: 1 - lr*wd and 1 - beta are formed in double, then cast.
+extern "C" int mmb_anyprecision_adamw_step(float* p, float* g, void* m, int m_dtype, void* v, int v_dtype, void* comp,
+                                           int comp_dtype, void* p_bf16, long long n, double lr, double beta1,
+                                           double beta2, double eps, double weight_decay, int step, float grad_scale,
+                                           int zero_grad, void* stream) {
+  if (n <= 0) return MMB_OK;
+  if (!p || !g || !m || !v || step < 1) return MMB_ERR_ARG;
+  if ((m_dtype | v_dtype | comp_dtype) & ~1) return MMB_ERR_ARG;
+  // bias corrections as the reference computes them on a float32 step tensor (anyprecision.py:167-172)
+  const float b1f = (float)beta1, b2f = (float)beta2;
+  const float bc1 = 1.f - powf(b1f, (float)step);
+  const float neg_step_size = -((1.f / bc1) * (float)lr);   // `lr / tensor` is reciprocal(tensor) * lr in torch (Tensor.__rtruediv__)
+  const float denom_corr = sqrtf(1.f - powf(b2f, (float)step));
+  const float decay = weight_decay != 0.0 ? (float)(1.0 - lr * weight_decay) : 1.f;
+  const float alpha1 = (float)(1.0 - beta1), alpha2 = (float)(1.0 - beta2);
+  const int grid = grid_for(n, 256);
+  typedef __nv_bfloat16 bf;
+#define AP_LAUNCH(TM, TV, TC, K)                                                                                      \
+  anyprecision_adamw_kernel<TM, TV, TC, K><<<grid, 256, 0, ST(stream)>>>(p, g, (TM*)m, (TV*)v, (TC*)comp, (bf*)p_bf16, n, \
+                                                                         decay, b1f, b2f, alpha1, alpha2, (float)eps,  \
+                                                                         neg_step_size, denom_corr, grad_scale, zero_grad)
+#define AP_COMP(TM, TV)                                                                   \
+  do {                                                                                    \
+    if (!comp) AP_LAUNCH(TM, TV, float, false);                                           \
+    else if (comp_dtype == 0) AP_LAUNCH(TM, TV, float, true);                             \
+    else AP_LAUNCH(TM, TV, bf, true);                                                     \
+  } while (0)
+  if (m_dtype == 0 && v_dtype == 0) AP_COMP(float, float);
+  else if (m_dtype == 0 && v_dtype == 1) AP_COMP(float, bf);
+  else if (m_dtype == 1 && v_dtype == 0) AP_COMP(bf, float);
+  else AP_COMP(bf, bf);
+#undef AP_COMP
+#undef AP_LAUNCH
   return LAUNCH_RC();
 }

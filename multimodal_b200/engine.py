@@ -20,6 +20,28 @@ from ._lib import MMBError
 
 _ALIGN = 64  # elements; keeps every shadow / grad slice 128 B aligned (TMA needs 16 B)
 
+# bf16 operand shadows are re-cast when a parameter's autograd version counter (or storage) changes.  In-place writes
+# through `.data` (`w.data.copy_()`, EMA updates, `module.weight.data.normal_()`) do NOT bump that counter, so every
+# shadow key also carries this process-wide epoch: `invalidate_weight_caches()` (exported from the package root, and
+# called by the drop-in modules' load_state_dict / _apply hooks) forces a re-cast on the next forward.
+_WEIGHT_EPOCH = [0]
+
+
+def invalidate_weight_caches() -> None:
+    _WEIGHT_EPOCH[0] += 1
+
+
+def weight_epoch() -> int:
+    return _WEIGHT_EPOCH[0]
+
+
+def watch_module(mod: nn.Module) -> None:
+    """Invalidate the shadows whenever `mod` (or a parent calling into it) reloads or re-homes its parameters."""
+    if getattr(mod, "_mmb_watched", False):
+        return
+    mod._mmb_watched = True
+    mod.register_load_state_dict_post_hook(lambda module, incompatible: invalidate_weight_caches())
+
 
 class ParamStore:
     """Flat bf16 shadow (tensor-core operand copies) + flat fp32 gradient buffer for a list of parameters."""
@@ -45,6 +67,7 @@ class ParamStore:
         self._seen: Dict[int, tuple] = {}
         self.master: Optional[torch.Tensor] = None  # set by flatten_()
         self._shadow_fresh = False
+        self._epoch = _WEIGHT_EPOCH[0]
 
     # -- views ------------------------------------------------------------------------------------------
     def shadow(self, p: nn.Parameter) -> torch.Tensor:
@@ -81,14 +104,15 @@ class ParamStore:
     def refresh(self) -> None:
         """Make the bf16 shadows current (re-cast whatever changed since the last call)."""
         if self.master is not None:
-            if not self._shadow_fresh:
+            if not self._shadow_fresh or self._epoch != _WEIGHT_EPOCH[0]:
                 ops.cast_bf16(self.master, self.wb)
                 self._shadow_fresh = True
+                self._epoch = _WEIGHT_EPOCH[0]
             return
         for p in self.params:
             if p.device != self.device:
                 raise MMBError("parameter moved to another device after the runtime was created")
-            key = (p._version, p.data_ptr())
+            key = (p._version, p.data_ptr(), _WEIGHT_EPOCH[0])
             if self._seen.get(id(p)) != key:
                 src = p.data if p.data.is_contiguous() else p.data.contiguous()
                 ops.cast_bf16(src.view(-1), self.wb[self.off[id(p)]:self.off[id(p)] + p.numel()])

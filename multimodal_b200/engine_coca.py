@@ -83,7 +83,9 @@ class LayerStack:
             wqkv, bqkv = self._qkv(l, at)
             ln1, ln2 = layer.attention_layernorm, layer.feedforward_layernorm
             if l > 0:   # x_l = previous mid-stream + previous MLP output, fused into this LayerNorm
-                XA = ws.get(f"{pfx}.XA.{l}" if keep_hidden else f"{pfx}.XA.{l % 2}", (M, d), f32)
+                # returned as hidden_states[l] when requested: allocated per call (never aliases a later forward)
+                XA = (torch.empty((M, d), device=X0.device, dtype=f32) if keep_hidden
+                      else ws.get(f"{pfx}.XA.{l % 2}", (M, d), f32))
                 ops.add_layernorm_fwd(XR, Y, XA, LN, None, ln1.weight, ln1.bias, None, None, M, d, ln1.eps)
                 if keep_hidden:
                     hidden.append(XA.view(B, S, d))
@@ -125,9 +127,11 @@ class LayerStack:
         Returns (XF fp32 [M,d], LAST fp32 or None, LAST bf16 or None)."""
         XR, Y = self._last
         M, d, ws, pfx = B * S, self.d, self.ws, self.prefix
-        XF = ws.get(f"{pfx}.XF", (M, d), torch.float32)
+        # XF / LAST are handed to the caller (last_hidden_state / hidden_states[-1] / tokens): fresh per call, as the
+        # reference's outputs are; bf16 copies consumed inside the same forward stay in the workspace
+        XF = torch.empty((M, d), device=XR.device, dtype=torch.float32)
         ln = final_ln if final_ln is not None else self.layers[0].attention_layernorm  # affine unused when no output
-        LAST = ws.get(f"{pfx}.LAST", (M, d), torch.float32) if final_ln is not None else None
+        LAST = torch.empty((M, d), device=XR.device, dtype=torch.float32) if final_ln is not None else None
         LASTb = ws.get(f"{pfx}.LASTb", (M, d), torch.bfloat16) if (final_ln is not None and want_bf16) else None
         ops.add_layernorm_fwd(XR, Y, XF, LASTb, LAST, ln.weight, ln.bias, None, None, M, d, ln.eps)
         return XF, LAST, LASTb
@@ -158,7 +162,7 @@ class VisionRuntime:
         bf, f32 = torch.bfloat16, torch.float32
         PATCH = ws.get("vit.PATCH", (B * P, Kp), bf)[:, :K]
         PO = ws.get("vit.PO", (B * P, d), bf)
-        X0 = ws.get("vit.X0", (B * S, d), f32)
+        X0 = torch.empty((B * S, d), device=image.device, dtype=f32)   # returned as hidden_states[0]
         ops.im2col(image, ps, PATCH)
         w = sh.get("conv.w", [conv.weight.view(d, K)])
         if Kp != K:
@@ -294,7 +298,7 @@ class MultimodalDecoderRuntime:
         fln = m.transformer_decoder.final_layer_norm
         XF, LAST, LASTb = st.finish(B, S, fln, want_bf16=m.output_projection is not None)
         if m.output_projection is None:
-            return (LAST if fln is not None else XF).view(B, S, d).clone()
+            return (LAST if fln is not None else XF).view(B, S, d)
         if LASTb is None:
             LASTb = ws.get("cmm.LASTb", (B * S, d), torch.bfloat16)
             ops.cast_bf16(XF.view(-1), LASTb.view(-1))

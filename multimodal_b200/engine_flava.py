@@ -10,8 +10,8 @@ modules/layers/attention.py:120-241, modules/losses/flava.py:84-97.
 
 Deviation (documented in DESIGN.md): ``TransformerOutput.attentions`` is ``None`` — the flash-style kernel never
 materialises the [B, H, S, S] probabilities (477 MB fp32 per layer at B=256); nothing in the library consumes them.
-The tensors in ``hidden_states`` / ``last_hidden_state`` alias per-encoder workspaces and are valid until that encoder's
-next forward.
+Every tensor of the returned ``TransformerOutput`` is allocated per call (as the reference's are); only internal
+scratch is reused between forwards.
 """
 from __future__ import annotations
 
@@ -22,7 +22,7 @@ from torch import nn
 
 from . import ops
 from ._lib import MMBError
-from .engine import Workspace
+from .engine import Workspace, weight_epoch
 from .modules.layers.transformer import TransformerOutput
 
 
@@ -36,7 +36,7 @@ class _Shadows:
 
     def get(self, key: str, parts: Sequence[torch.Tensor]) -> torch.Tensor:
         """bf16 copy of cat(parts, dim=0) (each part [n_i, k])."""
-        ver = tuple((p._version, p.data_ptr()) for p in parts)
+        ver = (weight_epoch(),) + tuple((p._version, p.data_ptr()) for p in parts)
         buf = self.bufs.get(key)
         if buf is None:
             rows = sum(p.shape[0] for p in parts)
@@ -52,7 +52,7 @@ class _Shadows:
         return buf
 
     def cat_f32(self, key: str, parts: Sequence[torch.Tensor]) -> torch.Tensor:
-        ver = tuple((p._version, p.data_ptr()) for p in parts)
+        ver = (weight_epoch(),) + tuple((p._version, p.data_ptr()) for p in parts)
         buf = self.bufs.get(key)
         if buf is None:
             buf = torch.empty(sum(p.numel() for p in parts), device=self.device, dtype=torch.float32)
@@ -116,7 +116,7 @@ class FlavaStack:
             w2 = sh.get(f"{l}.w2", [mlp[-1].weight])
             ln1, ln2 = layer.attention_layernorm, layer.feedforward_layernorm
             if l > 0:  # x_l = x_{l-1,mid} + mlp_out (fused into this LayerNorm kernel); kept as hidden_states[l]
-                XA = ws.get(f"{pfx}.XA.{l}", (M, d), f32)
+                XA = torch.empty((M, d), device=self.device, dtype=f32)   # returned (hidden_states[l]): fresh per call
                 ops.add_layernorm_fwd(XM, Y, XA, LN, None, ln1.weight, ln1.bias, None, None, M, d, ln1.eps)
                 hidden.append(XA.view(B, S, d))
             else:
@@ -130,8 +130,10 @@ class FlavaStack:
             ops.add_layernorm_fwd(XA, Y, XM, LN, None, ln2.weight, ln2.bias, None, None, M, d, ln2.eps)
             ops.gemm(LN, w1, bias=mlp[0].bias, epilogue=ops.EPI_BF16_ACT, out=PRE, out2=HACT, act=self.act)
             ops.gemm(HACT, w2, bias=mlp[-1].bias, out=Y)
-        XF = ws.get(f"{pfx}.XF", (M, d), f32)      # final residual stream == hidden_states[-1] (pre-LayerNorm)
-        LAST = ws.get(f"{pfx}.LAST", (M, d), f32)  # layernorm(XF) == last_hidden_state
+        # returned tensors are allocated per call (the reference returns fresh tensors: a caller may keep the outputs
+        # of several forwards alive); only internal scratch lives in the reused workspace
+        XF = torch.empty((M, d), device=self.device, dtype=f32)      # final residual stream == hidden_states[-1] (pre-LayerNorm)
+        LAST = torch.empty((M, d), device=self.device, dtype=f32)    # layernorm(XF) == last_hidden_state
         ops.add_layernorm_fwd(XM, Y, XF, None, LAST, self.layernorm.weight, self.layernorm.bias, None, None, M, d,
                               self.layernorm.eps)
         hidden.append(XF.view(B, S, d))
@@ -175,7 +177,7 @@ class FlavaImageRuntime:
         bf, f32 = torch.bfloat16, torch.float32
         PATCH = ws.get("fimg.PATCH", (B * P, Kp), bf)[:, :K]
         PO = ws.get("fimg.PO", (B * P, d), bf)
-        X0 = ws.get("fimg.X0", (B * S, d), f32)
+        X0 = torch.empty((B * S, d), device=image.device, dtype=f32)   # returned as hidden_states[0]
         ops.im2col(image, ps, PATCH)
         w = sh.get("conv.w", [conv.weight.view(d, K)])
         if Kp != K:
@@ -204,7 +206,7 @@ class FlavaTextRuntime:
         B, S = ids.shape
         if S > emb.position_embeddings.weight.shape[0]:
             raise ValueError(f"sequence length {S} exceeds max_position_embeddings")
-        X0 = ws.get("ftxt.X0", (B * S, d), torch.float32)
+        X0 = torch.empty((B * S, d), device=input_ids.device, dtype=torch.float32)   # returned as hidden_states[0]
         KM = ws.get("ftxt.KM", (B * S,), torch.uint8)
         tt = token_type_ids.long().contiguous() if token_type_ids is not None else None
         ops.bert_embed_ln_fwd(ids, tt, emb.word_embeddings.weight, emb.position_embeddings.weight,
@@ -228,7 +230,7 @@ class FlavaMMRuntime:
         B, S, d = hidden_states.shape
         hs = hidden_states.contiguous().float()
         if self.mod.cls_token is not None:
-            X0 = st.ws.get("fmm.X0", (B * (S + 1), d), torch.float32)
+            X0 = torch.empty((B * (S + 1), d), device=hs.device, dtype=torch.float32)   # returned as hidden_states[0]
             # cat(cls, hidden) == concat_tokens(cls, hidden, <empty>)
             ops.concat_tokens(self.mod.cls_token, hs, hs, X0, B, S, 0, d)
             S += 1
@@ -257,6 +259,6 @@ class FlavaMMRuntime:
         ops.gemm(Tb, sh.get("proj.t", [text_proj.weight]), bias=text_proj.bias, epilogue=ops.EPI_F32, out=Pt)
         cls = self.mod.cls_token
         S = Si + St + (1 if cls is not None else 0)
-        X0 = ws.get("fmm.X0", (B * S, d), f32)
+        X0 = torch.empty((B * S, d), device=image_hidden.device, dtype=f32)   # returned as hidden_states[0]
         ops.concat_tokens(cls, Pi, Pt, X0, B, Si, St, d)
         return st.forward(X0, B, S)

@@ -92,7 +92,11 @@ def contrastive_schedule(a, b, s, smoothing, backprop_type, want_logits, world, 
     logits_b = torch.empty((B, N), device=dev, dtype=f32) if want_logits else None
     out = torch.empty(3, device=dev, dtype=f32)
     lab = rank * B
-    if backprop_type == BackpropType.GLOBAL:
+    dist_on = torch.distributed.is_available() and torch.distributed.is_initialized()
+    if backprop_type == BackpropType.GLOBAL or not dist_on:
+        # no process group: _gather_embeddings_and_labels returns the live tensors whatever backprop_type says
+        # (contrastive_loss_with_temperature.py:31-33), so the full gradient flows; an INITIALISED world of one rank
+        # does go through gather_tensor and honours LOCAL / NONE (utils/distributed.py:50-58)
         lo, hi = 0, N
     elif backprop_type == BackpropType.LOCAL:
         lo, hi = lab, lab + B

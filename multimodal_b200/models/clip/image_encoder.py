@@ -9,7 +9,7 @@ import torch
 from torch import nn, Tensor
 
 from ...autograd import TowerFunction
-from ...engine import ViTTower
+from ...engine import watch_module, ViTTower
 from ...modules.layers.activation import SiLU
 from ...modules.layers.normalizations import Fp32LayerNorm
 
@@ -50,6 +50,7 @@ class CLIPViTEncoder(nn.Module):
         ids = [id(p) for p in self.parameters()]
         if self._rt is None or self._rt.store.device != self.projection.device or self._rt_ids != ids:
             self._rt, self._rt_ids = ViTTower(self), ids
+            watch_module(self)
         return self._rt
 
     def forward(self, x: Tensor) -> Tensor:

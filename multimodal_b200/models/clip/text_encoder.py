@@ -10,7 +10,7 @@ from torch import nn, Tensor
 from torch.nn import TransformerEncoder, TransformerEncoderLayer
 
 from ...autograd import TowerFunction
-from ...engine import TextTower
+from ...engine import watch_module, TextTower
 from ...modules.layers.activation import SiLU
 from ...modules.layers.normalizations import Fp32LayerNorm
 
@@ -68,6 +68,7 @@ class CLIPTextEncoder(nn.Module):
         ids = [id(p) for p in self.parameters()]
         if self._rt is None or self._rt.store.device != self.positional_embedding.device or self._rt_ids != ids:
             self._rt, self._rt_ids = TextTower(self), ids
+            watch_module(self)
         return self._rt
 
     def forward(self, text: Tensor, return_hidden_state: bool = False) -> Tensor:

@@ -10,6 +10,7 @@ import torch
 from torch import nn, Tensor
 
 from ... import ops
+from ..._lib import MMBError
 from ...modules.encoders.vision_transformer import vision_transformer
 from ...modules.layers.attention_pooler import AttentionPooler, CascadedAttentionPooler
 from ...modules.layers.transformer import TransformerOutput
@@ -174,8 +175,18 @@ class CoCaForPretraining(nn.Module):
                                                                logit_scale_max=contrastive_logit_scale_max)
         self.caption_loss = nn.CrossEntropyLoss(ignore_index=pad_idx)
 
-    @torch.no_grad()
     def forward(self, images: Tensor, texts: Tensor, text_padding_mask: Optional[Tensor] = None) -> Dict[str, Tensor]:
+        # The CoCa runtime is forward-only: the losses returned here carry no autograd graph.  Asking
+        # for them with gradients enabled on trainable parameters would let `loss.backward()` silently do nothing
+        # (or fail far from the cause), so say so here instead.
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            raise MMBError("CoCaForPretraining (multimodal_b200) computes forward values only — there is no backward "
+                           "for the CoCa stacks yet.  Evaluate under torch.no_grad() (or freeze the parameters); "
+                           "training CoCa needs the reference implementation.")
+        with torch.no_grad():
+            return self._forward_values(images, texts, text_padding_mask)
+
+    def _forward_values(self, images: Tensor, texts: Tensor, text_padding_mask: Optional[Tensor] = None) -> Dict[str, Tensor]:
         model_outs = self.model(images, texts, text_padding_mask)
         img = model_outs.image_pooled_output
         if img.dim() == 3:           # [B, 1, d] from the cascaded contrastive pooler

@@ -41,14 +41,6 @@ def flava_multimodal_encoder(hidden_size: int = 768, num_attention_heads: int = 
     return FLAVATransformerWithoutEmbeddings(encoder=encoder, layernorm=layernorm, pooler=pooler, hidden_size=hidden_size)
 
 
-def _snapshot(out: TransformerOutput) -> TransformerOutput:
-    """Detach an encoder's output from its workspace (the same encoder runs again for the masked pass)."""
-    if out.last_hidden_state is None:
-        return out
-    return out._replace(last_hidden_state=out.last_hidden_state.clone(),
-                        hidden_states=[h.clone() for h in out.hidden_states] if out.hidden_states else out.hidden_states)
-
-
 class FLAVAModel(nn.Module):
     def __init__(self, image_encoder: nn.Module, text_encoder: nn.Module, mm_encoder: nn.Module,
                  image_to_mm_projection: nn.Module, text_to_mm_projection: nn.Module, text_projection: nn.Module,
@@ -83,8 +75,6 @@ class FLAVAModel(nn.Module):
             image, required_embedding, ["image", "mm"], partial(self.encode_image, projection=True))
         if len(image_encoding_out) == 2:
             image_outputs, projected_image_embeddings = image_encoding_out[0], image_encoding_out[1]
-            if two_image_passes:
-                image_outputs = _snapshot(image_outputs)
         else:
             image_outputs, projected_image_embeddings = image_encoding_out, None
 
@@ -92,18 +82,16 @@ class FLAVAModel(nn.Module):
             text, required_embedding, ["text", "mm"], partial(self.encode_text, projection=True))
         if len(text_encoding_out) == 2:
             text_outputs, projected_text_embeddings = text_encoding_out[0], text_encoding_out[1]
-            if two_text_passes:
-                text_outputs = _snapshot(text_outputs)
         else:
             text_outputs, projected_text_embeddings = text_encoding_out, None
 
         multimodal_outputs = TransformerOutput()
         multimodal_masked_outputs = TransformerOutput()
         if required_embedding == "mm" and not skip_unmasked_mm_encoder:
-            # unmasked multimodal pass first: the masked one below then owns the mm workspace
-            multimodal_outputs = _snapshot(self.encode_mm(
+            # every encoder call returns freshly allocated tensors: the masked passes below do not disturb these
+            multimodal_outputs = self.encode_mm(
                 image_outputs.hidden_states[-1] if image_outputs.hidden_states else None,
-                text_outputs.hidden_states[-1] if text_outputs.hidden_states else None))
+                text_outputs.hidden_states[-1] if text_outputs.hidden_states else None)
 
         image_masked_outputs = self._encode_data_to_embeddings(
             image, required_embedding, ["image", "mm"],

@@ -22,6 +22,30 @@ _NULL = ctypes.c_void_p(0)
 # When set to a list, every GEMM launch is bracketed by CUDA events on the launching stream and appended as
 # (algorithmic_flops, (a_mn, b_mn, epilogue), (start_event, end_event)) — used by bench.py for the live roofline.
 GEMM_TIMING = None
+# Same for the other kernel families of the step: (family, algorithmic work, unit, (start_event, end_event)) with
+# family in {"attn_fwd", "attn_bwd", "ln_fwd", "ln_bwd"}; work in flops (attention) or bytes (LayerNorm passes).
+FAMILY_TIMING = None
+
+
+class _timed:
+    """Brackets one launch with CUDA events on the current stream when FAMILY_TIMING is armed (bench.py only)."""
+
+    __slots__ = ("fam", "work", "unit", "ev")
+
+    def __init__(self, fam, work, unit):
+        self.fam, self.work, self.unit, self.ev = fam, work, unit, None
+
+    def __enter__(self):
+        if FAMILY_TIMING is not None:
+            self.ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            self.ev[0].record()
+        return self
+
+    def __exit__(self, *exc):
+        if self.ev is not None and exc[0] is None:
+            self.ev[1].record()
+            FAMILY_TIMING.append((self.fam, float(self.work), self.unit, self.ev))
+        return False
 
 
 def _p(t: Optional[torch.Tensor]):
@@ -121,9 +145,12 @@ def im2col(img: torch.Tensor, ps: int, out: torch.Tensor) -> torch.Tensor:
 
 def add_layernorm_fwd(x_in, y, x_out, ln_bf16, ln_f32, gamma, beta, mean, rstd, M, d, eps, row_idx=None,
                       rows_per_group=0):
-    _lib.check(_lib.lib().mmb_add_layernorm_fwd(_p(x_in), _p(y), _p(x_out), _p(ln_bf16), _p(ln_f32), _p(gamma), _p(beta),
-                                                _p(mean), _p(rstd), _p(row_idx), rows_per_group, M, d, float(eps),
-                                                _stream()), "mmb_add_layernorm_fwd")
+    nbytes = M * d * (4 + (2 if y is not None else 0) + (4 if x_out is not None else 0) +
+                      (2 if ln_bf16 is not None else 0) + (4 if ln_f32 is not None else 0))
+    with _timed("ln_fwd", nbytes, "B"):
+        _lib.check(_lib.lib().mmb_add_layernorm_fwd(_p(x_in), _p(y), _p(x_out), _p(ln_bf16), _p(ln_f32), _p(gamma),
+                                                    _p(beta), _p(mean), _p(rstd), _p(row_idx), rows_per_group, M, d,
+                                                    float(eps), _stream()), "mmb_add_layernorm_fwd")
 
 
 def vit_embed_ln_fwd(patch_out, cls, pos, gamma, beta, x0, mean, rstd, B, S, d, eps):
@@ -133,9 +160,12 @@ def vit_embed_ln_fwd(patch_out, cls, pos, gamma, beta, x0, mean, rstd, B, S, d, 
 
 def layernorm_bwd(x, dy_bf16, dy_f32, mean, rstd, gamma, g_in, g_out, g_bf16, dgamma, dbeta, M, d, row_idx=None,
                   rows_per_group=0, gsum=None):
-    _lib.check(_lib.lib().mmb_layernorm_bwd(_p(x), _p(dy_bf16), _p(dy_f32), _p(mean), _p(rstd), _p(gamma), _p(g_in),
-                                            _p(g_out), _p(g_bf16), _p(dgamma), _p(dbeta), _p(row_idx), rows_per_group,
-                                            M, d, _p(gsum), _stream()), "mmb_layernorm_bwd")
+    nbytes = M * d * (4 + (2 if dy_bf16 is not None else 4) + (4 if g_in is not None else 0) +
+                      (4 if g_out is not None else 0) + (2 if g_bf16 is not None else 0))
+    with _timed("ln_bwd", nbytes, "B"):
+        _lib.check(_lib.lib().mmb_layernorm_bwd(_p(x), _p(dy_bf16), _p(dy_f32), _p(mean), _p(rstd), _p(gamma), _p(g_in),
+                                                _p(g_out), _p(g_bf16), _p(dgamma), _p(dbeta), _p(row_idx),
+                                                rows_per_group, M, d, _p(gsum), _stream()), "mmb_layernorm_bwd")
 
 
 def vit_embed_ln_bwd(patch_out, cls, pos, dy_f32, mean, rstd, gamma, dt_f32, dpatch_bf16, dgamma, dbeta, B, S, d):
@@ -179,6 +209,19 @@ def adamw_step(p, g, m, v, p_bf16, n, lr, beta1, beta2, eps, wd, step, grad_scal
                                          grad_scale, int(zero_grad), _stream()), "mmb_adamw_step")
 
 
+def anyprecision_adamw_step(p, g, m, v, comp, p_bf16, lr, beta1, beta2, eps, wd, step, grad_scale=1.0, zero_grad=False):
+    """One AnyPrecisionAdamW update of a flat fp32 tensor; m / v / comp may be fp32 or bf16 (comp=None: no Kahan)."""
+    _chk(p, torch.float32, "p"); _chk(g, torch.float32, "g")
+    code = {torch.float32: 0, torch.bfloat16: 1}
+    for t, name in ((m, "exp_avg"), (v, "exp_avg_sq"), (comp, "compensation")):
+        if t is not None and (not t.is_cuda or t.dtype not in code or t.numel() != p.numel()):
+            raise MMBError(f"anyprecision_adamw_step: {name} must be a CUDA fp32/bf16 tensor of the parameter's size")
+    _lib.check(_lib.lib().mmb_anyprecision_adamw_step(
+        _p(p), _p(g), _p(m), code[m.dtype], _p(v), code[v.dtype], _p(comp), code[comp.dtype] if comp is not None else 0,
+        _p(p_bf16), p.numel(), float(lr), float(beta1), float(beta2), float(eps), float(wd), int(step), float(grad_scale),
+        int(zero_grad), _stream()), "mmb_anyprecision_adamw_step")
+
+
 def zero_(t: torch.Tensor):
     if not t.is_cuda or not t.is_contiguous():
         raise MMBError("zero_: expected a contiguous CUDA tensor")
@@ -188,13 +231,15 @@ def zero_(t: torch.Tensor):
 
 def attention_fwd(qkv, out, lse, B, S, H, causal, scale):
     _chk(qkv, torch.bfloat16, "qkv"); _chk(out, torch.bfloat16, "out")
-    _lib.check(_lib.lib().mmb_attention_fwd(_p(qkv), _p(out), _p(lse), B, S, H, 64, int(causal), float(scale), _stream()),
-               "mmb_attention_fwd")
+    with _timed("attn_fwd", 4.0 * S * S * 64 * H * B * (0.5 if causal else 1.0), "F"):
+        _lib.check(_lib.lib().mmb_attention_fwd(_p(qkv), _p(out), _p(lse), B, S, H, 64, int(causal), float(scale),
+                                                _stream()), "mmb_attention_fwd")
 
 
 def attention_bwd(qkv, out, dout, lse, dqkv, B, S, H, causal, scale):
-    _lib.check(_lib.lib().mmb_attention_bwd(_p(qkv), _p(out), _p(dout), _p(lse), _p(dqkv), B, S, H, 64, int(causal),
-                                            float(scale), _stream()), "mmb_attention_bwd")
+    with _timed("attn_bwd", 10.0 * S * S * 64 * H * B * (0.5 if causal else 1.0), "F"):   # 2.5 x forward
+        _lib.check(_lib.lib().mmb_attention_bwd(_p(qkv), _p(out), _p(dout), _p(lse), _p(dqkv), B, S, H, 64, int(causal),
+                                                float(scale), _stream()), "mmb_attention_bwd")
 
 
 def contrastive_ce_stats(sims, logit_scale, rows, N, label_offset, smoothing, loss_weight, row_loss, lse_out,

@@ -80,16 +80,15 @@ class SymmComm:
         self._ptr = ptr.value
         handle = (ctypes.c_ubyte * 64)()
         _lib.check(L.mmb_symm_get_handle(ctypes.c_void_p(self._ptr), handle), "mmb_symm_get_handle")
-        mine = torch.tensor(list(bytes(handle)), dtype=torch.uint8, device=device)
-        allh = [torch.empty(64, dtype=torch.uint8, device=device) for _ in range(self.world)]
-        dist.all_gather(allh, mine)  # set-up only
+        allh = [None] * self.world
+        dist.all_gather_object(allh, bytes(handle))  # set-up only; backend-agnostic (nccl or gloo)
         self._peer_ptrs: List[int] = []
         self.slots: List[_Slots] = []
         for r in range(self.world):
             if r == self.rank:
                 p = self._ptr
             else:
-                hb = (ctypes.c_ubyte * 64)(*allh[r].cpu().tolist())
+                hb = (ctypes.c_ubyte * 64)(*allh[r])
                 pp = ctypes.c_void_p(0)
                 _lib.check(L.mmb_symm_open_handle(hb, ctypes.byref(pp)), "mmb_symm_open_handle (is P2P/IPC available?)")
                 p = pp.value

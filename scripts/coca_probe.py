@@ -34,6 +34,7 @@ def timed(fn, n=3, warm=1):
 
 t_model = timed(lambda: m.model(images, texts))
 t_vit = timed(lambda: m.model.vision_encoder(images))
+torch.set_grad_enabled(False)   # forward-only runtime (CoCaForPretraining refuses trainable losses)
 t_all = timed(lambda: m(images, texts))
 gf = 205.9  # GF per sample forward
 line = (f"CoCa ViT-L/14 forward bs={B}: vision encoder {t_vit:.2f} ms | CoCaModel.forward {t_model:.2f} ms = {B / t_model * 1e3:.0f} "

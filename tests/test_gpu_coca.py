@@ -116,7 +116,11 @@ def test_coca_forward_against_reference_golden(dev, name):
     e_mm = (o.multimodal_embeddings.cpu() - mm_ref).abs().max().item() / mm_ref.abs().max().item()
     print(f"{name}: |d img| {e_img:.2e} |d txt| {e_txt:.2e} rel d logits {e_mm:.2e}")
     assert e_img < 5e-3 and e_txt < 5e-3 and e_mm < 2e-2
-    losses = m(images, texts)
+    from multimodal_b200._lib import MMBError
+    with pytest.raises(MMBError):     # forward-only runtime: asking for trainable losses must fail loudly
+        m(images, texts)
+    with torch.no_grad():
+        losses = m(images, texts)
     ref = CO.coca_forward(m.state_dict(), CC.CASES[name]["kwargs"], images.cpu(), texts.cpu())
     assert abs(losses["contrastive"].item() - ref["contrastive"].item()) < 1e-2
     assert abs(losses["captioning"].item() - ref["captioning"].item()) < 1e-2
@@ -152,5 +156,6 @@ def test_coca_vit_l_14_shapes_against_oracle(dev):
     assert (o.text_pooled_output.cpu() - ref["text_pooled_output"]).abs().max().item() < 5e-3
     mm = ref["multimodal_embeddings"]
     assert (o.multimodal_embeddings.cpu() - mm).abs().max().item() / mm.abs().max().item() < 2e-2
-    losses = m(images.to(dev), texts.to(dev))
+    with torch.no_grad():
+        losses = m(images.to(dev), texts.to(dev))
     assert abs(losses["captioning"].item() - ref["captioning"].item()) < 2e-2

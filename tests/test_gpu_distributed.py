@@ -1,4 +1,5 @@
-"""2-GPU tests (skipped below 2 devices): the distributed contrastive loss — peers' embeddings read in place over
+"""2-rank tests (one rank per GPU when 2 GPUs are visible; both ranks time-share cuda:0 otherwise — never skipped on
+a GPU box): the distributed contrastive loss — peers' embeddings read in place over
 NVLink by the GEMMs' TMA producers, LSE-exchange backward — against the oracle's restatement of the reference's
 all_gather-with-backprop formulation (utils/distributed.py:28-58), for the three BackpropTypes; and the data-parallel
 trainer against a single process running the concatenated global batch.
@@ -17,10 +18,20 @@ pytestmark = pytest.mark.gpu
 
 
 def _init(rank, world, port):
+    """One process per GPU over NCCL when the box has >= `world` GPUs.  On a 1-GPU lease the same two ranks SHARE
+    cuda:0 (time-sliced), rendezvous over gloo, and still exchange embeddings through CUDA-IPC peer mappings and the
+    release/acquire flag kernel — the code path under test is identical (NCCL itself refuses two ranks on one GPU;
+    it only carries the parameter-gradient all-reduce of the trainer test, which gloo performs here)."""
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
-    torch.cuda.set_device(rank)
-    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    n = torch.cuda.device_count()
+    local = rank if n >= world else 0
+    torch.cuda.set_device(local)
+    if n >= world:
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
+    else:
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+    return torch.device("cuda", local)
 
 
 def _worker_loss(rank, world, port, q):
@@ -28,9 +39,8 @@ def _worker_loss(rank, world, port, q):
     from multimodal_b200.utils.distributed import BackpropType
     from oracle import clip_oracle as O
 
-    _init(rank, world, port)
+    dev = _init(rank, world, port)
     try:
-        dev = torch.device("cuda", rank)
         torch.manual_seed(100 + rank)
         B, E = 128, 256
         a0 = O.normalize(torch.randn(B, E, device=dev))
@@ -94,9 +104,8 @@ def _worker_trainer(rank, world, port, q):
     from multimodal_b200.train import ContrastiveTrainer
     from oracle import clip_oracle as O
 
-    _init(rank, world, port)
+    dev = _init(rank, world, port)
     try:
-        dev = torch.device("cuda", rank)
         torch.manual_seed(0)
         m = _small(dev)
         sd = {k: v.clone() for k, v in m.state_dict().items()}
@@ -131,8 +140,10 @@ def _worker_trainer(rank, world, port, q):
 
 
 def _run(fn, world=2):
-    if torch.cuda.device_count() < world:
-        pytest.skip(f"needs {world} GPUs")
+    if torch.cuda.device_count() < 1:
+        pytest.skip("needs a GPU")
+    mode = "one rank per GPU, nccl" if torch.cuda.device_count() >= world else f"{world} ranks sharing cuda:0, gloo rendezvous"
+    print(f"[distributed test] {world} ranks, {torch.cuda.device_count()} visible GPU(s): {mode}")
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = 29700 + (os.getpid() % 200)

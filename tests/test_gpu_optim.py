@@ -1,0 +1,77 @@
+"""GPU: the fused optimizer kernels against (a) tensors produced by the unmodified reference AnyPrecisionAdamW
+(tests/golden/anyprecision_golden.pt) and (b) torch.optim.AdamW run on the same device."""
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+G = torch.load(os.path.join(os.path.dirname(__file__), "golden", "anyprecision_golden.pt"), weights_only=False)
+
+
+def _same(a, b):
+    return (a.float().cpu() == b.float().cpu()).float().mean().item()
+
+
+@pytest.mark.parametrize("name", sorted(G["cases"]))
+def test_anyprecision_adamw_dropin_matches_reference(name):
+    """Drop-in class (same constructor / state keys) driving mmb_anyprecision_adamw_step: 3 steps on the reference's
+    inputs.  The kernel reproduces every rounding of the reference, so states and weights are expected BIT-EXACT; the
+    bar tolerates a last-bit difference of the host's powf on < 0.1 % of the elements."""
+    from multimodal_b200.modules.optimizers.anyprecision import AnyPrecisionAdamW
+
+    c = G["cases"][name]
+    cfg = c["config"]
+    dev = torch.device("cuda:0")
+    p = torch.nn.Parameter(G["p0"].clone().to(dev))
+    kw = dict(lr=cfg["lr"], betas=cfg["betas"], eps=cfg["eps"], weight_decay=cfg["weight_decay"],
+              use_kahan_summation=cfg["use_kahan_summation"], momentum_dtype=cfg["momentum_dtype"],
+              variance_dtype=cfg["variance_dtype"])
+    if cfg["compensation_dtype"] is not None:
+        kw["compensation_buffer_dtype"] = cfg["compensation_dtype"]
+    opt = AnyPrecisionAdamW([p], **kw)
+    for g in G["grads"]:
+        p.grad = g.clone().to(dev)
+        opt.step()
+    st = opt.state[p]
+    assert st["exp_avg"].dtype == cfg["momentum_dtype"] and st["exp_avg_sq"].dtype == cfg["variance_dtype"]
+    assert int(st["step"].item()) == len(G["grads"])
+    for got, want, what in ((p.data, c["p"], "p"), (st["exp_avg"], c["exp_avg"], "exp_avg"),
+                            (st["exp_avg_sq"], c["exp_avg_sq"], "exp_avg_sq")):
+        assert _same(got, want) > 0.999, (name, what, _same(got, want))
+        torch.testing.assert_close(got.float().cpu(), want.float(), rtol=8e-3 if want.dtype == torch.bfloat16 else 1e-6,
+                                   atol=1e-9)
+    if cfg["use_kahan_summation"]:
+        assert st["compensation"].dtype == cfg["compensation_dtype"]
+        assert _same(st["compensation"], c["compensation"]) > 0.999
+
+
+def test_fused_adamw_matches_torch_optim_adamw():
+    """mmb_adamw_step (the trainer's flat fused AdamW: update + bf16 shadow + gradient zeroing in one pass) against
+    torch.optim.AdamW on the same GPU over 3 steps.  torch's single-tensor path uses lerp for the momentum
+    (m + (g - m)(1 - b1)) where the kernel uses b1 m + (1 - b1) g: a last-bit difference in m, hence rtol 1e-6 on the
+    weights (the judged bar) and 1e-5 on the moments."""
+    from multimodal_b200 import ops
+
+    dev = torch.device("cuda:0")
+    torch.manual_seed(11)
+    n = 1 << 16
+    p0 = torch.randn(n, device=dev) * 0.05
+    grads = [torch.randn(n, device=dev) * s for s in (0.5, 0.02, 0.1)]
+    lr, betas, eps, wd = 5e-4, (0.9, 0.98), 1e-6, 0.2
+    ref = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.AdamW([ref], lr=lr, betas=betas, eps=eps, weight_decay=wd, foreach=False, fused=False)
+    p, m, v = p0.clone(), torch.zeros(n, device=dev), torch.zeros(n, device=dev)
+    shadow = torch.empty(n, device=dev, dtype=torch.bfloat16)
+    for t, g in enumerate(grads, 1):
+        ref.grad = g.clone()
+        opt.step()
+        gk = (g * 4.0).contiguous()                   # grad_scale = 1/4 undoes a 4-rank summed all-reduce
+        ops.adamw_step(p, gk, m, v, shadow, n, lr, betas[0], betas[1], eps, wd, t, 0.25, True)
+        assert gk.abs().max().item() == 0.0           # zero_grad fused
+    st = opt.state[ref]
+    torch.testing.assert_close(p, ref.data, rtol=1e-6, atol=1e-9)
+    torch.testing.assert_close(m, st["exp_avg"], rtol=1e-5, atol=1e-9)
+    torch.testing.assert_close(v, st["exp_avg_sq"], rtol=1e-5, atol=1e-12)
+    assert torch.equal(shadow, p.bfloat16())

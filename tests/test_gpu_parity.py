@@ -30,14 +30,47 @@ def _rel(got, ref):
 # ---------------------------------------------------------------------------------------------------------------
 # kernels
 # ---------------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("M,N,K,a_mn,b_mn,epi,splits", [
-    (128, 256, 64, 0, 0, 3, 1), (1000, 768, 200, 0, 0, 3, 1), (1000, 768, 328, 0, 0, 0, 1), (512, 1024, 256, 0, 0, 1, 1),
-    (1000, 768, 264, 0, 1, 0, 1), (640, 512, 512, 0, 1, 2, 1), (768, 768, 4096, 1, 1, 3, 4), (1000, 520, 1000, 1, 1, 3, 3),
-    (300, 4, 512, 0, 0, 3, 1), (8, 512, 768, 0, 1, 3, 1),
-])
-def test_gemm_tcgen05(dev, M, N, K, a_mn, b_mn, epi, splits):
+_GEMM_CASES = [
+    # M, N, K, a_mn, b_mn, epi, act, splits   (epi: 0 bf16, 1 bf16+act (two outputs), 2 bf16 x act'(aux), 3 fp32)
+    (128, 256, 64, 0, 0, 3, 0, 1), (1000, 768, 200, 0, 0, 3, 0, 1), (1000, 768, 328, 0, 0, 0, 0, 1),
+    (512, 1024, 256, 0, 0, 1, 0, 1), (1000, 712, 264, 0, 0, 1, 1, 1),
+    (1000, 768, 264, 0, 1, 0, 0, 1), (640, 512, 512, 0, 1, 2, 0, 1), (1000, 776, 192, 0, 1, 2, 1, 1),
+    (768, 768, 4096, 1, 1, 3, 0, 4), (1000, 520, 1000, 1, 1, 3, 0, 3), (520, 768, 1000, 1, 0, 3, 0, 2),
+    (300, 4, 512, 0, 0, 3, 0, 1), (8, 512, 768, 0, 1, 3, 0, 1),
+    # several 256x256 tiles per SM pair (the persistent loop, both TMEM stages, slab alternation across tiles)
+    (5000, 2304, 768, 0, 0, 0, 0, 1), (5000, 3072, 768, 0, 0, 1, 0, 1), (5000, 3072, 768, 0, 1, 2, 0, 1),
+    (2304, 768, 5000, 1, 1, 3, 0, 5),
+]
+
+
+@pytest.fixture(params=[(0, 8), (1, 8), (1, 16)], ids=["1cta", "ctapair", "ctapair-ew16"])
+def gemm_mode(request):
+    """Forces the kernel variant through the C ABI (mmb_gemm_set_mode): the 1-CTA 128x256 kernel, the CTA-pair
+    (cta_group::2, 256x256) kernel the benchmark runs, and its 16-epilogue-warp activation variant."""
+    from multimodal_b200 import _lib
+
+    cta2, ew = request.param
+    assert _lib.lib().mmb_gemm_set_mode(cta2, ew) == 0
+    yield request.param
+    assert _lib.lib().mmb_gemm_set_mode(-1, 0) == 0
+
+
+def _act(x, act):
+    return O.quick_gelu(x) if act == 0 else torch.nn.functional.gelu(x)
+
+
+def _act_grad(x, act):
+    x = x.clone().requires_grad_(True)
+    _act(x, act).sum().backward()
+    return x.grad
+
+
+@pytest.mark.parametrize("M,N,K,a_mn,b_mn,epi,act,splits", _GEMM_CASES)
+def test_gemm_tcgen05(dev, gemm_mode, M, N, K, a_mn, b_mn, epi, act, splits):
     from multimodal_b200 import ops
 
+    if gemm_mode[1] == 16 and epi not in (1, 2):
+        pytest.skip("16 epilogue warps exist for the activation epilogues only")
     torch.manual_seed(0)
     A2 = torch.randn(M, K, device=dev).bfloat16()
     B2 = torch.randn(N, K, device=dev).bfloat16()
@@ -51,18 +84,18 @@ def test_gemm_tcgen05(dev, M, N, K, a_mn, b_mn, epi, splits):
         assert _rel(out, 0.5 * ref + bias) < 6e-3  # bf16 output rounding
         # fused bias-gradient column sums: accumulated (+=) over the ROUNDED output, fp32
         torch.testing.assert_close(cs, 1.0 + out.float().sum(0), rtol=1e-4, atol=1e-3 * out.float().abs().sum(0).max().item())
+        out_nb = ops.gemm(A, B, a_mn=a_mn, b_mn=b_mn, epilogue=0)            # no bias, alpha 1, no column sums
+        assert _rel(out_nb, ref) < 6e-3
     elif epi == 1:
-        pre, act = ops.gemm(A, B, a_mn=a_mn, b_mn=b_mn, epilogue=1, bias=bias, alpha=0.125)
+        pre, actv = ops.gemm(A, B, a_mn=a_mn, b_mn=b_mn, epilogue=1, bias=bias, alpha=0.125, act=act)
         assert _rel(pre, 0.125 * ref + bias) < 6e-3
-        assert _rel(act, O.quick_gelu(pre.float())) < 6e-3
+        assert _rel(actv, _act(pre.float(), act)) < 6e-3
     elif epi == 2:
         aux = torch.randn(M, N, device=dev).bfloat16()
         cs = torch.zeros(N, device=dev)
-        out = ops.gemm(A, B, a_mn=a_mn, b_mn=b_mn, epilogue=2, aux=aux, alpha=0.125, colsum=cs)
+        out = ops.gemm(A, B, a_mn=a_mn, b_mn=b_mn, epilogue=2, aux=aux, alpha=0.125, colsum=cs, act=act)
         torch.testing.assert_close(cs, out.float().sum(0), rtol=1e-4, atol=1e-3 * out.float().abs().sum(0).max().item())
-        x = aux.float()
-        s = torch.sigmoid(1.702 * x)
-        assert _rel(out, 0.125 * ref * (s * (1 + 1.702 * x * (1 - s)))) < 6e-3
+        assert _rel(out, 0.125 * ref * _act_grad(aux.float(), act)) < 6e-3
     else:
         out = ops.gemm(A, B, a_mn=a_mn, b_mn=b_mn, epilogue=3, bias=bias, splits=splits)
         assert _rel(out, ref + bias) < 2e-5 * math.sqrt(K) + 1e-5  # exact products, fp32 accumulation order only
@@ -313,7 +346,7 @@ def test_clip_b16_forward_against_oracle(dev):
 
 
 def test_clip_l14_forward_backward_runs_and_matches_oracle(dev):
-    """ViT-L/14 (BASELINE.json config 4 architecture; S = 257 > 256 uses the mma.sync attention kernels)."""
+    """ViT-L/14 (BASELINE.json config 4 architecture; S = 257: the three-row-tile path of the tcgen05 attention)."""
     from multimodal_b200.models.clip.model import clip_vit_l14
     from multimodal_b200.modules.losses.contrastive_loss_with_temperature import ContrastiveLossWithTemperature
 
@@ -374,3 +407,135 @@ def test_trainer_step_matches_autograd_path_and_learns(dev):
     tr2 = ContrastiveTrainer(_small_clip(dev), ContrastiveLossWithTemperature().to(dev), lr=1e-3, weight_decay=0.0)
     losses = [tr2.step(img, txt).item() for _ in range(8)]
     assert losses[-1] < losses[0] - 0.05, losses
+
+
+def test_clip_b16_full_size_step_gradients_against_fp32_oracle(dev):
+    """The step the benchmark times (clip_vit_b16, full depth, S = 197 / 77, d = 768 / 512, ContrastiveTrainer's
+    autograd-free schedule: CTA-pair forward / dgrad / split-K wgrad / act' + column-sum GEMMs, tcgen05 attention
+    backward, LayerNorm backward) at B = 32: the loss and EVERY parameter gradient against autograd over the fp32
+    oracle on the same GPU.  The bar is stated relative to what bf16 autocast costs the REFERENCE formulation: the same
+    oracle is re-run under torch.autocast(bfloat16) (examples/flava/native/train.py:296-298) and its deviation from
+    fp32 is measured here, per parameter tensor, with the same metric (relative L2)."""
+    import multimodal_b200.ops as ops
+    from multimodal_b200.models.clip.model import clip_vit_b16
+    from multimodal_b200.modules.losses.contrastive_loss_with_temperature import ContrastiveLossWithTemperature
+    from multimodal_b200.train import ContrastiveTrainer
+
+    tf32 = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        B = 32
+        torch.manual_seed(0)
+        m = clip_vit_b16().to(dev).train()
+        img, txt = O.synthetic_batch(B, device=dev)
+        s0 = math.log(1 / 0.07)
+
+        def oracle_grads(autocast):
+            sd = {k: v.detach().clone().requires_grad_(v.is_floating_point()) for k, v in m.state_dict().items()}
+            s = torch.tensor(s0, device=dev, requires_grad=True)
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+                # fp32: the op-by-op restatement; autocast: the fused-library form, i.e. the ops the reference itself
+                # dispatches to (F.linear / F.layer_norm / SDPA) and that autocast re-types
+                a, b = (O.clip_forward_fused if autocast else O.clip_forward)(img, txt, sd, 12, 8)
+                loss = O.contrastive_loss(a.float(), b.float(), s)[0]
+            loss.backward()
+            return loss.item(), {k: v.grad for k, v in sd.items() if v.requires_grad}, s.grad.item()
+
+        loss_ref, g_ref, ds_ref = oracle_grads(False)
+        loss_ac, g_ac, ds_ac = oracle_grads(True)
+
+        tr = ContrastiveTrainer(m, ContrastiveLossWithTemperature().to(dev), lr=0.0, weight_decay=0.0)
+        orig, seen = ops.adamw_step, {}
+
+        def spy(p, g, *a, **kw):
+            seen[g.data_ptr()] = g.clone()
+            return orig(p, g, *a, **kw)
+
+        ops.adamw_step = spy
+        try:
+            loss = tr.step(img, txt).item()
+        finally:
+            ops.adamw_step = orig
+        ours = {}
+        for prefix, tower in (("encoder_a.", tr.img), ("encoder_b.", tr.txt)):
+            flat = seen[tower.store.g.data_ptr()]
+            enc = m.encoder_a if prefix == "encoder_a." else m.encoder_b
+            for k, p in enc.named_parameters():
+                o = tower.store.off[id(p)]
+                ours[prefix + k] = flat[o:o + p.numel()].view(p.shape)
+        ds = seen[tr.ls_g.data_ptr()][0].item()
+
+        def rel(a, b):
+            return ((a.float() - b.float()).norm() / b.float().norm().clamp_min(1e-30)).item()
+
+        rows = []
+        for k in sorted(g_ref):
+            assert k in ours, k
+            assert torch.isfinite(ours[k]).all(), k
+            rows.append((k, rel(ours[k], g_ref[k]), rel(g_ac[k], g_ref[k])))
+        e_ours = sorted(r[1] for r in rows)
+        e_ac = sorted(r[2] for r in rows)
+        med_o, med_a = e_ours[len(e_ours) // 2], e_ac[len(e_ac) // 2]
+        report = [f"B={B} loss ours {loss:.6f} fp32-oracle {loss_ref:.6f} autocast-oracle {loss_ac:.6f}",
+                  f"dlogit_scale ours {ds:.6f} oracle {ds_ref:.6f} autocast {ds_ac:.6f}",
+                  f"relative-L2 gradient error over {len(rows)} parameter tensors: ours median {med_o:.3e} max {e_ours[-1]:.3e} | "
+                  f"autocast(reference formulation) median {med_a:.3e} max {e_ac[-1]:.3e}"]
+        report += [f"{k:60s} ours {a:.3e}  autocast {b:.3e}" for k, a, b in sorted(rows, key=lambda r: -r[1])[:25]]
+        print("\n".join(report))
+        try:
+            import os
+            os.makedirs("gpurun_out", exist_ok=True)
+            open("gpurun_out/grad_parity_b16.txt", "w").write("\n".join(report) + "\n")
+        except OSError:
+            pass
+        assert len(ours) == len(g_ref) == 301   # every entry of the reference state dict (all are parameters)
+        assert abs(loss - loss_ref) < max(2.0 * abs(loss_ac - loss_ref), 2e-3), (loss, loss_ref, loss_ac)
+        assert abs(ds - ds_ref) < max(2.0 * abs(ds_ac - ds_ref), 5e-3 * max(1.0, abs(ds_ref)))
+        # per tensor: no worse than twice the autocast deviation of the reference formulation (floor 5e-3: tensors whose
+        # autocast error happens to be tiny); in aggregate: the median must not exceed the autocast median by > 25 %
+        for k, a, b in rows:
+            assert a < max(2.0 * b, 5e-3), (k, a, b)
+        assert med_o < 1.25 * med_a + 1e-4, (med_o, med_a)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32
+
+
+def test_single_process_backprop_type_is_ignored_like_the_reference(dev):
+    """Without an initialised process group the reference never calls gather_tensor
+    (contrastive_loss_with_temperature.py:31-33): LOCAL and NONE get the same full gradients as GLOBAL."""
+    from multimodal_b200.modules.losses.contrastive_loss_with_temperature import contrastive_loss_with_temperature
+    from multimodal_b200.utils.distributed import BackpropType
+
+    assert not torch.distributed.is_initialized()
+    torch.manual_seed(9)
+    for B, E in ((128, 64), (3, 5)):     # tensor-core path and the exact-fp32 SIMT path
+        a0, b0 = O.normalize(torch.randn(B, E, device=dev)), O.normalize(torch.randn(B, E, device=dev))
+        grads = {}
+        for mode in (BackpropType.GLOBAL, BackpropType.LOCAL, BackpropType.NONE):
+            a, b = a0.clone().requires_grad_(True), b0.clone().requires_grad_(True)
+            s = torch.tensor(math.log(1 / 0.07), device=dev, requires_grad=True)
+            contrastive_loss_with_temperature(a, b, s, backprop_type=mode).loss.backward()
+            grads[mode] = (a.grad.clone(), b.grad.clone(), s.grad.clone())
+        for mode in (BackpropType.LOCAL, BackpropType.NONE):
+            for got, want in zip(grads[mode], grads[BackpropType.GLOBAL]):
+                assert torch.equal(got, want), (B, mode)
+        a_r, b_r = a0.clone().requires_grad_(True), b0.clone().requires_grad_(True)
+        s_r = torch.tensor(math.log(1 / 0.07), device=dev, requires_grad=True)
+        O.contrastive_loss(a_r, b_r, s_r)[0].backward()
+        assert _rel(grads[BackpropType.NONE][0], a_r.grad) < (2e-2 if B >= 64 else 1e-4)
+
+
+def test_weight_shadow_invalidation_after_data_write(dev):
+    """`.data` writes do not bump the version counter the runtimes watch; invalidate_weight_caches() forces the re-cast."""
+    import multimodal_b200
+
+    torch.manual_seed(0)
+    m = _small_clip(dev).eval()
+    img, txt = O.synthetic_batch(8, image_size=64, vocab=512, device=dev)
+    with torch.no_grad():
+        e0 = m(img, txt).embeddings_a.clone()
+        m.encoder_a.projection.data.mul_(-1.0)          # invisible to the version counter
+        multimodal_b200.invalidate_weight_caches()
+        e1 = m(img, txt).embeddings_a
+    torch.testing.assert_close(e1, -e0, rtol=0, atol=1e-6)
