@@ -26,6 +26,17 @@ sys.path.insert(0, ROOT)
 F_FWD_B16 = 35.127e9 + 5.887e9
 F_STEP_B16 = 3.0 * F_FWD_B16
 METRIC = "image-text pairs/sec (CLIP ViT-B/16 contrastive pretrain step, bs=1024/GPU)"
+# BASELINE.json configs[3] (a parity / capability case, not the headline line): CLIP ViT-L/14, 4096 pairs per GPU
+# (global 32 768 on 8 GPUs), two-pass activation recompute in micro-batches.  SURVEY.md §8d: 175.22 GF forward per pair.
+F_STEP_L14 = 3.0 * (162.03e9 + 13.19e9)
+CONFIGS = {
+    "b16": {"builder": "clip_vit_b16", "f_step": F_STEP_B16, "batch": 1024, "micro_batch": None, "metric": METRIC,
+            "workload": "CLIP ViT-B/16 contrastive pretrain step (fwd+loss+bwd+grad-allreduce+AdamW)"},
+    "l14": {"builder": "clip_vit_l14", "f_step": F_STEP_L14, "batch": 4096, "micro_batch": 256,
+            "metric": "image-text pairs/sec (CLIP ViT-L/14 contrastive pretrain step, bs=4096/GPU, global 32768 on 8 GPUs)",
+            "workload": "CLIP ViT-L/14 contrastive pretrain step (two-pass recompute in micro-batches of 256: "
+                        "no-save forward of all slices -> global loss -> re-forward+backward per slice; +grad-allreduce+AdamW)"},
+}
 
 
 def parse():
@@ -34,7 +45,10 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "torch-eager-gpu"])
-    ap.add_argument("--batch", type=int, default=1024, help="per-GPU batch (default = the BASELINE.json config)")
+    ap.add_argument("--config", default="b16", choices=sorted(CONFIGS),
+                    help="b16 = the headline BASELINE.json configs[1]; l14 = configs[3] (ViT-L/14, 4096/GPU, recompute)")
+    ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (default = the config's)")
+    ap.add_argument("--micro-batch", type=int, default=None, help="recompute slice size (default = the config's)")
     ap.add_argument("--cpu-batch", type=int, default=4, help="sample size of the CPU reference/port legs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eager-baseline", action="store_true",
@@ -206,12 +220,12 @@ def run_torch_eager(args):
         return
     dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
     torch.cuda.set_device(dev)
-    r = torch_eager_gpu_run(args.batch, args.steps, args.warmup, dev)
+    r = torch_eager_gpu_run(args.batch or 1024, args.steps, args.warmup, dev)
     print(json.dumps({"impl": "torch-eager-gpu", "metric": METRIC, "value": r["value"], "unit": "pairs/s", "n_gpus": 1,
                       "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
                       "dtype": "bf16 autocast", "data": "synthetic",
                       "config": {"workload": "CLIP ViT-B/16 contrastive pretrain step, stock PyTorch eager on the same B200",
-                                 "per_gpu_batch": r["per_gpu_batch"], "requested_batch": args.batch}, "detail": r}))
+                                 "per_gpu_batch": r["per_gpu_batch"], "requested_batch": args.batch or 1024}, "detail": r}))
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -281,7 +295,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
 
     from multimodal_b200 import _lib, ops
-    from multimodal_b200.models.clip.model import clip_vit_b16
+    from multimodal_b200.models.clip import model as clip_models
     from multimodal_b200.modules.losses.contrastive_loss_with_temperature import ContrastiveLossWithTemperature
     from multimodal_b200.train import ContrastiveTrainer
     from oracle import clip_oracle as O  # only for the synthetic-input generator + the bounded cpu_baseline leg
@@ -295,9 +309,14 @@ def run_ours(args):
                 time.sleep(2)
             time.sleep(2)
     _lib.lib()  # fail loudly right away if the CUDA library is missing
-    B = args.batch
+    cfg = CONFIGS[args.config]
+    B = args.batch or cfg["batch"]
+    MB = args.micro_batch or cfg["micro_batch"]
+    if MB is not None and MB >= B:
+        MB = None
+    F_STEP = cfg["f_step"]
     torch.manual_seed(0)
-    model = clip_vit_b16().to(dev)
+    model = getattr(clip_models, cfg["builder"])().to(dev)
     loss_mod = ContrastiveLossWithTemperature().to(dev)
     trainer = ContrastiveTrainer(model, loss_mod)
 
@@ -320,7 +339,7 @@ def run_ours(args):
 
     # ---- warm-up (allocations, first-touch, clocks) ----
     for _ in range(max(args.warmup, 3)):
-        loss = trainer.step(img_d, txt_d)
+        loss = trainer.step(img_d, txt_d, micro_batch=MB)
     barrier()
 
     # ---- timed: device-resident inputs (no per-launch instrumentation inside this region) ----
@@ -332,7 +351,7 @@ def run_ours(args):
     barrier()
     e0.record()
     for _ in range(args.steps):
-        loss = trainer.step(img_d, txt_d)
+        loss = trainer.step(img_d, txt_d, micro_batch=MB)
     e1.record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
@@ -348,7 +367,7 @@ def run_ours(args):
     i0, i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     i0.record()
     for _ in range(INSTR_STEPS):
-        trainer.step(img_d, txt_d)
+        trainer.step(img_d, txt_d, micro_batch=MB)
     i1.record()
     barrier()
     ms_instr = i0.elapsed_time(i1) / INSTR_STEPS
@@ -386,7 +405,7 @@ def run_ours(args):
     t0.record()
     from multimodal_b200.train import HostPrefetcher
     for xi, xt in HostPrefetcher(((img_h, txt_h) for _ in range(args.steps)), dev):  # every H2D copy is inside t0..t1
-        l_host = float(trainer.step(xi, xt).item())                                   # D2H of the loss every step
+        l_host = float(trainer.step(xi, xt, micro_batch=MB).item())                   # D2H of the loss every step
     t1.record()
     barrier()
     ms_e2e = max_over_ranks(t0.elapsed_time(t1) / args.steps)
@@ -398,7 +417,7 @@ def run_ours(args):
 
     value = B * world / (ms_dev * 1e-3)
     e2e_val = B * world / (ms_e2e * 1e-3)
-    step_tf = value * F_STEP_B16 / 1e12 / world
+    step_tf = value * F_STEP / 1e12 / world
     burst_tf = None
     try:
         burst_tf = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"])
@@ -415,10 +434,10 @@ def run_ours(args):
     except Exception:  # noqa: BLE001
         pass
     out = {
-        "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "metric": cfg["metric"], "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic",
-        "config": {"workload": "CLIP ViT-B/16 contrastive pretrain step (fwd+loss+bwd+grad-allreduce+AdamW)",
+        "config": {"workload": cfg["workload"], "name": args.config, "micro_batch": MB,
                    "per_gpu_batch": B, "global_batch": B * world, "image": "224x224x3 fp32", "text_len": 77,
                    "parallelism": f"dp{world}", "l2": "activations (~84 GB/step) and inputs (616 MB) exceed the 126 MB L2; no flush needed",
                    "final_loss": final_loss},
@@ -431,7 +450,8 @@ def run_ours(args):
         "roofline": {"bound": "tensor", "achieved": step_tf, "peak": peak_tf, "unit": "TFLOP/s",
                      "frac": step_tf / peak_tf if peak_tf else None,
                      "frac_of_burst_peak": step_tf / burst_tf if burst_tf else None,
-                     "definition": "pairs/s/GPU x 123.04 GF (3 x forward GEMM+attention FLOPs) / measured sustained bf16 peak",
+                     "definition": f"pairs/s/GPU x {F_STEP / 1e9:.2f} GF (3 x forward GEMM+attention FLOPs, SURVEY.md §8d; a "
+                                   "recompute pass is NOT counted as useful work) / measured sustained bf16 peak",
                      "peak_source": peak_src,
                      "traffic": traffic, "traffic_launch": traffic_src,
                      "dominant_kernel": "mmb::gemm_kernel (tcgen05, all instantiations)",
@@ -441,7 +461,7 @@ def run_ours(args):
                      "gemm_by_kind": {k: {"tflops": v[0] / (v[1] * 1e-3) / 1e12, "ms_per_step": v[1] / INSTR_STEPS,
                                           "n": v[2] // INSTR_STEPS} for k, v in by_kind.items()}},
     }
-    if world == 1 and not args.no_eager_baseline:
+    if world == 1 and not args.no_eager_baseline and args.config == "b16":
         # info-only: stock PyTorch eager bf16-autocast on the same GPU, same batch (needs the trainer's memory back)
         try:
             del trainer, model, loss_mod
@@ -451,7 +471,7 @@ def run_ours(args):
             out["gpu_eager_baseline"] = torch_eager_gpu_run(B, 3, 2, dev)
         except Exception as e:  # noqa: BLE001 — never lose the line to the info leg
             out["gpu_eager_baseline"] = {"error": f"{type(e).__name__}: {str(e)[:160]}"}
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and args.config == "b16":
         val, dt, cores, done = cpu_port_run(3, 1, args.cpu_batch, budget_s=20.0)
         out["cpu_baseline"] = {"value": val, "unit": "pairs/s", "cores": cores, "kind": "port",
                                "sample": f"{args.cpu_batch} pairs/step x {done} steps (fwd+loss+bwd+SGD), fp32 eager oracle port"}

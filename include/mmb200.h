@@ -51,6 +51,31 @@ int mmb_gemm_bf16(const void* A, long long lda, int a_mn_major, const void* B, l
  * No reference counterpart: it exists so the parity tests can drive both kernels over every operand / epilogue case. */
 int mmb_gemm_set_mode(int cta2, int epilogue_warps);
 
+/* ---- fused similarity GEMM + temperature-scaled cross-entropy: the logits never reach HBM ---------------------------
+ * Replaces `torch.matmul(a, b_all.T) * exp(logit_scale)` + `F.cross_entropy` of
+ * modules/losses/contrastive_loss_with_temperature.py:90-107 (and serves any Linear -> CrossEntropy head).
+ * A [M,K], B [N,K] bf16 row-major; logits[m,n] = exp(*log_scale) * sum_k A[m,k] B[n,k] live in TMEM / registers only.
+ *
+ * mmb_gemm_ce_stats: online-softmax statistics.  For every row m and every 128-column part of this launch it writes one
+ *   float4 {max, sum e^(x-max), sum e^(x-max) x, sum x} into part[m * part_ld + part0 + ...] (mmb_gemm_ce_num_parts(N)
+ *   entries per row and launch), and xlabel[m] = logits[m, label0 + m] when that column exists in this launch.  Several
+ *   launches (one per peer GPU's column block, B read in place from the peer's buffer) fill disjoint part ranges.
+ * mmb_ce_stats_reduce: combines a row's parts into lse_out[m], row_loss[m] (label smoothing, optional masked-mean row
+ *   weights) and accumulates loss_weight * d(mean loss)/d(log_scale) into dscale_accum.
+ * mmb_gemm_ce_grad: recomputes the logits tile and writes d(loss_weight * mean CE)/d(sims) in bf16 (the operand of the
+ *   embedding-gradient GEMMs); columns [col_lo, col_hi) additionally receive the other direction's transposed term
+ *   rebuilt from lse_col (GLOBAL / LOCAL backprop without a reduce-scatter). */
+int mmb_gemm_ce_num_parts(int N);
+int mmb_gemm_ce_stats(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K,
+                      const float* log_scale, int label0, void* part, int part_ld, int part0, float* xlabel, void* stream);
+int mmb_ce_stats_reduce(const void* part, int part_ld, int n_parts, const float* xlabel, int rows, int n_total,
+                        float label_smoothing, float loss_weight, const float* row_w, float* row_loss, float* lse_out,
+                        float* dscale_accum, void* stream);
+int mmb_gemm_ce_grad(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K,
+                     const float* log_scale, int label0, int n_total, int rows_total, float label_smoothing,
+                     float loss_weight, const float* lse_row, const float* row_w, const float* lse_col,
+                     const float* col_w, int col_lo, int col_hi, void* dsims_bf16, long long ldd, void* stream);
+
 
 /* ---- HBM-bound kernels ------------------------------------------------------------------------------------ */
 

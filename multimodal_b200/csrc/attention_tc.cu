@@ -234,6 +234,258 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
 }
 
 // ------------------------------------------------------------------------------------------------
+// Forward, persistent PING-PONG version (round 2; default for S_pad <= 256).  One CTA per SM loops over
+// (batch, head, 128-query tile) work items; two tile buffers (smem operands + a 256-column TMEM score block each) are
+// in flight, each served by its own group of four worker warps:
+//   * producer warp: TMA loads of Q / K / V of tile n+2 start as soon as the PV MMA of tile n has left the buffer;
+//   * MMA warp: S_n = Q K^T, then — while group n&1 runs the softmax of tile n — S_{n+1}, then O_n = P_n V_n ...;
+//   * worker group g = n & 1: ONE THREAD PER QUERY ROW owning the whole row (no cross-thread max / sum exchange, no
+//     __syncthreads): pass 1 row maximum, pass 2 exp / row sum / bf16 P into the swizzled smem operand (aliasing Q | K),
+//     software-pipelined tcgen05.ld (chunk c+1 in flight while chunk c is reduced); epilogue O / l and the LSE.
+// The round-1 kernel (one tile per CTA, two CTAs per SM) exposed a serial chain per tile — TMA latency, MMA, pass 1,
+// __syncthreads, pass 2, __syncthreads, MMA, epilogue: 5.9 k clocks per tile per SM against a MUFU floor of 1.7 k — and
+// computed exp() for the padding rows of the last tile (59 of 128 rows at S = 197); rows >= S are skipped here.
+// TMEM: score block i at columns [256 i, 256 i + S_pad); O_i reuses columns [256 i, 256 i + 64).
+// ------------------------------------------------------------------------------------------------
+constexpr int FPP_WORKERS = 8;                      // two groups of four warps
+constexpr int FPP_THREADS = (FPP_WORKERS + 4) * 32; // + producer + MMA + 2 idle warps (register allocation is per 4 warps)
+constexpr int FPP_BUF = 6 * ATOM;                   // [P (4 atoms) aliasing Q (atom 0) | K (atoms 1-2)] + V (2 atoms)
+template <bool CAUSAL>
+__global__ void __launch_bounds__(FPP_THREADS, 1)
+attn_fwd_pp_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant__ CUtensorMap tmPad,
+                   const AttnTcArgs p, const int n_work) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sMaskAll = smem + 2 * FPP_BUF;                               // [2][256] key mask (kmask variant only)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sMaskAll + 512);
+  uint64_t* qk_full = bars;          // [2] Q, K landed                         producer (TMA) -> MMA warp
+  uint64_t* v_full = bars + 2;       // [2] V landed                            producer (TMA) -> MMA warp
+  uint64_t* buf_empty = bars + 4;    // [2] PV MMA complete: smem buffer free   MMA warp       -> producer
+  uint64_t* s_full = bars + 6;       // [2] S in TMEM                           MMA warp       -> worker group
+  uint64_t* p_full = bars + 8;       // [2] P in smem (4 warps)                 worker group   -> MMA warp
+  uint64_t* o_full = bars + 10;      // [2] O in TMEM                           MMA warp       -> worker group
+  uint64_t* t_empty = bars + 12;     // [2] O read out of TMEM (4 warps)        worker group   -> MMA warp
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int S = p.S, S_pad = p.S_pad, d = p.H * 64;
+  const int ntile = (S + 127) >> 7;
+  const bool has_mask = p.kmask != nullptr;
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tm128);
+    tma_prefetch_desc(&tmPad);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&qk_full[i], 1); mbar_init(&v_full[i], 1); mbar_init(&buf_empty[i], 1);
+      mbar_init(&s_full[i], 1); mbar_init(&p_full[i], FPP_WORKERS / 2);
+      mbar_init(&o_full[i], 1); mbar_init(&t_empty[i], FPP_WORKERS / 2);
+    }
+    fence_mbar_init();
+  }
+  if (warp == FPP_WORKERS) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == FPP_WORKERS) {
+    // ======================= TMA producer =======================
+    if (lane == 0) {
+      int n = 0;
+      for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++n) {
+        const int tile = w % ntile, bh = w / ntile;
+        const int h = bh % p.H, b = bh / p.H;
+        const int row0 = b * S, i = n & 1;
+        uint8_t* buf = smem + i * FPP_BUF;
+        mbar_wait(&buf_empty[i], ((n >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(&qk_full[i], ATOM + S_pad * 128);
+        tma_load_2d(&tm128, &qk_full[i], buf, h * 64, row0 + tile * 128);            // Q tile
+        tma_load_2d(&tmPad, &qk_full[i], buf + ATOM, d + h * 64, row0);              // K (all keys of the head)
+        mbar_arrive_expect_tx(&v_full[i], S_pad * 128);
+        tma_load_2d(&tmPad, &v_full[i], buf + 4 * ATOM, 2 * d + h * 64, row0);       // V
+      }
+    }
+  } else if (warp == FPP_WORKERS + 1) {
+    // ======================= MMA issuer =======================
+    if (lane == 0) {
+      const uint32_t id_s = idesc_rt(S_pad, false, false), id_o = idesc_rt(64, false, true);
+      const int nk = S_pad >> 4;
+      auto issue_pv = [&](int m) {            // O_m = P_m V_m  (K-steps of 16 keys)
+        const int i = m & 1;
+        const uint32_t ub = smem_u32(smem + i * FPP_BUF);
+        mbar_wait(&p_full[i], (m >> 1) & 1);
+        mbar_wait(&v_full[i], (m >> 1) & 1);
+        tc_fence_after();
+        for (int j = 0; j < nk; ++j)
+          umma_bf16(tmem + i * 256, desc_k(ub + (j >> 2) * ATOM + (j & 3) * 32), desc_mn(ub + 4 * ATOM + j * 2048), id_o,
+                    j > 0);
+        umma_commit(&o_full[i]);
+        umma_commit(&buf_empty[i]);
+      };
+      int n = 0;
+      for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++n) {
+        const int i = n & 1;
+        const uint32_t ub = smem_u32(smem + i * FPP_BUF);
+        mbar_wait(&qk_full[i], (n >> 1) & 1);
+        mbar_wait(&t_empty[i], ((n >> 1) & 1) ^ 1);      // O of tile n-2 has been read out of this TMEM block
+        tc_fence_after();
+        const uint64_t da = desc_k(ub), db = desc_k(ub + ATOM);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(tmem + i * 256, da + 2 * k, db + 2 * k, id_s, k > 0);
+        umma_commit(&s_full[i]);
+        if (n >= 1) issue_pv(n - 1);
+      }
+      if (n >= 1) issue_pv(n - 1);
+    }
+  } else if (warp < FPP_WORKERS) {
+    // ======================= worker groups: thread == query row, group g serves tiles n with (n & 1) == g ===========
+    const int grp = warp >> 2, q4 = warp & 3;
+    const int r = q4 * 32 + lane;
+    uint8_t* buf = smem + grp * FPP_BUF;
+    uint8_t* sMask = sMaskAll + grp * 256;
+    const uint32_t trow = tmem + grp * 256 + ((uint32_t)(q4 * 32) << 16);
+    const int nc32 = (S_pad + 31) >> 5;   // 32-column steps; the last one may be 16 wide (S_pad % 32 == 16)
+    int n = 0;
+    for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++n) {
+      if ((n & 1) != grp) continue;
+      const int tile = w % ntile, bh = w / ntile;
+      const int h = bh % p.H, b = bh / p.H;
+      const int row0 = b * S;
+      const int qi = tile * 128 + r;
+      const uint32_t par = (uint32_t)((n >> 1) & 1);
+      if (has_mask) {   // key-padding mask of this batch row -> smem (group-private), visible after the group barrier
+        for (int j = q4 * 32 + lane; j < 256; j += 128) sMask[j] = (j < S && p.kmask[(long long)b * S + j]) ? 1 : 0;
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+      }
+      mbar_wait(&s_full[grp], par);
+      tc_fence_after();
+      const bool row_ok = qi < S;                        // padding rows of the last tile: no math, nothing stored
+      const int kv_lim = CAUSAL ? min(S, qi + 1) : S;    // columns >= kv_lim are masked
+      float mx = -INFINITY, sum = 0.f;
+      if (row_ok) {
+        // ---- pass 1: row maximum (tcgen05.ld of step c+1 in flight while step c is reduced) ----
+        uint32_t va[32], vb[32];
+        auto ld = [&](int c, uint32_t (&v)[32]) {
+          if (c * 32 + 32 <= S_pad) tmem_ld32(trow + c * 32, v);
+          else tmem_ld16(trow + c * 32, reinterpret_cast<uint32_t(&)[16]>(v));
+        };
+        auto red_max = [&](int c, const uint32_t (&v)[32]) {
+          const int wdt = min(32, S_pad - c * 32);
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+            if (hf * 16 >= wdt) break;
+            const int c0 = c * 32 + hf * 16;
+            if (c0 + 16 <= kv_lim && !has_mask) {
+#pragma unroll
+              for (int e = 0; e < 16; ++e) mx = fmaxf(mx, __uint_as_float(v[hf * 16 + e]));
+            } else {
+#pragma unroll
+              for (int e = 0; e < 16; ++e)
+                if (c0 + e < kv_lim && (!has_mask || sMask[c0 + e])) mx = fmaxf(mx, __uint_as_float(v[hf * 16 + e]));
+            }
+          }
+        };
+        const int nc_act = CAUSAL ? min(nc32, (kv_lim + 31) >> 5) : nc32;   // steps that hold unmasked columns
+        ld(0, va);
+        for (int c = 0; c < nc_act; c += 2) {
+          tmem_ld_wait();
+          if (c + 1 < nc_act) ld(c + 1, vb);
+          red_max(c, va);
+          if (c + 1 < nc_act) {
+            tmem_ld_wait();
+            if (c + 2 < nc_act) ld(c + 2, va);
+            red_max(c + 1, vb);
+          }
+        }
+        mx = (mx == -INFINITY) ? 0.f : mx * p.scale_log2;   // fully masked row (kmask): exp() of nothing, l = 0
+        // ---- pass 2: p = 2^(s*scale*log2e - mx), row sum, bf16 P into the K-major swizzled operand ----
+        auto exp_store = [&](int c, const uint32_t (&v)[32]) {
+          const int wdt = min(32, S_pad - c * 32);
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+            if (hf * 16 >= wdt) break;
+            float pr[16];
+            const int c0 = c * 32 + hf * 16;
+            if (c0 + 16 <= kv_lim && !has_mask) {
+#pragma unroll
+              for (int e = 0; e < 16; ++e) {
+                pr[e] = ex2_approx(fmaf(__uint_as_float(v[hf * 16 + e]), p.scale_log2, -mx));
+                sum += pr[e];
+              }
+            } else {
+#pragma unroll
+              for (int e = 0; e < 16; ++e) {
+                const bool ok = (c0 + e < kv_lim) && (!has_mask || sMask[c0 + e]);
+                const float x = ok ? ex2_approx(fmaf(__uint_as_float(v[hf * 16 + e]), p.scale_log2, -mx)) : 0.f;
+                pr[e] = x;
+                sum += x;
+              }
+            }
+            store_p16(buf, r, c0, pr);
+          }
+        };
+        ld(0, va);
+        for (int c = 0; c < nc_act; c += 2) {
+          tmem_ld_wait();
+          if (c + 1 < nc_act) ld(c + 1, vb);
+          exp_store(c, va);
+          if (c + 1 < nc_act) {
+            tmem_ld_wait();
+            if (c + 2 < nc_act) ld(c + 2, va);
+            exp_store(c + 1, vb);
+          }
+        }
+        if (CAUSAL) {   // steps entirely above the diagonal: P = 0 (the PV MMA runs over all S_pad keys)
+          const float z[16] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          for (int c0 = nc_act * 32; c0 < S_pad; c0 += 16) store_p16(buf, r, c0, z);
+        }
+      }
+      // every S column of this row has been read (or is never needed): P may be consumed, TMEM block reused for O
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[grp]);
+      // ---- epilogue: O (TMEM, 64 columns) / l -> bf16 -> out ; LSE ----
+      mbar_wait(&o_full[grp], par);
+      tc_fence_after();
+      uint32_t o0[32], o1[32];
+      if (row_ok) {
+        tmem_ld32(trow, o0);
+        tmem_ld32(trow + 32, o1);
+        tmem_ld_wait();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&t_empty[grp]);
+      if (row_ok) {
+        const float inv = sum > 0.f ? 1.f / sum : 0.f;
+        __nv_bfloat16* dst = p.out + ((long long)(row0 + qi)) * d + h * 64;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const uint32_t* v = half == 0 ? o0 : o1;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 o;
+            o.x = pack_bf16x2(__uint_as_float(v[j * 8 + 0]) * inv, __uint_as_float(v[j * 8 + 1]) * inv);
+            o.y = pack_bf16x2(__uint_as_float(v[j * 8 + 2]) * inv, __uint_as_float(v[j * 8 + 3]) * inv);
+            o.z = pack_bf16x2(__uint_as_float(v[j * 8 + 4]) * inv, __uint_as_float(v[j * 8 + 5]) * inv);
+            o.w = pack_bf16x2(__uint_as_float(v[j * 8 + 6]) * inv, __uint_as_float(v[j * 8 + 7]) * inv);
+            reinterpret_cast<uint4*>(dst)[half * 4 + j] = o;
+          }
+        }
+        if (p.lse) p.lse[((long long)b * p.H + h) * S + qi] = (mx + log2f(sum)) * 0.6931471805599453f;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == FPP_WORKERS) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+constexpr int FPP_SMEM = 1024 + 2 * FPP_BUF + 512 + 256;
+
+// ------------------------------------------------------------------------------------------------
 // Backward, persistent version (round-1 final): ONE CTA per SM loops over (batch, head, 128-row tile) work items with
 // every resource double-buffered, so nothing on the critical path of the two-CTA kernels above is exposed any more
 // (measured with scripts/attn_trace.py: 28 % of a CTA's life was the TMA prologue, 12 % the epilogue, and inside the
@@ -1023,6 +1275,27 @@ static int attention_fwd_tc_impl(const void* qkv, void* out, float* lse, const u
     if (rc) return rc;
   }
   const int smem_bytes = big ? FWD_SMEM_BIG : FWD_SMEM;
+  static int fwd_variant = -1;   // MMB_ATTN_FWD=tile selects the round-1 one-tile-per-CTA kernel (A/B testing)
+  if (fwd_variant < 0) {
+    const char* e = getenv("MMB_ATTN_FWD");
+    fwd_variant = (e && e[0] == 't') ? 1 : 0;
+  }
+  if (!big && fwd_variant == 0) {
+    AttnTcArgs a{};
+    a.S = S; a.H = H; a.S_pad = S_pad; a.scale = scale; a.scale_log2 = scale * 1.4426950408889634f;
+    a.lse = lse; a.out = (__nv_bfloat16*)out; a.kmask = kmask;
+    const int n_work = ((S + 127) / 128) * H * B;
+    const int grid_p = n_work < num_sms() ? n_work : num_sms();
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (causal) {
+      cudaFuncSetAttribute(attn_fwd_pp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FPP_SMEM);
+      attn_fwd_pp_kernel<true><<<grid_p, FPP_THREADS, FPP_SMEM, st>>>(tm128, tmPad, a, n_work);
+    } else {
+      cudaFuncSetAttribute(attn_fwd_pp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FPP_SMEM);
+      attn_fwd_pp_kernel<false><<<grid_p, FPP_THREADS, FPP_SMEM, st>>>(tm128, tmPad, a, n_work);
+    }
+    return (int)cudaGetLastError();
+  }
   AttnTcArgs a{};
   a.S = S; a.H = H; a.S_pad = S_pad; a.scale = scale; a.scale_log2 = scale * 1.4426950408889634f;
   a.lse = lse; a.out = (__nv_bfloat16*)out; a.kmask = kmask;

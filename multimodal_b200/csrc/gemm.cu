@@ -52,6 +52,22 @@ struct GemmArgs {
   long long ldd0, ldd1;
   float* colsum;              // bf16 epilogues (not ACT): colsum[n] += sum_m bf16(D0[m,n]) (bias gradient), or nullptr
   int reduce_add;             // fp32 epilogue: TMA reduce-add instead of store
+  // ---- temperature-scaled cross-entropy epilogues (EPI_CE_STATS / EPI_CE_GRAD): logits = exp(*ce_log_scale) * acc
+  // are consumed in registers and never written to HBM (contrastive_loss_with_temperature.py:90-107)
+  const float* ce_log_scale;  // device scalar (logit_scale parameter)
+  int ce_label0;              // the label column of output row r is ce_label0 + r in THIS launch's column space
+  int ce_n_total;             // columns of the whole logits row (all launches), for the smoothing term eps / N
+  float ce_smoothing;
+  float ce_gs;                // CE_GRAD: loss_weight / rows (row scale when there are no row weights)
+  float ce_loss_weight;
+  const float* ce_lse_row;    // CE_GRAD: [M] row log-sum-exp (natural log)
+  const float* ce_row_w;      // CE_GRAD: [M] masked-mean row weights or nullptr
+  const float* ce_lse_col;    // CE_GRAD: [N] row-LSE of the other direction's global row j (transposed term) or nullptr
+  const float* ce_col_w;      // CE_GRAD: [N] weights of those rows or nullptr
+  int ce_col_lo, ce_col_hi;   // CE_GRAD: columns that receive the transposed term
+  float4* ce_part;            // CE_STATS: [M][ce_part_ld] partial (max, sum e^(x-max), sum e^(x-max) x, sum x)
+  int ce_part_ld, ce_part0;   // CE_STATS: row pitch (in float4) and first part index of this launch
+  float* ce_xlabel;           // CE_STATS: [M] logit at the label column
 };
 
 template <int NT> __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory"); }
@@ -240,14 +256,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             tma_load_2d(&tmD1, &aux_bar[g], sAux + g * SLAB_BYTES, n0 + g * 64, m0);
           }
       }
-      if (EPI != EPI_F32 && p.bias != nullptr) {
+      constexpr bool IS_CE = (EPI == EPI_CE_STATS || EPI == EPI_CE_GRAD);
+      if (EPI != EPI_F32 && !IS_CE && p.bias != nullptr) {
         // stage the tile's bias slice in shared memory (every reader of the previous tile's slice has passed that
         // tile's last group barrier); global-load latency is taken here, under the MMAs, instead of in every group
         if (epi_tid < BLOCK_N) sBias[epi_tid] = (add_bias && n0 + epi_tid < p.N) ? __ldg(p.bias + n0 + epi_tid) : 0.f;
       }
+      if (EPI == EPI_CE_GRAD && p.ce_lse_col != nullptr) {   // column LSEs (log2 units) of the transposed term
+        if (epi_tid < BLOCK_N)
+          sBias[epi_tid] = (n0 + epi_tid < p.N) ? __ldg(p.ce_lse_col + n0 + epi_tid) * 1.4426950408889634f : 0.f;
+      }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      if (EPI != EPI_F32 && p.bias != nullptr) epi_bar_sync<ENT>();
+      if ((EPI != EPI_F32 && !IS_CE && p.bias != nullptr) || (EPI == EPI_CE_GRAD && p.ce_lse_col != nullptr))
+        epi_bar_sync<ENT>();
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N;
       // All TMEM reads of this accumulator stage are complete (tcgen05.wait::ld) -> hand it back to the MMA warp.
       auto release_acc = [&]() {
@@ -259,7 +281,53 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
       };
 
-      if (EPI == EPI_F32) {
+      if (EPI == EPI_CE_STATS) {
+        // Online softmax statistics of this thread's row over its columns of the tile; nothing but 16 B per
+        // (row, 128-column part) leaves the SM.  x = T * acc (natural-log logits); exponentials in base 2.
+        const float T = __expf(__ldg(p.ce_log_scale));
+        const float T2 = T * 1.4426950408889634f;
+        const int lab = p.ce_label0 + m0 + row;
+        float m2 = -INFINITY, se = 0.f, sex = 0.f, sx = 0.f;
+        uint32_t vbuf[2][CWE];
+        auto ld_group = [&](int g, uint32_t (&v)[CWE]) {
+          if (CWE == 32) tmem_ld32(t_addr + g * 64 + half * 32, reinterpret_cast<uint32_t(&)[32]>(v));
+          else           tmem_ld16(t_addr + g * 64 + half * 16, reinterpret_cast<uint32_t(&)[16]>(v));
+        };
+        ld_group(0, vbuf[0]);
+#pragma unroll
+        for (int g = 0; g < BLOCK_N / 64; ++g) {
+          if (n0 + g * 64 >= p.N) break;
+          uint32_t (&v)[CWE] = vbuf[g & 1];
+          const int nb = n0 + g * 64 + half * CWE;
+          tmem_ld_wait();
+          if (g + 1 < BLOCK_N / 64 && n0 + (g + 1) * 64 < p.N) ld_group(g + 1, vbuf[(g + 1) & 1]);
+          else release_acc();
+          float gm = -INFINITY;
+#pragma unroll
+          for (int e = 0; e < CWE; ++e)
+            if (nb + e < p.N) gm = fmaxf(gm, __uint_as_float(v[e]));
+          if (gm > -INFINITY) {
+            const float gm2 = gm * T2;
+            if (gm2 > m2) {
+              const float rs = ex2_approx(m2 - gm2);   // m2 == -inf on the first group: 2^-inf = 0 (se, sex are 0 anyway)
+              se *= rs; sex *= rs; m2 = gm2;
+            }
+#pragma unroll
+            for (int e = 0; e < CWE; ++e) {
+              if (nb + e < p.N) {
+                const float a = __uint_as_float(v[e]);
+                const float x = a * T;
+                const float pe = ex2_approx(fmaf(a, T2, -m2));
+                se += pe; sex = fmaf(pe, x, sex); sx += x;
+                if (nb + e == lab && m0 + row < p.M) p.ce_xlabel[m0 + row] = x;
+              }
+            }
+          }
+        }
+        if (m0 + row < p.M)
+          p.ce_part[(long long)(m0 + row) * p.ce_part_ld + p.ce_part0 + n_blk * NP + half] =
+              make_float4(m2 * 0.6931471805599453f, se, sex, sx);
+      } else if (EPI == EPI_F32) {
         // fp32 output: a 32-column chunk is one 128 B x 128 row slab.  Half h owns chunks c == h (mod 2), slab h, named
         // barrier 1+h and its own TMA bulk-group accounting (issued by its first thread).
         const int htid = epi_tid & 127;
@@ -307,6 +375,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           if (CWE == 32) tmem_ld32(t_addr + g * 64 + half * 32, reinterpret_cast<uint32_t(&)[32]>(v));
           else           tmem_ld16(t_addr + g * 64 + half * 16, reinterpret_cast<uint32_t(&)[16]>(v));
         };
+        // EPI_CE_GRAD: per-row constants of this thread's row
+        float ce_T = 0.f, ce_T2 = 0.f, ce_lse2 = 0.f, ce_gsT = 0.f, ce_gcT = 0.f, ce_eps_n = 0.f;
+        int ce_lab = -1;
+        if (EPI == EPI_CE_GRAD) {
+          const int gr = min(m0 + row, p.M - 1);
+          ce_T = __expf(__ldg(p.ce_log_scale));
+          ce_T2 = ce_T * 1.4426950408889634f;
+          ce_lse2 = __ldg(p.ce_lse_row + gr) * 1.4426950408889634f;
+          ce_gsT = ce_T * (p.ce_row_w ? p.ce_loss_weight * __ldg(p.ce_row_w + gr) : p.ce_gs);
+          ce_gcT = ce_T * p.ce_gs;
+          ce_eps_n = p.ce_smoothing / (float)p.ce_n_total;
+          ce_lab = p.ce_label0 + m0 + row;
+        }
         ld_group(0, vbuf[0]);
 #pragma unroll
         for (int g = 0; g < NG4; ++g) {
@@ -332,7 +413,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
           for (int j = 0; j < CWE / 8; ++j) {  // 8 columns -> one 16 B chunk
             float f[8];
-            if (add_bias) {
+            if (EPI == EPI_CE_GRAD) {
+              // d(loss_weight * mean CE) / d sims of this row block, plus (columns [col_lo, col_hi)) the transposed
+              // other-direction term rebuilt from the column LSEs — see contrastive_ce_grad_kernel (loss.cu)
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const int n = nb + j * 8 + e;
+                const float a = __uint_as_float(v[j * 8 + e]);
+                const float tt = ((n == ce_lab) ? (1.f - p.ce_smoothing) : 0.f) + ce_eps_n;
+                float gsum = ce_gsT * (ex2_approx(fmaf(a, ce_T2, -ce_lse2)) - tt);
+                if (p.ce_lse_col != nullptr && n >= p.ce_col_lo && n < p.ce_col_hi) {
+                  const float wc = p.ce_col_w ? p.ce_loss_weight * ce_T * __ldg(p.ce_col_w + min(n, p.N - 1)) : ce_gcT;
+                  if (wc != 0.f) gsum += wc * (ex2_approx(fmaf(a, ce_T2, -sBias[g * 64 + h * CWE + j * 8 + e])) - tt);
+                }
+                f[e] = gsum;
+              }
+            } else if (add_bias) {
               const float4 b0 = *reinterpret_cast<const float4*>(sBias + g * 64 + h * CWE + j * 8);
               const float4 b1 = *reinterpret_cast<const float4*>(sBias + g * 64 + h * CWE + j * 8 + 4);
               const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
@@ -375,7 +471,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               *reinterpret_cast<uint4*>(dst1 + off) = oa;
             }
           }
-          (void)nb;
           fence_proxy_async_smem();                       // generic-proxy slab writes -> visible to the TMA engine
           if (epi_tid == 0) tma_store_wait_read<0>();     // stores of the previous group have left their slab
           epi_bar_sync<ENT>();
@@ -562,12 +657,13 @@ extern "C" int mmb_gemm_set_mode(int cta2, int epilogue_warps) {
   return MMB_OK;
 }
 
-extern "C" int mmb_gemm_bf16(const void* A, long long lda, int a_mn_major, const void* B, long long ldb,
-                             int b_mn_major, void* D0, long long ldd0, void* D1, long long ldd1, int M, int N, int K,
-                             int epilogue, int act, float alpha, const float* bias, const void* aux,
-                             long long ld_aux, int splits, int accumulate, float* colsum, void* stream_) {
+static int gemm_dispatch(const void* A, long long lda, int a_mn_major, const void* B, long long ldb, int b_mn_major,
+                         void* D0, long long ldd0, void* D1, long long ldd1, int M, int N, int K, int epilogue, int act,
+                         float alpha, const float* bias, const void* aux, long long ld_aux, int splits, int accumulate,
+                         float* colsum, const GemmArgs* ce, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (M <= 0 || N <= 0 || K <= 0) return MMB_ERR_ARG;
+  if ((epilogue == EPI_CE_STATS || epilogue == EPI_CE_GRAD) && (!ce || a_mn_major || b_mn_major)) return MMB_ERR_ARG;
   if ((lda & 7) || (ldb & 7)) return MMB_ERR_ARG;
   if (epilogue == EPI_F32 ? (N & 3) : (N & 7)) return MMB_ERR_ARG;
   // CTA-pair mode (cta_group::2, 256x256 tiles) for everything large enough to fill the 74 SM pairs at least once;
@@ -580,7 +676,8 @@ extern "C" int mmb_gemm_bf16(const void* A, long long lda, int a_mn_major, const
   const int cta2_env = g_force_cta2 >= 0 ? g_force_cta2 : cta2_env0;   // mmb_gemm_set_mode() wins over the env var
   const long long big_tiles = (long long)((M + 255) / 256) * ((N + BLOCK_N - 1) / BLOCK_N);
   const bool cta2 = cta2_env == 1 || (cta2_env == -1 && M >= 512 && big_tiles * (splits < 1 ? 1 : splits) >= 37);
-  GemmArgs g;
+  GemmArgs g{};
+  if (ce) g = *ce;   // cross-entropy epilogue parameters (the geometry fields below are overwritten)
   g.M = M; g.N = N; g.K = K;
   g.m_tiles = cta2 ? (M + 255) / 256 : (M + BLOCK_M - 1) / BLOCK_M;
   g.n_tiles = (N + BLOCK_N - 1) / BLOCK_N;
@@ -609,7 +706,9 @@ extern "C" int mmb_gemm_bf16(const void* A, long long lda, int a_mn_major, const
   if (!b_mn_major) rc = make_tmap_2d(&tB, B, 2, false, K, N, ldb * 2, 64, cta2 ? 128 : BLOCK_N);
   else             rc = make_tmap_2d(&tB, B, 2, false, N, K, ldb * 2, 64, BLOCK_K);
   if (rc) return rc;
-  if (epilogue == EPI_F32) {
+  if (epilogue == EPI_CE_STATS) {
+    tD0 = tA; tD1 = tA;   // no tensor output: 16 B of statistics per (row, 128-column part)
+  } else if (epilogue == EPI_F32) {
     if (ldd0 & 3) return MMB_ERR_ARG;
     rc = make_tmap_2d(&tD0, D0, 4, true, N, M, ldd0 * 4, 32, 128);
     if (rc) return rc;
@@ -646,6 +745,13 @@ extern "C" int mmb_gemm_bf16(const void* A, long long lda, int a_mn_major, const
   }
   const int ew_env = g_force_ew > 0 ? g_force_ew : ew_env0;
   const bool act_epi = epilogue == EPI_BF16_ACT || epilogue == EPI_BF16_DACT;
+  if (epilogue == EPI_CE_STATS || epilogue == EPI_CE_GRAD) {
+    if (epilogue == EPI_CE_STATS)
+      return cta2 ? launch_impl<false, false, EPI_CE_STATS, 0, true, 8>(tA, tB, tD0, tD1, g, stream)
+                  : launch_impl<false, false, EPI_CE_STATS, 0, false, 8>(tA, tB, tD0, tD1, g, stream);
+    return cta2 ? launch_impl<false, false, EPI_CE_GRAD, 0, true, 8>(tA, tB, tD0, tD1, g, stream)
+                : launch_impl<false, false, EPI_CE_GRAD, 0, false, 8>(tA, tB, tD0, tD1, g, stream);
+  }
 #define MMB_CASE(AM, BM, E, AC)                                                                                     \
   if (am == AM && bm == BM && epilogue == E && (AC < 0 || act == AC)) {                                             \
     constexpr int EWX = (E == EPI_BF16_ACT || E == EPI_BF16_DACT) ? 16 : 8;                                         \
@@ -667,4 +773,45 @@ extern "C" int mmb_gemm_bf16(const void* A, long long lda, int a_mn_major, const
   MMB_CASE(1, 0, EPI_F32, -1)
 #undef MMB_CASE
   return MMB_ERR_UNSUPPORTED;
+}
+
+extern "C" int mmb_gemm_bf16(const void* A, long long lda, int a_mn_major, const void* B, long long ldb,
+                             int b_mn_major, void* D0, long long ldd0, void* D1, long long ldd1, int M, int N, int K,
+                             int epilogue, int act, float alpha, const float* bias, const void* aux,
+                             long long ld_aux, int splits, int accumulate, float* colsum, void* stream_) {
+  if (epilogue < EPI_BF16 || epilogue > EPI_F32) return MMB_ERR_ARG;
+  return gemm_dispatch(A, lda, a_mn_major, B, ldb, b_mn_major, D0, ldd0, D1, ldd1, M, N, K, epilogue, act, alpha, bias,
+                       aux, ld_aux, splits, accumulate, colsum, nullptr, stream_);
+}
+
+// ---- fused similarity GEMM + temperature-scaled cross-entropy (no logits in HBM) ------------------------------------
+// Number of float4 partials per row one mmb_gemm_ce_stats launch over N columns writes (two 128-column parts per tile).
+extern "C" int mmb_gemm_ce_num_parts(int N) { return N <= 0 ? 0 : 2 * ((N + BLOCK_N - 1) / BLOCK_N); }
+
+extern "C" int mmb_gemm_ce_stats(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K,
+                                 const float* log_scale, int label0, void* part, int part_ld, int part0, float* xlabel,
+                                 void* stream) {
+  if (!log_scale || !part || !xlabel || part_ld <= 0 || part0 < 0 || part0 + mmb_gemm_ce_num_parts(N) > part_ld ||
+      (reinterpret_cast<uintptr_t>(part) & 15))
+    return MMB_ERR_ARG;
+  GemmArgs ce{};
+  ce.ce_log_scale = log_scale; ce.ce_label0 = label0;
+  ce.ce_part = reinterpret_cast<float4*>(part); ce.ce_part_ld = part_ld; ce.ce_part0 = part0; ce.ce_xlabel = xlabel;
+  return gemm_dispatch(A, lda, 0, B, ldb, 0, nullptr, 0, nullptr, 0, M, N, K, EPI_CE_STATS, 0, 1.f, nullptr, nullptr, 0, 1, 0,
+                       nullptr, &ce, stream);
+}
+
+extern "C" int mmb_gemm_ce_grad(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K,
+                                const float* log_scale, int label0, int n_total, int rows_total, float smoothing,
+                                float loss_weight, const float* lse_row, const float* row_w, const float* lse_col,
+                                const float* col_w, int col_lo, int col_hi, void* dsims_bf16, long long ldd,
+                                void* stream) {
+  if (!log_scale || !lse_row || !dsims_bf16 || n_total <= 0 || rows_total <= 0) return MMB_ERR_ARG;
+  GemmArgs ce{};
+  ce.ce_log_scale = log_scale; ce.ce_label0 = label0; ce.ce_n_total = n_total; ce.ce_smoothing = smoothing;
+  ce.ce_loss_weight = loss_weight; ce.ce_gs = loss_weight / (float)rows_total;
+  ce.ce_lse_row = lse_row; ce.ce_row_w = row_w; ce.ce_lse_col = lse_col; ce.ce_col_w = col_w;
+  ce.ce_col_lo = col_lo; ce.ce_col_hi = col_hi;
+  return gemm_dispatch(A, lda, 0, B, ldb, 0, dsims_bf16, ldd, nullptr, 0, M, N, K, EPI_CE_GRAD, 0, 1.f, nullptr, nullptr, 0, 1,
+                       0, nullptr, &ce, stream);
 }

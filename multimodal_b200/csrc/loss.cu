@@ -113,6 +113,54 @@ __global__ void contrastive_ce_grad_kernel(const float* __restrict__ sims, long 
   }
 }
 
+// Combines the per-(row, 128-column part) online-softmax statistics written by the fused similarity GEMM
+// (gemm.cu, EPI_CE_STATS: float4 {max, sum e^(x-max), sum e^(x-max) x, sum x}, x = T * sim) into what
+// contrastive_ce_stats_kernel derives from materialised logits: row LSE, row loss (label smoothing, row weights) and
+// the contribution to d loss / d logit_scale = sum_j (p_ij - t_ij) x_ij = E_p[x] - (1-eps) x_label - eps mean(x).
+// One warp per row; parts with an empty column range carry sum == 0 and are skipped.
+__global__ void ce_stats_reduce_kernel(const float4* __restrict__ part, int part_ld, int n_parts,
+                                       const float* __restrict__ xlabel, int rows, int n_total, float smoothing,
+                                       float loss_weight, const float* __restrict__ row_w, float* __restrict__ row_loss,
+                                       float* __restrict__ lse_out, float* __restrict__ dscale_accum) {
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (i >= rows) return;
+  const float4* pr = part + (long long)i * part_ld;
+  float mx = -INFINITY;
+  for (int k = lane; k < n_parts; k += 32) {
+    const float4 q = pr[k];
+    if (q.y > 0.f) mx = fmaxf(mx, q.x);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float se = 0.f, sex = 0.f, sx = 0.f;
+  for (int k = lane; k < n_parts; k += 32) {
+    const float4 q = pr[k];
+    if (q.y > 0.f) {
+      const float w = __expf(q.x - mx);
+      se += q.y * w; sex += q.z * w;
+    }
+    sx += q.w;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    se += __shfl_xor_sync(0xffffffffu, se, o);
+    sex += __shfl_xor_sync(0xffffffffu, sex, o);
+    sx += __shfl_xor_sync(0xffffffffu, sx, o);
+  }
+  if (lane == 0) {
+    const float lse = mx + logf(se);
+    const float l_label = xlabel[i];
+    const float mean_logit = sx / n_total;
+    const float loss = (1.f - smoothing) * (lse - l_label) + smoothing * (lse - mean_logit);
+    const float wrow = row_w ? row_w[i] : 1.f / rows;
+    if (row_loss) row_loss[i] = row_w ? loss * wrow * rows : loss;
+    if (lse_out) lse_out[i] = lse;
+    if (dscale_accum)
+      atomicAdd(dscale_accum, (sex / se - (1.f - smoothing) * l_label - smoothing * mean_logit) * loss_weight * wrow);
+  }
+}
+
 // out[0] = scale * sum(in[0..n))  (deterministic single-block tree; n is a batch size)
 __global__ void sum_scale_kernel(const float* __restrict__ in, int n, float scale, float* __restrict__ out, int accumulate) {
   __shared__ float red[32];
@@ -194,5 +242,15 @@ extern "C" int mmb_matmul_f32(const float* A, long long lda, int ta, const float
   dim3 grid((N + 31) / 32, (M + 31) / 32), block(32, 32);
   matmul_f32_kernel<<<grid, block, 0, reinterpret_cast<cudaStream_t>(stream)>>>(A, lda, ta, B, ldb, tb, C, ldc, M, N, K,
                                                                                alpha, accumulate);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int mmb_ce_stats_reduce(const void* part, int part_ld, int n_parts, const float* xlabel, int rows, int n_total,
+                                   float label_smoothing, float loss_weight, const float* row_w, float* row_loss,
+                                   float* lse_out, float* dscale_accum, void* stream) {
+  if (!part || !xlabel || rows <= 0 || n_parts <= 0 || n_parts > part_ld || n_total <= 0) return MMB_ERR_ARG;
+  ce_stats_reduce_kernel<<<(rows + 7) / 8, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const float4*>(part), part_ld, n_parts, xlabel, rows, n_total, label_smoothing, loss_weight, row_w,
+      row_loss, lse_out, dscale_accum);
   return (int)cudaGetLastError();
 }

@@ -14,6 +14,8 @@
 #define EPI_BF16_ACT 1   /* D0 = bf16(pre), D1 = bf16(act(D0)), pre = alpha*acc + bias */
 #define EPI_BF16_DACT 2  /* D0 = bf16(alpha*acc * act'(aux)) */
 #define EPI_F32 3        /* D0 = fp32(alpha*acc + bias), optional reduce-add (split-K / accumulate) */
+#define EPI_CE_STATS 4   /* no tensor output: per (row, 128-column part) online-softmax statistics of T*acc */
+#define EPI_CE_GRAD 5    /* D0 = bf16(d loss / d acc) of the temperature-scaled cross-entropy, from T*acc in registers */
 
 #define ACT_QUICK_GELU 0
 #define ACT_GELU_ERF 1

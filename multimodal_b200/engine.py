@@ -288,7 +288,8 @@ class ViTTower:
                                       prefix="img")
         self.gen = 0
 
-    def forward(self, image: torch.Tensor, training: bool) -> torch.Tensor:
+    def forward(self, image: torch.Tensor, training: bool, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """out (optional): fp32 [B, E] destination of the embeddings (e.g. a row block of a larger buffer)."""
         mod, st, ws, d = self.mod, self.store, self.ws, self.d
         if image.dtype != torch.float32:
             image = image.float()
@@ -320,7 +321,7 @@ class ViTTower:
         mP = ws.get("img.mP", (B,), f32); rP = ws.get("img.rP", (B,), f32)
         ops.add_layernorm_fwd(XM, Y, XSEL, LNP, None, mod.ln_post.weight, mod.ln_post.bias, mP, rP, B, d, mod.ln_post.eps,
                               row_idx=None, rows_per_group=S)
-        EMB = torch.empty((B, self.E), device=image.device, dtype=f32)
+        EMB = out if out is not None else torch.empty((B, self.E), device=image.device, dtype=f32)
         ops.gemm(LNP, st.shadow(mod.projection), b_mn=True, epilogue=ops.EPI_F32, out=EMB)
         self.B, self.S, self.P = B, S, P
         self.gen += 1
@@ -370,7 +371,8 @@ class TextTower:
                                       act=ops.ACT_QUICK_GELU, prefix="txt")
         self.gen = 0
 
-    def forward(self, text: torch.Tensor, training: bool, return_hidden_state: bool = False) -> torch.Tensor:
+    def forward(self, text: torch.Tensor, training: bool, return_hidden_state: bool = False,
+                out: Optional[torch.Tensor] = None) -> torch.Tensor:
         mod, st, ws, d = self.mod, self.store, self.ws, self.d
         if text.dtype != torch.int64:
             text = text.long()
@@ -394,7 +396,7 @@ class TextTower:
         mF = ws.get("txt.mF", (B,), f32); rF = ws.get("txt.rF", (B,), f32)
         ops.add_layernorm_fwd(XM, Y, XSEL, LNF, None, mod.ln_final.weight, mod.ln_final.bias, mF, rF, B, d,
                               mod.ln_final.eps, row_idx=IDX, rows_per_group=S)
-        EMB = torch.empty((B, self.E), device=text.device, dtype=f32)
+        EMB = out if out is not None else torch.empty((B, self.E), device=text.device, dtype=f32)
         ops.gemm(LNF, st.shadow(mod.projection.weight), epilogue=ops.EPI_F32, out=EMB)
         self.B, self.S = B, S
         self.tokens = text if training else None

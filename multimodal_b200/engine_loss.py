@@ -102,8 +102,14 @@ def contrastive_schedule(a, b, s, smoothing, backprop_type, want_logits, world, 
         lo, hi = lab, lab + B
     else:
         lo, hi = 0, 0
-    SA = torch.empty((B, N), device=dev, dtype=f32)
-    SB = torch.empty((B, N), device=dev, dtype=f32)
+    # Fused path (default whenever the caller does not ask for the logits): the similarity GEMMs consume their
+    # accumulators in the epilogue (online-softmax statistics forward, d loss / d sims backward) and fp32 logits are
+    # never written to HBM — 1 GiB at BASELINE config 4.  want_logits keeps the materialising schedule.
+    fused = tensor_path and not want_logits
+    SA = SB = None
+    if not fused:
+        SA = torch.empty((B, N), device=dev, dtype=f32)
+        SB = torch.empty((B, N), device=dev, dtype=f32)
     RW = CW = None
     if mask is not None:
         if mask.shape != (B,):
@@ -120,11 +126,22 @@ def contrastive_schedule(a, b, s, smoothing, backprop_type, want_logits, world, 
         if RW is not None:
             my.w[p].copy_(RW)
         comm.barrier()                                    # peers' embeddings are readable
-        for r in range(world):                            # TMA loads of the B operand read peer r's buffer in place
-            ops.gemm(my.a[p], comm.slots[r].b[p], epilogue=ops.EPI_F32, out=SA[:, r * B:(r + 1) * B])
-            ops.gemm(my.b[p], comm.slots[r].a[p], epilogue=ops.EPI_F32, out=SB[:, r * B:(r + 1) * B])
-        ops.contrastive_ce_stats(SA, s, B, N, lab, smoothing, 0.5, RLA, my.lse_a[p], dS, logits_a, RW)
-        ops.contrastive_ce_stats(SB, s, B, N, lab, smoothing, 0.5, RLB, my.lse_b[p], dS, logits_b, RW)
+        if fused:
+            npp = ops.gemm_ce_num_parts(B)                # float4 partials per row and per-peer launch
+            PA = torch.empty((B, world * npp, 4), device=dev, dtype=f32)
+            PB = torch.empty((B, world * npp, 4), device=dev, dtype=f32)
+            XA, XB = torch.empty(B, device=dev, dtype=f32), torch.empty(B, device=dev, dtype=f32)
+            for r in range(world):                        # one launch per peer: its B operand is the peer's buffer
+                ops.gemm_ce_stats(my.a[p], comm.slots[r].b[p], s, lab - r * B, PA, r * npp, XA)
+                ops.gemm_ce_stats(my.b[p], comm.slots[r].a[p], s, lab - r * B, PB, r * npp, XB)
+            ops.ce_stats_reduce(PA, world * npp, XA, B, N, smoothing, 0.5, RW, RLA, my.lse_a[p], dS)
+            ops.ce_stats_reduce(PB, world * npp, XB, B, N, smoothing, 0.5, RW, RLB, my.lse_b[p], dS)
+        else:
+            for r in range(world):                        # TMA loads of the B operand read peer r's buffer in place
+                ops.gemm(my.a[p], comm.slots[r].b[p], epilogue=ops.EPI_F32, out=SA[:, r * B:(r + 1) * B])
+                ops.gemm(my.b[p], comm.slots[r].a[p], epilogue=ops.EPI_F32, out=SB[:, r * B:(r + 1) * B])
+            ops.contrastive_ce_stats(SA, s, B, N, lab, smoothing, 0.5, RLA, my.lse_a[p], dS, logits_a, RW)
+            ops.contrastive_ce_stats(SB, s, B, N, lab, smoothing, 0.5, RLB, my.lse_b[p], dS, logits_b, RW)
         LA = LB = None
         if hi > lo:
             if world > 1:
@@ -141,8 +158,20 @@ def contrastive_schedule(a, b, s, smoothing, backprop_type, want_logits, world, 
                 LA, LB, CW = my.lse_a[p], my.lse_b[p], RW
         DSA = torch.empty((B, N), device=dev, dtype=bf)
         DSB = torch.empty((B, N), device=dev, dtype=bf)
-        ops.contrastive_ce_grad(SA, s, B, N, lab, smoothing, 0.5, my.lse_a[p], LB, lo, hi, DSA, None, RW, CW)
-        ops.contrastive_ce_grad(SB, s, B, N, lab, smoothing, 0.5, my.lse_b[p], LA, lo, hi, DSB, None, RW, CW)
+        if fused:
+            for r in range(world):                        # recompute the logits tile, emit d loss / d sims directly
+                c0 = r * B
+                clo, chi = min(max(lo - c0, 0), B), min(max(hi - c0, 0), B)
+                sl = slice(c0, c0 + B)
+                ops.gemm_ce_grad(my.a[p], comm.slots[r].b[p], s, lab - c0, N, B, smoothing, 0.5, my.lse_a[p], RW,
+                                 LB[sl] if (LB is not None and chi > clo) else None, CW[sl] if CW is not None else None,
+                                 clo, chi, DSA[:, sl])
+                ops.gemm_ce_grad(my.b[p], comm.slots[r].a[p], s, lab - c0, N, B, smoothing, 0.5, my.lse_b[p], RW,
+                                 LA[sl] if (LA is not None and chi > clo) else None, CW[sl] if CW is not None else None,
+                                 clo, chi, DSB[:, sl])
+        else:
+            ops.contrastive_ce_grad(SA, s, B, N, lab, smoothing, 0.5, my.lse_a[p], LB, lo, hi, DSA, None, RW, CW)
+            ops.contrastive_ce_grad(SB, s, B, N, lab, smoothing, 0.5, my.lse_b[p], LA, lo, hi, DSB, None, RW, CW)
         dA = torch.empty((B, E), device=dev, dtype=f32)
         dB = torch.empty((B, E), device=dev, dtype=f32)
         for r in range(world):

@@ -264,6 +264,43 @@ def contrastive_ce_grad(sims, logit_scale, rows, N, label_offset, smoothing, los
                                                   _p(row_w), _p(col_w), _stream()), "mmb_contrastive_ce_grad")
 
 
+def gemm_ce_num_parts(N: int) -> int:
+    return int(_lib.lib().mmb_gemm_ce_num_parts(int(N)))
+
+
+def gemm_ce_stats(A, B, log_scale, label0, part, part0, xlabel):
+    """Fused similarity GEMM + online-softmax statistics (logits never written): see include/mmb200.h."""
+    _chk(A, torch.bfloat16, "A"); _chk(B, torch.bfloat16, "B"); _rowmajor(A, "A"); _rowmajor(B, "B")
+    _chk(part, torch.float32, "part"); _chk(xlabel, torch.float32, "xlabel")
+    M, K = A.shape
+    N = B.shape[0]
+    if B.shape[1] != K or part.dim() != 3 or part.shape[0] != M or part.shape[2] != 4 or not part.is_contiguous():
+        raise MMBError("gemm_ce_stats: expected B [N,K] and a contiguous part buffer [M, parts, 4]")
+    _lib.check(_lib.lib().mmb_gemm_ce_stats(_p(A), A.stride(0), _p(B), B.stride(0), M, N, K, _p(log_scale), int(label0),
+                                            _p(part), part.shape[1], int(part0), _p(xlabel), _stream()), "mmb_gemm_ce_stats")
+
+
+def ce_stats_reduce(part, n_parts, xlabel, rows, n_total, smoothing, loss_weight, row_w, row_loss, lse_out, dscale_accum):
+    _lib.check(_lib.lib().mmb_ce_stats_reduce(_p(part), part.shape[1], int(n_parts), _p(xlabel), rows, n_total,
+                                              float(smoothing), float(loss_weight), _p(row_w), _p(row_loss), _p(lse_out),
+                                              _p(dscale_accum), _stream()), "mmb_ce_stats_reduce")
+
+
+def gemm_ce_grad(A, B, log_scale, label0, n_total, rows_total, smoothing, loss_weight, lse_row, row_w, lse_col, col_w,
+                 col_lo, col_hi, dsims):
+    """Recomputes the logits tile by tile and writes d loss / d sims (bf16) straight from the accumulators."""
+    _chk(A, torch.bfloat16, "A"); _chk(B, torch.bfloat16, "B"); _rowmajor(A, "A"); _rowmajor(B, "B")
+    _chk(dsims, torch.bfloat16, "dsims"); _rowmajor(dsims, "dsims")
+    M, K = A.shape
+    N = B.shape[0]
+    if tuple(dsims.shape) != (M, N):
+        raise MMBError(f"gemm_ce_grad: dsims shape {tuple(dsims.shape)} != {(M, N)}")
+    _lib.check(_lib.lib().mmb_gemm_ce_grad(_p(A), A.stride(0), _p(B), B.stride(0), M, N, K, _p(log_scale), int(label0),
+                                           int(n_total), int(rows_total), float(smoothing), float(loss_weight), _p(lse_row),
+                                           _p(row_w), _p(lse_col), _p(col_w), int(col_lo), int(col_hi), _p(dsims),
+                                           dsims.stride(0), _stream()), "mmb_gemm_ce_grad")
+
+
 def sum_scale(inp, n, scale, out, accumulate=False):
     _lib.check(_lib.lib().mmb_sum_scale(_p(inp), n, float(scale), _p(out), int(accumulate), _stream()), "mmb_sum_scale")
 

@@ -41,7 +41,8 @@ class ContrastiveTrainer:
 
     def __init__(self, model, loss_module, lr: float = 5e-4, betas=(0.9, 0.98), eps: float = 1e-6,
                  weight_decay: float = 0.2, label_smoothing: float = 0.0,
-                 backprop_type: BackpropType = BackpropType.GLOBAL, grad_chunks: int = 3):
+                 backprop_type: BackpropType = BackpropType.GLOBAL, grad_chunks: int = 3,
+                 overlap_allreduce: Optional[bool] = None):
         self.model, self.loss_module = model, loss_module
         self.img = model.encoder_a._runtime()
         self.txt = model.encoder_b._runtime()
@@ -60,6 +61,15 @@ class ContrastiveTrainer:
         self.smoothing = label_smoothing
         self.backprop_type = backprop_type
         self.grad_chunks = max(1, grad_chunks)
+        # Gradient all-reduce scheduling.  Round 1 overlapped chunked all-reduces with the image tower's backward; on
+        # 8 GPUs that cost more than it hid (190.9 vs 179.9 ms/step): the NCCL CTAs take SMs away from the persistent
+        # one-CTA-per-SM GEMMs, whose displaced CTAs then run as a second wave (GEMM throughput 1175 -> 1113 TFLOP/s),
+        # whereas the whole 600 MB all-reduce is only ~1.5 ms over NVSwitch.  Default now: both flat gradient buffers
+        # are reduced right after the backward, nothing runs beside the GEMMs (MMB_OVERLAP_ALLREDUCE=1: round-1 schedule).
+        if overlap_allreduce is None:
+            import os
+            overlap_allreduce = os.environ.get("MMB_OVERLAP_ALLREDUCE", "0") == "1"
+        self.overlap_allreduce = bool(overlap_allreduce)
         self._works: List = []
         self.kernel_launches = 0
 
@@ -75,18 +85,38 @@ class ContrastiveTrainer:
         idx = sorted({(L * i) // self.grad_chunks for i in range(1, self.grad_chunks)})
         return [st.off[id(next(layers[i].parameters()))] for i in idx if 0 < i < L]
 
-    def step(self, image: torch.Tensor, text: torch.Tensor) -> torch.Tensor:
-        """One optimisation step on this rank's micro-batch; returns the (device) loss of this rank."""
+    def step(self, image: torch.Tensor, text: torch.Tensor, micro_batch: Optional[int] = None) -> torch.Tensor:
+        """One optimisation step on this rank's batch; returns the (device) loss of this rank.
+
+        micro_batch (optional, must divide the batch): activation recompute for batches whose saved activations do not
+        fit the 180 GB of HBM (BASELINE config 4: ViT-L/14 at 4096 pairs per GPU would need ~830 GB).  The contrastive
+        loss couples every pair of the GLOBAL batch, so the towers cannot simply be run on slices: pass 1 runs both
+        towers slice by slice WITHOUT saving activations and collects the embeddings; the loss and the embedding
+        gradients are computed once on the full batch (exactly as in the un-sliced step); pass 2 re-runs each slice with
+        saving and back-propagates its rows of the embedding gradient, parameter gradients accumulating in the flat
+        buffer.  One extra forward (4/3 of the compute) — the trade the reference's activation checkpointing makes
+        (examples/flava/native/train.py:148-165).  Results are identical to the un-sliced step up to fp32 summation
+        order."""
         img, txt = self.img, self.txt
         dev = image.device
         f32 = torch.float32
         B = image.shape[0]
+        mb = B if micro_batch is None else int(micro_batch)
+        if mb <= 0 or B % mb:
+            raise MMBError(f"micro_batch {micro_batch} must divide the per-rank batch {B}")
         # reference: logit_scale.data.clamp_ every forward (contrastive_loss_with_temperature.py:193)
         self.ls.data.clamp_(self.loss_module.logit_scale_min, self.loss_module.logit_scale_max)
         self.ls_buf[0:1].copy_(self.ls.data.reshape(1))
         # ---------------- forward ----------------
-        ea = img.forward(image, True)
-        eb = txt.forward(text, True)
+        if mb == B:
+            ea = img.forward(image, True)
+            eb = txt.forward(text, True)
+        else:
+            ea = torch.empty((B, img.E), device=dev, dtype=f32)
+            eb = torch.empty((B, txt.E), device=dev, dtype=f32)
+            for i in range(0, B, mb):
+                img.forward(image[i:i + mb], False, out=ea[i:i + mb])
+                txt.forward(text[i:i + mb], False, out=eb[i:i + mb])
         E = ea.shape[1]
         na, nb = torch.empty_like(ea), torch.empty_like(eb)
         ia, ib = torch.empty(B, device=dev, dtype=f32), torch.empty(B, device=dev, dtype=f32)
@@ -100,10 +130,24 @@ class ContrastiveTrainer:
         ops.l2norm_bwd(dA, na, ia, dea, None, B, E)
         ops.l2norm_bwd(dB, nb, ib, deb, None, B, E)
         self._works = []
-        txt.backward(deb)
-        self._allreduce(txt.store.g)                      # overlaps with the image tower's backward
-        bounds = self._layer_boundaries(img) if self.world > 1 else []
-        if bounds:
+        if mb != B:
+            for i in range(0, B, mb):                     # pass 2: re-forward with saving, back-propagate the slice
+                txt.forward(text[i:i + mb], True)
+                txt.backward(deb[i:i + mb])
+            for i in range(0, B, mb):
+                img.forward(image[i:i + mb], True)
+                img.backward(dea[i:i + mb])
+            self._allreduce(txt.store.g)
+            self._allreduce(img.store.g)
+            bounds = None
+        else:
+            txt.backward(deb)
+            if self.overlap_allreduce:
+                self._allreduce(txt.store.g)              # overlaps with the image tower's backward
+            bounds = self._layer_boundaries(img) if (self.world > 1 and self.overlap_allreduce) else []
+        if bounds is None:
+            pass
+        elif bounds:
             st = img.store
             cuts = bounds + [st.total]
             state = {"hi": len(cuts) - 1}
@@ -123,6 +167,8 @@ class ContrastiveTrainer:
             self._allreduce(st.g[0:cuts[0]])
         else:
             img.backward(dea)
+            if not self.overlap_allreduce:
+                self._allreduce(txt.store.g)
             self._allreduce(img.store.g)
         self.ls_g[0:1].copy_(dS.reshape(1))
         self._allreduce(self.ls_g)

@@ -65,6 +65,15 @@ def _worker_loss(rank, world, port, q):
                     rel = ((got - want).abs().max() / want.abs().max()).item()
                     assert rel < 3e-2, (mode, eps, name, rel)
                 assert abs(s.grad.item() - sr.grad.item()) < 5e-3 * max(1.0, abs(sr.grad.item())), (mode, eps)
+                # the FUSED schedule (what the trainer runs: per-peer similarity GEMMs whose epilogues keep the logits in
+                # registers) against the materialising one just checked
+                from multimodal_b200.engine_loss import contrastive_schedule
+                f = contrastive_schedule(a0, b0, s.detach().reshape(1), eps, mode, False, world, rank, mask)
+                assert abs(f[0].item() - res.loss.item()) < 2e-5 * max(1.0, abs(res.loss.item())), (mode, eps)
+                for got, want, name in ((f[5], a.grad, "dA"), (f[6], b.grad, "dB")):
+                    rel = ((got - want).abs().max() / want.abs().max().clamp_min(1e-20)).item()
+                    assert rel < 1e-2, ("fused", mode, eps, name, rel)
+                assert abs(f[7].item() - s.grad.item()) < 1e-4 * max(1.0, abs(s.grad.item())), ("fused", mode, eps)
         q.put((rank, "ok"))
     finally:
         dist.destroy_process_group()

@@ -539,3 +539,75 @@ def test_weight_shadow_invalidation_after_data_write(dev):
         multimodal_b200.invalidate_weight_caches()
         e1 = m(img, txt).embeddings_a
     torch.testing.assert_close(e1, -e0, rtol=0, atol=1e-6)
+
+
+def test_micro_batched_recompute_step_equals_full_step(dev):
+    """ContrastiveTrainer.step(micro_batch=...) (two-pass activation recompute for BASELINE config 4) gives the loss and
+    the parameter gradients of the un-sliced step: the loss couples the whole batch, the towers are re-run per slice."""
+    import multimodal_b200.ops as ops
+    from multimodal_b200.modules.losses.contrastive_loss_with_temperature import ContrastiveLossWithTemperature
+    from multimodal_b200.train import ContrastiveTrainer
+
+    torch.manual_seed(0)
+    m1 = _small_clip(dev)
+    m2 = _small_clip(dev, {k: v.clone() for k, v in m1.state_dict().items()})
+    img, txt = O.synthetic_batch(64, image_size=64, vocab=512, device=dev)
+
+    def grads(model, mb):
+        tr = ContrastiveTrainer(model, ContrastiveLossWithTemperature().to(dev), lr=0.0, weight_decay=0.0)
+        orig, seen = ops.adamw_step, {}
+
+        def spy(p, g, *a, **kw):
+            seen[g.data_ptr()] = g.clone()
+            return orig(p, g, *a, **kw)
+
+        ops.adamw_step = spy
+        try:
+            loss = tr.step(img, txt, micro_batch=mb)
+        finally:
+            ops.adamw_step = orig
+        return loss.item(), seen[tr.img.store.g.data_ptr()], seen[tr.txt.store.g.data_ptr()], seen[tr.ls_g.data_ptr()]
+
+    l_full, gi, gt, gs = grads(m1, None)
+    l_mb, gi2, gt2, gs2 = grads(m2, 16)
+    assert abs(l_full - l_mb) < 1e-6, (l_full, l_mb)
+    # same kernels on the same rows; only the fp32 accumulation order of the weight gradients differs (4 slices)
+    assert _rel(gi2, gi) < 2e-3 and _rel(gt2, gt) < 2e-3, (_rel(gi2, gi), _rel(gt2, gt))
+    assert abs(gs[0].item() - gs2[0].item()) < 1e-5 * max(1.0, abs(gs[0].item()))
+
+
+@pytest.mark.parametrize("B,E,eps,masked", [(256, 512, 0.0, False), (256, 512, 0.1, True), (1000, 768, 0.05, False),
+                                           (64, 64, 0.0, False)])
+def test_fused_similarity_gemm_cross_entropy_matches_materialised_path(dev, gemm_mode, B, E, eps, masked):
+    """The fused loss (similarity GEMM whose epilogue keeps the logits in registers: online-softmax statistics forward,
+    d loss / d sims backward — mmb_gemm_ce_stats / mmb_ce_stats_reduce / mmb_gemm_ce_grad) against the schedule that
+    materialises fp32 logits, and against autograd over the oracle; both GEMM kernels (1-CTA and CTA-pair)."""
+    from multimodal_b200.engine_loss import contrastive_schedule
+    from multimodal_b200.utils.distributed import BackpropType
+
+    if gemm_mode[1] == 16:
+        pytest.skip("the cross-entropy epilogues use 8 epilogue warps")
+    torch.manual_seed(21)
+    a = O.normalize(torch.randn(B, E, device=dev))
+    b = O.normalize(torch.randn(B, E, device=dev))
+    s = torch.tensor([math.log(1 / 0.07)], device=dev)
+    mask = (torch.rand(B, device=dev) < 0.7) if masked else None
+    if mask is not None:
+        mask[0] = True
+    fused = contrastive_schedule(a, b, s, eps, BackpropType.GLOBAL, False, 1, 0, mask)
+    mat = contrastive_schedule(a, b, s, eps, BackpropType.GLOBAL, True, 1, 0, mask)
+    # same bf16 operands, same fp32 accumulators: only the reduction order and ex2/exp differ
+    assert abs(fused[0].item() - mat[0].item()) < 2e-5 * max(1.0, abs(mat[0].item()))
+    assert abs(fused[3].item() - mat[3].item()) < 2e-5 * max(1.0, abs(mat[3].item()))     # loss_a
+    assert abs(fused[4].item() - mat[4].item()) < 2e-5 * max(1.0, abs(mat[4].item()))     # loss_b
+    assert _rel(fused[5], mat[5]) < 1e-2 and _rel(fused[6], mat[6]) < 1e-2                # dA, dB (bf16 d sims)
+    assert abs(fused[7].item() - mat[7].item()) < 1e-4 * max(1.0, abs(mat[7].item()))     # d logit_scale
+    assert fused[1].numel() == 0                                                          # no logits were produced
+    a_r, b_r = a.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    s_r = s[0].clone().requires_grad_(True)
+    if mask is None:
+        ref = O.contrastive_loss(a_r, b_r, s_r, label_smoothing=eps)
+        ref[0].backward()
+        assert abs(fused[0].item() - ref[0].item()) < 3e-3
+        assert _rel(fused[5], a_r.grad) < 2e-2 and _rel(fused[6], b_r.grad) < 2e-2
+        assert abs(fused[7].item() - s_r.grad.item()) < 3e-3 * max(1.0, abs(s_r.grad.item()))
