@@ -358,10 +358,16 @@ attn_fwd_pp_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
       }
       mbar_wait(&s_full[grp], par);
       tc_fence_after();
-      const bool row_ok = qi < S;                        // padding rows of the last tile: no math, nothing stored
-      const int kv_lim = CAUSAL ? min(S, qi + 1) : S;    // columns >= kv_lim are masked
+      // tcgen05.ld / tcgen05.wait are .sync.aligned: every lane of the warp must execute them together, so all
+      // control flow around them is WARP-uniform.  A warp whose 32 rows are all padding (last tile) skips the math; in a
+      // partially valid warp the padding lanes run along on whatever their TMEM rows hold (finite or not, it stays in
+      // their own P rows / O rows, which are never stored).
+      const bool row_ok = qi < S;
+      const bool warp_ok = tile * 128 + q4 * 32 < S;     // uniform: the warp's first row is a real query
+      const int kv_lim = CAUSAL ? min(S, qi + 1) : S;    // columns >= kv_lim are masked (per lane)
+      const int kv_lim_w = CAUSAL ? min(S, tile * 128 + q4 * 32 + 32) : S;   // uniform bound over the warp's rows
       float mx = -INFINITY, sum = 0.f;
-      if (row_ok) {
+      if (warp_ok) {
         // ---- pass 1: row maximum (tcgen05.ld of step c+1 in flight while step c is reduced) ----
         uint32_t va[32], vb[32];
         auto ld = [&](int c, uint32_t (&v)[32]) {
@@ -384,7 +390,7 @@ attn_fwd_pp_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
             }
           }
         };
-        const int nc_act = CAUSAL ? min(nc32, (kv_lim + 31) >> 5) : nc32;   // steps that hold unmasked columns
+        const int nc_act = CAUSAL ? min(nc32, (kv_lim_w + 31) >> 5) : nc32;   // steps with unmasked columns (uniform)
         ld(0, va);
         for (int c = 0; c < nc_act; c += 2) {
           tmem_ld_wait();
@@ -448,7 +454,7 @@ attn_fwd_pp_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
       mbar_wait(&o_full[grp], par);
       tc_fence_after();
       uint32_t o0[32], o1[32];
-      if (row_ok) {
+      if (warp_ok) {      // uniform
         tmem_ld32(trow, o0);
         tmem_ld32(trow + 32, o1);
         tmem_ld_wait();

@@ -72,6 +72,6 @@ def test_fused_adamw_matches_torch_optim_adamw():
         assert gk.abs().max().item() == 0.0           # zero_grad fused
     st = opt.state[ref]
     torch.testing.assert_close(p, ref.data, rtol=1e-6, atol=1e-9)
-    torch.testing.assert_close(m, st["exp_avg"], rtol=1e-5, atol=1e-9)
+    torch.testing.assert_close(m, st["exp_avg"], rtol=1e-5, atol=2e-8)     # |m| ~ 5e-2; cancellation near zero
     torch.testing.assert_close(v, st["exp_avg_sq"], rtol=1e-5, atol=1e-12)
     assert torch.equal(shadow, p.bfloat16())
