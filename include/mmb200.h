@@ -163,6 +163,12 @@ int mmb_attention_bwd(const void* qkv, const void* out, const void* dout, const 
 int mmb_attention_fwd_kmask(const void* qkv, void* out, float* lse, const unsigned char* kmask, int B, int S, int H,
                             int head_dim, int causal, float scale, void* stream);
 
+/* Attention probabilities on request: probs fp32 [B,H,S,S] = exp(q.k*scale - lse) (0 where masked), recomputed from the
+ * packed QKV and the row LSE written by mmb_attention_fwd*.  Serves `TransformerOutput.attentions` of the FLAVA
+ * encoders (models/flava/transformer.py:255-293; modules/layers/attention.py:220-239 returns the softmax output). */
+int mmb_attention_probs(const void* qkv, const float* lse, const unsigned char* kmask, float* probs, int B, int S, int H,
+                        int causal, float scale, void* stream);
+
 /* ---- FLAVA encoder front/back ends (config 3, forward) -------------------------------------------------------- */
 /* x = LayerNorm(word[ids] + pos[arange(S)] + type[type_ids or 0]) — BERTTextEmbeddings.forward,
  * modules/layers/text_embedding.py:70-104.  ids/type_ids int64 (bit-exact gathers).  kmask_out (optional) receives

@@ -32,6 +32,7 @@ PROTOTYPES = {
     "mmb_attention_fwd": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, f32, vp]),
     "mmb_attention_bwd": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, vp]),
     "mmb_attention_fwd_kmask": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, vp]),
+    "mmb_attention_probs": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, f32, vp]),
     "mmb_bert_embed_ln_fwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, ll, i32, i32, i32, i32, f32, vp]),
     "mmb_vit_assemble_fwd": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]),
     "mmb_gather_rows_cast": (i32, [vp, vp, i32, i32, i32, i32, vp]),

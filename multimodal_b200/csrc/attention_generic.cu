@@ -208,6 +208,70 @@ static int launch_generic(const AttnGenArgs& a, int B, cudaStream_t st) {
   return (int)cudaGetLastError();
 }
 
+
+
+// ------------------------------------------------------------------------------------------------
+// Attention PROBABILITIES on request: probs[b, h, i, j] = exp(q_i . k_j * scale - lse[b, h, i]) (0 where the key
+// padding mask / causal mask removes the key), fp32 [B, H, S, S].  The fused attention kernels never materialise
+// them; FLAVA's encoders return them (`TransformerOutput.attentions`, models/flava/transformer.py:255-293 via
+// modules/layers/attention.py:220-239), so they are recomputed from the packed QKV and the row LSE the forward
+// kernel already produced.  Memory-bound on the fp32 output (S*S*4 B per head); SIMT dot products from padded smem.
+// Grid (ceil(S/32), H, B), 256 threads: 8 warps x 4 query rows, lanes over keys.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+attn_probs_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ lse, const uint8_t* __restrict__ kmask,
+                  float* __restrict__ probs, int S, int H, int causal, float scale_log2) {
+  extern __shared__ uint8_t psm[];
+  constexpr int PITCH = 144;                 // 64 bf16 + 16 B pad: 9 x 16 B per row -> conflict-free 16 B row reads
+  uint8_t* sK = psm;                         // [S][PITCH]
+  uint8_t* sQ = psm + (size_t)S * PITCH;     // [32][PITCH]
+  const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int d = H * 64;
+  const long long row0 = (long long)b * S;
+  for (int idx = threadIdx.x; idx < S * 8; idx += 256) {          // K rows of this head: 8 x 16 B each
+    const int j = idx >> 3, c = idx & 7;
+    *reinterpret_cast<uint4*>(sK + j * PITCH + c * 16) =
+        *reinterpret_cast<const uint4*>(qkv + (row0 + j) * 3 * d + d + h * 64 + c * 8);
+  }
+  for (int idx = threadIdx.x; idx < 32 * 8; idx += 256) {
+    const int i = idx >> 3, c = idx & 7, qi = qb * 32 + i;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (qi < S) v = *reinterpret_cast<const uint4*>(qkv + (row0 + qi) * 3 * d + h * 64 + c * 8);
+    *reinterpret_cast<uint4*>(sQ + i * PITCH + c * 16) = v;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int rr = 0; rr < 4; ++rr) {
+    const int i = warp * 4 + rr, qi = qb * 32 + i;
+    if (qi >= S) break;
+    float q[64];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const uint4 v = *reinterpret_cast<const uint4*>(sQ + i * PITCH + c * 16);   // broadcast
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { q[c * 8 + 2 * e] = bf16_lo(w[e]); q[c * 8 + 2 * e + 1] = bf16_hi(w[e]); }
+    }
+    const float l2 = lse[((long long)b * H + h) * S + qi] * 1.4426950408889634f;
+    float* out = probs + (((long long)b * H + h) * S + qi) * S;
+    for (int j = lane; j < S; j += 32) {
+      float acc = 0.f;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const uint4 v = *reinterpret_cast<const uint4*>(sK + j * PITCH + c * 16);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          acc = fmaf(q[c * 8 + 2 * e], bf16_lo(w[e]), acc);
+          acc = fmaf(q[c * 8 + 2 * e + 1], bf16_hi(w[e]), acc);
+        }
+      }
+      const bool keep = (!causal || j <= qi) && (!kmask || kmask[row0 + j]);
+      out[j] = keep ? ex2_approx(fmaf(acc, scale_log2, -l2)) : 0.f;
+    }
+  }
+}
+
 }  // namespace mmb
 
 using namespace mmb;
@@ -233,4 +297,16 @@ extern "C" int mmb_attention_fwd_generic(const void* q, long long ldq, long long
     case 128: return launch_generic<128>(a, B, st);
     default: return MMB_ERR_UNSUPPORTED;
   }
+}
+
+// probs fp32 [B, H, S, S] from the packed QKV [B*S, 3*H*64] and the forward's row LSE [B, H, S] (head_dim 64).
+extern "C" int mmb_attention_probs(const void* qkv, const float* lse, const unsigned char* kmask, float* probs, int B,
+                                   int S, int H, int causal, float scale, void* stream) {
+  if (B <= 0 || S <= 0 || H <= 0 || !qkv || !lse || !probs) return MMB_ERR_ARG;
+  const int smem = (S + 32) * 144;
+  if (smem > 200 * 1024) return MMB_ERR_UNSUPPORTED;
+  cudaFuncSetAttribute(attn_probs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  attn_probs_kernel<<<dim3((S + 31) / 32, H, B), 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
+      (const __nv_bfloat16*)qkv, lse, kmask, probs, S, H, causal, scale * 1.4426950408889634f);
+  return (int)cudaGetLastError();
 }

@@ -8,8 +8,10 @@ Reference call stack: models/flava/model.py:127-298, models/flava/image_encoder.
 modules/encoders/bert_text_encoder.py:67-120, models/flava/transformer.py:47-77,155-176,255-293,
 modules/layers/attention.py:120-241, modules/losses/flava.py:84-97.
 
-Deviation (documented in DESIGN.md): ``TransformerOutput.attentions`` is ``None`` — the flash-style kernel never
-materialises the [B, H, S, S] probabilities (477 MB fp32 per layer at B=256); nothing in the library consumes them.
+``TransformerOutput.attentions``: the flash-style kernel never materialises the [B, H, S, S] probabilities (477 MB
+fp32 per layer at B=256) and nothing in the library consumes them, so they are produced ON REQUEST only
+(`module.output_attentions = True`, or `return_attn_weights=True` on the text encoder): one extra kernel per layer
+recomputes them from the packed QKV and the row LSE.  Default: ``None`` (documented deviation).
 Every tensor of the returned ``TransformerOutput`` is allocated per call (as the reference's are); only internal
 scratch is reused between forwards.
 """
@@ -93,7 +95,10 @@ class FlavaStack:
         self.ws = Workspace(dev)
         self.sh = _Shadows(dev)
 
-    def forward(self, X0: torch.Tensor, B: int, S: int, kmask: Optional[torch.Tensor] = None) -> TransformerOutput:
+    def forward(self, X0: torch.Tensor, B: int, S: int, kmask: Optional[torch.Tensor] = None,
+                want_attn: bool = False) -> TransformerOutput:
+        """want_attn: also return every layer's attention probabilities fp32 [B, H, S, S] (`attentions`), recomputed
+        from the packed QKV and the row LSE of the fused attention kernel (mmb_attention_probs)."""
         d, ff, H, ws, sh = self.d, self.ff, self.H, self.ws, self.sh
         M = B * S
         bf, f32 = torch.bfloat16, torch.float32
@@ -106,6 +111,8 @@ class FlavaStack:
         PRE = ws.get(f"{pfx}.PRE", (M, ff), bf)
         HACT = ws.get(f"{pfx}.HACT", (M, ff), bf)
         hidden: List[torch.Tensor] = [X0.view(B, S, d)]
+        attns: Optional[List[torch.Tensor]] = [] if want_attn else None
+        LSE = ws.get(f"{pfx}.LSE", (B * H * S,), f32) if want_attn else None
         XA = X0
         for l, layer in enumerate(self.layers):
             at, mlp = layer.attention, layer.feedforward.model
@@ -123,9 +130,13 @@ class FlavaStack:
                 ops.add_layernorm_fwd(XA, None, None, LN, None, ln1.weight, ln1.bias, None, None, M, d, ln1.eps)
             ops.gemm(LN, wqkv, bias=bqkv, out=QKV)
             if kmask is not None:
-                ops.attention_fwd_kmask(QKV, O, None, kmask, B, S, H, False, 0.125)
+                ops.attention_fwd_kmask(QKV, O, LSE, kmask, B, S, H, False, 0.125)
             else:
-                ops.attention_fwd(QKV, O, None, B, S, H, False, 0.125)
+                ops.attention_fwd(QKV, O, LSE, B, S, H, False, 0.125)
+            if want_attn:
+                P = torch.empty((B, H, S, S), device=self.device, dtype=f32)
+                ops.attention_probs(QKV, LSE, kmask, P, B, S, H, False, 0.125)
+                attns.append(P)
             ops.gemm(O, wo, bias=at.output.bias, out=Y)
             ops.add_layernorm_fwd(XA, Y, XM, LN, None, ln2.weight, ln2.bias, None, None, M, d, ln2.eps)
             ops.gemm(LN, w1, bias=mlp[0].bias, epilogue=ops.EPI_BF16_ACT, out=PRE, out2=HACT, act=self.act)
@@ -146,7 +157,7 @@ class FlavaStack:
                      out=pooled)
             ops.tanh_(pooled)
         return TransformerOutput(last_hidden_state=LAST.view(B, S, d), pooler_output=pooled, hidden_states=hidden,
-                                 attentions=None)
+                                 attentions=attns)
 
     def project_first_token(self, last_hidden_state: torch.Tensor, linear: nn.Linear, key: str) -> torch.Tensor:
         """linear(last_hidden_state[:, 0, :]) (models/flava/model.py:244-246, 261-263)."""
@@ -163,7 +174,8 @@ class FlavaImageRuntime:
         self.mod = mod
         self.stack = FlavaStack(mod.encoder, mod.layernorm, mod.pooler, "fimg")
 
-    def forward(self, pixel_values: torch.Tensor, image_patches_mask: Optional[torch.Tensor] = None) -> TransformerOutput:
+    def forward(self, pixel_values: torch.Tensor, image_patches_mask: Optional[torch.Tensor] = None,
+                want_attn: bool = False) -> TransformerOutput:
         emb, st = self.mod.embeddings, self.stack
         ws, sh, d = st.ws, st.sh, st.d
         conv = emb.patch_embeddings.projection
@@ -190,7 +202,7 @@ class FlavaImageRuntime:
             pm = image_patches_mask.reshape(B, P).to(torch.uint8).contiguous()
         ops.vit_assemble_fwd(PO, emb.cls_token, emb.position_embeddings, emb.mask_token if pm is not None else None, pm, X0,
                              B, S, d)
-        return st.forward(X0, B, S)
+        return st.forward(X0, B, S, want_attn=want_attn)
 
 
 class FlavaTextRuntime:
@@ -199,7 +211,7 @@ class FlavaTextRuntime:
         self.stack = FlavaStack(mod.encoder, mod.layernorm, mod.pooler, "ftxt")
 
     def forward(self, input_ids: torch.Tensor, attention_mask: Optional[torch.Tensor] = None,
-                token_type_ids: Optional[torch.Tensor] = None) -> TransformerOutput:
+                token_type_ids: Optional[torch.Tensor] = None, want_attn: bool = False) -> TransformerOutput:
         emb, st = self.mod.embeddings, self.stack
         ws, d = st.ws, st.d
         ids = input_ids.long().contiguous()
@@ -216,7 +228,7 @@ class FlavaTextRuntime:
             if attention_mask.dim() != 2:
                 raise NotImplementedError("only [batch, seq_len] padding masks are supported on the accelerated path")
             KM = (attention_mask != 0).to(torch.uint8).contiguous().view(-1)
-        return st.forward(X0, B, S, kmask=KM)
+        return st.forward(X0, B, S, kmask=KM, want_attn=want_attn)
 
 
 class FlavaMMRuntime:
@@ -224,7 +236,7 @@ class FlavaMMRuntime:
         self.mod = mod
         self.stack = FlavaStack(mod.encoder, mod.layernorm, mod.pooler, "fmm")
 
-    def forward(self, hidden_states: torch.Tensor) -> TransformerOutput:
+    def forward(self, hidden_states: torch.Tensor, want_attn: bool = False) -> TransformerOutput:
         """hidden_states: fp32 [B, S, d] (already projected and concatenated image|text tokens)."""
         st = self.stack
         B, S, d = hidden_states.shape
@@ -236,10 +248,10 @@ class FlavaMMRuntime:
             S += 1
         else:
             X0 = hs.view(B * S, d)
-        return st.forward(X0, B, S)
+        return st.forward(X0, B, S, want_attn=want_attn)
 
     def forward_projected(self, image_hidden: torch.Tensor, text_hidden: torch.Tensor, image_proj: nn.Linear,
-                          text_proj: nn.Linear) -> TransformerOutput:
+                          text_proj: nn.Linear, want_attn: bool = False) -> TransformerOutput:
         """FLAVAModel.encode_mm (models/flava/model.py:283-298): project both token streams to the multimodal width
         (two tcgen05 GEMMs, fp32 out + bias), then [cls | image | text] assembled by one kernel straight into X0."""
         st = self.stack
@@ -261,4 +273,4 @@ class FlavaMMRuntime:
         S = Si + St + (1 if cls is not None else 0)
         X0 = torch.empty((B * S, d), device=image_hidden.device, dtype=f32)   # returned as hidden_states[0]
         ops.concat_tokens(cls, Pi, Pt, X0, B, Si, St, d)
-        return st.forward(X0, B, S)
+        return st.forward(X0, B, S, want_attn=want_attn)

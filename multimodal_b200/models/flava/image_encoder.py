@@ -79,7 +79,7 @@ class ImageTransformer(_RuntimeOwner):
                 f"Input image size ({height}*{width}) doesn't match model ({pe.image_size[0]}*{pe.image_size[1]}).")
         if image_patches_mask is not None and self.embeddings.mask_token is None:
             warnings.warn("image_patches_mask passed but use_image_masking in init was false. Ignoring.")
-        return self._runtime().forward(pixel_values, image_patches_mask)
+        return self._runtime().forward(pixel_values, image_patches_mask, want_attn=bool(getattr(self, "output_attentions", False)))
 
 
 def _img_runtime(mod):

@@ -124,10 +124,21 @@ class FLAVAModel(nn.Module):
             return encoded_image, projected_embeddings
         return encoded_image
 
+    def set_output_attentions(self, flag: bool = True) -> "FLAVAModel":
+        """The reference always returns `TransformerOutput.attentions` ([B, H, S, S] fp32 per layer).  Here they cost an
+        extra kernel and 4*S*S bytes per head and layer, so they are opt-in: call this (or set `.output_attentions`
+        on an individual encoder) to get them; otherwise `attentions` is None."""
+        self.output_attentions = bool(flag)
+        for enc in (self.image_encoder, self.text_encoder, self.mm_encoder):
+            if enc is not None:
+                enc.output_attentions = bool(flag)
+        return self
+
     @torch.no_grad()
     def encode_text(self, text: Tensor, text_mask: Optional[Tensor] = None, projection: bool = False
                     ) -> Union[Tuple[TransformerOutput, Tensor], Optional[TransformerOutput]]:
-        encoded_text = self.text_encoder(input_ids=text, attention_mask=text_mask, return_attn_weights=True,
+        encoded_text = self.text_encoder(input_ids=text, attention_mask=text_mask,
+                                         return_attn_weights=bool(getattr(self, "output_attentions", False)),
                                          return_hidden_states=True)
         if projection:
             projected_embeddings = self._project_cls(self.text_encoder, encoded_text, self.text_projection, "tproj")
@@ -149,8 +160,9 @@ class FLAVAModel(nn.Module):
     def encode_mm(self, image_embedding: Tensor, text_embedding: Tensor) -> TransformerOutput:
         if image_embedding is None or text_embedding is None:
             return TransformerOutput()
-        return self.mm_encoder._runtime().forward_projected(image_embedding, text_embedding,
-                                                            self.image_to_mm_projection, self.text_to_mm_projection)
+        return self.mm_encoder._runtime().forward_projected(
+            image_embedding, text_embedding, self.image_to_mm_projection, self.text_to_mm_projection,
+            want_attn=bool(getattr(self.mm_encoder, "output_attentions", False)))
 
 
 def flava_model(

@@ -107,7 +107,7 @@ class FLAVATransformerWithoutEmbeddings(_RuntimeOwner):
             raise ValueError("You have to specify hidden_states")
         if attention_mask is not None:
             raise NotImplementedError("attention_mask on the multimodal encoder is not on the accelerated path")
-        return self._runtime().forward(hidden_states)
+        return self._runtime().forward(hidden_states, want_attn=bool(getattr(self, "output_attentions", False)))
 
 
 def _mm_runtime(mod):

@@ -3,8 +3,9 @@ state-dict keys and argument meaning; the forward is `engine_flava.FlavaTextRunt
 pad-derived key mask consumed by the tcgen05 attention kernel, fused layer stack, layernorm, pooler).
 
 On the accelerated path: `input_ids` (required), `attention_mask` of shape [batch, seq_len], `token_type_ids`.
-`position_ids` / `inputs_embeds` raise NotImplementedError; `return_attn_weights` is accepted and yields
-``attentions=None`` (flash-style attention never materialises the probabilities)."""
+`position_ids` / `inputs_embeds` raise NotImplementedError; `return_attn_weights=True` returns the
+per-layer attention probabilities (recomputed from QKV + row LSE by mmb_attention_probs; the fused attention kernel
+itself never materialises them)."""
 from typing import Callable, Optional
 
 import torch
@@ -37,7 +38,7 @@ class BERTTextEncoder(_RuntimeOwner):
             raise NotImplementedError("inputs_embeds / position_ids are not on the accelerated path")
         if self.layernorm is None:
             raise NotImplementedError("BERTTextEncoder without a final layernorm is not on the accelerated path")
-        out = self._runtime().forward(input_ids, attention_mask, token_type_ids)
+        out = self._runtime().forward(input_ids, attention_mask, token_type_ids, want_attn=bool(return_attn_weights))
         if not return_hidden_states:
             out = out._replace(hidden_states=None)
         return out

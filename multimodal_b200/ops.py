@@ -326,6 +326,12 @@ def attention_fwd_kmask(qkv, out, lse, kmask, B, S, H, causal, scale):
                                                   float(scale), _stream()), "mmb_attention_fwd_kmask")
 
 
+def attention_probs(qkv, lse, kmask, probs, B, S, H, causal, scale):
+    _chk(qkv, torch.bfloat16, "qkv"); _chk(lse, torch.float32, "lse"); _chk(probs, torch.float32, "probs")
+    _lib.check(_lib.lib().mmb_attention_probs(_p(qkv), _p(lse), _p(kmask), _p(probs), B, S, H, int(causal), float(scale),
+                                              _stream()), "mmb_attention_probs")
+
+
 def bert_embed_ln_fwd(ids, type_ids, word, pos, type_emb, gamma, beta, x, kmask_out, pad_id, B, S, d, V, eps):
     _chk(ids, torch.int64, "ids")
     _lib.check(_lib.lib().mmb_bert_embed_ln_fwd(_p(ids), _p(type_ids), _p(word), _p(pos), _p(type_emb), _p(gamma), _p(beta),

@@ -90,6 +90,41 @@ def test_attention_fwd_key_padding_mask(dev, B, S, H):
     ref = (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(B * S, d)
     err = (out.float() - ref).abs().max().item()
     assert err < 2e-2, err  # bf16 P and bf16 output rounding on |o| <~ 3
+    # attention probabilities on request (TransformerOutput.attentions): recomputed from QKV + the forward's row LSE
+    lse = torch.empty(B * H * S, device=dev)
+    kmf = km.to(torch.uint8).contiguous().view(-1)
+    ops.attention_fwd_kmask(qkv, out, lse, kmf, B, S, H, False, 0.125)
+    probs = torch.empty(B, H, S, S, device=dev)
+    ops.attention_probs(qkv, lse, kmf, probs, B, S, H, False, 0.125)
+    torch.testing.assert_close(probs, torch.softmax(s, -1), rtol=2e-3, atol=2e-5)   # fp32 dot products, ex2.approx
+    assert (probs.sum(-1) - 1).abs().max().item() < 1e-3
+    assert probs.masked_select(~km[:, None, None, :].expand_as(probs)).abs().max().item() == 0.0
+
+
+def test_flava_attentions_on_request(dev):
+    """`TransformerOutput.attentions` (always returned by the reference: models/flava/image_encoder.py:220-233) is
+    opt-in here: None by default, one [B, H, S, S] tensor per layer after `set_output_attentions()`; the probabilities
+    must reproduce the layer's attention output when applied to V, i.e. they ARE what the fused kernel used."""
+    from multimodal_b200.models.flava import flava_model
+
+    name = "flava_small"
+    g = torch.load(GOLD)[name]
+    m = FC.build(flava_model, name).to(dev)
+    inp = {k: v.to(dev) for k, v in g["inputs"].items()}
+    o = m(image=inp["image"], text=inp["text"])
+    assert o.image.attentions is None and o.text.attentions is None
+    m.set_output_attentions(True)
+    o2 = m(image=inp["image"], text=inp["text"], skip_unmasked_mm_encoder=False)
+    for part, out in (("image", o2.image), ("text", o2.text), ("multimodal", o2.multimodal)):
+        att = out.attentions
+        n_layers = len(out.hidden_states) - 1
+        assert att is not None and len(att) == n_layers, part
+        B, S = out.last_hidden_state.shape[:2]
+        for a in att:
+            assert a.shape[0] == B and a.shape[2] == a.shape[3] == S and a.dtype == torch.float32
+            rows = a.sum(-1)
+            assert torch.isfinite(a).all() and (rows - 1).abs().max().item() < 2e-3, part
+    torch.testing.assert_close(o2.image.last_hidden_state, o.image.last_hidden_state)   # asking does not change results
 
 
 @pytest.mark.parametrize("name", list(FC.CASES))
