@@ -149,6 +149,9 @@ int mmb_anyprecision_adamw_step(float* p, float* g, void* m, int m_dtype, void* 
                                 double eps, double weight_decay, int step, float grad_scale, int zero_grad,
                                 void* stream);
 int mmb_memset_async(void* p, int value, long long bytes, void* stream);
+/* Standalone activation, fp32: kind MMB_ACT_QUICK_GELU = x*sigmoid(1.702x) (modules/layers/activation.py:24-25),
+ * MMB_ACT_GELU_ERF = nn.GELU().  (Inside the encoders the activation is a GEMM epilogue.) */
+int mmb_act_fwd(const float* x, float* y, long long n, int kind, void* stream);
 
 /* ---- attention --------------------------------------------------------------------------------------------- */
 /* O = softmax(Q K^T * scale [+ causal mask]) V per (batch, head), head_dim 64, S <= 384 (tcgen05 kernels; larger S

@@ -28,6 +28,7 @@ PROTOTYPES = {
     "mmb_l2norm_bwd": (i32, [vp, vp, vp, vp, vp, i32, i32, vp]),
     "mmb_adamw_step": (i32, [vp, vp, vp, vp, vp, ll, f32, f32, f32, f32, f32, i32, f32, i32, vp]),
     "mmb_anyprecision_adamw_step": (i32, [vp, vp, vp, i32, vp, i32, vp, i32, vp, ll, f64, f64, f64, f64, f64, i32, f32, i32, vp]),
+    "mmb_act_fwd": (i32, [vp, vp, ll, i32, vp]),
     "mmb_memset_async": (i32, [vp, i32, ll, vp]),
     "mmb_attention_fwd": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, f32, vp]),
     "mmb_attention_bwd": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, vp]),

@@ -759,6 +759,16 @@ __global__ void anyprecision_adamw_kernel(float* __restrict__ p, float* __restri
   }
 }
 
+
+// Standalone activation (the encoders fuse it into the FC1 GEMM epilogue; this serves `SiLU()(x)` / `nn.GELU` called
+// on their own): y = x * sigmoid(1.702 x) (activation.py:24-25) or exact-erf GELU, fp32 in / out.
+__global__ void act_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, long long n, int kind) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = x[i];
+    y[i] = kind == ACT_QUICK_GELU ? v / (1.f + __expf(-1.702f * v)) : 0.5f * v * (1.f + erff(v * 0.70710678118654752f));
+  }
+}
+
 }  // namespace mmb
 
 using namespace mmb;
@@ -975,5 +985,12 @@ extern "C" int mmb_anyprecision_adamw_step(float* p, float* g, void* m, int m_dt
   else AP_COMP(bf, bf);
 #undef AP_COMP
 #undef AP_LAUNCH
+  return LAUNCH_RC();
+}
+
+extern "C" int mmb_act_fwd(const float* x, float* y, long long n, int kind, void* stream) {
+  if (n <= 0) return MMB_OK;
+  if (kind != ACT_QUICK_GELU && kind != ACT_GELU_ERF) return MMB_ERR_ARG;
+  act_fwd_kernel<<<grid_for(n, 256), 256, 0, ST(stream)>>>(x, y, n, kind);
   return LAUNCH_RC();
 }

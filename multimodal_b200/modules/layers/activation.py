@@ -2,7 +2,7 @@
 
 ``SiLU`` is the reference's (mis)named QuickGELU, ``sigmoid(1.702 x) * x``.  In this package it only TAGS which fused
 GEMM epilogue a transformer stack uses (``multimodal_b200.ops.ACT_QUICK_GELU``); the arithmetic lives in
-``csrc/gemm.cu``.  Calling it on a CUDA tensor is not part of the hot path and is therefore not provided.
+``csrc/gemm.cu``.  Called on its own on a CUDA tensor it runs one elementwise kernel (forward values).
 """
 from torch import nn, Tensor
 
@@ -13,4 +13,13 @@ class SiLU(nn.Module):
     r"""QuickGELU marker: :math:`x \cdot \sigma(1.702 x)` (computed inside the FC1 GEMM epilogue)."""
 
     def forward(self, x: Tensor) -> Tensor:
-        raise MMBError("SiLU (QuickGELU) is fused into the MLP GEMM epilogue; it is not a standalone op here")
+        """Standalone: one elementwise kernel (values only; inside the encoders it is the FC1 GEMM epilogue)."""
+        import torch
+
+        from ... import ops
+
+        if torch.is_grad_enabled() and x.requires_grad:
+            raise MMBError("standalone SiLU (QuickGELU) has no autograd path; it is fused inside the encoder runtimes")
+        if not x.is_cuda:
+            raise MMBError("SiLU: expected a CUDA tensor (multimodal_b200 has no CPU path)")
+        return ops.act_fwd(x.contiguous().float(), ops.ACT_QUICK_GELU).to(x.dtype)

@@ -30,4 +30,7 @@ class MLP(nn.Module):
         self.model = nn.Sequential(*layers)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        raise MMBError("MLP is fused into the encoder runtime (GEMM + activation epilogue); not a standalone op here")
+        """Standalone forward (values only) of the [Linear, activation, Linear] form: GEMM + fused activation, GEMM."""
+        from ...engine_layers import mlp_forward
+
+        return mlp_forward(self, x)

@@ -2,7 +2,7 @@
 (`MultiHeadSelfAttention` with the fused ``input_proj [3d, d]``; `MultiHeadAttentionWithCache` with separate
 ``q_proj / k_proj / v_proj / output_proj``).  They execute inside the owning encoder / decoder / pooler runtime
 (engine_coca.py): packed-QKV tcgen05 GEMM + attention kernel; F.scaled_dot_product_attention is never called."""
-from typing import Any
+from typing import Any, Optional
 
 from torch import nn, Tensor
 
@@ -17,8 +17,11 @@ class MultiHeadSelfAttention(nn.Module):
         self.num_heads = num_heads
         self.dropout = dropout
 
-    def forward(self, *args: Any, **kwargs: Any) -> Tensor:
-        raise MMBError("MultiHeadSelfAttention is fused into the encoder runtime; not a standalone op here")
+    def forward(self, query: Tensor, attn_mask: Optional[Tensor] = None, is_causal: bool = False) -> Tensor:
+        """Standalone forward (values only): packed in-projection GEMM -> attention kernel -> out-projection GEMM."""
+        from ...engine_layers import mhsa_forward
+
+        return mhsa_forward(self, query, attn_mask, is_causal)
 
 
 class MultiHeadAttentionWithCache(nn.Module):

@@ -56,5 +56,8 @@ class PatchEmbeddings(nn.Module):
         assert self.conv_projection.bias is not None
         nn.init.zeros_(self.conv_projection.bias)
 
-    def forward(self, *args: Any, **kwargs: Any) -> PatchEmbeddingsOutput:
-        raise MMBError("PatchEmbeddings runs inside VisionTransformer's fused runtime; not a standalone op here")
+    def forward(self, image: Tensor, image_patches_mask: Optional[Tensor] = None) -> PatchEmbeddingsOutput:
+        """Standalone forward (values only): im2col + tcgen05 GEMM + token assembly, as inside VisionTransformer."""
+        from ...engine_layers import patch_embeddings_forward
+
+        return patch_embeddings_forward(self, image, image_patches_mask)

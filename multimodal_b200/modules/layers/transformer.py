@@ -2,7 +2,8 @@
 CoCa encoder returns) and the parameter containers `TransformerEncoderLayer` / `TransformerEncoder` (:31-259) and
 `TransformerDecoderLayer` / `TransformerDecoder` (:262-657) — same constructors, state-dict keys and creation order.
 The layers execute inside `engine_coca.LayerStack` (fused kernels), owned by VisionTransformer / CoCaTextDecoder /
-CoCaMultimodalDecoder."""
+CoCaMultimodalDecoder; `TransformerEncoderLayer` / `TransformerEncoder` are also callable on their own (forward values,
+same kernels: `engine_layers.py`).  The decoder classes stay containers (KV-cache decoding is outside the path)."""
 from typing import Any, Callable, List, NamedTuple, Optional, Tuple
 
 from torch import nn, Tensor
@@ -44,8 +45,11 @@ class TransformerEncoderLayer(nn.Module):
         self.feedforward_layernorm = Fp32LayerNorm(d_model, eps=layer_norm_eps)
         self.norm_first = norm_first
 
-    def forward(self, *args: Any, **kwargs: Any) -> Tensor:
-        raise MMBError("TransformerEncoderLayer runs inside its encoder's fused runtime; not a standalone op here")
+    def forward(self, hidden_states: Tensor, attention_mask: Optional[Tensor] = None) -> Tensor:
+        """Standalone forward (values only; inside VisionTransformer the layer runs in the fused LayerStack)."""
+        from ...engine_layers import encoder_layer_forward
+
+        return encoder_layer_forward(self, hidden_states, attention_mask)
 
 
 class TransformerEncoder(nn.Module):
@@ -62,8 +66,12 @@ class TransformerEncoder(nn.Module):
         if final_layer_norm_eps:
             self.final_layer_norm = Fp32LayerNorm(d_model, eps=final_layer_norm_eps)
 
-    def forward(self, *args: Any, **kwargs: Any) -> TransformerOutput:
-        raise MMBError("TransformerEncoder runs inside VisionTransformer's fused runtime; not a standalone op here")
+    def forward(self, hidden_states: Tensor, attention_mask: Optional[Tensor] = None,
+                return_hidden_states: bool = False) -> TransformerOutput:
+        """Standalone forward (values only; inside VisionTransformer the stack runs in the fused LayerStack)."""
+        from ...engine_layers import encoder_forward
+
+        return encoder_forward(self, hidden_states, attention_mask, return_hidden_states)
 
 
 class TransformerDecoderLayer(nn.Module):

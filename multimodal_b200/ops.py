@@ -222,6 +222,15 @@ def anyprecision_adamw_step(p, g, m, v, comp, p_bf16, lr, beta1, beta2, eps, wd,
         int(zero_grad), _stream()), "mmb_anyprecision_adamw_step")
 
 
+def act_fwd(x: torch.Tensor, kind: int) -> torch.Tensor:
+    _chk(x, torch.float32, "x")
+    if not x.is_contiguous():
+        raise MMBError("act_fwd: x must be contiguous")
+    y = torch.empty_like(x)
+    _lib.check(_lib.lib().mmb_act_fwd(_p(x), _p(y), x.numel(), int(kind), _stream()), "mmb_act_fwd")
+    return y
+
+
 def zero_(t: torch.Tensor):
     if not t.is_cuda or not t.is_contiguous():
         raise MMBError("zero_: expected a contiguous CUDA tensor")
