@@ -74,3 +74,13 @@ class L2NormalizeFunction(torch.autograd.Function):
 
 def l2_normalize(x: torch.Tensor, eps: float = 1e-12) -> torch.Tensor:
     return L2NormalizeFunction.apply(x, eps)
+
+
+def autocast_out(t: torch.Tensor) -> torch.Tensor:
+    """Dtype convention of the reference under ``torch.autocast`` (examples/flava/native/train.py:296-298): the towers'
+    last op is a matmul / Linear, whose autocast output is the autocast dtype (bf16).  The kernels always produce fp32
+    embeddings; inside an autocast region they are cast at the module boundary (differentiably), outside they stay fp32
+    as the reference's fp32 modules return."""
+    if t.is_cuda and torch.is_autocast_enabled():
+        return t.to(torch.get_autocast_gpu_dtype())
+    return t

@@ -9,6 +9,7 @@ import torch
 from torch import nn, Tensor
 
 from ...autograd import TowerFunction
+from ...autograd import autocast_out as _autocast_out
 from ...engine import watch_module, ViTTower
 from ...modules.layers.activation import SiLU
 from ...modules.layers.normalizations import Fp32LayerNorm
@@ -61,4 +62,4 @@ class CLIPViTEncoder(nn.Module):
             raise ValueError(f"Expected 3 channels found {x.size(1)}")
         rt = self._runtime()
         params = rt.store.params if torch.is_grad_enabled() else ()
-        return TowerFunction.apply(rt, x, *params)
+        return _autocast_out(TowerFunction.apply(rt, x, *params))

@@ -10,6 +10,8 @@ from torch import nn, Tensor
 from torch.nn import TransformerEncoder, TransformerEncoderLayer
 
 from ...autograd import TowerFunction
+from ..._lib import MMBError
+from ...autograd import autocast_out as _autocast_out
 from ...engine import watch_module, TextTower
 from ...modules.layers.activation import SiLU
 from ...modules.layers.normalizations import Fp32LayerNorm
@@ -77,9 +79,10 @@ class CLIPTextEncoder(nn.Module):
         rt = self._runtime()
         if return_hidden_state:
             if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-                # TODO: hidden-state output has no backward schedule yet (not on the contrastive path)
-                with torch.no_grad():
-                    return rt.forward(text, False, return_hidden_state=True)
-            return rt.forward(text, False, return_hidden_state=True)
+                # the [B, 77, width] hidden-state output is not on the contrastive path and has no backward schedule:
+                # returning a detached tensor would silently drop the gradient, so refuse instead
+                raise MMBError("CLIPTextEncoder(return_hidden_state=True) returns forward values only (no backward "
+                               "schedule for the per-token output); call it under torch.no_grad()")
+            return _autocast_out(rt.forward(text, False, return_hidden_state=True))
         params = rt.store.params if torch.is_grad_enabled() else ()
-        return TowerFunction.apply(rt, text, *params)
+        return _autocast_out(TowerFunction.apply(rt, text, *params))

@@ -17,7 +17,7 @@ if ! grep -q " passed" gpurun_out/r2a_gate_attn.log || grep -q "failed" gpurun_o
 fi
 echo "MMB_ATTN_FWD=$MMB_ATTN_FWD MMB_ATTN_BWD=$MMB_ATTN_BWD" > gpurun_out/r2a_variants.txt
 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2a_smoke.log 2>&1; echo "smoke rc=$?" >> gpurun_out/r2a_smoke.log
-for f in tests/test_gpu_optim.py tests/test_gpu_parity.py tests/test_gpu_flava.py tests/test_gpu_coca.py tests/test_gpu_distributed.py; do
+for f in tests/test_gpu_optim.py tests/test_gpu_parity.py tests/test_gpu_layers.py tests/test_gpu_flava.py tests/test_gpu_coca.py tests/test_gpu_distributed.py; do
   timeout 900 python -m pytest $f -q -m gpu -s --timeout=600 > gpurun_out/r2a_$(basename $f .py).log 2>&1
   echo "rc=$?" >> gpurun_out/r2a_$(basename $f .py).log
 done

@@ -611,3 +611,28 @@ def test_fused_similarity_gemm_cross_entropy_matches_materialised_path(dev, gemm
         assert abs(fused[0].item() - ref[0].item()) < 3e-3
         assert _rel(fused[5], a_r.grad) < 2e-2 and _rel(fused[6], b_r.grad) < 2e-2
         assert abs(fused[7].item() - s_r.grad.item()) < 3e-3 * max(1.0, abs(s_r.grad.item()))
+
+
+def test_autocast_output_dtype_and_hidden_state_guard(dev):
+    """Under torch.autocast the reference's towers return the autocast dtype (their last op is a matmul / Linear); the
+    per-token hidden-state output of the text tower has no backward schedule and must not silently drop gradients."""
+    from multimodal_b200._lib import MMBError
+    from multimodal_b200.modules.losses.contrastive_loss_with_temperature import ContrastiveLossWithTemperature
+
+    torch.manual_seed(0)
+    m = _small_clip(dev)
+    img, txt = O.synthetic_batch(8, image_size=64, vocab=512, device=dev)
+    out32 = m(img, txt)
+    assert out32.embeddings_a.dtype == torch.float32
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        out = m(img, txt)
+        loss = ContrastiveLossWithTemperature().to(dev)(out.embeddings_a, out.embeddings_b)
+    assert out.embeddings_a.dtype == torch.bfloat16 and out.embeddings_b.dtype == torch.bfloat16
+    torch.testing.assert_close(out.embeddings_a.float(), out32.embeddings_a, rtol=0, atol=4e-3)   # one bf16 rounding
+    loss.backward()                                         # gradients flow through the boundary cast
+    assert m.encoder_a.projection.grad is not None and torch.isfinite(m.encoder_a.projection.grad).all()
+    with pytest.raises(MMBError):
+        m.encoder_b(txt, return_hidden_state=True)
+    with torch.no_grad():
+        hs = m.encoder_b(txt, return_hidden_state=True)
+    assert hs.shape == (8, 77, 128)
