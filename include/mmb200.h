@@ -71,6 +71,14 @@ int mmb_gemm_ce_stats(const void* A, long long lda, const void* B, long long ldb
 int mmb_ce_stats_reduce(const void* part, int part_ld, int n_parts, const float* xlabel, int rows, int n_total,
                         float label_smoothing, float loss_weight, const float* row_w, float* row_loss, float* lse_out,
                         float* dscale_accum, void* stream);
+/* Vocabulary heads (Linear -> nn.CrossEntropyLoss(ignore_index), models/coca/coca_model.py:443-454): the same fused
+ * statistics GEMM with an explicit int32 label column per row, and the reduce that yields accum[0] += sum of the kept
+ * rows' losses, accum[1] += their count (mean = accum[0] / accum[1]); rows whose label == ignore_index are skipped. */
+int mmb_gemm_ce_stats_labels(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K,
+                             const float* log_scale, const int* labels, void* part, int part_ld, int part0,
+                             float* xlabel, void* stream);
+int mmb_ce_labels_reduce(const void* part, int part_ld, int n_parts, const float* xlabel, const int* labels,
+                         int ignore_index, int rows, float* row_loss, float* accum, void* stream);
 int mmb_gemm_ce_grad(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K,
                      const float* log_scale, int label0, int n_total, int rows_total, float label_smoothing,
                      float loss_weight, const float* lse_row, const float* row_w, const float* lse_col,

@@ -11,6 +11,8 @@ PROTOTYPES = {
     "mmb_gemm_set_mode": (i32, [i32, i32]),
     "mmb_gemm_ce_num_parts": (i32, [i32]),
     "mmb_gemm_ce_stats": (i32, [vp, ll, vp, ll, i32, i32, i32, vp, i32, vp, i32, i32, vp, vp]),
+    "mmb_gemm_ce_stats_labels": (i32, [vp, ll, vp, ll, i32, i32, i32, vp, vp, vp, i32, i32, vp, vp]),
+    "mmb_ce_labels_reduce": (i32, [vp, i32, i32, vp, vp, i32, i32, vp, vp, vp]),
     "mmb_ce_stats_reduce": (i32, [vp, i32, i32, vp, i32, i32, f32, f32, vp, vp, vp, vp, vp]),
     "mmb_gemm_ce_grad": (i32, [vp, ll, vp, ll, i32, i32, i32, vp, i32, i32, i32, f32, f32, vp, vp, vp, vp, i32, i32, vp, ll, vp]),
     "mmb_cast_f32_to_bf16": (i32, [vp, vp, ll, vp]),

@@ -56,6 +56,7 @@ struct GemmArgs {
   // are consumed in registers and never written to HBM (contrastive_loss_with_temperature.py:90-107)
   const float* ce_log_scale;  // device scalar (logit_scale parameter)
   int ce_label0;              // the label column of output row r is ce_label0 + r in THIS launch's column space
+  const int* ce_labels;       // CE_STATS, optional: explicit label column per row (any out-of-range value = none here)
   int ce_n_total;             // columns of the whole logits row (all launches), for the smoothing term eps / N
   float ce_smoothing;
   float ce_gs;                // CE_GRAD: loss_weight / rows (row scale when there are no row weights)
@@ -286,7 +287,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         // (row, 128-column part) leaves the SM.  x = T * acc (natural-log logits); exponentials in base 2.
         const float T = __expf(__ldg(p.ce_log_scale));
         const float T2 = T * 1.4426950408889634f;
-        const int lab = p.ce_label0 + m0 + row;
+        const int lab = p.ce_labels ? __ldg(p.ce_labels + min(m0 + row, p.M - 1)) : p.ce_label0 + m0 + row;
         float m2 = -INFINITY, se = 0.f, sex = 0.f, sx = 0.f;
         uint32_t vbuf[2][CWE];
         auto ld_group = [&](int g, uint32_t (&v)[CWE]) {
@@ -665,7 +666,7 @@ static int gemm_dispatch(const void* A, long long lda, int a_mn_major, const voi
   if (M <= 0 || N <= 0 || K <= 0) return MMB_ERR_ARG;
   if ((epilogue == EPI_CE_STATS || epilogue == EPI_CE_GRAD) && (!ce || a_mn_major || b_mn_major)) return MMB_ERR_ARG;
   if ((lda & 7) || (ldb & 7)) return MMB_ERR_ARG;
-  if (epilogue == EPI_F32 ? (N & 3) : (N & 7)) return MMB_ERR_ARG;
+  if (epilogue != EPI_CE_STATS && (epilogue == EPI_F32 ? (N & 3) : (N & 7))) return MMB_ERR_ARG;   // CE_STATS writes no tensor
   // CTA-pair mode (cta_group::2, 256x256 tiles) for everything large enough to fill the 74 SM pairs at least once;
   // MMB_GEMM_CTA2=0 forces the 1-CTA kernel (A/B testing), =1 forces pairs.
   static int cta2_env0 = -2;
@@ -788,17 +789,32 @@ extern "C" int mmb_gemm_bf16(const void* A, long long lda, int a_mn_major, const
 // Number of float4 partials per row one mmb_gemm_ce_stats launch over N columns writes (two 128-column parts per tile).
 extern "C" int mmb_gemm_ce_num_parts(int N) { return N <= 0 ? 0 : 2 * ((N + BLOCK_N - 1) / BLOCK_N); }
 
-extern "C" int mmb_gemm_ce_stats(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K,
-                                 const float* log_scale, int label0, void* part, int part_ld, int part0, float* xlabel,
-                                 void* stream) {
+static int gemm_ce_stats_impl(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K,
+                              const float* log_scale, int label0, const int* labels, void* part, int part_ld, int part0,
+                              float* xlabel, void* stream) {
   if (!log_scale || !part || !xlabel || part_ld <= 0 || part0 < 0 || part0 + mmb_gemm_ce_num_parts(N) > part_ld ||
       (reinterpret_cast<uintptr_t>(part) & 15))
     return MMB_ERR_ARG;
   GemmArgs ce{};
-  ce.ce_log_scale = log_scale; ce.ce_label0 = label0;
+  ce.ce_log_scale = log_scale; ce.ce_label0 = label0; ce.ce_labels = labels;
   ce.ce_part = reinterpret_cast<float4*>(part); ce.ce_part_ld = part_ld; ce.ce_part0 = part0; ce.ce_xlabel = xlabel;
   return gemm_dispatch(A, lda, 0, B, ldb, 0, nullptr, 0, nullptr, 0, M, N, K, EPI_CE_STATS, 0, 1.f, nullptr, nullptr, 0, 1, 0,
                        nullptr, &ce, stream);
+}
+
+extern "C" int mmb_gemm_ce_stats(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K,
+                                 const float* log_scale, int label0, void* part, int part_ld, int part0, float* xlabel,
+                                 void* stream) {
+  return gemm_ce_stats_impl(A, lda, B, ldb, M, N, K, log_scale, label0, nullptr, part, part_ld, part0, xlabel, stream);
+}
+// Same with an explicit label column per row (int32 [M]; a value outside [0, N) — e.g. an ignore_index — matches no
+// column: xlabel[m] is then left untouched): Linear -> CrossEntropy heads over a vocabulary
+// (models/coca/coca_model.py:443-454: captioning loss over the 49 408-entry vocabulary without a [B*76, V] logits tensor).
+extern "C" int mmb_gemm_ce_stats_labels(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K,
+                                        const float* log_scale, const int* labels, void* part, int part_ld, int part0,
+                                        float* xlabel, void* stream) {
+  if (!labels) return MMB_ERR_ARG;
+  return gemm_ce_stats_impl(A, lda, B, ldb, M, N, K, log_scale, 0, labels, part, part_ld, part0, xlabel, stream);
 }
 
 extern "C" int mmb_gemm_ce_grad(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K,

@@ -161,6 +161,41 @@ __global__ void ce_stats_reduce_kernel(const float4* __restrict__ part, int part
   }
 }
 
+// Label cross-entropy from the fused GEMM's partial statistics (Linear -> nn.CrossEntropyLoss(ignore_index) heads,
+// models/coca/coca_model.py:447-452): accum[0] += sum over kept rows of (lse - x_label), accum[1] += number of kept rows.
+__global__ void ce_labels_reduce_kernel(const float4* __restrict__ part, int part_ld, int n_parts,
+                                        const float* __restrict__ xlabel, const int* __restrict__ labels, int ignore_index,
+                                        int rows, float* __restrict__ row_loss, float* __restrict__ accum) {
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (i >= rows) return;
+  if (labels[i] == ignore_index) {
+    if (lane == 0 && row_loss) row_loss[i] = 0.f;
+    return;
+  }
+  const float4* pr = part + (long long)i * part_ld;
+  float mx = -INFINITY;
+  for (int k = lane; k < n_parts; k += 32) {
+    const float4 q = pr[k];
+    if (q.y > 0.f) mx = fmaxf(mx, q.x);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float se = 0.f;
+  for (int k = lane; k < n_parts; k += 32) {
+    const float4 q = pr[k];
+    if (q.y > 0.f) se += q.y * __expf(q.x - mx);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) se += __shfl_xor_sync(0xffffffffu, se, o);
+  if (lane == 0) {
+    const float loss = mx + logf(se) - xlabel[i];
+    if (row_loss) row_loss[i] = loss;
+    atomicAdd(accum, loss);
+    atomicAdd(accum + 1, 1.f);
+  }
+}
+
 // out[0] = scale * sum(in[0..n))  (deterministic single-block tree; n is a batch size)
 __global__ void sum_scale_kernel(const float* __restrict__ in, int n, float scale, float* __restrict__ out, int accumulate) {
   __shared__ float red[32];
@@ -252,5 +287,13 @@ extern "C" int mmb_ce_stats_reduce(const void* part, int part_ld, int n_parts, c
   ce_stats_reduce_kernel<<<(rows + 7) / 8, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const float4*>(part), part_ld, n_parts, xlabel, rows, n_total, label_smoothing, loss_weight, row_w,
       row_loss, lse_out, dscale_accum);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int mmb_ce_labels_reduce(const void* part, int part_ld, int n_parts, const float* xlabel, const int* labels,
+                                    int ignore_index, int rows, float* row_loss, float* accum, void* stream) {
+  if (!part || !xlabel || !labels || !accum || rows <= 0 || n_parts <= 0 || n_parts > part_ld) return MMB_ERR_ARG;
+  ce_labels_reduce_kernel<<<(rows + 7) / 8, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const float4*>(part), part_ld, n_parts, xlabel, labels, ignore_index, rows, row_loss, accum);
   return (int)cudaGetLastError();
 }

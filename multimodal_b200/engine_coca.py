@@ -285,7 +285,9 @@ class MultimodalDecoderRuntime:
         dev = mod.transformer_decoder.layer[0].attention.q_proj.weight.device
         self.stack = LayerStack(mod.transformer_decoder.layer, "cmm", dev)
 
-    def forward(self, texts: torch.Tensor, images: torch.Tensor) -> torch.Tensor:
+    def forward(self, texts: torch.Tensor, images: torch.Tensor, return_hidden: bool = False):
+        """return_hidden: skip the vocabulary projection and return (hidden bf16 [B*S, d], bf16 weight [V, d]) — the
+        operands of the fused Linear -> CrossEntropy kernel (CoCaForPretraining never needs the [B, S, V] logits)."""
         m, st = self.mod, self.stack
         ws, sh, d = st.ws, st.sh, st.d
         B, S, _ = texts.shape
@@ -298,10 +300,14 @@ class MultimodalDecoderRuntime:
         fln = m.transformer_decoder.final_layer_norm
         XF, LAST, LASTb = st.finish(B, S, fln, want_bf16=m.output_projection is not None)
         if m.output_projection is None:
+            if return_hidden:
+                raise MMBError("return_hidden needs an output projection (the vocabulary head)")
             return (LAST if fln is not None else XF).view(B, S, d)
         if LASTb is None:
             LASTb = ws.get("cmm.LASTb", (B * S, d), torch.bfloat16)
             ops.cast_bf16(XF.view(-1), LASTb.view(-1))
+        if return_hidden:
+            return LASTb, sh.get("oproj", [m.output_projection.weight])
         V = m.output_projection.weight.shape[0]
         out = torch.empty((B * S, V), device=st.device, dtype=torch.float32)
         ops.gemm(LASTb, sh.get("oproj", [m.output_projection.weight]), bias=m.output_projection.bias,

@@ -47,6 +47,11 @@ class CoCaModel(nn.Module):
 
     @torch.no_grad()
     def forward(self, images: Tensor, texts: Tensor, text_padding_mask: Optional[Tensor] = None) -> MultimodalOutput:
+        return self._forward_impl(images, texts, text_padding_mask, want_logits=True)
+
+    def _forward_impl(self, images: Tensor, texts: Tensor, text_padding_mask: Optional[Tensor], want_logits: bool):
+        """want_logits=False (CoCaForPretraining): the multimodal decoder stops before its vocabulary projection and the
+        third field is (hidden bf16 [B*S, d], projection weight bf16 [V, d]) for the fused Linear -> CrossEntropy."""
         vision_encoder_outs = self.vision_encoder(images)
         if isinstance(vision_encoder_outs, TransformerOutput):
             image_embeddings = vision_encoder_outs.last_hidden_state
@@ -69,7 +74,11 @@ class CoCaModel(nn.Module):
         pooled_text_embeddings, text_tokens = self.text_decoder(texts, text_padding_mask)
         contrastive_text_embeddings = _l2_normalize(pooled_text_embeddings)
 
-        multimodal_embeddings = self.multimodal_decoder(text_tokens, captioning_image_embeddings)
+        if want_logits or getattr(self.multimodal_decoder, "output_projection", None) is None:
+            multimodal_embeddings = self.multimodal_decoder(text_tokens, captioning_image_embeddings)
+        else:
+            multimodal_embeddings = self.multimodal_decoder._runtime().forward(text_tokens, captioning_image_embeddings,
+                                                                               return_hidden=True)
         return MultimodalOutput(contrastive_image_embeddings, contrastive_text_embeddings, multimodal_embeddings)
 
     def _vision_proj(self, x: Tensor) -> Tensor:
@@ -187,18 +196,31 @@ class CoCaForPretraining(nn.Module):
             return self._forward_values(images, texts, text_padding_mask)
 
     def _forward_values(self, images: Tensor, texts: Tensor, text_padding_mask: Optional[Tensor] = None) -> Dict[str, Tensor]:
-        model_outs = self.model(images, texts, text_padding_mask)
+        fused = isinstance(self.model, CoCaModel)       # a user-supplied model only promises MultimodalOutput
+        model_outs = (self.model._forward_impl(images, texts, text_padding_mask, want_logits=False) if fused
+                      else self.model(images, texts, text_padding_mask))
         img = model_outs.image_pooled_output
         if img.dim() == 3:           # [B, 1, d] from the cascaded contrastive pooler
             img = img.squeeze(1)
         contrastive_loss = self.contrastive_loss(img, model_outs.text_pooled_output)
-        logits = model_outs.multimodal_embeddings
-        B, S, V = logits.shape
-        labels = texts[:, 1:].contiguous().long()      # captioning_labels (:443)
-        if labels.shape[1] != S:
-            raise ValueError(f"caption labels {tuple(labels.shape)} do not match logits {tuple(logits.shape)}")
-        acc = ops.zero_(torch.empty(2, device=logits.device, dtype=torch.float32))
-        ops.ce_labels(logits.view(B * S, V), labels.view(-1), 1, self.caption_loss.ignore_index, B * S, V, None, acc)
+        labels = texts[:, 1:].contiguous()              # captioning_labels (:443)
+        B, S = labels.shape
+        acc = ops.zero_(torch.empty(2, device=labels.device, dtype=torch.float32))
+        mm = model_outs.multimodal_embeddings
+        if isinstance(mm, tuple):
+            # fused vocabulary head: hidden [B*S, d] x W[V, d]^T with the cross-entropy statistics taken
+            # in the GEMM epilogue — the [B*S, 49 408] logits (7.7 GB fp32 at B = 512) are never written
+            hidden, weight = mm
+            if hidden.shape[0] != B * S:
+                raise ValueError(f"caption labels {tuple(labels.shape)} do not match the decoder output rows {hidden.shape[0]}")
+            ops.linear_cross_entropy(hidden, weight, labels.reshape(-1).to(torch.int32), self.caption_loss.ignore_index, acc)
+        else:
+            logits = mm
+            if logits.shape[1] != S:
+                raise ValueError(f"caption labels {tuple(labels.shape)} do not match logits {tuple(logits.shape)}")
+            V = logits.shape[-1]
+            ops.ce_labels(logits.reshape(B * S, V).contiguous().float(), labels.long().view(-1), 1,
+                          self.caption_loss.ignore_index, B * S, V, None, acc)
         captioning_loss = acc[0] / acc[1]
         return {"contrastive": contrastive_loss, "captioning": captioning_loss}
 

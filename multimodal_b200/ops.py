@@ -289,6 +289,27 @@ def gemm_ce_stats(A, B, log_scale, label0, part, part0, xlabel):
                                             _p(part), part.shape[1], int(part0), _p(xlabel), _stream()), "mmb_gemm_ce_stats")
 
 
+def linear_cross_entropy(hidden_bf16, weight_bf16, labels_i32, ignore_index, accum, row_loss=None):
+    """Fused Linear(no bias) -> CrossEntropy(ignore_index): accum[0] += sum of kept rows' losses, accum[1] += count.
+    The [M, V] logits are never written (mmb_gemm_ce_stats_labels + mmb_ce_labels_reduce)."""
+    _chk(hidden_bf16, torch.bfloat16, "hidden"); _chk(weight_bf16, torch.bfloat16, "weight")
+    _rowmajor(hidden_bf16, "hidden"); _rowmajor(weight_bf16, "weight")
+    _chk(labels_i32, torch.int32, "labels"); _chk(accum, torch.float32, "accum")
+    M, K = hidden_bf16.shape
+    V = weight_bf16.shape[0]
+    if weight_bf16.shape[1] != K or labels_i32.numel() != M or not labels_i32.is_contiguous():
+        raise MMBError("linear_cross_entropy: expected weight [V, K] and contiguous int32 labels [M]")
+    npar = gemm_ce_num_parts(V)
+    part = torch.empty((M, npar, 4), device=hidden_bf16.device, dtype=torch.float32)
+    xlabel = torch.zeros(M, device=hidden_bf16.device, dtype=torch.float32)
+    zero = torch.zeros(1, device=hidden_bf16.device, dtype=torch.float32)      # log(temperature) = 0
+    _lib.check(_lib.lib().mmb_gemm_ce_stats_labels(_p(hidden_bf16), hidden_bf16.stride(0), _p(weight_bf16),
+                                                   weight_bf16.stride(0), M, V, K, _p(zero), _p(labels_i32), _p(part), npar, 0,
+                                                   _p(xlabel), _stream()), "mmb_gemm_ce_stats_labels")
+    _lib.check(_lib.lib().mmb_ce_labels_reduce(_p(part), npar, npar, _p(xlabel), _p(labels_i32), int(ignore_index), M,
+                                               _p(row_loss), _p(accum), _stream()), "mmb_ce_labels_reduce")
+
+
 def ce_stats_reduce(part, n_parts, xlabel, rows, n_total, smoothing, loss_weight, row_w, row_loss, lse_out, dscale_accum):
     _lib.check(_lib.lib().mmb_ce_stats_reduce(_p(part), part.shape[1], int(n_parts), _p(xlabel), rows, n_total,
                                               float(smoothing), float(loss_weight), _p(row_w), _p(row_loss), _p(lse_out),

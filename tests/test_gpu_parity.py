@@ -636,3 +636,24 @@ def test_autocast_output_dtype_and_hidden_state_guard(dev):
     with torch.no_grad():
         hs = m.encoder_b(txt, return_hidden_state=True)
     assert hs.shape == (8, 77, 128)
+
+
+@pytest.mark.parametrize("M,K,V", [(300, 128, 300), (1000, 768, 49408), (64, 384, 512)])
+def test_fused_linear_cross_entropy_vocab_head(dev, M, K, V):
+    """Linear(no bias) -> CrossEntropy(ignore_index) without the [M, V] logits (mmb_gemm_ce_stats_labels +
+    mmb_ce_labels_reduce; CoCa's captioning loss, models/coca/coca_model.py:443-454) against torch on fp32 logits."""
+    from multimodal_b200 import ops
+
+    torch.manual_seed(4)
+    h = (torch.randn(M, K, device=dev) * 0.5).bfloat16()
+    w = (torch.randn(V, K, device=dev) * 0.05).bfloat16()
+    labels = torch.randint(0, V, (M,), device=dev)
+    labels[::7] = 0                                           # ignore_index rows
+    acc = torch.zeros(2, device=dev)
+    row = torch.empty(M, device=dev)
+    ops.linear_cross_entropy(h, w, labels.to(torch.int32), 0, acc, row_loss=row)
+    logits = h.float() @ w.float().t()
+    ref = torch.nn.functional.cross_entropy(logits, labels, ignore_index=0, reduction="none")
+    assert acc[1].item() == (labels != 0).sum().item()
+    torch.testing.assert_close(row, ref, rtol=2e-4, atol=2e-4)   # same bf16 operands, fp32 accumulation; ex2.approx
+    assert abs((acc[0] / acc[1]).item() - ref.sum().item() / (labels != 0).sum().item()) < 2e-4
