@@ -45,6 +45,7 @@ struct AttnTcArgs {
   __nv_bfloat16* dqkv;          // bwd: [B*S, 3d]
   float* dsum;                  // bwd: rowsum(dO * O) [B,H,S], written by the dQ kernel, read by the dK/dV kernel
   const uint8_t* kmask;         // fwd: optional key-padding mask [B,S], 1 = attend (utils/attention.py:13-53)
+  int prefetch;                 // bwd (column-split kernel): software-pipelined chunk loop (MMB_ATTN_PREFETCH=0 disables: A/B)
 };
 
 __device__ __forceinline__ uint64_t desc_k(uint32_t saddr) { return make_smem_desc_sw128(saddr, 16, 1024); }
@@ -508,7 +509,8 @@ constexpr int FPP_SMEM = 1024 + 2 * FPP_BUF + 512 + 256;
 // TMEM (512 columns): [S|dP] buffer i at i*128 (S +0, dP +64); accumulators of tile parity j at 256 + j*128 (+0, +64).
 // Barrier phases are derived from running counters (tile sequence n, global chunk sequence g).
 // ------------------------------------------------------------------------------------------------
-constexpr int P_STATS = 2;   // statistics warps: softmax LSE and D = rowsum(dO*O), one tile ahead
+constexpr int P_STATS = 1;   // statistics warp: softmax LSE and D = rowsum(dO*O), one tile ahead (12 warps per CTA ->
+                             // 168 registers per thread: register allocation is per 4 warps, 13 warps would cap at 128)
 // NG column groups per row: 4*NG worker warps (TMEM lane quadrant = warp & 3, column group = warp >> 2), then the
 // producer warp, the score issuer, the accumulate issuer and the statistics warps.
 template <bool CAUSAL, bool DKDV, int NG>
@@ -684,26 +686,38 @@ attn_bwd_persist_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gr
       const long long sbase = ((long long)b * p.H + h) * S;
       mbar_wait(&stat_empty[n & 1], ((n >> 1) & 1) ^ 1);
       if (!DKDV) {
+        // one warp covers the tile's 128 rows: 4 rows per lane, two at a time with all 32 16-byte loads of the pair in
+        // flight before the first FMA (a row-by-row loop would chain four global-load latencies per tile)
 #pragma unroll
-        for (int k = 0; k < 128 / (P_STATS * 32); ++k) {
-          const int rr = t + k * (P_STATS * 32);
-          const int ri = tile * 128 + rr;
-          float acc = 0.f, L = 0.f;
-          if (ri < S) {
-            const uint4* po = reinterpret_cast<const uint4*>(p.o_in + (long long)(row0 + ri) * d + h * 64);
-            const uint4* pd = reinterpret_cast<const uint4*>(p.dout + (long long)(row0 + ri) * d + h * 64);
+        for (int k = 0; k < 128 / (P_STATS * 32); k += 2) {
+          uint4 va[2][8], vc[2][8];
+          float Lr[2] = {0.f, 0.f};
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int ri = tile * 128 + t + (k + u) * (P_STATS * 32);
+            const int rc = min(ri, S - 1);      // clamped: loads always legal, results of padding rows discarded
+            const uint4* po = reinterpret_cast<const uint4*>(p.o_in + (long long)(row0 + rc) * d + h * 64);
+            const uint4* pd = reinterpret_cast<const uint4*>(p.dout + (long long)(row0 + rc) * d + h * 64);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { va[u][j] = __ldg(po + j); vc[u][j] = __ldg(pd + j); }
+            Lr[u] = __ldg(p.lse + sbase + rc) * 1.4426950408889634f;
+          }
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int rr = t + (k + u) * (P_STATS * 32);
+            const int ri = tile * 128 + rr;
+            float acc = 0.f;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const uint4 a = __ldg(po + j), c = __ldg(pd + j);
+              const uint4 a = va[u][j], c = vc[u][j];
               acc += bf16_lo(a.x) * bf16_lo(c.x) + bf16_hi(a.x) * bf16_hi(c.x) + bf16_lo(a.y) * bf16_lo(c.y) +
                      bf16_hi(a.y) * bf16_hi(c.y) + bf16_lo(a.z) * bf16_lo(c.z) + bf16_hi(a.z) * bf16_hi(c.z) +
                      bf16_lo(a.w) * bf16_lo(c.w) + bf16_hi(a.w) * bf16_hi(c.w);
             }
-            L = p.lse[sbase + ri] * 1.4426950408889634f;
-            p.dsum[sbase + ri] = acc;
+            if (ri < S) p.dsum[sbase + ri] = acc;
+            wL[rr] = ri < S ? Lr[u] : 0.f;
+            wL[256 + rr] = ri < S ? acc : 0.f;
           }
-          wL[rr] = L;
-          wL[256 + rr] = acc;
         }
       } else {
 #pragma unroll
@@ -740,27 +754,37 @@ attn_bwd_persist_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gr
       }
       if (threadIdx.x == 0) PTRACE(DKDV, 0, 41);
 
+      // Software-pipelined chunk loop (round 2): the tcgen05.ld of chunk c+1 is issued before the fence / arrive that
+      // publishes chunk c, and the dS-buffer check runs under the loads in flight, so the fixed latencies the phase
+      // trace found serialised per chunk (barrier check ~250 clk, tcgen05.ld ~250, buffer check ~220, fence + arrive
+      // ~240: profiles/r1_attn_bwd_phase_trace.txt) overlap each other.  The score issuer runs 6-7 k clocks ahead, so
+      // S/dP of the next chunk are always in TMEM by then.  (First chunk of a tile: loaded here, not prefetched — the
+      // tile epilogue in between needs the registers.)
+      uint32_t sv[CW], dv[CW];
+      auto issue_ld = [&](int sbx) {
+        if (CW == 32) {
+          tmem_ld32(trow + sbx * 128 + grp * 32, reinterpret_cast<uint32_t(&)[32]>(sv));
+          tmem_ld32(trow + sbx * 128 + 64 + grp * 32, reinterpret_cast<uint32_t(&)[32]>(dv));
+        } else {
+          tmem_ld16(trow + sbx * 128 + grp * 16, reinterpret_cast<uint32_t(&)[16]>(sv));
+          tmem_ld16(trow + sbx * 128 + 64 + grp * 16, reinterpret_cast<uint32_t(&)[16]>(dv));
+        }
+      };
       for (int c = 0; c < nc; ++c, ++g) {
         const int sb = (int)(g & 1);
         const int wc = min(64, S_pad - c * 64);
         if (threadIdx.x == 0) PTRACE(DKDV, 0, c * 5 + 0);
-        mbar_wait(&sdp_full[sb], (uint32_t)((g >> 1) & 1));
-        tc_fence_after();
-        if (threadIdx.x == 0) PTRACE(DKDV, 0, c * 5 + 1);
-        uint32_t sv[CW], dv[CW];
-        if (CW == 32) {
-          tmem_ld32(trow + sb * 128 + grp * 32, reinterpret_cast<uint32_t(&)[32]>(sv));
-          tmem_ld32(trow + sb * 128 + 64 + grp * 32, reinterpret_cast<uint32_t(&)[32]>(dv));
-        } else {
-          tmem_ld16(trow + sb * 128 + grp * 16, reinterpret_cast<uint32_t(&)[16]>(sv));
-          tmem_ld16(trow + sb * 128 + 64 + grp * 16, reinterpret_cast<uint32_t(&)[16]>(dv));
+        if (c == 0 || !p.prefetch) {
+          mbar_wait(&sdp_full[sb], (uint32_t)((g >> 1) & 1));
+          tc_fence_after();
+          issue_ld(sb);
         }
+        if (threadIdx.x == 0) PTRACE(DKDV, 0, c * 5 + 1);
+        mbar_wait(&ds_empty[sb], (uint32_t)(((g >> 1) & 1) ^ 1));  // accumulate MMAs of chunk g-2 have left the buffer
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&sdp_empty[sb]);
-        if (threadIdx.x == 0) PTRACE(DKDV, 0, c * 5 + 2);
-        mbar_wait(&ds_empty[sb], (uint32_t)(((g >> 1) & 1) ^ 1));  // accumulate MMAs of chunk g-2 have left the buffer
         if (threadIdx.x == 0) PTRACE(DKDV, 0, c * 5 + 3);
         uint8_t* myDS = sDS + sb * ATOM;
         uint8_t* myPT = sPT + sb * ATOM;
@@ -820,6 +844,12 @@ attn_bwd_persist_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gr
               if (DKDV) store_p16(myPT, r, grp * CW + half * 16, pt);
             }
           }
+        }
+        if (p.prefetch && c + 1 < nc) {   // prefetch S/dP of the next chunk (sv / dv are dead: everything above is in smem)
+          const long long gn = g + 1;
+          mbar_wait(&sdp_full[gn & 1], (uint32_t)((gn >> 1) & 1));
+          tc_fence_after();
+          issue_ld((int)(gn & 1));
         }
         fence_proxy_async_smem();
         __syncwarp();
@@ -895,7 +925,10 @@ __global__ void __launch_bounds__((8 + 3 + PP_STATS) * 32, 1)   // 12 warps -> 1
 attn_bwd_pp_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_constant__ CUtensorMap tmQKV64,
                    const __grid_constant__ CUtensorMap tmDO128, const __grid_constant__ CUtensorMap tmDO64,
                    const AttnTcArgs p, const int n_work) {
-  constexpr int RING = DKDV ? 3 : 4;
+  // Two chunks are in flight at once (one per worker group) and each takes a group ~2x as long as in the column-split
+  // kernel, so the chunk-operand ring must hold the two active chunks PLUS the prefetch distance that covers the
+  // TMA latency: 5 / 6 stages (round-2 measurement: with 3 / 4 the groups starved on ring_full, 2.76 vs 1.88 ms).
+  constexpr int RING = DKDV ? 5 : 6;
   constexpr int CH = 8192;  // one 64-row x 128 B chunk operand
   constexpr int P_WORKERS = 8;
   constexpr int SLD = 2 * SMAX;  // floats per statistics buffer: lse(log2) [SMAX] | rowsum(dO*O) [SMAX]
@@ -909,17 +942,17 @@ attn_bwd_pp_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_co
   uint64_t* bars = reinterpret_cast<uint64_t*>(sLD + 2 * SLD);
   uint64_t* tile_full = bars;            // [2]  tile operands landed                 producer(TMA) -> score issuer
   uint64_t* tile_empty = bars + 2;       // [2]  last score MMA of the tile complete  score issuer  -> producer
-  uint64_t* ring_full = bars + 4;        // [RING]
-  uint64_t* ring_empty = bars + 8;       // [RING] accumulate MMAs of the chunk complete            -> producer
-  uint64_t* sdp_full = bars + 12;        // [2]  S_c/dP_c in TMEM                     score issuer  -> worker group
-  uint64_t* sdp_empty = bars + 14;       // [2]  the group has read them (4 warps)                  -> score issuer
-  uint64_t* ds_full = bars + 16;         // [2]  dS_c (P^T_c) in smem (4 warps)       worker group  -> acc issuer
-  uint64_t* ds_empty = bars + 18;        // [2]  accumulate MMAs done with them       acc issuer    -> worker group
-  uint64_t* acc_full = bars + 20;        // [2]  accumulators of the tile final       acc issuer    -> workers
-  uint64_t* acc_empty = bars + 22;       // [2]  workers have read them (8 warps)                   -> acc issuer
-  uint64_t* stat_full = bars + 24;       // [2]  LSE / D of the tile in sLD (2 warps) stats warps   -> workers
-  uint64_t* stat_empty = bars + 26;      // [2]  workers are done with them (8 warps)               -> stats warps
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 28);
+  uint64_t* ring_full = bars + 4;        // [RING <= 8]
+  uint64_t* ring_empty = bars + 12;      // [RING <= 8] accumulate MMAs of the chunk complete       -> producer
+  uint64_t* sdp_full = bars + 20;        // [2]  S_c/dP_c in TMEM                     score issuer  -> worker group
+  uint64_t* sdp_empty = bars + 22;       // [2]  the group has read them (4 warps)                  -> score issuer
+  uint64_t* ds_full = bars + 24;         // [2]  dS_c (P^T_c) in smem (4 warps)       worker group  -> acc issuer
+  uint64_t* ds_empty = bars + 26;        // [2]  accumulate MMAs done with them       acc issuer    -> worker group
+  uint64_t* acc_full = bars + 28;        // [2]  accumulators of the tile final       acc issuer    -> workers
+  uint64_t* acc_empty = bars + 30;       // [2]  workers have read them (8 warps)                   -> acc issuer
+  uint64_t* stat_full = bars + 32;       // [2]  LSE / D of the tile in sLD (1 warp)  stats warp    -> workers
+  uint64_t* stat_empty = bars + 34;      // [2]  workers are done with them (8 warps)               -> stats warp
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 36);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int S = p.S, S_pad = p.S_pad, d = p.H * 64;
@@ -1054,26 +1087,38 @@ attn_bwd_pp_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_co
       const long long sbase = ((long long)b * p.H + h) * S;
       mbar_wait(&stat_empty[n & 1], ((n >> 1) & 1) ^ 1);
       if (!DKDV) {
+        // one warp covers the tile's 128 rows: 4 rows per lane, processed two at a time with all 32 16-byte loads of
+        // the pair in flight before the first FMA (a row-by-row loop chains four global-load latencies per tile)
 #pragma unroll
-        for (int k = 0; k < 128 / (PP_STATS * 32); ++k) {
-          const int rr = t + k * (PP_STATS * 32);
-          const int ri = tile * 128 + rr;
-          float acc = 0.f, L = 0.f;
-          if (ri < S) {
-            const uint4* po = reinterpret_cast<const uint4*>(p.o_in + (long long)(row0 + ri) * d + h * 64);
-            const uint4* pd = reinterpret_cast<const uint4*>(p.dout + (long long)(row0 + ri) * d + h * 64);
+        for (int k = 0; k < 128 / (PP_STATS * 32); k += 2) {
+          uint4 va[2][8], vc[2][8];
+          float Lr[2] = {0.f, 0.f};
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int ri = tile * 128 + t + (k + u) * (PP_STATS * 32);
+            const int rc = min(ri, S - 1);      // clamped: loads always legal, results of padding rows discarded
+            const uint4* po = reinterpret_cast<const uint4*>(p.o_in + (long long)(row0 + rc) * d + h * 64);
+            const uint4* pd = reinterpret_cast<const uint4*>(p.dout + (long long)(row0 + rc) * d + h * 64);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { va[u][j] = __ldg(po + j); vc[u][j] = __ldg(pd + j); }
+            Lr[u] = __ldg(p.lse + sbase + rc) * 1.4426950408889634f;
+          }
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int rr = t + (k + u) * (PP_STATS * 32);
+            const int ri = tile * 128 + rr;
+            float acc = 0.f;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const uint4 a = __ldg(po + j), c = __ldg(pd + j);
+              const uint4 a = va[u][j], c = vc[u][j];
               acc += bf16_lo(a.x) * bf16_lo(c.x) + bf16_hi(a.x) * bf16_hi(c.x) + bf16_lo(a.y) * bf16_lo(c.y) +
                      bf16_hi(a.y) * bf16_hi(c.y) + bf16_lo(a.z) * bf16_lo(c.z) + bf16_hi(a.z) * bf16_hi(c.z) +
                      bf16_lo(a.w) * bf16_lo(c.w) + bf16_hi(a.w) * bf16_hi(c.w);
             }
-            L = p.lse[sbase + ri] * 1.4426950408889634f;
-            p.dsum[sbase + ri] = acc;
+            if (ri < S) p.dsum[sbase + ri] = acc;
+            wL[rr] = ri < S ? Lr[u] : 0.f;
+            wL[SMAX + rr] = ri < S ? acc : 0.f;
           }
-          wL[rr] = L;
-          wL[SMAX + rr] = acc;
         }
       } else {
 #pragma unroll
@@ -1244,8 +1289,8 @@ attn_bwd_pp_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_co
   }
 }
 
-constexpr int BWDPP_DQ_SMEM = 1024 + 4 * ATOM + 4 * 16384 + 2 * ATOM + 2 * 2 * SMAX * 4 + 512;     // 171.5 KB
-constexpr int BWDPP_DKDV_SMEM = 1024 + 4 * ATOM + 3 * 16384 + 4 * ATOM + 2 * 2 * SMAX * 4 + 512;   // 187.5 KB
+constexpr int BWDPP_DQ_SMEM = 1024 + 4 * ATOM + 6 * 16384 + 2 * ATOM + 2 * 2 * SMAX * 4 + 512;     // 203.5 KB
+constexpr int BWDPP_DKDV_SMEM = 1024 + 4 * ATOM + 5 * 16384 + 4 * ATOM + 2 * 2 * SMAX * 4 + 512;   // 219.5 KB
 
 constexpr int BWDP_DQ_SMEM = 1024 + 4 * ATOM + 4 * 16384 + 2 * ATOM + 4096 + 512;              // 169.5 KB
 constexpr int BWDP_DKDV_SMEM = 1024 + 4 * ATOM + 3 * 16384 + 4 * ATOM + 4096 + 512;            // 185.5 KB
@@ -1281,12 +1326,16 @@ static int attention_fwd_tc_impl(const void* qkv, void* out, float* lse, const u
     if (rc) return rc;
   }
   const int smem_bytes = big ? FWD_SMEM_BIG : FWD_SMEM;
-  static int fwd_variant = -1;   // MMB_ATTN_FWD=tile selects the round-1 one-tile-per-CTA kernel (A/B testing)
+  // Forward kernel choice (measured, B = 1024): single-tile sequences (S <= 128: the text tower, 0.192 vs 0.242 ms) run
+  // on the persistent ping-pong kernel; longer ones (image tower: 0.62 vs 0.74 ms) on the one-tile-per-CTA kernel, whose
+  // two resident CTAs per SM hide the per-tile load latency that two smem buffers cannot prefetch away.
+  // MMB_ATTN_FWD=tile / =pp force one of them (A/B testing).
+  static int fwd_variant = -1;
   if (fwd_variant < 0) {
     const char* e = getenv("MMB_ATTN_FWD");
-    fwd_variant = (e && e[0] == 't') ? 1 : 0;
+    fwd_variant = (e && e[0] == 't') ? 1 : (e && e[0] == 'p') ? 0 : 2;
   }
-  if (!big && fwd_variant == 0) {
+  if (!big && (fwd_variant == 0 || (fwd_variant == 2 && S <= 128))) {
     AttnTcArgs a{};
     a.S = S; a.H = H; a.S_pad = S_pad; a.scale = scale; a.scale_log2 = scale * 1.4426950408889634f;
     a.lse = lse; a.out = (__nv_bfloat16*)out; a.kmask = kmask;
@@ -1363,13 +1412,20 @@ extern "C" int mmb_attention_bwd_tc(const void* qkv, const void* out, const void
   a.S = S; a.H = H; a.S_pad = S_pad; a.scale = scale; a.scale_log2 = scale * 1.4426950408889634f;
   a.lse = const_cast<float*>(lse); a.o_in = (const __nv_bfloat16*)out; a.dout = (const __nv_bfloat16*)dout;
   a.dqkv = (__nv_bfloat16*)dqkv; a.dsum = dsum;
+  static int prefetch_env = -1;
+  if (prefetch_env < 0) {
+    const char* e = getenv("MMB_ATTN_PREFETCH");
+    prefetch_env = (e && e[0] == '0') ? 0 : 1;
+  }
+  a.prefetch = prefetch_env;
   const int n_work = ((S + 127) / 128) * H * B;
   const int grid_p = n_work < num_sms() ? n_work : num_sms();
-  // MMB_ATTN_BWD=colsplit selects the round-1 column-split persistent kernel (A/B testing; S <= 256 only)
+  // Two persistent backward kernels: the column-split one (S <= 256; default there: 1.88 ms per image layer at
+  // B = 1024) and the ping-pong one (the only one for 256 < S <= 384).  MMB_ATTN_BWD=pp / =colsplit force one (A/B).
   static int variant = -1;
   if (variant < 0) {
     const char* e = getenv("MMB_ATTN_BWD");
-    variant = (e && e[0] == 'c') ? 1 : 0;
+    variant = (e && e[0] == 'p') ? 0 : 1;
   }
   if (variant == 1 && S <= 256) {
 #define LAUNCH_BWDP(C, K, SM)                                                                                     \

@@ -140,16 +140,16 @@ def test_activation_layernorm_mlp_standalone():
     from multimodal_b200.modules.layers.normalizations import Fp32LayerNorm
 
     torch.manual_seed(3)
-    x = torch.randn(7, 33, 200, device=dev)
+    x = torch.randn(7, 33, 256, device=dev)
     torch.testing.assert_close(SiLU()(x), torch.sigmoid(1.702 * x) * x, rtol=1e-5, atol=1e-6)
     # the reference's known answer (tests/modules/layers/test_activation.py:12-16): SiLU(1) = 0.8458
     assert abs(SiLU()(torch.ones(1, device=dev)).item() - 0.8458) < 1e-4
-    ln = Fp32LayerNorm(200).to(dev)
+    ln = Fp32LayerNorm(256).to(dev)   # the LayerNorm kernels take widths that are multiples of 128
     with torch.no_grad():
         ln.weight.normal_(1, 0.1); ln.bias.normal_(0, 0.1)
         got = ln(x.bfloat16())
         assert got.dtype == torch.bfloat16                                  # type_as(x) (normalizations.py:25)
-        ref = F.layer_norm(x.bfloat16().float(), (200,), ln.weight, ln.bias, ln.eps)
+        ref = F.layer_norm(x.bfloat16().float(), (256,), ln.weight, ln.bias, ln.eps)
     assert _rel(got, ref) < 1e-2
     mlp = MLP(256, 128, 512, dropout=0.0, activation=torch.nn.GELU).to(dev)
     y = torch.randn(40, 256, device=dev)

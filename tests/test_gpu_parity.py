@@ -519,7 +519,8 @@ def test_single_process_backprop_type_is_ignored_like_the_reference(dev):
             grads[mode] = (a.grad.clone(), b.grad.clone(), s.grad.clone())
         for mode in (BackpropType.LOCAL, BackpropType.NONE):
             for got, want in zip(grads[mode], grads[BackpropType.GLOBAL]):
-                assert torch.equal(got, want), (B, mode)
+                # same schedule, same kernels; d logit_scale is an atomic sum over rows (order differs run to run)
+                torch.testing.assert_close(got, want, rtol=1e-5, atol=1e-7)
         a_r, b_r = a0.clone().requires_grad_(True), b0.clone().requires_grad_(True)
         s_r = torch.tensor(math.log(1 / 0.07), device=dev, requires_grad=True)
         O.contrastive_loss(a_r, b_r, s_r)[0].backward()
