@@ -492,11 +492,16 @@ def test_clip_b16_full_size_step_gradients_against_fp32_oracle(dev):
         assert len(ours) == len(g_ref) == 301   # every entry of the reference state dict (all are parameters)
         assert abs(loss - loss_ref) < max(2.0 * abs(loss_ac - loss_ref), 2e-3), (loss, loss_ref, loss_ac)
         assert abs(ds - ds_ref) < max(2.0 * abs(ds_ac - ds_ref), 5e-3 * max(1.0, abs(ds_ref)))
-        # per tensor: no worse than twice the autocast deviation of the reference formulation (floor 5e-3: tensors whose
-        # autocast error happens to be tiny); in aggregate: the median must not exceed the autocast median by > 25 %
+        # Bars (measured on B200, profiles/r2_grad_parity_b16_fullsize.txt: ours median 1.6e-2 / max 2.5e-2, the
+        # reference formulation under autocast median 2.7e-2 / max 1.2e-1 — the fp32 residual stream and fp32 statistics
+        # make this path MORE accurate than the reference's own bf16-autocast training path):
+        #   per tensor  : within 1.25x of the autocast deviation of that tensor (floor 5e-3 for tensors whose autocast
+        #                 error happens to be tiny) and never above 4e-2 relative L2;
+        #   in aggregate: median below the autocast median and below 2.5e-2.
+        # A wrong split-K reduction, a dropped tile or a mis-scaled epilogue moves a tensor's relative L2 error to O(1).
         for k, a, b in rows:
-            assert a < max(2.0 * b, 5e-3), (k, a, b)
-        assert med_o < 1.25 * med_a + 1e-4, (med_o, med_a)
+            assert a < max(1.25 * b, 5e-3) and a < 4e-2, (k, a, b)
+        assert med_o < med_a and med_o < 2.5e-2, (med_o, med_a)
     finally:
         torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32
 
