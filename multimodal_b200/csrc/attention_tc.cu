@@ -45,7 +45,6 @@ struct AttnTcArgs {
   __nv_bfloat16* dqkv;          // bwd: [B*S, 3d]
   float* dsum;                  // bwd: rowsum(dO * O) [B,H,S], written by the dQ kernel, read by the dK/dV kernel
   const uint8_t* kmask;         // fwd: optional key-padding mask [B,S], 1 = attend (utils/attention.py:13-53)
-  int prefetch;                 // bwd (column-split kernel): software-pipelined chunk loop (MMB_ATTN_PREFETCH=0 disables: A/B)
 };
 
 __device__ __forceinline__ uint64_t desc_k(uint32_t saddr) { return make_smem_desc_sw128(saddr, 16, 1024); }
@@ -147,9 +146,12 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
   const int nchunk = S_pad >> 4;
   const int c_lo = grp == 0 ? 0 : (nchunk + 1) / 2, c_hi = grp == 0 ? (nchunk + 1) / 2 : nchunk;
   const int kv_lim = CAUSAL ? min(S, qi + 1) : S;  // columns >= kv_lim are masked
+  // a warp whose 32 rows are all padding (last tile: 59 of 128 rows at S = 197) skips both softmax passes (warp-uniform,
+  // so the .sync.aligned tcgen05.ld stay convergent); its P rows are never read back and its O rows never stored
+  const bool warp_ok = qt * 128 + q4 * 32 < S;
 
   float mx = -INFINITY;
-  for (int c = c_lo; c < c_hi; ++c) {
+  for (int c = c_lo; warp_ok && c < c_hi; ++c) {
     uint32_t v[16];
     tmem_ld16(trow + c * 16, v);
     tmem_ld_wait();
@@ -166,7 +168,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
   __syncthreads();  // also orders: every thread has finished reading Q/K smem?  (MMA done) -> sP may be written
   mx = fmaxf(sRed[r], sRed[128 + r]) * p.scale_log2;
   float sum = 0.f;
-  for (int c = c_lo; c < c_hi; ++c) {
+  for (int c = c_lo; warp_ok && c < c_hi; ++c) {
     uint32_t v[16];
     tmem_ld16(trow + c * 16, v);
     tmem_ld_wait();
@@ -509,8 +511,7 @@ constexpr int FPP_SMEM = 1024 + 2 * FPP_BUF + 512 + 256;
 // TMEM (512 columns): [S|dP] buffer i at i*128 (S +0, dP +64); accumulators of tile parity j at 256 + j*128 (+0, +64).
 // Barrier phases are derived from running counters (tile sequence n, global chunk sequence g).
 // ------------------------------------------------------------------------------------------------
-constexpr int P_STATS = 1;   // statistics warp: softmax LSE and D = rowsum(dO*O), one tile ahead (12 warps per CTA ->
-                             // 168 registers per thread: register allocation is per 4 warps, 13 warps would cap at 128)
+constexpr int P_STATS = 2;   // statistics warps: softmax LSE and D = rowsum(dO*O), one tile ahead
 // NG column groups per row: 4*NG worker warps (TMEM lane quadrant = warp & 3, column group = warp >> 2), then the
 // producer warp, the score issuer, the accumulate issuer and the statistics warps.
 template <bool CAUSAL, bool DKDV, int NG>
@@ -686,38 +687,26 @@ attn_bwd_persist_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gr
       const long long sbase = ((long long)b * p.H + h) * S;
       mbar_wait(&stat_empty[n & 1], ((n >> 1) & 1) ^ 1);
       if (!DKDV) {
-        // one warp covers the tile's 128 rows: 4 rows per lane, two at a time with all 32 16-byte loads of the pair in
-        // flight before the first FMA (a row-by-row loop would chain four global-load latencies per tile)
 #pragma unroll
-        for (int k = 0; k < 128 / (P_STATS * 32); k += 2) {
-          uint4 va[2][8], vc[2][8];
-          float Lr[2] = {0.f, 0.f};
-#pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const int ri = tile * 128 + t + (k + u) * (P_STATS * 32);
-            const int rc = min(ri, S - 1);      // clamped: loads always legal, results of padding rows discarded
-            const uint4* po = reinterpret_cast<const uint4*>(p.o_in + (long long)(row0 + rc) * d + h * 64);
-            const uint4* pd = reinterpret_cast<const uint4*>(p.dout + (long long)(row0 + rc) * d + h * 64);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) { va[u][j] = __ldg(po + j); vc[u][j] = __ldg(pd + j); }
-            Lr[u] = __ldg(p.lse + sbase + rc) * 1.4426950408889634f;
-          }
-#pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const int rr = t + (k + u) * (P_STATS * 32);
-            const int ri = tile * 128 + rr;
-            float acc = 0.f;
+        for (int k = 0; k < 128 / (P_STATS * 32); ++k) {
+          const int rr = t + k * (P_STATS * 32);
+          const int ri = tile * 128 + rr;
+          float acc = 0.f, L = 0.f;
+          if (ri < S) {
+            const uint4* po = reinterpret_cast<const uint4*>(p.o_in + (long long)(row0 + ri) * d + h * 64);
+            const uint4* pd = reinterpret_cast<const uint4*>(p.dout + (long long)(row0 + ri) * d + h * 64);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const uint4 a = va[u][j], c = vc[u][j];
+              const uint4 a = __ldg(po + j), c = __ldg(pd + j);
               acc += bf16_lo(a.x) * bf16_lo(c.x) + bf16_hi(a.x) * bf16_hi(c.x) + bf16_lo(a.y) * bf16_lo(c.y) +
                      bf16_hi(a.y) * bf16_hi(c.y) + bf16_lo(a.z) * bf16_lo(c.z) + bf16_hi(a.z) * bf16_hi(c.z) +
                      bf16_lo(a.w) * bf16_lo(c.w) + bf16_hi(a.w) * bf16_hi(c.w);
             }
-            if (ri < S) p.dsum[sbase + ri] = acc;
-            wL[rr] = ri < S ? Lr[u] : 0.f;
-            wL[256 + rr] = ri < S ? acc : 0.f;
+            L = p.lse[sbase + ri] * 1.4426950408889634f;
+            p.dsum[sbase + ri] = acc;
           }
+          wL[rr] = L;
+          wL[256 + rr] = acc;
         }
       } else {
 #pragma unroll
@@ -754,37 +743,27 @@ attn_bwd_persist_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gr
       }
       if (threadIdx.x == 0) PTRACE(DKDV, 0, 41);
 
-      // Software-pipelined chunk loop (round 2): the tcgen05.ld of chunk c+1 is issued before the fence / arrive that
-      // publishes chunk c, and the dS-buffer check runs under the loads in flight, so the fixed latencies the phase
-      // trace found serialised per chunk (barrier check ~250 clk, tcgen05.ld ~250, buffer check ~220, fence + arrive
-      // ~240: profiles/r1_attn_bwd_phase_trace.txt) overlap each other.  The score issuer runs 6-7 k clocks ahead, so
-      // S/dP of the next chunk are always in TMEM by then.  (First chunk of a tile: loaded here, not prefetched — the
-      // tile epilogue in between needs the registers.)
-      uint32_t sv[CW], dv[CW];
-      auto issue_ld = [&](int sbx) {
-        if (CW == 32) {
-          tmem_ld32(trow + sbx * 128 + grp * 32, reinterpret_cast<uint32_t(&)[32]>(sv));
-          tmem_ld32(trow + sbx * 128 + 64 + grp * 32, reinterpret_cast<uint32_t(&)[32]>(dv));
-        } else {
-          tmem_ld16(trow + sbx * 128 + grp * 16, reinterpret_cast<uint32_t(&)[16]>(sv));
-          tmem_ld16(trow + sbx * 128 + 64 + grp * 16, reinterpret_cast<uint32_t(&)[16]>(dv));
-        }
-      };
       for (int c = 0; c < nc; ++c, ++g) {
         const int sb = (int)(g & 1);
         const int wc = min(64, S_pad - c * 64);
         if (threadIdx.x == 0) PTRACE(DKDV, 0, c * 5 + 0);
-        if (c == 0 || !p.prefetch) {
-          mbar_wait(&sdp_full[sb], (uint32_t)((g >> 1) & 1));
-          tc_fence_after();
-          issue_ld(sb);
-        }
+        mbar_wait(&sdp_full[sb], (uint32_t)((g >> 1) & 1));
+        tc_fence_after();
         if (threadIdx.x == 0) PTRACE(DKDV, 0, c * 5 + 1);
-        mbar_wait(&ds_empty[sb], (uint32_t)(((g >> 1) & 1) ^ 1));  // accumulate MMAs of chunk g-2 have left the buffer
+        uint32_t sv[CW], dv[CW];
+        if (CW == 32) {
+          tmem_ld32(trow + sb * 128 + grp * 32, reinterpret_cast<uint32_t(&)[32]>(sv));
+          tmem_ld32(trow + sb * 128 + 64 + grp * 32, reinterpret_cast<uint32_t(&)[32]>(dv));
+        } else {
+          tmem_ld16(trow + sb * 128 + grp * 16, reinterpret_cast<uint32_t(&)[16]>(sv));
+          tmem_ld16(trow + sb * 128 + 64 + grp * 16, reinterpret_cast<uint32_t(&)[16]>(dv));
+        }
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&sdp_empty[sb]);
+        if (threadIdx.x == 0) PTRACE(DKDV, 0, c * 5 + 2);
+        mbar_wait(&ds_empty[sb], (uint32_t)(((g >> 1) & 1) ^ 1));  // accumulate MMAs of chunk g-2 have left the buffer
         if (threadIdx.x == 0) PTRACE(DKDV, 0, c * 5 + 3);
         uint8_t* myDS = sDS + sb * ATOM;
         uint8_t* myPT = sPT + sb * ATOM;
@@ -844,12 +823,6 @@ attn_bwd_persist_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gr
               if (DKDV) store_p16(myPT, r, grp * CW + half * 16, pt);
             }
           }
-        }
-        if (p.prefetch && c + 1 < nc) {   // prefetch S/dP of the next chunk (sv / dv are dead: everything above is in smem)
-          const long long gn = g + 1;
-          mbar_wait(&sdp_full[gn & 1], (uint32_t)((gn >> 1) & 1));
-          tc_fence_after();
-          issue_ld((int)(gn & 1));
         }
         fence_proxy_async_smem();
         __syncwarp();
@@ -1412,12 +1385,6 @@ extern "C" int mmb_attention_bwd_tc(const void* qkv, const void* out, const void
   a.S = S; a.H = H; a.S_pad = S_pad; a.scale = scale; a.scale_log2 = scale * 1.4426950408889634f;
   a.lse = const_cast<float*>(lse); a.o_in = (const __nv_bfloat16*)out; a.dout = (const __nv_bfloat16*)dout;
   a.dqkv = (__nv_bfloat16*)dqkv; a.dsum = dsum;
-  static int prefetch_env = -1;
-  if (prefetch_env < 0) {
-    const char* e = getenv("MMB_ATTN_PREFETCH");
-    prefetch_env = (e && e[0] == '0') ? 0 : 1;
-  }
-  a.prefetch = prefetch_env;
   const int n_work = ((S + 127) / 128) * H * B;
   const int grid_p = n_work < num_sms() ? n_work : num_sms();
   // Two persistent backward kernels: the column-split one (S <= 256; default there: 1.88 ms per image layer at

@@ -34,7 +34,8 @@ def scale(metric, v):
     u = units[col[metric]]
     if v is None:
         return None
-    mult = {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1.0, "usecond": 1e-6, "msecond": 1e-3, "nsecond": 1e-9, "second": 1.0}
+    mult = {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1.0, "usecond": 1e-6, "msecond": 1e-3, "nsecond": 1e-9, "second": 1.0,
+            "us": 1e-6, "ms": 1e-3, "ns": 1e-9, "s": 1.0}
     return v * mult[u] if u in mult else v
 
 
