@@ -89,6 +89,8 @@ int mmb_gemm_ce_grad(const void* A, long long lda, const void* B, long long ldb,
 
 /* dst[i] = bf16(src[i]) — parameter shadow for the tensor-core operands (what torch.autocast does per call). */
 int mmb_cast_f32_to_bf16(const float* src, void* dst_bf16, long long n, void* stream);
+/* bf16 -> fp32 (result of the optional bf16-compressed gradient all-reduce back into the optimizer's fp32 input). */
+int mmb_cast_bf16_to_f32(const void* src, float* dst, long long n, void* stream);
 
 /* Patch im2col + cast: img fp32 [B,3,H,W] -> bf16 [B*(H/ps)*(W/ps), 3*ps*ps] with row pitch ld_out elements (>= 3*ps*ps;
  * a multiple of 8 keeps the rows TMA-addressable, e.g. 592 for 14x14 patches), K order (c,kh,kw), patches row-major.

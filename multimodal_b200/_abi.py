@@ -16,6 +16,7 @@ PROTOTYPES = {
     "mmb_ce_stats_reduce": (i32, [vp, i32, i32, vp, i32, i32, f32, f32, vp, vp, vp, vp, vp]),
     "mmb_gemm_ce_grad": (i32, [vp, ll, vp, ll, i32, i32, i32, vp, i32, i32, i32, f32, f32, vp, vp, vp, vp, i32, i32, vp, ll, vp]),
     "mmb_cast_f32_to_bf16": (i32, [vp, vp, ll, vp]),
+    "mmb_cast_bf16_to_f32": (i32, [vp, vp, ll, vp]),
     "mmb_im2col_patches": (i32, [vp, vp, ll, i32, i32, i32, i32, vp]),
     "mmb_add_layernorm_fwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, f32, vp]),
     "mmb_vit_embed_ln_fwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, f32, vp]),

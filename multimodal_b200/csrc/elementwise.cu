@@ -38,6 +38,16 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat1
   if (blockIdx.x == 0 && threadIdx.x < (n & 3)) dst[(n4 << 2) + threadIdx.x] = __float2bfloat16(src[(n4 << 2) + threadIdx.x]);
 }
 
+// bf16 -> fp32 (the bf16-compressed gradient all-reduce hands its result back to the fp32 optimizer input)
+__global__ void cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, long long n) {
+  const long long n4 = n >> 2;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const uint2 v = __ldg(reinterpret_cast<const uint2*>(src) + i);
+    reinterpret_cast<float4*>(dst)[i] = make_float4(bf16_lo(v.x), bf16_hi(v.x), bf16_lo(v.y), bf16_hi(v.y));
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) dst[(n4 << 2) + threadIdx.x] = __bfloat162float(src[(n4 << 2) + threadIdx.x]);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Patch im2col + cast: image [B,3,H,W] fp32 -> patches [B*P, 3*ps*ps] bf16, K order (c, kh, kw) == the flattening
 // of conv.weight [width,3,ps,ps] (models/clip/image_encoder.py:50-56,91).  Patch index row-major (py, px)
@@ -779,6 +789,13 @@ extern "C" int mmb_cast_f32_to_bf16(const float* src, void* dst, long long n, vo
   if (n <= 0) return MMB_OK;
   if ((reinterpret_cast<uintptr_t>(src) & 15) || (reinterpret_cast<uintptr_t>(dst) & 7)) return MMB_ERR_ARG;
   cast_f32_bf16_kernel<<<grid_for(n / 4 + 1, 256), 256, 0, ST(stream)>>>(src, (__nv_bfloat16*)dst, n);
+  return LAUNCH_RC();
+}
+
+extern "C" int mmb_cast_bf16_to_f32(const void* src, float* dst, long long n, void* stream) {
+  if (n <= 0) return MMB_OK;
+  if ((reinterpret_cast<uintptr_t>(dst) & 15) || (reinterpret_cast<uintptr_t>(src) & 7)) return MMB_ERR_ARG;
+  cast_bf16_f32_kernel<<<grid_for(n / 4 + 1, 256), 256, 0, ST(stream)>>>((const __nv_bfloat16*)src, dst, n);
   return LAUNCH_RC();
 }
 

@@ -135,6 +135,14 @@ def cast_bf16(src: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Te
     return out
 
 
+def cast_f32(src: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    _chk(src, torch.bfloat16, "src"); _chk(out, torch.float32, "out")
+    if not (src.is_contiguous() and out.is_contiguous()) or src.numel() != out.numel():
+        raise MMBError("cast_f32: contiguous tensors of equal size expected")
+    _lib.check(_lib.lib().mmb_cast_bf16_to_f32(_p(src), _p(out), src.numel(), _stream()), "mmb_cast_bf16_to_f32")
+    return out
+
+
 def im2col(img: torch.Tensor, ps: int, out: torch.Tensor) -> torch.Tensor:
     _chk(img, torch.float32, "img"); _chk(out, torch.bfloat16, "out")
     B, C, H, W = img.shape

@@ -19,6 +19,17 @@ from .engine_loss import _dist_state, contrastive_schedule
 from .utils.distributed import BackpropType
 
 
+class _CastBack:
+    """Pending bf16 all-reduce whose result is cast back into the fp32 gradient buffer when waited for."""
+
+    def __init__(self, work, src_bf16, dst_f32):
+        self.work, self.src, self.dst = work, src_bf16, dst_f32
+
+    def wait(self):
+        self.work.wait()
+        ops.cast_f32(self.src, self.dst)
+
+
 class _FlatAdamW:
     def __init__(self, store: ParamStore, lr, betas, eps, weight_decay):
         store.flatten_()
@@ -70,12 +81,26 @@ class ContrastiveTrainer:
             import os
             overlap_allreduce = os.environ.get("MMB_OVERLAP_ALLREDUCE", "0") == "1"
         self.overlap_allreduce = bool(overlap_allreduce)
+        # MMB_GRAD_ALLREDUCE=bf16: compress the flat gradients to bf16 for the all-reduce (half the NVLink payload; the
+        # reduced sum is cast back into the fp32 buffer the optimizer reads).  Default fp32: bit-identical semantics to a
+        # single process on the concatenated batch.  Only applies to the non-overlapped schedule.
+        import os as _os
+        self.allreduce_bf16 = _os.environ.get("MMB_GRAD_ALLREDUCE", "fp32").lower() == "bf16"
+        self._gb = {}
         self._works: List = []
         self.kernel_launches = 0
 
     # -- gradient all-reduce (NCCL) ------------------------------------------------------------------------
     def _allreduce(self, t: torch.Tensor):
         if self.world > 1:
+            if self.allreduce_bf16 and not self.overlap_allreduce and t.numel() >= (1 << 20):
+                gb = self._gb.get(t.data_ptr())
+                if gb is None or gb.numel() != t.numel():
+                    gb = self._gb[t.data_ptr()] = torch.empty(t.numel(), device=t.device, dtype=torch.bfloat16)
+                ops.cast_bf16(t, gb)
+                work = dist.all_reduce(gb, op=dist.ReduceOp.SUM, async_op=True)
+                self._works.append(_CastBack(work, gb, t))
+                return
             self._works.append(dist.all_reduce(t, op=dist.ReduceOp.SUM, async_op=True))
 
     def _layer_boundaries(self, tower) -> List[int]:
