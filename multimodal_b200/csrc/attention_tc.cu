@@ -880,6 +880,362 @@ attn_bwd_persist_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gr
 }
 
 // ------------------------------------------------------------------------------------------------
+// Backward, FUSED single pass (round 2).  The two-pass kernels above recompute S and dP (and their exponentials, the
+// 64 KB-per-chunk TMEM reads that bound the workers) once for dQ and once for dK/dV.  Here ONE pass in the dK/dV
+// orientation (tile rows = keys) also produces dQ: the dS^T chunk the workers leave in shared memory for
+// dK += dS^T_c Q_c is, read as an MN-major A operand, exactly dS_c — so dQ_c += dS_c K_j is one more accumulate-MMA
+// against the resident K tile.  Two 64-query chunks form one M = 128 operand (two MN blocks 16 KB apart), and the
+// partial sums over the key tiles of a head are accumulated IN TMEM across the key-tile loop, so nothing is reduced
+// through global memory or DSMEM.  Work item = (batch, head); S <= 256 (<= 2 key tiles, <= 4 query chunks, <= 2 dQ
+// blocks).
+// TMEM (512 columns): [S^T|dP^T] buffer i at i*128 (+0, +64); dV at 256, dK at 320 (one key tile at a time);
+//                     dQ block p (queries 128p ..) at 384 + 64p, alive for the whole work item.
+// smem: K_j | V_j tile operands x 2 (64 KB), (Q_c | dO_c) chunk ring x 3 (48 KB), dS^T x 4 (chunk c -> buffer c: the
+// pairs (0,1), (2,3) are the two dQ A operands; 64 KB), P^T x 2 (32 KB), per-query LSE / D x 2 (4 KB).
+// Warps: 8 workers (thread = key row x column half), TMA producer, score issuer, accumulate issuer, 2 statistics warps.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t desc_mn_a(uint32_t saddr) { return make_smem_desc_sw128(saddr, 16384, 1024); }
+
+// NSTAT statistics warps: 2 -> 13 warps, 128 registers per thread (register allocation is per 4 warps; ~180 B of
+// spills); 1 -> 12 warps, 168 registers, no spills, half the statistics bandwidth.
+template <bool CAUSAL, int NSTAT>
+__global__ void __launch_bounds__((8 + 3 + NSTAT) * 32, 1)
+attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_constant__ CUtensorMap tmQKV64,
+                      const __grid_constant__ CUtensorMap tmDO64, const AttnTcArgs p, const int n_work) {
+  constexpr int RING = 3;
+  constexpr int CH = 8192;  // one 64-row x 128 B chunk operand
+  constexpr int P_WORKERS = 8;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sA = smem;                                   // [2 key-tile buffers][K_j 16 KB | V_j 16 KB]
+  uint8_t* sRing = sA + 4 * ATOM;                       // RING x (Q_c 8 KB | dO_c 8 KB)
+  uint8_t* sDS = sRing + RING * 2 * CH;                 // [4] dS^T chunk c (16 KB each)
+  uint8_t* sPT = sDS + 4 * ATOM;                        // [2] P^T chunk
+  float* sLD = reinterpret_cast<float*>(sPT + 2 * ATOM);   // [2][512]: lse(log2) [256] | rowsum(dO*O) [256] per query
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sLD + 2 * 512);
+  uint64_t* tile_full = bars;            // [2]  K_j, V_j landed                              producer -> both issuers
+  uint64_t* tile_empty = bars + 2;       // [2]  both issuers' last MMA on the tile complete (2 commits) -> producer
+  uint64_t* ring_full = bars + 4;        // [RING]
+  uint64_t* ring_empty = bars + 8;       // [RING] accumulate MMAs of the chunk complete                -> producer
+  uint64_t* sdp_full = bars + 12;        // [2]  S^T_c / dP^T_c in TMEM                 score issuer    -> workers
+  uint64_t* sdp_empty = bars + 14;       // [2]  workers have read them (8 warps)                       -> score issuer
+  uint64_t* ds_full = bars + 16;         // [2]  dS^T_c and P^T_c in smem (8 warps)     workers         -> acc issuer
+  uint64_t* pt_empty = bars + 18;        // [2]  dV / dK MMAs of the chunk complete     acc issuer      -> workers
+  uint64_t* dsb_empty = bars + 20;       // [4]  dQ MMA of the chunk's pair complete    acc issuer      -> workers
+  uint64_t* acc_full = bars + 24;        // [1]  dV, dK of the key tile final           acc issuer      -> workers
+  uint64_t* acc_empty = bars + 25;       // [1]  workers have read them (8 warps)                       -> acc issuer
+  uint64_t* dq_full = bars + 26;         // [1]  dQ of the work item final              acc issuer      -> workers
+  uint64_t* dq_empty = bars + 27;        // [1]  workers have read it (8 warps)                         -> acc issuer
+  uint64_t* stat_full = bars + 28;       // [2]  LSE / D of the work item in sLD        stats warps     -> workers
+  uint64_t* stat_empty = bars + 30;      // [2]  workers are done with them (8 warps)                   -> stats warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 32);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int S = p.S, S_pad = p.S_pad, d = p.H * 64;
+  const int nc = (S_pad + 63) >> 6;      // query chunks (<= 4)
+  const int ntile = (S + 127) >> 7;      // key tiles (<= 2)
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmQKV128); tma_prefetch_desc(&tmQKV64); tma_prefetch_desc(&tmDO64);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tile_full[i], 1); mbar_init(&tile_empty[i], 2);
+      mbar_init(&sdp_full[i], 1); mbar_init(&sdp_empty[i], P_WORKERS);
+      mbar_init(&ds_full[i], P_WORKERS); mbar_init(&pt_empty[i], 1);
+      mbar_init(&stat_full[i], NSTAT); mbar_init(&stat_empty[i], P_WORKERS);
+    }
+    for (int i = 0; i < 4; ++i) mbar_init(&dsb_empty[i], 1);
+    for (int i = 0; i < RING; ++i) { mbar_init(&ring_full[i], 1); mbar_init(&ring_empty[i], 1); }
+    mbar_init(acc_full, 1); mbar_init(acc_empty, P_WORKERS);
+    mbar_init(dq_full, 1); mbar_init(dq_empty, P_WORKERS);
+    fence_mbar_init();
+  }
+  if (warp == P_WORKERS) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == P_WORKERS) {
+    // ======================= TMA producer =======================
+    if (lane == 0) {
+      int nt = 0;
+      int g = 0;
+      for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+        const int h = w % p.H, b = w / p.H;
+        const int row0 = b * S;
+        for (int j = 0; j < ntile; ++j, ++nt) {
+          const int tb = nt & 1;
+          mbar_wait(&tile_empty[tb], ((nt >> 1) & 1) ^ 1);
+          uint8_t* a0 = sA + tb * 2 * ATOM;
+          mbar_arrive_expect_tx(&tile_full[tb], 2 * ATOM);
+          tma_load_2d(&tmQKV128, &tile_full[tb], a0, d + h * 64, row0 + j * 128);             // K tile
+          tma_load_2d(&tmQKV128, &tile_full[tb], a0 + ATOM, 2 * d + h * 64, row0 + j * 128);  // V tile
+          for (int c = 0; c < nc; ++c, ++g) {
+            const int st = g % RING;
+            mbar_wait(&ring_empty[st], (uint32_t)(((g / RING) & 1) ^ 1));
+            uint8_t* dst = sRing + st * 2 * CH;
+            mbar_arrive_expect_tx(&ring_full[st], 2 * CH);
+            tma_load_2d(&tmQKV64, &ring_full[st], dst, h * 64, row0 + c * 64);        // Q_c
+            tma_load_2d(&tmDO64, &ring_full[st], dst + CH, h * 64, row0 + c * 64);     // dO_c
+          }
+        }
+      }
+    }
+  } else if (warp == P_WORKERS + 1) {
+    // ======================= score issuer: S^T_c = K_j Q_c^T, dP^T_c = V_j dO_c^T =======================
+    if (lane == 0) {
+      const uint32_t uA = smem_u32(sA), uRing = smem_u32(sRing);
+      int nt = 0;
+      int g = 0;
+      for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+        for (int j = 0; j < ntile; ++j, ++nt) {
+          const int tb = nt & 1;
+          mbar_wait(&tile_full[tb], (nt >> 1) & 1);
+          const uint64_t a0 = desc_k(uA + tb * 2 * ATOM), a1 = desc_k(uA + tb * 2 * ATOM + ATOM);
+          for (int c = 0; c < nc; ++c, ++g) {
+            const int st = g % RING, sb = g & 1;
+            const int wc = min(64, S_pad - c * 64);
+            mbar_wait(&ring_full[st], (uint32_t)((g / RING) & 1));
+            mbar_wait(&sdp_empty[sb], (uint32_t)(((g >> 1) & 1) ^ 1));
+            tc_fence_after();
+            const uint32_t id = idesc_rt(wc, false, false);
+            const uint32_t ub = uRing + st * 2 * CH;
+            const uint64_t b0 = desc_k(ub), b1 = desc_k(ub + CH);
+            const uint32_t tS = tmem + sb * 128;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_bf16(tS, a0 + 2 * k, b0 + 2 * k, id, k > 0);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_bf16(tS + 64, a1 + 2 * k, b1 + 2 * k, id, k > 0);
+            umma_commit(&sdp_full[sb]);
+          }
+          umma_commit(&tile_empty[tb]);   // this thread's MMAs on the tile buffer (1 of 2 arrivals)
+        }
+      }
+    }
+  } else if (warp == P_WORKERS + 2) {
+    // ======================= accumulate issuer: dV += P^T_c dO_c ; dK += dS^T_c Q_c ; dQ_pair += dS_pair K_j ========
+    if (lane == 0) {
+      const uint32_t uA = smem_u32(sA), uRing = smem_u32(sRing), uDS = smem_u32(sDS), uPT = smem_u32(sPT);
+      const uint32_t id = idesc_rt(64, false, true);      // A K-major (P^T / dS^T rows = keys), B MN-major
+      const uint32_t idq = idesc_rt(64, true, true);      // A MN-major (dS^T read as dS), B MN-major (K_j)
+      int n = 0, nt = 0;
+      int g = 0;
+      for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++n) {
+        for (int j = 0; j < ntile; ++j, ++nt) {
+          const int tb = nt & 1;
+          const int kk = min(8, (min(S - j * 128, 128) + 15) >> 4);   // 16-key steps of this tile that hold real keys
+          mbar_wait(&acc_empty[0], (uint32_t)((nt & 1) ^ 1));          // dV / dK of the previous key tile read out
+          if (j == 0) mbar_wait(&dq_empty[0], (uint32_t)((n & 1) ^ 1)); // dQ of the previous work item read out
+          mbar_wait(&tile_full[tb], (nt >> 1) & 1);                    // K_j (B operand of the dQ MMAs) landed
+          const uint32_t uK = uA + tb * 2 * ATOM;
+          for (int c = 0; c < nc; ++c, ++g) {
+            const int st = g % RING, sb = g & 1;
+            const int wc = min(64, S_pad - c * 64);
+            mbar_wait(&ds_full[sb], (uint32_t)((g >> 1) & 1));
+            mbar_wait(&ring_full[st], (uint32_t)((g / RING) & 1));  // long complete; acquires the TMA writes for this thread
+            tc_fence_after();
+            const uint32_t ub = uRing + st * 2 * CH;
+            const int ks = wc >> 4;
+            for (int k = 0; k < ks; ++k)
+              umma_bf16(tmem + 256, desc_k(uPT + sb * ATOM + k * 32), desc_mn(ub + CH + k * 2048), id, (c > 0 || k > 0));
+            for (int k = 0; k < ks; ++k)
+              umma_bf16(tmem + 320, desc_k(uDS + c * ATOM + k * 32), desc_mn(ub + k * 2048), id, (c > 0 || k > 0));
+            umma_commit(&pt_empty[sb]);
+            umma_commit(&ring_empty[st]);
+            if ((c & 1) || c == nc - 1) {   // the pair (2q, 2q+1) of dS^T chunks is complete: dQ block q += dS K_j
+              const int q = c >> 1;
+              for (int k = 0; k < kk; ++k)
+                umma_bf16(tmem + 384 + q * 64, desc_mn_a(uDS + 2 * q * ATOM + k * 2048), desc_mn(uK + k * 2048), idq,
+                          (j > 0 || k > 0));
+              umma_commit(&dsb_empty[2 * q]);
+              if (2 * q + 1 < nc) umma_commit(&dsb_empty[2 * q + 1]);
+            }
+            if (c == nc - 1) {
+              umma_commit(&acc_full[0]);
+              umma_commit(&tile_empty[tb]);   // 2 of 2 arrivals: K_j / V_j may be overwritten
+            }
+          }
+        }
+        umma_commit(&dq_full[0]);
+      }
+    }
+  } else if (warp >= P_WORKERS + 3) {
+    // ======================= statistics warps: sLD[n & 1] = {LSE (log2 units) [256], D [256]} of the work item ========
+    const int t = (warp - (P_WORKERS + 3)) * 32 + lane;   // 0 .. 63
+    int n = 0;
+    for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++n) {
+      const int h = w % p.H, b = w / p.H;
+      const int row0 = b * S;
+      float* wL = sLD + (n & 1) * 512;
+      const long long sbase = ((long long)b * p.H + h) * S;
+      mbar_wait(&stat_empty[n & 1], ((n >> 1) & 1) ^ 1);
+      for (int qi = t; qi < 256; qi += NSTAT * 32) {
+        float acc = 0.f, L = 0.f;
+        if (qi < S) {
+          const uint4* po = reinterpret_cast<const uint4*>(p.o_in + (long long)(row0 + qi) * d + h * 64);
+          const uint4* pd = reinterpret_cast<const uint4*>(p.dout + (long long)(row0 + qi) * d + h * 64);
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) {
+            const uint4 a = __ldg(po + jj), c = __ldg(pd + jj);
+            acc += bf16_lo(a.x) * bf16_lo(c.x) + bf16_hi(a.x) * bf16_hi(c.x) + bf16_lo(a.y) * bf16_lo(c.y) +
+                   bf16_hi(a.y) * bf16_hi(c.y) + bf16_lo(a.z) * bf16_lo(c.z) + bf16_hi(a.z) * bf16_hi(c.z) +
+                   bf16_lo(a.w) * bf16_lo(c.w) + bf16_hi(a.w) * bf16_hi(c.w);
+          }
+          L = p.lse[sbase + qi] * 1.4426950408889634f;
+        }
+        wL[qi] = L;
+        wL[256 + qi] = acc;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&stat_full[n & 1]);
+    }
+  } else {
+    // ======================= 8 worker warps: thread == key row x column half =======================
+    const int q4 = warp & 3, grp = warp >> 2;
+    const int r = q4 * 32 + lane;
+    const uint32_t trow = tmem + ((uint32_t)(q4 * 32) << 16);
+    const long long ld = 3LL * d;
+    int n = 0, nt = 0;
+    int g = 0;
+    for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++n) {
+      const int h = w % p.H, b = w / p.H;
+      const int row0 = b * S;
+      const float* sL = sLD + (n & 1) * 512;
+      const float* sD = sL + 256;
+      mbar_wait(&stat_full[n & 1], (n >> 1) & 1);
+      for (int j = 0; j < ntile; ++j, ++nt) {
+        const int ri = j * 128 + r;   // key index of this thread's row
+        for (int c = 0; c < nc; ++c, ++g) {
+          const int sb = g & 1;
+          const int wc = min(64, S_pad - c * 64);
+          mbar_wait(&sdp_full[sb], (uint32_t)((g >> 1) & 1));
+          tc_fence_after();
+          uint32_t sv[32], dv[32];
+          tmem_ld32(trow + sb * 128 + grp * 32, sv);
+          tmem_ld32(trow + sb * 128 + 64 + grp * 32, dv);
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&sdp_empty[sb]);
+          mbar_wait(&pt_empty[sb], (uint32_t)(((g >> 1) & 1) ^ 1));   // dV / dK MMAs of chunk g-2 have left P^T[sb]
+          mbar_wait(&dsb_empty[c], (uint32_t)((nt & 1) ^ 1));          // the previous key tile's dQ MMA has left dS^T[c]
+          uint8_t* myDS = sDS + c * ATOM;
+          uint8_t* myPT = sPT + sb * ATOM;
+          const int cbase = c * 64 + grp * 32;
+          const bool full = (ri < S) && (cbase + 32 <= S) && (!CAUSAL || ri <= cbase);
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            float ds[16], pt[16];
+            if (ri >= S) {
+#pragma unroll
+              for (int e = 0; e < 16; ++e) { ds[e] = 0.f; pt[e] = 0.f; }
+            } else if (full) {
+              const float4* pl = reinterpret_cast<const float4*>(sL + cbase + half * 16);
+              const float4* pd = reinterpret_cast<const float4*>(sD + cbase + half * 16);
+#pragma unroll
+              for (int e4 = 0; e4 < 4; ++e4) {
+                const float4 l4 = pl[e4], d4 = pd[e4];
+                const float ls[4] = {l4.x, l4.y, l4.z, l4.w}, dd[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const int e = e4 * 4 + k;
+                  const float pv = ex2_approx(fmaf(__uint_as_float(sv[half * 16 + e]), p.scale_log2, -ls[k]));
+                  pt[e] = pv;
+                  ds[e] = pv * (__uint_as_float(dv[half * 16 + e]) - dd[k]) * p.scale;
+                }
+              }
+            } else {
+#pragma unroll
+              for (int e = 0; e < 16; ++e) {
+                const int cj = cbase + half * 16 + e;
+                const bool valid = (cj < S) && (!CAUSAL || ri <= cj);
+                const float L = sL[cj & 255], Dv = sD[cj & 255];
+                const float pv = valid ? ex2_approx(__uint_as_float(sv[half * 16 + e]) * p.scale_log2 - L) : 0.f;
+                pt[e] = pv;
+                ds[e] = pv * (__uint_as_float(dv[half * 16 + e]) - Dv) * p.scale;
+              }
+            }
+            if (grp * 32 + half * 16 < wc) {
+              store_p16(myDS, r, grp * 32 + half * 16, ds);
+              store_p16(myPT, r, grp * 32 + half * 16, pt);
+            }
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&ds_full[sb]);
+        }
+        // ---- key-tile epilogue: dV (V block, 2d) and dK (K block, d) of rows ri -> bf16 -> dqkv ----
+        mbar_wait(&acc_full[0], (uint32_t)(nt & 1));
+        tc_fence_after();
+        uint32_t v0[32], v1[32];
+        tmem_ld32(trow + 256 + grp * 32, v0);
+        tmem_ld32(trow + 320 + grp * 32, v1);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[0]);
+        if (ri < S) {
+#pragma unroll
+          for (int which = 0; which < 2; ++which) {
+            const uint32_t* v = which == 0 ? v0 : v1;
+            __nv_bfloat16* dst = p.dqkv + (long long)(row0 + ri) * ld + (which == 0 ? 2 * d : d) + h * 64 + grp * 32;
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+              uint4 o;
+              o.x = pack_bf16x2(__uint_as_float(v[jj * 8 + 0]), __uint_as_float(v[jj * 8 + 1]));
+              o.y = pack_bf16x2(__uint_as_float(v[jj * 8 + 2]), __uint_as_float(v[jj * 8 + 3]));
+              o.z = pack_bf16x2(__uint_as_float(v[jj * 8 + 4]), __uint_as_float(v[jj * 8 + 5]));
+              o.w = pack_bf16x2(__uint_as_float(v[jj * 8 + 6]), __uint_as_float(v[jj * 8 + 7]));
+              reinterpret_cast<uint4*>(dst)[jj] = o;
+            }
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&stat_empty[n & 1]);   // this warp no longer reads sLD[n & 1]
+      // ---- work-item epilogue: dQ blocks (TMEM lane = query within the block) -> bf16 -> Q block of dqkv ----
+      mbar_wait(&dq_full[0], (uint32_t)(n & 1));
+      tc_fence_after();
+      {
+        uint32_t v0[32], v1[32];
+        tmem_ld32(trow + 384 + grp * 32, v0);
+        if (nc > 2) tmem_ld32(trow + 448 + grp * 32, v1);   // uniform
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&dq_empty[0]);
+#pragma unroll
+        for (int blk = 0; blk < 2; ++blk) {
+          const int qi = blk * 128 + r;
+          if (blk * 2 < nc && qi < S) {
+            const uint32_t* v = blk == 0 ? v0 : v1;
+            __nv_bfloat16* dst = p.dqkv + (long long)(row0 + qi) * ld + h * 64 + grp * 32;
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+              uint4 o;
+              o.x = pack_bf16x2(__uint_as_float(v[jj * 8 + 0]), __uint_as_float(v[jj * 8 + 1]));
+              o.y = pack_bf16x2(__uint_as_float(v[jj * 8 + 2]), __uint_as_float(v[jj * 8 + 3]));
+              o.z = pack_bf16x2(__uint_as_float(v[jj * 8 + 4]), __uint_as_float(v[jj * 8 + 5]));
+              o.w = pack_bf16x2(__uint_as_float(v[jj * 8 + 6]), __uint_as_float(v[jj * 8 + 7]));
+              reinterpret_cast<uint4*>(dst)[jj] = o;
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == P_WORKERS) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+constexpr int BWDF_SMEM = 1024 + 4 * ATOM + 3 * 16384 + 4 * ATOM + 2 * ATOM + 4096 + 512;   // 213.5 KB
+#ifndef MMB_ATTN_BWD_DEFAULT
+#define MMB_ATTN_BWD_DEFAULT 1   /* 1 = column-split two-pass, 2 = fused single pass (S <= 256) */
+#endif
+
+// ------------------------------------------------------------------------------------------------
 // Backward, persistent PING-PONG version (round 2; default).  Same producer / two issuers / statistics warps as
 // attn_bwd_persist_kernel, but the eight worker warps form TWO GROUPS that serve ALTERNATE chunks (group = parity of
 // the running chunk counter) instead of splitting every chunk's columns.  In the column-split kernel all workers hit
@@ -1387,12 +1743,28 @@ extern "C" int mmb_attention_bwd_tc(const void* qkv, const void* out, const void
   a.dqkv = (__nv_bfloat16*)dqkv; a.dsum = dsum;
   const int n_work = ((S + 127) / 128) * H * B;
   const int grid_p = n_work < num_sms() ? n_work : num_sms();
-  // Two persistent backward kernels: the column-split one (S <= 256; default there: 1.88 ms per image layer at
-  // B = 1024) and the ping-pong one (the only one for 256 < S <= 384).  MMB_ATTN_BWD=pp / =colsplit force one (A/B).
+  // Backward kernels: the two-pass column-split one (S <= 256), the fused single-pass one (S <= 256) and the two-pass
+  // ping-pong one (the only one for 256 < S <= 384).  MMB_ATTN_BWD=fused / =colsplit / =pp force one (A/B).
   static int variant = -1;
   if (variant < 0) {
     const char* e = getenv("MMB_ATTN_BWD");
-    variant = (e && e[0] == 'p') ? 0 : 1;
+    variant = (e && e[0] == 'p') ? 0 : (e && e[0] == 'f') ? 2 : (e && e[0] == 'c') ? 1 : MMB_ATTN_BWD_DEFAULT;
+  }
+  if (variant == 2 && S <= 256) {
+    const int n_items = B * H;
+    const int grid_f = n_items < num_sms() ? n_items : num_sms();
+    static int nstat = -1;   // MMB_ATTN_FUSED_STATS=1|2: statistics warps of the fused kernel (A/B)
+    if (nstat < 0) {
+      const char* e = getenv("MMB_ATTN_FUSED_STATS");
+      nstat = (e && e[0] == '2') ? 2 : 1;
+    }
+#define LAUNCH_BWDF(C, NS)                                                                                       \
+    cudaFuncSetAttribute(attn_bwd_fused_kernel<C, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWDF_SMEM); \
+    attn_bwd_fused_kernel<C, NS><<<grid_f, (8 + 3 + NS) * 32, BWDF_SMEM, st>>>(q128, q64, o64, a, n_items);
+    if (causal) { if (nstat == 2) { LAUNCH_BWDF(true, 2) } else { LAUNCH_BWDF(true, 1) } }
+    else        { if (nstat == 2) { LAUNCH_BWDF(false, 2) } else { LAUNCH_BWDF(false, 1) } }
+#undef LAUNCH_BWDF
+    return (int)cudaGetLastError();
   }
   if (variant == 1 && S <= 256) {
 #define LAUNCH_BWDP(C, K, SM)                                                                                     \
