@@ -170,6 +170,9 @@ int mmb_attention_fwd(const void* qkv, void* out, float* lse, int B, int S, int 
                       float scale, void* stream);
 int mmb_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, int B, int S,
                       int H, int head_dim, int causal, float scale, void* stream);
+/* Number of kernels one mmb_attention_bwd call launches at sequence length S (1: fused single-pass kernel, S <= 256;
+ * 2: dQ pass + dK/dV pass) — for callers that count launches. */
+int mmb_attention_bwd_launches(int S);
 
 /* Same with a key-padding mask [B,S] (1 = attend, 0 = masked_fill(-inf)): the BERT-style attention of the FLAVA text
  * tower (modules/encoders/bert_text_encoder.py:87-93 -> modules/layers/attention.py:228-229).  S <= 384. */

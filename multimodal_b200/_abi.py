@@ -35,6 +35,7 @@ PROTOTYPES = {
     "mmb_memset_async": (i32, [vp, i32, ll, vp]),
     "mmb_attention_fwd": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, f32, vp]),
     "mmb_attention_bwd": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, vp]),
+    "mmb_attention_bwd_launches": (i32, [i32]),
     "mmb_attention_fwd_kmask": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, vp]),
     "mmb_attention_probs": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, f32, vp]),
     "mmb_bert_embed_ln_fwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, ll, i32, i32, i32, i32, f32, vp]),

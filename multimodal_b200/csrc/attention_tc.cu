@@ -1232,7 +1232,7 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
 }
 constexpr int BWDF_SMEM = 1024 + 4 * ATOM + 3 * 16384 + 4 * ATOM + 2 * ATOM + 4096 + 512;   // 213.5 KB
 #ifndef MMB_ATTN_BWD_DEFAULT
-#define MMB_ATTN_BWD_DEFAULT 1   /* 1 = column-split two-pass, 2 = fused single pass (S <= 256) */
+#define MMB_ATTN_BWD_DEFAULT 2   /* 1 = column-split two-pass, 2 = fused single pass (S <= 256): 1.27 vs 1.88 ms at B/16 */
 #endif
 
 // ------------------------------------------------------------------------------------------------
@@ -1707,6 +1707,17 @@ extern "C" int mmb_attention_fwd_kmask(const void* qkv, void* out, float* lse, c
   return attention_fwd_tc_impl(qkv, out, lse, kmask, B, S, H, causal, scale, stream);
 }
 
+static int attn_bwd_variant() {   // 0 = two-pass ping-pong, 1 = two-pass column-split, 2 = fused single pass
+  static int variant = -1;
+  if (variant < 0) {
+    const char* e = getenv("MMB_ATTN_BWD");
+    variant = (e && e[0] == 'p') ? 0 : (e && e[0] == 'f') ? 2 : (e && e[0] == 'c') ? 1 : MMB_ATTN_BWD_DEFAULT;
+  }
+  return variant;
+}
+// kernels one mmb_attention_bwd call launches at sequence length S (callers that count launches: bench.py gpu_launches)
+extern "C" int mmb_attention_bwd_launches(int S) { return (attn_bwd_variant() == 2 && S <= 256) ? 1 : 2; }
+
 extern "C" int mmb_attention_bwd_tc(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
                                     int B, int S, int H, int causal, float scale, void* stream) {
   if (B <= 0 || S <= 0 || S > SMAX) return MMB_ERR_UNSUPPORTED;
@@ -1745,11 +1756,7 @@ extern "C" int mmb_attention_bwd_tc(const void* qkv, const void* out, const void
   const int grid_p = n_work < num_sms() ? n_work : num_sms();
   // Backward kernels: the two-pass column-split one (S <= 256), the fused single-pass one (S <= 256) and the two-pass
   // ping-pong one (the only one for 256 < S <= 384).  MMB_ATTN_BWD=fused / =colsplit / =pp force one (A/B).
-  static int variant = -1;
-  if (variant < 0) {
-    const char* e = getenv("MMB_ATTN_BWD");
-    variant = (e && e[0] == 'p') ? 0 : (e && e[0] == 'f') ? 2 : (e && e[0] == 'c') ? 1 : MMB_ATTN_BWD_DEFAULT;
-  }
+  const int variant = attn_bwd_variant();
   if (variant == 2 && S <= 256) {
     const int n_items = B * H;
     const int grid_f = n_items < num_sms() ? n_items : num_sms();

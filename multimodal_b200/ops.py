@@ -257,6 +257,7 @@ def attention_bwd(qkv, out, dout, lse, dqkv, B, S, H, causal, scale):
     with _timed("attn_bwd", 10.0 * S * S * 64 * H * B * (0.5 if causal else 1.0), "F"):   # 2.5 x forward
         _lib.check(_lib.lib().mmb_attention_bwd(_p(qkv), _p(out), _p(dout), _p(lse), _p(dqkv), B, S, H, 64, int(causal),
                                                 float(scale), _stream()), "mmb_attention_bwd")
+        _lib.LAUNCHES += _lib.lib().mmb_attention_bwd_launches(S) - 1   # two kernels for the two-pass variants
 
 
 def contrastive_ce_stats(sims, logit_scale, rows, N, label_offset, smoothing, loss_weight, row_loss, lse_out,
