@@ -45,6 +45,7 @@ struct AttnTcArgs {
   __nv_bfloat16* dqkv;          // bwd: [B*S, 3d]
   float* dsum;                  // bwd: rowsum(dO * O) [B,H,S], written by the dQ kernel, read by the dK/dV kernel
   const uint8_t* kmask;         // fwd: optional key-padding mask [B,S], 1 = attend (utils/attention.py:13-53)
+  int l2_prefetch;              // bwd fused: prefetch the next work item's operands into L2 (MMB_ATTN_L2PF=0 disables)
 };
 
 __device__ __forceinline__ uint64_t desc_k(uint32_t saddr) { return make_smem_desc_sw128(saddr, 16, 1024); }
@@ -493,6 +494,313 @@ attn_fwd_pp_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
   }
 }
 constexpr int FPP_SMEM = 1024 + 2 * FPP_BUF + 512 + 256;
+
+// ------------------------------------------------------------------------------------------------
+// Forward, persistent ITEM kernel (round 2, second iteration; 128 < S <= 256, no mask: the image towers).  Work item =
+// one (batch, head) with BOTH of its 128-query tiles, so K and V are fetched once per head instead of once per tile:
+//   * producer warp: Q (2 tiles) + K of item n+1 are loaded as soon as both S = Q K^T MMAs of item n have completed,
+//     V of item n+1 as soon as both P V MMAs of item n have - operands are single-buffered, their lifetimes staggered;
+//   * two MMA issuer warps, one per query tile, each running its own  S_t -> (softmax) -> O_t  chain, so the two tiles
+//     drift into anti-phase: the tensor pipe works for one tile while the other tile's softmax owns the issue slots;
+//   * two softmax groups of four warps, thread == query row: pass 1 row maximum with 3-input max on four independent
+//     chains, pass 2 packed f32x2 scale/subtract and row sums (FFMA2 / FADD2), ex2, bf16 P into its own swizzled smem
+//     operand (2 x 64 KB), tcgen05.ld of chunk c+1 in flight while chunk c is processed.
+// Measured floors on this part (scripts/probes/tmem_probe.cu): tcgen05.ld 345 B/clk/SM with 8 warps (one 128x256 fp32
+// block in 380 clk), MUFU.EX2 ~62 /clk/SM, so neither TMEM reads nor exp bound the softmax: instruction issue does
+// (the round-1 tile kernel spends 8.7 warp-instructions per score element at 33 % issue utilisation).
+// smem: Q 32 KB | K 32 KB | V 32 KB | P_0 64 KB | P_1 64 KB = 224 KB.  TMEM: S_t at columns [256 t, 256 t + S_pad), O_t
+// reuses [256 t, 256 t + 64) once the softmax has consumed S_t.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t pk2(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void upk2(uint64_t r, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(r)); }
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t fmul2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+
+constexpr int FIT_THREADS = 12 * 32;   // 8 softmax warps + producer + 2 MMA issuers + 1 idle (registers: per 4 warps)
+constexpr int FIT_SMEM = 1024 + 14 * ATOM + 256;
+__global__ void __launch_bounds__(FIT_THREADS, 1)
+attn_fwd_item_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant__ CUtensorMap tmPad,
+                     const AttnTcArgs p, const int n_items, const int stagger, unsigned long long* trace) {
+  // trace (debug, scripts/attn_item_trace.py): per-phase SM-clock totals of CTAs 0-3, [cta][warp][64]
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sQ = smem;                 // 2 atoms: query tile 0, query tile 1
+  uint8_t* sK = smem + 2 * ATOM;      // S_pad rows
+  uint8_t* sV = smem + 4 * ATOM;      // S_pad rows
+  uint8_t* sPall = smem + 6 * ATOM;   // 2 x 4 atoms
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 14 * ATOM);
+  uint64_t* qk_full = bars;           // Q, K landed                              producer -> MMA warps
+  uint64_t* v_full = bars + 1;        // V landed                                 producer -> MMA warps
+  uint64_t* qk_empty = bars + 2;      // both S MMAs complete (2 commits)         MMA warps -> producer
+  uint64_t* v_empty = bars + 3;       // both PV MMAs complete (2 commits)        MMA warps -> producer
+  uint64_t* s_full = bars + 4;        // [2] S_t in TMEM                          MMA warp t -> softmax group t
+  uint64_t* p_full = bars + 6;        // [2] P_t in smem (4 warps)                softmax group t -> MMA warp t
+  uint64_t* o_full = bars + 8;        // [2] O_t in TMEM                          MMA warp t -> softmax group t
+  uint64_t* s_free = bars + 10;       // [2] O_t read out of TMEM (4 warps)       softmax group t -> MMA warp t
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int S = p.S, S_pad = p.S_pad, d = p.H * 64;
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tm128);
+    tma_prefetch_desc(&tmPad);
+    mbar_init(qk_full, 1); mbar_init(v_full, 1); mbar_init(qk_empty, 2); mbar_init(v_empty, 2);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 4); mbar_init(&o_full[i], 1); mbar_init(&s_free[i], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 8) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 8) {
+    // ======================= TMA producer =======================
+    if (lane == 0) {
+      int it = 0;
+      for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
+        const int h = w % p.H, b = w / p.H;
+        const int row0 = b * S;
+        const uint32_t par = (uint32_t)(it & 1);
+        mbar_wait(qk_empty, par ^ 1);
+        mbar_arrive_expect_tx(qk_full, 2 * ATOM + S_pad * 128);
+        tma_load_2d(&tm128, qk_full, sQ, h * 64, row0);
+        tma_load_2d(&tm128, qk_full, sQ + ATOM, h * 64, row0 + 128);
+        tma_load_2d(&tmPad, qk_full, sK, d + h * 64, row0);
+        mbar_wait(v_empty, par ^ 1);
+        mbar_arrive_expect_tx(v_full, S_pad * 128);
+        tma_load_2d(&tmPad, v_full, sV, 2 * d + h * 64, row0);
+      }
+    }
+  } else if (warp == 9 || warp == 10) {
+    // ======================= MMA issuer of query tile t =======================
+    if (lane == 0) {
+      const int t = warp - 9;
+      const uint32_t id_s = idesc_rt(S_pad, false, false), id_o = idesc_rt(64, false, true);
+      const int nk = S_pad >> 4;
+      const uint32_t uQ = smem_u32(sQ) + t * ATOM, uK = smem_u32(sK), uV = smem_u32(sV);
+      const uint32_t uP = smem_u32(sPall) + t * 4 * ATOM;
+      const uint32_t tacc = tmem + t * 256;
+      int it = 0;
+      // Anti-phase start: tile 1's chain begins once tile 0's first softmax has finished, so that from then on one
+      // group's exp pass (MUFU-bound: 16 ex2 / clk / SM) overlaps the other group's maximum pass, MMA waits and epilogue
+      // instead of both groups fighting for the MUFU at the same time and idling together afterwards.
+      if (stagger && t == 1) mbar_wait(&p_full[0], 0);
+      for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
+        const uint32_t par = (uint32_t)(it & 1);
+        mbar_wait(qk_full, par);
+        mbar_wait(&s_free[t], par ^ 1);       // O_t of the previous item has left this TMEM block
+        tc_fence_after();
+        if (trace && blockIdx.x < 4 && it < 24) trace[(blockIdx.x * 12 + warp) * 64 + 2 * it] = clock64();
+        const uint64_t da = desc_k(uQ), db = desc_k(uK);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(tacc, da + 2 * k, db + 2 * k, id_s, k > 0);
+        umma_commit(&s_full[t]);
+        umma_commit(qk_empty);
+        mbar_wait(&p_full[t], par);
+        mbar_wait(v_full, par);
+        tc_fence_after();
+        if (trace && blockIdx.x < 4 && it < 24) trace[(blockIdx.x * 12 + warp) * 64 + 2 * it + 1] = clock64();
+        for (int j = 0; j < nk; ++j)
+          umma_bf16(tacc, desc_k(uP + (j >> 2) * ATOM + (j & 3) * 32), desc_mn(uV + j * 2048), id_o, j > 0);
+        umma_commit(&o_full[t]);
+        umma_commit(v_empty);
+      }
+    }
+  } else if (warp < 8) {
+    // ======================= softmax group t: thread == query row of tile t =======================
+    const int t = warp >> 2, q4 = warp & 3;
+    const int r = q4 * 32 + lane;
+    const int qi = t * 128 + r;
+    uint8_t* sP = sPall + t * 4 * ATOM;
+    const uint32_t trow = tmem + t * 256 + ((uint32_t)(q4 * 32) << 16);
+    const bool row_ok = qi < S;
+    const bool warp_ok = t * 128 + q4 * 32 < S;   // warp-uniform (tcgen05.ld / wait are .sync.aligned)
+    const int nfull = S >> 5;                     // 32-column steps whose keys are all real
+    const int nstep = (S_pad + 31) >> 5;          // + at most one partial step (16 or 32 columns wide, some keys padding)
+    const uint64_t c2 = pk2(p.scale_log2, p.scale_log2);
+    int it = 0;
+    const bool tr = trace != nullptr && blockIdx.x < 4 && lane == 0;
+    unsigned long long* trw = trace + (blockIdx.x * 12 + warp) * 64;
+    long long tp = tr ? clock64() : 0, acc_ws = 0, acc_p1 = 0, acc_p2 = 0, acc_wo = 0, acc_ep = 0;
+    for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
+      const int h = w % p.H, b = w / p.H;
+      const uint32_t par = (uint32_t)(it & 1);
+      mbar_wait(&s_full[t], par);
+      tc_fence_after();
+      long long t0 = 0, t1 = 0;
+      if (tr) { t0 = clock64(); acc_ws += t0 - tp; if (it < 20) trw[8 + 2 * it] = t0; }
+      float mx = 0.f, sum = 1.f;
+      if (warp_ok) {
+        uint32_t va[32], vb[32];
+        auto ld = [&](int c, uint32_t (&v)[32]) {
+          if (c * 32 + 32 <= S_pad) tmem_ld32(trow + c * 32, v);
+          else tmem_ld16(trow + c * 32, reinterpret_cast<uint32_t(&)[16]>(v));
+        };
+        // ---- pass 1: row maximum, four independent chains ----
+        float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+        auto red_max = [&](int c, const uint32_t (&v)[32]) {
+          if (c < nfull) {
+#pragma unroll
+            for (int e = 0; e < 32; e += 8) {
+              m0 = fmax3(m0, __uint_as_float(v[e]), __uint_as_float(v[e + 1]));
+              m1 = fmax3(m1, __uint_as_float(v[e + 2]), __uint_as_float(v[e + 3]));
+              m2 = fmax3(m2, __uint_as_float(v[e + 4]), __uint_as_float(v[e + 5]));
+              m3 = fmax3(m3, __uint_as_float(v[e + 6]), __uint_as_float(v[e + 7]));
+            }
+          } else {
+            const int nv = S - c * 32;     // real keys in the partial step (< 32)
+#pragma unroll
+            for (int e = 0; e < 32; ++e)
+              if (e < nv) m0 = fmaxf(m0, __uint_as_float(v[e]));
+          }
+        };
+        ld(0, va);
+        for (int c = 0; c < nstep; c += 2) {
+          tmem_ld_wait();
+          if (c + 1 < nstep) ld(c + 1, vb);
+          red_max(c, va);
+          if (c + 1 < nstep) {
+            tmem_ld_wait();
+            if (c + 2 < nstep) ld(c + 2, va);
+            red_max(c + 1, vb);
+          }
+        }
+        mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * p.scale_log2;
+        if (tr) { t1 = clock64(); acc_p1 += t1 - t0; }
+        // ---- pass 2: p = 2^(s * scale * log2e - mx), row sum, bf16 P into the K-major swizzled operand ----
+        const uint64_t nm2 = pk2(-mx, -mx);
+        uint64_t s0 = pk2(0.f, 0.f), s1 = s0;
+        float st = 0.f;
+        auto exp_store = [&](int c, const uint32_t (&v)[32]) {
+          if (c < nfull) {
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+              uint32_t pk[8];
+#pragma unroll
+              for (int e = 0; e < 16; e += 4) {
+                float x0, x1, x2, x3;
+                upk2(ffma2(pk2(__uint_as_float(v[hf * 16 + e]), __uint_as_float(v[hf * 16 + e + 1])), c2, nm2), x0, x1);
+                upk2(ffma2(pk2(__uint_as_float(v[hf * 16 + e + 2]), __uint_as_float(v[hf * 16 + e + 3])), c2, nm2), x2, x3);
+                x0 = ex2_approx(x0); x1 = ex2_approx(x1); x2 = ex2_approx(x2); x3 = ex2_approx(x3);
+                s0 = fadd2(s0, pk2(x0, x1));
+                s1 = fadd2(s1, pk2(x2, x3));
+                pk[e >> 1] = pack_bf16x2(x0, x1);
+                pk[(e >> 1) + 1] = pack_bf16x2(x2, x3);
+              }
+              const int j0 = c * 32 + hf * 16;
+              uint8_t* a = sP + (j0 >> 6) * ATOM + r * 128;
+              const int c8 = (j0 & 63) >> 3;
+              *reinterpret_cast<uint4*>(a + ((c8 ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              *reinterpret_cast<uint4*>(a + (((c8 + 1) ^ (r & 7)) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            }
+          } else {
+            const int nv = S - c * 32, wdt = S_pad - c * 32;   // real keys / columns of the partial step
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+              if (hf * 16 >= wdt) break;
+              float pr[16];
+#pragma unroll
+              for (int e = 0; e < 16; ++e) {
+                const float x = (hf * 16 + e < nv) ? ex2_approx(fmaf(__uint_as_float(v[hf * 16 + e]), p.scale_log2, -mx)) : 0.f;
+                pr[e] = x;
+                st += x;
+              }
+              store_p16(sP, r, c * 32 + hf * 16, pr);
+            }
+          }
+        };
+        ld(0, va);
+        for (int c = 0; c < nstep; c += 2) {
+          tmem_ld_wait();
+          if (c + 1 < nstep) ld(c + 1, vb);
+          exp_store(c, va);
+          if (c + 1 < nstep) {
+            tmem_ld_wait();
+            if (c + 2 < nstep) ld(c + 2, va);
+            exp_store(c + 1, vb);
+          }
+        }
+        float a0, a1, a2, a3;
+        upk2(s0, a0, a1);
+        upk2(s1, a2, a3);
+        sum = (a0 + a1) + (a2 + a3) + st;
+      }
+      // every S column of this row has been read: P may be consumed, the TMEM block reused for O
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[t]);
+      long long t2 = 0;
+      if (tr) { t2 = clock64(); acc_p2 += t2 - t1; if (it < 20) trw[9 + 2 * it] = t2; }
+      // ---- epilogue: O (64 columns) / l -> bf16 -> out ; LSE ----
+      mbar_wait(&o_full[t], par);
+      tc_fence_after();
+      if (tr) { const long long t3 = clock64(); acc_wo += t3 - t2; t2 = t3; }
+      uint32_t o0[32], o1[32];
+      if (warp_ok) {
+        tmem_ld32(trow, o0);
+        tmem_ld32(trow + 32, o1);
+        tmem_ld_wait();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_free[t]);
+      if (row_ok) {
+        const float inv = 1.f / sum;
+        __nv_bfloat16* dst = p.out + ((long long)(b * S + qi)) * d + h * 64;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const uint32_t* v = half == 0 ? o0 : o1;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 o;
+            o.x = pack_bf16x2(__uint_as_float(v[j * 8 + 0]) * inv, __uint_as_float(v[j * 8 + 1]) * inv);
+            o.y = pack_bf16x2(__uint_as_float(v[j * 8 + 2]) * inv, __uint_as_float(v[j * 8 + 3]) * inv);
+            o.z = pack_bf16x2(__uint_as_float(v[j * 8 + 4]) * inv, __uint_as_float(v[j * 8 + 5]) * inv);
+            o.w = pack_bf16x2(__uint_as_float(v[j * 8 + 6]) * inv, __uint_as_float(v[j * 8 + 7]) * inv);
+            reinterpret_cast<uint4*>(dst)[half * 4 + j] = o;
+          }
+        }
+        if (p.lse) p.lse[((long long)b * p.H + h) * S + qi] = (mx + log2f(sum)) * 0.6931471805599453f;
+      }
+      if (tr) { tp = clock64(); acc_ep += tp - t2; }
+    }
+    if (tr) {
+      trw[0] = acc_ws; trw[1] = acc_p1; trw[2] = acc_p2; trw[3] = acc_wo; trw[4] = acc_ep; trw[5] = it;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
 
 // ------------------------------------------------------------------------------------------------
 // Backward, persistent version (round-1 final): ONE CTA per SM loops over (batch, head, 128-row tile) work items with
@@ -962,6 +1270,20 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
       for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
         const int h = w % p.H, b = w / p.H;
         const int row0 = b * S;
+        if (p.l2_prefetch && w + (int)gridDim.x < n_work) {
+          // the 3-stage chunk ring is shallower than the HBM latency (chunk period >= 700 + L/2 clocks):
+          // pull the NEXT work item's operands into L2 now, so that its ring loads see L2 latency instead
+          const int w2 = w + gridDim.x;
+          const int h2 = w2 % p.H, r2 = (w2 / p.H) * S;
+          for (int j = 0; j < ntile; ++j) {
+            tma_prefetch_l2_2d(&tmQKV128, d + h2 * 64, r2 + j * 128);
+            tma_prefetch_l2_2d(&tmQKV128, 2 * d + h2 * 64, r2 + j * 128);
+          }
+          for (int c = 0; c < nc; ++c) {
+            tma_prefetch_l2_2d(&tmQKV64, h2 * 64, r2 + c * 64);
+            tma_prefetch_l2_2d(&tmDO64, h2 * 64, r2 + c * 64);
+          }
+        }
         for (int j = 0; j < ntile; ++j, ++nt) {
           const int tb = nt & 1;
           mbar_wait(&tile_empty[tb], ((nt >> 1) & 1) ^ 1);
@@ -1082,8 +1404,8 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
           }
           L = p.lse[sbase + qi] * 1.4426950408889634f;
         }
-        wL[qi] = L;
-        wL[256 + qi] = acc;
+        wL[qi] = -L;                     // negated: the workers' packed FFMA2 adds them
+        wL[256 + qi] = -acc * p.scale;   // -D * scale:  dS = P * (dP * scale - D * scale)
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&stat_full[n & 1]);
@@ -1122,39 +1444,54 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
           uint8_t* myPT = sPT + sb * ATOM;
           const int cbase = c * 64 + grp * 32;
           const bool full = (ri < S) && (cbase + 32 <= S) && (!CAUSAL || ri <= cbase);
+          const uint64_t c2 = pk2(p.scale_log2, p.scale_log2), sc2 = pk2(p.scale, p.scale);
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
-            float ds[16], pt[16];
+            if (grp * 32 + half * 16 >= wc) continue;   // columns past S_pad (last chunk): nothing reads them (uniform)
+            uint8_t* aDS = myDS + ((grp * 32 + half * 16) >> 6) * ATOM + r * 128;
+            uint8_t* aPT = myPT + ((grp * 32 + half * 16) >> 6) * ATOM + r * 128;
+            const int c8 = ((grp * 32 + half * 16) & 63) >> 3;
+            const int o0 = (c8 ^ (r & 7)) << 4, o1 = ((c8 + 1) ^ (r & 7)) << 4;
             if (ri >= S) {
-#pragma unroll
-              for (int e = 0; e < 16; ++e) { ds[e] = 0.f; pt[e] = 0.f; }
+              *reinterpret_cast<uint4*>(aDS + o0) = make_uint4(0, 0, 0, 0);
+              *reinterpret_cast<uint4*>(aDS + o1) = make_uint4(0, 0, 0, 0);
+              *reinterpret_cast<uint4*>(aPT + o0) = make_uint4(0, 0, 0, 0);
+              *reinterpret_cast<uint4*>(aPT + o1) = make_uint4(0, 0, 0, 0);
             } else if (full) {
+              // packed f32x2 math: p = 2^(s c - L), dS = p (dP scale - D scale); sL / sD hold -L and -D scale
               const float4* pl = reinterpret_cast<const float4*>(sL + cbase + half * 16);
               const float4* pd = reinterpret_cast<const float4*>(sD + cbase + half * 16);
+              uint32_t kp[8], kd[8];
 #pragma unroll
               for (int e4 = 0; e4 < 4; ++e4) {
                 const float4 l4 = pl[e4], d4 = pd[e4];
-                const float ls[4] = {l4.x, l4.y, l4.z, l4.w}, dd[4] = {d4.x, d4.y, d4.z, d4.w};
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                  const int e = e4 * 4 + k;
-                  const float pv = ex2_approx(fmaf(__uint_as_float(sv[half * 16 + e]), p.scale_log2, -ls[k]));
-                  pt[e] = pv;
-                  ds[e] = pv * (__uint_as_float(dv[half * 16 + e]) - dd[k]) * p.scale;
-                }
+                const int e = half * 16 + e4 * 4;
+                float x0, x1, x2, x3, g0, g1, g2, g3;
+                upk2(ffma2(pk2(__uint_as_float(sv[e]), __uint_as_float(sv[e + 1])), c2, pk2(l4.x, l4.y)), x0, x1);
+                upk2(ffma2(pk2(__uint_as_float(sv[e + 2]), __uint_as_float(sv[e + 3])), c2, pk2(l4.z, l4.w)), x2, x3);
+                x0 = ex2_approx(x0); x1 = ex2_approx(x1); x2 = ex2_approx(x2); x3 = ex2_approx(x3);
+                const uint64_t t01 = ffma2(pk2(__uint_as_float(dv[e]), __uint_as_float(dv[e + 1])), sc2, pk2(d4.x, d4.y));
+                const uint64_t t23 = ffma2(pk2(__uint_as_float(dv[e + 2]), __uint_as_float(dv[e + 3])), sc2, pk2(d4.z, d4.w));
+                upk2(fmul2(pk2(x0, x1), t01), g0, g1);
+                upk2(fmul2(pk2(x2, x3), t23), g2, g3);
+                kp[e4 * 2] = pack_bf16x2(x0, x1); kp[e4 * 2 + 1] = pack_bf16x2(x2, x3);
+                kd[e4 * 2] = pack_bf16x2(g0, g1); kd[e4 * 2 + 1] = pack_bf16x2(g2, g3);
               }
+              *reinterpret_cast<uint4*>(aDS + o0) = make_uint4(kd[0], kd[1], kd[2], kd[3]);
+              *reinterpret_cast<uint4*>(aDS + o1) = make_uint4(kd[4], kd[5], kd[6], kd[7]);
+              *reinterpret_cast<uint4*>(aPT + o0) = make_uint4(kp[0], kp[1], kp[2], kp[3]);
+              *reinterpret_cast<uint4*>(aPT + o1) = make_uint4(kp[4], kp[5], kp[6], kp[7]);
             } else {
+              float ds[16], pt[16];
 #pragma unroll
               for (int e = 0; e < 16; ++e) {
                 const int cj = cbase + half * 16 + e;
                 const bool valid = (cj < S) && (!CAUSAL || ri <= cj);
-                const float L = sL[cj & 255], Dv = sD[cj & 255];
-                const float pv = valid ? ex2_approx(__uint_as_float(sv[half * 16 + e]) * p.scale_log2 - L) : 0.f;
+                const float nL = sL[cj & 255], nDs = sD[cj & 255];
+                const float pv = valid ? ex2_approx(fmaf(__uint_as_float(sv[half * 16 + e]), p.scale_log2, nL)) : 0.f;
                 pt[e] = pv;
-                ds[e] = pv * (__uint_as_float(dv[half * 16 + e]) - Dv) * p.scale;
+                ds[e] = pv * fmaf(__uint_as_float(dv[half * 16 + e]), p.scale, nDs);
               }
-            }
-            if (grp * 32 + half * 16 < wc) {
               store_p16(myDS, r, grp * 32 + half * 16, ds);
               store_p16(myPT, r, grp * 32 + half * 16, pt);
             }
@@ -1631,6 +1968,10 @@ constexpr int FWD_SMEM_BIG = 1024 + 9 * ATOM + 2048 + 384 + 64;
 
 using namespace mmb;
 
+// debug (not in include/mmb200.h): device buffer [4][12][64] receiving per-phase SM-clock totals of the item forward
+// kernel's first four CTAs (scripts/attn_item_trace.py); nullptr = off
+static unsigned long long* g_item_trace = nullptr;
+extern "C" int mmb_debug_attn_item_trace(void* p) { g_item_trace = (unsigned long long*)p; return 0; }
 #ifdef MMB_ATTN_TRACE
 extern "C" int mmb_debug_attn_trace(void* p) { return (int)cudaMemcpyToSymbol(g_attn_trace, &p, sizeof(p)); }
 #endif
@@ -1662,7 +2003,23 @@ static int attention_fwd_tc_impl(const void* qkv, void* out, float* lse, const u
   static int fwd_variant = -1;
   if (fwd_variant < 0) {
     const char* e = getenv("MMB_ATTN_FWD");
-    fwd_variant = (e && e[0] == 't') ? 1 : (e && e[0] == 'p') ? 0 : 2;
+    fwd_variant = (e && e[0] == 't') ? 1 : (e && e[0] == 'p') ? 0 : (e && e[0] == 'i') ? 3 : 2;
+  }
+  if (fwd_variant == 3 && S > 128 && S <= 256 && !causal && !kmask) {
+    AttnTcArgs a{};
+    a.S = S; a.H = H; a.S_pad = S_pad; a.scale = scale; a.scale_log2 = scale * 1.4426950408889634f;
+    a.lse = lse; a.out = (__nv_bfloat16*)out;
+    const int n_items = H * B;
+    const int grid_i = n_items < num_sms() ? n_items : num_sms();
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    cudaFuncSetAttribute(attn_fwd_item_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FIT_SMEM);
+    static int stagger = -1;
+    if (stagger < 0) {
+      const char* e2 = getenv("MMB_ATTN_ITEM_STAGGER");
+      stagger = (e2 && e2[0] == '0') ? 0 : 1;
+    }
+    attn_fwd_item_kernel<<<grid_i, FIT_THREADS, FIT_SMEM, st>>>(tm128, tmPad, a, n_items, stagger, g_item_trace);
+    return (int)cudaGetLastError();
   }
   if (!big && (fwd_variant == 0 || (fwd_variant == 2 && S <= 128))) {
     AttnTcArgs a{};
@@ -1760,6 +2117,12 @@ extern "C" int mmb_attention_bwd_tc(const void* qkv, const void* out, const void
   if (variant == 2 && S <= 256) {
     const int n_items = B * H;
     const int grid_f = n_items < num_sms() ? n_items : num_sms();
+    static int l2pf = -1;
+    if (l2pf < 0) {
+      const char* e = getenv("MMB_ATTN_L2PF");
+      l2pf = (e && e[0] == '0') ? 0 : 1;
+    }
+    a.l2_prefetch = l2pf;
     static int nstat = -1;   // MMB_ATTN_FUSED_STATS=1|2: statistics warps of the fused kernel (A/B)
     if (nstat < 0) {
       const char* e = getenv("MMB_ATTN_FUSED_STATS");

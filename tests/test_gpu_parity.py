@@ -112,7 +112,11 @@ def _attn_ref(qkv, B, S, H, causal):
 
 
 @pytest.mark.parametrize("B,S,H,causal", [(2, 197, 12, False), (3, 77, 8, True), (2, 5, 2, False), (1, 257, 16, False),
-                                         (2, 16, 1, True), (1, 1, 2, True)])
+                                         (2, 16, 1, True), (1, 1, 2, True),
+                                         # persistent kernels looping over several work items per CTA (> 148 items),
+                                         # tile boundaries of the two-tile forward / fused backward kernels
+                                         (40, 197, 12, False), (25, 129, 12, False), (13, 256, 12, False),
+                                         (30, 224, 6, False), (60, 77, 8, True)])
 def test_attention_fwd_bwd(dev, B, S, H, causal):
     from multimodal_b200 import ops
 
@@ -125,6 +129,12 @@ def test_attention_fwd_bwd(dev, B, S, H, causal):
     qf = qkv.float().requires_grad_(True)
     ref = _attn_ref(qf, B, S, H, causal)
     assert _rel(out, ref) < 8e-3  # bf16 P and bf16 output
+    with torch.no_grad():   # the row log-sum-exp the backward (and the attention-probability kernel) consumes
+        q, k, _ = qkv.float().view(B, S, 3, H, 64).permute(2, 0, 3, 1, 4)
+        att = q @ k.transpose(-1, -2) / 8.0
+        if causal:
+            att = att + torch.full((S, S), float("-inf"), device=qkv.device).triu(1)
+        torch.testing.assert_close(lse.view(B, H, S), torch.logsumexp(att, -1), rtol=1e-4, atol=2e-4)
     dout = (torch.randn(B * S, d, device=dev) * 0.5).bfloat16()
     ref.backward(dout.float())
     dqkv = torch.empty_like(qkv)
