@@ -46,6 +46,7 @@ struct AttnTcArgs {
   float* dsum;                  // bwd: rowsum(dO * O) [B,H,S], written by the dQ kernel, read by the dK/dV kernel
   const uint8_t* kmask;         // fwd: optional key-padding mask [B,S], 1 = attend (utils/attention.py:13-53)
   int l2_prefetch;              // bwd fused: prefetch the next work item's operands into L2 (MMB_ATTN_L2PF=0 disables)
+  unsigned long long* trace;    // debug: per-phase SM-clock totals of CTAs 0-3 (scripts/attn_item_trace.py), or nullptr
 };
 
 __device__ __forceinline__ uint64_t desc_k(uint32_t saddr) { return make_smem_desc_sw128(saddr, 16, 1024); }
@@ -89,7 +90,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
   uint64_t* bars = reinterpret_cast<uint64_t*>(sMask + 384);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const uint32_t ncols = S_pad <= 128 ? 128u : (S_pad <= 256 ? 256u : 512u);
   const bool has_mask = p.kmask != nullptr;
@@ -111,7 +112,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
   const uint32_t tmem = *tmem_slot;
   const int row0 = b * S;
 
-  if (threadIdx.x == 0) {
+  if (warp == 0 && elect_one()) {
     // K / V rows [0, min(S_pad,256)) come in one box (tmPad), the remainder (S_pad > 256) in a second one (tmRem)
     const int n1 = big ? 256 : S_pad, n2 = S_pad - n1;
     mbar_arrive_expect_tx(&bars[0], ATOM + S_pad * 128);
@@ -196,7 +197,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
   __syncthreads();
   const float l = sRed[256 + r] + sRed[384 + r];
 
-  if (threadIdx.x == 0) {
+  if (warp == 0 && elect_one()) {
     tc_fence_after();
     mbar_wait(&bars[1], 0);
     const uint32_t id = idesc_rt(64, false, true);
@@ -271,7 +272,7 @@ attn_fwd_pp_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
   uint64_t* t_empty = bars + 12;     // [2] O read out of TMEM (4 warps)        worker group   -> MMA warp
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const int S = p.S, S_pad = p.S_pad, d = p.H * 64;
   const int ntile = (S + 127) >> 7;
   const bool has_mask = p.kmask != nullptr;
@@ -293,7 +294,7 @@ attn_fwd_pp_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
 
   if (warp == FPP_WORKERS) {
     // ======================= TMA producer =======================
-    if (lane == 0) {
+    if (elect_one()) {
       int n = 0;
       for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++n) {
         const int tile = w % ntile, bh = w / ntile;
@@ -310,7 +311,7 @@ attn_fwd_pp_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
     }
   } else if (warp == FPP_WORKERS + 1) {
     // ======================= MMA issuer =======================
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t id_s = idesc_rt(S_pad, false, false), id_o = idesc_rt(64, false, true);
       const int nk = S_pad >> 4;
       auto issue_pv = [&](int m) {            // O_m = P_m V_m  (K-steps of 16 keys)
@@ -540,9 +541,11 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
 
 constexpr int FIT_THREADS = 12 * 32;   // 8 softmax warps + producer + 2 MMA issuers + 1 idle (registers: per 4 warps)
 constexpr int FIT_SMEM = 1024 + 14 * ATOM + 256;
+template <bool TRACE>
 __global__ void __launch_bounds__(FIT_THREADS, 1)
 attn_fwd_item_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant__ CUtensorMap tmPad,
-                     const AttnTcArgs p, const int n_items, const int stagger, unsigned long long* trace) {
+                     const __grid_constant__ CUtensorMap tmOut, const AttnTcArgs p, const int n_items, const int stagger,
+                     unsigned long long* trace) {
   // trace (debug, scripts/attn_item_trace.py): per-phase SM-clock totals of CTAs 0-3, [cta][warp][64]
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -561,11 +564,12 @@ attn_fwd_item_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_con
   uint64_t* s_free = bars + 10;       // [2] O_t read out of TMEM (4 warps)       softmax group t -> MMA warp t
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const int S = p.S, S_pad = p.S_pad, d = p.H * 64;
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tm128);
     tma_prefetch_desc(&tmPad);
+    tma_prefetch_desc(&tmOut);
     mbar_init(qk_full, 1); mbar_init(v_full, 1); mbar_init(qk_empty, 2); mbar_init(v_empty, 2);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 4); mbar_init(&o_full[i], 1); mbar_init(&s_free[i], 4);
@@ -580,7 +584,7 @@ attn_fwd_item_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_con
 
   if (warp == 8) {
     // ======================= TMA producer =======================
-    if (lane == 0) {
+    if (elect_one()) {
       int it = 0;
       for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
         const int h = w % p.H, b = w / p.H;
@@ -598,7 +602,7 @@ attn_fwd_item_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_con
     }
   } else if (warp == 9 || warp == 10) {
     // ======================= MMA issuer of query tile t =======================
-    if (lane == 0) {
+    if (elect_one()) {
       const int t = warp - 9;
       const uint32_t id_s = idesc_rt(S_pad, false, false), id_o = idesc_rt(64, false, true);
       const int nk = S_pad >> 4;
@@ -615,7 +619,7 @@ attn_fwd_item_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_con
         mbar_wait(qk_full, par);
         mbar_wait(&s_free[t], par ^ 1);       // O_t of the previous item has left this TMEM block
         tc_fence_after();
-        if (trace && blockIdx.x < 4 && it < 24) trace[(blockIdx.x * 12 + warp) * 64 + 2 * it] = clock64();
+        if (TRACE && blockIdx.x < 4 && it < 24) trace[(blockIdx.x * 12 + warp) * 64 + 2 * it] = clock64();
         const uint64_t da = desc_k(uQ), db = desc_k(uK);
 #pragma unroll
         for (int k = 0; k < 4; ++k) umma_bf16(tacc, da + 2 * k, db + 2 * k, id_s, k > 0);
@@ -624,7 +628,7 @@ attn_fwd_item_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_con
         mbar_wait(&p_full[t], par);
         mbar_wait(v_full, par);
         tc_fence_after();
-        if (trace && blockIdx.x < 4 && it < 24) trace[(blockIdx.x * 12 + warp) * 64 + 2 * it + 1] = clock64();
+        if (TRACE && blockIdx.x < 4 && it < 24) trace[(blockIdx.x * 12 + warp) * 64 + 2 * it + 1] = clock64();
         for (int j = 0; j < nk; ++j)
           umma_bf16(tacc, desc_k(uP + (j >> 2) * ATOM + (j & 3) * 32), desc_mn(uV + j * 2048), id_o, j > 0);
         umma_commit(&o_full[t]);
@@ -644,7 +648,7 @@ attn_fwd_item_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_con
     const int nstep = (S_pad + 31) >> 5;          // + at most one partial step (16 or 32 columns wide, some keys padding)
     const uint64_t c2 = pk2(p.scale_log2, p.scale_log2);
     int it = 0;
-    const bool tr = trace != nullptr && blockIdx.x < 4 && lane == 0;
+    const bool tr = TRACE && blockIdx.x < 4 && lane == 0;
     unsigned long long* trw = trace + (blockIdx.x * 12 + warp) * 64;
     long long tp = tr ? clock64() : 0, acc_ws = 0, acc_p1 = 0, acc_p2 = 0, acc_wo = 0, acc_ep = 0;
     for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
@@ -663,14 +667,19 @@ attn_fwd_item_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_con
         };
         // ---- pass 1: row maximum, four independent chains ----
         float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+        float m4 = -INFINITY, m5 = -INFINITY, m6 = -INFINITY, m7 = -INFINITY;
         auto red_max = [&](int c, const uint32_t (&v)[32]) {
-          if (c < nfull) {
+          if (c < nfull) {   // eight independent 3-input chains (scripts/probes/softmax_probe.cu: 55 vs 89 clk / step)
 #pragma unroll
-            for (int e = 0; e < 32; e += 8) {
+            for (int e = 0; e < 32; e += 16) {
               m0 = fmax3(m0, __uint_as_float(v[e]), __uint_as_float(v[e + 1]));
               m1 = fmax3(m1, __uint_as_float(v[e + 2]), __uint_as_float(v[e + 3]));
               m2 = fmax3(m2, __uint_as_float(v[e + 4]), __uint_as_float(v[e + 5]));
               m3 = fmax3(m3, __uint_as_float(v[e + 6]), __uint_as_float(v[e + 7]));
+              m4 = fmax3(m4, __uint_as_float(v[e + 8]), __uint_as_float(v[e + 9]));
+              m5 = fmax3(m5, __uint_as_float(v[e + 10]), __uint_as_float(v[e + 11]));
+              m6 = fmax3(m6, __uint_as_float(v[e + 12]), __uint_as_float(v[e + 13]));
+              m7 = fmax3(m7, __uint_as_float(v[e + 14]), __uint_as_float(v[e + 15]));
             }
           } else {
             const int nv = S - c * 32;     // real keys in the partial step (< 32)
@@ -690,7 +699,11 @@ attn_fwd_item_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_con
             red_max(c + 1, vb);
           }
         }
-        mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * p.scale_log2;
+        mx = fmaxf(fmaxf(fmax3(m0, m1, m2), fmax3(m3, m4, m5)), fmaxf(m6, m7)) * p.scale_log2;
+        // the previous item's O tile was staged in the first atom of sP for its TMA store: the store must have read
+        // it before pass 2 overwrites the atom (one elected thread waits, the group barrier tells the others)
+        if (q4 == 0 && lane == 0) tma_store_wait_read<0>();
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + t) : "memory");
         if (tr) { t1 = clock64(); acc_p1 += t1 - t0; }
         // ---- pass 2: p = 2^(s * scale * log2e - mx), row sum, bf16 P into the K-major swizzled operand ----
         const uint64_t nm2 = pk2(-mx, -mx);
@@ -749,6 +762,8 @@ attn_fwd_item_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_con
         upk2(s0, a0, a1);
         upk2(s1, a2, a3);
         sum = (a0 + a1) + (a2 + a3) + st;
+      } else {
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + t) : "memory");   // the group barrier of the branch above
       }
       // every S column of this row has been read: P may be consumed, the TMEM block reused for O
       fence_proxy_async_smem();
@@ -770,9 +785,12 @@ attn_fwd_item_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_con
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_free[t]);
-      if (row_ok) {
-        const float inv = 1.f / sum;
-        __nv_bfloat16* dst = p.out + ((long long)(b * S + qi)) * d + h * 64;
+      // O tile -> bf16 -> swizzled staging atom (P_t is dead once O_t exists) -> ONE TMA store per tile: a 3-D box
+      // [1 batch][128 rows][64 columns] that the tensor map clips at the sequence length.  (Direct st.global of one
+      // 128 B row per thread costs 32 L1 wavefronts per instruction, 2.2-3.8 k clocks per tile in the phase trace.)
+      if (warp_ok) {
+        const float inv = row_ok ? 1.f / sum : 0.f;
+        uint8_t* a = sP + r * 128;
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           const uint32_t* v = half == 0 ? o0 : o1;
@@ -783,16 +801,23 @@ attn_fwd_item_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_con
             o.y = pack_bf16x2(__uint_as_float(v[j * 8 + 2]) * inv, __uint_as_float(v[j * 8 + 3]) * inv);
             o.z = pack_bf16x2(__uint_as_float(v[j * 8 + 4]) * inv, __uint_as_float(v[j * 8 + 5]) * inv);
             o.w = pack_bf16x2(__uint_as_float(v[j * 8 + 6]) * inv, __uint_as_float(v[j * 8 + 7]) * inv);
-            reinterpret_cast<uint4*>(dst)[half * 4 + j] = o;
+            *reinterpret_cast<uint4*>(a + (((half * 4 + j) ^ (r & 7)) << 4)) = o;
           }
         }
-        if (p.lse) p.lse[((long long)b * p.H + h) * S + qi] = (mx + log2f(sum)) * 0.6931471805599453f;
+        if (row_ok && p.lse) p.lse[((long long)b * p.H + h) * S + qi] = (mx + log2f(sum)) * 0.6931471805599453f;
+      }
+      fence_proxy_async_smem();
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + t) : "memory");
+      if (q4 == 0 && lane == 0) {
+        tma_store_3d(&tmOut, sP, h * 64, t * 128, b);
+        tma_store_commit();
       }
       if (tr) { tp = clock64(); acc_ep += tp - t2; }
     }
     if (tr) {
       trw[0] = acc_ws; trw[1] = acc_p1; trw[2] = acc_p2; trw[3] = acc_wo; trw[4] = acc_ep; trw[5] = it;
     }
+    if (q4 == 0 && lane == 0) tma_store_wait_all<0>();   // smem must outlive the last store's read
   }
   tc_fence_before();
   __syncthreads();
@@ -853,7 +878,7 @@ attn_bwd_persist_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gr
   uint64_t* stat_empty = bars + 26;      // [2]  workers are done with them (8 warps)               -> stats warps
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 28);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const int S = p.S, S_pad = p.S_pad, d = p.H * 64;
   const int nc = (S_pad + 63) >> 6;
   const int ntile = (S + 127) >> 7;
@@ -878,7 +903,7 @@ attn_bwd_persist_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gr
 
   if (warp == P_WORKERS) {
     // ======================= TMA producer =======================
-    if (lane == 0) {
+    if (elect_one()) {
       int n = 0;
       long long g = 0;
       for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++n) {
@@ -913,7 +938,7 @@ attn_bwd_persist_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gr
     }
   } else if (warp == P_WORKERS + 1) {
     // ======================= score issuer: S_c = A0 B0_c^T, dP_c = A1 B1_c^T =======================
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t uA = smem_u32(sA), uRing = smem_u32(sRing);
       int n = 0;
       long long g = 0;
@@ -946,7 +971,7 @@ attn_bwd_persist_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gr
     }
   } else if (warp == P_WORKERS + 2) {
     // ======================= accumulate issuer: dQ += dS_c K_c  |  dV += P^T_c dO_c ; dK += dS^T_c Q_c ==============
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t uRing = smem_u32(sRing), uDS = smem_u32(sDS), uPT = smem_u32(sPT);
       const uint32_t id = idesc_rt(64, false, true);
       int n = 0;
@@ -1238,7 +1263,7 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
   uint64_t* stat_empty = bars + 30;      // [2]  workers are done with them (8 warps)                   -> stats warps
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 32);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const int S = p.S, S_pad = p.S_pad, d = p.H * 64;
   const int nc = (S_pad + 63) >> 6;      // query chunks (<= 4)
   const int ntile = (S + 127) >> 7;      // key tiles (<= 2)
@@ -1264,7 +1289,7 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
 
   if (warp == P_WORKERS) {
     // ======================= TMA producer =======================
-    if (lane == 0) {
+    if (elect_one()) {
       int nt = 0;
       int g = 0;
       for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
@@ -1294,6 +1319,7 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
           for (int c = 0; c < nc; ++c, ++g) {
             const int st = g % RING;
             mbar_wait(&ring_empty[st], (uint32_t)(((g / RING) & 1) ^ 1));
+            if (p.trace && blockIdx.x < 4 && g < 48) p.trace[(blockIdx.x * 12 + 8) * 64 + g] = clock64();
             uint8_t* dst = sRing + st * 2 * CH;
             mbar_arrive_expect_tx(&ring_full[st], 2 * CH);
             tma_load_2d(&tmQKV64, &ring_full[st], dst, h * 64, row0 + c * 64);        // Q_c
@@ -1304,7 +1330,7 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
     }
   } else if (warp == P_WORKERS + 1) {
     // ======================= score issuer: S^T_c = K_j Q_c^T, dP^T_c = V_j dO_c^T =======================
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t uA = smem_u32(sA), uRing = smem_u32(sRing);
       int nt = 0;
       int g = 0;
@@ -1317,8 +1343,10 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
             const int st = g % RING, sb = g & 1;
             const int wc = min(64, S_pad - c * 64);
             mbar_wait(&ring_full[st], (uint32_t)((g / RING) & 1));
+            if (p.trace && blockIdx.x < 4 && g < 24) p.trace[(blockIdx.x * 12 + 9) * 64 + 2 * g] = clock64();
             mbar_wait(&sdp_empty[sb], (uint32_t)(((g >> 1) & 1) ^ 1));
             tc_fence_after();
+            if (p.trace && blockIdx.x < 4 && g < 24) p.trace[(blockIdx.x * 12 + 9) * 64 + 2 * g + 1] = clock64();
             const uint32_t id = idesc_rt(wc, false, false);
             const uint32_t ub = uRing + st * 2 * CH;
             const uint64_t b0 = desc_k(ub), b1 = desc_k(ub + CH);
@@ -1335,7 +1363,7 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
     }
   } else if (warp == P_WORKERS + 2) {
     // ======================= accumulate issuer: dV += P^T_c dO_c ; dK += dS^T_c Q_c ; dQ_pair += dS_pair K_j ========
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t uA = smem_u32(sA), uRing = smem_u32(sRing), uDS = smem_u32(sDS), uPT = smem_u32(sPT);
       const uint32_t id = idesc_rt(64, false, true);      // A K-major (P^T / dS^T rows = keys), B MN-major
       const uint32_t idq = idesc_rt(64, true, true);      // A MN-major (dS^T read as dS), B MN-major (K_j)
@@ -1355,6 +1383,7 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
             mbar_wait(&ds_full[sb], (uint32_t)((g >> 1) & 1));
             mbar_wait(&ring_full[st], (uint32_t)((g / RING) & 1));  // long complete; acquires the TMA writes for this thread
             tc_fence_after();
+            if (p.trace && blockIdx.x < 4 && g < 24) p.trace[(blockIdx.x * 12 + 10) * 64 + 2 * g] = clock64();
             const uint32_t ub = uRing + st * 2 * CH;
             const int ks = wc >> 4;
             for (int k = 0; k < ks; ++k)
@@ -1375,6 +1404,7 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
               umma_commit(&acc_full[0]);
               umma_commit(&tile_empty[tb]);   // 2 of 2 arrivals: K_j / V_j may be overwritten
             }
+            if (p.trace && blockIdx.x < 4 && g < 24) p.trace[(blockIdx.x * 12 + 10) * 64 + 2 * g + 1] = clock64();
           }
         }
         umma_commit(&dq_full[0]);
@@ -1418,12 +1448,18 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
     const long long ld = 3LL * d;
     int n = 0, nt = 0;
     int g = 0;
+    const bool tr = p.trace != nullptr && blockIdx.x < 4 && lane == 0;
+    unsigned long long* trw = p.trace + (blockIdx.x * 12 + warp) * 64;
+    long long tq = tr ? clock64() : 0, a_stat = 0, a_sdp = 0, a_ld = 0, a_buf = 0, a_cmp = 0, a_accw = 0, a_epi = 0, a_dqw = 0,
+              a_dqe = 0;
+#define BT(acc) do { if (tr) { const long long tn_ = clock64(); acc += tn_ - tq; tq = tn_; } } while (0)
     for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++n) {
       const int h = w % p.H, b = w / p.H;
       const int row0 = b * S;
       const float* sL = sLD + (n & 1) * 512;
       const float* sD = sL + 256;
       mbar_wait(&stat_full[n & 1], (n >> 1) & 1);
+      BT(a_stat);
       for (int j = 0; j < ntile; ++j, ++nt) {
         const int ri = j * 128 + r;   // key index of this thread's row
         for (int c = 0; c < nc; ++c, ++g) {
@@ -1431,6 +1467,8 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
           const int wc = min(64, S_pad - c * 64);
           mbar_wait(&sdp_full[sb], (uint32_t)((g >> 1) & 1));
           tc_fence_after();
+          BT(a_sdp);
+          if (tr && g < 24) trw[16 + 2 * g] = tq;
           uint32_t sv[32], dv[32];
           tmem_ld32(trow + sb * 128 + grp * 32, sv);
           tmem_ld32(trow + sb * 128 + 64 + grp * 32, dv);
@@ -1438,8 +1476,10 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&sdp_empty[sb]);
+          BT(a_ld);
           mbar_wait(&pt_empty[sb], (uint32_t)(((g >> 1) & 1) ^ 1));   // dV / dK MMAs of chunk g-2 have left P^T[sb]
           mbar_wait(&dsb_empty[c], (uint32_t)((nt & 1) ^ 1));          // the previous key tile's dQ MMA has left dS^T[c]
+          BT(a_buf);
           uint8_t* myDS = sDS + c * ATOM;
           uint8_t* myPT = sPT + sb * ATOM;
           const int cbase = c * 64 + grp * 32;
@@ -1499,10 +1539,14 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) mbar_arrive(&ds_full[sb]);
+          BT(a_cmp);
+          if (tr && g < 24) trw[17 + 2 * g] = tq;
         }
         // ---- key-tile epilogue: dV (V block, 2d) and dK (K block, d) of rows ri -> bf16 -> dqkv ----
         mbar_wait(&acc_full[0], (uint32_t)(nt & 1));
         tc_fence_after();
+        BT(a_accw);
+        if (tr && warp == 0 && nt < 12) p.trace[(blockIdx.x * 12 + 11) * 64 + nt] = tq;
         uint32_t v0[32], v1[32];
         tmem_ld32(trow + 256 + grp * 32, v0);
         tmem_ld32(trow + 320 + grp * 32, v1);
@@ -1529,9 +1573,11 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&stat_empty[n & 1]);   // this warp no longer reads sLD[n & 1]
+      BT(a_epi);
       // ---- work-item epilogue: dQ blocks (TMEM lane = query within the block) -> bf16 -> Q block of dqkv ----
       mbar_wait(&dq_full[0], (uint32_t)(n & 1));
       tc_fence_after();
+      BT(a_dqw);
       {
         uint32_t v0[32], v1[32];
         tmem_ld32(trow + 384 + grp * 32, v0);
@@ -1558,7 +1604,13 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
           }
         }
       }
+      BT(a_dqe);
     }
+    if (tr) {
+      trw[0] = a_stat; trw[1] = a_sdp; trw[2] = a_ld; trw[3] = a_buf; trw[4] = a_cmp; trw[5] = a_accw; trw[6] = a_epi;
+      trw[7] = a_dqw; trw[8] = a_dqe; trw[9] = n;
+    }
+#undef BT
   }
   tc_fence_before();
   __syncthreads();
@@ -1620,7 +1672,7 @@ attn_bwd_pp_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_co
   uint64_t* stat_empty = bars + 34;      // [2]  workers are done with them (8 warps)               -> stats warp
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 36);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const int S = p.S, S_pad = p.S_pad, d = p.H * 64;
   const int nc = (S_pad + 63) >> 6;
   const int ntile = (S + 127) >> 7;
@@ -1645,7 +1697,7 @@ attn_bwd_pp_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_co
 
   if (warp == P_WORKERS) {
     // ======================= TMA producer =======================
-    if (lane == 0) {
+    if (elect_one()) {
       int n = 0;
       long long g = 0;
       for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++n) {
@@ -1680,7 +1732,7 @@ attn_bwd_pp_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_co
     }
   } else if (warp == P_WORKERS + 1) {
     // ======================= score issuer: S_c = A0 B0_c^T, dP_c = A1 B1_c^T =======================
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t uA = smem_u32(sA), uRing = smem_u32(sRing);
       int n = 0;
       long long g = 0;
@@ -1709,7 +1761,7 @@ attn_bwd_pp_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_co
     }
   } else if (warp == P_WORKERS + 2) {
     // ======================= accumulate issuer: dQ += dS_c K_c  |  dV += P^T_c dO_c ; dK += dS^T_c Q_c ==============
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t uRing = smem_u32(sRing), uDS = smem_u32(sDS), uPT = smem_u32(sPT);
       const uint32_t id = idesc_rt(64, false, true);
       int n = 0;
@@ -1996,29 +2048,37 @@ static int attention_fwd_tc_impl(const void* qkv, void* out, float* lse, const u
     if (rc) return rc;
   }
   const int smem_bytes = big ? FWD_SMEM_BIG : FWD_SMEM;
-  // Forward kernel choice (measured, B = 1024): single-tile sequences (S <= 128: the text tower, 0.192 vs 0.242 ms) run
-  // on the persistent ping-pong kernel; longer ones (image tower: 0.62 vs 0.74 ms) on the one-tile-per-CTA kernel, whose
-  // two resident CTAs per SM hide the per-tile load latency that two smem buffers cannot prefetch away.
-  // MMB_ATTN_FWD=tile / =pp force one of them (A/B testing).
+  // Forward kernel choice (measured, B = 1024): single-tile sequences (S <= 128: the text tower, 0.170 vs 0.238 ms) run
+  // on the persistent ping-pong kernel; two-tile sequences without a mask (the image towers, S = 197) on the item kernel
+  // (0.387 ms vs 0.618 tile / 0.606 ping-pong); everything else (masks, causal S > 128, 256 < S <= 384) on the
+  // one-tile-per-CTA kernel.  MMB_ATTN_FWD=tile / =pp / =item force one where it applies (A/B testing).
   static int fwd_variant = -1;
   if (fwd_variant < 0) {
     const char* e = getenv("MMB_ATTN_FWD");
     fwd_variant = (e && e[0] == 't') ? 1 : (e && e[0] == 'p') ? 0 : (e && e[0] == 'i') ? 3 : 2;
   }
-  if (fwd_variant == 3 && S > 128 && S <= 256 && !causal && !kmask) {
+  if ((fwd_variant == 3 || fwd_variant == 2) && S > 128 && S <= 256 && !causal && !kmask) {
     AttnTcArgs a{};
     a.S = S; a.H = H; a.S_pad = S_pad; a.scale = scale; a.scale_log2 = scale * 1.4426950408889634f;
     a.lse = lse; a.out = (__nv_bfloat16*)out;
     const int n_items = H * B;
     const int grid_i = n_items < num_sms() ? n_items : num_sms();
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    cudaFuncSetAttribute(attn_fwd_item_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FIT_SMEM);
+    cudaFuncSetAttribute(attn_fwd_item_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FIT_SMEM);
     static int stagger = -1;
     if (stagger < 0) {
       const char* e2 = getenv("MMB_ATTN_ITEM_STAGGER");
       stagger = (e2 && e2[0] == '0') ? 0 : 1;
     }
-    attn_fwd_item_kernel<<<grid_i, FIT_THREADS, FIT_SMEM, st>>>(tm128, tmPad, a, n_items, stagger, g_item_trace);
+    CUtensorMap tmOut;   // [B][S][d] view of out: the per-tile store box is clipped at S (rows of the next batch stay intact)
+    rc = make_tmap_3d_bf16(&tmOut, out, (uint64_t)d, (uint64_t)S, (uint64_t)B, (uint64_t)d * 2, (uint64_t)S * d * 2, 64, 128);
+    if (rc) return rc;
+    if (g_item_trace) {
+      cudaFuncSetAttribute(attn_fwd_item_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FIT_SMEM);
+      attn_fwd_item_kernel<true><<<grid_i, FIT_THREADS, FIT_SMEM, st>>>(tm128, tmPad, tmOut, a, n_items, stagger, g_item_trace);
+    } else {
+      attn_fwd_item_kernel<false><<<grid_i, FIT_THREADS, FIT_SMEM, st>>>(tm128, tmPad, tmOut, a, n_items, stagger, nullptr);
+    }
     return (int)cudaGetLastError();
   }
   if (!big && (fwd_variant == 0 || (fwd_variant == 2 && S <= 128))) {
@@ -2123,6 +2183,7 @@ extern "C" int mmb_attention_bwd_tc(const void* qkv, const void* out, const void
       l2pf = (e && e[0] == '0') ? 0 : 1;
     }
     a.l2_prefetch = l2pf;
+    a.trace = g_item_trace;
     static int nstat = -1;   // MMB_ATTN_FUSED_STATS=1|2: statistics warps of the fused kernel (A/B)
     if (nstat < 0) {
       const char* e = getenv("MMB_ATTN_FUSED_STATS");

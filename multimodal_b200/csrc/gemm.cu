@@ -109,7 +109,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   uint64_t* aux_bar = bars + 2 * STAGES + 2 * ACC_STAGES;  // [2] aux slab landed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2 * ACC_STAGES + 2);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = uniform_warp_idx();   // warp-uniform for ptxas: the issue loops below keep their operands in URs
   const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
@@ -144,7 +144,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       for (int t = tile_first; t < total_tiles; t += tile_step) {
@@ -185,7 +185,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0 && rank == 0) {
+    if (rank == 0 && elect_one()) {
       constexpr uint32_t idesc = make_idesc_bf16(TILE_M, BLOCK_N, A_MN, B_MN);
       // K-major SW128: 8-row groups 1024 B apart (SBO); LBO unused. MN-major SW128: 64-element MN blocks
       // (one TMA box, BLOCK_K rows x 128 B) 8192 B apart (LBO); 8-row k groups 1024 B apart (SBO).
@@ -603,6 +603,23 @@ int make_tmap_2d(CUtensorMap* out, const void* ptr, int elem_bytes, bool is_f32,
     g_tmap_cache[slot].valid = true;
   }
   return MMB_OK;
+}
+
+// 3-D bf16 tensor [dim2, dim1, inner] (pitch1 / pitch2 in bytes), box = [1, box1, box_inner], 128B swizzle: a box never
+// crosses a dim1 boundary, so per-batch row tiles are clipped at the sequence length (attention forward epilogue).
+int make_tmap_3d_bf16(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t dim1, uint64_t dim2, uint64_t pitch1,
+                      uint64_t pitch2, uint32_t box_inner, uint32_t box1) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) return MMB_ERR_DRIVER;
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (pitch1 & 15) || (pitch2 & 15) || box_inner * 2 != 128) return MMB_ERR_ARG;
+  cuuint64_t gdim[3] = {inner, dim1, dim2};
+  cuuint64_t gstr[2] = {pitch1, pitch2};
+  cuuint32_t box[3] = {box_inner, box1, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? MMB_OK : MMB_ERR_DRIVER;
 }
 
 static int g_num_sms = 0;

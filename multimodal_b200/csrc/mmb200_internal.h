@@ -23,5 +23,7 @@
 namespace mmb {
 int make_tmap_2d(CUtensorMap* out, const void* ptr, int elem_bytes, bool is_f32, uint64_t inner, uint64_t outer,
                  uint64_t pitch_bytes, uint32_t box_inner, uint32_t box_outer);
+int make_tmap_3d_bf16(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t dim1, uint64_t dim2, uint64_t pitch1,
+                      uint64_t pitch2, uint32_t box_inner, uint32_t box1);
 int num_sms();
 }  // namespace mmb

@@ -1,0 +1,148 @@
+// Micro-benchmark of the attention softmax inner loops on register-resident scores (no TMEM, no MMA): clocks per
+// 32-score step per warp for the variants the forward kernels use.  Build:
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o build/softmax_probe scripts/probes/softmax_probe.cu
+#include <cstdio>
+#include <cstdint>
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+
+__device__ __forceinline__ uint64_t pk2(float a, float b) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void upk2(uint64_t r, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(r)); }
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) { uint64_t r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) { uint64_t r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ float fmax3(float a, float b, float c) { float r; asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r; }
+__device__ __forceinline__ float ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ uint32_t pack(float lo, float hi) { __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi); return *reinterpret_cast<uint32_t*>(&v); }
+
+// MODE 0: packed (FFMA2, 32 MUFU, FADD2 x2 chains, F2FP, 4 STS.128)   1: scalar, 4 sum chains   2: packed, no STS
+//      3: packed, no F2FP / STS   4: MUFU + 4 scalar sums only   5: pass 1, FMNMX3 4 chains   6: pass 1, FMNMX 4 chains
+//      7: pass 1, FMNMX3 8 chains   8: MODE 0 with half of the exponentials as a degree-3 polynomial on the FMA pipe
+template <int MODE>
+__global__ void __launch_bounds__(512) k(long long* clk, float* sink, int reps, float seed) {
+  extern __shared__ uint8_t smem[];
+  const int r = threadIdx.x & 127;
+  uint8_t* sP = smem + (threadIdx.x >> 7) * 16384;
+  float v[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = seed * (float)((threadIdx.x * 7 + i * 13) & 255) - 3.f;
+  const float c = 0.18f, mx = 1.5f;
+  const uint64_t c2 = pk2(c, c), nm2 = pk2(-mx, -mx);
+  uint64_t s0 = pk2(0.f, 0.f), s1 = s0;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = -1e30f, a5 = -1e30f, a6 = -1e30f, a7 = -1e30f;
+  __syncthreads();
+  const long long t0 = clock64();
+  for (int rep = 0; rep < reps; ++rep) {
+    const float rf = (float)rep * 1e-6f;
+    if (MODE <= 3 || MODE == 8) {
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        uint32_t pk[8];
+#pragma unroll
+        for (int e = 0; e < 16; e += 4) {
+          float x0, x1, x2, x3;
+          if (MODE == 1) {
+            x0 = fmaf(v[hf * 16 + e] + rf, c, -mx); x1 = fmaf(v[hf * 16 + e + 1] + rf, c, -mx);
+            x2 = fmaf(v[hf * 16 + e + 2] + rf, c, -mx); x3 = fmaf(v[hf * 16 + e + 3] + rf, c, -mx);
+          } else {
+            upk2(ffma2(pk2(v[hf * 16 + e] + rf, v[hf * 16 + e + 1]), c2, nm2), x0, x1);
+            upk2(ffma2(pk2(v[hf * 16 + e + 2] + rf, v[hf * 16 + e + 3]), c2, nm2), x2, x3);
+          }
+          if (MODE == 8) {
+            // x2, x3 on the FMA pipe: 2^x = 2^n * p(f), n = round(x), f = x - n in [-0.5, 0.5], degree-3 minimax
+            x0 = ex2(x0); x1 = ex2(x1);
+            const uint64_t mg = pk2(12582912.f, 12582912.f);
+            const uint64_t xx = pk2(fmaxf(x2, -125.f), fmaxf(x3, -125.f));
+            const uint64_t t = fadd2(xx, mg);
+            const uint64_t n = fadd2(t, pk2(-12582912.f, -12582912.f));
+            float n0, n1, f0, f1, t0f, t1f;
+            upk2(n, n0, n1); upk2(t, t0f, t1f);
+            f0 = fmaxf(x2, -125.f) - n0; f1 = fmaxf(x3, -125.f) - n1;
+            uint64_t p = ffma2(pk2(f0, f1), pk2(0.0555041f, 0.0555041f), pk2(0.2402265f, 0.2402265f));
+            p = ffma2(p, pk2(f0, f1), pk2(0.6931472f, 0.6931472f));
+            p = ffma2(p, pk2(f0, f1), pk2(1.f, 1.f));
+            float p0, p1;
+            upk2(p, p0, p1);
+            x2 = __uint_as_float(__float_as_uint(p0) + (__float_as_uint(t0f) << 23));
+            x3 = __uint_as_float(__float_as_uint(p1) + (__float_as_uint(t1f) << 23));
+          } else {
+            x0 = ex2(x0); x1 = ex2(x1); x2 = ex2(x2); x3 = ex2(x3);
+          }
+          if (MODE == 1) { a0 += x0; a1 += x1; a2 += x2; a3 += x3; }
+          else { s0 = fadd2(s0, pk2(x0, x1)); s1 = fadd2(s1, pk2(x2, x3)); }
+          if (MODE != 3) { pk[e >> 1] = pack(x0, x1); pk[(e >> 1) + 1] = pack(x2, x3); }
+        }
+        if (MODE == 0 || MODE == 1 || MODE == 8) {
+          const int j0 = ((rep & 1) * 32 + hf * 16);
+          uint8_t* a = sP + r * 128;
+          const int c8 = (j0 & 63) >> 3;
+          *reinterpret_cast<uint4*>(a + ((c8 ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          *reinterpret_cast<uint4*>(a + (((c8 + 1) ^ (r & 7)) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        } else if (MODE == 2) {
+          a0 += __uint_as_float(pk[0] ^ pk[1] ^ pk[2] ^ pk[3] ^ pk[4] ^ pk[5] ^ pk[6] ^ pk[7]);
+        }
+      }
+    } else if (MODE == 4) {
+#pragma unroll
+      for (int e = 0; e < 32; e += 4) {
+        a0 += ex2(v[e] + rf); a1 += ex2(v[e + 1] + rf); a2 += ex2(v[e + 2] + rf); a3 += ex2(v[e + 3] + rf);
+      }
+    } else if (MODE == 5) {
+#pragma unroll
+      for (int e = 0; e < 32; e += 8) {
+        a4 = fmax3(a4, v[e] + rf, v[e + 1]); a5 = fmax3(a5, v[e + 2] + rf, v[e + 3]);
+        a6 = fmax3(a6, v[e + 4] + rf, v[e + 5]); a7 = fmax3(a7, v[e + 6] + rf, v[e + 7]);
+      }
+    } else if (MODE == 6) {
+#pragma unroll
+      for (int e = 0; e < 32; e += 4) {
+        a4 = fmaxf(a4, v[e] + rf); a5 = fmaxf(a5, v[e + 1] + rf); a6 = fmaxf(a6, v[e + 2] + rf); a7 = fmaxf(a7, v[e + 3] + rf);
+      }
+    } else if (MODE == 7) {
+#pragma unroll
+      for (int e = 0; e < 32; e += 16) {
+        a0 = fmax3(a0, v[e] + rf, v[e + 1]); a1 = fmax3(a1, v[e + 2] + rf, v[e + 3]);
+        a2 = fmax3(a2, v[e + 4] + rf, v[e + 5]); a3 = fmax3(a3, v[e + 6] + rf, v[e + 7]);
+        a4 = fmax3(a4, v[e + 8] + rf, v[e + 9]); a5 = fmax3(a5, v[e + 10] + rf, v[e + 11]);
+        a6 = fmax3(a6, v[e + 12] + rf, v[e + 13]); a7 = fmax3(a7, v[e + 14] + rf, v[e + 15]);
+      }
+    }
+  }
+  __syncthreads();
+  const long long t1 = clock64();
+  if (threadIdx.x == 0) clk[blockIdx.x] = t1 - t0;
+  float q0, q1, q2, q3;
+  upk2(s0, q0, q1); upk2(s1, q2, q3);
+  sink[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7 + q0 + q1 + q2 + q3 + smem[threadIdx.x];
+}
+
+template <int MODE>
+void run(const char* name, long long* clk, float* sink) {
+  long long h[148];
+  const int reps = 2000;
+  cudaFuncSetAttribute(k<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
+  for (int warps : {4, 8, 16}) {
+    for (int it = 0; it < 2; ++it) {
+      k<MODE><<<148, warps * 32, 65536>>>(clk, sink, reps, 0.02f);
+      cudaError_t e = cudaDeviceSynchronize();
+      if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return; }
+    }
+    cudaMemcpy(h, clk, sizeof(h), cudaMemcpyDeviceToHost);
+    printf("%-58s %2d warps: %7.1f clk per 32-score step per warp, %6.2f scores/clk/SM\n", name, warps, (double)h[0] / reps,
+           (double)reps * 32 * warps * 32 / h[0]);
+  }
+}
+
+int main() {
+  long long* clk; float* sink;
+  cudaMalloc(&clk, 148 * 8); cudaMalloc(&sink, 148 * 512 * 4);
+  run<0>("pass 2 packed: FFMA2 + MUFU + FADD2 + F2FP + STS.128", clk, sink);
+  run<1>("pass 2 scalar: FFMA + MUFU + FADD x4 + F2FP + STS.128", clk, sink);
+  run<2>("pass 2 packed, no STS", clk, sink);
+  run<3>("pass 2 packed, no F2FP, no STS", clk, sink);
+  run<4>("MUFU.EX2 + 4 scalar sum chains only", clk, sink);
+  run<8>("pass 2 packed, half the exps as a cubic on the FMA pipe", clk, sink);
+  run<5>("pass 1: FMNMX3, 4 chains", clk, sink);
+  run<6>("pass 1: FMNMX, 4 chains", clk, sink);
+  run<7>("pass 1: FMNMX3, 8 chains", clk, sink);
+  return 0;
+}

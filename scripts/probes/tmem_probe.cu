@@ -102,6 +102,7 @@ __global__ void alu_kernel(long long* clk, float* sink, int reps, float seed) {
   __syncthreads();
   const long long t0 = clock64();
   for (int r = 0; r < reps; ++r) {
+    const float rf = (float)r * 1e-7f;   // rep-dependent input: identical asm statements would otherwise be merged
     if (MODE == 0) {   // ex2 + serial sum
 #pragma unroll
       for (int i = 0; i < 32; ++i) { float e; asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x[i] - s0 * 1e-30f)); s0 += e; }
@@ -109,10 +110,10 @@ __global__ void alu_kernel(long long* clk, float* sink, int reps, float seed) {
 #pragma unroll
       for (int i = 0; i < 32; i += 4) {
         float e0, e1, e2, e3;
-        asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(x[i]));
-        asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(x[i + 1]));
-        asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(e2) : "f"(x[i + 2]));
-        asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(e3) : "f"(x[i + 3]));
+        asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(x[i] + rf));
+        asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(x[i + 1] + rf));
+        asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(e2) : "f"(x[i + 2] + rf));
+        asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(e3) : "f"(x[i + 3] + rf));
         s0 += e0; s1 += e1; s2 += e2; s3 += e3;
       }
     } else if (MODE == 2) {   // serial max chain
@@ -130,6 +131,40 @@ __global__ void alu_kernel(long long* clk, float* sink, int reps, float seed) {
   const long long t1 = clock64();
   if (threadIdx.x == 0) clk[blockIdx.x] = t1 - t0;
   sink[blockIdx.x * blockDim.x + threadIdx.x] = s0 + s1 + s2 + s3;
+}
+
+// FFMA vs FFMA2 issue rate: 8 independent accumulator chains per thread
+template <int MODE>
+__global__ void fma_kernel(long long* clk, float* sink, int reps, float seed) {
+  float a[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) a[i] = seed * (threadIdx.x + i);
+  const float b = 1.0001f, c = 0.5f;
+  __syncthreads();
+  const long long t0 = clock64();
+  for (int r = 0; r < reps; ++r) {
+    if (MODE == 0) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) a[i] = fmaf(a[i], b, c);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; i += 2) {
+        unsigned long long p, q, w, o;
+        asm("mov.b64 %0, {%1, %2};" : "=l"(p) : "f"(a[i]), "f"(a[i + 1]));
+        asm("mov.b64 %0, {%1, %2};" : "=l"(q) : "f"(b), "f"(b));
+        asm("mov.b64 %0, {%1, %2};" : "=l"(w) : "f"(c), "f"(c));
+        asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(o) : "l"(p), "l"(q), "l"(w));
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(a[i]), "=f"(a[i + 1]) : "l"(o));
+      }
+    }
+  }
+  __syncthreads();
+  const long long t1 = clock64();
+  if (threadIdx.x == 0) clk[blockIdx.x] = t1 - t0;
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += a[i];
+  sink[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
 int main() {
@@ -165,6 +200,18 @@ int main() {
       cudaMemcpy(h, clk, sizeof(h), cudaMemcpyDeviceToHost);
       const double n = 1000.0 * 32 * warps * 32;
       printf("%-24s %2d warps: %8lld clk -> %6.2f elem/clk/SM\n", an[mode], warps, h[0], n / h[0]);
+    }
+  for (int mode = 0; mode < 2; ++mode)
+    for (int warps : {4, 8, 16}) {
+      for (int it = 0; it < 2; ++it) {
+        if (mode == 0) fma_kernel<0><<<148, warps * 32>>>(clk, (float*)sink, 2000, 0.001f);
+        if (mode == 1) fma_kernel<1><<<148, warps * 32>>>(clk, (float*)sink, 2000, 0.001f);
+        cudaDeviceSynchronize();
+      }
+      cudaMemcpy(h, clk, sizeof(h), cudaMemcpyDeviceToHost);
+      const double n = 2000.0 * 16 * warps * 32;
+      printf("%-24s %2d warps: %8lld clk -> %6.1f fma/clk/SM\n", mode == 0 ? "FFMA, 16 chains" : "FFMA2, 8 packed chains", warps, h[0],
+             n / h[0]);
     }
   return 0;
 }
