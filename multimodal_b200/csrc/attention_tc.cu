@@ -1234,7 +1234,8 @@ __device__ __forceinline__ uint64_t desc_mn_a(uint32_t saddr) { return make_smem
 template <bool CAUSAL, int NSTAT>
 __global__ void __launch_bounds__((8 + 3 + NSTAT) * 32, 1)
 attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_constant__ CUtensorMap tmQKV64,
-                      const __grid_constant__ CUtensorMap tmDO64, const AttnTcArgs p, const int n_work) {
+                      const __grid_constant__ CUtensorMap tmDO64, const __grid_constant__ CUtensorMap tmDQKV,
+                      const AttnTcArgs p, const int n_work) {
   constexpr int RING = 3;
   constexpr int CH = 8192;  // one 64-row x 128 B chunk operand
   constexpr int P_WORKERS = 8;
@@ -1268,7 +1269,7 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
   const int nc = (S_pad + 63) >> 6;      // query chunks (<= 4)
   const int ntile = (S + 127) >> 7;      // key tiles (<= 2)
   if (threadIdx.x == 0) {
-    tma_prefetch_desc(&tmQKV128); tma_prefetch_desc(&tmQKV64); tma_prefetch_desc(&tmDO64);
+    tma_prefetch_desc(&tmQKV128); tma_prefetch_desc(&tmQKV64); tma_prefetch_desc(&tmDO64); tma_prefetch_desc(&tmDQKV);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tile_full[i], 1); mbar_init(&tile_empty[i], 2);
       mbar_init(&sdp_full[i], 1); mbar_init(&sdp_empty[i], P_WORKERS);
@@ -1386,24 +1387,24 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
             if (p.trace && blockIdx.x < 4 && g < 24) p.trace[(blockIdx.x * 12 + 10) * 64 + 2 * g] = clock64();
             const uint32_t ub = uRing + st * 2 * CH;
             const int ks = wc >> 4;
-            for (int k = 0; k < ks; ++k)
-              umma_bf16(tmem + 256, desc_k(uPT + sb * ATOM + k * 32), desc_mn(ub + CH + k * 2048), id, (c > 0 || k > 0));
-            for (int k = 0; k < ks; ++k)
-              umma_bf16(tmem + 320, desc_k(uDS + c * ATOM + k * 32), desc_mn(ub + k * 2048), id, (c > 0 || k > 0));
+            {   // descriptor bases once per chunk; a 16-key / 16-query step advances the start address by 32 B (K-major)
+                // or 2048 B (MN-major) = +2 / +128 in the descriptor's (address >> 4) field
+              const uint64_t aPT = desc_k(uPT + sb * ATOM), bDO = desc_mn(ub + CH);
+              const uint64_t aDS = desc_k(uDS + c * ATOM), bQ = desc_mn(ub);
+              for (int k = 0; k < ks; ++k) umma_bf16(tmem + 256, aPT + 2 * k, bDO + 128 * k, id, (c > 0 || k > 0));
+              for (int k = 0; k < ks; ++k) umma_bf16(tmem + 320, aDS + 2 * k, bQ + 128 * k, id, (c > 0 || k > 0));
+            }
             umma_commit(&pt_empty[sb]);
             umma_commit(&ring_empty[st]);
+            if (c == nc - 1) umma_commit(&acc_full[0]);   // dV / dK of the key tile are final: before the dQ MMAs below
             if ((c & 1) || c == nc - 1) {   // the pair (2q, 2q+1) of dS^T chunks is complete: dQ block q += dS K_j
               const int q = c >> 1;
-              for (int k = 0; k < kk; ++k)
-                umma_bf16(tmem + 384 + q * 64, desc_mn_a(uDS + 2 * q * ATOM + k * 2048), desc_mn(uK + k * 2048), idq,
-                          (j > 0 || k > 0));
+              const uint64_t aQ = desc_mn_a(uDS + 2 * q * ATOM), bK = desc_mn(uK);
+              for (int k = 0; k < kk; ++k) umma_bf16(tmem + 384 + q * 64, aQ + 128 * k, bK + 128 * k, idq, (j > 0 || k > 0));
               umma_commit(&dsb_empty[2 * q]);
               if (2 * q + 1 < nc) umma_commit(&dsb_empty[2 * q + 1]);
             }
-            if (c == nc - 1) {
-              umma_commit(&acc_full[0]);
-              umma_commit(&tile_empty[tb]);   // 2 of 2 arrivals: K_j / V_j may be overwritten
-            }
+            if (c == nc - 1) umma_commit(&tile_empty[tb]);   // 2 of 2 arrivals: K_j / V_j may be overwritten
             if (p.trace && blockIdx.x < 4 && g < 24) p.trace[(blockIdx.x * 12 + 10) * 64 + 2 * g + 1] = clock64();
           }
         }
@@ -1448,6 +1449,31 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
     const long long ld = 3LL * d;
     int n = 0, nt = 0;
     int g = 0;
+    // Output tiles (dV, dK per key tile; dQ per work item) leave through smem + ONE TMA store each (3-D box clipped at the
+    // sequence length) instead of one 64 B piece of a row per thread (32 L1 wavefronts per st.global.v4: 2-3.8 k clocks
+    // per epilogue in the phase trace).  Staging reuses operand buffers that are dead at that point: P^T[0|1] for dV | dK
+    // (acc_full: every MMA of the tile has completed), dS^T[0|1] for the dQ blocks (dq_full).  Before the workers write
+    // those buffers again the elected thread waits for the bulk stores to have read them (store_sync).
+    bool store_pending = false;
+    auto store_sync = [&]() {
+      if (store_pending) {
+        if (warp == 0 && elect_one()) tma_store_wait_read<0>();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        store_pending = false;
+      }
+    };
+    auto stage32 = [&](uint8_t* buf, const uint32_t (&v)[32]) {   // this thread's 32 fp32 -> 64 B of row r, swizzled
+      uint8_t* a = buf + r * 128;
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        uint4 o;
+        o.x = pack_bf16x2(__uint_as_float(v[jj * 8 + 0]), __uint_as_float(v[jj * 8 + 1]));
+        o.y = pack_bf16x2(__uint_as_float(v[jj * 8 + 2]), __uint_as_float(v[jj * 8 + 3]));
+        o.z = pack_bf16x2(__uint_as_float(v[jj * 8 + 4]), __uint_as_float(v[jj * 8 + 5]));
+        o.w = pack_bf16x2(__uint_as_float(v[jj * 8 + 6]), __uint_as_float(v[jj * 8 + 7]));
+        *reinterpret_cast<uint4*>(a + (((grp * 4 + jj) ^ (r & 7)) << 4)) = o;
+      }
+    };
     const bool tr = p.trace != nullptr && blockIdx.x < 4 && lane == 0;
     unsigned long long* trw = p.trace + (blockIdx.x * 12 + warp) * 64;
     long long tq = tr ? clock64() : 0, a_stat = 0, a_sdp = 0, a_ld = 0, a_buf = 0, a_cmp = 0, a_accw = 0, a_epi = 0, a_dqw = 0,
@@ -1479,6 +1505,7 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
           BT(a_ld);
           mbar_wait(&pt_empty[sb], (uint32_t)(((g >> 1) & 1) ^ 1));   // dV / dK MMAs of chunk g-2 have left P^T[sb]
           mbar_wait(&dsb_empty[c], (uint32_t)((nt & 1) ^ 1));          // the previous key tile's dQ MMA has left dS^T[c]
+          store_sync();                                                // ... and the last epilogue's bulk stores the staging
           BT(a_buf);
           uint8_t* myDS = sDS + c * ATOM;
           uint8_t* myPT = sPT + sb * ATOM;
@@ -1554,22 +1581,18 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&acc_empty[0]);
-        if (ri < S) {
-#pragma unroll
-          for (int which = 0; which < 2; ++which) {
-            const uint32_t* v = which == 0 ? v0 : v1;
-            __nv_bfloat16* dst = p.dqkv + (long long)(row0 + ri) * ld + (which == 0 ? 2 * d : d) + h * 64 + grp * 32;
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj) {
-              uint4 o;
-              o.x = pack_bf16x2(__uint_as_float(v[jj * 8 + 0]), __uint_as_float(v[jj * 8 + 1]));
-              o.y = pack_bf16x2(__uint_as_float(v[jj * 8 + 2]), __uint_as_float(v[jj * 8 + 3]));
-              o.z = pack_bf16x2(__uint_as_float(v[jj * 8 + 4]), __uint_as_float(v[jj * 8 + 5]));
-              o.w = pack_bf16x2(__uint_as_float(v[jj * 8 + 6]), __uint_as_float(v[jj * 8 + 7]));
-              reinterpret_cast<uint4*>(dst)[jj] = o;
-            }
-          }
+        store_sync();
+        stage32(sPT, v0);
+        stage32(sPT + ATOM, v1);
+        fence_proxy_async_smem();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (warp == 0 && elect_one()) {
+          tma_store_3d(&tmDQKV, sPT, 2 * d + h * 64, j * 128, b);          // dV rows of key tile j (V block of dqkv)
+          tma_store_3d(&tmDQKV, sPT + ATOM, d + h * 64, j * 128, b);       // dK rows (K block)
+          tma_store_commit();
         }
+        store_pending = true;
+        if (tr) trw[10] += clock64() - tq;   // first-tile epilogues (the per-item BT(a_epi) only sees the last one)
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&stat_empty[n & 1]);   // this warp no longer reads sLD[n & 1]
@@ -1586,26 +1609,21 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&dq_empty[0]);
-#pragma unroll
-        for (int blk = 0; blk < 2; ++blk) {
-          const int qi = blk * 128 + r;
-          if (blk * 2 < nc && qi < S) {
-            const uint32_t* v = blk == 0 ? v0 : v1;
-            __nv_bfloat16* dst = p.dqkv + (long long)(row0 + qi) * ld + h * 64 + grp * 32;
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj) {
-              uint4 o;
-              o.x = pack_bf16x2(__uint_as_float(v[jj * 8 + 0]), __uint_as_float(v[jj * 8 + 1]));
-              o.y = pack_bf16x2(__uint_as_float(v[jj * 8 + 2]), __uint_as_float(v[jj * 8 + 3]));
-              o.z = pack_bf16x2(__uint_as_float(v[jj * 8 + 4]), __uint_as_float(v[jj * 8 + 5]));
-              o.w = pack_bf16x2(__uint_as_float(v[jj * 8 + 6]), __uint_as_float(v[jj * 8 + 7]));
-              reinterpret_cast<uint4*>(dst)[jj] = o;
-            }
-          }
+        store_sync();
+        stage32(sDS, v0);
+        if (nc > 2) stage32(sDS + ATOM, v1);
+        fence_proxy_async_smem();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (warp == 0 && elect_one()) {
+          tma_store_3d(&tmDQKV, sDS, h * 64, 0, b);                        // dQ, queries 0 .. 127 (Q block of dqkv)
+          if (nc > 2) tma_store_3d(&tmDQKV, sDS + ATOM, h * 64, 128, b);   // queries 128 ..
+          tma_store_commit();
         }
+        store_pending = true;
       }
       BT(a_dqe);
     }
+    if (warp == 0 && elect_one()) tma_store_wait_all<0>();   // smem must outlive the last bulk stores' reads
     if (tr) {
       trw[0] = a_stat; trw[1] = a_sdp; trw[2] = a_ld; trw[3] = a_buf; trw[4] = a_cmp; trw[5] = a_accw; trw[6] = a_epi;
       trw[7] = a_dqw; trw[8] = a_dqe; trw[9] = n;
@@ -2189,9 +2207,12 @@ extern "C" int mmb_attention_bwd_tc(const void* qkv, const void* out, const void
       const char* e = getenv("MMB_ATTN_FUSED_STATS");
       nstat = (e && e[0] == '2') ? 2 : 1;
     }
+    CUtensorMap tmDQKV;   // [B][S][3d] view of dqkv: the per-tile store boxes are clipped at S
+    rc = make_tmap_3d_bf16(&tmDQKV, dqkv, 3ull * d, (uint64_t)S, (uint64_t)B, 3ull * d * 2, (uint64_t)S * 3 * d * 2, 64, 128);
+    if (rc) return rc;
 #define LAUNCH_BWDF(C, NS)                                                                                       \
     cudaFuncSetAttribute(attn_bwd_fused_kernel<C, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWDF_SMEM); \
-    attn_bwd_fused_kernel<C, NS><<<grid_f, (8 + 3 + NS) * 32, BWDF_SMEM, st>>>(q128, q64, o64, a, n_items);
+    attn_bwd_fused_kernel<C, NS><<<grid_f, (8 + 3 + NS) * 32, BWDF_SMEM, st>>>(q128, q64, o64, tmDQKV, a, n_items);
     if (causal) { if (nstat == 2) { LAUNCH_BWDF(true, 2) } else { LAUNCH_BWDF(true, 1) } }
     else        { if (nstat == 2) { LAUNCH_BWDF(false, 2) } else { LAUNCH_BWDF(false, 1) } }
 #undef LAUNCH_BWDF

@@ -36,7 +36,7 @@ for cta in range(2):
         a = t[cta, w]
         n = max(1, int(a[9]))
         print(f"  worker {w}: items {int(a[9])}  per item: " + " | ".join(f"{nm} {int(a[i]) // n}" for i, nm in enumerate(names)) +
-              f" | sum {sum(int(a[i]) for i in range(9)) // n}")
+              f" | first-tile epi {int(a[10]) // n} | sum {sum(int(a[i]) for i in range(9)) // n}")
     base = int(t[cta, 0, 16])
     st = [(int(t[cta, 0, 16 + 2 * i]) - base, int(t[cta, 0, 17 + 2 * i]) - base) for i in range(20)]
     print(f"  worker 0: (S/dP ready, dS done) of chunks 0-19, clocks: {st}")
