@@ -629,8 +629,10 @@ attn_fwd_item_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_con
         mbar_wait(v_full, par);
         tc_fence_after();
         if (TRACE && blockIdx.x < 4 && it < 24) trace[(blockIdx.x * 12 + warp) * 64 + 2 * it + 1] = clock64();
-        for (int j = 0; j < nk; ++j)
-          umma_bf16(tacc, desc_k(uP + (j >> 2) * ATOM + (j & 3) * 32), desc_mn(uV + j * 2048), id_o, j > 0);
+        {   // descriptor bases once; per 16-key step: P advances 32 B inside an atom (+2), 16 KB per atom (+1024); V 2048 B (+128)
+          const uint64_t aP = desc_k(uP), bV = desc_mn(uV);
+          for (int j = 0; j < nk; ++j) umma_bf16(tacc, aP + (uint64_t)((j >> 2) * (ATOM >> 4) + (j & 3) * 2), bV + 128 * j, id_o, j > 0);
+        }
         umma_commit(&o_full[t]);
         umma_commit(v_empty);
       }

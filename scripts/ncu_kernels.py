@@ -48,7 +48,7 @@ def once():
     ops.gemm(dpre, x, a_mn=True, b_mn=True, epilogue=ops.EPI_F32, out=dw1, splits=ops.wgrad_splits(ff, d, M),
              accumulate=True)                                                                   # 4 FC1 wgrad (split-K)
     ops.attention_fwd(qkv, o, lse, B, S, H, False, 0.125)                                       # 5 attn fwd
-    ops.attention_bwd(qkv, o, gb, lse, dqkv, B, S, H, False, 0.125)                             # 6,7 attn bwd dQ, dK/dV
+    ops.attention_bwd(qkv, o, gb, lse, dqkv, B, S, H, False, 0.125)                             # 6 attn bwd (fused: one kernel)
     ops.add_layernorm_fwd(xs, gb, xo, ln, None, g, bta, mean, rstd, M, d, 1e-5)                 # 8 add + LayerNorm fwd
     ops.layernorm_bwd(xo, gb, None, mean, rstd, g, G, G, Gb, dg, db, M, d, gsum=gs)             # 9 LayerNorm bwd
 

@@ -1,6 +1,6 @@
 """Aggregates the ncu source page (per-instruction stall samples) of one kernel into segments that end at a
 synchronisation landmark (mbarrier try_wait / arrive, tcgen05.ld, tcgen05.commit, BAR): shows where the warps of a
-warp-specialised kernel spend their time.   python scripts/ncu_segments.py <report.ncu-rep> <kernel regex> [min %]"""
+warp-specialised kernel spend their time.   python scripts/ncu_segments.py <report.ncu-rep> <kernel regex> [min %] [n-th matching launch]"""
 import csv
 import subprocess
 import sys
@@ -10,6 +10,13 @@ minp = float(sys.argv[3]) if len(sys.argv) > 3 else 0.4
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", f"regex:{rx}"], capture_output=True,
                      text=True).stdout
 rows = list(csv.reader(out.splitlines()))
+starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"]   # one block per matching launch
+nth = int(sys.argv[4]) if len(sys.argv) > 4 else 0
+if len(starts) >= 2 and all(rows[starts[i]] == rows[starts[i + 1]] for i in range(0, len(starts) - 1, 2)):
+    starts = starts[::2] + [len(rows)]   # ncu prints every launch twice (SASS view, source view): keep the first
+    rows_end = {starts[i]: starts[i + 1] for i in range(len(starts) - 1)}
+rows = rows[starts[nth]:(starts[nth + 1] if nth + 1 < len(starts) else len(rows))]
+print(rows[0][1][:110])
 hi = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
 h = rows[hi]
 ia, isrc, isamp, iex = h.index("Address"), h.index("Source"), h.index("# Samples"), h.index("Instructions Executed")

@@ -39,8 +39,27 @@ def scale(metric, v):
     return v * mult[u] if u in mult else v
 
 
-NAMES = ["gemm_qkv_fwd", "gemm_fc1_act", "gemm_fc2_dgrad_dact", "gemm_fc1_wgrad", "attn_fwd", "attn_bwd_dq", "attn_bwd_dkdv",
-         "add_ln_fwd", "ln_bwd"]
+GEMM_ORDER = ["gemm_qkv_fwd", "gemm_fc1_act", "gemm_fc2_dgrad_dact", "gemm_fc1_wgrad"]   # launch order in ncu_kernels.py
+
+
+def key_of(kname, seen):
+    """Stable key from the kernel name (the backward is one fused kernel or a dQ + dK/dV pair, depending on the build)."""
+    if "gemm_kernel" in kname:
+        k = GEMM_ORDER[seen["gemm"]] if seen["gemm"] < len(GEMM_ORDER) else f"gemm{seen['gemm']}"
+        seen["gemm"] += 1
+        return k
+    if "attn_fwd" in kname:
+        return "attn_fwd"
+    if "attn_bwd_fused" in kname:
+        return "attn_bwd_fused"
+    if "attn_bwd" in kname:
+        seen["bwd"] += 1
+        return "attn_bwd_dq" if seen["bwd"] == 1 else "attn_bwd_dkdv"
+    if "add_ln_fwd" in kname:
+        return "add_ln_fwd"
+    if "ln_bwd" in kname:
+        return "ln_bwd"
+    return None
 M, d, ff, B, S, H = 201728, 768, 3072, 1024, 197, 12
 ALGO = {  # algorithmic bytes / flops of the launch
     "gemm_qkv_fwd": (M * d * 2 + 3 * d * d * 2 + M * 3 * d * 2, 2.0 * M * 3 * d * d),
@@ -50,6 +69,7 @@ ALGO = {  # algorithmic bytes / flops of the launch
     "attn_fwd": (M * 3 * d * 2 + M * d * 2, 4.0 * S * S * 64 * H * B),
     "attn_bwd_dq": (M * 3 * d * 2 + 2 * M * d * 2 + M * d * 2, 4.0 * S * S * 64 * H * B * 1.5),
     "attn_bwd_dkdv": (M * 3 * d * 2 + M * d * 2 + 2 * M * d * 2, 4.0 * S * S * 64 * H * B * 2.0),
+    "attn_bwd_fused": (M * 3 * d * 2 + 2 * M * d * 2 + M * 3 * d * 2, 4.0 * S * S * 64 * H * B * 2.5),
     "add_ln_fwd": (M * d * 12, 0.0),
     "ln_bwd": (M * d * 16, 0.0),
 }
@@ -57,8 +77,9 @@ out = {"source": f"profiles/{tag}_ncu_kernels.csv (ncu --set full --clock-contro
        "kernels": {}}
 lines = [["launch", "kernel"] + have + ["algorithmic_bytes", "algorithmic_flops", "dram_GBps", "TFLOPs"]]
 kcol = col.get("Kernel Name")
+seen = {"gemm": 0, "bwd": 0}
 for i, r in enumerate(data):
-    name = NAMES[i] if i < len(NAMES) else f"launch{i}"
+    name = key_of(r[kcol], seen) or f"launch{i}"
     vals = {m: scale(m, num(r[col[m]])) for m in have}
     ab, af = ALGO.get(name, (None, None))
     t = vals.get("gpu__time_duration.sum")
