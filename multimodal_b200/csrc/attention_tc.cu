@@ -1497,42 +1497,9 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
           tc_fence_after();
           BT(a_sdp);
           if (tr && g < 24) trw[16 + 2 * g] = tq;
-          // Phase A (while the dP^T load is in flight and before any buffer wait): p = 2^(s c - L) in place over the S^T
-          // registers — the MUFU-bound part of the chunk.  Phase B: dS = p (dP scale - D scale), bf16 P^T / dS^T stores.
           uint32_t sv[32], dv[32];
           tmem_ld32(trow + sb * 128 + grp * 32, sv);
-          tmem_ld_wait();
           tmem_ld32(trow + sb * 128 + 64 + grp * 32, dv);
-          const int cbase = c * 64 + grp * 32;
-          const bool full = (ri < S) && (cbase + 32 <= S) && (!CAUSAL || ri <= cbase);
-          const uint64_t c2 = pk2(p.scale_log2, p.scale_log2), sc2 = pk2(p.scale, p.scale);
-          if (ri < S) {
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-              if (grp * 32 + half * 16 >= wc) continue;   // columns past S_pad (last chunk): nothing reads them (uniform)
-              if (full) {
-                const float4* pl = reinterpret_cast<const float4*>(sL + cbase + half * 16);   // -L (log2 units)
-#pragma unroll
-                for (int e4 = 0; e4 < 4; ++e4) {
-                  const float4 l4 = pl[e4];
-                  const int e = half * 16 + e4 * 4;
-                  float x0, x1, x2, x3;
-                  upk2(ffma2(pk2(__uint_as_float(sv[e]), __uint_as_float(sv[e + 1])), c2, pk2(l4.x, l4.y)), x0, x1);
-                  upk2(ffma2(pk2(__uint_as_float(sv[e + 2]), __uint_as_float(sv[e + 3])), c2, pk2(l4.z, l4.w)), x2, x3);
-                  sv[e] = __float_as_uint(ex2_approx(x0)); sv[e + 1] = __float_as_uint(ex2_approx(x1));
-                  sv[e + 2] = __float_as_uint(ex2_approx(x2)); sv[e + 3] = __float_as_uint(ex2_approx(x3));
-                }
-              } else {
-#pragma unroll
-                for (int e = 0; e < 16; ++e) {
-                  const int cj = cbase + half * 16 + e;
-                  const bool valid = (cj < S) && (!CAUSAL || ri <= cj);
-                  const float pv = valid ? ex2_approx(fmaf(__uint_as_float(sv[half * 16 + e]), p.scale_log2, sL[cj & 255])) : 0.f;
-                  sv[half * 16 + e] = __float_as_uint(pv);
-                }
-              }
-            }
-          }
           tmem_ld_wait();
           tc_fence_before();
           __syncwarp();
@@ -1544,9 +1511,12 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
           BT(a_buf);
           uint8_t* myDS = sDS + c * ATOM;
           uint8_t* myPT = sPT + sb * ATOM;
+          const int cbase = c * 64 + grp * 32;
+          const bool full = (ri < S) && (cbase + 32 <= S) && (!CAUSAL || ri <= cbase);
+          const uint64_t c2 = pk2(p.scale_log2, p.scale_log2), sc2 = pk2(p.scale, p.scale);
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
-            if (grp * 32 + half * 16 >= wc) continue;
+            if (grp * 32 + half * 16 >= wc) continue;   // columns past S_pad (last chunk): nothing reads them (uniform)
             uint8_t* aDS = myDS + ((grp * 32 + half * 16) >> 6) * ATOM + r * 128;
             uint8_t* aPT = myPT + ((grp * 32 + half * 16) >> 6) * ATOM + r * 128;
             const int c8 = ((grp * 32 + half * 16) & 63) >> 3;
@@ -1557,15 +1527,18 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
               *reinterpret_cast<uint4*>(aPT + o0) = make_uint4(0, 0, 0, 0);
               *reinterpret_cast<uint4*>(aPT + o1) = make_uint4(0, 0, 0, 0);
             } else if (full) {
-              const float4* pd = reinterpret_cast<const float4*>(sD + cbase + half * 16);   // -D * scale
+              // packed f32x2 math: p = 2^(s c - L), dS = p (dP scale - D scale); sL / sD hold -L and -D scale
+              const float4* pl = reinterpret_cast<const float4*>(sL + cbase + half * 16);
+              const float4* pd = reinterpret_cast<const float4*>(sD + cbase + half * 16);
               uint32_t kp[8], kd[8];
 #pragma unroll
               for (int e4 = 0; e4 < 4; ++e4) {
-                const float4 d4 = pd[e4];
+                const float4 l4 = pl[e4], d4 = pd[e4];
                 const int e = half * 16 + e4 * 4;
-                const float x0 = __uint_as_float(sv[e]), x1 = __uint_as_float(sv[e + 1]), x2 = __uint_as_float(sv[e + 2]),
-                            x3 = __uint_as_float(sv[e + 3]);
-                float g0, g1, g2, g3;
+                float x0, x1, x2, x3, g0, g1, g2, g3;
+                upk2(ffma2(pk2(__uint_as_float(sv[e]), __uint_as_float(sv[e + 1])), c2, pk2(l4.x, l4.y)), x0, x1);
+                upk2(ffma2(pk2(__uint_as_float(sv[e + 2]), __uint_as_float(sv[e + 3])), c2, pk2(l4.z, l4.w)), x2, x3);
+                x0 = ex2_approx(x0); x1 = ex2_approx(x1); x2 = ex2_approx(x2); x3 = ex2_approx(x3);
                 const uint64_t t01 = ffma2(pk2(__uint_as_float(dv[e]), __uint_as_float(dv[e + 1])), sc2, pk2(d4.x, d4.y));
                 const uint64_t t23 = ffma2(pk2(__uint_as_float(dv[e + 2]), __uint_as_float(dv[e + 3])), sc2, pk2(d4.z, d4.w));
                 upk2(fmul2(pk2(x0, x1), t01), g0, g1);
@@ -1582,9 +1555,11 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
 #pragma unroll
               for (int e = 0; e < 16; ++e) {
                 const int cj = cbase + half * 16 + e;
-                const float pv = __uint_as_float(sv[half * 16 + e]);   // 0 where masked
+                const bool valid = (cj < S) && (!CAUSAL || ri <= cj);
+                const float nL = sL[cj & 255], nDs = sD[cj & 255];
+                const float pv = valid ? ex2_approx(fmaf(__uint_as_float(sv[half * 16 + e]), p.scale_log2, nL)) : 0.f;
                 pt[e] = pv;
-                ds[e] = pv * fmaf(__uint_as_float(dv[half * 16 + e]), p.scale, sD[cj & 255]);
+                ds[e] = pv * fmaf(__uint_as_float(dv[half * 16 + e]), p.scale, nDs);
               }
               store_p16(myDS, r, grp * 32 + half * 16, ds);
               store_p16(myPT, r, grp * 32 + half * 16, pt);
