@@ -506,39 +506,13 @@ constexpr int FPP_SMEM = 1024 + 2 * FPP_BUF + 512 + 256;
 //   * two softmax groups of four warps, thread == query row: pass 1 row maximum with 3-input max on four independent
 //     chains, pass 2 packed f32x2 scale/subtract and row sums (FFMA2 / FADD2), ex2, bf16 P into its own swizzled smem
 //     operand (2 x 64 KB), tcgen05.ld of chunk c+1 in flight while chunk c is processed.
-// Measured floors on this part (scripts/probes/tmem_probe.cu): tcgen05.ld 345 B/clk/SM with 8 warps (one 128x256 fp32
-// block in 380 clk), MUFU.EX2 ~62 /clk/SM, so neither TMEM reads nor exp bound the softmax: instruction issue does
-// (the round-1 tile kernel spends 8.7 warp-instructions per score element at 33 % issue utilisation).
+// Measured floors on this part (scripts/probes/{tmem,softmax}_probe.cu): tcgen05.ld 345 B/clk/SM with 8 warps (one
+// 128x256 fp32 block in 380 clk); MUFU.EX2 16 / clk / SM, so the exp pass is MUFU-bound at 15 scores / clk / SM (>= 3.3 k
+// clocks per work item) and everything else — max pass, MMA waits, epilogue — has to hide under the other tile's exp pass
+// (the round-1 tile kernel spent 8.7 warp-instructions per score element at 33 % issue utilisation).
 // smem: Q 32 KB | K 32 KB | V 32 KB | P_0 64 KB | P_1 64 KB = 224 KB.  TMEM: S_t at columns [256 t, 256 t + S_pad), O_t
 // reuses [256 t, 256 t + 64) once the softmax has consumed S_t.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint64_t pk2(float a, float b) {
-  uint64_t r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
-  return r;
-}
-__device__ __forceinline__ void upk2(uint64_t r, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(r)); }
-__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
-  uint64_t r;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-  return r;
-}
-__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
-  uint64_t r;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-  return r;
-}
-__device__ __forceinline__ uint64_t fmul2(uint64_t a, uint64_t b) {
-  uint64_t r;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-  return r;
-}
-__device__ __forceinline__ float fmax3(float a, float b, float c) {
-  float r;
-  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
-  return r;
-}
-
 constexpr int FIT_THREADS = 12 * 32;   // 8 softmax warps + producer + 2 MMA issuers + 1 idle (registers: per 4 warps)
 constexpr int FIT_SMEM = 1024 + 14 * ATOM + 256;
 template <bool TRACE>

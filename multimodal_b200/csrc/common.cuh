@@ -284,6 +284,35 @@ __device__ __forceinline__ float rcp_approx(float x) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// ---- packed fp32 pairs (sm_100: FFMA2 / FADD2 / FMUL2 take one issue slot for two lanes' worth of FMA-pipe work; the
+// FMA-pipe time is unchanged — scripts/probes/tmem_probe.cu: 123 fma/clk/SM either way) and 3-input max (FMNMX3) ----
+__device__ __forceinline__ uint64_t pk2(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void upk2(uint64_t r, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(r)); }
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t fmul2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+
 // branch-free (no IEEE slow paths): the epilogue must keep 8+ independent elements in flight to hide MUFU latency
 __device__ __forceinline__ float fast_sigmoid(float z) {
   return rcp_approx(1.f + ex2_approx(-1.4426950408889634f * z));
@@ -304,6 +333,25 @@ __device__ __forceinline__ float quick_gelu_grad(float x) {
   const float u = 0.851f * x;
   const float t = tanh_approx(u);
   return fmaf(0.5f, fmaf(u, fmaf(-t, t, 1.f), t), 0.5f);
+}
+// Packed versions (two elements per FMA-pipe instruction): same formulas, same tanh.approx per element.
+__device__ __forceinline__ uint64_t tanh2(uint64_t u) {
+  float a, b;
+  upk2(u, a, b);
+  return pk2(tanh_approx(a), tanh_approx(b));
+}
+__device__ __forceinline__ uint64_t quick_gelu2(uint64_t x) {
+  const uint64_t t = tanh2(fmul2(x, pk2(0.851f, 0.851f))), h = fmul2(x, pk2(0.5f, 0.5f));
+  return ffma2(h, t, h);
+}
+__device__ __forceinline__ uint64_t quick_gelu_grad2(uint64_t x) {
+  const uint64_t u = fmul2(x, pk2(0.851f, 0.851f));
+  float t0, t1;
+  upk2(u, t0, t1);
+  t0 = tanh_approx(t0); t1 = tanh_approx(t1);
+  const uint64_t t = pk2(t0, t1);
+  const uint64_t w = ffma2(pk2(-t0, -t1), t, pk2(1.f, 1.f));           // 1 - t^2
+  return ffma2(pk2(0.5f, 0.5f), ffma2(u, w, t), pk2(0.5f, 0.5f));       // 0.5 (1 + t + u (1 - t^2))
 }
 // Exact (erf) GELU, as nn.GELU() in the FLAVA / CoCa MLPs (torchmultimodal/modules/layers/mlp.py:35)
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
