@@ -198,6 +198,9 @@ int mmb_vit_assemble_fwd(const void* patch_out_bf16, const float* cls, const flo
                          const unsigned char* patch_mask, float* x, int B, int S, int d, void* stream);
 /* out[b,:] = bf16(x[b*rows_per_group + row, :]) — `hidden[:, 0]` selects (Pooler, projections; losses/flava.py:92-96). */
 int mmb_gather_rows_cast(const float* x, void* out_bf16, int B, int rows_per_group, int row, int d, void* stream);
+/* out[m,:] = bf16(x[idx[m]*ld : +d]), idx int64 flat row numbers: the boolean-mask select `hidden_states[masked_tokens, :]`
+ * of MaskedPredictionLoss.forward (modules/losses/flava.py:212-215) and `multimodal_masked_sequence[pos_mask]` (:430). */
+int mmb_gather_rows_idx_cast(const float* x, long long ld, const long long* idx, void* out_bf16, int n, int d, void* stream);
 int mmb_tanh_inplace(float* x, long long n, void* stream);
 /* out[b] = cat([cls], a[b], b[b]) along tokens — models/flava/transformer.py:55-58 + model.py:294-297. */
 int mmb_concat_tokens(const float* cls, const float* a, const float* b, float* out, int B, int Sa, int Sb, int d,

@@ -41,6 +41,7 @@ PROTOTYPES = {
     "mmb_bert_embed_ln_fwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, ll, i32, i32, i32, i32, f32, vp]),
     "mmb_vit_assemble_fwd": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]),
     "mmb_gather_rows_cast": (i32, [vp, vp, i32, i32, i32, i32, vp]),
+    "mmb_gather_rows_idx_cast": (i32, [vp, ll, vp, vp, i32, i32, vp]),
     "mmb_tanh_inplace": (i32, [vp, ll, vp]),
     "mmb_concat_tokens": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, vp]),
     "mmb_coca_text_embed_fwd": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]),

@@ -350,6 +350,24 @@ __global__ void __launch_bounds__(256) ce_labels_kernel(const float* __restrict_
   }
 }
 
+// out[m,:] = bf16(x[idx[m]*ld : +d])   (boolean-mask row selects `hidden[masked_tokens, :]` of the FLAVA masked-prediction
+// losses, modules/losses/flava.py:212-215, as a GEMM operand; idx = flat row numbers of the kept tokens)
+__global__ void gather_rows_idx_cast_kernel(const float* __restrict__ x, long long ld, const long long* __restrict__ idx,
+                                            __nv_bfloat16* __restrict__ out, int n, int d) {
+  const int d4 = d >> 2;
+  const long long total = (long long)n * d4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % d4) * 4;
+    const long long m = i / d4;
+    const float4 v = *reinterpret_cast<const float4*>(x + idx[m] * ld + c);
+    uint2 u;
+    u.x = pack_bf16x2(v.x, v.y);
+    u.y = pack_bf16x2(v.z, v.w);
+    *reinterpret_cast<uint2*>(out + m * d + c) = u;
+  }
+}
+
 // out[b,:] = bf16(x[(b*rows_per_group + row)*d : +d])   (select one token per sequence, e.g. CLS, as a GEMM operand)
 __global__ void gather_rows_cast_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int B,
                                         int rows_per_group, int row, int d) {
@@ -954,6 +972,14 @@ extern "C" int mmb_gather_rows_cast(const float* x, void* out_bf16, int B, int r
   if (d & 3) return MMB_ERR_ARG;
   gather_rows_cast_kernel<<<grid_for((long long)B * d / 4, 256), 256, 0, ST(stream)>>>(x, (__nv_bfloat16*)out_bf16, B,
                                                                                      rows_per_group, row, d);
+  return LAUNCH_RC();
+}
+extern "C" int mmb_gather_rows_idx_cast(const float* x, long long ld, const long long* idx, void* out_bf16, int n, int d,
+                                        void* stream) {
+  if ((d & 3) || (ld & 3) || n < 0) return MMB_ERR_ARG;
+  if (n == 0) return MMB_OK;
+  gather_rows_idx_cast_kernel<<<grid_for((long long)n * d / 4, 256), 256, 0, ST(stream)>>>(x, ld, idx,
+                                                                                           (__nv_bfloat16*)out_bf16, n, d);
   return LAUNCH_RC();
 }
 extern "C" int mmb_tanh_inplace(float* x, long long n, void* stream) {

@@ -12,7 +12,7 @@ from torch import nn, Tensor
 
 from ...modules.layers.normalizations import Fp32LayerNorm
 from ...modules.layers.transformer import TransformerOutput
-from ...modules.losses.flava import Pooler
+from ...modules.losses.flava import FLAVAPretrainingLoss, FLAVAPretrainingLossOutput, Pooler
 from .image_encoder import flava_image_encoder
 from .text_encoder import flava_text_encoder
 from .transformer import FLAVATransformerWithoutEmbeddings, TransformerEncoder
@@ -163,6 +163,61 @@ class FLAVAModel(nn.Module):
         return self.mm_encoder._runtime().forward_projected(
             image_embedding, text_embedding, self.image_to_mm_projection, self.text_to_mm_projection,
             want_attn=bool(getattr(self.mm_encoder, "output_attentions", False)))
+
+
+class FLAVAForPreTraining(nn.Module):
+    """torchmultimodal/models/flava/model.py:300-377: FLAVAModel + image codebook + FLAVAPretrainingLoss.
+    `image_codebook` is any module mapping `image_for_codebook` to integer token ids per patch (the reference's
+    DalleVAEEncoder needs the DALL_E package and a download; it is not part of this library)."""
+
+    def __init__(self, model: FLAVAModel, image_codebook: nn.Module, loss: FLAVAPretrainingLoss) -> None:
+        super().__init__()
+        self.model = model
+        self.image_codebook = image_codebook
+        self.loss = loss
+
+    def encode_image(self, image: Tensor, cls_index: int = 0) -> Tensor:
+        return self.model.encode_image(image, projection=True)[1]
+
+    def encode_text(self, text: Tensor, text_mask: Optional[Tensor] = None, cls_index: int = 0) -> Tensor:
+        return self.model.encode_text(text, text_mask, projection=True)[1]
+
+    def forward(self, image: Optional[Tensor] = None, text: Optional[Tensor] = None,
+                image_for_codebook: Optional[Tensor] = None, image_patches_mask: Optional[Tensor] = None,
+                text_masked: Optional[Tensor] = None, required_embedding: Optional[str] = None,
+                skip_unmasked_mm_encoder: bool = True, itm_labels: Optional[Tensor] = None,
+                mlm_labels: Optional[Tensor] = None) -> FLAVAPretrainingLossOutput:
+        image_labels = None
+        if image_for_codebook is not None:
+            image_labels = self.image_codebook(image_for_codebook).flatten(1)
+            image_patches_mask = image_patches_mask.flatten(1).to(torch.bool)
+            image_labels[~image_patches_mask] = -1
+        flava_output: FLAVAOutput = self.model(
+            image=image, text=text, image_patches_mask=image_patches_mask, text_masked=text_masked,
+            required_embedding=required_embedding, skip_unmasked_mm_encoder=skip_unmasked_mm_encoder)
+        return self.loss(
+            image_sequence=flava_output.image.last_hidden_state,
+            text_sequence=flava_output.text.last_hidden_state,
+            image_masked_sequence=flava_output.image_masked.last_hidden_state,
+            text_masked_sequence=flava_output.text_masked.last_hidden_state,
+            multimodal_sequence=(flava_output.multimodal.last_hidden_state if not skip_unmasked_mm_encoder else None),
+            multimodal_masked_sequence=flava_output.multimodal_masked.last_hidden_state,
+            itm_labels=itm_labels, mim_labels=image_labels, mlm_labels=mlm_labels,
+            projected_image_embeddings=flava_output.projected_image_embeddings,
+            projected_text_embeddings=flava_output.projected_text_embeddings)
+
+
+def flava_model_for_pretraining(image_codebook: Optional[nn.Module] = None, codebook_image_size: int = 112,
+                                pretrained: bool = False, **flava_model_kwargs: Any) -> FLAVAForPreTraining:
+    """models/flava/model.py:524-551.  The reference builds a DalleVAEEncoder codebook (DALL_E package + download);
+    here the caller passes the codebook module (any module producing integer token ids per patch)."""
+    if image_codebook is None:
+        raise NotImplementedError("flava_model_for_pretraining: pass image_codebook=<module>; the reference's "
+                                  "DalleVAEEncoder needs the DALL_E package and a network download")
+    model = flava_model(**flava_model_kwargs)
+    hidden_size = flava_model_kwargs.get("multimodal_hidden_size", 768)
+    losses = FLAVAPretrainingLoss(hidden_size=hidden_size)
+    return FLAVAForPreTraining(model=model, image_codebook=image_codebook, loss=losses)
 
 
 def flava_model(

@@ -387,6 +387,16 @@ def gather_rows_cast(x, out, B, rows_per_group, row, d):
     _lib.check(_lib.lib().mmb_gather_rows_cast(_p(x), _p(out), B, rows_per_group, row, d, _stream()), "mmb_gather_rows_cast")
 
 
+def gather_rows_idx_cast(x, idx, out, d):
+    """out[m, :] = bf16(x2d[idx[m], :]); x fp32 viewed as rows of `d` elements with row pitch x.stride(-2)."""
+    _chk(x, torch.float32, "x"); _chk(idx, torch.int64, "idx"); _chk(out, torch.bfloat16, "out")
+    if x.stride(-1) != 1 or not idx.is_contiguous() or not out.is_contiguous():
+        raise MMBError("gather_rows_idx_cast: expected unit inner stride, contiguous idx / out")
+    _lib.check(_lib.lib().mmb_gather_rows_idx_cast(_p(x), x.stride(-2), _p(idx), _p(out), idx.numel(), d, _stream()),
+               "mmb_gather_rows_idx_cast")
+    return out
+
+
 def tanh_(x):
     _chk(x, torch.float32, "x")
     _lib.check(_lib.lib().mmb_tanh_inplace(_p(x), x.numel(), _stream()), "mmb_tanh_inplace")
