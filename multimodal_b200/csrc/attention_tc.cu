@@ -627,10 +627,6 @@ attn_fwd_item_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_con
     const bool tr = TRACE && blockIdx.x < 4 && lane == 0;
     unsigned long long* trw = trace + (blockIdx.x * 12 + warp) * 64;
     long long tp = tr ? clock64() : 0, acc_ws = 0, acc_p1 = 0, acc_p2 = 0, acc_wo = 0, acc_ep = 0;
-    auto stage_sync = [&]() {   // every thread of the group, exactly once per item
-      if (q4 == 0 && lane == 0) tma_store_wait_read<0>();
-      asm volatile("bar.sync %0, 128;" ::"r"(1 + t) : "memory");
-    };
     for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
       const int h = w % p.H, b = w / p.H;
       const uint32_t par = (uint32_t)(it & 1);
@@ -668,17 +664,22 @@ attn_fwd_item_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_con
               if (e < nv) m0 = fmaxf(m0, __uint_as_float(v[e]));
           }
         };
-        // two 32-column loads per tcgen05.wait::ld: in the kernel a load costs ~250 clocks of latency (the tensor pipe is
-        // writing TMEM at the same time) against ~55 clocks of max work per step, so the pass is bound by the NUMBER of
-        // waits (phase trace: 1.7 k clocks for 7 waits)
+        ld(0, va);
         for (int c = 0; c < nstep; c += 2) {
-          ld(c, va);
-          if (c + 1 < nstep) ld(c + 1, vb);
           tmem_ld_wait();
+          if (c + 1 < nstep) ld(c + 1, vb);
           red_max(c, va);
-          if (c + 1 < nstep) red_max(c + 1, vb);
+          if (c + 1 < nstep) {
+            tmem_ld_wait();
+            if (c + 2 < nstep) ld(c + 2, va);
+            red_max(c + 1, vb);
+          }
         }
         mx = fmaxf(fmaxf(fmax3(m0, m1, m2), fmax3(m3, m4, m5)), fmaxf(m6, m7)) * p.scale_log2;
+        // the previous item's O tile was staged in the first atom of sP for its TMA store: the store must have read
+        // it before pass 2 overwrites the atom (one elected thread waits, the group barrier tells the others)
+        if (q4 == 0 && lane == 0) tma_store_wait_read<0>();
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + t) : "memory");
         if (tr) { t1 = clock64(); acc_p1 += t1 - t0; }
         // ---- pass 2: p = 2^(s * scale * log2e - mx), row sum, bf16 P into the K-major swizzled operand ----
         const uint64_t nm2 = pk2(-mx, -mx);
@@ -722,12 +723,8 @@ attn_fwd_item_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_con
             }
           }
         };
-        // The previous item's O tile is staged in the LAST atom of sP (columns 192 .. 255) for its TMA store: the store
-        // must have read it before step 6 of this pass writes that atom — one elected thread waits, the group barrier
-        // tells the others.  (Staging in atom 0 put that wait, ~1 k clocks of store latency, right in front of pass 2.)
         ld(0, va);
         for (int c = 0; c < nstep; c += 2) {
-          if (c == 6) stage_sync();
           tmem_ld_wait();
           if (c + 1 < nstep) ld(c + 1, vb);
           exp_store(c, va);
@@ -741,8 +738,8 @@ attn_fwd_item_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_con
         upk2(s0, a0, a1);
         upk2(s1, a2, a3);
         sum = (a0 + a1) + (a2 + a3) + st;
-      } else if (nstep > 6) {
-        stage_sync();   // the group barrier of the branch above
+      } else {
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + t) : "memory");   // the group barrier of the branch above
       }
       // every S column of this row has been read: P may be consumed, the TMEM block reused for O
       fence_proxy_async_smem();
@@ -767,10 +764,9 @@ attn_fwd_item_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_con
       // O tile -> bf16 -> swizzled staging atom (P_t is dead once O_t exists) -> ONE TMA store per tile: a 3-D box
       // [1 batch][128 rows][64 columns] that the tensor map clips at the sequence length.  (Direct st.global of one
       // 128 B row per thread costs 32 L1 wavefronts per instruction, 2.2-3.8 k clocks per tile in the phase trace.)
-      if (nstep <= 6) stage_sync();   // S_pad <= 192: pass 2 never writes the staging atom, wait for the store only now
       if (warp_ok) {
         const float inv = row_ok ? 1.f / sum : 0.f;
-        uint8_t* a = sP + 3 * ATOM + r * 128;
+        uint8_t* a = sP + r * 128;
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           const uint32_t* v = half == 0 ? o0 : o1;
@@ -789,7 +785,7 @@ attn_fwd_item_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_con
       fence_proxy_async_smem();
       asm volatile("bar.sync %0, 128;" ::"r"(1 + t) : "memory");
       if (q4 == 0 && lane == 0) {
-        tma_store_3d(&tmOut, sP + 3 * ATOM, h * 64, t * 128, b);
+        tma_store_3d(&tmOut, sP, h * 64, t * 128, b);
         tma_store_commit();
       }
       if (tr) { tp = clock64(); acc_ep += tp - t2; }
