@@ -69,7 +69,6 @@ struct GemmArgs {
   float4* ce_part;            // CE_STATS: [M][ce_part_ld] partial (max, sum e^(x-max), sum e^(x-max) x, sum x)
   int ce_part_ld, ce_part0;   // CE_STATS: row pitch (in float4) and first part index of this launch
   float* ce_xlabel;           // CE_STATS: [M] logit at the label column
-  int debug;                  // MMB_GEMM_DEBUG (experiments only): 1 = skip the 2nd TMA store, 2 = skip the act math, 4 = skip all TMA stores, 8 = skip fence+barrier
 };
 
 template <int NT> __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory"); }
@@ -462,8 +461,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               float a[8];
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                a[2 * e] = (p.debug & 2) ? bf16_lo(pr[e]) : act_fn<ACT>(bf16_lo(pr[e]));
-                a[2 * e + 1] = (p.debug & 2) ? bf16_hi(pr[e]) : act_fn<ACT>(bf16_hi(pr[e]));
+                a[2 * e] = act_fn<ACT>(bf16_lo(pr[e]));
+                a[2 * e + 1] = act_fn<ACT>(bf16_hi(pr[e]));
               }
               uint4 oa;
               oa.x = pack_bf16x2(a[0], a[1]);
@@ -473,14 +472,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               *reinterpret_cast<uint4*>(dst1 + off) = oa;
             }
           }
-          if (!(p.debug & 8)) {
-            fence_proxy_async_smem();                       // generic-proxy slab writes -> visible to the TMA engine
-            if (epi_tid == 0) tma_store_wait_read<0>();     // stores of the previous group have left their slab
-            epi_bar_sync<ENT>();
-          }
-          if (epi_tid == 0 && !(p.debug & 4)) {
+          fence_proxy_async_smem();                       // generic-proxy slab writes -> visible to the TMA engine
+          if (epi_tid == 0) tma_store_wait_read<0>();     // stores of the previous group have left their slab
+          epi_bar_sync<ENT>();
+          if (epi_tid == 0) {
             tma_store_2d(&tmD0, slab0, n0 + g * 64, m0);
-            if (DUAL && !(p.debug & 1)) tma_store_2d(&tmD1, slab0 + SLAB_BYTES, n0 + g * 64, m0);
+            if (DUAL) tma_store_2d(&tmD1, slab0 + SLAB_BYTES, n0 + g * 64, m0);
             tma_store_commit();
           }
           if (EPI == EPI_BF16_DACT) {
@@ -714,11 +711,6 @@ static int gemm_dispatch(const void* A, long long lda, int a_mn_major, const voi
   g.ld_aux = ld_aux;
   g.d0 = D0; g.d1 = D1; g.ldd0 = ldd0; g.ldd1 = ldd1;
   g.reduce_add = (accumulate || g.splits > 1) ? 1 : 0;
-  {
-    static int dbg = -1;   // MMB_GEMM_DEBUG: experiment switches of the bf16 epilogue (results are WRONG with any of them set)
-    if (dbg < 0) { const char* e = getenv("MMB_GEMM_DEBUG"); dbg = e ? atoi(e) : 0; }
-    g.debug = dbg;
-  }
   if (colsum && (epilogue == EPI_F32 || epilogue == EPI_BF16_ACT || (reinterpret_cast<uintptr_t>(colsum) & 15)))
     return MMB_ERR_ARG;
   g.colsum = colsum;
