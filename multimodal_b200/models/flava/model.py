@@ -182,29 +182,31 @@ class FLAVAForPreTraining(nn.Module):
     def encode_text(self, text: Tensor, text_mask: Optional[Tensor] = None, cls_index: int = 0) -> Tensor:
         return self.model.encode_text(text, text_mask, projection=True)[1]
 
+    def _codebook_labels(self, image_for_codebook: Tensor, patches_mask: Tensor):
+        """Token id per patch from the codebook; unmasked patches get the ignore label -1 (model.py:347-351)."""
+        keep = patches_mask.flatten(1).to(torch.bool)
+        ids = self.image_codebook(image_for_codebook).flatten(1)
+        ids[~keep] = -1
+        return ids, keep
+
     def forward(self, image: Optional[Tensor] = None, text: Optional[Tensor] = None,
                 image_for_codebook: Optional[Tensor] = None, image_patches_mask: Optional[Tensor] = None,
                 text_masked: Optional[Tensor] = None, required_embedding: Optional[str] = None,
                 skip_unmasked_mm_encoder: bool = True, itm_labels: Optional[Tensor] = None,
                 mlm_labels: Optional[Tensor] = None) -> FLAVAPretrainingLossOutput:
-        image_labels = None
+        mim_labels = None
         if image_for_codebook is not None:
-            image_labels = self.image_codebook(image_for_codebook).flatten(1)
-            image_patches_mask = image_patches_mask.flatten(1).to(torch.bool)
-            image_labels[~image_patches_mask] = -1
-        flava_output: FLAVAOutput = self.model(
-            image=image, text=text, image_patches_mask=image_patches_mask, text_masked=text_masked,
-            required_embedding=required_embedding, skip_unmasked_mm_encoder=skip_unmasked_mm_encoder)
-        return self.loss(
-            image_sequence=flava_output.image.last_hidden_state,
-            text_sequence=flava_output.text.last_hidden_state,
-            image_masked_sequence=flava_output.image_masked.last_hidden_state,
-            text_masked_sequence=flava_output.text_masked.last_hidden_state,
-            multimodal_sequence=(flava_output.multimodal.last_hidden_state if not skip_unmasked_mm_encoder else None),
-            multimodal_masked_sequence=flava_output.multimodal_masked.last_hidden_state,
-            itm_labels=itm_labels, mim_labels=image_labels, mlm_labels=mlm_labels,
-            projected_image_embeddings=flava_output.projected_image_embeddings,
-            projected_text_embeddings=flava_output.projected_text_embeddings)
+            mim_labels, image_patches_mask = self._codebook_labels(image_for_codebook, image_patches_mask)
+        enc: FLAVAOutput = self.model(image=image, text=text, image_patches_mask=image_patches_mask,
+                                      text_masked=text_masked, required_embedding=required_embedding,
+                                      skip_unmasked_mm_encoder=skip_unmasked_mm_encoder)
+        # last hidden state of every encoder pass -> the loss's *_sequence arguments (model.py:362-377)
+        seq = {f"{name}_sequence": getattr(enc, name).last_hidden_state
+               for name in ("image", "text", "image_masked", "text_masked", "multimodal_masked")}
+        seq["multimodal_sequence"] = None if skip_unmasked_mm_encoder else enc.multimodal.last_hidden_state
+        return self.loss(itm_labels=itm_labels, mim_labels=mim_labels, mlm_labels=mlm_labels,
+                         projected_image_embeddings=enc.projected_image_embeddings,
+                         projected_text_embeddings=enc.projected_text_embeddings, **seq)
 
 
 def flava_model_for_pretraining(image_codebook: Optional[nn.Module] = None, codebook_image_size: int = 112,

@@ -16,14 +16,16 @@ def flava_text_encoder(num_hidden_layers: int = 12, hidden_size: int = 768, num_
                        layer_norm_eps: float = 1e-12, dropout: float = 0.0, vocab_size: int = 30522,
                        pad_token_id: int = 0, type_vocab_size: int = 2, max_position_embeddings: int = 512,
                        initializer_range: float = 0.02) -> BERTTextEncoder:
-    embeddings = BERTTextEmbeddings(hidden_size=hidden_size, vocab_size=vocab_size, pad_token_id=pad_token_id,
-                                    type_vocab_size=type_vocab_size, max_position_embeddings=max_position_embeddings,
-                                    layer_norm_eps=layer_norm_eps, dropout=dropout)
-    encoder = TransformerEncoder(n_layer=num_hidden_layers, d_model=hidden_size, n_head=num_attention_heads,
-                                 dim_feedforward=intermediate_size, activation=intermediate_activation,
-                                 layer_norm_eps=layer_norm_eps, dropout=dropout, norm_first=True)
-    layernorm = Fp32LayerNorm(hidden_size, eps=layer_norm_eps)
-    pooler = Pooler(hidden_size=hidden_size)
-    weight_init_fn = partial(init_transformer_weights, initializer_range=initializer_range)
-    return BERTTextEncoder(embeddings=embeddings, encoder=encoder, layernorm=layernorm, pooler=pooler,
-                           weight_init_fn=weight_init_fn)
+    # Sub-modules are built in the reference's order (embeddings, encoder, final LayerNorm, pooler): keyword values are
+    # evaluated left to right, so a seeded build consumes the RNG exactly like the reference builder does.
+    common = dict(layer_norm_eps=layer_norm_eps, dropout=dropout)
+    return BERTTextEncoder(
+        embeddings=BERTTextEmbeddings(hidden_size=hidden_size, vocab_size=vocab_size, pad_token_id=pad_token_id,
+                                      type_vocab_size=type_vocab_size, max_position_embeddings=max_position_embeddings,
+                                      **common),
+        encoder=TransformerEncoder(n_layer=num_hidden_layers, d_model=hidden_size, n_head=num_attention_heads,
+                                   dim_feedforward=intermediate_size, activation=intermediate_activation, norm_first=True,
+                                   **common),
+        layernorm=Fp32LayerNorm(hidden_size, eps=layer_norm_eps),
+        pooler=Pooler(hidden_size=hidden_size),
+        weight_init_fn=partial(init_transformer_weights, initializer_range=initializer_range))

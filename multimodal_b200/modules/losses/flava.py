@@ -18,7 +18,7 @@ tests/test_gpu_flava_pretraining.py.
 import math
 import warnings
 from collections import OrderedDict
-from dataclasses import dataclass, field, fields
+from dataclasses import field, fields, make_dataclass
 from typing import Any, Callable, Optional, Union
 
 import torch
@@ -57,55 +57,32 @@ class ModelOutput(OrderedDict):
             yield f.name, getattr(self, f.name)
 
 
-@dataclass
-class ITMLossOutput(ModelOutput):
-    logits: Tensor
-    loss: Tensor
+def _output(name: str, required=(), optional=(), base=ModelOutput, extra=None):
+    """Builds one of the reference's output containers (losses/flava.py:30-81): a dataclass over `base` whose fields are
+    `required` (positional tensors) followed by `optional` (default None) and `extra` (name -> default factory)."""
+    spec = [(f, Tensor) for f in required]
+    spec += [(f, Optional[Any], field(default_factory=fac)) for f, fac in (extra or {}).items()]
+    spec += [(f, Optional[Any], None) for f in optional]
+    cls = make_dataclass(name, spec, bases=(base,))
+    cls.__module__ = __name__
+    return cls
 
 
-@dataclass
-class MaskedPredictionLossOutput(ModelOutput):
-    logits: Tensor
-    loss: Tensor
-
-
-@dataclass
-class FLAVAGlobalContrastiveLossOutput(OrderedDict):
-    text_embedding: Tensor
-    image_embedding: Tensor
-    logit_scale: Tensor
-    image_logits: Tensor
-    text_logits: Tensor
-    image_loss: Tensor
-    text_loss: Tensor
-    loss: Tensor
-
-
-@dataclass
-class FLAVAPretrainingLossesCollection(ModelOutput):
-    mmm_text_loss: Optional[Tensor] = None
-    mmm_image_loss: Optional[Tensor] = None
-    mim_loss: Optional[Tensor] = None
-    mlm_loss: Optional[Tensor] = None
-    itm_loss: Optional[Tensor] = None
-    global_contrastive_loss: Optional[Tensor] = None
-
-
-@dataclass
-class FLAVAPretrainingLossOutput(ModelOutput):
-    losses: FLAVAPretrainingLossesCollection = field(default_factory=FLAVAPretrainingLossesCollection)
-    mlm_output: Optional[MaskedPredictionLossOutput] = None
-    mim_output: Optional[MaskedPredictionLossOutput] = None
-    mmm_text_output: Optional[MaskedPredictionLossOutput] = None
-    mmm_image_output: Optional[MaskedPredictionLossOutput] = None
-    itm_output: Optional[ITMLossOutput] = None
-    global_contrastive_output: Optional[FLAVAGlobalContrastiveLossOutput] = None
-    image_sequence: Optional[Tensor] = None
-    text_sequence: Optional[Tensor] = None
-    image_masked_sequence: Optional[Tensor] = None
-    text_masked_sequence: Optional[Tensor] = None
-    multimodal_sequence: Optional[Tensor] = None
-    multimodal_masked_sequence: Optional[Tensor] = None
+_HEAD_FIELDS = ("logits", "loss")
+ITMLossOutput = _output("ITMLossOutput", _HEAD_FIELDS)
+MaskedPredictionLossOutput = _output("MaskedPredictionLossOutput", _HEAD_FIELDS)
+FLAVAGlobalContrastiveLossOutput = _output(
+    "FLAVAGlobalContrastiveLossOutput",
+    ("text_embedding", "image_embedding", "logit_scale", "image_logits", "text_logits", "image_loss", "text_loss", "loss"),
+    base=OrderedDict)
+_LOSS_NAMES = ("mmm_text_loss", "mmm_image_loss", "mim_loss", "mlm_loss", "itm_loss", "global_contrastive_loss")
+FLAVAPretrainingLossesCollection = _output("FLAVAPretrainingLossesCollection", optional=_LOSS_NAMES)
+FLAVAPretrainingLossOutput = _output(
+    "FLAVAPretrainingLossOutput",
+    optional=("mlm_output", "mim_output", "mmm_text_output", "mmm_image_output", "itm_output", "global_contrastive_output",
+              "image_sequence", "text_sequence", "image_masked_sequence", "text_masked_sequence", "multimodal_sequence",
+              "multimodal_masked_sequence"),
+    extra={"losses": FLAVAPretrainingLossesCollection})
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -373,67 +350,74 @@ class FLAVAPretrainingLoss(nn.Module):
         self.mmm_text_loss_weight = mmm_text_loss_weight
         self.itm_loss_weight = itm_loss_weight
 
+    def _weighted(self, out, weight: float, slot: str, result: FLAVAPretrainingLossOutput):
+        """`outputs.<x>_output.loss *= weight; outputs.losses.<x>_loss = ...` of the reference, without the in-place op."""
+        out.loss = out.loss * weight
+        setattr(result, slot + "_output", out)
+        setattr(result.losses, slot + "_loss", out.loss)
+
+    def _positive_pairs(self, mm_masked: Tensor, itm_labels: Optional[Tensor]) -> Tensor:
+        # :416-424 — pairs with itm label != 0; if there is none, every pair counts
+        n = mm_masked.size(0)
+        if itm_labels is None:
+            return torch.ones(n, dtype=torch.bool, device=mm_masked.device)
+        pos = itm_labels.ne(0)
+        return pos if bool(pos.any()) else torch.ones_like(pos)
+
     def forward(self, image_sequence: Optional[Tensor] = None, text_sequence: Optional[Tensor] = None,
                 image_masked_sequence: Optional[Tensor] = None, text_masked_sequence: Optional[Tensor] = None,
                 multimodal_sequence: Optional[Tensor] = None, multimodal_masked_sequence: Optional[Tensor] = None,
                 itm_labels: Optional[Tensor] = None, mim_labels: Optional[Tensor] = None,
                 mlm_labels: Optional[Tensor] = None, projected_image_embeddings: Optional[Tensor] = None,
                 projected_text_embeddings: Optional[Tensor] = None) -> FLAVAPretrainingLossOutput:
-        # Control flow of the reference (:370-484), line for line in meaning; every tensor op on hidden states is a kernel
-        # of this library, the boolean / index bookkeeping on the (tiny) label tensors stays in torch.
-        outputs = FLAVAPretrainingLossOutput()
+        """Same branches as the reference (:370-484).  Every tensor op on hidden states is a kernel of this library; the
+        boolean / index bookkeeping on the (tiny) label tensors stays in torch."""
+        res = FLAVAPretrainingLossOutput()
+        mm = multimodal_masked_sequence
+        unimodal = mm is None
         pos_mask = None
-        if image_masked_sequence is not None and self.mim_weight > 0 and multimodal_masked_sequence is None:
-            start_index = -mim_labels.size(1) if mim_labels is not None else 1
-            outputs.mim_output = self.mim_loss(image_masked_sequence[:, start_index:, :], mim_labels)
-            outputs.mim_output.loss = outputs.mim_output.loss * self.mim_weight
-            outputs.losses.mim_loss = outputs.mim_output.loss
-        if text_masked_sequence is not None and self.mlm_weight > 0 and multimodal_masked_sequence is None:
-            start_index = -mlm_labels.size(1) if mlm_labels is not None else 1
-            outputs.mlm_output = self.mlm_loss(text_masked_sequence[:, start_index:, :], mlm_labels)
-            outputs.mlm_output.loss = outputs.mlm_output.loss * self.mlm_weight
-            outputs.losses.mlm_loss = outputs.mlm_output.loss
-        if multimodal_masked_sequence is not None and self.itm_loss_weight > 0:
-            if itm_labels is not None:
-                pos_pairs = itm_labels.ne(0)
-                pos_mask = torch.where(pos_pairs.any(), pos_pairs, pos_pairs.new([True]))
-            else:
-                pos_mask = torch.ones(multimodal_masked_sequence.size(0), device=multimodal_masked_sequence.device).bool()
-            outputs.itm_output = self.itm_loss(multimodal_masked_sequence, itm_labels)
-            outputs.itm_output.loss = outputs.itm_output.loss * self.itm_loss_weight
-            outputs.losses.itm_loss = outputs.itm_output.loss
-            # `multimodal_masked_sequence[pos_mask]` (:430): instead of copying the kept sequences, the labels of the
-            # dropped pairs are set to ignore_index — the masked-prediction losses then select exactly the same rows
-            if pos_mask.numel() == 1:
-                pos_mask = pos_mask.expand(multimodal_masked_sequence.size(0))
-            drop = ~pos_mask
-            if (mlm_labels is None or mim_labels is None) and bool(drop.any()):
-                # label-free (inference) use with negative pairs: the predictions cover the kept sequences only
-                multimodal_masked_sequence = multimodal_masked_sequence[pos_mask]
-                drop = drop[pos_mask]
-                mlm_labels = mlm_labels[pos_mask] if mlm_labels is not None else None
-                mim_labels = mim_labels[pos_mask] if mim_labels is not None else None
-            if mlm_labels is not None:
-                mlm_labels = mlm_labels.masked_fill(drop[:, None], self.mmm_loss["mlm"].ignore_index)
-            if mim_labels is not None:
-                mim_labels = mim_labels.masked_fill(drop[:, None], self.mmm_loss["mim"].ignore_index)
-        if multimodal_masked_sequence is not None and self.mmm_text_loss_weight > 0:
-            start_index = -mlm_labels.size(1) if mlm_labels is not None else -(text_masked_sequence.size(1) - 1)
-            sequence_for_text = multimodal_masked_sequence[:, start_index:, :]
-            outputs.mmm_text_output = self.mmm_loss["mlm"](sequence_for_text, mlm_labels)
-            outputs.mmm_text_output.loss = outputs.mmm_text_output.loss * self.mmm_text_loss_weight
-            outputs.losses.mmm_text_loss = outputs.mmm_text_output.loss
-        if multimodal_masked_sequence is not None and self.mmm_image_loss_weight > 0:
-            # starts from 2: one CLS of the multimodal encoder and one that comes from the image encoder (:451-452)
-            total_indices = mim_labels.size(1) if mlm_labels is not None else (image_masked_sequence.size(1) - 1)
-            sequence_for_image = multimodal_masked_sequence[:, 2:2 + total_indices, :]
-            outputs.mmm_image_output = self.mmm_loss["mim"](sequence_for_image, mim_labels)
-            outputs.mmm_image_output.loss = outputs.mmm_image_output.loss * self.mmm_image_loss_weight
-            outputs.losses.mmm_image_loss = outputs.mmm_image_output.loss
-        if (projected_image_embeddings is not None and projected_text_embeddings is not None
-                and self.contrastive_loss_weight > 0):
-            outputs.global_contrastive_output = self.contrastive_loss(
-                projected_image_embeddings, projected_text_embeddings, pos_mask)
-            outputs.global_contrastive_output.loss = outputs.global_contrastive_output.loss * self.contrastive_loss_weight
-            outputs.losses.global_contrastive_loss = outputs.global_contrastive_output.loss
-        return outputs
+
+        # -- unimodal masked prediction (:386-413): the sequence tail that lines up with the labels (CLS dropped) --
+        if unimodal and image_masked_sequence is not None and self.mim_weight > 0:
+            tail = mim_labels.size(1) if mim_labels is not None else image_masked_sequence.size(1) - 1
+            self._weighted(self.mim_loss(image_masked_sequence[:, -tail:, :], mim_labels), self.mim_weight, "mim", res)
+        if unimodal and text_masked_sequence is not None and self.mlm_weight > 0:
+            tail = mlm_labels.size(1) if mlm_labels is not None else text_masked_sequence.size(1) - 1
+            self._weighted(self.mlm_loss(text_masked_sequence[:, -tail:, :], mlm_labels), self.mlm_weight, "mlm", res)
+
+        # -- image-text matching + restriction of the masked-multimodal losses to the positive pairs (:415-435) --
+        if not unimodal and self.itm_loss_weight > 0:
+            pos_mask = self._positive_pairs(mm, itm_labels)
+            self._weighted(self.itm_loss(mm, itm_labels), self.itm_loss_weight, "itm", res)
+            negatives = ~pos_mask
+            if bool(negatives.any()):
+                if mlm_labels is None or mim_labels is None:
+                    # label-free (inference) call: predictions cover the kept sequences only, as `mm[pos_mask]` does
+                    mm = mm[pos_mask]
+                    mlm_labels = None if mlm_labels is None else mlm_labels[pos_mask]
+                    mim_labels = None if mim_labels is None else mim_labels[pos_mask]
+                else:
+                    # instead of copying the kept sequences, the labels of the dropped pairs become ignore_index: the
+                    # masked-prediction heads then select exactly the rows `mm[pos_mask]` would have contributed
+                    ign_t, ign_i = self.mmm_loss["mlm"].ignore_index, self.mmm_loss["mim"].ignore_index
+                    mlm_labels = mlm_labels.masked_fill(negatives[:, None], ign_t)
+                    mim_labels = mim_labels.masked_fill(negatives[:, None], ign_i)
+
+        # -- masked multimodal modelling (:437-466): text tokens are the sequence tail, image patches follow the two CLS --
+        if not unimodal and self.mmm_text_loss_weight > 0:
+            tail = mlm_labels.size(1) if mlm_labels is not None else text_masked_sequence.size(1) - 1
+            self._weighted(self.mmm_loss["mlm"](mm[:, -tail:, :], mlm_labels), self.mmm_text_loss_weight, "mmm_text", res)
+        if not unimodal and self.mmm_image_loss_weight > 0:
+            # reference quirk kept (:454-458): the patch count comes from mim_labels only when mlm_labels is given
+            n_patch = mim_labels.size(1) if mlm_labels is not None else image_masked_sequence.size(1) - 1
+            self._weighted(self.mmm_loss["mim"](mm[:, 2:2 + n_patch, :], mim_labels), self.mmm_image_loss_weight,
+                           "mmm_image", res)
+
+        # -- global contrastive loss over the projected CLS embeddings (:468-482) --
+        have_proj = projected_image_embeddings is not None and projected_text_embeddings is not None
+        if have_proj and self.contrastive_loss_weight > 0:
+            gc = self.contrastive_loss(projected_image_embeddings, projected_text_embeddings, pos_mask)
+            gc.loss = gc.loss * self.contrastive_loss_weight
+            res.global_contrastive_output = gc
+            res.losses.global_contrastive_loss = gc.loss
+        return res
