@@ -86,6 +86,8 @@ class ContrastiveTrainer:
         # single process on the concatenated batch.  Only applies to the non-overlapped schedule.
         import os as _os
         self.allreduce_bf16 = _os.environ.get("MMB_GRAD_ALLREDUCE", "fp32").lower() == "bf16"
+        self.tower_streams = _os.environ.get("MMB_TOWER_STREAMS", "0") == "1"   # text tower on a side stream (see step())
+        self._side = None
         self._gb = {}
         self._works: List = []
         self.kernel_launches = 0
@@ -133,7 +135,27 @@ class ContrastiveTrainer:
         self.ls.data.clamp_(self.loss_module.logit_scale_min, self.loss_module.logit_scale_max)
         self.ls_buf[0:1].copy_(self.ls.data.reshape(1))
         # ---------------- forward ----------------
-        if mb == B:
+        # The two towers are independent until the loss.  With tower_streams the text tower runs on a side stream: its
+        # LayerNorm / attention / elementwise kernels (HBM- or latency-bound, small smem footprint) then share the SMs
+        # with the image tower's persistent GEMM CTAs (bound by the L2 <-> SM path) instead of queueing behind them, and
+        # each tower's kernels fill the other's tails.  Only kernels without shared scratch run concurrently (the fused
+        # attention backward keeps its statistics in smem; the two-pass kernels share one D buffer -> S <= 256 only).
+        par = (self.tower_streams and mb == B and getattr(img, "S", 1 << 30) <= 256 and getattr(txt, "S", 1 << 30) <= 256)   # S is known after the first step
+        main = torch.cuda.current_stream(dev)
+        if par:
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=dev)
+            side = self._side
+            ev = torch.cuda.Event()
+            ev.record(main)                      # inputs (and the previous optimizer step) are ordered before the side stream
+            with torch.cuda.stream(side):
+                side.wait_event(ev)
+                eb = txt.forward(text, True)
+                ev_t = torch.cuda.Event()
+                ev_t.record(side)
+            ea = img.forward(image, True)
+            main.wait_event(ev_t)
+        elif mb == B:
             ea = img.forward(image, True)
             eb = txt.forward(text, True)
         else:
@@ -162,6 +184,19 @@ class ContrastiveTrainer:
             for i in range(0, B, mb):
                 img.forward(image[i:i + mb], True)
                 img.backward(dea[i:i + mb])
+            self._allreduce(txt.store.g)
+            self._allreduce(img.store.g)
+            bounds = None
+        elif par:
+            ev = torch.cuda.Event()
+            ev.record(main)                      # deb is ready
+            with torch.cuda.stream(self._side):
+                self._side.wait_event(ev)
+                txt.backward(deb)
+                ev_t = torch.cuda.Event()
+                ev_t.record(self._side)
+            img.backward(dea)
+            main.wait_event(ev_t)
             self._allreduce(txt.store.g)
             self._allreduce(img.store.g)
             bounds = None
