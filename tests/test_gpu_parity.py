@@ -116,7 +116,9 @@ def _attn_ref(qkv, B, S, H, causal):
                                          # persistent kernels looping over several work items per CTA (> 148 items),
                                          # tile boundaries of the two-tile forward / fused backward kernels
                                          (40, 197, 12, False), (25, 129, 12, False), (13, 256, 12, False),
-                                         (30, 224, 6, False), (60, 77, 8, True)])
+                                         (30, 224, 6, False), (60, 77, 8, True),
+                                         # causal masks across the two key tiles / four query chunks of the fused backward
+                                         (5, 200, 4, True), (3, 256, 2, True), (4, 130, 3, True)])
 def test_attention_fwd_bwd(dev, B, S, H, causal):
     from multimodal_b200 import ops
 
