@@ -1,14 +1,16 @@
-// tcgen05 attention for S <= 256, head_dim 64 (CLIP ViT-B/16 image S=197, text S=77): scores and gradients are
-// computed by 5th-gen tensor cores with TMEM accumulators; operands are staged by TMA straight out of the packed
-// in-projection output [B*S, 3d] (no head split/merge copies).  One thread per tile row does the softmax math on
-// TMEM rows (tcgen05.ld 32x32b), two warpgroups split the columns.
+// tcgen05 attention for S <= 384, head_dim 64 (CLIP ViT-B/16 image S = 197, text S = 77; ViT-L/14 S = 257; FLAVA): scores
+// and gradients are computed by 5th-gen tensor cores with TMEM accumulators; operands are staged by TMA straight out of
+// the packed in-projection output [B*S, 3d] (no head split / merge copies); the softmax / dS math runs one thread per tile
+// row on TMEM rows (tcgen05.ld 32x32b).  Replaces F.scaled_dot_product_attention + autograd (torch/nn/functional.py:6682).
 //
-//   fwd   (b,h,q-tile):  S = Q K^T (TMEM, <=256 cols) -> softmax -> P (bf16, smem, K-major) -> O = P V (TMEM)
-//   dq    (b,h,q-tile):  per 64-wide kv chunk c: S_c = Q K_c^T, dP_c = dO V_c^T -> dS_c -> dQ += dS_c K_c
-//   dkdv  (b,h,kv-tile): per 64-wide q chunk c: S^T_c = K Q_c^T, dP^T_c = V dO_c^T -> P^T_c, dS^T_c ->
-//                        dV += P^T_c dO_c ; dK += dS^T_c Q_c
-// The chunked backward kernels double-buffer the S/dP accumulators in TMEM so the MMAs of chunk c+1 run under the
-// elementwise work of chunk c.  Replaces F.scaled_dot_product_attention + autograd (torch/nn/functional.py:6682).
+// Kernels in this file (dispatch: mmb_attention_fwd_tc / _bwd_tc at the end; DESIGN.md section 4 has the measurements):
+//   forward   attn_fwd_item_kernel   128 < S <= 256, no mask: persistent, work item = (batch, head) with both query tiles
+//             attn_fwd_pp_kernel     S <= 128: persistent, two worker groups alternate tiles
+//             attn_fwd_tc_kernel     everything else (key mask, causal S > 128, 256 < S <= 384): one tile per CTA
+//   backward  attn_bwd_fused_kernel  S <= 256: ONE pass, rows = keys, dQ accumulated in TMEM across the key tiles
+//             attn_bwd_pp_kernel     256 < S <= 384: dQ pass + dK/dV pass, worker groups alternate 64-row chunks
+//             attn_bwd_persist_kernel  the round-1 two-pass kernel (MMB_ATTN_BWD=colsplit, A/B only)
+// Every tcgen05.mma / TMA issue runs on an elected lane of a shfl-uniform warp (common.cuh: elect_one, uniform_warp_idx).
 #include "common.cuh"
 #include "mmb200_internal.h"
 #include <stdlib.h>
@@ -239,7 +241,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
 }
 
 // ------------------------------------------------------------------------------------------------
-// Forward, persistent PING-PONG version (round 2; default for S_pad <= 256).  One CTA per SM loops over
+// Forward, persistent PING-PONG version (round 2; used for S <= 128: the text tower).  One CTA per SM loops over
 // (batch, head, 128-query tile) work items; two tile buffers (smem operands + a 256-column TMEM score block each) are
 // in flight, each served by its own group of four worker warps:
 //   * producer warp: TMA loads of Q / K / V of tile n+2 start as soon as the PV MMA of tile n has left the buffer;
@@ -1201,7 +1203,8 @@ attn_bwd_persist_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gr
 //                     dQ block p (queries 128p ..) at 384 + 64p, alive for the whole work item.
 // smem: K_j | V_j tile operands x 2 (64 KB), (Q_c | dO_c) chunk ring x 3 (48 KB), dS^T x 4 (chunk c -> buffer c: the
 // pairs (0,1), (2,3) are the two dQ A operands; 64 KB), P^T x 2 (32 KB), per-query LSE / D x 2 (4 KB).
-// Warps: 8 workers (thread = key row x column half), TMA producer, score issuer, accumulate issuer, 2 statistics warps.
+// Warps: 8 workers (thread = key row x column half), TMA producer, score issuer, accumulate issuer, NSTAT statistics
+// warps.  Output tiles (dV, dK per key tile, dQ per work item) leave through dead operand buffers + TMA stores.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint64_t desc_mn_a(uint32_t saddr) { return make_smem_desc_sw128(saddr, 16384, 1024); }
 
@@ -1615,7 +1618,7 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
 }
 constexpr int BWDF_SMEM = 1024 + 4 * ATOM + 3 * 16384 + 4 * ATOM + 2 * ATOM + 4096 + 512;   // 213.5 KB
 #ifndef MMB_ATTN_BWD_DEFAULT
-#define MMB_ATTN_BWD_DEFAULT 2   /* 1 = column-split two-pass, 2 = fused single pass (S <= 256): 1.27 vs 1.88 ms at B/16 */
+#define MMB_ATTN_BWD_DEFAULT 2   /* 1 = column-split two-pass, 2 = fused single pass (S <= 256): 0.93 vs 1.88 ms at B/16 */
 #endif
 
 // ------------------------------------------------------------------------------------------------
