@@ -207,6 +207,35 @@ int mmb_concat_tokens(const float* cls, const float* a, const float* b, float* o
                       void* stream);
 
 
+/* ---- FLAVA encoders, backward (config 3 as a training step; autograd of the files cited on the forward entries) -- */
+/* Backward of mmb_attention_fwd_kmask (fused single-pass tcgen05 kernel, S <= 256): masked keys get P = dS = 0. */
+int mmb_attention_bwd_kmask(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
+                            const unsigned char* kmask, int B, int S, int H, int head_dim, int causal, float scale,
+                            void* stream);
+/* Backward of mmb_bert_embed_ln_fwd: the pre-LayerNorm sum and its statistics are recomputed from the tables; dx is
+ * scatter-added into dword[ids] / dpos[s] / dtype[type_ids], dgamma / dbeta are accumulated (all fp32, += ). */
+int mmb_bert_embed_ln_bwd(const long long* ids, const long long* type_ids, const float* word, const float* pos,
+                          const float* type, const float* gamma, const float* dy, float* dword, float* dpos, float* dtype,
+                          float* dgamma, float* dbeta, int B, int S, int d, int V, float eps, void* stream);
+/* Backward of mmb_vit_assemble_fwd for the patch rows: dpatch[b*P+p] = bf16(mask ? 0 : g[b,off+p]) (the operand of the
+ * patch-projection weight gradient), dmask_token += sum of the masked rows' g.  dcls / dpos: mmb_batch_sum of g. */
+int mmb_vit_assemble_bwd(const float* g, const unsigned char* patch_mask, void* dpatch_bf16, float* dmask_token, int B,
+                         int S, int d, int has_cls, void* stream);
+/* Inverse of mmb_concat_tokens for gradients: g [B, cls+Sa+Sb, d] fp32 -> bf16 [B*Sa, d] and [B*Sb, d]. */
+int mmb_split_tokens_cast(const float* g, void* a_bf16, void* b_bf16, int B, int Sa, int Sb, int d, int has_cls,
+                          void* stream);
+/* dx = dy * (1 - y^2), y = tanh(x) (Pooler, modules/losses/flava.py:92-96); fp32 and / or bf16 output. */
+int mmb_tanh_bwd(const float* dy, const float* y, float* dx, void* dx_bf16, long long n, void* stream);
+/* dst[b*rows_per_group + row, :] += src[b, :] — gradient of the `hidden[:, row]` select (mmb_gather_rows_cast). */
+int mmb_scatter_rows_add(const float* src, float* dst, int B, int rows_per_group, int row, int d, void* stream);
+/* dst[idx[m]*ld : +d] += src[m, :] (atomics; idx may repeat) — gradient of mmb_gather_rows_idx_cast. */
+int mmb_scatter_rows_idx_add(const float* src, const long long* idx, float* dst, long long ld, int n, int d, void* stream);
+/* d loss / d logits (bf16) of the label-indexed mean cross-entropy of mmb_ce_labels: w * (softmax - onehot) for kept rows,
+ * 0 for ignored rows, w = grad_scale / max(accum[1], 1) (accum = the forward's {sum, count}; NULL: w = grad_scale). */
+int mmb_ce_labels_bwd(const float* logits, long long ld, const long long* labels, long long label_stride,
+                      long long ignore_index, int M, int V, const float* accum, float grad_scale, void* dlogits_bf16,
+                      long long ldd, void* stream);
+
 /* ---- CoCa forward helpers ------------------------------------------------------------------ */
 /* x[b,s] = emb[ids[b,s]] + pos[s] (s < S-1), x[b,S-1] = cls + pos[S-1]; ids is [B, S-1] when cls != NULL, else [B, S]
  * — CoCaTextEmbeddings.forward, models/coca/text_decoder.py:48-60. */

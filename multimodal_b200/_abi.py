@@ -58,6 +58,14 @@ PROTOTYPES = {
     "mmb_symm_close_handle": (i32, [vp]),
     "mmb_symm_signal_wait": (i32, [vp, vp, i32, i32, i32, vp]),
     "mmb_sum_scale": (i32, [vp, i32, f32, vp, i32, vp]),
+    "mmb_attention_bwd_kmask": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, vp]),
+    "mmb_bert_embed_ln_bwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, vp]),
+    "mmb_vit_assemble_bwd": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, vp]),
+    "mmb_split_tokens_cast": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, vp]),
+    "mmb_tanh_bwd": (i32, [vp, vp, vp, vp, ll, vp]),
+    "mmb_scatter_rows_add": (i32, [vp, vp, i32, i32, i32, i32, vp]),
+    "mmb_scatter_rows_idx_add": (i32, [vp, vp, vp, ll, i32, i32, vp]),
+    "mmb_ce_labels_bwd": (i32, [vp, ll, vp, ll, ll, i32, i32, vp, f32, vp, ll, vp]),
 }
 
 

@@ -1467,6 +1467,8 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
       BT(a_stat);
       for (int j = 0; j < ntile; ++j, ++nt) {
         const int ri = j * 128 + r;   // key index of this thread's row
+        // a key that is out of range or padded out by the key mask contributes P = dS = 0 (its dK / dV rows stay zero)
+        const bool key_dead = (ri >= S) || (p.kmask != nullptr && p.kmask[(long long)b * S + ri] == 0);
         for (int c = 0; c < nc; ++c, ++g) {
           const int sb = g & 1;
           const int wc = min(64, S_pad - c * 64);
@@ -1489,7 +1491,7 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
           uint8_t* myDS = sDS + c * ATOM;
           uint8_t* myPT = sPT + sb * ATOM;
           const int cbase = c * 64 + grp * 32;
-          const bool full = (ri < S) && (cbase + 32 <= S) && (!CAUSAL || ri <= cbase);
+          const bool full = !key_dead && (cbase + 32 <= S) && (!CAUSAL || ri <= cbase);
           const uint64_t c2 = pk2(p.scale_log2, p.scale_log2), sc2 = pk2(p.scale, p.scale);
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
@@ -1498,7 +1500,7 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
             uint8_t* aPT = myPT + ((grp * 32 + half * 16) >> 6) * ATOM + r * 128;
             const int c8 = ((grp * 32 + half * 16) & 63) >> 3;
             const int o0 = (c8 ^ (r & 7)) << 4, o1 = ((c8 + 1) ^ (r & 7)) << 4;
-            if (ri >= S) {
+            if (key_dead) {
               *reinterpret_cast<uint4*>(aDS + o0) = make_uint4(0, 0, 0, 0);
               *reinterpret_cast<uint4*>(aDS + o1) = make_uint4(0, 0, 0, 0);
               *reinterpret_cast<uint4*>(aPT + o0) = make_uint4(0, 0, 0, 0);
@@ -2132,9 +2134,11 @@ static int attn_bwd_variant() {   // 0 = two-pass ping-pong, 1 = two-pass column
 // kernels one mmb_attention_bwd call launches at sequence length S (callers that count launches: bench.py gpu_launches)
 extern "C" int mmb_attention_bwd_launches(int S) { return (attn_bwd_variant() == 2 && S <= 256) ? 1 : 2; }
 
-extern "C" int mmb_attention_bwd_tc(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
-                                    int B, int S, int H, int causal, float scale, void* stream) {
+static int attention_bwd_tc_impl(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
+                                 const uint8_t* kmask, int B, int S, int H, int causal, float scale, void* stream) {
   if (B <= 0 || S <= 0 || S > SMAX) return MMB_ERR_UNSUPPORTED;
+  // key-padding mask: implemented in the fused single-pass kernel only (S <= 256, the default variant)
+  if (kmask != nullptr && !(attn_bwd_variant() == 2 && S <= 256)) return MMB_ERR_UNSUPPORTED;
   const int d = H * 64, S_pad = (S + 15) & ~15;
   CUtensorMap q128, q64, o128, o64;
   int rc = make_tmap_2d(&q128, qkv, 2, false, 3ull * d, (uint64_t)B * S, 3ull * d * 2, 64, 128);
@@ -2165,7 +2169,7 @@ extern "C" int mmb_attention_bwd_tc(const void* qkv, const void* out, const void
   AttnTcArgs a{};
   a.S = S; a.H = H; a.S_pad = S_pad; a.scale = scale; a.scale_log2 = scale * 1.4426950408889634f;
   a.lse = const_cast<float*>(lse); a.o_in = (const __nv_bfloat16*)out; a.dout = (const __nv_bfloat16*)dout;
-  a.dqkv = (__nv_bfloat16*)dqkv; a.dsum = dsum;
+  a.dqkv = (__nv_bfloat16*)dqkv; a.dsum = dsum; a.kmask = kmask;
   const int n_work = ((S + 127) / 128) * H * B;
   const int grid_p = n_work < num_sms() ? n_work : num_sms();
   // Backward kernels: the two-pass column-split one (S <= 256), the fused single-pass one (S <= 256) and the two-pass
@@ -2223,6 +2227,19 @@ extern "C" int mmb_attention_bwd_tc(const void* qkv, const void* out, const void
   }
 #undef LAUNCH_BWDPP
   return (int)cudaGetLastError();
+}
+
+extern "C" int mmb_attention_bwd_tc(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
+                                    int B, int S, int H, int causal, float scale, void* stream) {
+  return attention_bwd_tc_impl(qkv, out, dout, lse, dqkv, nullptr, B, S, H, causal, scale, stream);
+}
+// Backward of mmb_attention_fwd_kmask: masked keys get P = dS = 0, i.e. zero dK / dV rows and no share in dQ
+// (modules/layers/attention.py:220-239 under autograd, additive -inf mask of utils/attention.py:13-53).
+extern "C" int mmb_attention_bwd_kmask(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
+                                       const unsigned char* kmask, int B, int S, int H, int head_dim, int causal,
+                                       float scale, void* stream) {
+  if (head_dim != 64) return MMB_ERR_UNSUPPORTED;
+  return attention_bwd_tc_impl(qkv, out, dout, lse, dqkv, kmask, B, S, H, causal, scale, stream);
 }
 
 // Public entry points (include/mmb200.h).  Every sequence length up to SMAX = 384 runs on the tcgen05 kernels above;

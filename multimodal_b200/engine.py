@@ -43,6 +43,11 @@ def watch_module(mod: nn.Module) -> None:
     mod.register_load_state_dict_post_hook(lambda module, incompatible: invalidate_weight_caches())
 
 
+def _require_cuda(dev: torch.device) -> None:
+    if dev.type != "cuda":
+        raise MMBError("multimodal_b200 modules must live on a CUDA device (no CPU path); call .cuda() first")
+
+
 class ParamStore:
     """Flat bf16 shadow (tensor-core operand copies) + flat fp32 gradient buffer for a list of parameters."""
 
@@ -51,8 +56,7 @@ class ParamStore:
         if not self.params:
             raise MMBError("ParamStore: no parameters")
         dev = self.params[0].device
-        if dev.type != "cuda":
-            raise MMBError("multimodal_b200 modules must live on a CUDA device (no CPU path); call .cuda() first")
+        _require_cuda(dev)
         self.device = dev
         self.off: Dict[int, int] = {}
         off = 0
@@ -68,6 +72,8 @@ class ParamStore:
         self.master: Optional[torch.Tensor] = None  # set by flatten_()
         self._shadow_fresh = False
         self._epoch = _WEIGHT_EPOCH[0]
+        self._packs: List[list] = []   # [key tensor, parts, version seen]: fp32 concatenations kept current by refresh()
+        self._keys: List[torch.Tensor] = []
 
     # -- views ------------------------------------------------------------------------------------------
     def shadow(self, p: nn.Parameter) -> torch.Tensor:
@@ -85,6 +91,34 @@ class ParamStore:
     def grad2d(self, p: nn.Parameter) -> torch.Tensor:
         o = self.off[id(p)]
         return self.g[o:o + p.numel()].view(p.shape[0], -1)
+
+    def pack(self, parts: Sequence[nn.Parameter], fp32: bool = False) -> torch.Tensor:
+        """Present consecutive parameters as ONE tensor (rows concatenated): e.g. separate query / key / value Linears
+        as the packed [3d, d] in-projection operand.  Returns a key tensor accepted by shadow() / grad() (views spanning
+        all parts).  fp32=True: the key is a real fp32 concatenation, kept current by refresh(), usable as a kernel
+        operand (biases); otherwise it is a shape-only placeholder."""
+        offs = [self.off[id(p)] for p in parts]
+        for a, b, p in zip(offs, offs[1:], parts):
+            if b != a + p.numel():
+                raise MMBError("ParamStore.pack: parts must be consecutive in the store with sizes that are multiples "
+                               f"of {_ALIGN} elements")
+        shape = (sum(p.shape[0] for p in parts),) + tuple(parts[0].shape[1:])
+        if fp32:
+            key = torch.empty(shape, device=self.device, dtype=torch.float32)
+            self._packs.append([key, list(parts), None])
+        else:
+            key = torch.empty(shape, device="meta", dtype=torch.float32)
+        self.off[id(key)] = offs[0]
+        self._keys.append(key)   # keeps id(key) unique for the lifetime of the store
+        return key
+
+    def _refresh_packs(self, force: bool) -> None:
+        for ent in self._packs:
+            key, parts, seen = ent
+            ver = tuple((p._version, p.data_ptr()) for p in parts) + (_WEIGHT_EPOCH[0],)
+            if force or seen != ver:
+                torch.cat([p.data.reshape(-1) for p in parts], out=key.view(-1))   # a few KB of biases: plumbing
+                ent[2] = ver
 
     # -- maintenance ------------------------------------------------------------------------------------
     def flatten_(self) -> None:
@@ -106,6 +140,7 @@ class ParamStore:
         if self.master is not None:
             if not self._shadow_fresh or self._epoch != _WEIGHT_EPOCH[0]:
                 ops.cast_bf16(self.master, self.wb)
+                self._refresh_packs(True)
                 self._shadow_fresh = True
                 self._epoch = _WEIGHT_EPOCH[0]
             return
@@ -117,6 +152,7 @@ class ParamStore:
                 src = p.data if p.data.is_contiguous() else p.data.contiguous()
                 ops.cast_bf16(src.view(-1), self.wb[self.off[id(p)]:self.off[id(p)] + p.numel()])
                 self._seen[id(p)] = key
+        self._refresh_packs(False)
 
     def mark_dirty(self) -> None:
         self._shadow_fresh = False
@@ -131,6 +167,8 @@ class Workspace:
     def __init__(self, device):
         self.device = device
         self.bufs: Dict[str, torch.Tensor] = {}
+        self.X0: Optional[torch.Tensor] = None      # set by TransformerStack.forward(training=True): layer-0 input
+        self.kmask: Optional[torch.Tensor] = None   # ... and the key-padding mask that forward used
 
     def get(self, name: str, shape, dtype) -> torch.Tensor:
         t = self.bufs.get(name)
@@ -167,11 +205,17 @@ class TransformerStack:
 
     def _buf(self, name, l, shape, dtype, training):
         key = f"{self.prefix}.{name}.{l if training else 0}"
-        return self.ws.get(key, shape, dtype)
+        return (self._save if training else self.ws).get(key, shape, dtype)
 
-    def forward(self, X0: torch.Tensor, B: int, S: int, training: bool):
+    def forward(self, X0: torch.Tensor, B: int, S: int, training: bool, kmask: Optional[torch.Tensor] = None,
+                save: Optional["Workspace"] = None):
         """X0: fp32 [B*S, d] residual stream entering layer 0.  Returns (XM_last fp32, Y bf16): the final residual
-        stream is XM_last + Y (the add is fused into whichever LayerNorm consumes it)."""
+        stream is XM_last + Y (the add is fused into whichever LayerNorm consumes it).
+        kmask: optional uint8 [B*S] key-padding mask (1 = attend).  save: the Workspace that receives the activations a
+        training forward keeps for its backward (default: the stack's own — ONE in-flight training forward; callers
+        that run the same stack several times before the backward pass a fresh Workspace per call)."""
+        self._save = save if save is not None else self.ws
+        self._save.kmask = kmask if training else None
         st, d, ff, H = self.store, self.d, self.ff, self.H
         M = B * S
         bf, f32 = torch.bfloat16, torch.float32
@@ -198,7 +242,10 @@ class TransformerStack:
                 ops.add_layernorm_fwd(XM_prev, Y, XA, LN1, None, layer.norm1.weight, layer.norm1.bias, m1, r1, M, d,
                                       layer.norm1.eps)
             ops.gemm(LN1, st.shadow(at.in_proj_weight), bias=at.in_proj_bias, out=QKV)
-            ops.attention_fwd(QKV, O, LSE, B, S, H, self.causal, self.scale)
+            if kmask is not None:
+                ops.attention_fwd_kmask(QKV, O, LSE, kmask, B, S, H, self.causal, self.scale)
+            else:
+                ops.attention_fwd(QKV, O, LSE, B, S, H, self.causal, self.scale)
             ops.gemm(O, st.shadow(at.out_proj.weight), bias=at.out_proj.bias, out=Y)
             ops.add_layernorm_fwd(XA, Y, XM, LN2, None, layer.norm2.weight, layer.norm2.bias, m2, r2, M, d,
                                   layer.norm2.eps)
@@ -208,6 +255,7 @@ class TransformerStack:
             XM_prev = XM
         self.saved = training
         self._X0 = X0 if training else None
+        self._save.X0 = self._X0
         return XM_prev, Y
 
     def top_bias_grad(self) -> torch.Tensor:
@@ -215,12 +263,17 @@ class TransformerStack:
         return self.store.grad(self.layers[-1].linear2.bias)
 
     def backward(self, G: torch.Tensor, Gb: torch.Tensor, B: int, S: int, on_layer_done=None,
-                 top_bias_done: bool = False) -> torch.Tensor:
+                 top_bias_done: bool = False, save: Optional["Workspace"] = None) -> torch.Tensor:
         """G (fp32) / Gb (bf16 copy): gradient w.r.t. the final residual stream [B*S, d].  Returns G w.r.t. X0
         (in place).  Parameter gradients are ACCUMULATED into the ParamStore's flat fp32 buffer.
         The bias gradients of linear2 / out_proj are column sums of Gb; they are produced by the LayerNorm-backward
         kernel that writes Gb (`gsum`), not by a separate pass (top_bias_done: the caller's kernel did the top one)."""
-        if not self.saved:
+        if save is None:
+            if not self.saved:
+                raise MMBError("backward called without a saved training forward")
+            save = self.ws
+        X0, kmask = save.X0, getattr(save, "kmask", None)
+        if X0 is None:
             raise MMBError("backward called without a saved training forward")
         st, d, ff, H = self.store, self.d, self.ff, self.H
         M = B * S
@@ -232,13 +285,13 @@ class TransformerStack:
             layer = self.layers[l]
             at = layer.self_attn
             f32 = torch.float32
-            g = lambda n, shape, dt: self.ws.get(f"{self.prefix}.{n}.{l}", shape, dt)  # noqa: E731
+            g = lambda n, shape, dt: save.get(f"{self.prefix}.{n}.{l}", shape, dt)  # noqa: E731
             LN1, QKV, O = g("LN1", (M, d), bf), g("QKV", (M, 3 * d), bf), g("O", (M, d), bf)
             LSE = g("LSE", (B * H * S,), f32)
             XM, LN2 = g("XM", (M, d), f32), g("LN2", (M, d), bf)
             PRE, HACT = g("PRE", (M, ff), bf), g("HACT", (M, ff), bf)
             m1, r1, m2, r2 = g("m1", (M,), f32), g("r1", (M,), f32), g("m2", (M,), f32), g("r2", (M,), f32)
-            XA = self._X0 if l == 0 else g("XA", (M, d), f32)
+            XA = X0 if l == 0 else g("XA", (M, d), f32)
             # ---- MLP branch:  y = W2 act(W1 LN2(x) + b1) + b2 ----
             ops.gemm(Gb, HACT, a_mn=True, b_mn=True, epilogue=ops.EPI_F32, out=st.grad(layer.linear2.weight),
                      splits=sp(d, ff, M), accumulate=True)
@@ -259,7 +312,10 @@ class TransformerStack:
             ops.gemm(Gb, O, a_mn=True, b_mn=True, epilogue=ops.EPI_F32, out=st.grad(at.out_proj.weight),
                      splits=sp(d, d, M), accumulate=True)
             ops.gemm(Gb, st.shadow(at.out_proj.weight), b_mn=True, out=T1)  # dO
-            ops.attention_bwd(QKV, O, T1, LSE, T3, B, S, H, self.causal, self.scale)
+            if kmask is not None:
+                ops.attention_bwd_kmask(QKV, O, T1, LSE, T3, kmask, B, S, H, self.causal, self.scale)
+            else:
+                ops.attention_bwd(QKV, O, T1, LSE, T3, B, S, H, self.causal, self.scale)
             ops.gemm(T3, LN1, a_mn=True, b_mn=True, epilogue=ops.EPI_F32, out=st.grad(at.in_proj_weight),
                      splits=sp(3 * d, d, M), accumulate=True)
             ops.colsum_bf16(T3, st.grad(at.in_proj_bias), M, 3 * d, 3 * d)

@@ -22,6 +22,7 @@ from typing import Dict, List, Optional, Sequence
 import torch
 from torch import nn
 
+from . import engine as _engine
 from . import ops
 from ._lib import MMBError
 from .engine import Workspace, weight_epoch
@@ -89,8 +90,7 @@ class FlavaStack:
             raise MMBError(f"unsupported MLP activation {type(act).__name__} (FLAVA uses nn.GELU)")
         self.layernorm, self.pooler, self.prefix = layernorm, pooler, prefix
         dev = l0.attention.query.weight.device
-        if dev.type != "cuda":
-            raise MMBError("multimodal_b200 modules must live on a CUDA device (no CPU path); call .cuda() first")
+        _engine._require_cuda(dev)
         self.device = dev
         self.ws = Workspace(dev)
         self.sh = _Shadows(dev)

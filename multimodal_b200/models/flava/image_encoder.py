@@ -65,7 +65,6 @@ class ImageTransformer(_RuntimeOwner):
             weight_init_fn = partial(init_transformer_weights, initializer_range=initializer_range)
         self.apply(weight_init_fn)
 
-    @torch.no_grad()
     def forward(self, pixel_values: Optional[Tensor] = None, image_patches_mask: Optional[Tensor] = None,
                 attention_mask: Optional[Tensor] = None) -> TransformerOutput:
         if pixel_values is None:
@@ -79,7 +78,14 @@ class ImageTransformer(_RuntimeOwner):
                 f"Input image size ({height}*{width}) doesn't match model ({pe.image_size[0]}*{pe.image_size[1]}).")
         if image_patches_mask is not None and self.embeddings.mask_token is None:
             warnings.warn("image_patches_mask passed but use_image_masking in init was false. Ignoring.")
-        return self._runtime().forward(pixel_values, image_patches_mask, want_attn=bool(getattr(self, "output_attentions", False)))
+        from ... import engine_flava_train as T
+        if T.wants_grad(self):   # training: forward keeps activations, autograd nodes carry the explicit backward
+            if getattr(self, "output_attentions", False):
+                raise NotImplementedError("attention probabilities are not produced by the training forward")
+            return T.encoder_output(self._train_runtime(), (pixel_values, image_patches_mask), (), self.pooler)
+        with torch.no_grad():
+            return self._runtime().forward(pixel_values, image_patches_mask,
+                                           want_attn=bool(getattr(self, "output_attentions", False)))
 
 
 def _img_runtime(mod):
@@ -87,7 +93,13 @@ def _img_runtime(mod):
     return FlavaImageRuntime(mod)
 
 
+def _img_train_runtime(mod):
+    from ...engine_flava_train import FlavaImageTrainRuntime
+    return FlavaImageTrainRuntime(mod)
+
+
 ImageTransformer._runtime_cls = staticmethod(_img_runtime)
+ImageTransformer._train_runtime_cls = staticmethod(_img_train_runtime)
 
 
 def flava_image_encoder(hidden_size: int = 768, num_attention_heads: int = 12, num_hidden_layers: int = 12,

@@ -54,7 +54,6 @@ class FLAVAModel(nn.Module):
         self.text_projection = text_projection
         self.image_projection = image_projection
 
-    @torch.no_grad()
     def forward(self, image: Optional[Tensor] = None, text: Optional[Tensor] = None,
                 image_patches_mask: Optional[Tensor] = None, text_masked: Optional[Tensor] = None,
                 required_embedding: Optional[str] = None, skip_unmasked_mm_encoder: bool = True) -> FLAVAOutput:
@@ -112,7 +111,6 @@ class FLAVAModel(nn.Module):
                            projected_image_embeddings=projected_image_embeddings,
                            projected_text_embeddings=projected_text_embeddings)
 
-    @torch.no_grad()
     def encode_image(self, image: Tensor, image_patches_mask: Optional[Tensor] = None, projection: bool = False
                      ) -> Union[Tuple[TransformerOutput, Tensor], Optional[TransformerOutput]]:
         if image_patches_mask is not None:
@@ -134,7 +132,6 @@ class FLAVAModel(nn.Module):
                 enc.output_attentions = bool(flag)
         return self
 
-    @torch.no_grad()
     def encode_text(self, text: Tensor, text_mask: Optional[Tensor] = None, projection: bool = False
                     ) -> Union[Tuple[TransformerOutput, Tensor], Optional[TransformerOutput]]:
         encoded_text = self.text_encoder(input_ids=text, attention_mask=text_mask,
@@ -147,7 +144,11 @@ class FLAVAModel(nn.Module):
 
     @staticmethod
     def _project_cls(encoder: nn.Module, out: TransformerOutput, linear: nn.Module, key: str) -> Tensor:
-        return encoder._runtime().stack.project_first_token(out.last_hidden_state, linear, key)
+        from ... import engine_flava_train as T
+        if torch.is_grad_enabled() and (out.last_hidden_state.requires_grad or T.wants_grad(linear)):
+            return T.first_token_linear(out.last_hidden_state, linear)
+        with torch.no_grad():
+            return encoder._runtime().stack.project_first_token(out.last_hidden_state, linear, key)
 
     def _encode_data_to_embeddings(self, data: Optional[Tensor], selected_head_encoder: str, encoder_options: List[str],
                                    encode_callable: Callable[..., Any]) -> Any:
@@ -156,13 +157,17 @@ class FLAVAModel(nn.Module):
             output = encode_callable(data)
         return output
 
-    @torch.no_grad()
     def encode_mm(self, image_embedding: Tensor, text_embedding: Tensor) -> TransformerOutput:
         if image_embedding is None or text_embedding is None:
             return TransformerOutput()
-        return self.mm_encoder._runtime().forward_projected(
-            image_embedding, text_embedding, self.image_to_mm_projection, self.text_to_mm_projection,
-            want_attn=bool(getattr(self.mm_encoder, "output_attentions", False)))
+        from ... import engine_flava_train as T
+        enc, ip, tp = self.mm_encoder, self.image_to_mm_projection, self.text_to_mm_projection
+        if T.wants_grad(enc, ip, tp) or (torch.is_grad_enabled() and
+                                          (image_embedding.requires_grad or text_embedding.requires_grad)):
+            return T.encoder_output(enc._train_runtime(ip, tp), None, (image_embedding, text_embedding), enc.pooler)
+        with torch.no_grad():
+            return enc._runtime().forward_projected(
+                image_embedding, text_embedding, ip, tp, want_attn=bool(getattr(enc, "output_attentions", False)))
 
 
 class FLAVAForPreTraining(nn.Module):

@@ -3,7 +3,7 @@
 
 Same constructors, state-dict keys (``layer.{i}.attention.{query,key,value,output}``, ``feedforward.model.{0,2}``,
 ``attention_layernorm``, ``feedforward_layernorm``) and initialisation order.  The layers themselves never run as torch
-modules: the owning encoder hands the whole stack to ``engine_flava.FlavaStack`` (forward only).
+modules: the owning encoder hands the whole stack to ``engine_flava.FlavaStack`` (inference) or ``engine_flava_train`` (forward + backward under autograd).
 """
 from functools import partial
 from typing import Any, Callable, Optional
@@ -82,6 +82,16 @@ class _RuntimeOwner(nn.Module):
             object.__setattr__(self, "_rt_ids", ids)
         return self._rt
 
+    def _train_runtime(self, *extra: Optional[nn.Module]):
+        """The training runtime (engine_flava_train): forward that keeps activations + explicit backward.  `extra`:
+        modules outside this encoder whose parameters its fused front end owns (the multimodal projections)."""
+        mods = [m for m in extra if m is not None]
+        ids = [(id(p), p.device) for m in (self, *mods) for p in m.parameters()]
+        if getattr(self, "_trt", None) is None or self._trt_ids != ids:
+            object.__setattr__(self, "_trt", type(self)._train_runtime_cls(self, *extra))
+            object.__setattr__(self, "_trt_ids", ids)
+        return self._trt
+
 
 class FLAVATransformerWithoutEmbeddings(_RuntimeOwner):
     """The multimodal encoder (transformer.py:18-77): [cls | hidden_states] -> L layers -> layernorm -> pooler."""
@@ -101,13 +111,16 @@ class FLAVATransformerWithoutEmbeddings(_RuntimeOwner):
             weight_init_fn = partial(init_transformer_weights, initializer_range=initializer_range)
         self.apply(weight_init_fn)
 
-    @torch.no_grad()
     def forward(self, hidden_states: Optional[Tensor] = None, attention_mask: Optional[Tensor] = None) -> TransformerOutput:
         if hidden_states is None:
             raise ValueError("You have to specify hidden_states")
         if attention_mask is not None:
             raise NotImplementedError("attention_mask on the multimodal encoder is not on the accelerated path")
-        return self._runtime().forward(hidden_states, want_attn=bool(getattr(self, "output_attentions", False)))
+        from ... import engine_flava_train as T
+        if T.wants_grad(self) or (torch.is_grad_enabled() and hidden_states.requires_grad):
+            return T.encoder_output(self._train_runtime(None, None), None, (hidden_states,), self.pooler)
+        with torch.no_grad():
+            return self._runtime().forward(hidden_states, want_attn=bool(getattr(self, "output_attentions", False)))
 
 
 def _mm_runtime(mod):
@@ -115,4 +128,10 @@ def _mm_runtime(mod):
     return FlavaMMRuntime(mod)
 
 
+def _mm_train_runtime(mod, image_proj=None, text_proj=None):
+    from ...engine_flava_train import FlavaMMTrainRuntime
+    return FlavaMMTrainRuntime(mod, image_proj, text_proj)
+
+
 FLAVATransformerWithoutEmbeddings._runtime_cls = staticmethod(_mm_runtime)
+FLAVATransformerWithoutEmbeddings._train_runtime_cls = staticmethod(_mm_train_runtime)

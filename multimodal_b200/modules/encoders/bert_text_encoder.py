@@ -27,7 +27,6 @@ class BERTTextEncoder(_RuntimeOwner):
         if weight_init_fn:
             self.apply(weight_init_fn)
 
-    @torch.no_grad()
     def forward(self, input_ids: Optional[Tensor] = None, attention_mask: Optional[Tensor] = None,
                 token_type_ids: Optional[Tensor] = None, position_ids: Optional[Tensor] = None,
                 inputs_embeds: Optional[Tensor] = None, return_attn_weights: bool = False,
@@ -38,7 +37,15 @@ class BERTTextEncoder(_RuntimeOwner):
             raise NotImplementedError("inputs_embeds / position_ids are not on the accelerated path")
         if self.layernorm is None:
             raise NotImplementedError("BERTTextEncoder without a final layernorm is not on the accelerated path")
-        out = self._runtime().forward(input_ids, attention_mask, token_type_ids, want_attn=bool(return_attn_weights))
+        from ... import engine_flava_train as T
+        if T.wants_grad(self):   # training: forward keeps activations, autograd nodes carry the explicit backward
+            if return_attn_weights:
+                raise NotImplementedError("attention probabilities are not produced by the training forward")
+            out = T.encoder_output(self._train_runtime(), (input_ids, attention_mask, token_type_ids), (), self.pooler)
+        else:
+            with torch.no_grad():
+                out = self._runtime().forward(input_ids, attention_mask, token_type_ids,
+                                              want_attn=bool(return_attn_weights))
         if not return_hidden_states:
             out = out._replace(hidden_states=None)
         return out
@@ -49,7 +56,13 @@ def _txt_runtime(mod):
     return FlavaTextRuntime(mod)
 
 
+def _txt_train_runtime(mod):
+    from ...engine_flava_train import FlavaTextTrainRuntime
+    return FlavaTextTrainRuntime(mod)
+
+
 BERTTextEncoder._runtime_cls = staticmethod(_txt_runtime)
+BERTTextEncoder._train_runtime_cls = staticmethod(_txt_train_runtime)
 
 
 def bert_text_encoder(hidden_size: int = 768, num_hidden_layers: int = 6, num_attention_heads: int = 12,

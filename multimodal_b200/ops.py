@@ -431,3 +431,60 @@ def ce_labels(logits, labels, label_stride, ignore_index, M, V, row_loss, accum)
     _chk(logits, torch.float32, "logits"); _chk(labels, torch.int64, "labels"); _rowmajor(logits, "logits")
     _lib.check(_lib.lib().mmb_ce_labels(_p(logits), logits.stride(0), _p(labels), int(label_stride), int(ignore_index), M,
                                         V, _p(row_loss), _p(accum), _stream()), "mmb_ce_labels")
+
+
+# ---- FLAVA / CoCa backward helpers ------------------------------------------------------------------------------
+def attention_bwd_kmask(qkv, out, dout, lse, dqkv, kmask, B, S, H, causal, scale):
+    _chk(qkv, torch.bfloat16, "qkv"); _chk(kmask, torch.uint8, "kmask")
+    with _timed("attn_bwd", 10.0 * S * S * 64 * H * B, "F"):
+        _lib.check(_lib.lib().mmb_attention_bwd_kmask(_p(qkv), _p(out), _p(dout), _p(lse), _p(dqkv), _p(kmask), B, S, H, 64,
+                                                      int(causal), float(scale), _stream()), "mmb_attention_bwd_kmask")
+
+
+def bert_embed_ln_bwd(ids, type_ids, word, pos, type_emb, gamma, dy, dword, dpos, dtype_emb, dgamma, dbeta, B, S, d, V, eps):
+    _chk(ids, torch.int64, "ids"); _chk(dy, torch.float32, "dy")
+    _lib.check(_lib.lib().mmb_bert_embed_ln_bwd(_p(ids), _p(type_ids), _p(word), _p(pos), _p(type_emb), _p(gamma), _p(dy),
+                                                _p(dword), _p(dpos), _p(dtype_emb), _p(dgamma), _p(dbeta), B, S, d, V,
+                                                float(eps), _stream()), "mmb_bert_embed_ln_bwd")
+
+
+def vit_assemble_bwd(g, patch_mask, dpatch, dmask_token, B, S, d, has_cls=True):
+    _chk(g, torch.float32, "g"); _chk(dpatch, torch.bfloat16, "dpatch")
+    _lib.check(_lib.lib().mmb_vit_assemble_bwd(_p(g), _p(patch_mask), _p(dpatch), _p(dmask_token), B, S, d, int(has_cls),
+                                               _stream()), "mmb_vit_assemble_bwd")
+
+
+def split_tokens_cast(g, a, b, B, Sa, Sb, d, has_cls=True):
+    _chk(g, torch.float32, "g")
+    _lib.check(_lib.lib().mmb_split_tokens_cast(_p(g), _p(a), _p(b), B, Sa, Sb, d, int(has_cls), _stream()),
+               "mmb_split_tokens_cast")
+
+
+def tanh_bwd(dy, y, dx=None, dx_bf16=None):
+    _chk(dy, torch.float32, "dy"); _chk(y, torch.float32, "y")
+    if not (dy.is_contiguous() and y.is_contiguous()) or dy.numel() != y.numel():
+        raise MMBError("tanh_bwd: contiguous tensors of equal size expected")
+    _lib.check(_lib.lib().mmb_tanh_bwd(_p(dy), _p(y), _p(dx), _p(dx_bf16), y.numel(), _stream()), "mmb_tanh_bwd")
+
+
+def scatter_rows_add(src, dst, B, rows_per_group, row, d):
+    _chk(src, torch.float32, "src"); _chk(dst, torch.float32, "dst")
+    _lib.check(_lib.lib().mmb_scatter_rows_add(_p(src), _p(dst), B, rows_per_group, row, d, _stream()),
+               "mmb_scatter_rows_add")
+
+
+def scatter_rows_idx_add(src, idx, dst, d):
+    """dst2d[idx[m], :] += src[m, :]; dst fp32 viewed as rows of `d` elements with row pitch dst.stride(-2)."""
+    _chk(src, torch.float32, "src"); _chk(idx, torch.int64, "idx"); _chk(dst, torch.float32, "dst")
+    if not src.is_contiguous() or not idx.is_contiguous() or dst.stride(-1) != 1:
+        raise MMBError("scatter_rows_idx_add: contiguous src / idx and unit inner stride of dst expected")
+    _lib.check(_lib.lib().mmb_scatter_rows_idx_add(_p(src), _p(idx), _p(dst), dst.stride(-2), idx.numel(), d, _stream()),
+               "mmb_scatter_rows_idx_add")
+
+
+def ce_labels_bwd(logits, labels, label_stride, ignore_index, M, V, accum, grad_scale, dlogits):
+    _chk(logits, torch.float32, "logits"); _chk(labels, torch.int64, "labels"); _chk(dlogits, torch.bfloat16, "dlogits")
+    _rowmajor(logits, "logits"); _rowmajor(dlogits, "dlogits")
+    _lib.check(_lib.lib().mmb_ce_labels_bwd(_p(logits), logits.stride(0), _p(labels), int(label_stride), int(ignore_index),
+                                            M, V, _p(accum), float(grad_scale), _p(dlogits), dlogits.stride(0), _stream()),
+               "mmb_ce_labels_bwd")

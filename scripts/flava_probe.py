@@ -21,6 +21,7 @@ def log(*a):
     lines.append(s)
 
 
+@torch.no_grad()   # inference runtime (with grad mode on, trainable modules take the training runtime)
 def main():
     dev = torch.device("cuda:0")
     gold = torch.load(os.path.join(ROOT, "tests", "golden", "flava_golden.pt"))

@@ -1,0 +1,281 @@
+"""TEST INFRASTRUCTURE ONLY: torch (CPU) emulation of the C-ABI kernels' CONTRACTS, as documented in include/mmb200.h.
+
+Purpose: the host-side schedules (engine.py / engine_flava_train.py: which buffer goes to which kernel, in which order,
+which gradient slot accumulates what) are plain Python and can be checked without a GPU by swapping `multimodal_b200.ops`
+entry points for these functions (``install(monkeypatch)``) and comparing the result with autograd over the oracle.
+The emulation keeps the kernels' storage types (bf16 tensors are rounded exactly where the kernels round) and fp32
+arithmetic; it is never imported by the package and is not a fallback — the product raises without the CUDA library.
+"""
+import math
+
+import torch
+
+BF, F32 = torch.bfloat16, torch.float32
+EPI_BF16, EPI_BF16_ACT, EPI_BF16_DACT, EPI_F32 = 0, 1, 2, 3
+
+
+def _act(x, kind):
+    return x * torch.sigmoid(1.702 * x) if kind == 0 else torch.nn.functional.gelu(x)
+
+
+def _act_grad(x, kind):
+    if kind == 0:
+        s = torch.sigmoid(1.702 * x)
+        return s * (1 + 1.702 * x * (1 - s))
+    return 0.5 * (1 + torch.erf(x / math.sqrt(2))) + x * torch.exp(-0.5 * x * x) / math.sqrt(2 * math.pi)
+
+
+def gemm(A, B, *, a_mn=False, b_mn=False, epilogue=EPI_BF16, out=None, out2=None, bias=None, aux=None, alpha=1.0,
+         act=0, splits=1, accumulate=False, colsum=None):
+    assert A.dtype == BF and B.dtype == BF
+    Af = A.float().t() if a_mn else A.float()
+    Bf = B.float().t() if b_mn else B.float()
+    assert Af.shape[1] == Bf.shape[1], (Af.shape, Bf.shape)
+    acc = alpha * (Af @ Bf.t())
+    M, N = acc.shape
+    if bias is not None:
+        assert bias.dtype == F32 and bias.numel() == N
+        acc = acc + bias.detach().view(1, N)
+    odt = F32 if epilogue == EPI_F32 else BF
+    if out is None:
+        out = torch.empty((M, N), dtype=odt)
+    assert out.dtype == odt and tuple(out.shape) == (M, N), (out.dtype, out.shape, (M, N))
+    if epilogue == EPI_F32:
+        out.copy_(out + acc if accumulate else acc)
+        return out
+    assert not accumulate
+    if epilogue == EPI_BF16:
+        out.copy_(acc.to(BF))
+        return out
+    if epilogue == EPI_BF16_ACT:
+        if out2 is None:
+            out2 = torch.empty((M, N), dtype=BF)
+        out.copy_(acc.to(BF))
+        out2.copy_(_act(out.float(), act).to(BF))
+        return out, out2
+    assert epilogue == EPI_BF16_DACT and aux is not None and aux.dtype == BF
+    res = (acc * _act_grad(aux.float(), act)).to(BF)
+    out.copy_(res)
+    if colsum is not None:
+        colsum.add_(res.float().sum(0))
+    return out
+
+
+def cast_bf16(src, out=None):
+    assert src.dtype == F32
+    if out is None:
+        out = torch.empty(src.shape, dtype=BF)
+    out.copy_(src.detach().to(BF).view(out.shape))
+    return out
+
+
+def zero_(t):
+    t.zero_()
+    return t
+
+
+def im2col(img, ps, out):
+    B, C, H, W = img.shape
+    cols = torch.nn.functional.unfold(img, kernel_size=ps, stride=ps)      # [B, C*ps*ps, P]
+    out.copy_(cols.transpose(1, 2).reshape(-1, C * ps * ps).to(BF))
+    return out
+
+
+def _ln_rows(x, gamma, beta, eps):
+    mean = x.mean(-1, keepdim=True)
+    var = ((x - mean) ** 2).mean(-1, keepdim=True)
+    rstd = torch.rsqrt(var + eps)
+    return (x - mean) * rstd * gamma.detach() + beta.detach(), mean.squeeze(-1), rstd.squeeze(-1)
+
+
+def add_layernorm_fwd(x_in, y, x_out, ln_bf16, ln_f32, gamma, beta, mean, rstd, M, d, eps, row_idx=None,
+                      rows_per_group=0):
+    if rows_per_group > 0:
+        phys = torch.arange(M) * rows_per_group + (row_idx.long() if row_idx is not None else 0)
+    else:
+        phys = torch.arange(M)
+    x = torch.zeros(M, d)
+    if x_in is not None:
+        x = x + x_in.detach().reshape(-1, d)[phys]
+    if y is not None:
+        x = x + y.reshape(-1, d)[phys].float()
+    out, m, r = _ln_rows(x, gamma, beta, eps)
+    if x_out is not None:
+        x_out.view(-1, d)[:M].copy_(x)
+    if ln_bf16 is not None:
+        ln_bf16.view(-1, d)[:M].copy_(out.to(BF))
+    if ln_f32 is not None:
+        ln_f32.view(-1, d)[:M].copy_(out)
+    if mean is not None:
+        mean.copy_(m)
+    if rstd is not None:
+        rstd.copy_(r)
+
+
+def layernorm_bwd(x, dy_bf16, dy_f32, mean, rstd, gamma, g_in, g_out, g_bf16, dgamma, dbeta, M, d, row_idx=None,
+                  rows_per_group=0, gsum=None):
+    assert (dy_bf16 is None) != (dy_f32 is None)
+    if rows_per_group > 0:
+        phys = torch.arange(M) * rows_per_group + (row_idx.long() if row_idx is not None else 0)
+    else:
+        phys = torch.arange(M)
+    xx = x.detach().reshape(-1, d)[:M]
+    dy = (dy_bf16.float() if dy_bf16 is not None else dy_f32).reshape(-1, d)[:M]
+    h = (xx - mean.view(M, 1)) * rstd.view(M, 1)
+    if dgamma is not None:
+        dgamma.add_((dy * h).sum(0))
+    if dbeta is not None:
+        dbeta.add_(dy.sum(0))
+    dyg = dy * gamma.detach()
+    dx = rstd.view(M, 1) * (dyg - dyg.mean(-1, keepdim=True) - h * (dyg * h).mean(-1, keepdim=True))
+    if g_in is not None:
+        dx = dx + g_in.reshape(-1, d)[phys]
+    if g_out is not None:
+        g_out.view(-1, d)[phys] = dx
+    if g_bf16 is not None:
+        gb = dx.to(BF)
+        g_bf16.view(-1, d)[phys] = gb
+        if gsum is not None:
+            gsum.add_(gb.float().sum(0))
+
+
+def batch_sum(inp, out, Bn, ld, n):
+    flat = inp.detach().reshape(-1)
+    rows = torch.stack([flat[b * ld:b * ld + n] for b in range(Bn)])
+    out.view(-1)[:n].add_(rows.sum(0))
+
+
+def colsum_bf16(x, out, M, N, ld):
+    assert x.dtype == BF
+    out.view(-1)[:N].add_(x.reshape(-1, ld)[:M, :N].float().sum(0))
+
+
+def _attn(qkv, B, S, H, causal, scale, kmask):
+    d = H * 64
+    q, k, v = (t.reshape(B, S, H, 64).transpose(1, 2) for t in qkv.float().view(B, S, 3 * d).split(d, dim=-1))
+    s = (q @ k.transpose(-1, -2)) * scale
+    if causal:
+        s = s + torch.full((S, S), float("-inf")).triu(1)
+    if kmask is not None:
+        s = s.masked_fill(~kmask.view(B, 1, 1, S).bool(), float("-inf"))
+    return q, k, v, s
+
+
+def attention_fwd(qkv, out, lse, B, S, H, causal, scale, kmask=None):
+    q, k, v, s = _attn(qkv, B, S, H, causal, scale, kmask)
+    out.copy_((torch.softmax(s, -1) @ v).transpose(1, 2).reshape(B * S, H * 64).to(BF))
+    if lse is not None:
+        lse.copy_(torch.logsumexp(s, -1).reshape(-1))
+
+
+def attention_fwd_kmask(qkv, out, lse, kmask, B, S, H, causal, scale):
+    attention_fwd(qkv, out, lse, B, S, H, causal, scale, kmask)
+
+
+def attention_bwd(qkv, out, dout, lse, dqkv, B, S, H, causal, scale, kmask=None):
+    qf = qkv.float().requires_grad_(True)
+    with torch.enable_grad():
+        _, _, v, s = _attn(qf, B, S, H, causal, scale, kmask)
+        o = (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(B * S, H * 64)
+        o.backward(dout.float())
+    dqkv.copy_(qf.grad.to(BF))
+
+
+def attention_bwd_kmask(qkv, out, dout, lse, dqkv, kmask, B, S, H, causal, scale):
+    attention_bwd(qkv, out, dout, lse, dqkv, B, S, H, causal, scale, kmask)
+
+
+def vit_assemble_fwd(patch_out, cls, pos, mask_token, patch_mask, x, B, S, d):
+    off = 1 if cls is not None else 0
+    P = S - off
+    e = patch_out.float().view(B, P, d)
+    if patch_mask is not None and mask_token is not None:
+        e = torch.where(patch_mask.view(B, P, 1).bool(), mask_token.detach().view(1, 1, d).expand(B, P, d), e)
+    if cls is not None:
+        e = torch.cat([cls.detach().view(1, 1, d).expand(B, 1, d), e], 1)
+    x.view(B, S, d).copy_(e + pos.detach().view(1, S, d))
+
+
+def vit_assemble_bwd(g, patch_mask, dpatch, dmask_token, B, S, d, has_cls=True):
+    off = 1 if has_cls else 0
+    P = S - off
+    gp = g.view(B, S, d)[:, off:]
+    if patch_mask is not None:
+        m = patch_mask.view(B, P, 1).bool()
+        if dmask_token is not None:
+            dmask_token.view(-1).add_((gp * m).sum((0, 1)))
+        gp = torch.where(m, torch.zeros_like(gp), gp)
+    dpatch.copy_(gp.reshape(B * P, d).to(BF))
+
+
+def bert_embed_ln_fwd(ids, type_ids, word, pos, type_emb, gamma, beta, x, kmask_out, pad_id, B, S, d, V, eps):
+    tt = type_ids if type_ids is not None else torch.zeros_like(ids)
+    e = word.detach()[ids] + pos.detach()[:S][None] + type_emb.detach()[tt]
+    out, _, _ = _ln_rows(e, gamma, beta, eps)
+    x.view(B, S, d).copy_(out)
+    if kmask_out is not None:
+        kmask_out.copy_((ids != pad_id).to(torch.uint8).view(-1))
+
+
+def bert_embed_ln_bwd(ids, type_ids, word, pos, type_emb, gamma, dy, dword, dpos, dtype_emb, dgamma, dbeta, B, S, d, V, eps):
+    tt = type_ids if type_ids is not None else torch.zeros_like(ids)
+    w, p, t, g = (z.detach().clone().requires_grad_(True) for z in (word, pos, type_emb, gamma))
+    b = torch.zeros(d, requires_grad=True)
+    with torch.enable_grad():
+        out = torch.nn.functional.layer_norm(w[ids] + p[:S][None] + t[tt], (d,), g, b, eps)
+        out.backward(dy.view(B, S, d))
+    for dst, src in ((dword, w), (dpos, p), (dtype_emb, t), (dgamma, g), (dbeta, b)):
+        if dst is not None:
+            dst.add_(src.grad)
+
+
+def concat_tokens(cls, a, b, out, B, Sa, Sb, d):
+    parts = []
+    if cls is not None:
+        parts.append(cls.detach().view(1, 1, d).expand(B, 1, d))
+    parts.append(a.detach().reshape(B, -1, d)[:, :Sa])
+    if Sb:
+        parts.append(b.detach().reshape(B, Sb, d))
+    out.view(B, -1, d).copy_(torch.cat(parts, 1))
+
+
+def split_tokens_cast(g, a, b, B, Sa, Sb, d, has_cls=True):
+    off = 1 if has_cls else 0
+    gv = g.view(B, off + Sa + Sb, d)
+    if a is not None and Sa:
+        a.copy_(gv[:, off:off + Sa].reshape(-1, d).to(BF))
+    if b is not None and Sb:
+        b.copy_(gv[:, off + Sa:].reshape(-1, d).to(BF))
+
+
+def gather_rows_cast(x, out, B, rows_per_group, row, d):
+    out.copy_(x.detach().view(B, rows_per_group, d)[:, row].to(BF))
+
+
+def tanh_(x):
+    return x.tanh_()
+
+
+def tanh_bwd(dy, y, dx=None, dx_bf16=None):
+    v = dy * (1 - y * y)
+    if dx is not None:
+        dx.copy_(v)
+    if dx_bf16 is not None:
+        dx_bf16.copy_(v.to(BF))
+
+
+def scatter_rows_add(src, dst, B, rows_per_group, row, d):
+    dst.view(B, rows_per_group, d)[:, row] += src
+
+
+NAMES = [n for n, f in list(globals().items()) if callable(f) and not n.startswith("_") and n not in ("install",)]
+
+
+def install(monkeypatch):
+    """Swap the kernel wrappers of multimodal_b200.ops for the emulation and lift the CUDA-device guard."""
+    from multimodal_b200 import engine, ops
+
+    for n in NAMES:
+        if hasattr(ops, n):
+            monkeypatch.setattr(ops, n, globals()[n])
+    monkeypatch.setattr(engine, "_require_cuda", lambda dev: None)

@@ -22,6 +22,14 @@ def dev():
     return torch.device("cuda:0")
 
 
+@pytest.fixture(autouse=True)
+def _inference():
+    """This file pins the INFERENCE runtime (engine_flava.py); with grad mode on, trainable modules take the training
+    runtime instead (engine_flava_train.py, covered by tests/test_gpu_flava_train.py)."""
+    with torch.no_grad():
+        yield
+
+
 def _close(got, ref, name, tol=2e-2):
     got, ref = got.float().cpu(), ref.float().cpu()
     assert got.shape == ref.shape, (name, got.shape, ref.shape)

@@ -1,0 +1,323 @@
+"""GPU parity of the FLAVA encoders' BACKWARD (BASELINE.json config 3 as a training step): every kernel added for it
+against torch autograd of the same op, and every parameter gradient of `FLAVAModel.forward` against autograd over the
+fp32 oracle (oracle/flava_oracle.py, the restatement pinned to the reference goldens) on the same GPU.
+
+Tolerance: GEMM operands (activations, weights, gradients) are rounded to bf16 with fp32 accumulation, fp32 residual
+stream / LayerNorm / softmax statistics; a parameter-gradient tensor must agree with the fp32 oracle to a relative L2
+error below 6e-2 (d = 128 toy widths, B = 3: few rows per reduction, so the rounding noise does not average out as in
+the full-size CLIP test where the same kernels measure 1.6e-2) and cosine > 0.995.  A wrong mask, a dropped tile or a
+mis-routed gradient moves a tensor to O(1).  `key.bias` gradients are exactly zero in exact arithmetic (softmax is
+shift-invariant); they are checked against the size of the matching `query.bias` gradient instead.
+"""
+import math
+import os
+
+import pytest
+import torch
+
+import flava_cases as FC
+from oracle import flava_oracle as FO
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(autouse=True)
+def _no_tf32():
+    old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    yield
+    torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+
+
+def _rel(a, b):
+    return ((a.float() - b.float()).norm() / b.float().norm().clamp_min(1e-30)).item()
+
+
+@pytest.mark.parametrize("B,S,H", [(3, 12, 2), (4, 77, 12), (2, 256, 4), (2, 200, 3), (40, 77, 12), (3, 130, 2)])
+def test_attention_bwd_key_padding_mask(dev, B, S, H):
+    from multimodal_b200 import ops
+
+    torch.manual_seed(2)
+    d = 64 * H
+    qkv = (torch.randn(B * S, 3 * d, device=dev) * 0.7).bfloat16()
+    lens = torch.randint(1, S + 1, (B,), device=dev)
+    lens[0] = S
+    km = (torch.arange(S, device=dev)[None] < lens[:, None])
+    km[-1, 0] = False   # a hole that is not right padding
+    km[-1, -1] = True
+    kmf = km.to(torch.uint8).contiguous().view(-1)
+    out = torch.empty(B * S, d, device=dev, dtype=torch.bfloat16)
+    lse = torch.empty(B * H * S, device=dev)
+    ops.attention_fwd_kmask(qkv, out, lse, kmf, B, S, H, False, 0.125)
+    qf = qkv.float().requires_grad_(True)
+    q, k, v = (t.view(B, S, H, 64).transpose(1, 2) for t in qf.view(B, S, 3 * d).split(d, dim=-1))
+    s = (q @ k.transpose(-1, -2)) * 0.125
+    s = s.masked_fill(~km[:, None, None, :], float("-inf"))
+    ref = (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(B * S, d)
+    dout = (torch.randn(B * S, d, device=dev) * 0.5).bfloat16()
+    ref.backward(dout.float())
+    dqkv = torch.full_like(qkv, float("nan"))
+    ops.attention_bwd_kmask(qkv, out, dout, lse, dqkv, kmf, B, S, H, False, 0.125)
+    assert torch.isfinite(dqkv.float()).all()
+    assert _rel(dqkv, qf.grad) < 1e-2
+    # masked keys: exactly zero dK / dV rows
+    g = dqkv.float().view(B, S, 3, d)
+    assert g[:, :, 1:][~km].abs().max().item() == 0.0
+
+
+def test_flava_backward_helper_kernels(dev):
+    from multimodal_b200 import ops
+
+    torch.manual_seed(0)
+    F = torch.nn.functional
+    # ---- BERT embeddings + LayerNorm backward
+    B, S, d, V = 5, 13, 256, 50
+    ids = torch.randint(0, V, (B, S), device=dev)
+    tt = torch.randint(0, 2, (B, S), device=dev)
+    word = torch.randn(V, d, device=dev, requires_grad=True)
+    pos = torch.randn(32, d, device=dev, requires_grad=True)
+    typ = torch.randn(2, d, device=dev, requires_grad=True)
+    gam = torch.randn(d, device=dev, requires_grad=True)
+    bet = torch.randn(d, device=dev, requires_grad=True)
+    dy = torch.randn(B * S, d, device=dev)
+    ref = F.layer_norm(word[ids] + pos[:S][None] + typ[tt], (d,), gam, bet, 1e-12)
+    ref.backward(dy.view(B, S, d))
+    dw, dp, dt = torch.zeros(V, d, device=dev), torch.zeros(32, d, device=dev), torch.zeros(2, d, device=dev)
+    dg, db = torch.zeros(d, device=dev), torch.zeros(d, device=dev)
+    ops.bert_embed_ln_bwd(ids, tt, word.detach(), pos.detach(), typ.detach(), gam.detach(), dy, dw, dp, dt, dg, db, B, S, d,
+                          V, 1e-12)
+    for got, want, name in ((dw, word.grad, "word"), (dp, pos.grad, "pos"), (dt, typ.grad, "type"), (dg, gam.grad, "gamma"),
+                            (db, bet.grad, "beta")):
+        torch.testing.assert_close(got, want, rtol=2e-4, atol=2e-4, msg=name)
+    # accumulation (+=) and default token types
+    ops.bert_embed_ln_bwd(ids, None, word.detach(), pos.detach(), typ.detach(), gam.detach(), dy, dw, None, None, None, None,
+                          B, S, d, V, 1e-12)
+    assert torch.isfinite(dw).all()
+    # ---- token assembly backward (mask-token substitution)
+    P = S - 1
+    g = torch.randn(B, S, d, device=dev)
+    pm = torch.rand(B, P, device=dev) < 0.5
+    dpatch = torch.full((B * P, d), float("nan"), device=dev, dtype=torch.bfloat16)
+    dmask = torch.zeros(d, device=dev)
+    ops.vit_assemble_bwd(g, pm.to(torch.uint8).contiguous(), dpatch, dmask, B, S, d, True)
+    want = torch.where(pm[..., None], torch.zeros_like(g[:, 1:]), g[:, 1:]).reshape(B * P, d).bfloat16()
+    assert torch.equal(dpatch, want)
+    torch.testing.assert_close(dmask, (g[:, 1:] * pm[..., None]).sum((0, 1)), rtol=1e-5, atol=1e-4)
+    dpatch2 = torch.empty_like(dpatch)
+    ops.vit_assemble_bwd(g, None, dpatch2, None, B, S, d, True)
+    assert torch.equal(dpatch2, g[:, 1:].reshape(B * P, d).bfloat16())
+    # ---- concat inverse
+    Sa, Sb = 4, 6
+    g2 = torch.randn(B, 1 + Sa + Sb, d, device=dev)
+    a = torch.empty(B * Sa, d, device=dev, dtype=torch.bfloat16)
+    b = torch.empty(B * Sb, d, device=dev, dtype=torch.bfloat16)
+    ops.split_tokens_cast(g2, a, b, B, Sa, Sb, d, True)
+    assert torch.equal(a, g2[:, 1:1 + Sa].reshape(-1, d).bfloat16())
+    assert torch.equal(b, g2[:, 1 + Sa:].reshape(-1, d).bfloat16())
+    # ---- tanh backward, row scatters
+    y = torch.tanh(torch.randn(B, d, device=dev))
+    dyy = torch.randn(B, d, device=dev)
+    dx, dxb = torch.empty(B, d, device=dev), torch.empty(B, d, device=dev, dtype=torch.bfloat16)
+    ops.tanh_bwd(dyy, y, dx, dxb)
+    torch.testing.assert_close(dx, dyy * (1 - y * y), rtol=1e-6, atol=1e-6)
+    assert torch.equal(dxb, dx.bfloat16())
+    dst = torch.randn(B * 7, d, device=dev)
+    want = dst.clone().view(B, 7, d)
+    want[:, 2] += dx
+    ops.scatter_rows_add(dx, dst, B, 7, 2, d)
+    assert torch.equal(dst.view(B, 7, d), want)
+    idx = torch.tensor([3, 0, 3, 9, 3], device=dev)
+    dst2 = torch.zeros(12, d, device=dev)
+    ops.scatter_rows_idx_add(dx, idx, dst2, d)
+    torch.testing.assert_close(dst2, torch.zeros(12, d, device=dev).index_add_(0, idx, dx), rtol=1e-6, atol=1e-6)
+    # ---- label cross-entropy backward on materialised logits
+    M, Vv = 9, 1003
+    logits = (torch.randn(M, Vv, device=dev) * 3).requires_grad_(True)
+    labels = torch.randint(0, Vv, (M,), device=dev)
+    labels[2] = -1
+    labels[7] = -1
+    loss = F.cross_entropy(logits, labels, ignore_index=-1)
+    loss.backward()
+    accum = torch.zeros(2, device=dev)
+    ops.ce_labels(logits.detach(), labels, 1, -1, M, Vv, None, accum)
+    dl = torch.empty(M, Vv + 5, device=dev, dtype=torch.bfloat16)[:, :Vv]
+    ops.ce_labels_bwd(logits.detach(), labels, 1, -1, M, Vv, accum, 1.0, dl)
+    assert _rel(dl, logits.grad) < 6e-3   # bf16 rounding of the output
+    assert dl[2].abs().max().item() == 0.0
+
+
+def _oracle_outputs(sd, cfg, inp):
+    """oracle forward of FLAVAModel (required_embedding='mm', skip_unmasked_mm_encoder=True) with autograd intact."""
+    o = {}
+    o["image"] = FO.image_encoder(inp["image"], sd, cfg)
+    o["text"] = FO.text_encoder(inp["text"], sd, cfg)
+    o["image_masked"] = FO.image_encoder(inp["image"], sd, cfg, inp["image_patches_mask"])
+    o["text_masked"] = FO.text_encoder(inp["text_masked"], sd, cfg)
+    o["multimodal_masked"] = FO.mm_encoder(o["image_masked"]["hidden_states"][-1], o["text_masked"]["hidden_states"][-1],
+                                           sd, cfg)
+    flat = {}
+    for f, t in o.items():
+        flat[f + ".last_hidden_state"] = t["last_hidden_state"]
+        flat[f + ".pooler_output"] = t["pooler_output"]
+    flat["projected_image_embeddings"] = FO._lin(o["image"]["last_hidden_state"][:, 0], sd, "image_projection")
+    flat["projected_text_embeddings"] = FO._lin(o["text"]["last_hidden_state"][:, 0], sd, "text_projection")
+    return flat
+
+
+def _model_outputs(out):
+    flat = {}
+    for f in ("image", "text", "image_masked", "text_masked", "multimodal_masked"):
+        t = getattr(out, f)
+        flat[f + ".last_hidden_state"] = t.last_hidden_state
+        flat[f + ".pooler_output"] = t.pooler_output
+    flat["projected_image_embeddings"] = out.projected_image_embeddings
+    flat["projected_text_embeddings"] = out.projected_text_embeddings
+    return flat
+
+
+def _cfg(kw):
+    return dict(patch_size=kw.get("patch_size", 16),
+                image_num_hidden_layers=kw.get("image_num_hidden_layers", 12),
+                image_num_attention_heads=kw.get("image_num_attention_heads", 12),
+                text_num_hidden_layers=kw.get("text_num_hidden_layers", 12),
+                text_num_attention_heads=kw.get("text_num_attention_heads", 12),
+                multimodal_num_hidden_layers=kw.get("multimodal_num_hidden_layers", 6),
+                multimodal_num_attention_heads=kw.get("multimodal_num_attention_heads", 12))
+
+
+def _grad_parity(dev, m, cfg, inp, tag, bar):
+    """loss = sum_k <w_k, output_k> over every differentiable output of FLAVAModel.forward, fixed random w_k."""
+    m = m.to(dev).train()
+    inp = {k: v.to(dev) for k, v in inp.items()}
+    sd = {k: v.detach().clone().requires_grad_(True) for k, v in m.state_dict().items()}
+    ref_out = _oracle_outputs(sd, cfg, inp)
+    gen = torch.Generator(device="cpu").manual_seed(9)
+    w = {k: torch.randn(v.shape, generator=gen).to(dev) / math.sqrt(v[0].numel()) for k, v in ref_out.items()}
+    loss_ref = sum((w[k] * v).sum() for k, v in ref_out.items())
+    loss_ref.backward()
+
+    out = m(image=inp["image"], text=inp["text"], image_patches_mask=inp["image_patches_mask"],
+            text_masked=inp["text_masked"])
+    got_out = _model_outputs(out)
+    for k, v in ref_out.items():   # the training forward produces the reference's values
+        assert got_out[k].requires_grad, k
+        e = (got_out[k].detach() - v.detach()).abs().max().item() / v.detach().abs().max().item()
+        assert e < 2e-2, (k, e)
+    assert out.image.hidden_states[-1].requires_grad and len(out.image.hidden_states) == cfg["image_num_hidden_layers"] + 1
+    loss = sum((w[k] * v).sum() for k, v in got_out.items())
+    assert abs(loss.item() - loss_ref.item()) < 2e-2 * max(1.0, abs(loss_ref.item()))
+    loss.backward()
+
+    rows = []
+    named = dict(m.named_parameters())
+    assert set(named) == set(sd)
+    for k, p in named.items():
+        assert p.grad is not None and torch.isfinite(p.grad).all(), k
+        ref = sd[k].grad
+        if k.endswith(".key.bias"):
+            qn = sd[k.replace(".key.bias", ".query.bias")].grad.norm().item()
+            assert p.grad.norm().item() < 0.25 * qn + 1e-6, (k, p.grad.norm().item(), qn)
+            continue
+        if k == "text_encoder.embeddings.word_embeddings.weight":
+            # nn.Embedding(padding_idx=pad_token_id) (text_embedding.py:40): the pad row receives no gradient; the
+            # oracle's plain table lookup does not model that, so its pad row is dropped from the comparison
+            pad = m.text_encoder.embeddings.pad_token_id
+            assert p.grad[pad].abs().max().item() == 0.0
+            ref = ref.clone()
+            ref[pad] = 0
+        if ref is None or ref.norm().item() == 0.0:
+            assert p.grad.abs().max().item() < 1e-6, k
+            continue
+        cos = torch.nn.functional.cosine_similarity(p.grad.flatten().float(), ref.flatten().float(), dim=0).item()
+        rows.append((k, _rel(p.grad, ref), cos))
+    errs = sorted(r[1] for r in rows)
+    report = [f"{tag}: loss ours {loss.item():.6f} oracle {loss_ref.item():.6f}; relative-L2 gradient error over {len(rows)} "
+              f"parameter tensors: median {errs[len(errs) // 2]:.3e} max {errs[-1]:.3e}"]
+    report += [f"{k:75s} rel {a:.3e} cos {c:.6f}" for k, a, c in sorted(rows, key=lambda r: -r[1])[:20]]
+    print("\n".join(report))
+    try:
+        os.makedirs("gpurun_out", exist_ok=True)
+        open(f"gpurun_out/flava_grad_parity_{tag}.txt", "w").write("\n".join(report) + "\n")
+    except OSError:
+        pass
+    for k, a, c in rows:
+        assert a < bar and c > 0.995, (k, a, c)
+    return m
+
+
+def test_flava_small_gradients_against_fp32_oracle(dev):
+    from multimodal_b200.models.flava import flava_model
+
+    name = "flava_small"
+    m = FC.build(flava_model, name)
+    m = _grad_parity(dev, m, _cfg(FC.CASES[name]["kwargs"]), FC.inputs(name), "small", 6e-2)
+    # a second step on the same module: shadows follow an in-place parameter update, saved state is per call
+    with torch.no_grad():
+        for p in m.parameters():
+            p.add_(0.01 * torch.randn_like(p))
+            p.grad = None
+    _grad_parity(dev, m, _cfg(FC.CASES[name]["kwargs"]), FC.inputs(name), "small_step2", 6e-2)
+
+
+def test_flava_base_width_gradients_against_fp32_oracle(dev):
+    """d = 768 / 12 heads, 224x224 images, 77 tokens: S = 197 / 77 / 275 as in config 3 (2 + 2 + 1 layers): the CTA-pair
+    GEMM instantiations, the fused attention backward (S = 197), the masked one (S = 77 with ragged padding) and the
+    two-pass backward (S = 275) of the multimodal encoder."""
+    from multimodal_b200.models.flava import flava_model
+
+    kw = dict(image_num_hidden_layers=2, text_num_hidden_layers=2, multimodal_num_hidden_layers=1, vocab_size=1000,
+              max_position_embeddings=128)
+    torch.manual_seed(0)
+    m = flava_model(**kw)
+    gen = torch.Generator().manual_seed(3)
+    with torch.no_grad():
+        for p in m.parameters():
+            p.add_(0.02 * torch.randn(p.shape, generator=gen))
+    B, St = 4, 77
+    image = torch.randn(B, 3, 224, 224, generator=gen)
+    text = torch.randint(1, 1000, (B, St), generator=gen)
+    text[1, 40:] = 0
+    text[3, 9:] = 0
+    tm = text.clone()
+    tm[:, 3] = 999
+    pm = torch.rand(B, 196, generator=gen) < 0.4
+    _grad_parity(dev, m, _cfg(kw), dict(image=image, text=text, text_masked=tm, image_patches_mask=pm), "base", 4e-2)
+
+
+def test_flava_mm_encoder_direct_call_and_frozen_parts(dev):
+    """`FLAVATransformerWithoutEmbeddings.forward(hidden_states)` under autograd (gradient w.r.t. its input), and a model
+    whose text encoder is frozen (requires_grad False -> inference runtime for that encoder, no gradients for it)."""
+    from multimodal_b200.models.flava import flava_model
+
+    name = "flava_small"
+    m = FC.build(flava_model, name).to(dev).train()
+    cfg = _cfg(FC.CASES[name]["kwargs"])
+    torch.manual_seed(4)
+    h = torch.randn(3, 20, 256, device=dev, requires_grad=True)
+    out = m.mm_encoder(h)
+    sd = {k: v.detach().clone().requires_grad_(True) for k, v in m.state_dict().items()}
+    hr = h.detach().clone().requires_grad_(True)
+    x = torch.cat([sd["mm_encoder.cls_token"].expand(3, -1, -1), hr], 1)
+    ref = FO.encoder_stack(x, sd, "mm_encoder", cfg["multimodal_num_hidden_layers"], cfg["multimodal_num_attention_heads"],
+                           1e-12)
+    w = torch.randn_like(ref["last_hidden_state"]) / 16
+    (ref["last_hidden_state"] * w).sum().backward()
+    (out.last_hidden_state * w).sum().backward()
+    assert _rel(h.grad, hr.grad) < 6e-2
+    assert _rel(m.mm_encoder.cls_token.grad, sd["mm_encoder.cls_token"].grad) < 6e-2
+    for p in m.parameters():
+        p.grad = None
+    for p in m.text_encoder.parameters():
+        p.requires_grad_(False)
+    inp = {k: v.to(dev) for k, v in FC.inputs(name).items()}
+    o = m(image=inp["image"], text=inp["text"])
+    assert not o.text.last_hidden_state.requires_grad and o.image.last_hidden_state.requires_grad
+    (o.projected_image_embeddings.sum() + o.projected_text_embeddings.sum()).backward()
+    assert all(p.grad is None for p in m.text_encoder.parameters())
+    assert m.text_projection.weight.grad is not None and m.image_encoder.embeddings.cls_token.grad is not None
