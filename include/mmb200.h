@@ -231,10 +231,14 @@ int mmb_scatter_rows_add(const float* src, float* dst, int B, int rows_per_group
 /* dst[idx[m]*ld : +d] += src[m, :] (atomics; idx may repeat) — gradient of mmb_gather_rows_idx_cast. */
 int mmb_scatter_rows_idx_add(const float* src, const long long* idx, float* dst, long long ld, int n, int d, void* stream);
 /* d loss / d logits (bf16) of the label-indexed mean cross-entropy of mmb_ce_labels: w * (softmax - onehot) for kept rows,
- * 0 for ignored rows, w = grad_scale / max(accum[1], 1) (accum = the forward's {sum, count}; NULL: w = grad_scale). */
+ * 0 for ignored rows, w = grad_scale * (grad_scale_dev ? *grad_scale_dev : 1) / max(accum[1], 1) (accum = the forward's
+ * {sum, count}; NULL: count 1; grad_scale_dev: the incoming d loss as a device scalar, no host sync). */
 int mmb_ce_labels_bwd(const float* logits, long long ld, const long long* labels, long long label_stride,
-                      long long ignore_index, int M, int V, const float* accum, float grad_scale, void* dlogits_bf16,
-                      long long ldd, void* stream);
+                      long long ignore_index, int M, int V, const float* accum, float grad_scale,
+                      const float* grad_scale_dev, void* dlogits_bf16, long long ldd, void* stream);
+/* dx = bf16(dy * act'(pre)), bf16 tensors of n elements; kind = ACT_QUICK_GELU (0) / ACT_GELU_ERF (1): the activation
+ * backward outside a GEMM epilogue (MaskedPredictionHead transform, modules/losses/flava.py:174-180 under autograd). */
+int mmb_act_bwd(const void* dy_bf16, const void* pre_bf16, void* dx_bf16, long long n, int kind, void* stream);
 
 /* ---- CoCa forward helpers ------------------------------------------------------------------ */
 /* x[b,s] = emb[ids[b,s]] + pos[s] (s < S-1), x[b,S-1] = cls + pos[S-1]; ids is [B, S-1] when cls != NULL, else [B, S]

@@ -65,7 +65,8 @@ PROTOTYPES = {
     "mmb_tanh_bwd": (i32, [vp, vp, vp, vp, ll, vp]),
     "mmb_scatter_rows_add": (i32, [vp, vp, i32, i32, i32, i32, vp]),
     "mmb_scatter_rows_idx_add": (i32, [vp, vp, vp, ll, i32, i32, vp]),
-    "mmb_ce_labels_bwd": (i32, [vp, ll, vp, ll, ll, i32, i32, vp, f32, vp, ll, vp]),
+    "mmb_ce_labels_bwd": (i32, [vp, ll, vp, ll, ll, i32, i32, vp, f32, vp, vp, ll, vp]),
+    "mmb_act_bwd": (i32, [vp, vp, vp, ll, i32, vp]),
 }
 
 

@@ -201,13 +201,13 @@ __global__ void scatter_rows_idx_add_kernel(const float* __restrict__ src, const
 
 // Cross-entropy backward on materialised fp32 logits (label-indexed, ignore_index; mean over kept rows):
 //   dlogits[m, v] = bf16( w * (exp(logits[m,v] - lse[m]) - [v == label[m]]) ),  w = grad_scale / max(count, 1) for kept
-//   rows and 0 for ignored rows.  lse is recomputed per row here (one CTA per row: max pass, sum pass, write pass).
+//   rows and 0 for ignored rows (grad_scale: host factor x optional device scalar).  lse is recomputed per row here (one CTA per row: max pass, sum pass, write pass).
 // (autograd of F.cross_entropy(ignore_index) in modules/losses/flava.py:143-238 and models/coca/coca_model.py:443-454)
 __global__ void __launch_bounds__(256) ce_labels_bwd_kernel(const float* __restrict__ logits, long long ld,
                                                            const long long* __restrict__ labels, long long label_stride,
                                                            long long ignore_index, int V, const float* __restrict__ accum,
-                                                           float grad_scale, __nv_bfloat16* __restrict__ dlogits,
-                                                           long long ldd) {
+                                                           float grad_scale, const float* __restrict__ gscale_dev,
+                                                           __nv_bfloat16* __restrict__ dlogits, long long ldd) {
   __shared__ float red[8];
   __shared__ float bc;
   const int m = blockIdx.x;
@@ -247,11 +247,25 @@ __global__ void __launch_bounds__(256) ce_labels_bwd_kernel(const float* __restr
   __syncthreads();
   const float inv = 1.f / bc;
   const float cnt = accum ? fmaxf(accum[1], 1.f) : 1.f;
-  const float w = grad_scale / cnt;
+  const float w = grad_scale * (gscale_dev ? gscale_dev[0] : 1.f) / cnt;   // gscale_dev: the incoming d loss, on the device
   for (int v = threadIdx.x; v < V; v += blockDim.x) {
     const float pv = __expf(row[v] - mx) * inv;
     out[v] = __float2bfloat16(w * (pv - (v == lab ? 1.f : 0.f)));
   }
+}
+
+// dx = bf16(dy * act'(pre)) on bf16 tensors: the activation backward when the gradient does not come out of a GEMM
+// epilogue (EPI_BF16_DACT covers that case) — MaskedPredictionHead: LayerNorm backward -> GELU' (losses/flava.py:174-180)
+template <int ACT>
+__global__ void act_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ pre,
+                               __nv_bfloat16* __restrict__ dx, long long n) {
+  const long long n2 = n >> 1;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x) {
+    const uint32_t a = reinterpret_cast<const uint32_t*>(dy)[i], b = reinterpret_cast<const uint32_t*>(pre)[i];
+    reinterpret_cast<uint32_t*>(dx)[i] = pack_bf16x2(bf16_lo(a) * act_grad<ACT>(bf16_lo(b)), bf16_hi(a) * act_grad<ACT>(bf16_hi(b)));
+  }
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0)
+    dx[n - 1] = __float2bfloat16(__bfloat162float(dy[n - 1]) * act_grad<ACT>(__bfloat162float(pre[n - 1])));
 }
 
 }  // namespace mmb
@@ -318,9 +332,20 @@ extern "C" int mmb_scatter_rows_idx_add(const float* src, const long long* idx, 
 
 extern "C" int mmb_ce_labels_bwd(const float* logits, long long ld, const long long* labels, long long label_stride,
                                  long long ignore_index, int M, int V, const float* accum, float grad_scale,
-                                 void* dlogits_bf16, long long ldd, void* stream) {
+                                 const float* grad_scale_dev, void* dlogits_bf16, long long ldd, void* stream) {
   if (M <= 0 || V <= 0) return MMB_ERR_ARG;
   ce_labels_bwd_kernel<<<M, 256, 0, ST(stream)>>>(logits, ld, labels, label_stride, ignore_index, V, accum, grad_scale,
-                                                  (__nv_bfloat16*)dlogits_bf16, ldd);
+                                                  grad_scale_dev, (__nv_bfloat16*)dlogits_bf16, ldd);
+  return LAUNCH_RC();
+}
+
+extern "C" int mmb_act_bwd(const void* dy_bf16, const void* pre_bf16, void* dx_bf16, long long n, int kind, void* stream) {
+  if (n <= 0) return MMB_OK;
+  if ((reinterpret_cast<uintptr_t>(dy_bf16) | reinterpret_cast<uintptr_t>(pre_bf16) | reinterpret_cast<uintptr_t>(dx_bf16)) & 3)
+    return MMB_ERR_ARG;
+  const __nv_bfloat16 *dy = (const __nv_bfloat16*)dy_bf16, *pre = (const __nv_bfloat16*)pre_bf16;
+  if (kind == ACT_QUICK_GELU) act_bwd_kernel<0><<<grid_cap(n / 2 + 1, 256), 256, 0, ST(stream)>>>(dy, pre, (__nv_bfloat16*)dx_bf16, n);
+  else if (kind == ACT_GELU_ERF) act_bwd_kernel<1><<<grid_cap(n / 2 + 1, 256), 256, 0, ST(stream)>>>(dy, pre, (__nv_bfloat16*)dx_bf16, n);
+  else return MMB_ERR_ARG;
   return LAUNCH_RC();
 }

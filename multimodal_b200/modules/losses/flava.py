@@ -11,8 +11,11 @@ containers.  The modules are parameter containers; the arithmetic runs on the li
 * global contrastive loss (:241-293): `F.normalize` kernels + the fused similarity-GEMM / cross-entropy runtime of
   `contrastive_loss_with_temperature` with the positive-pair mask.
 
-Forward values only, like the FLAVA encoders: asking for an autograd graph raises instead of silently
-returning constants.  GEMM operands are bf16 (fp32 accumulate, fp32 LayerNorm / softmax statistics); tolerances in
+With grad mode on and trainable parameters (or inputs that require grad) the same modules build an autograd graph:
+the heads run as the Functions of ``engine_flava_heads`` (one fused node per masked-prediction head, explicit backward
+schedules on the library's kernels), the pooler as ``engine_flava_train.FirstTokenLinearFunction``, the contrastive loss
+through ``engine_loss.ContrastiveFunction``.  Under ``torch.no_grad()`` they compute forward values only.
+GEMM operands are bf16 (fp32 accumulate, fp32 LayerNorm / softmax statistics); tolerances in
 tests/test_gpu_flava_pretraining.py.
 """
 import math
@@ -88,18 +91,26 @@ FLAVAPretrainingLossOutput = _output(
 # ---------------------------------------------------------------------------------------------------------------------
 # runtime helpers (kernel launches only)
 # ---------------------------------------------------------------------------------------------------------------------
-def _no_graph(what: str, *mods_or_tensors: Any) -> None:
-    """Forward-only runtime: refuse to hand back a value that autograd would treat as a constant."""
+def _wants_graph(*mods_or_tensors: Any) -> bool:
+    """True when the caller expects an autograd graph through this call: grad mode on and a trainable parameter or an
+    input that requires grad.  Those calls take the autograd Functions of engine_flava_heads / engine_flava_train (same
+    kernels forward, explicit backward schedules); everything else runs the forward-value path under no_grad."""
     if not torch.is_grad_enabled():
-        return
+        return False
     for x in mods_or_tensors:
         if isinstance(x, nn.Module):
             if any(p.requires_grad for p in x.parameters()):
-                raise MMBError(f"{what} computes forward values only (no backward schedule yet); call it under "
-                               "torch.no_grad()")
+                return True
         elif isinstance(x, Tensor) and x.requires_grad:
-            raise MMBError(f"{what} computes forward values only (no backward schedule yet); call it under "
-                           "torch.no_grad()")
+            return True
+    return False
+
+
+def _no_graph(what: str, *mods_or_tensors: Any) -> None:
+    """Forward-value-only entry points: refuse to hand back a value that autograd would treat as a constant."""
+    if _wants_graph(*mods_or_tensors):
+        raise MMBError(f"{what} computes forward values only on this call path (no labels -> no loss to differentiate); "
+                       "call it under torch.no_grad()")
 
 
 def _rows_view(x: Tensor) -> Tensor:
@@ -175,7 +186,9 @@ class Pooler(nn.Module):
 
     def forward(self, hidden_states: Tensor) -> Tensor:
         # losses/flava.py:91-97: dense + tanh on the first token
-        _no_graph("Pooler", self, hidden_states)
+        if _wants_graph(self, hidden_states):
+            from ...engine_flava_train import first_token_linear
+            return first_token_linear(hidden_states, self.dense, use_tanh=True)
         x = _rows_view(hidden_states)
         keep = torch.zeros(x.shape[:2], dtype=torch.bool, device=x.device)
         keep[:, 0] = True
@@ -190,7 +203,9 @@ class TwoWayHead(nn.Module):
         self.seq_relationship = nn.Linear(hidden_size, 2)
 
     def forward(self, pooled_output: Tensor) -> Tensor:
-        _no_graph("TwoWayHead", self, pooled_output)
+        if _wants_graph(self, pooled_output):
+            from ...engine_flava_heads import small_linear
+            return small_linear(pooled_output, self.seq_relationship)
         return _linear_f32(_bf16(pooled_output.float()), self.seq_relationship.weight, self.seq_relationship.bias)
 
 
@@ -209,6 +224,9 @@ class ITMLoss(nn.Module):
         scores = self.cls(pooled_output)
         if labels is None:
             loss = torch.zeros((), device=scores.device)
+        elif scores.requires_grad:
+            from ...engine_flava_heads import cross_entropy
+            loss = cross_entropy(scores.reshape(-1, 2), labels.reshape(-1).long(), self.ignore_index)
         else:
             loss = _cross_entropy(scores.reshape(-1, 2), labels.reshape(-1).long(), self.ignore_index)
         return ITMLossOutput(logits=scores, loss=loss)
@@ -271,8 +289,14 @@ class MaskedPredictionLoss(nn.Module):
     def forward(self, hidden_states: Tensor, masked_labels: Optional[Tensor] = None) -> MaskedPredictionLossOutput:
         if self.training:
             assert_labels_are_present(masked_labels, "masked labels")
-        _no_graph("MaskedPredictionLoss", self, hidden_states)
-        if masked_labels is not None:
+        training = _wants_graph(self, hidden_states)
+        if masked_labels is not None and training:
+            from ...engine_flava_heads import masked_prediction
+            masked_tokens = masked_labels.ne(self.ignore_index)                  # :212-215
+            kept_labels = masked_labels[masked_tokens].long()
+            prediction, masked_loss = masked_prediction(hidden_states, masked_tokens, kept_labels, self.cls,
+                                                        self.ignore_index)
+        elif masked_labels is not None:
             masked_tokens = masked_labels.ne(self.ignore_index)                  # :212-215
             kept_labels = masked_labels[masked_tokens].long()
             prediction = self.cls._forward_rows(_select_rows_bf16(hidden_states, masked_tokens))
@@ -283,7 +307,7 @@ class MaskedPredictionLoss(nn.Module):
         else:
             prediction = self.cls(hidden_states)
             masked_loss = torch.zeros((), device=hidden_states.device)
-        if torch.isnan(masked_loss) and self.ignore_nan:
+        if self.ignore_nan and torch.isnan(masked_loss):   # the host read-back only when the option is on
             warnings.warn("NaN detected in masked_loss. Replacing it with 0.")
             masked_loss = torch.nan_to_num(masked_loss, nan=0.0)
         return MaskedPredictionLossOutput(logits=prediction, loss=masked_loss)
@@ -310,11 +334,16 @@ class FLAVAGlobalContrastiveLoss(nn.Module):
         return y
 
     def forward(self, image_sequence: Tensor, text_sequence: Tensor, mask: Tensor) -> FLAVAGlobalContrastiveLossOutput:
-        _no_graph("FLAVAGlobalContrastiveLoss", self, image_sequence, text_sequence)
-        text_embedding = self._normalize(text_sequence)
-        image_embedding = self._normalize(image_sequence)
+        training = _wants_graph(self, image_sequence, text_sequence)
+        if training:
+            from ...autograd import l2_normalize
+            text_embedding = l2_normalize(text_sequence.float())
+            image_embedding = l2_normalize(image_sequence.float())
+        else:
+            text_embedding = self._normalize(text_sequence)
+            image_embedding = self._normalize(image_sequence)
         self.logit_scale.data.clamp_(0, 4.6052)                                  # :273
-        with torch.no_grad():
+        with torch.set_grad_enabled(training):
             output = contrastive_loss_with_temperature(
                 embeddings_a=image_embedding, embeddings_b=text_embedding, logit_scale=self.logit_scale, mask=mask,
                 backprop_type=BackpropType.GLOBAL)                               # always GLOBAL for FLAVA (:280-281)

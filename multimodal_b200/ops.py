@@ -482,9 +482,19 @@ def scatter_rows_idx_add(src, idx, dst, d):
                "mmb_scatter_rows_idx_add")
 
 
-def ce_labels_bwd(logits, labels, label_stride, ignore_index, M, V, accum, grad_scale, dlogits):
+def ce_labels_bwd(logits, labels, label_stride, ignore_index, M, V, accum, grad_scale, dlogits, gscale=None):
+    """gscale: optional fp32 device scalar multiplied into grad_scale (the incoming d loss; no host read-back)."""
     _chk(logits, torch.float32, "logits"); _chk(labels, torch.int64, "labels"); _chk(dlogits, torch.bfloat16, "dlogits")
     _rowmajor(logits, "logits"); _rowmajor(dlogits, "dlogits")
+    if gscale is not None:
+        _chk(gscale, torch.float32, "gscale")
     _lib.check(_lib.lib().mmb_ce_labels_bwd(_p(logits), logits.stride(0), _p(labels), int(label_stride), int(ignore_index),
-                                            M, V, _p(accum), float(grad_scale), _p(dlogits), dlogits.stride(0), _stream()),
-               "mmb_ce_labels_bwd")
+                                            M, V, _p(accum), float(grad_scale), _p(gscale), _p(dlogits), dlogits.stride(0),
+                                            _stream()), "mmb_ce_labels_bwd")
+
+
+def act_bwd(dy, pre, dx, kind):
+    _chk(dy, torch.bfloat16, "dy"); _chk(pre, torch.bfloat16, "pre"); _chk(dx, torch.bfloat16, "dx")
+    if not (dy.is_contiguous() and pre.is_contiguous() and dx.is_contiguous()) or not (dy.numel() == pre.numel() == dx.numel()):
+        raise MMBError("act_bwd: contiguous bf16 tensors of equal size expected")
+    _lib.check(_lib.lib().mmb_act_bwd(_p(dy), _p(pre), _p(dx), dy.numel(), int(kind), _stream()), "mmb_act_bwd")

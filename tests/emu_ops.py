@@ -268,6 +268,55 @@ def scatter_rows_add(src, dst, B, rows_per_group, row, d):
     dst.view(B, rows_per_group, d)[:, row] += src
 
 
+def gather_rows_idx_cast(x, idx, out, d):
+    ld = x.stride(-2)
+    flat = x.detach().as_strided((int(idx.max().item()) + 1 if idx.numel() else 0, d), (ld, 1))
+    out.copy_(flat[idx].to(BF))
+    return out
+
+
+def scatter_rows_idx_add(src, idx, dst, d):
+    dst.view(-1, d).index_add_(0, idx, src)
+
+
+def ce_labels(logits, labels, label_stride, ignore_index, M, V, row_loss, accum):
+    lab = labels.view(-1)[::label_stride][:M]
+    keep = lab != ignore_index
+    lg = logits.detach()[:M, :V]
+    nll = torch.logsumexp(lg, -1) - lg.gather(1, lab.clamp_min(0).view(-1, 1)).squeeze(1)
+    nll = torch.where(keep, nll, torch.zeros_like(nll))
+    if row_loss is not None:
+        row_loss.copy_(nll)
+    accum[0] += nll.sum()
+    accum[1] += keep.sum()
+
+
+def ce_labels_bwd(logits, labels, label_stride, ignore_index, M, V, accum, grad_scale, dlogits, gscale=None):
+    lab = labels.view(-1)[::label_stride][:M]
+    keep = lab != ignore_index
+    p = torch.softmax(logits.detach()[:M, :V], -1)
+    p[torch.arange(M)[keep], lab[keep]] -= 1
+    w = grad_scale * (float(gscale[0]) if gscale is not None else 1.0) / (max(float(accum[1]), 1.0) if accum is not None else 1.0)
+    dlogits.copy_((w * p * keep.view(-1, 1)).to(BF))
+
+
+def act_bwd(dy, pre, dx, kind):
+    dx.copy_((dy.float() * _act_grad(pre.float(), kind)).to(BF))
+
+
+def cast_f32(src, out):
+    out.copy_(src.float())
+    return out
+
+
+def matmul_f32(A, B, *, ta=False, tb=False, out=None, alpha=1.0, accumulate=False):
+    r = alpha * ((A.t() if ta else A) @ (B.t() if tb else B))
+    if out is None:
+        return r
+    out.copy_(out + r if accumulate else r)
+    return out
+
+
 NAMES = [n for n, f in list(globals().items()) if callable(f) and not n.startswith("_") and n not in ("install",)]
 
 

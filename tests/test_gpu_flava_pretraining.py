@@ -55,8 +55,9 @@ def test_pretraining_loss_against_reference_golden(dev, golden, name):
     with torch.no_grad():
         o = m(**kw)
     _compare(PC.flatten_loss_output(o), golden[f"loss.{name}"])
-    with pytest.raises(MMBError):          # forward-only runtime: a trainable call must fail loudly
-        m(**kw)
+    o2 = m(**kw)                           # grad mode on + trainable heads: the autograd path, same values
+    assert all(v.requires_grad for v in o2.losses.values() if v is not None)
+    _compare(PC.flatten_loss_output(o2), golden[f"loss.{name}"])
 
 
 def test_flava_for_pretraining_against_reference_golden(dev, golden):

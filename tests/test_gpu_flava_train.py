@@ -16,6 +16,8 @@ import pytest
 import torch
 
 import flava_cases as FC
+import flava_pretraining_cases as PC
+from oracle import flava_loss_oracle as LO
 from oracle import flava_oracle as FO
 
 pytestmark = pytest.mark.gpu
@@ -321,3 +323,120 @@ def test_flava_mm_encoder_direct_call_and_frozen_parts(dev):
     (o.projected_image_embeddings.sum() + o.projected_text_embeddings.sum()).backward()
     assert all(p.grad is None for p in m.text_encoder.parameters())
     assert m.text_projection.weight.grad is not None and m.image_encoder.embeddings.cls_token.grad is not None
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# pre-training heads: FLAVAPretrainingLoss under autograd
+# ---------------------------------------------------------------------------------------------------------------------
+_SEQ = ("image_sequence", "text_sequence", "image_masked_sequence", "text_masked_sequence", "multimodal_masked_sequence",
+        "projected_image_embeddings", "projected_text_embeddings")
+
+
+def _oracle_loss_total(sd, kw, weights):
+    """Sum of the oracle's losses with autograd intact (LO.pretraining_loss detaches its state dict: restated here from
+    the same per-head oracle functions, FLAVAPretrainingLoss.forward :370-484)."""
+    mm = kw.get("multimodal_masked_sequence")
+    mlm, mim, itm = kw.get("mlm_labels"), kw.get("mim_labels"), kw.get("itm_labels")
+    total, parts, pos_mask = 0.0, {}, None
+    if mm is None:
+        _, parts["mim"] = LO.masked_prediction(kw["image_masked_sequence"][:, -mim.size(1):], mim, sd, "mim_loss")
+        _, parts["mlm"] = LO.masked_prediction(kw["text_masked_sequence"][:, -mlm.size(1):], mlm, sd, "mlm_loss")
+    else:
+        pos = itm.ne(0)
+        pos_mask = pos if bool(pos.any()) else torch.ones_like(pos)
+        _, parts["itm"] = LO.itm(mm, itm, sd)
+        mmk, mlmk, mimk = mm[pos_mask], mlm[pos_mask], mim[pos_mask]
+        _, parts["mmm_text"] = LO.masked_prediction(mmk[:, -mlmk.size(1):], mlmk, sd, "mmm_loss.mlm")
+        _, parts["mmm_image"] = LO.masked_prediction(mmk[:, 2:2 + mimk.size(1)], mimk, sd, "mmm_loss.mim")
+    if weights.get("contrastive", 1.0) > 0:
+        parts["contrastive"] = LO.global_contrastive(kw["projected_image_embeddings"], kw["projected_text_embeddings"],
+                                                     pos_mask, sd)["loss"]
+    for k, v in parts.items():
+        total = total + weights.get(k, 1.0) * v
+    return total, parts
+
+
+def _loss_grad_parity(dev, name, contrastive_weight, tag, bar=4e-2):
+    from multimodal_b200.modules.losses.flava import FLAVAPretrainingLoss
+
+    torch.manual_seed(0)
+    m = FLAVAPretrainingLoss(contrastive_loss_weight=contrastive_weight, mlm_weight=0.7, mim_weight=1.3,
+                             mmm_text_loss_weight=0.9, mmm_image_loss_weight=1.1, itm_loss_weight=0.8, **PC.LOSS_KW)
+    g = torch.Generator().manual_seed(13)
+    with torch.no_grad():
+        for p in m.parameters():
+            if p.dim() > 0:
+                p.add_(0.05 * torch.randn(p.shape, generator=g))
+    m = m.to(dev).train()
+    weights = dict(mlm=0.7, mim=1.3, mmm_text=0.9, mmm_image=1.1, itm=0.8, contrastive=contrastive_weight)
+    kw = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in PC.loss_calls()[name].items()}
+    kw_ref = {k: (v.detach().clone().requires_grad_(True) if k in _SEQ else v) for k, v in kw.items()}
+    kw_our = {k: (v.detach().clone().requires_grad_(True) if k in _SEQ else v) for k, v in kw.items()}
+    sd = {k: v.detach().clone().requires_grad_(True) for k, v in m.state_dict().items()}
+    total_ref, parts = _oracle_loss_total(sd, kw_ref, weights)
+    total_ref.backward()
+    out = m(**kw_our)
+    losses = [v for v in out.losses.values() if v is not None]
+    assert len(losses) == len(parts) and all(v.requires_grad for v in losses)
+    total = sum(losses)
+    assert abs(total.item() - total_ref.item()) < 2e-2 * max(1.0, abs(total_ref.item())), (total.item(), total_ref.item())
+    total.backward()
+    rows = []
+    for k, p in m.named_parameters():
+        ref = sd[k].grad
+        if ref is None or ref.norm().item() == 0.0:   # heads of the branch not taken / logit_scale with weight 0
+            assert p.grad is None or p.grad.abs().max().item() < 1e-6, k
+            continue
+        assert p.grad is not None and torch.isfinite(p.grad).all(), k
+        rows.append((k, _rel(p.grad, ref)))
+    for k in _SEQ:
+        if k in kw_ref and kw_ref[k].grad is not None and kw_ref[k].grad.norm().item() > 0:
+            assert kw_our[k].grad is not None, k
+            rows.append(("input:" + k, _rel(kw_our[k].grad, kw_ref[k].grad)))
+    report = [f"{tag}: total loss ours {total.item():.6f} oracle {total_ref.item():.6f}"]
+    report += [f"{k:60s} rel {a:.3e}" for k, a in sorted(rows, key=lambda r: -r[1])]
+    print("\n".join(report))
+    try:
+        os.makedirs("gpurun_out", exist_ok=True)
+        open(f"gpurun_out/flava_loss_grad_parity_{tag}.txt", "w").write("\n".join(report) + "\n")
+    except OSError:
+        pass
+    assert len(rows) >= 8
+    for k, a in rows:
+        assert a < bar, (k, a)
+
+
+@pytest.mark.parametrize("name", ["unimodal", "multimodal"])
+def test_pretraining_loss_gradients_against_fp32_oracle(dev, name):
+    """MLM / MIM (unimodal branch) and ITM / MMM text / MMM image (multimodal branch) + the global contrastive loss over
+    the positive pairs: every head parameter's gradient and the gradient w.r.t. every incoming sequence."""
+    _loss_grad_parity(dev, name, 1.0, name)
+
+
+def test_flava_for_pretraining_step_trains(dev):
+    """FLAVAForPreTraining end to end under autograd: encoders (two passes each) -> multimodal encoder -> all heads;
+    every trainable parameter that the reference's graph reaches gets a finite gradient, and three SGD steps on the same
+    batch lower the total loss."""
+    from multimodal_b200.models.flava import flava_model, FLAVAForPreTraining
+    from multimodal_b200.modules.losses.flava import FLAVAPretrainingLoss
+
+    m = PC.build_model(flava_model, FLAVAForPreTraining, FLAVAPretrainingLoss).to(dev).train()
+    inp, _ = PC.model_inputs()
+    inp = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in inp.items()}
+    opt = torch.optim.SGD(m.parameters(), lr=0.05)
+    hist = []
+    for step in range(4):
+        opt.zero_grad(set_to_none=True)
+        out = m(**inp)
+        total = sum(v for v in out.losses.values() if v is not None)
+        assert total.requires_grad and torch.isfinite(total)
+        total.backward()
+        if step == 0:
+            missing = [k for k, p in m.named_parameters() if p.grad is None]
+            # the unimodal MIM / MLM heads are not on the multimodal branch's graph (losses/flava.py:386-413)
+            assert all(k.startswith(("loss.mim_loss", "loss.mlm_loss")) for k in missing), missing
+            assert all(torch.isfinite(p.grad).all() for p in m.parameters() if p.grad is not None)
+        hist.append(total.item())
+        opt.step()
+    print("FLAVAForPreTraining total loss over SGD steps:", hist)
+    assert hist[-1] < hist[0], hist
