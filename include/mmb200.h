@@ -254,6 +254,16 @@ int mmb_attention_fwd_generic(const void* q, long long ldq, long long bsq, const
                               const void* v, long long ldv, long long bsv, void* out, long long ldo, long long bso,
                               const void* mask, long long mask_bs, long long mask_qs, int B, int Sq, int Skv, int H,
                               int head_dim, int causal, float scale, void* stream);
+/* Backward of mmb_attention_fwd_generic (same addressing; SIMT, fp32 arithmetic — these layers are ~3 % of CoCa's FLOPs).
+ * dq / dk / dv (bf16) use the strides of q / k / v; dq_bf16 may be NULL.  dq_f32 (optional, fp32 [Sq, ldq32], accumulated
+ * with atomics: zero it first) receives the gradient of batch-shared queries (bsq = 0) summed over the batch.
+ * scratch: fp32 [2 * B * H * Sq] (row LSE and rowsum(P * dP)).  Autograd of F.scaled_dot_product_attention at
+ * modules/layers/multi_head_attention.py:74-76,171-173 for the CoCa poolers / decoders. */
+int mmb_attention_bwd_generic(const void* q, long long ldq, long long bsq, const void* k, long long ldk, long long bsk,
+                              const void* v, long long ldv, long long bsv, const void* dout, long long ldo, long long bso,
+                              const void* mask, long long mask_bs, long long mask_qs, void* dq_bf16, float* dq_f32,
+                              long long ldq32, void* dk_bf16, void* dv_bf16, float* scratch, int B, int Sq, int Skv, int H,
+                              int head_dim, int causal, float scale, void* stream);
 /* accum[0] += sum_i CE(logits[i,:], labels[i*label_stride]) over rows with label != ignore_index; accum[1] += #rows
  * — nn.CrossEntropyLoss(ignore_index=pad_idx), models/coca/coca_model.py:425,447-450 (forward). */
 int mmb_ce_labels(const float* logits, long long ld, const long long* labels, long long label_stride,

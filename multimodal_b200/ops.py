@@ -498,3 +498,25 @@ def act_bwd(dy, pre, dx, kind):
     if not (dy.is_contiguous() and pre.is_contiguous() and dx.is_contiguous()) or not (dy.numel() == pre.numel() == dx.numel()):
         raise MMBError("act_bwd: contiguous bf16 tensors of equal size expected")
     _lib.check(_lib.lib().mmb_act_bwd(_p(dy), _p(pre), _p(dx), dy.numel(), int(kind), _stream()), "mmb_act_bwd")
+
+
+def attention_bwd_generic(q, k, v, dout, dk, dv, *, B, Sq, Skv, H, head_dim, bsq, bsk, bsv, bso, scale, dq=None,
+                          dq_f32=None, mask=None, mask_bs=0, mask_qs=0, causal=False):
+    """Backward of attention_fwd_generic.  q/k/v/dout and dq/dk/dv: 2-D bf16 views (dq/dk/dv with the row / batch strides
+    of q/k/v).  dq_f32: fp32 [Sq, >= H*head_dim], zeroed by the caller, for batch-shared queries (bsq = 0)."""
+    for t, n in ((q, "q"), (k, "k"), (v, "v"), (dout, "dout"), (dk, "dk"), (dv, "dv")):
+        _chk(t, torch.bfloat16, n); _rowmajor(t, n)
+    if dk.stride(0) != k.stride(0) or dv.stride(0) != v.stride(0) or (dq is not None and dq.stride(0) != q.stride(0)):
+        raise MMBError("attention_bwd_generic: dq / dk / dv must have the row strides of q / k / v")
+    if dq is not None:
+        _chk(dq, torch.bfloat16, "dq"); _rowmajor(dq, "dq")
+    if dq_f32 is not None:
+        _chk(dq_f32, torch.float32, "dq_f32"); _rowmajor(dq_f32, "dq_f32")
+    if mask is not None:
+        _chk(mask, torch.uint8, "mask")
+    scratch = torch.empty(2 * B * H * Sq, device=q.device, dtype=torch.float32)
+    _lib.check(_lib.lib().mmb_attention_bwd_generic(
+        _p(q), q.stride(0), int(bsq), _p(k), k.stride(0), int(bsk), _p(v), v.stride(0), int(bsv), _p(dout), dout.stride(0),
+        int(bso), _p(mask), int(mask_bs), int(mask_qs), _p(dq), _p(dq_f32), dq_f32.stride(0) if dq_f32 is not None else 0,
+        _p(dk), _p(dv), _p(scratch), B, Sq, Skv, H, head_dim, int(causal), float(scale), _stream()),
+        "mmb_attention_bwd_generic")
