@@ -168,7 +168,11 @@ class Workspace:
         self.device = device
         self.bufs: Dict[str, torch.Tensor] = {}
         self.X0: Optional[torch.Tensor] = None      # set by TransformerStack.forward(training=True): layer-0 input
-        self.kmask: Optional[torch.Tensor] = None   # ... and the key-padding mask that forward used
+        self.kmask: Optional[torch.Tensor] = None   # ... and the key-padding mask / [B,S,S] mask / cross-attention
+        self.mask3: Optional[torch.Tensor] = None   #     source that forward used
+        self.enc: Optional[torch.Tensor] = None
+        self.S_enc = 0
+        self.dENC: Optional[torch.Tensor] = None    # set by backward: gradient w.r.t. the cross-attention source
 
     def get(self, name: str, shape, dtype) -> torch.Tensor:
         t = self.bufs.get(name)
@@ -208,14 +212,21 @@ class TransformerStack:
         return (self._save if training else self.ws).get(key, shape, dtype)
 
     def forward(self, X0: torch.Tensor, B: int, S: int, training: bool, kmask: Optional[torch.Tensor] = None,
-                save: Optional["Workspace"] = None):
+                save: Optional["Workspace"] = None, mask3: Optional[torch.Tensor] = None,
+                enc: Optional[torch.Tensor] = None, S_enc: int = 0):
         """X0: fp32 [B*S, d] residual stream entering layer 0.  Returns (XM_last fp32, Y bf16): the final residual
         stream is XM_last + Y (the add is fused into whichever LayerNorm consumes it).
-        kmask: optional uint8 [B*S] key-padding mask (1 = attend).  save: the Workspace that receives the activations a
+        kmask: optional uint8 [B*S] key-padding mask (1 = attend).  mask3: optional uint8 [B, S, S] mask (general
+        attention kernels).  enc / S_enc: bf16 [B*S_enc, d_kv] cross-attention source for layers that carry a
+        `cross_attn` block (TransformerDecoderLayer: modules/layers/transformer.py:354-377).  save: the Workspace that receives the activations a
         training forward keeps for its backward (default: the stack's own — ONE in-flight training forward; callers
         that run the same stack several times before the backward pass a fresh Workspace per call)."""
         self._save = save if save is not None else self.ws
         self._save.kmask = kmask if training else None
+        self._save.mask3 = mask3 if training else None
+        self._save.enc, self._save.S_enc = (enc, S_enc) if training else (None, 0)
+        if mask3 is not None and kmask is not None:
+            raise MMBError("TransformerStack: pass either a key-padding mask or a [B, S, S] mask, not both")
         st, d, ff, H = self.store, self.d, self.ff, self.H
         M = B * S
         bf, f32 = torch.bfloat16, torch.float32
@@ -242,13 +253,38 @@ class TransformerStack:
                 ops.add_layernorm_fwd(XM_prev, Y, XA, LN1, None, layer.norm1.weight, layer.norm1.bias, m1, r1, M, d,
                                       layer.norm1.eps)
             ops.gemm(LN1, st.shadow(at.in_proj_weight), bias=at.in_proj_bias, out=QKV)
-            if kmask is not None:
+            if mask3 is not None:
+                ops.attention_fwd_generic(QKV[:, :d], QKV[:, d:2 * d], QKV[:, 2 * d:], O, B=B, Sq=S, Skv=S, H=H, head_dim=64,
+                                          bsq=S * 3 * d, bsk=S * 3 * d, bsv=S * 3 * d, bso=S * d, scale=self.scale,
+                                          mask=mask3, mask_bs=S * S, mask_qs=S, causal=self.causal)
+            elif kmask is not None:
                 ops.attention_fwd_kmask(QKV, O, LSE, kmask, B, S, H, self.causal, self.scale)
             else:
                 ops.attention_fwd(QKV, O, LSE, B, S, H, self.causal, self.scale)
             ops.gemm(O, st.shadow(at.out_proj.weight), bias=at.out_proj.bias, out=Y)
-            ops.add_layernorm_fwd(XA, Y, XM, LN2, None, layer.norm2.weight, layer.norm2.bias, m2, r2, M, d,
-                                  layer.norm2.eps)
+            ca = getattr(layer, "cross_attn", None)
+            if ca is not None and enc is not None:
+                # x1 = x + self-attention (XM);  x2 = x1 + cross-attention(LN_c(x1), enc) (XC);  the MLP reads LN2(x2)
+                lnc = layer.norm_cross
+                Se = S_enc
+                LNC = self._buf("LNC", l, (M, d), bf, training)
+                QC = self._buf("QC", l, (M, d), bf, training)
+                KVC = self._buf("KVC", l, (B * Se, 2 * d), bf, training)
+                OC = self._buf("OC", l, (M, d), bf, training)
+                XC = self._buf("XC", l, (M, d), f32, training)
+                mc = self._buf("mc", l, (M,), f32, training); rc = self._buf("rc", l, (M,), f32, training)
+                ops.add_layernorm_fwd(XA, Y, XM, LNC, None, lnc.weight, lnc.bias, mc, rc, M, d, lnc.eps)
+                ops.gemm(LNC, st.shadow(ca.q_w), bias=ca.q_b, out=QC)
+                ops.gemm(enc, st.shadow(ca.kv_w), bias=ca.kv_b, out=KVC)
+                ops.attention_fwd_generic(QC, KVC[:, :d], KVC[:, d:], OC, B=B, Sq=S, Skv=Se, H=H, head_dim=64, bsq=S * d,
+                                          bsk=Se * 2 * d, bsv=Se * 2 * d, bso=S * d, scale=self.scale)
+                ops.gemm(OC, st.shadow(ca.out_proj.weight), bias=ca.out_proj.bias, out=Y)
+                ops.add_layernorm_fwd(XM, Y, XC, LN2, None, layer.norm2.weight, layer.norm2.bias, m2, r2, M, d,
+                                      layer.norm2.eps)
+                XM = XC
+            else:
+                ops.add_layernorm_fwd(XA, Y, XM, LN2, None, layer.norm2.weight, layer.norm2.bias, m2, r2, M, d,
+                                      layer.norm2.eps)
             ops.gemm(LN2, st.shadow(layer.linear1.weight), bias=layer.linear1.bias, epilogue=ops.EPI_BF16_ACT, out=PRE,
                      out2=HACT, act=self.act)
             ops.gemm(HACT, st.shadow(layer.linear2.weight), bias=layer.linear2.bias, out=Y)
@@ -273,6 +309,8 @@ class TransformerStack:
                 raise MMBError("backward called without a saved training forward")
             save = self.ws
         X0, kmask = save.X0, getattr(save, "kmask", None)
+        mask3, enc, Se = getattr(save, "mask3", None), getattr(save, "enc", None), getattr(save, "S_enc", 0)
+        save.dENC = None
         if X0 is None:
             raise MMBError("backward called without a saved training forward")
         st, d, ff, H = self.store, self.d, self.ff, self.H
@@ -289,6 +327,8 @@ class TransformerStack:
             LN1, QKV, O = g("LN1", (M, d), bf), g("QKV", (M, 3 * d), bf), g("O", (M, d), bf)
             LSE = g("LSE", (B * H * S,), f32)
             XM, LN2 = g("XM", (M, d), f32), g("LN2", (M, d), bf)
+            ca = getattr(layer, "cross_attn", None) if enc is not None else None
+            XMID = g("XC", (M, d), f32) if ca is not None else XM     # the stream the MLP branch was added to
             PRE, HACT = g("PRE", (M, ff), bf), g("HACT", (M, ff), bf)
             m1, r1, m2, r2 = g("m1", (M,), f32), g("r1", (M,), f32), g("m2", (M,), f32), g("r2", (M,), f32)
             XA = X0 if l == 0 else g("XA", (M, d), f32)
@@ -306,13 +346,48 @@ class TransformerStack:
             if not fuse:
                 ops.colsum_bf16(dPRE, st.grad(layer.linear1.bias), M, ff, ff)
             ops.gemm(dPRE, st.shadow(layer.linear1.weight), b_mn=True, out=T1)
-            ops.layernorm_bwd(XM, T1, None, m2, r2, layer.norm2.weight, G, G, Gb, st.grad(layer.norm2.weight),
-                              st.grad(layer.norm2.bias), M, d, gsum=st.grad(at.out_proj.bias))
+            ops.layernorm_bwd(XMID, T1, None, m2, r2, layer.norm2.weight, G, G, Gb, st.grad(layer.norm2.weight),
+                              st.grad(layer.norm2.bias), M, d,
+                              gsum=st.grad(ca.out_proj.bias if ca is not None else at.out_proj.bias))
+            if ca is not None:
+                # ---- cross-attention branch:  x2 = x1 + Wo_c Attn(Wq LN_c(x1), Wkv enc) ----
+                lnc = layer.norm_cross
+                dkv = enc.shape[1]
+                LNC, QC, OC = g("LNC", (M, d), bf), g("QC", (M, d), bf), g("OC", (M, d), bf)
+                KVC = g("KVC", (B * Se, 2 * d), bf)
+                mc, rc = g("mc", (M,), f32), g("rc", (M,), f32)
+                ops.gemm(Gb, OC, a_mn=True, b_mn=True, epilogue=ops.EPI_F32, out=st.grad(ca.out_proj.weight),
+                         splits=sp(d, d, M), accumulate=True)
+                ops.gemm(Gb, st.shadow(ca.out_proj.weight), b_mn=True, out=T1)      # d OC
+                dQC = self.ws.get(f"{self.prefix}.dQC", (M, d), bf)
+                dKVC = self.ws.get(f"{self.prefix}.dKVC", (B * Se, 2 * d), bf)
+                ops.attention_bwd_generic(QC, KVC[:, :d], KVC[:, d:], T1, dKVC[:, :d], dKVC[:, d:], dq=dQC, B=B, Sq=S,
+                                          Skv=Se, H=H, head_dim=64, bsq=S * d, bsk=Se * 2 * d, bsv=Se * 2 * d, bso=S * d,
+                                          scale=self.scale)
+                ops.gemm(dQC, LNC, a_mn=True, b_mn=True, epilogue=ops.EPI_F32, out=st.grad(ca.q_w), splits=sp(d, d, M),
+                         accumulate=True)
+                ops.colsum_bf16(dQC, st.grad(ca.q_b), M, d, d)
+                ops.gemm(dKVC, enc, a_mn=True, b_mn=True, epilogue=ops.EPI_F32, out=st.grad(ca.kv_w),
+                         splits=sp(2 * d, dkv, B * Se), accumulate=True)
+                ops.colsum_bf16(dKVC, st.grad(ca.kv_b), B * Se, 2 * d, 2 * d)
+                if save.dENC is None:   # gradient w.r.t. the cross-attention source, summed over the layers
+                    save.dENC = torch.empty((B * Se, dkv), device=G.device, dtype=f32)
+                    ops.gemm(dKVC, st.shadow(ca.kv_w), b_mn=True, epilogue=ops.EPI_F32, out=save.dENC)
+                else:
+                    ops.gemm(dKVC, st.shadow(ca.kv_w), b_mn=True, epilogue=ops.EPI_F32, out=save.dENC, accumulate=True)
+                ops.gemm(dQC, st.shadow(ca.q_w), b_mn=True, out=T1)                  # d LN_c(x1)
+                ops.layernorm_bwd(XM, T1, None, mc, rc, lnc.weight, G, G, Gb, st.grad(lnc.weight), st.grad(lnc.bias), M, d,
+                                  gsum=st.grad(at.out_proj.bias))
             # ---- attention branch ----
             ops.gemm(Gb, O, a_mn=True, b_mn=True, epilogue=ops.EPI_F32, out=st.grad(at.out_proj.weight),
                      splits=sp(d, d, M), accumulate=True)
             ops.gemm(Gb, st.shadow(at.out_proj.weight), b_mn=True, out=T1)  # dO
-            if kmask is not None:
+            if mask3 is not None:
+                ops.attention_bwd_generic(QKV[:, :d], QKV[:, d:2 * d], QKV[:, 2 * d:], T1, T3[:, d:2 * d], T3[:, 2 * d:],
+                                          dq=T3[:, :d], B=B, Sq=S, Skv=S, H=H, head_dim=64, bsq=S * 3 * d, bsk=S * 3 * d,
+                                          bsv=S * 3 * d, bso=S * d, scale=self.scale, mask=mask3, mask_bs=S * S, mask_qs=S,
+                                          causal=self.causal)
+            elif kmask is not None:
                 ops.attention_bwd_kmask(QKV, O, T1, LSE, T3, kmask, B, S, H, self.causal, self.scale)
             else:
                 ops.attention_bwd(QKV, O, T1, LSE, T3, B, S, H, self.causal, self.scale)

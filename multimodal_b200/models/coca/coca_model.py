@@ -28,10 +28,20 @@ class MultimodalOutput(NamedTuple):
 
 def _l2_normalize(x: Tensor) -> Tensor:
     """F.normalize(x, dim=-1) (eps 1e-12) on the fused kernel."""
+    if torch.is_grad_enabled() and x.requires_grad:
+        from ...autograd import l2_normalize
+        return l2_normalize(x.float())
     x = x.contiguous().float()
     y = torch.empty_like(x)
     ops.l2norm_fwd(x, y, None, None, x.shape[0], x.shape[1])
     return y
+
+
+class TrainHidden(NamedTuple):
+    """Third field of `MultimodalOutput` on CoCaForPretraining's training path: the multimodal decoder's hidden states
+    [B, S, d] (autograd history) and its vocabulary projection, consumed by the fused Linear -> CrossEntropy node."""
+    hidden: Tensor
+    projection: nn.Module
 
 
 class CoCaModel(nn.Module):
@@ -45,7 +55,6 @@ class CoCaModel(nn.Module):
         self.vision_proj = vision_proj
         self._proj_rt = None
 
-    @torch.no_grad()
     def forward(self, images: Tensor, texts: Tensor, text_padding_mask: Optional[Tensor] = None) -> MultimodalOutput:
         return self._forward_impl(images, texts, text_padding_mask, want_logits=True)
 
@@ -76,6 +85,11 @@ class CoCaModel(nn.Module):
 
         if want_logits or getattr(self.multimodal_decoder, "output_projection", None) is None:
             multimodal_embeddings = self.multimodal_decoder(text_tokens, captioning_image_embeddings)
+        elif self.multimodal_decoder.wants_graph(text_tokens, captioning_image_embeddings):
+            # training: hidden states with autograd history; CoCaForPretraining fuses projection + cross-entropy
+            multimodal_embeddings = TrainHidden(
+                self.multimodal_decoder.hidden_states(text_tokens, captioning_image_embeddings),
+                self.multimodal_decoder.output_projection)
         else:
             multimodal_embeddings = self.multimodal_decoder._runtime().forward(text_tokens, captioning_image_embeddings,
                                                                                return_hidden=True)
@@ -85,6 +99,9 @@ class CoCaModel(nn.Module):
         """self.vision_proj(x) for x [B, 1, d] or [B, d] (coca_model.py:115) as a tcgen05 GEMM, fp32 out."""
         from ...engine_flava import _Shadows
 
+        if torch.is_grad_enabled() and (x.requires_grad or self.vision_proj.weight.requires_grad):
+            from ...engine_coca_train import linear_f32
+            return linear_f32(x.float(), self.vision_proj)
         squeeze = x.dim() == 3
         B = x.shape[0]
         x2 = x.reshape(-1, x.shape[-1]).contiguous().float()
@@ -189,11 +206,32 @@ class CoCaForPretraining(nn.Module):
         # for them with gradients enabled on trainable parameters would let `loss.backward()` silently do nothing
         # (or fail far from the cause), so say so here instead.
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise MMBError("CoCaForPretraining (multimodal_b200) computes forward values only — there is no backward "
-                           "for the CoCa stacks yet.  Evaluate under torch.no_grad() (or freeze the parameters); "
-                           "training CoCa needs the reference implementation.")
+            return self._forward_train(images, texts, text_padding_mask)
         with torch.no_grad():
             return self._forward_values(images, texts, text_padding_mask)
+
+    def _forward_train(self, images: Tensor, texts: Tensor, text_padding_mask: Optional[Tensor] = None) -> Dict[str, Tensor]:
+        """Both losses with autograd history (every stack, the poolers and the vocabulary head have backward schedules:
+        engine_coca_train.py)."""
+        from ...engine_coca_train import linear_cross_entropy
+
+        fused = isinstance(self.model, CoCaModel)
+        model_outs = (self.model._forward_impl(images, texts, text_padding_mask, want_logits=False) if fused
+                      else self.model(images, texts, text_padding_mask))
+        img = model_outs.image_pooled_output
+        if img.dim() == 3:
+            img = img.squeeze(1)
+        contrastive_loss = self.contrastive_loss(img, model_outs.text_pooled_output)
+        labels = texts[:, 1:].contiguous()              # captioning_labels (:443)
+        mm = model_outs.multimodal_embeddings
+        if isinstance(mm, TrainHidden):
+            if mm.hidden.shape[:2] != labels.shape:
+                raise ValueError(f"caption labels {tuple(labels.shape)} do not match the decoder output {tuple(mm.hidden.shape)}")
+            captioning_loss = linear_cross_entropy(mm.hidden, mm.projection, labels, self.caption_loss.ignore_index)
+        else:   # a model without a vocabulary projection of its own / a user-supplied model: logits arrive materialised
+            from ...engine_flava_heads import cross_entropy
+            captioning_loss = cross_entropy(mm.reshape(-1, mm.shape[-1]), labels.reshape(-1), self.caption_loss.ignore_index)
+        return {"contrastive": contrastive_loss, "captioning": captioning_loss}
 
     def _forward_values(self, images: Tensor, texts: Tensor, text_padding_mask: Optional[Tensor] = None) -> Dict[str, Tensor]:
         fused = isinstance(self.model, CoCaModel)       # a user-supplied model only promises MultimodalOutput

@@ -28,11 +28,28 @@ class CoCaMultimodalDecoder(_RuntimeOwner):
         self.register_buffer("causal_mask", get_causal_attention_mask(input_seq_len).to(dtype=torch.bool),
                              persistent=False)
 
-    @torch.no_grad()
     def forward(self, texts: Tensor, images: Tensor) -> Tensor:
         seq_len = texts.shape[1]
         assert self.causal_mask.shape == (seq_len, seq_len)
-        return self._runtime().forward(texts, images)
+        from ... import engine_coca_train as T
+        if self.wants_graph(texts, images):
+            hidden = self.hidden_states(texts, images)
+            if self.output_projection is not None:
+                hidden = T.linear_f32(hidden, self.output_projection)
+            return hidden
+        with torch.no_grad():
+            return self._runtime().forward(texts, images)
+
+    def wants_graph(self, texts: Tensor, images: Tensor) -> bool:
+        from ... import engine_coca_train as T
+        return T.wants_grad(self) or (torch.is_grad_enabled() and (texts.requires_grad or images.requires_grad))
+
+    def hidden_states(self, texts: Tensor, images: Tensor) -> Tensor:
+        """Training path: the decoder output after its final LayerNorm, [B, S, d] with autograd history (the vocabulary
+        projection is applied by the caller: `forward`, or fused with the cross-entropy in CoCaForPretraining)."""
+        from ... import engine_coca_train as T
+        (out,) = T.run(self._train_runtime(), None, (texts, images))
+        return out.view(texts.shape[0], texts.shape[1], -1)
 
 
 def _mm_runtime(mod):
@@ -40,4 +57,10 @@ def _mm_runtime(mod):
     return MultimodalDecoderRuntime(mod)
 
 
+def _mm_train_runtime(mod):
+    from ...engine_coca_train import MultimodalDecoderTrainRuntime
+    return MultimodalDecoderTrainRuntime(mod)
+
+
 CoCaMultimodalDecoder._runtime_cls = staticmethod(_mm_runtime)
+CoCaMultimodalDecoder._train_runtime_cls = staticmethod(_mm_train_runtime)

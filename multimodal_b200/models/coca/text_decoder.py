@@ -83,7 +83,6 @@ class CoCaTextDecoder(_RuntimeOwner):
         mask = (padding_mask * self.causal_mask).unsqueeze(1)
         return mask
 
-    @torch.no_grad()
     def forward(self, input_ids: Tensor, padding_mask: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
         if self.embed_cls:
             if input_ids.shape[1] == self.num_positions:
@@ -97,7 +96,13 @@ class CoCaTextDecoder(_RuntimeOwner):
         mask_u8 = None
         if mask.dim() == 4:   # [B, 1, S, S] (batch-dependent); a bare causal_mask runs as the kernels' causal flag
             mask_u8 = (mask[:, 0] != 0).to(torch.uint8).contiguous()
-        return self._runtime().forward(input_ids, mask_u8, S)
+        from ... import engine_coca_train as T
+        if T.wants_grad(self):
+            pooled, XF = T.run(self._train_runtime(), (input_ids, mask_u8, S), ())
+            B = input_ids.shape[0]
+            return pooled, XF.view(B, S, -1)[:, :-1]       # tokens: every row but the appended CLS one (:190-191)
+        with torch.no_grad():
+            return self._runtime().forward(input_ids, mask_u8, S)
 
 
 def _txt_runtime(mod):
@@ -105,4 +110,10 @@ def _txt_runtime(mod):
     return TextDecoderRuntime(mod)
 
 
+def _txt_train_runtime(mod):
+    from ...engine_coca_train import TextDecoderTrainRuntime
+    return TextDecoderTrainRuntime(mod)
+
+
 CoCaTextDecoder._runtime_cls = staticmethod(_txt_runtime)
+CoCaTextDecoder._train_runtime_cls = staticmethod(_txt_train_runtime)

@@ -23,7 +23,6 @@ class VisionTransformer(_RuntimeOwner):
         if weight_init_fn:
             self.apply(weight_init_fn)
 
-    @torch.no_grad()
     def forward(self, images: Tensor, image_patches_mask: Optional[Tensor] = None,
                 attention_mask: Optional[Tensor] = None) -> TransformerOutput:
         if attention_mask is not None:
@@ -35,7 +34,17 @@ class VisionTransformer(_RuntimeOwner):
                 {emb.image_size[0]}*{emb.image_size[1]} expected by model")
         if image_patches_mask is not None and emb.mask_token is None:
             warnings.warn("image_patches_mask passed but use_image_masking in init was false. Ignoring.")
-        out = self._runtime().forward(images, image_patches_mask)
+        from ... import engine_coca_train as T
+        if T.wants_grad(self):   # training: forward keeps activations, the autograd node carries the explicit backward
+            rt = self._train_runtime()
+            (last,) = T.run(rt, (images, image_patches_mask), ())
+            hidden, rt.last_hidden = rt.last_hidden, None
+            B, S, d = hidden[0].shape
+            out = TransformerOutput(last_hidden_state=last.view(B, S, d), pooler_output=None, hidden_states=hidden,
+                                    attentions=None)
+        else:
+            with torch.no_grad():
+                out = self._runtime().forward(images, image_patches_mask)
         if self.pooler is not None:
             out = out._replace(pooler_output=self.pooler(out.last_hidden_state))
         return out
@@ -46,7 +55,13 @@ def _vit_runtime(mod):
     return VisionRuntime(mod)
 
 
+def _vit_train_runtime(mod):
+    from ...engine_coca_train import VisionTrainRuntime
+    return VisionTrainRuntime(mod)
+
+
 VisionTransformer._runtime_cls = staticmethod(_vit_runtime)
+VisionTransformer._train_runtime_cls = staticmethod(_vit_train_runtime)
 
 
 def vision_transformer(*, patch_size: int, hidden_dim: int, dim_feedforward: int, n_layer: int, n_head: int,

@@ -1,7 +1,8 @@
 """`AttentionPooler` / `CascadedAttentionPooler` — drop-in for torchmultimodal/modules/layers/attention_pooler.py
 :16-101.  Forward = `engine_coca.PoolerRuntime`: LayerNorm-ed keys/values projected by one packed GEMM, the learned
 queries projected once (they do not depend on the batch), cross-attention on the general attention kernel (head_dim 96
-for CoCa ViT-L/14), output projection + ln_post."""
+for CoCa ViT-L/14), output projection + ln_post.  With grad mode on and trainable parameters (or an input that requires grad) the call
+runs `engine_coca_train.PoolerTrainRuntime` under autograd (the learned queries' gradient is summed over the batch)."""
 from typing import List
 
 import torch
@@ -21,9 +22,13 @@ class AttentionPooler(_RuntimeOwner):
         self.ln_k = nn.LayerNorm(input_embed_dim, layer_norm_eps)
         self.ln_post = nn.LayerNorm(output_embed_dim, layer_norm_eps)
 
-    @torch.no_grad()
     def forward(self, x: Tensor) -> Tensor:
-        return self._runtime().forward(x)
+        from ... import engine_coca_train as T
+        if T.wants_grad(self) or (torch.is_grad_enabled() and x.requires_grad):
+            (out,) = T.run(self._train_runtime(), None, (x,))
+            return out.view(x.shape[0], self.query.shape[0], self.query.shape[1])
+        with torch.no_grad():
+            return self._runtime().forward(x)
 
 
 def _pool_runtime(mod):
@@ -31,7 +36,13 @@ def _pool_runtime(mod):
     return PoolerRuntime(mod, "pool")
 
 
+def _pool_train_runtime(mod):
+    from ...engine_coca_train import PoolerTrainRuntime
+    return PoolerTrainRuntime(mod)
+
+
 AttentionPooler._runtime_cls = staticmethod(_pool_runtime)
+AttentionPooler._train_runtime_cls = staticmethod(_pool_train_runtime)
 
 
 class CascadedAttentionPooler(nn.Module):
@@ -39,7 +50,6 @@ class CascadedAttentionPooler(nn.Module):
         super().__init__()
         self.poolers = nn.ModuleList(poolers)
 
-    @torch.no_grad()
     def forward(self, x: Tensor) -> List[Tensor]:
         pooler_outs = []
         for pooler in self.poolers:

@@ -317,6 +317,63 @@ def matmul_f32(A, B, *, ta=False, tb=False, out=None, alpha=1.0, accumulate=Fals
     return out
 
 
+def _gen_attn(q, k, v, B, Sq, Skv, H, hd, bsq, scale, mask, causal):
+    d = H * hd
+    qh = (q.view(1, Sq, H, hd).expand(B, Sq, H, hd) if bsq == 0 else q.reshape(B, Sq, H, hd)).transpose(1, 2)
+    kh, vh = k.reshape(B, Skv, H, hd).transpose(1, 2), v.reshape(B, Skv, H, hd).transpose(1, 2)
+    s = (qh @ kh.transpose(-1, -2)) * scale
+    if causal:
+        s = s + torch.full((Sq, Skv), float("-inf")).triu(1)
+    if mask is not None:
+        mk = mask.bool()
+        mk = mk.view(B, 1, Sq, Skv) if mk.numel() == B * Sq * Skv else mk.view(B, 1, 1, Skv)
+        s = s.masked_fill(~mk, float("-inf"))
+    p = torch.nan_to_num(torch.softmax(s, -1), nan=0.0)
+    return (p @ vh).transpose(1, 2).reshape(B * Sq, d)
+
+
+def attention_fwd_generic(q, k, v, out, *, B, Sq, Skv, H, head_dim, bsq, bsk, bsv, bso, scale, mask=None, mask_bs=0,
+                          mask_qs=0, causal=False):
+    out.copy_(_gen_attn(q.float(), k.float(), v.float(), B, Sq, Skv, H, head_dim, bsq, scale, mask, causal).to(BF))
+
+
+def attention_bwd_generic(q, k, v, dout, dk, dv, *, B, Sq, Skv, H, head_dim, bsq, bsk, bsv, bso, scale, dq=None,
+                          dq_f32=None, mask=None, mask_bs=0, mask_qs=0, causal=False):
+    qf, kf, vf = (t.float().clone().requires_grad_(True) for t in (q, k, v))
+    with torch.enable_grad():
+        _gen_attn(qf, kf, vf, B, Sq, Skv, H, head_dim, bsq, scale, mask, causal).backward(dout.float())
+    dk.copy_(kf.grad.to(BF))
+    dv.copy_(vf.grad.to(BF))
+    if dq is not None:
+        dq.copy_(qf.grad.to(BF))
+    if dq_f32 is not None:
+        dq_f32[:, :H * head_dim] += qf.grad
+
+
+def coca_text_embed_fwd(ids, emb, cls, pos, x, B, S, d, V):
+    e = emb.detach()[ids]
+    if cls is not None:
+        e = torch.cat([e, cls.detach().reshape(1, 1, d).expand(B, 1, d)], 1)
+    x.view(B, S, d).copy_(e + pos.detach().reshape(1, -1, d)[:, :S])
+
+
+def l2norm_fwd(x, y, y_bf16, inv_norm, B, E, eps=1e-12):
+    inv = 1.0 / x.detach().norm(dim=1).clamp_min(eps)
+    y.copy_(x.detach() * inv[:, None])
+    if y_bf16 is not None:
+        y_bf16.copy_(y.to(BF))
+    if inv_norm is not None:
+        inv_norm.copy_(inv)
+
+
+def l2norm_bwd(dy, y, inv_norm, dx, dx_bf16, B, E):
+    r = inv_norm[:, None] * (dy - y * (y * dy).sum(1, keepdim=True))
+    if dx is not None:
+        dx.copy_(r)
+    if dx_bf16 is not None:
+        dx_bf16.copy_(r.to(BF))
+
+
 NAMES = [n for n, f in list(globals().items()) if callable(f) and not n.startswith("_") and n not in ("install",)]
 
 

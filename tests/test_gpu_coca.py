@@ -22,6 +22,15 @@ def dev():
     return torch.device("cuda:0")
 
 
+@pytest.fixture(autouse=True)
+def _inference():
+    """This file pins the INFERENCE runtime (engine_coca.py); with grad mode on, trainable modules take the training
+    runtime instead (engine_coca_train.py, covered by tests/test_gpu_coca_train.py)."""
+    with torch.no_grad():
+        yield
+
+
+
 @pytest.mark.parametrize("B,Sq,Skv,H,D,shared_q,causal,mask_kind", [
     (3, 32, 64, 4, 96, True, False, None),      # pooler: batch-shared queries, head_dim 96
     (2, 256, 256, 8, 96, True, False, None),    # CoCa ViT-L/14 captioning pooler shape
@@ -116,11 +125,13 @@ def test_coca_forward_against_reference_golden(dev, name):
     e_mm = (o.multimodal_embeddings.cpu() - mm_ref).abs().max().item() / mm_ref.abs().max().item()
     print(f"{name}: |d img| {e_img:.2e} |d txt| {e_txt:.2e} rel d logits {e_mm:.2e}")
     assert e_img < 5e-3 and e_txt < 5e-3 and e_mm < 2e-2
-    from multimodal_b200._lib import MMBError
-    with pytest.raises(MMBError):     # forward-only runtime: asking for trainable losses must fail loudly
-        m(images, texts)
     with torch.no_grad():
         losses = m(images, texts)
+    with torch.enable_grad():         # grad mode on + trainable parameters: the autograd path, same values
+        tl = m(images, texts)
+    assert tl["contrastive"].requires_grad and tl["captioning"].requires_grad
+    assert abs(tl["contrastive"].item() - losses["contrastive"].item()) < 1e-2
+    assert abs(tl["captioning"].item() - losses["captioning"].item()) < 1e-2
     ref = CO.coca_forward(m.state_dict(), CC.CASES[name]["kwargs"], images.cpu(), texts.cpu())
     assert abs(losses["contrastive"].item() - ref["contrastive"].item()) < 1e-2
     assert abs(losses["captioning"].item() - ref["captioning"].item()) < 1e-2

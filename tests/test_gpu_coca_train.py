@@ -84,3 +84,129 @@ def test_attention_bwd_generic(dev, B, Sq, Skv, H, hd, kind):
     else:
         assert torch.isfinite(dq.float()).all()
         assert _rel(dq, qf.grad) < 1e-2
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# whole model: every parameter gradient of CoCaModel + the captioning head against autograd over the fp32 oracle
+# ---------------------------------------------------------------------------------------------------------------------
+def _cfg(kw):
+    cfg = dict(kw)
+    cfg.setdefault("pad_idx", 0)
+    return cfg
+
+
+def coca_grad_parity(dev, name, tag, with_contrastive=True, bar=5e-2):
+    """loss = captioning cross-entropy + <w_i, image_pooled> + <w_t, text_pooled> (fixed random w: exercises both
+    contrastive branches independently of the loss kernels) [+ the contrastive loss itself when with_contrastive]."""
+    import os
+
+    import coca_cases as CC
+    from oracle import coca_oracle as CO
+    from multimodal_b200.models.coca.coca_model import coca_for_pretraining, TrainHidden
+    from multimodal_b200.engine_coca_train import linear_cross_entropy
+
+    F = torch.nn.functional
+    m = CC.build(lambda **kw: coca_for_pretraining(**kw), name).to(dev).train()
+    cfg = _cfg(CC.CASES[name]["kwargs"])
+    inp = {k: v.to(dev) for k, v in CC.inputs(name).items()}
+    images, texts = inp["images"], inp["texts"]
+    sd = {k: v.detach().clone().requires_grad_(True) for k, v in m.state_dict().items()}
+
+    # ---- oracle with autograd intact (CO.coca_forward detaches: same composition from its parts)
+    x = CO.vision_encoder(images, sd, cfg)
+    H = cfg["pooler_n_head"]
+    if cfg.get("cascaded_pooler", True):
+        cap = CO.attention_pooler(x, sd, "model.vision_pooler.poolers.0", H)
+        con = CO.attention_pooler(cap, sd, "model.vision_pooler.poolers.1", H)
+    else:
+        both = CO.attention_pooler(x, sd, "model.vision_pooler", H)
+        con, cap = both[:, 0], both[:, 1:]
+    img = F.normalize(CO._lin(con, sd, "model.vision_proj"), dim=-1)
+    pooled, tokens = CO.text_decoder(texts, sd, cfg)
+    txt = F.normalize(pooled, dim=-1)
+    logits = CO.multimodal_decoder(tokens, cap, sd, cfg)
+    cap_ref = F.cross_entropy(logits.reshape(-1, logits.shape[-1]), texts[:, 1:].reshape(-1), ignore_index=cfg["pad_idx"])
+    gen = torch.Generator().manual_seed(21)
+    wi, wt = torch.randn(img.shape, generator=gen).to(dev), torch.randn(txt.shape, generator=gen).to(dev)
+    total_ref = cap_ref + (wi * img).sum() + (wt * txt).sum()
+    if with_contrastive:
+        a = img.squeeze(1) if img.dim() == 3 else img
+        T = torch.exp(sd["contrastive_loss.logit_scale"].clamp(0.0, 4.6052))
+        lab = torch.arange(a.shape[0], device=dev)
+        total_ref = total_ref + (F.cross_entropy(a @ txt.t() * T, lab) + F.cross_entropy(txt @ a.t() * T, lab)) / 2
+    total_ref.backward()
+
+    # ---- the drop-in under autograd
+    outs = m.model._forward_impl(images, texts, None, want_logits=False)
+    assert isinstance(outs.multimodal_embeddings, TrainHidden)
+    cap_loss = linear_cross_entropy(outs.multimodal_embeddings.hidden, outs.multimodal_embeddings.projection,
+                                    texts[:, 1:].contiguous(), m.caption_loss.ignore_index)
+    assert abs(cap_loss.item() - cap_ref.item()) < 2e-2 * max(1.0, abs(cap_ref.item())), (cap_loss.item(), cap_ref.item())
+    total = cap_loss + (wi * outs.image_pooled_output).sum() + (wt * outs.text_pooled_output).sum()
+    if with_contrastive:
+        io = outs.image_pooled_output
+        total = total + m.contrastive_loss(io.squeeze(1) if io.dim() == 3 else io, outs.text_pooled_output)
+    assert abs(total.item() - total_ref.item()) < 3e-2 * max(1.0, abs(total_ref.item())), (total.item(), total_ref.item())
+    total.backward()
+
+    rows = []
+    for k, p in m.named_parameters():
+        ref = sd[k].grad
+        if ref is None or ref.norm().item() == 0.0:
+            assert p.grad is None or p.grad.abs().max().item() < 1e-5, k
+            continue
+        assert p.grad is not None and torch.isfinite(p.grad).all(), k
+        if k.endswith("k_proj.bias"):      # exactly zero in exact arithmetic (softmax shift invariance)
+            continue
+        if k == "model.text_decoder.embeddings.token_embeddings.weight" and m.model.text_decoder.embeddings.token_embeddings.padding_idx is not None:
+            pad = m.model.text_decoder.embeddings.token_embeddings.padding_idx
+            assert p.grad[pad].abs().max().item() == 0.0
+            ref = ref.clone()
+            ref[pad] = 0
+        rows.append((k, _rel(p.grad, ref)))
+    report = [f"{tag}: total ours {total.item():.6f} oracle {total_ref.item():.6f}; captioning {cap_loss.item():.6f} / {cap_ref.item():.6f}"]
+    errs = sorted(r[1] for r in rows)
+    report.append(f"relative-L2 gradient error over {len(rows)} parameter tensors: median {errs[len(errs) // 2]:.3e} max {errs[-1]:.3e}")
+    report += [f"{k:80s} rel {a:.3e}" for k, a in sorted(rows, key=lambda r: -r[1])[:20]]
+    print("\n".join(report))
+    try:
+        os.makedirs("gpurun_out", exist_ok=True)
+        open(f"gpurun_out/coca_grad_parity_{tag}.txt", "w").write("\n".join(report) + "\n")
+    except OSError:
+        pass
+    assert len(rows) > 40
+    for k, a in rows:
+        assert a < bar, (k, a)
+    return m
+
+
+@pytest.mark.parametrize("name", ["coca_small", "coca_parallel"])
+def test_coca_gradients_against_fp32_oracle(dev, name):
+    old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = False
+    try:
+        coca_grad_parity(dev, name, name, with_contrastive=(name == "coca_parallel"))
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+
+
+def test_coca_for_pretraining_step_trains(dev):
+    """CoCaForPretraining.forward under autograd: both losses carry a graph, three SGD steps lower their sum."""
+    import coca_cases as CC
+    from multimodal_b200.models.coca.coca_model import coca_for_pretraining
+
+    name = "coca_parallel"     # B = 8: the contrastive loss runs on its exact-fp32 SIMT path
+    m = CC.build(lambda **kw: coca_for_pretraining(**kw), name).to(dev).train()
+    inp = {k: v.to(dev) for k, v in CC.inputs(name).items()}
+    opt = torch.optim.SGD(m.parameters(), lr=0.02)
+    hist = []
+    for _ in range(4):
+        opt.zero_grad(set_to_none=True)
+        out = m(inp["images"], inp["texts"])
+        total = out["contrastive"] + out["captioning"]
+        assert total.requires_grad and torch.isfinite(total)
+        total.backward()
+        hist.append(total.item())
+        opt.step()
+    print("CoCaForPretraining total loss over SGD steps:", hist)
+    assert hist[-1] < hist[0], hist
