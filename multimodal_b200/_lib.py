@@ -58,10 +58,15 @@ def build(force: bool = False, verbose: bool = False) -> Path:
             raise RuntimeError(f"nvcc failed for {s}:\n{out}")
         if verbose and out:
             print(out)
-    link = [nvcc, "-shared", "-o", str(LIB_PATH), *map(str, objs), "-lcudart_static", "-ldl", "-lpthread", "-lrt"]
+    # link into a temporary name and rename: a concurrent reader (another rank importing the package, a snapshot of
+    # the tree) never sees a half-written library
+    tmp = LIB_PATH.with_name(LIB_PATH.name + f".tmp{os.getpid()}")
+    link = [nvcc, "-shared", "-o", str(tmp), *map(str, objs), "-lcudart_static", "-ldl", "-lpthread", "-lrt"]
     r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
+        tmp.unlink(missing_ok=True)
         raise RuntimeError(f"link failed:\n{r.stdout}")
+    os.replace(tmp, LIB_PATH)
     return LIB_PATH
 
 
