@@ -298,6 +298,19 @@ int mmb_matmul_f32(const float* A, long long lda, int ta, const float* B, long l
 int mmb_sum_scale(const float* in, int n, float scale, float* out, int accumulate, void* stream);
 
 
+/* ---- GPU input pipeline, image half ------------------------------------------------------------- */
+/* The CLIP image transform on decoded uint8 RGB images, bit-exact with the reference's PIL / torchvision pipeline
+ * (torchmultimodal/transforms/clip_transform.py:300-352: Resize(BICUBIC) + CenterCrop, or RandomResizedCrop with the crop
+ * box sampled by the host, then ToTensor + Normalize).  src_ptrs: DEVICE array of n device pointers to HWC uint8 images;
+ * geom: DEVICE int32 [n, 12] = {H, W, row pitch (bytes), box_left, box_top, box_w, box_h (the region that is resized, as a
+ * standalone image), rw, rh (size it is resized to), crop_left, crop_top (offset of the out x out window in the resized
+ * region), flags (bit0: horizontal pass needed = rw != box_w, bit1: vertical pass needed = rh != box_h)};
+ * table: DEVICE int32 scratch [n, 2, out, 2 + mmb_clip_image_transform_max_taps()]; outp: fp32 [n, 3, out, out];
+ * mean3 / std3: HOST float[3].  The caller guarantees ceil(2 * max(box/r, 1)) * 2 + 1 <= max_taps for both axes. */
+int mmb_clip_image_transform_max_taps(void);
+int mmb_clip_image_transform(const void* src_ptrs, const int* geom, int* table, float* outp, int n_images, int out,
+                             const float* mean3_host, const float* std3_host, void* stream);
+
 /* ---- symmetric (CUDA-IPC peer-mapped) memory: the loss path's replacement for NCCL all_gather ----------------- */
 /* Replaces torch.distributed(.nn.functional).all_gather at utils/distributed.py:47-52: every rank allocates one
  * buffer, exchanges the 64-byte IPC handles once (host side, any transport), maps the peers' buffers, and the

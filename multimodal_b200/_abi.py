@@ -67,6 +67,8 @@ PROTOTYPES = {
     "mmb_scatter_rows_idx_add": (i32, [vp, vp, vp, ll, i32, i32, vp]),
     "mmb_ce_labels_bwd": (i32, [vp, ll, vp, ll, ll, i32, i32, vp, f32, vp, vp, ll, vp]),
     "mmb_act_bwd": (i32, [vp, vp, vp, ll, i32, vp]),
+    "mmb_clip_image_transform_max_taps": (i32, []),
+    "mmb_clip_image_transform": (i32, [vp, vp, vp, vp, i32, i32, vp, vp, vp]),
     "mmb_attention_bwd_generic": (i32, [vp, ll, ll, vp, ll, ll, vp, ll, ll, vp, ll, ll, vp, ll, ll, vp, vp, ll, vp, vp, vp,
                                         i32, i32, i32, i32, i32, i32, f32, vp]),
 }

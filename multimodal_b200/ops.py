@@ -520,3 +520,24 @@ def attention_bwd_generic(q, k, v, dout, dk, dv, *, B, Sq, Skv, H, head_dim, bsq
         int(bso), _p(mask), int(mask_bs), int(mask_qs), _p(dq), _p(dq_f32), dq_f32.stride(0) if dq_f32 is not None else 0,
         _p(dk), _p(dv), _p(scratch), B, Sq, Skv, H, head_dim, int(causal), float(scale), _stream()),
         "mmb_attention_bwd_generic")
+
+
+# ---- GPU input pipeline (image transform) -----------------------------------------------------------------------
+def clip_image_transform_max_taps() -> int:
+    return int(_lib.lib().mmb_clip_image_transform_max_taps())
+
+
+def clip_image_transform(src_ptrs, geom, out, mean, std):
+    """src_ptrs int64 [n] (device pointers of HWC uint8 images), geom int32 [n, 12] (include/mmb200.h), out fp32
+    [n, 3, S, S]; mean / std: 3 Python floats each."""
+    _chk(src_ptrs, torch.int64, "src_ptrs"); _chk(geom, torch.int32, "geom"); _chk(out, torch.float32, "out")
+    n, _, S, S2 = out.shape
+    if S != S2 or tuple(geom.shape) != (n, 12) or src_ptrs.numel() != n or not (geom.is_contiguous() and out.is_contiguous()):
+        raise MMBError("clip_image_transform: expected geom [n, 12], src_ptrs [n], out [n, 3, S, S] (contiguous)")
+    table = torch.empty((n, 2, S, 2 + clip_image_transform_max_taps()), device=out.device, dtype=torch.int32)
+    m3 = (ctypes.c_float * 3)(*[float(v) for v in mean])
+    s3 = (ctypes.c_float * 3)(*[float(v) for v in std])
+    _lib.check(_lib.lib().mmb_clip_image_transform(_p(src_ptrs), _p(geom), _p(table), _p(out), n, S,
+                                                   ctypes.cast(m3, ctypes.c_void_p), ctypes.cast(s3, ctypes.c_void_p),
+                                                   _stream()), "mmb_clip_image_transform")
+    return out
