@@ -547,3 +547,52 @@ def linear_f32(x: torch.Tensor, linear: nn.Linear) -> torch.Tensor:
 def linear_cross_entropy(hidden: torch.Tensor, linear: nn.Linear, labels: torch.Tensor, ignore_index: int) -> torch.Tensor:
     return LinearCrossEntropyFunction.apply(hidden.reshape(-1, hidden.shape[-1]), linear.weight, linear.bias, labels,
                                             ignore_index)
+
+
+class LayersTrainRuntime:
+    """A standalone pre-norm `TransformerEncoderLayer` or `TransformerEncoder` (modules/layers/transformer.py:31-259) called
+    on its own under autograd: hidden_states [B, S, d] in (differentiable), residual stream (and final LayerNorm) out."""
+
+    def __init__(self, owner: nn.Module, layers, final_ln: Optional[nn.Module]):
+        self.s = _Stack(owner, layers, "lyr", causal=False)
+        self.store = self.s.store
+        self.final_ln = final_ln
+
+    def forward(self, data, diff):
+        (mask_u8,) = data
+        (x,) = diff
+        s = self.s
+        B, S, d = x.shape
+        self.store.refresh()
+        save = Workspace(s.device)
+        X0 = torch.empty((B * S, d), device=s.device, dtype=torch.float32)
+        X0.view(B, S, d).copy_(x)
+        XM, Y = s.stack.forward(X0, B, S, True, save=save, mask3=mask_u8)
+        XF, LAST = s.finish(XM, Y, B * S, self.final_ln, save)
+        save.B, save.S = B, S
+        self.last_hidden = ([X0.view(B, S, d)] + [save.bufs[f"lyr.XA.{l}"].view(B, S, d) for l in range(1, s.L)]
+                            + [XF.view(B, S, d)])
+        return ((LAST if LAST is not None else XF),), save
+
+    def backward(self, save, dOUT):
+        s = self.s
+        d, B, S = s.d, save.B, save.S
+        M = B * S
+        fln = self.final_ln
+        dOUT = _f32(dOUT, (M, d))
+        G, Gb, done = s.start_backward(save, M, fln, dOUT if fln is not None else None, None if fln is not None else dOUT)
+        G = s.stack.backward(G, Gb, B, S, top_bias_done=done, save=save)
+        return (G.view(B, S, d).clone(),)
+
+
+def standalone_layers(owner: nn.Module, layers, final_ln, hidden_states: torch.Tensor, mask_u8):
+    """-> (output [B, S, d] with autograd history, hidden_states list) for a standalone layer / encoder call."""
+    ids = [(id(p), p.device) for p in owner.parameters()]
+    rt = getattr(owner, "_mmb_trt", None)
+    if rt is None or getattr(owner, "_mmb_trt_ids", None) != ids:
+        rt = LayersTrainRuntime(owner, layers, final_ln)
+        object.__setattr__(owner, "_mmb_trt", rt)
+        object.__setattr__(owner, "_mmb_trt_ids", ids)
+    (out,) = run(rt, (mask_u8,), (hidden_states.float(),))
+    hidden, rt.last_hidden = rt.last_hidden, None
+    return out.view(hidden_states.shape), hidden

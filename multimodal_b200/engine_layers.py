@@ -7,8 +7,10 @@ exposes — and tests — on their own are callable outside an encoder:
   modules/layers/mlp.py:13-66                    MLP ([Linear, activation, Linear] form)
 
 They launch exactly the kernels the fused encoder schedules launch (tcgen05 GEMMs with bias / activation epilogues,
-tcgen05 attention, the add+LayerNorm kernel); nothing is computed by PyTorch.  Forward values only: there is no
-autograd graph, and asking for one (grad mode on, trainable parameters) raises instead of returning detached tensors.
+tcgen05 attention, the add+LayerNorm kernel); nothing is computed by PyTorch.  Pre-norm `TransformerEncoderLayer` /
+`TransformerEncoder` also train on their own (grad mode on: `engine_coca_train.LayersTrainRuntime`, the CLIP towers' fused
+forward / backward schedule); the other standalone modules compute forward values only, and asking them for an autograd
+graph raises instead of returning detached tensors.
 Shape limits are those of the kernels: head_dim 64 (fused attention; 96 / 128 and arbitrary boolean masks go through
 the general kernel), feature sizes multiples of 8, 3-channel images.
 """
@@ -30,6 +32,10 @@ def forward_only_guard(mod: nn.Module, what: str) -> None:
     if torch.is_grad_enabled() and any(p.requires_grad for p in mod.parameters()):
         raise MMBError(f"{what} (multimodal_b200) computes forward values only when called on its own — its backward "
                        "exists inside the CLIP towers' fused schedule.  Call it under torch.no_grad().")
+
+
+def _wants_graph(mod: nn.Module, x: torch.Tensor) -> bool:
+    return torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in mod.parameters()))
 
 
 def _cuda(t: torch.Tensor, what: str) -> None:
@@ -143,7 +149,14 @@ def mlp_forward(mod: nn.Module, x: torch.Tensor) -> torch.Tensor:
 def encoder_layer_forward(mod: nn.Module, hidden_states: torch.Tensor,
                           attention_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
     """TransformerEncoderLayer.forward (transformer.py:95-154), pre-norm (:95-111) and post-norm (:113-128)."""
-    forward_only_guard(mod, "TransformerEncoderLayer")
+    if _wants_graph(mod, hidden_states):
+        if not mod.norm_first:
+            raise MMBError("standalone post-norm TransformerEncoderLayer has no backward schedule; call it under "
+                           "torch.no_grad()")
+        from .engine_coca_train import standalone_layers
+        B, S, _ = hidden_states.shape
+        return standalone_layers(mod, [mod], None, hidden_states,
+                                 _bool_mask_u8(attention_mask, B, S, "TransformerEncoderLayer"))[0]
     _cuda(hidden_states, "TransformerEncoderLayer")
     B, S, d = hidden_states.shape
     at, mlp = mod.attention, mod.feedforward.model
@@ -194,7 +207,14 @@ def encoder_forward(mod: nn.Module, hidden_states: torch.Tensor, attention_mask:
     """TransformerEncoder.forward (transformer.py:216-259): the layers (+ optional final LayerNorm)."""
     from .modules.layers.transformer import TransformerOutput
 
-    forward_only_guard(mod, "TransformerEncoder")
+    if _wants_graph(mod, hidden_states):
+        if not all(layer.norm_first for layer in mod.layer):
+            raise MMBError("standalone post-norm TransformerEncoder has no backward schedule; call it under torch.no_grad()")
+        from .engine_coca_train import standalone_layers
+        B, S, _ = hidden_states.shape
+        out, hidden = standalone_layers(mod, mod.layer, mod.final_layer_norm, hidden_states,
+                                        _bool_mask_u8(attention_mask, B, S, "TransformerEncoder"))
+        return TransformerOutput(last_hidden_state=out, hidden_states=hidden if return_hidden_states else None)
     _cuda(hidden_states, "TransformerEncoder")
     x = hidden_states
     all_hidden = [x] if return_hidden_states else None

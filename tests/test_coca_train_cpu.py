@@ -17,3 +17,8 @@ def emu(monkeypatch):
 @pytest.mark.parametrize("name", list(CC.CASES))
 def test_coca_training_schedule_against_oracle_with_emulated_kernels(emu, name):
     G.coca_grad_parity(torch.device("cpu"), name, "cpu_emu_" + name, with_contrastive=False)
+
+
+@pytest.mark.parametrize("masked", [False, True])
+def test_standalone_encoder_layers_train_with_emulated_kernels(emu, masked):
+    G.standalone_layers_grad_parity(torch.device("cpu"), masked)

@@ -210,3 +210,80 @@ def test_coca_for_pretraining_step_trains(dev):
         opt.step()
     print("CoCaForPretraining total loss over SGD steps:", hist)
     assert hist[-1] < hist[0], hist
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# standalone pre-norm TransformerEncoderLayer / TransformerEncoder under autograd
+# ---------------------------------------------------------------------------------------------------------------------
+def _encoder_ref(mod, x, mask):
+    """fp32 torch restatement of modules/layers/transformer.py:95-111, 216-259 (pre-norm) on the module's parameters."""
+    F = torch.nn.functional
+    layers = list(mod.layer) if hasattr(mod, "layer") else [mod]
+    for layer in layers:
+        at, mlp = layer.attention, layer.feedforward.model
+        B, S, d = x.shape
+        H = at.num_heads
+        h = F.layer_norm(x, (d,), layer.attention_layernorm.weight, layer.attention_layernorm.bias, layer.attention_layernorm.eps)
+        q, k, v = (t.view(B, S, H, d // H).transpose(1, 2) for t in F.linear(h, at.input_proj.weight, at.input_proj.bias).chunk(3, -1))
+        s = q @ k.transpose(-1, -2) / math.sqrt(d // H)
+        if mask is not None:
+            s = s.masked_fill(~mask.view(B, 1, S, S), float("-inf"))
+        a = (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(B, S, d)
+        x = x + F.linear(a, at.output_proj.weight, at.output_proj.bias)
+        h = F.layer_norm(x, (d,), layer.feedforward_layernorm.weight, layer.feedforward_layernorm.bias, layer.feedforward_layernorm.eps)
+        x = x + F.linear(F.gelu(F.linear(h, mlp[0].weight, mlp[0].bias)), mlp[-1].weight, mlp[-1].bias)
+    fln = getattr(mod, "final_layer_norm", None)
+    if fln is not None:
+        x = F.layer_norm(x, (x.shape[-1],), fln.weight, fln.bias, fln.eps)
+    return x
+
+
+def standalone_layers_grad_parity(dev, masked):
+    import copy
+
+    from multimodal_b200.modules.layers.transformer import TransformerEncoder
+
+    torch.manual_seed(0)
+    m = TransformerEncoder(n_layer=2, d_model=128, n_head=2, dim_feedforward=256, activation=torch.nn.GELU,
+                           layer_norm_eps=1e-5, norm_first=True, final_layer_norm_eps=1e-5).to(dev)
+    with torch.no_grad():
+        for p in m.parameters():
+            p.add_(0.05 * torch.randn_like(p))
+    ref_m = copy.deepcopy(m)
+    B, S = 3, 19
+    x = torch.randn(B, S, 128, device=dev)
+    mask = None
+    if masked:
+        mask = torch.rand(B, S, S, device=dev) < 0.7
+        mask[:, :, 0] = True
+    w = torch.randn(B, S, 128, device=dev) / 11
+    xr = x.clone().requires_grad_(True)
+    (_encoder_ref(ref_m, xr, mask) * w).sum().backward()
+    xo = x.clone().requires_grad_(True)
+    out = m(xo, mask, return_hidden_states=True)
+    assert out.last_hidden_state.requires_grad and len(out.hidden_states) == 3
+    (out.last_hidden_state * w).sum().backward()
+    assert _rel(xo.grad, xr.grad) < 5e-2
+    for (k, p), (_, q) in zip(m.named_parameters(), ref_m.named_parameters()):
+        assert p.grad is not None, k
+        assert _rel(p.grad, q.grad) < 5e-2, (k, _rel(p.grad, q.grad))
+    # a single layer called on its own
+    layer, ref_l = m.layer[0], ref_m.layer[0]
+    for p in list(layer.parameters()) + list(ref_l.parameters()):
+        p.grad = None
+    xr = x.clone().requires_grad_(True)
+    (_encoder_ref(ref_l, xr, mask) * w).sum().backward()
+    xo = x.clone().requires_grad_(True)
+    (layer(xo, mask) * w).sum().backward()
+    assert _rel(xo.grad, xr.grad) < 5e-2
+    assert _rel(layer.feedforward.model[0].weight.grad, ref_l.feedforward.model[0].weight.grad) < 5e-2
+
+
+@pytest.mark.parametrize("masked", [False, True])
+def test_standalone_encoder_layers_train(dev, masked):
+    old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = False
+    try:
+        standalone_layers_grad_parity(dev, masked)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
