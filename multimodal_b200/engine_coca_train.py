@@ -454,32 +454,53 @@ def run(rt, data, diff: Sequence[torch.Tensor] = ()) -> Tuple[torch.Tensor, ...]
 
 
 class LinearF32Function(torch.autograd.Function):
-    """y = x @ W^T (+ b) for a 2-D fp32 x, tensor-core GEMMs both ways (dims multiples of 8)."""
+    """y = x @ W^T (+ b) for a 2-D fp32 x, tensor-core GEMMs both ways.  The output width is padded to a multiple of 8
+    internally (bf16 rows of d y must be 16-byte multiples for the TMA operands of the backward GEMMs)."""
 
     @staticmethod
     def forward(ctx, x, weight, bias):
+        N, K = weight.shape
+        Np = (N + 7) // 8 * 8
+        dev = x.device
         xb = ops.cast_bf16(x.detach().contiguous().float())
         wb = ops.cast_bf16(weight.detach().contiguous())
-        out = torch.empty((xb.shape[0], wb.shape[0]), device=x.device, dtype=torch.float32)
-        ops.gemm(xb, wb, bias=bias.detach().float().contiguous() if bias is not None else None, epilogue=ops.EPI_F32, out=out)
+        bp = bias.detach().float().contiguous() if bias is not None else None
+        if Np != N:
+            wp = torch.zeros((Np, K), device=dev, dtype=torch.bfloat16)
+            wp[:N].copy_(wb)
+            wb = wp
+            if bp is not None:
+                b2 = torch.zeros(Np, device=dev, dtype=torch.float32)
+                b2[:N].copy_(bp)
+                bp = b2
+        out = torch.empty((xb.shape[0], Np), device=dev, dtype=torch.float32)
+        ops.gemm(xb, wb, bias=bp, epilogue=ops.EPI_F32, out=out)
         ctx.save_for_backward(xb, wb)
-        ctx.has_bias = bias is not None
-        return out
+        ctx.has_bias, ctx.N = bias is not None, N
+        return out[:, :N]
 
     @staticmethod
     def backward(ctx, dy):
         xb, wb = ctx.saved_tensors
-        dyb = ops.cast_bf16(dy.contiguous().float())
+        N, Np = ctx.N, wb.shape[0]
+        dyf = dy.contiguous().float()
+        if Np != N:
+            pad = torch.zeros((dyf.shape[0], Np), device=dy.device, dtype=torch.float32)
+            pad[:, :N].copy_(dyf)
+            dyf = pad
+        dyb = ops.cast_bf16(dyf)
         dx = dW = db = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty(xb.shape, device=dy.device, dtype=torch.float32)
             ops.gemm(dyb, wb, b_mn=True, epilogue=ops.EPI_F32, out=dx)
         if ctx.needs_input_grad[1]:
-            dW = torch.empty(wb.shape, device=dy.device, dtype=torch.float32)
-            ops.gemm(dyb, xb, a_mn=True, b_mn=True, epilogue=ops.EPI_F32, out=dW)
+            gw = torch.empty(wb.shape, device=dy.device, dtype=torch.float32)
+            ops.gemm(dyb, xb, a_mn=True, b_mn=True, epilogue=ops.EPI_F32, out=gw)
+            dW = gw[:N]
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            db = torch.zeros(wb.shape[0], device=dy.device, dtype=torch.float32)
-            ops.colsum_bf16(dyb, db, dyb.shape[0], wb.shape[0], wb.shape[0])
+            gb = torch.zeros(Np, device=dy.device, dtype=torch.float32)
+            ops.colsum_bf16(dyb, gb, dyb.shape[0], Np, Np)
+            db = gb[:N]
         return dx, dW, db
 
 
