@@ -108,9 +108,11 @@ def coca_grad_parity(dev, name, tag, with_contrastive=True, bar=5e-2):
     F = torch.nn.functional
     m = CC.build(lambda **kw: coca_for_pretraining(**kw), name).to(dev).train()
     cfg = _cfg(CC.CASES[name]["kwargs"])
-    inp = {k: v.to(dev) for k, v in CC.inputs(name).items()}
-    images, texts = inp["images"], inp["texts"]
-    sd = {k: v.detach().clone().requires_grad_(True) for k, v in m.state_dict().items()}
+    cpu_inp = CC.inputs(name)
+    inp = {k: v.to(dev) for k, v in cpu_inp.items()}
+    # the oracle builds its masks on the CPU: it runs there (fp32), the drop-in on `dev`
+    sd = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in m.state_dict().items()}
+    images, texts = cpu_inp["images"], cpu_inp["texts"]
 
     # ---- oracle with autograd intact (CO.coca_forward detaches: same composition from its parts)
     x = CO.vision_encoder(images, sd, cfg)
@@ -127,16 +129,17 @@ def coca_grad_parity(dev, name, tag, with_contrastive=True, bar=5e-2):
     logits = CO.multimodal_decoder(tokens, cap, sd, cfg)
     cap_ref = F.cross_entropy(logits.reshape(-1, logits.shape[-1]), texts[:, 1:].reshape(-1), ignore_index=cfg["pad_idx"])
     gen = torch.Generator().manual_seed(21)
-    wi, wt = torch.randn(img.shape, generator=gen).to(dev), torch.randn(txt.shape, generator=gen).to(dev)
+    wi, wt = torch.randn(img.shape, generator=gen), torch.randn(txt.shape, generator=gen)
     total_ref = cap_ref + (wi * img).sum() + (wt * txt).sum()
     if with_contrastive:
         a = img.squeeze(1) if img.dim() == 3 else img
         T = torch.exp(sd["contrastive_loss.logit_scale"].clamp(0.0, 4.6052))
-        lab = torch.arange(a.shape[0], device=dev)
+        lab = torch.arange(a.shape[0])
         total_ref = total_ref + (F.cross_entropy(a @ txt.t() * T, lab) + F.cross_entropy(txt @ a.t() * T, lab)) / 2
     total_ref.backward()
 
     # ---- the drop-in under autograd
+    images, texts, wi, wt = inp["images"], inp["texts"], wi.to(dev), wt.to(dev)
     outs = m.model._forward_impl(images, texts, None, want_logits=False)
     assert isinstance(outs.multimodal_embeddings, TrainHidden)
     cap_loss = linear_cross_entropy(outs.multimodal_embeddings.hidden, outs.multimodal_embeddings.projection,
@@ -163,7 +166,7 @@ def coca_grad_parity(dev, name, tag, with_contrastive=True, bar=5e-2):
             assert p.grad[pad].abs().max().item() == 0.0
             ref = ref.clone()
             ref[pad] = 0
-        rows.append((k, _rel(p.grad, ref)))
+        rows.append((k, _rel(p.grad.cpu(), ref)))
     report = [f"{tag}: total ours {total.item():.6f} oracle {total_ref.item():.6f}; captioning {cap_loss.item():.6f} / {cap_ref.item():.6f}"]
     errs = sorted(r[1] for r in rows)
     report.append(f"relative-L2 gradient error over {len(rows)} parameter tensors: median {errs[len(errs) // 2]:.3e} max {errs[-1]:.3e}")
