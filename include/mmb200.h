@@ -311,6 +311,19 @@ int mmb_clip_image_transform_max_taps(void);
 int mmb_clip_image_transform(const void* src_ptrs, const int* geom, int* table, float* outp, int n_images, int out,
                              const float* mean3_host, const float* std3_host, void* stream);
 
+/* ---- input pipeline, text half: host-side byte-level BPE (no device work) ------------------------------------------- */
+/* The merge loop of CLIPBPETokenizer (torchmultimodal/transforms/clip_transform.py:82-190) as native host code.
+ * mmb_bpe_create: merges_utf8 = the whole merges file (header line dropped, then num_merges lines; <= 0: all), bos / eos
+ * = the special-token strings; returns an opaque handle and the vocabulary size (512 + merges + 2).
+ * mmb_bpe_encode: words = concatenated UTF-8 bytes of the lower-cased, regex-split word pieces of a batch, piece i =
+ * [offsets[i], offsets[i+1]); out_ids (capacity offsets[n_words]) receives the ids, out_counts[i] their number per piece.
+ * mmb_bpe_token_id: id of a vocabulary string (-1 if absent).  Thread-safe per handle (internal word cache). */
+int mmb_bpe_create(const char* merges_utf8, long long n_bytes, int num_merges, const char* bos, const char* eos,
+                   void** handle, int* vocab_size);
+int mmb_bpe_encode(void* handle, const char* words, const long long* offsets, int n_words, int* out_ids, int* out_counts);
+int mmb_bpe_token_id(void* handle, const char* token);
+int mmb_bpe_destroy(void* handle);
+
 /* ---- symmetric (CUDA-IPC peer-mapped) memory: the loss path's replacement for NCCL all_gather ----------------- */
 /* Replaces torch.distributed(.nn.functional).all_gather at utils/distributed.py:47-52: every rank allocates one
  * buffer, exchanges the 64-byte IPC handles once (host side, any transport), maps the peers' buffers, and the
