@@ -38,7 +38,7 @@ def _act_code(act: nn.Module) -> int:
     raise MMBError(f"unsupported MLP activation {type(act).__name__} on the accelerated path (nn.GELU only)")
 
 
-def _qkv_first(layers, extra_first=()) -> List[nn.Parameter]:
+def _qkv_first(layers) -> List[nn.Parameter]:
     """Parameter order that makes the separate q / k / v (and cross k / v) projections packable."""
     out: List[nn.Parameter] = []
     for layer in layers:

@@ -398,7 +398,7 @@ def first_token_linear(x: torch.Tensor, linear: nn.Linear, use_tanh: bool = Fals
     return FirstTokenLinearFunction.apply(x, linear.weight, linear.bias, use_tanh)
 
 
-def encoder_output(rt, data, diff, pooler: Optional[nn.Module], B_S_d=None) -> TransformerOutput:
+def encoder_output(rt, data, diff, pooler: Optional[nn.Module]) -> TransformerOutput:
     """Training-mode TransformerOutput of one encoder call (pooler applied through FirstTokenLinearFunction)."""
     LAST, XF, hidden = run_encoder(rt, data, diff)
     B, S, d = hidden[0].shape

@@ -16,7 +16,6 @@ import torch
 from torch import nn, Tensor
 
 from .. import _lib
-from .._lib import MMBError
 from .clip_transform import CLIP_DEFAULT_MEAN, CLIP_DEFAULT_STD, CLIPImageTransform
 
 CLIP_DEFAULT_VOCAB_BPE_PATH = "http://download.pytorch.org/models/text/clip_merges.bpe"
