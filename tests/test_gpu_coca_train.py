@@ -188,7 +188,7 @@ def test_coca_gradients_against_fp32_oracle(dev, name):
     old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
     torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = False
     try:
-        coca_grad_parity(dev, name, name, with_contrastive=(name == "coca_parallel"))
+        coca_grad_parity(dev, name, name, with_contrastive=(name == "coca_parallel"), bar=4e-2)   # measured max 1.8e-2
     finally:
         torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
 

@@ -4,8 +4,8 @@ fp32 oracle (oracle/flava_oracle.py, the restatement pinned to the reference gol
 
 Tolerance: GEMM operands (activations, weights, gradients) are rounded to bf16 with fp32 accumulation, fp32 residual
 stream / LayerNorm / softmax statistics; a parameter-gradient tensor must agree with the fp32 oracle to a relative L2
-error below 6e-2 (d = 128 toy widths, B = 3: few rows per reduction, so the rounding noise does not average out as in
-the full-size CLIP test where the same kernels measure 1.6e-2) and cosine > 0.995.  A wrong mask, a dropped tile or a
+error below 3e-2 and cosine > 0.995 (measured on B200: max 1.3e-2 at the toy widths, 1.2e-2 at d = 768; heads 5.1e-3 with
+a bar of 1.5e-2; the full-size CLIP test measures 1.6e-2 with the same kernels).  A wrong mask, a dropped tile or a
 mis-routed gradient moves a tensor to O(1).  `key.bias` gradients are exactly zero in exact arithmetic (softmax is
 shift-invariant); they are checked against the size of the matching `query.bias` gradient instead.
 """
@@ -258,13 +258,13 @@ def test_flava_small_gradients_against_fp32_oracle(dev):
 
     name = "flava_small"
     m = FC.build(flava_model, name)
-    m = _grad_parity(dev, m, _cfg(FC.CASES[name]["kwargs"]), FC.inputs(name), "small", 6e-2)
+    m = _grad_parity(dev, m, _cfg(FC.CASES[name]["kwargs"]), FC.inputs(name), "small", 3e-2)   # measured max 1.3e-2
     # a second step on the same module: shadows follow an in-place parameter update, saved state is per call
     with torch.no_grad():
         for p in m.parameters():
             p.add_(0.01 * torch.randn_like(p))
             p.grad = None
-    _grad_parity(dev, m, _cfg(FC.CASES[name]["kwargs"]), FC.inputs(name), "small_step2", 6e-2)
+    _grad_parity(dev, m, _cfg(FC.CASES[name]["kwargs"]), FC.inputs(name), "small_step2", 3e-2)
 
 
 def test_flava_base_width_gradients_against_fp32_oracle(dev):
@@ -289,7 +289,7 @@ def test_flava_base_width_gradients_against_fp32_oracle(dev):
     tm = text.clone()
     tm[:, 3] = 999
     pm = torch.rand(B, 196, generator=gen) < 0.4
-    _grad_parity(dev, m, _cfg(kw), dict(image=image, text=text, text_masked=tm, image_patches_mask=pm), "base", 4e-2)
+    _grad_parity(dev, m, _cfg(kw), dict(image=image, text=text, text_masked=tm, image_patches_mask=pm), "base", 3e-2)   # measured max 1.2e-2
 
 
 def test_flava_mm_encoder_direct_call_and_frozen_parts(dev):
@@ -410,7 +410,7 @@ def _loss_grad_parity(dev, name, contrastive_weight, tag, bar=4e-2):
 def test_pretraining_loss_gradients_against_fp32_oracle(dev, name):
     """MLM / MIM (unimodal branch) and ITM / MMM text / MMM image (multimodal branch) + the global contrastive loss over
     the positive pairs: every head parameter's gradient and the gradient w.r.t. every incoming sequence."""
-    _loss_grad_parity(dev, name, 1.0, name)
+    _loss_grad_parity(dev, name, 1.0, name, bar=1.5e-2)   # measured max 5.1e-3 (profiles/r2b_flava_heads_grad_parity_*.txt)
 
 
 def test_flava_for_pretraining_step_trains(dev):
