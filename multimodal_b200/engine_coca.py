@@ -1,4 +1,5 @@
-"""Forward runtime of the CoCa model family (BASELINE.json config 5 / SURVEY.md §8 a14; forward only).
+"""Forward runtime of the CoCa model family (BASELINE.json config 5 / SURVEY.md §8 a14): the inference path
+(torch.no_grad); the training path with backward schedules is engine_coca_train.py.
 
 One generic pre-norm layer runner serves the TorchMultimodal `TransformerEncoder` (fused `input_proj`) and
 `TransformerDecoder` (separate q/k/v projections, optional cross-attention) of modules/layers/transformer.py:31-657:

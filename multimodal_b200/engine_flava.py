@@ -1,4 +1,5 @@
-"""Forward runtime of the FLAVA encoders (BASELINE.json config 3: image + text + multimodal towers, forward only).
+"""Forward runtime of the FLAVA encoders (BASELINE.json config 3: image + text + multimodal towers): the inference path
+(torch.no_grad); the training path with backward schedules is engine_flava_train.py.
 
 Same kernels as the CLIP path; what differs is the parameter layout (separate query/key/value Linears, packed here
 into one [3d, d] operand), the exact-erf GELU epilogue, eps = 1e-12 LayerNorms, BERT embeddings + key-padding mask,

@@ -191,7 +191,8 @@ def coca_vit_l_14() -> CoCaModel:
 
 
 class CoCaForPretraining(nn.Module):
-    """coca_model.py:398-454: contrastive + captioning losses on top of CoCaModel (forward values; no autograd)."""
+    """coca_model.py:398-454: contrastive + captioning losses on top of CoCaModel.  Grad mode on + trainable parameters:
+    both losses carry an autograd graph (engine_coca_train.py); under torch.no_grad(): forward values."""
 
     def __init__(self, model: CoCaModel, pad_idx: int = 0, contrastive_logit_scale_min: Optional[float] = math.log(1.0),
                  contrastive_logit_scale_max: Optional[float] = math.log(100.0)):
@@ -202,9 +203,6 @@ class CoCaForPretraining(nn.Module):
         self.caption_loss = nn.CrossEntropyLoss(ignore_index=pad_idx)
 
     def forward(self, images: Tensor, texts: Tensor, text_padding_mask: Optional[Tensor] = None) -> Dict[str, Tensor]:
-        # The CoCa runtime is forward-only: the losses returned here carry no autograd graph.  Asking
-        # for them with gradients enabled on trainable parameters would let `loss.backward()` silently do nothing
-        # (or fail far from the cause), so say so here instead.
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             return self._forward_train(images, texts, text_padding_mask)
         with torch.no_grad():
