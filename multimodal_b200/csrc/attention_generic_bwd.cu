@@ -3,9 +3,10 @@
 // and the multimodal decoder's cross-attention under autograd (modules/layers/multi_head_attention.py:74-76,171-173).
 // These are ~3 % of CoCa's FLOPs, so this is a plain SIMT design chosen for being easy to verify, not a tensor-core one:
 //
-//   kernel Q : one warp per (batch, head, query i).  Sweeps the keys three times in blocks of 32 (lane = key):
-//              row LSE  ->  D_i = sum_j p_ij dP_ij  ->  dS_ij = p_ij (dP_ij - D_i) scale, and accumulates
-//              dQ_i = sum_j dS_ij k_j with lane = channel group (dS broadcast by shuffle).  Writes LSE_i / D_i for kernel KV.
+//   kernel Q : one warp per (batch, head, query i), lane = key within blocks of 32.  Skv <= 512: one sweep, the lane's scores
+//              and dP stay in registers (row LSE -> D_i = sum_j p_ij dP_ij -> dS_ij = p_ij (dP_ij - D_i) scale); longer key
+//              sequences: three sweeps that recompute them.  dQ_i = sum_j dS_ij k_j is accumulated with lane = channel
+//              group (dS broadcast by shuffle).  Writes LSE_i / D_i for kernel KV.
 //   kernel KV: one warp per (batch, head, key j).  Sweeps the queries in blocks of 32 (lane = query), recomputes
 //              p_ij / dS_ij from LSE_i / D_i and accumulates dV_j = sum_i p_ij dO_i, dK_j = sum_i dS_ij q_i.
 //
@@ -75,7 +76,61 @@ __global__ void __launch_bounds__(256) attn_gen_bwd_q_kernel(const AttnGenBwdArg
   float* dO = sdo[warp];
   for (int c = lane; c < HD; c += 32) { q[c] = __bfloat162float(qrow[c]); dO[c] = __bfloat162float(dorow[c]); }
   __syncwarp();
-  // sweep 1: row max / sum (log2 domain)
+  float acc[CPL];
+#pragma unroll
+  for (int e = 0; e < CPL; ++e) acc[e] = 0.f;
+  constexpr int KB = 16;   // key blocks whose scores / dP one lane keeps in registers: Skv <= 512
+  if (a.Skv <= 32 * KB) {
+    // ---- one sweep over the keys: s_j and dP_j of this lane's keys stay in registers (2 dot products per pair instead
+    //      of the 5 of the three-sweep path below)
+    const int nb = (a.Skv + 31) >> 5;
+    float sc[KB], dp[KB];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int jb = 0; jb < KB; ++jb) {
+      sc[jb] = -INFINITY;
+      dp[jb] = 0.f;
+      if (jb < nb) {
+        const int j = jb * 32 + lane;
+        if (j < a.Skv && attends(a, b, i, j)) {
+          sc[jb] = dot_row(kbase + (long long)j * a.ldk, q, HD) * a.scale_log2;
+          dp[jb] = dot_row(vbase + (long long)j * a.ldv, dO, HD);
+          mx = fmaxf(mx, sc[jb]);
+        }
+      }
+    }
+    mx = wred_max(mx);
+    float sum = 0.f;
+#pragma unroll
+    for (int jb = 0; jb < KB; ++jb)
+      if (jb < nb && sc[jb] > -INFINITY) sum += exp2f(sc[jb] - mx);
+    sum = wred_sum(sum);
+    const float lse2 = (sum > 0.f) ? mx + log2f(sum) : INFINITY;
+    float D = 0.f;
+#pragma unroll
+    for (int jb = 0; jb < KB; ++jb)
+      if (jb < nb) {
+        sc[jb] = (sc[jb] > -INFINITY) ? exp2f(sc[jb] - lse2) : 0.f;   // now p_j
+        D += sc[jb] * dp[jb];
+      }
+    D = wred_sum(D);
+    if (lane == 0) { a.lse[row] = lse2; a.dsum[row] = D; }
+#pragma unroll
+    for (int jb = 0; jb < KB; ++jb)
+      if (jb < nb) {
+        const float ds = sc[jb] * (dp[jb] - D) * a.scale;
+        const int j0 = jb * 32, nj = min(32, a.Skv - j0);
+        for (int t = 0; t < nj; ++t) {
+          const float dst = __shfl_sync(0xffffffffu, ds, t);
+          if (dst != 0.f) {   // uniform across the warp
+            const __nv_bfloat16* kr = kbase + (long long)(j0 + t) * a.ldk + lane * CPL;
+#pragma unroll
+            for (int e = 0; e < CPL; ++e) acc[e] += dst * __bfloat162float(kr[e]);
+          }
+        }
+      }
+  } else {
+  // ---- three-sweep path (any Skv): sweep 1: row max / sum (log2 domain)
   float mx = -INFINITY;
   for (int j0 = 0; j0 < a.Skv; j0 += 32) {
     const int j = j0 + lane;
@@ -103,9 +158,6 @@ __global__ void __launch_bounds__(256) attn_gen_bwd_q_kernel(const AttnGenBwdArg
   D = wred_sum(D);
   if (lane == 0) { a.lse[row] = lse2; a.dsum[row] = D; }
   // sweep 3: dS and dQ
-  float acc[CPL];
-#pragma unroll
-  for (int e = 0; e < CPL; ++e) acc[e] = 0.f;
   for (int j0 = 0; j0 < a.Skv; j0 += 32) {
     const int j = j0 + lane;
     float ds = 0.f;
@@ -123,6 +175,7 @@ __global__ void __launch_bounds__(256) attn_gen_bwd_q_kernel(const AttnGenBwdArg
       }
     }
   }
+  }   // three-sweep path
   if (a.dq) {
     __nv_bfloat16* o = a.dq + b * a.bsq + (long long)i * a.ldq + h * HD + lane * CPL;
 #pragma unroll
