@@ -25,7 +25,6 @@ def _rel(a, b):
     (3, 21, 21, 2, 64, "mask"),           # text decoder: [B, S, S] boolean mask on a packed QKV buffer
     (2, 33, 33, 3, 64, "causal"),
     (2, 40, 600, 2, 64, "cross"),         # more than 512 keys: the three-sweep path of the query kernel
-    (1, 300, 513, 1, 128, "shared_q"),
 ])
 def test_attention_bwd_generic(dev, B, Sq, Skv, H, hd, kind):
     from multimodal_b200 import ops
