@@ -1,7 +1,9 @@
 // Backward of the general attention forward (attention_generic.cu): cross-attention, head_dim 64 / 96 / 128,
 // batch-shared (learned) queries, arbitrary boolean masks — the CoCa poolers, the text decoder's [causal x padding] mask
 // and the multimodal decoder's cross-attention under autograd (modules/layers/multi_head_attention.py:74-76,171-173).
-// These are ~3 % of CoCa's FLOPs, so this is a plain SIMT design chosen for being easy to verify, not a tensor-core one:
+// These are ~3 % of CoCa's FLOPs, so this is a plain SIMT design chosen for being easy to verify, not a tensor-core one.
+// Two generations live here: the row-per-warp kernels described first (fallback: MMB_ATTN_GEN_BWD=rows, and Skv > 512 for
+// the query kernel) and their shared-memory tiled variants (default; 3.1x faster at CoCa ViT-L/14 shapes), further down.
 //
 //   kernel Q : one warp per (batch, head, query i), lane = key within blocks of 32.  Skv <= 512: one sweep, the lane's scores
 //              and dP stay in registers (row LSE -> D_i = sum_j p_ij dP_ij -> dS_ij = p_ij (dP_ij - D_i) scale); longer key
