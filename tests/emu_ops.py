@@ -374,6 +374,39 @@ def l2norm_bwd(dy, y, inv_norm, dx, dx_bf16, B, E):
         dx_bf16.copy_(r.to(BF))
 
 
+def vit_embed_ln_fwd(patch_out, cls, pos, gamma, beta, x0, mean, rstd, B, S, d, eps):
+    t = torch.cat([cls.detach().reshape(1, 1, d).expand(B, 1, d), patch_out.float().view(B, S - 1, d)], 1) + pos.detach().reshape(1, S, d)
+    out, m, r = _ln_rows(t.reshape(B * S, d), gamma, beta, eps)
+    x0.view(B * S, d).copy_(out)
+    mean.copy_(m)
+    rstd.copy_(r)
+
+
+def vit_embed_ln_bwd(patch_out, cls, pos, dy_f32, mean, rstd, gamma, dt_f32, dpatch_bf16, dgamma, dbeta, B, S, d):
+    t = (torch.cat([cls.detach().reshape(1, 1, d).expand(B, 1, d), patch_out.float().view(B, S - 1, d)], 1)
+         + pos.detach().reshape(1, S, d)).reshape(B * S, d)
+    dy = dy_f32.reshape(B * S, d).clone()
+    h = (t - mean.view(-1, 1)) * rstd.view(-1, 1)
+    dgamma.add_((dy * h).sum(0))
+    dbeta.add_(dy.sum(0))
+    dyg = dy * gamma.detach()
+    dx = rstd.view(-1, 1) * (dyg - dyg.mean(-1, keepdim=True) - h * (dyg * h).mean(-1, keepdim=True))
+    dt_f32.view(B * S, d).copy_(dx)
+    dpatch_bf16.view(B, S - 1, d).copy_(dx.view(B, S, d)[:, 1:].to(BF))
+
+
+def text_embed_fwd(tokens, emb, pos, x, B, S, d, V):
+    x.view(B, S, d).copy_(emb.detach()[tokens] + pos.detach().reshape(1, S, d))
+
+
+def text_embed_bwd(tokens, g, demb, B, S, d):
+    demb.index_add_(0, tokens.reshape(-1), g.reshape(B * S, d))
+
+
+def argmax_tokens(tokens, idx, B, S):
+    idx.copy_(tokens.argmax(-1).to(torch.int32))
+
+
 NAMES = [n for n, f in list(globals().items()) if callable(f) and not n.startswith("_") and n not in ("install",)]
 
 
